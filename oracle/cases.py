@@ -1,0 +1,63 @@
+"""TEST INFRASTRUCTURE — the parity cases (small versions of BASELINE.json's configs plus
+one case per loss / control / SDE / target combination the kernel claims to support).
+
+Values follow the reference YAMLs cited per case (paths relative to /root/reference/conf).
+`batch` is the golden-fixture batch; the -m gpu tests re-run the same case at larger B
+against the oracle.
+"""
+
+LIN = lambda steps: {"steps": steps}  # noqa: E731
+
+CASES = {
+    # BASELINE cfg1: solver/basic_dis.yaml + target/dw_shift.yaml, loss.method=lv
+    "dis_dw1_lv": dict(target="dw_shift", dim=1, sde="vp", prior="gauss", ctrl="lerp",
+                       clip_model=1e4, clip_score=1e4, gate_bias=1.0, loss="time_reversal",
+                       method="lv", max_rnd=None, timesteps=LIN(50), batch=64, seed=1),
+    # BASELINE cfg2: basic_dis + GMM-40 "fab" d=2 (distr/gauss.py:42-47), lv
+    "dis_gmm2_lv": dict(target="gmm40", dim=2, sde="vp", prior="gauss", ctrl="lerp",
+                        clip_model=1e4, clip_score=1e4, gate_bias=1.0, loss="time_reversal",
+                        method="lv", max_rnd=None, timesteps=LIN(100), batch=64, seed=1),
+    # same, kl training semantics (rnd0 = 0, no Ito term): loss/time_reversal.yaml
+    "dis_gmm2_kl": dict(target="gmm40", dim=2, sde="vp", prior="gauss", ctrl="lerp",
+                        clip_model=1e4, clip_score=1e4, gate_bias=1.0, loss="time_reversal",
+                        method="kl", max_rnd=None, timesteps=LIN(100), batch=64, seed=2),
+    # BASELINE cfg3: solver/basic_pis.yaml + target/funnel.yaml (kl)
+    "pis_funnel10_kl": dict(target="funnel", dim=10, sde="bm_pis", prior="delta", ctrl="score",
+                            clip_model=1e4, clip_score=1e4, gate_bias=0.01, loss="reference_sde",
+                            method="kl", max_rnd=None, timesteps=LIN(200), batch=64, seed=1),
+    # BASELINE cfg4 / north-star headline: solver/dis.yaml (clips 10, max_rnd 1e8), GMM-40 d=50
+    "dis_gmm50_lv": dict(target="gmm40", dim=50, sde="vp", prior="gauss", ctrl="lerp",
+                         clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
+                         method="lv", max_rnd=1e8, timesteps=LIN(100), batch=48, seed=1),
+    # solver/dds.yaml with the basic_dds grid (end 6.4 -> 129 steps; last dt ~ 0), funnel
+    "dds_funnel10_lv": dict(target="funnel", dim=10, sde=None, prior="gauss", ctrl="score",
+                            clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="exp_integrator",
+                            method="lv", max_rnd=1e8, alpha=1.0, sigma=1.0,
+                            timesteps=dict(rescale_t="cosine", end=6.4, dt=0.05), batch=64, seed=3),
+    # solver/dds_euler.yaml: ReferenceSDELoss with reference_ctrl = sigma * prior score, VP
+    "eulerdds_gmm2_lv": dict(target="gmm_rand", dim=2, sde="vp", prior="gauss", ctrl="score",
+                             clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="reference_sde",
+                             method="lv", euler_dds=True, max_rnd=1e8, timesteps=LIN(60), batch=64, seed=4),
+    # solver/dis_no_score.yaml: ClippedCtrl; sde/const.yaml (ConstOU) to cover that coefficient family
+    "dis_noscore_constou_gauss5": dict(target="gauss", dim=5, sde="const_ou", prior="gauss", ctrl="clipped",
+                                       clip_model=10.0, loss="time_reversal", method="lv", max_rnd=1e8,
+                                       timesteps=LIN(40), batch=64, seed=5),
+    # model/lerp_prior.yaml, model/lerp_target.yaml; MultiWell; heterogeneous GMM; per-dim gate (lerp_dim)
+    "dis_lerpprior_multiwell4": dict(target="multiwell", dim=4, sde="vp", prior="gauss", ctrl="lerp_prior",
+                                     clip_model=1e4, clip_score=1e4, gate_bias=1.0, loss="time_reversal",
+                                     method="kl_ito", max_rnd=None, timesteps=LIN(40), batch=64, seed=6),
+    "dis_lerptarget_gmmrand3_dimgate": dict(target="gmm_rand", dim=3, sde="vp", prior="gauss", ctrl="lerp_target",
+                                            clip_model=1e4, clip_score=5.0, gate_bias=1.0, gate_dim=3,
+                                            loss="time_reversal", method="lv", max_rnd=None,
+                                            clip_target=50.0, timesteps=LIN(40), batch=64, seed=7),
+}
+
+# eval-mode variants: (case, compute_weights, return_traj)  — losses/oc.py:258-278, :371-392
+EVAL_CASES = {
+    "dis_gmm2_lv": [(True, True), (False, False)],
+    "dis_dw1_lv": [(True, True)],
+    "pis_funnel10_kl": [(True, False)],
+    "dds_funnel10_lv": [(True, True)],
+}
+
+NOISE_SEED = 0x5DE5_0001

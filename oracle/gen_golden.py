@@ -1,0 +1,128 @@
+"""TEST INFRASTRUCTURE — freeze outputs of the UNMODIFIED reference rollout as golden vectors.
+
+    python -m oracle.gen_golden            # writes tests/golden/<case>.npz
+
+Runs only where /root/reference exists (the build container; it cannot travel to the GPU
+box).  For every case in `oracle/cases.py` it builds the reference objects without Hydra
+(oracle/ref_harness.py), draws x0 from the reference prior, injects the Philox noise stream
+of `oracle/philox.py` through `torch.randn_like`, calls the reference's own
+`loss.simulate` / `loss.__call__` / `loss.eval` (sde_sampler/losses/oc.py) and stores
+
+    spec/...   raw parameters as extracted by sde_sampler_b200.spec.extract_spec
+    x0, train/{x_T, rnd, loss, n_filtered}, eval<i>/{x_T, rnd, xs?, log_norm_const_*, lv_loss}
+
+The reference has no rollout fixtures of its own — these are the pin.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import philox, ref_harness, specio  # noqa: E402
+from oracle.cases import CASES, EVAL_CASES, NOISE_SEED  # noqa: E402
+
+
+def run_case(name: str, case: dict) -> dict:
+    import torch
+
+    from sde_sampler_b200.spec import extract_spec
+
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    built = ref_harness.build_case(case)
+    loss, ts = built["loss"], built["ts"]
+    B, d = case["batch"], case["dim"]
+    T = ts.shape[0] - 1
+    torch.manual_seed(1000 + case.get("seed", 1))
+    x0 = built["prior"].sample((B,)).float()
+    # spread the initial points a little for Delta priors? No: keep the reference semantics.
+    noise = philox.normal_noise(NOISE_SEED, B, T, d)
+    noise_t = torch.from_numpy(noise)
+
+    method = case["method"]
+    compute_ito = method != "kl"
+    change = method in ("lv", "lv_traj")
+    out = {"x0": x0.numpy().copy(), "ts": ts.numpy().copy(), "torch_version": torch.__version__}
+
+    kind = case["loss"]
+    kw = dict(terminal_unnorm_log_prob=built["terminal"])
+    if kind == "time_reversal":
+        kw["initial_log_prob"] = built["second"]
+        sim_kw = dict(train=True)
+    else:
+        kw["reference_log_prob"] = built["second"]
+        sim_kw = {}
+
+    # --- train-mode rollout exactly as __call__ drives it (losses/oc.py:232-256 etc.)
+    with ref_harness.injected_noise(noise_t):
+        x_T, rnd, _ = loss.simulate(ts, x0.clone(), compute_ito_int=compute_ito,
+                                    change_sde_ctrl=change, return_traj=False, **kw, **sim_kw)
+    n_before = loss.n_filtered
+    lval, metrics = loss.compute_loss(rnd.detach(), samples=x_T.detach())
+    out["train"] = {"x_T": x_T.detach().numpy().copy(), "rnd": rnd.detach().numpy().copy(),
+                    "loss": float(lval), "n_filtered": int(loss.n_filtered - n_before)}
+
+    # target object proxy so that extract_spec sees solver-like clipped_target_unnorm_log_prob
+    class _SolverShim:
+        def __init__(self, target, clip_target):
+            self.target = target
+            self.clip_target = clip_target
+
+        def clipped_target_unnorm_log_prob(self, x):
+            raise RuntimeError("shim is introspected, never called")
+
+    shim = _SolverShim(built["target"], case.get("clip_target"))
+    if case.get("euler_dds"):
+        class _EulerShim:
+            def __init__(self, prior, sde):
+                self.prior, self.sde = prior, sde
+
+            def reference_ctrl(self, t, x):
+                return self.sde.diff(t, x) * self.prior.score(x)
+        loss.reference_ctrl = _EulerShim(built["prior"], built["sde"]).reference_ctrl
+    spec = extract_spec(loss, kind, ts, shim.clipped_target_unnorm_log_prob, built["second"],
+                        train=True, compute_ito=compute_ito)
+    out["spec"] = spec.to_dict()
+
+    # --- eval-mode rollouts (losses/oc.py:258-278): train=False, change_sde_ctrl=False
+    for j, (cw, rt) in enumerate(EVAL_CASES.get(name, [])):
+        with torch.no_grad(), ref_harness.injected_noise(noise_t):
+            res = loss.eval(ts, x0.clone(), compute_weights=cw, return_traj=rt, **kw)
+        with torch.no_grad(), ref_harness.injected_noise(noise_t):
+            ekw = dict(train=False) if kind == "time_reversal" else dict(change_sde_ctrl=False)
+            _, rnd_e, _ = loss.simulate(ts, x0.clone(), compute_ito_int=cw, return_traj=False, **kw, **ekw)
+        e = {"compute_weights": bool(cw), "return_traj": bool(rt),
+             "x_T": res.samples.numpy().copy(), "rnd": rnd_e.numpy().copy(),
+             "log_norm_const_preds": {k: float(v) for k, v in res.log_norm_const_preds.items()},
+             "metrics": {k: float(v) for k, v in res.metrics.items()}}
+        if cw:
+            e["weights"] = res.weights.numpy().copy()
+        if rt:
+            e["xs"] = res.xs.numpy().copy()
+        out[f"eval{j}"] = e
+    return out
+
+
+def main():
+    if not ref_harness.available():
+        raise SystemExit("reference not available; golden vectors can only be generated in the build container")
+    outdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    names = sys.argv[1:] or list(CASES)
+    for name in names:
+        out = run_case(name, CASES[name])
+        path = os.path.join(outdir, f"{name}.npz")
+        specio.save(path, out)
+        tr = out["train"]
+        print(f"{name:36s} B={out['x0'].shape[0]:4d} d={out['x0'].shape[1]:3d} T={out['ts'].shape[0]-1:4d} "
+              f"loss={tr['loss']:+.6e} |rnd|max={np.abs(tr['rnd']).max():.3e} "
+              f"|x_T|max={np.abs(tr['x_T']).max():.3e} size={os.path.getsize(path)/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

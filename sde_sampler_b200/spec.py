@@ -1,0 +1,273 @@
+"""Host-side introspection of the reference's plugin objects -> a flat `RolloutSpec`.
+
+The reference hands its losses *objects and bound methods* (SURVEY §8b "Callables are
+bound methods"): `generative_ctrl` (ClippedCtrl / ScoreCtrl / Lerp*Ctrl wrapping a
+FourierMLP + TimeEmbed gate, reference models/reparam.py, models/mlp.py), `sde`
+(VP / ConstOU / ScaledBM, eq/sdes.py), `solver.clipped_target_unnorm_log_prob`,
+`prior.log_prob`, `reference_distr.log_prob` (solver/oc.py:158-163, :213-215, :257-259).
+
+`extract_spec` recovers the raw parameters from those objects by duck typing on class
+name + attribute names, so that it accepts both the reference's classes and the
+parameter-holder mirrors in `sde_sampler_b200.plugins`.  Anything it cannot express in
+the kernel's descriptor raises `NotImplementedError` — there is no fallback path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable
+
+import numpy as np
+import torch
+
+CTRL_KINDS = {"ClippedCtrl": "clipped", "ScoreCtrl": "score", "LerpCtrl": "lerp",
+              "LerpPriorCtrl": "lerp_prior", "LerpTargetCtrl": "lerp_target"}
+LOSS_KINDS = ("time_reversal", "reference_sde", "exp_integrator")
+METHODS = ("kl", "kl_ito", "lv", "lv_traj")
+
+
+def _np(t) -> np.ndarray:
+    if isinstance(t, torch.Tensor):
+        return t.detach().to("cpu", torch.float32).numpy().copy()
+    return np.asarray(t, dtype=np.float32)
+
+
+def _f(v) -> float:
+    if isinstance(v, torch.Tensor):
+        return float(v.detach().cpu())
+    return float(v)
+
+
+def _owner(fn: Callable, what: str):
+    owner = getattr(fn, "__self__", None)
+    if owner is None:
+        raise NotImplementedError(
+            f"{what} must be a bound method of a supported object (got {fn!r}); the fused "
+            "rollout evaluates densities in-kernel and cannot call arbitrary Python.")
+    return owner
+
+
+def _cls(obj) -> str:
+    return type(obj).__name__
+
+
+# ----------------------------------------------------------------------------- networks
+def _check_gelu(act, where):
+    if _cls(act) != "GELU" or getattr(act, "approximate", "none") != "none":
+        raise NotImplementedError(f"{where}: only exact-erf nn.GELU() is supported (got {act!r})")
+
+
+def _time_embed_params(te) -> dict:
+    """TimeEmbed (reference models/mlp.py:43-82)."""
+    _check_gelu(te.activation, "TimeEmbed")
+    hidden = [(_np(l.weight), _np(l.bias)) for l in te.hidden_layer]
+    return {"phase": _np(te.timestep_phase).reshape(-1), "hidden": hidden,
+            "out_w": _np(te.out_layer.weight), "out_b": _np(te.out_layer.bias)}
+
+
+def _fourier_mlp_params(net) -> dict:
+    """FourierMLP (reference models/mlp.py:85-122)."""
+    if _cls(net) != "FourierMLP":
+        raise NotImplementedError(f"base_model {_cls(net)} is not supported (FourierMLP only)")
+    _check_gelu(net.activation, "FourierMLP")
+    return {"in_w": _np(net.input_embed.weight), "in_b": _np(net.input_embed.bias),
+            "hidden": [(_np(l.weight), _np(l.bias)) for l in net.hidden_layer],
+            "out_w": _np(net.out_layer.weight), "out_b": _np(net.out_layer.bias),
+            "time_embed": _time_embed_params(net.timestep_embed)}
+
+
+# ------------------------------------------------------------------------- distributions
+def _diag_gauss(distr, dim) -> dict:
+    """Gauss / IsotropicGauss / Delta (reference distr/gauss.py:158-242, distr/delta.py)."""
+    if _cls(distr) not in ("Gauss", "IsotropicGauss", "Delta"):
+        raise NotImplementedError(f"{_cls(distr)} is not a supported Gaussian prior/reference")
+    loc = np.broadcast_to(_np(distr.loc).reshape(-1), (dim,)).copy()
+    scale = np.broadcast_to(_np(distr.scale).reshape(-1), (dim,)).copy()
+    lnc = getattr(distr, "log_norm_const", 0.0) or 0.0
+    if abs(float(lnc)) > 0:
+        raise NotImplementedError("Gaussian prior/reference with log_norm_const != 0")
+    return {"loc": loc, "scale": scale}
+
+
+def _target_params(target, dim) -> dict:
+    name = _cls(target)
+    lnc = getattr(target, "log_norm_const", None)
+    if name == "GMM":
+        # distr/gauss.py:66-140
+        loc, scale = _np(target.loc), _np(target.scale)
+        if target.mixture_weights is None:
+            logw = np.zeros((1,), np.float32)
+        else:
+            w = target.mixture_weights.detach().cpu().double()
+            # Categorical(probs=w) normalises; logits = log(w / sum w)
+            logw = torch.log(w / w.sum()).float().numpy()
+        return {"kind": "gmm", "loc": loc, "scale": scale, "log_weights": logw,
+                "log_norm_const": float(lnc or 0.0)}
+    if name in ("Gauss", "IsotropicGauss"):
+        g = {"loc": np.broadcast_to(_np(target.loc).reshape(-1), (dim,)).copy(),
+             "scale": np.broadcast_to(_np(target.scale).reshape(-1), (dim,)).copy()}
+        return {"kind": "gauss", **g, "log_norm_const": float(lnc or 0.0)}
+    if name == "DoubleWell":
+        # distr/double_well.py:14-45 — unnorm_log_prob has no constant
+        return {"kind": "multiwell", "n_dw": 1, "separation": _f(target.separation),
+                "shift": _f(target.shift)}
+    if name == "MultiWell":
+        # distr/double_well.py:103-179; Gaussian part: loc=shift, scale=1, constant folded to 0
+        dw = target.double_well
+        if target.gauss is not None:
+            gs = _np(target.gauss.scale).reshape(-1)
+            gl = _np(target.gauss.loc).reshape(-1)
+            if not (np.allclose(gs, 1.0) and np.allclose(gl, _f(dw.shift))):
+                raise NotImplementedError("MultiWell with a non-standard Gaussian part")
+        return {"kind": "multiwell", "n_dw": int(target.n_double_wells),
+                "separation": _f(dw.separation), "shift": _f(dw.shift)}
+    if name == "Funnel":
+        # distr/funnel.py:11-80
+        return {"kind": "funnel", "variance": float(target.variance),
+                "log_norm_const": float(lnc or 0.0)}
+    raise NotImplementedError(
+        f"target {name} is not implemented in the fused rollout (supported: GMM, Gauss, "
+        "IsotropicGauss, DoubleWell, MultiWell, Funnel)")
+
+
+def _sde_params(sde) -> dict | None:
+    if sde is None:
+        return None
+    name = _cls(sde)
+    if getattr(sde, "noise_type", "diagonal") not in ("diagonal", "scalar"):
+        raise NotImplementedError(f"sde noise type {sde.noise_type}")
+    if name == "VP":
+        return {"kind": "vp", "beta_min": _f(sde.diff_coeff_sq_min), "beta_max": _f(sde.diff_coeff_sq_max),
+                "scale": _f(sde.scale_diff_coeff), "terminal_t": _f(sde.terminal_t), "sign": float(sde.sign)}
+    if name in ("ConstOU", "ScaledBM"):
+        return {"kind": "const_ou", "drift_coeff": _f(sde.drift_coeff), "diff_coeff": _f(sde.diff_coeff),
+                "terminal_t": _f(sde.terminal_t), "sign": float(sde.sign)}
+    raise NotImplementedError(f"sde {name} is not supported (VP, ConstOU, ScaledBM)")
+
+
+# ------------------------------------------------------------------------------ the spec
+@dataclass
+class RolloutSpec:
+    """Raw, framework-free description of one rollout call (numpy arrays + scalars)."""
+    dim: int
+    ts: np.ndarray
+    loss: dict
+    ctrl: dict
+    mlp: dict
+    gate: dict | None
+    sde: dict | None
+    prior: dict | None
+    ref: dict | None
+    target: dict
+    extras: dict = field(default_factory=dict)
+
+    def to_dict(self) -> dict:
+        return {"dim": self.dim, "ts": self.ts, "loss": dict(self.loss), "ctrl": dict(self.ctrl),
+                "mlp": self.mlp, "gate": self.gate, "sde": self.sde, "prior": self.prior,
+                "ref": self.ref, "target": dict(self.target)}
+
+
+def extract_spec(loss_obj, loss_kind: str, ts: torch.Tensor, terminal_unnorm_log_prob: Callable,
+                 second_log_prob: Callable | None, *, train: bool, compute_ito: bool,
+                 return_traj: bool = False) -> RolloutSpec:
+    """Build the spec for one `simulate` call of a fused loss.
+
+    `second_log_prob` is `initial_log_prob` (TimeReversalLoss, losses/oc.py:160) or
+    `reference_log_prob` (ReferenceSDELoss :291, ExponentialIntegratorSDELoss :405)."""
+    assert loss_kind in LOSS_KINDS
+    if loss_obj.method not in METHODS:
+        raise ValueError("Unknown loss method.")
+    if getattr(loss_obj, "inference_ctrl", None) is not None:
+        raise NotImplementedError("learned inference_ctrl (Bridge) needs div_x autograd; out of scope (SURVEY §8a1)")
+    if loss_obj.sde_ctrl_noise is not None or loss_obj.sde_ctrl_dropout is not None:
+        raise NotImplementedError("sde_ctrl_noise / sde_ctrl_dropout are not implemented (SURVEY §8a4)")
+
+    ctrl = loss_obj.generative_ctrl
+    kind = CTRL_KINDS.get(_cls(ctrl))
+    if kind is None:
+        raise NotImplementedError(f"control {_cls(ctrl)} is not supported {tuple(CTRL_KINDS)}")
+    if getattr(ctrl, "hard_constrain", False):
+        raise NotImplementedError("hard_constrain=True")
+    mlp = _fourier_mlp_params(ctrl.base_model)
+    dim = int(mlp["in_w"].shape[1])
+    if mlp["out_w"].shape[0] != dim:
+        raise NotImplementedError("FourierMLP with dim_out != dim")
+
+    cd: dict[str, Any] = {"kind": kind, "clip_model": ctrl.clip_model}
+    gate = None
+    target_obj = None
+    prior = None
+    sde = _sde_params(loss_obj.sde)
+    if kind != "clipped":
+        cd["scale_score"] = float(ctrl.scale_score)
+        cd["clip_score"] = ctrl.clip_score
+        if ctrl.score_model is not None:
+            if _cls(ctrl.score_model) != "TimeEmbed":
+                raise NotImplementedError("score_model must be a TimeEmbed (x-independent gate)")
+            gate = _time_embed_params(ctrl.score_model)
+            if gate["out_w"].shape[0] not in (1, dim):
+                raise NotImplementedError("gate dim_out must be 1 or dim")
+        target_obj = _owner(ctrl.target_score, "target_score")
+        if kind in ("lerp", "lerp_prior", "lerp_target"):
+            if sde is None:
+                raise ValueError("Lerp controls need an sde")
+            if _sde_params(ctrl.sde) != sde:
+                raise NotImplementedError("control and loss use different SDEs")
+            prior = _diag_gauss(_owner(ctrl.prior_score, "prior_score"), dim)
+
+    # terminal density: solver.clipped_target_unnorm_log_prob (solver/oc.py:48-54) or target.unnorm_log_prob
+    owner = _owner(terminal_unnorm_log_prob, "terminal_unnorm_log_prob")
+    clip_target = None
+    if hasattr(owner, "target") and hasattr(owner, "clip_target"):
+        clip_target = owner.clip_target
+        term_obj = owner.target
+    else:
+        term_obj = owner
+    if target_obj is not None and term_obj is not target_obj:
+        raise NotImplementedError("control's target_score and terminal_unnorm_log_prob refer to different targets")
+    target = _target_params(term_obj, dim)
+    target["clip_target"] = clip_target
+    if getattr(loss_obj, "filter_samples", None) is not None:
+        raise NotImplementedError("filter_samples (target.filter) is not implemented")
+
+    ld: dict[str, Any] = {"kind": loss_kind, "method": loss_obj.method, "train": bool(train),
+                          "compute_ito": bool(compute_ito), "return_traj": bool(return_traj),
+                          "max_rnd": loss_obj.max_rnd, "traj_per_sample": int(loss_obj.traj_per_sample)}
+    ref = None
+    if loss_kind == "time_reversal":
+        if sde is None:
+            raise ValueError("TimeReversalLoss needs an sde")
+        if not (train and loss_obj.method in ("kl", "kl_ito")):
+            p = _diag_gauss(_owner(second_log_prob, "initial_log_prob"), dim)
+            if prior is not None and not (np.array_equal(p["loc"], prior["loc"]) and np.array_equal(p["scale"], prior["scale"])):
+                raise NotImplementedError("initial_log_prob and prior_score refer to different priors")
+            prior = p
+    else:
+        ref = _diag_gauss(_owner(second_log_prob, "reference_log_prob"), dim)
+        if loss_kind == "reference_sde":
+            if sde is None:
+                raise ValueError("ReferenceSDELoss needs an sde")
+            rc = getattr(loss_obj, "reference_ctrl", None)
+            ld["reference_ctrl"] = rc is not None
+            if rc is not None:
+                # EulerDDS.reference_ctrl = sde.diff * prior.score (solver/oc.py:305-306)
+                rc_owner = _owner(rc, "reference_ctrl")
+                if not hasattr(rc_owner, "prior"):
+                    raise NotImplementedError("reference_ctrl must be EulerDDS-style (owner with .prior)")
+                p = _diag_gauss(rc_owner.prior, dim)
+                if prior is not None and not np.array_equal(p["loc"], prior["loc"]):
+                    raise NotImplementedError("reference_ctrl prior differs from control prior")
+                prior = p
+        else:
+            ld["alpha"] = float(loss_obj.alpha)
+            ld["sigma"] = float(loss_obj.sigma)
+
+    ts_np = _np(ts).reshape(-1)
+    if ts_np.shape[0] < 2:
+        raise ValueError("need at least one time step")
+    return RolloutSpec(dim=dim, ts=ts_np, loss=ld, ctrl=cd, mlp=mlp, gate=gate, sde=sde,
+                       prior=prior, ref=ref, target=target)
+
+
+def inf_if_none(v) -> float:
+    return math.inf if v is None else float(v)
