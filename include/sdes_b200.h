@@ -1,0 +1,150 @@
+/* sdes_b200.h — C ABI of the B200-native controlled-SDE rollout.
+ *
+ * This is the drop-in boundary for ONE path of juliusberner/sde_sampler: the T-step
+ * rollout `simulate()` of the three optimal-control losses
+ *     TimeReversalLoss.simulate               sde_sampler/losses/oc.py:156-230
+ *     ReferenceSDELoss.simulate               sde_sampler/losses/oc.py:286-343
+ *     ExponentialIntegratorSDELoss.simulate   sde_sampler/losses/oc.py:400-457
+ * together with everything those loops call per step (control wrappers
+ * models/reparam.py:13-200, FourierMLP/TimeEmbed models/mlp.py:43-122, SDE coefficients
+ * eq/sdes.py:125-269, target / prior densities and scores distr/{gauss,double_well,
+ * funnel}.py) and the reductions that follow them (BaseOCLoss.filter / compute_loss /
+ * compute_results, losses/oc.py:50-123).
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the binding a maintainer
+ * adds is the ctypes stub in INTEGRATION.md (and sde_sampler_b200/_cabi.py is that stub).
+ *
+ * Conventions: plain pointers and sizes, no torch types. All array pointers are DEVICE
+ * pointers (fp32 unless stated) on the device that is current when the call is made; all
+ * work is enqueued on `stream` (a cudaStream_t passed as void*), nothing is allocated,
+ * nothing synchronises the host.  State lives only in the descriptor: calls are re-entrant.
+ * Return value 0 = ok, negative = error (sdes_last_error() gives the text, thread-local).
+ */
+#ifndef SDES_B200_H
+#define SDES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDES_ABI_VERSION 1
+#define SDES_CHANNELS 64     /* FourierMLP / TimeEmbed width (conf/model/base/fouriermlp.yaml:3) */
+#define SDES_MAX_DIM 64      /* state dimension supported by the fused kernel this round   */
+#define SDES_MAX_HIDDEN 6    /* hidden layers per network                                    */
+#define SDES_MAX_COMPONENTS 64 /* GMM components                                           */
+
+/* which simulate() — losses/oc.py */
+enum { SDES_LOSS_TIME_REVERSAL = 0, SDES_LOSS_REFERENCE_SDE = 1, SDES_LOSS_EXP_INTEGRATOR = 2 };
+/* generative_ctrl wrapper — models/reparam.py */
+enum { SDES_CTRL_CLIPPED = 0, SDES_CTRL_SCORE = 1, SDES_CTRL_LERP = 2, SDES_CTRL_LERP_PRIOR = 3,
+       SDES_CTRL_LERP_TARGET = 4 };
+/* sde coefficient family — eq/sdes.py */
+enum { SDES_SDE_NONE = 0, SDES_SDE_VP = 1, SDES_SDE_CONST_OU = 2 /* ConstOU and ScaledBM */ };
+/* analytic target — distr/*.py.  Gauss / IsotropicGauss targets are passed as GMM with K=1. */
+enum { SDES_TARGET_GMM = 0, SDES_TARGET_MULTIWELL = 1 /* DoubleWell = n_dw=d=1 */, SDES_TARGET_FUNNEL = 2 };
+
+/* flags */
+#define SDES_F_RND0_ZERO      (1u << 0) /* rnd starts at 0 instead of log p_prior(x0) (oc.py:168-172)   */
+#define SDES_F_COMPUTE_ITO    (1u << 1) /* accumulate the Ito integral (oc.py:218-219,:330-331,:440-443) */
+#define SDES_F_SUB_DIV_INT    (1u << 2) /* eval: rnd -= int_s^t div(mu)  (oc.py:210-211)               */
+#define SDES_F_RETURN_TRAJ    (1u << 3) /* write xs (T+1,B,d)  (oc.py:221-222,:228-229)                  */
+#define SDES_F_NOISE_FROM_HBM (1u << 4) /* parity mode: eps read from `noise` (T,B,d) instead of Philox */
+#define SDES_F_REFERENCE_CTRL (1u << 5) /* Euler-DDS reference_ctrl = sigma * prior score (solver/oc.py:305-306) */
+#define SDES_F_HAS_GATE       (1u << 6) /* ctrl.score_model (a TimeEmbed gate) is present                */
+#define SDES_F_MLP_SIMT       (1u << 7) /* evaluate the control MLP with fp32 FFMA instead of tcgen05    */
+
+/* Layout of the flat fp32 parameter blob `params` (torch (out,in) row-major weights, C = 64):
+ *   FourierMLP (models/mlp.py:85-122)
+ *     in_w[C*d] in_b[C]
+ *     te_phase[C]  te_h0_w[C*2C] te_h0_b[C]  { te_hk_w[C*C] te_hk_b[C] } x (te_hidden-1)  te_out_w[C*C] te_out_b[C]
+ *     { h_w[C*C] h_b[C] } x n_hidden
+ *     out_w[d*C] out_b[d]
+ *   gate TimeEmbed (models/mlp.py:43-82), only with SDES_F_HAS_GATE
+ *     g_phase[C]  g_h0_w[C*2C] g_h0_b[C]  { g_hk_w[C*C] g_hk_b[C] } x (gate_hidden-1)  g_out_w[gate_dim*C] g_out_b[gate_dim]
+ */
+typedef struct SdesRolloutDesc {
+    uint32_t struct_bytes;   /* = sizeof(SdesRolloutDesc), checked */
+    uint32_t abi_version;    /* = SDES_ABI_VERSION, checked */
+    int32_t loss_kind, ctrl_kind, sde_kind, target_kind;
+    uint32_t flags;
+    int32_t dim;             /* d, 1..SDES_MAX_DIM */
+    int32_t n_steps;         /* T >= 1; ts has T+1 entries */
+    int32_t n_hidden;        /* FourierMLP hidden (C->C) layers = num_layers-2 */
+    int32_t te_hidden;       /* hidden layers of FourierMLP.timestep_embed (>=1; reference: 1) */
+    int32_t gate_hidden;     /* hidden layers of the gate TimeEmbed (>=1; reference: 3) */
+    int32_t gate_dim;        /* 1 or d */
+    int32_t n_components;    /* GMM: K */
+    int32_t n_double_wells;  /* MULTIWELL */
+    int64_t batch;           /* B trajectories in this call (this rank's shard) */
+    uint64_t traj_offset;    /* global index of trajectory 0 (Philox counter; shard-invariant noise) */
+    uint64_t seed;           /* Philox key */
+    /* +/-inf = no clip (utils/common.py:83-84) */
+    float clip_model, clip_score, clip_target, scale_score;
+    float alpha, sigma;      /* ExponentialIntegratorSDELoss (oc.py:395-398) */
+    /* eq/sdes.py: VP uses beta_min/beta_max/scale_diff/terminal_t/sign; CONST_OU drift_coeff/diff_coeff/sign */
+    float beta_min, beta_max, scale_diff, terminal_t, sde_sign, drift_coeff, diff_coeff;
+    /* targets: MULTIWELL separation/shift; FUNNEL variance; all: log_norm_const */
+    float separation, shift, variance, log_norm_const;
+    const float* ts;         /* (T+1) */
+    const float* params;     /* blob, layout above */
+    int64_t n_params;        /* its length in floats, checked against the layout */
+    const float* gmm_loc;    /* (K,d) */
+    const float* gmm_scale;  /* (K,d) */
+    const float* gmm_weights;/* (K) unnormalised mixture weights, or NULL = uniform */
+    const float* prior_loc;  /* (d) diagonal Gaussian prior (initial cost, Lerp* ctrl, reference ctrl), may be NULL if unused */
+    const float* prior_scale;
+    const float* ref_loc;    /* (d) reference_distr of REFERENCE_SDE / EXP_INTEGRATOR terminal cost */
+    const float* ref_scale;
+    const float* x0;         /* (B,d) row-major */
+    const float* noise;      /* (T,B,d) with SDES_F_NOISE_FROM_HBM, else NULL */
+    float* x_T;              /* (B,d) out */
+    float* rnd;              /* (B)   out */
+    float* xs;               /* (T+1,B,d) out with SDES_F_RETURN_TRAJ, else NULL */
+    void* workspace;         /* >= sdes_workspace_bytes(desc), 256-byte aligned */
+    size_t workspace_bytes;
+} SdesRolloutDesc;
+
+/* ABI version of the loaded library (== SDES_ABI_VERSION of the header it was built from). */
+int sdes_version(void);
+
+/* Text of the last error on this thread ("" if none). */
+const char* sdes_last_error(void);
+
+/* Bytes of device scratch one sdes_rollout_fwd call needs (per-step tables, re-laid-out weights). */
+size_t sdes_workspace_bytes(const SdesRolloutDesc* desc);
+
+/* The whole rollout: replaces `loss.simulate(ts, x, ...)` (losses/oc.py:156,:286,:400).
+ * Enqueues (1) a small prologue kernel that hoists everything x-independent into per-step
+ * tables and (2) ONE persistent kernel that carries each trajectory through all T steps. */
+int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream);
+
+/* Statistics of rnd that BaseOCLoss.filter/compute_loss/compute_results reduce to
+ * (losses/oc.py:50-123).  out_stats (device, 8 doubles):
+ *   [0] n_kept  [1] sum(rnd | kept)  [2] sum(rnd^2 | kept)  [3] max(-rnd | kept)
+ *   [4] sum(exp(-rnd - [3]) | kept)  [5] n_total  [6],[7] reserved (0)
+ * keep-mask by mask_mode: 0 = isfinite(rnd), 1 = rnd < max_rnd (oc.py:50-58), 2 = keep all
+ * (compute_results applies no mask, oc.py:94-123); `sample_mask` (B bytes, 0 = drop; may be
+ * NULL) is the result of the caller's filter_samples(x_T) (oc.py:53-55), AND-ed in.
+ * Ranks combine these without touching rnd again: n, sums add; max is max; the exp-sums are
+ * rescaled by exp([3]_rank - [3]_global) and added. */
+int sdes_rnd_stats(const float* rnd, int64_t batch, int mask_mode, float max_rnd,
+                   const uint8_t* sample_mask, double* out_stats, void* stream);
+
+/* Importance weights exp(-rnd - max(-rnd)) (losses/oc.py:104-105); the shift is stats[3], read on device. */
+int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* weights, void* stream);
+
+/* The noise stream on its own: eps (T,B,d) exactly as the fused kernel draws it in registers
+ * (Philox4x32-10 keyed by seed, counter (traj_offset+b, step, dim/4) + Box-Muller).  Test hook. */
+int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32_t n_steps,
+                       int32_t dim, float* out, void* stream);
+
+/* Kernel launches performed by this process through the library since load (for bench accounting). */
+int64_t sdes_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDES_B200_H */

@@ -1,0 +1,316 @@
+// sdes_api.cu — the extern "C" surface declared in include/sdes_b200.h, descriptor validation,
+// workspace layout, the rnd-statistics kernels and the noise-stream test hook.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "sdes_common.cuh"
+
+namespace sdes {
+void launch_prepare(const KParams& p, cudaStream_t stream);
+cudaError_t launch_rollout_simt(const KParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream);
+bool mma_supported(const KParams& p);
+int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad);
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static bool blob_layout(const SdesRolloutDesc& d, BlobLayout& bl) {
+    const int64_t dim = d.dim;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += n; return r; };
+    bl.in_w = take(C * dim);
+    bl.in_b = take(C);
+    bl.te_phase = take(C);
+    for (int l = 0; l < d.te_hidden; ++l) {
+        bl.te_h_w[l] = take((int64_t)C * (l == 0 ? 2 * C : C));
+        bl.te_h_b[l] = take(C);
+    }
+    bl.te_out_w = take(C * C);
+    bl.te_out_b = take(C);
+    for (int l = 0; l < d.n_hidden; ++l) {
+        bl.h_w[l] = take(C * C);
+        bl.h_b[l] = take(C);
+    }
+    bl.out_w = take(dim * C);
+    bl.out_b = take(dim);
+    if (d.flags & SDES_F_HAS_GATE) {
+        bl.g_phase = take(C);
+        for (int l = 0; l < d.gate_hidden; ++l) {
+            bl.g_h_w[l] = take((int64_t)C * (l == 0 ? 2 * C : C));
+            bl.g_h_b[l] = take(C);
+        }
+        bl.g_out_w = take((int64_t)d.gate_dim * C);
+        bl.g_out_b = take(d.gate_dim);
+    }
+    bl.total = o;
+    return true;
+}
+
+static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
+    const int dpad = pad_dim(d.dim);
+    const int64_t T = d.n_steps, K = d.target_kind == SDES_TARGET_GMM ? d.n_components : 0;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o = align_up(o + n, 64); return r; };
+    w.dpad = dpad;
+    w.tab = take(T * TAB_STRIDE);
+    w.emb = take(T * C);
+    w.gate = take(T * dpad);
+    w.gmm_mu = take(K * dpad);
+    w.gmm_h = take(K * dpad);
+    w.gmm_c = take(64);
+    w.prior = take(2 * dpad + 4);
+    w.ref = take(2 * dpad + 4);
+    w.w_simt_len = (int64_t)d.dim * C + C + (int64_t)d.n_hidden * (C * C + C) + (int64_t)C * dpad + dpad;
+    w.w_simt = take(w.w_simt_len);
+    w.w_mma_len = mma_weight_image_floats(d, dpad);
+    w.w_mma = take(w.w_mma_len);
+    w.counter = take(4);
+    w.total = o;
+}
+
+static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
+    if (d == nullptr) return fail(-1, "desc is NULL");
+    if (d->struct_bytes != sizeof(SdesRolloutDesc))
+        return fail(-2, "desc.struct_bytes=%u but this library expects %zu", d->struct_bytes, sizeof(SdesRolloutDesc));
+    if (d->abi_version != SDES_ABI_VERSION) return fail(-2, "desc.abi_version=%u, library is %d", d->abi_version, SDES_ABI_VERSION);
+    if (d->dim < 1 || d->dim > SDES_MAX_DIM) return fail(-3, "dim=%d not in [1,%d]", d->dim, SDES_MAX_DIM);
+    if (d->n_steps < 1) return fail(-3, "n_steps=%d < 1", d->n_steps);
+    if (d->batch < 0) return fail(-3, "batch < 0");
+    if (d->traj_offset + (uint64_t)d->batch > 0xFFFFFFFFull) return fail(-3, "traj_offset + batch exceeds the 32-bit Philox trajectory counter");
+    if (d->n_hidden < 0 || d->n_hidden > SDES_MAX_HIDDEN) return fail(-3, "n_hidden=%d not in [0,%d]", d->n_hidden, SDES_MAX_HIDDEN);
+    if (d->te_hidden < 1 || d->te_hidden > SDES_MAX_HIDDEN) return fail(-3, "te_hidden=%d not in [1,%d]", d->te_hidden, SDES_MAX_HIDDEN);
+    if (d->loss_kind < 0 || d->loss_kind > SDES_LOSS_EXP_INTEGRATOR) return fail(-3, "bad loss_kind %d", d->loss_kind);
+    if (d->ctrl_kind < 0 || d->ctrl_kind > SDES_CTRL_LERP_TARGET) return fail(-3, "bad ctrl_kind %d", d->ctrl_kind);
+    if (d->sde_kind < 0 || d->sde_kind > SDES_SDE_CONST_OU) return fail(-3, "bad sde_kind %d", d->sde_kind);
+    if (d->target_kind < 0 || d->target_kind > SDES_TARGET_FUNNEL) return fail(-3, "bad target_kind %d", d->target_kind);
+    if (d->loss_kind != SDES_LOSS_EXP_INTEGRATOR && d->sde_kind == SDES_SDE_NONE) return fail(-3, "this loss needs an sde");
+    if (d->ctrl_kind >= SDES_CTRL_LERP && d->sde_kind == SDES_SDE_NONE) return fail(-3, "Lerp controls need an sde");
+    if (d->flags & SDES_F_HAS_GATE) {
+        if (d->gate_hidden < 1 || d->gate_hidden > SDES_MAX_HIDDEN) return fail(-3, "gate_hidden=%d not in [1,%d]", d->gate_hidden, SDES_MAX_HIDDEN);
+        if (d->gate_dim != 1 && d->gate_dim != d->dim) return fail(-3, "gate_dim=%d must be 1 or dim", d->gate_dim);
+    }
+    if (d->target_kind == SDES_TARGET_GMM && (d->n_components < 1 || d->n_components > SDES_MAX_COMPONENTS))
+        return fail(-3, "n_components=%d not in [1,%d]", d->n_components, SDES_MAX_COMPONENTS);
+    if (d->target_kind == SDES_TARGET_MULTIWELL && (d->n_double_wells < 0 || d->n_double_wells > d->dim))
+        return fail(-3, "n_double_wells=%d not in [0,dim]", d->n_double_wells);
+    if (d->target_kind == SDES_TARGET_FUNNEL && d->dim < 2) return fail(-3, "funnel needs dim >= 2");
+    BlobLayout bl;
+    blob_layout(*d, bl);
+    if (d->n_params != bl.total) return fail(-4, "n_params=%lld but the layout for this descriptor has %lld floats", (long long)d->n_params, (long long)bl.total);
+    if (!need_ptrs) return 0;
+    if (!d->ts || !d->params || !d->x0 || !d->x_T || !d->rnd) return fail(-5, "ts/params/x0/x_T/rnd must be non-NULL");
+    if (d->target_kind == SDES_TARGET_GMM && (!d->gmm_loc || !d->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");
+    const bool need_prior = (d->loss_kind == SDES_LOSS_TIME_REVERSAL && !(d->flags & SDES_F_RND0_ZERO)) ||
+                            d->ctrl_kind == SDES_CTRL_LERP || d->ctrl_kind == SDES_CTRL_LERP_PRIOR ||
+                            (d->flags & SDES_F_REFERENCE_CTRL);
+    if (need_prior && (!d->prior_loc || !d->prior_scale)) return fail(-5, "prior_loc/prior_scale are NULL but this configuration reads the prior");
+    if (d->loss_kind != SDES_LOSS_TIME_REVERSAL && (!d->ref_loc || !d->ref_scale)) return fail(-5, "ref_loc/ref_scale are NULL");
+    if ((d->flags & SDES_F_NOISE_FROM_HBM) && !d->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
+    if ((d->flags & SDES_F_RETURN_TRAJ) && !d->xs) return fail(-5, "SDES_F_RETURN_TRAJ set but xs is NULL");
+    if (!d->workspace) return fail(-5, "workspace is NULL");
+    if (reinterpret_cast<uintptr_t>(d->workspace) % 256 != 0) return fail(-5, "workspace must be 256-byte aligned");
+    return 0;
+}
+
+// ------------------------------------------------------------------------- rnd statistics
+// One CTA: B is at most a few 1e6 floats, the rollout that produced them took milliseconds.
+__global__ void __launch_bounds__(1024) rnd_stats_kernel(const float* __restrict__ rnd, int64_t B, int mode,
+                                                         float max_rnd, const uint8_t* __restrict__ smask,
+                                                         double* __restrict__ out) {
+    __shared__ double s_a[32], s_b[32], s_c[32];
+    __shared__ float s_m[32];
+    __shared__ float s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double n = 0.0, s1 = 0.0, s2 = 0.0;
+    float mx = -INFINITY;
+    bool nan_seen = false;
+    for (int64_t i = tid; i < B; i += blockDim.x) {
+        const float r = rnd[i];
+        // losses/oc.py:50-58; mode 2 = no mask (compute_results, :94-123)
+        bool keep = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
+        if (smask != nullptr) keep = keep && smask[i] != 0;
+        if (keep) {
+            n += 1.0;
+            s1 += (double)r;
+            s2 += (double)r * (double)r;
+            mx = fmaxf(mx, -r);
+            nan_seen |= (r != r);
+        }
+    }
+    if (nan_seen) mx = NAN;
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = (mx != mx || om != om) ? NAN : fmaxf(mx, om);
+    }
+    if (lane == 0) { s_a[warp] = n; s_b[warp] = s1; s_c[warp] = s2; s_m[warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        n = s_a[lane]; s1 = s_b[lane]; s2 = s_c[lane]; mx = s_m[lane];
+        for (int o = 16; o > 0; o >>= 1) {
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = (mx != mx || om != om) ? NAN : fmaxf(mx, om);
+        }
+        if (lane == 0) {
+            out[0] = n; out[1] = s1; out[2] = s2; out[3] = (double)mx; out[5] = (double)B; out[6] = 0.0; out[7] = 0.0;
+            s_max = mx;
+        }
+    }
+    __syncthreads();
+    const float gmx = s_max;
+    double se = 0.0;
+    for (int64_t i = tid; i < B; i += blockDim.x) {
+        const float r = rnd[i];
+        bool keep = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
+        if (smask != nullptr) keep = keep && smask[i] != 0;
+        if (keep) se += (double)expf(-r - gmx);
+    }
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    __syncthreads();
+    if (lane == 0) s_a[warp] = se;
+    __syncthreads();
+    if (warp == 0) {
+        se = s_a[lane];
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        if (lane == 0) out[4] = se;
+    }
+}
+
+__global__ void weights_kernel(const float* __restrict__ rnd, int64_t B, const double* __restrict__ stats,
+                               float* __restrict__ w) {
+    const float mx = (float)stats[3];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+        w[i] = expf(-rnd[i] - mx);  // losses/oc.py:104-105
+}
+
+__global__ void philox_normal_kernel(uint64_t seed, uint64_t traj_offset, int64_t B, int T, int dim, float* __restrict__ out) {
+    const int nchunk = (dim + 3) / 4;
+    const int64_t total = (int64_t)T * B * nchunk;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(e % nchunk);
+        const int64_t b = (e / nchunk) % B;
+        const int i = (int)(e / ((int64_t)nchunk * B));
+        float n[4];
+        normal4(seed, (uint32_t)(traj_offset + (uint64_t)b), (uint32_t)i, (uint32_t)q, n[0], n[1], n[2], n[3]);
+        for (int r = 0; r < 4; ++r)
+            if (4 * q + r < dim) out[((int64_t)i * B + b) * dim + 4 * q + r] = n[r];
+    }
+}
+
+static int sm_count_cached() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace sdes
+
+using namespace sdes;
+
+extern "C" {
+
+int sdes_version(void) { return SDES_ABI_VERSION; }
+
+const char* sdes_last_error(void) { return g_err; }
+
+int64_t sdes_launch_count(void) { return g_launches.load(); }
+
+size_t sdes_workspace_bytes(const SdesRolloutDesc* desc) {
+    if (validate(desc, false) != 0) return 0;
+    WsLayout w;
+    ws_layout(*desc, w);
+    return (size_t)w.total * sizeof(float);
+}
+
+int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
+    g_err[0] = 0;
+    int rc = validate(desc, true);
+    if (rc != 0) return rc;
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = *desc;
+    blob_layout(p.d, p.bl);
+    ws_layout(p.d, p.ws);
+    if ((size_t)p.ws.total * sizeof(float) > desc->workspace_bytes)
+        return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, (size_t)p.ws.total * sizeof(float));
+    if (desc->batch == 0) return 0;
+    p.n_tiles = (int)((desc->batch + 31) / 32);
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    launch_prepare(p, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "prepare kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    const int sms = sm_count_cached();
+    if (desc->flags & SDES_F_MLP_SIMT) {
+        e = launch_rollout_simt(p, sms, stream);
+    } else {
+        if (!mma_supported(p)) return fail(-8, "the tcgen05 engine does not support this descriptor (dim=%d, n_hidden=%d); set SDES_F_MLP_SIMT", desc->dim, desc->n_hidden);
+        e = launch_rollout_mma(p, sms, stream);
+    }
+    if (e != cudaSuccess) return fail(-7, "rollout kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_rnd_stats(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,
+                   double* out_stats, void* stream_) {
+    g_err[0] = 0;
+    if (!rnd || !out_stats) return fail(-5, "rnd/out_stats NULL");
+    if (mask_mode < 0 || mask_mode > 2) return fail(-3, "mask_mode must be 0 (isfinite), 1 (< max_rnd) or 2 (all)");
+    rnd_stats_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, out_stats);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "rnd_stats launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* weights, void* stream_) {
+    g_err[0] = 0;
+    if (!rnd || !stats || !weights) return fail(-5, "rnd/stats/weights NULL");
+    if (batch == 0) return 0;
+    const int blocks = (int)((batch + 255) / 256 < 1184 ? (batch + 255) / 256 : 1184);
+    weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, stats, weights);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32_t n_steps, int32_t dim, float* out,
+                       void* stream_) {
+    g_err[0] = 0;
+    if (!out) return fail(-5, "out NULL");
+    if (batch <= 0 || n_steps <= 0 || dim <= 0) return fail(-3, "batch, n_steps, dim must be positive");
+    philox_normal_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(seed, traj_offset, batch, n_steps, dim, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "philox launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+}  // extern "C"

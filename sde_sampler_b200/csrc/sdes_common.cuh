@@ -1,0 +1,128 @@
+// sdes_common.cuh — shared device helpers and the host<->kernel parameter block.
+// Part of the B200-native rollout behind include/sdes_b200.h.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdes_b200.h"
+
+namespace sdes {
+
+constexpr int C = SDES_CHANNELS;  // network width
+constexpr int TAB_STRIDE = 8;     // floats per step in the scalar table
+// scalar table columns (one row per time step i, s = ts[i], t = ts[i+1])
+enum { TAB_DT = 0, TAB_SQRT_DT = 1, TAB_MU = 2, TAB_SIGMA = 3, TAB_DIV_INT = 4, TAB_LERP_W = 5,
+       TAB_BETA_K = 6, TAB_ALPHA_K = 7 };
+
+constexpr float LOG_2PI = 1.8378770664093453f;
+
+// Offsets (in floats) of everything the prologue kernel writes into the workspace.
+struct WsLayout {
+    int dpad;          // padded state dimension (template parameter of the rollout kernel)
+    int64_t tab;       // T * TAB_STRIDE
+    int64_t emb;       // T * C        FourierMLP.timestep_embed(s)        (models/mlp.py:116)
+    int64_t gate;      // T * dpad     clip(score_model(s), clip_model)    (models/reparam.py:68-76)
+    int64_t gmm_mu;    // K * dpad
+    int64_t gmm_h;     // K * dpad     0.5 / scale^2
+    int64_t gmm_c;     // K (padded to 64)   log w_k - sum_j log scale_kj - d/2 log 2pi
+    int64_t prior;     // 2 * dpad     loc | 1/scale^2           , + [2*dpad] = log-normaliser
+    int64_t ref;       // 2 * dpad + 4
+    int64_t w_simt;    // SIMT weights: WtIn[d][C] bIn[C] {Wt[C][C] b[C]} x nh  WtOut[C][dpad] bOut[dpad]
+    int64_t w_simt_len;
+    int64_t w_mma;     // tcgen05 operand images (see sdes_rollout_mma.cu)
+    int64_t w_mma_len;
+    int64_t counter;   // 4 uint32: dynamic tile counter
+    int64_t total;     // floats
+};
+
+// Offsets (in floats) inside the caller's parameter blob (layout: include/sdes_b200.h).
+struct BlobLayout {
+    int64_t in_w, in_b, te_phase, te_h_w[SDES_MAX_HIDDEN], te_h_b[SDES_MAX_HIDDEN], te_out_w, te_out_b;
+    int64_t h_w[SDES_MAX_HIDDEN], h_b[SDES_MAX_HIDDEN], out_w, out_b;
+    int64_t g_phase, g_h_w[SDES_MAX_HIDDEN], g_h_b[SDES_MAX_HIDDEN], g_out_w, g_out_b;
+    int64_t total;
+};
+
+// Everything a kernel needs, passed by value.
+struct KParams {
+    SdesRolloutDesc d;
+    WsLayout ws;
+    BlobLayout bl;
+    int n_tiles;  // warp tiles of 32 trajectories
+};
+
+__host__ __device__ inline int pad_dim(int d) {
+    if (d <= 4) return 4;
+    if (d <= 8) return 8;
+    if (d <= 12) return 12;
+    if (d <= 16) return 16;
+    if (d <= 32) return 32;
+    if (d <= 52) return 52;
+    return 64;
+}
+
+// ------------------------------------------------------------------------------------ math
+__device__ __forceinline__ float clipf(float v, float c) {
+    // utils/common.py:83-84 `tensor.clip(-max_norm, max_norm)`; c = +inf means no clip. NaN propagates.
+    return fminf(fmaxf(v, -c), c) + (v != v ? v : 0.0f);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    // torch.nn.GELU() default (exact erf; conf/model/base/fouriermlp.yaml:5-6)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float torch_lerp(float a, float b, float w) {
+    // torch.lerp: w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)
+    const float diff = b - a;
+    return (w < 0.5f) ? fmaf(w, diff, a) : (b - diff * (1.0f - w));
+}
+
+// ---------------------------------------------------------------------------------- philox
+// Counter-based noise stream, restated on the CPU in oracle/philox.py (bit-exact integers).
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t PHILOX_STREAM = 0x5DE5A301u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float u01(uint32_t r) {
+    // (0, 1]: r * 2^-32 + 2^-33, one FMA (the conversion rounds to nearest; product exact)
+    return fmaf(__uint2float_rn(r), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& n0, float& n1) {
+    const float ua = u01(ra), ub = u01(rb);
+    // rad = sqrt(-2 ln ua).  log2 via MUFU; -2 ln2 folded into one multiply.
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(ua));
+    const float theta = fmaf(6.283185307179586f, ub, -3.141592653589793f);
+    float sn, cs;
+    __sincosf(theta, &sn, &cs);
+    n0 = rad * cs;
+    n1 = rad * sn;
+}
+
+// four standard normals for (trajectory, step, dim chunk)
+__device__ __forceinline__ void normal4(uint64_t seed, uint32_t traj, uint32_t step, uint32_t chunk,
+                                        float& e0, float& e1, float& e2, float& e3) {
+    const uint4 r = philox4x32_10(traj, step, chunk, PHILOX_STREAM, (uint32_t)seed, (uint32_t)(seed >> 32));
+    box_muller(r.x, r.y, e0, e1);
+    box_muller(r.z, r.w, e2, e3);
+}
+
+}  // namespace sdes

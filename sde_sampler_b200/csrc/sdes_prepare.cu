@@ -1,0 +1,224 @@
+// sdes_prepare.cu — the prologue kernel: everything on the rollout path that does not
+// depend on the state x is hoisted out of the T-step loop into per-step tables.
+//
+//   * FourierMLP.timestep_embed(s_i)  (models/mlp.py:115-116 evaluates it on B identical rows
+//     every step)                                               -> emb  (T, C)
+//   * the scalar gate score_model(s_i), clipped (models/reparam.py:68-76) -> gate (T, dpad)
+//   * SDE coefficients mu(s_i), sigma(s_i), int div mu (eq/sdes.py:88-99,:222-245), dt, sqrt(dt),
+//     exponential-integrator alpha_k, beta_k (losses/oc.py:429-430)  -> tab  (T, 8)
+//   * kernel-ready images of the weights and of the target / prior parameters.
+//
+// Blocks [0, T) do one time step each; the remaining blocks re-lay-out parameters.
+#include "sdes_common.cuh"
+
+namespace sdes {
+
+__device__ __forceinline__ float linspace_coeff(int c) {
+    // torch.linspace(0.1, 100, 64) fp32 (models/mlp.py:58): step = (end-start)/(steps-1);
+    // first half start + step*i, second half end - step*(steps-1-i)  (ATen RangeFactories).
+    const float start = 0.1f, end = 100.0f;
+    const float step = __fdiv_rn(__fsub_rn(end, start), (float)(C - 1));
+    return (c < C / 2) ? __fadd_rn(start, __fmul_rn(step, (float)c))
+                       : __fsub_rn(end, __fmul_rn(step, (float)(C - 1 - c)));
+}
+
+// One TimeEmbed forward (models/mlp.py:71-82) for a single time value, by one block.
+// buf_a/buf_b: 2C floats each.  Result (n_out values) left in buf_out[0..n_out).
+__device__ void time_embed_row(const float* __restrict__ blob, int64_t o_phase, const int64_t* o_hw,
+                               const int64_t* o_hb, int n_hidden, int64_t o_ow, int64_t o_ob, int n_out,
+                               float s, float* buf_a, float* buf_b, float* buf_out) {
+    const int tid = threadIdx.x;
+    if (tid < 2 * C) {
+        const int c = tid & (C - 1);
+        // (coeff * t) + phase, separately rounded as the reference's two tensor ops
+        const float arg = __fadd_rn(__fmul_rn(linspace_coeff(c), s), blob[o_phase + c]);
+        buf_a[tid] = (tid < C) ? sinf(arg) : cosf(arg);
+    }
+    __syncthreads();
+    float* in = buf_a;
+    float* out = buf_b;
+    int k_in = 2 * C;
+    for (int l = 0; l < n_hidden; ++l) {
+        if (tid < C) {
+            const float* w = blob + o_hw[l] + (int64_t)tid * k_in;
+            float acc = blob[o_hb[l] + tid];
+            for (int k = 0; k < k_in; ++k) acc = fmaf(w[k], in[k], acc);
+            out[tid] = gelu_erf(acc);
+        }
+        __syncthreads();
+        float* tmp = in; in = out; out = tmp;
+        k_in = C;
+    }
+    if (tid < n_out) {
+        const float* w = blob + o_ow + (int64_t)tid * C;
+        float acc = blob[o_ob + tid];
+        for (int k = 0; k < C; ++k) acc = fmaf(w[k], in[k], acc);
+        buf_out[tid] = acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
+    const SdesRolloutDesc& d = p.d;
+    float* ws = reinterpret_cast<float*>(d.workspace);
+    const float* blob = d.params;
+    const int T = d.n_steps, dim = d.dim, dpad = p.ws.dpad;
+    const int tid = threadIdx.x;
+
+    if ((int)blockIdx.x < T) {
+        __shared__ float buf_a[2 * C], buf_b[2 * C], buf_out[C];
+        const int i = blockIdx.x;
+        const float s = d.ts[i], t = d.ts[i + 1];
+        const float dt = __fsub_rn(t, s);
+        if (tid == 0) {
+            float mu = 0.f, sigma = 0.f, div_int = 0.f, lerp_w = 0.f;
+            if (d.sde_kind == SDES_SDE_VP) {
+                // VP._diff_coeff_sq_t eq/sdes.py:222-229: generative (sign>0) runs beta_max -> beta_min
+                const float ws_ = __fdiv_rn(s, d.terminal_t), wt_ = __fdiv_rn(t, d.terminal_t);
+                const float b0 = d.sde_sign > 0.f ? d.beta_max : d.beta_min;
+                const float b1 = d.sde_sign > 0.f ? d.beta_min : d.beta_max;
+                const float beta_s = torch_lerp(b0, b1, ws_), beta_t = torch_lerp(b0, b1, wt_);
+                mu = d.sde_sign * 0.5f * beta_s;                        // :231-232
+                sigma = d.scale_diff * sqrtf(beta_s);                   // :234-235
+                div_int = d.sde_sign * 0.25f * (beta_t + beta_s) * dt * (float)dim;  // :237-245, :88-91
+                lerp_w = ws_;
+            } else if (d.sde_kind == SDES_SDE_CONST_OU) {
+                mu = d.sde_sign * d.drift_coeff;                        // eq/sdes.py:141-145
+                sigma = d.diff_coeff;
+                div_int = d.sde_sign * d.drift_coeff * dt * (float)dim;
+                lerp_w = __fdiv_rn(s, d.terminal_t);
+            }
+            float beta_k = 0.f, alpha_k = 0.f;
+            if (d.loss_kind == SDES_LOSS_EXP_INTEGRATOR) {
+                beta_k = fminf(fmaxf(d.alpha * sqrtf(dt), 0.f), 1.f);   // losses/oc.py:429
+                alpha_k = sqrtf(1.0f - beta_k * beta_k);                // :430
+            }
+            float* row = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
+            row[TAB_DT] = dt;
+            row[TAB_SQRT_DT] = sqrtf(dt);
+            row[TAB_MU] = mu;
+            row[TAB_SIGMA] = sigma;
+            row[TAB_DIV_INT] = div_int;
+            row[TAB_LERP_W] = lerp_w;
+            row[TAB_BETA_K] = beta_k;
+            row[TAB_ALPHA_K] = alpha_k;
+        }
+        // FourierMLP.timestep_embed(s)
+        time_embed_row(blob, p.bl.te_phase, p.bl.te_h_w, p.bl.te_h_b, d.te_hidden, p.bl.te_out_w,
+                       p.bl.te_out_b, C, s, buf_a, buf_b, buf_out);
+        if (tid < C) ws[p.ws.emb + (int64_t)i * C + tid] = buf_out[tid];
+        __syncthreads();
+        // gate
+        float* grow = ws + p.ws.gate + (int64_t)i * dpad;
+        if (d.flags & SDES_F_HAS_GATE) {
+            time_embed_row(blob, p.bl.g_phase, p.bl.g_h_w, p.bl.g_h_b, d.gate_hidden, p.bl.g_out_w,
+                           p.bl.g_out_b, d.gate_dim, s, buf_a, buf_b, buf_out);
+            if (tid < dpad)
+                grow[tid] = tid < dim ? clipf(buf_out[d.gate_dim == 1 ? 0 : tid], d.clip_model) : 0.f;
+        } else if (tid < dpad) {
+            grow[tid] = tid < dim ? 1.0f : 0.f;
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ parameter images
+    const int64_t nthreads = (int64_t)(gridDim.x - T) * blockDim.x;
+    const int64_t gtid = (int64_t)(blockIdx.x - T) * blockDim.x + tid;
+    const int nh = d.n_hidden;
+
+    if (gtid == 0) {
+        uint32_t* ctr = reinterpret_cast<uint32_t*>(ws + p.ws.counter);
+        ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0u;
+    }
+
+    // SIMT weight image: WtIn[d][C] bIn[C] {Wt[C][C] b[C]} x nh  WtOut[C][dpad] bOut[dpad]
+    {
+        float* w = ws + p.ws.w_simt;
+        int64_t o = 0;
+        for (int64_t e = gtid; e < (int64_t)dim * C; e += nthreads) {
+            const int k = (int)(e / C), n = (int)(e % C);
+            w[o + e] = blob[p.bl.in_w + (int64_t)n * dim + k];
+        }
+        o += (int64_t)dim * C;
+        for (int64_t e = gtid; e < C; e += nthreads) w[o + e] = blob[p.bl.in_b + e];
+        o += C;
+        for (int l = 0; l < nh; ++l) {
+            for (int64_t e = gtid; e < C * C; e += nthreads) {
+                const int k = (int)(e / C), n = (int)(e % C);
+                w[o + e] = blob[p.bl.h_w[l] + (int64_t)n * C + k];
+            }
+            o += C * C;
+            for (int64_t e = gtid; e < C; e += nthreads) w[o + e] = blob[p.bl.h_b[l] + e];
+            o += C;
+        }
+        for (int64_t e = gtid; e < (int64_t)C * dpad; e += nthreads) {
+            const int k = (int)(e / dpad), n = (int)(e % dpad);
+            w[o + e] = n < dim ? blob[p.bl.out_w + (int64_t)n * C + k] : 0.f;
+        }
+        o += (int64_t)C * dpad;
+        for (int64_t e = gtid; e < dpad; e += nthreads) w[o + e] = e < dim ? blob[p.bl.out_b + e] : 0.f;
+    }
+
+    // GMM image (distr/gauss.py:119-140): mu, h = 0.5/scale^2, c_k = log w_k - sum log scale - d/2 log 2pi
+    if (d.target_kind == SDES_TARGET_GMM) {
+        const int K = d.n_components;
+        for (int64_t e = gtid; e < (int64_t)K * dpad; e += nthreads) {
+            const int k = (int)(e / dpad), j = (int)(e % dpad);
+            float mu = 0.f, h = 0.f;
+            if (j < dim) {
+                mu = d.gmm_loc[(int64_t)k * dim + j];
+                const float sc = d.gmm_scale[(int64_t)k * dim + j];
+                h = 0.5f / (sc * sc);
+            }
+            ws[p.ws.gmm_mu + e] = mu;
+            ws[p.ws.gmm_h + e] = h;
+        }
+        for (int64_t k = gtid; k < 64; k += nthreads) {
+            float c = -INFINITY;
+            if (k < K) {
+                float logw = 0.f;
+                if (d.gmm_weights != nullptr) {
+                    float tot = 0.f;
+                    for (int q = 0; q < K; ++q) tot += d.gmm_weights[q];
+                    logw = logf(d.gmm_weights[k] / tot);  // Categorical(probs=w) normalises
+                }
+                float sl = 0.f;
+                for (int j = 0; j < dim; ++j) sl += logf(d.gmm_scale[k * dim + j]);
+                c = logw - sl - 0.5f * (float)dim * LOG_2PI;
+            }
+            ws[p.ws.gmm_c + k] = c;
+        }
+    }
+
+    // diagonal Gaussians: loc | 1/scale^2 | log-normaliser   (distr/gauss.py:131-140, :215-223)
+    for (int which = 0; which < 2; ++which) {
+        const float* loc = which == 0 ? d.prior_loc : d.ref_loc;
+        const float* scale = which == 0 ? d.prior_scale : d.ref_scale;
+        float* out = ws + (which == 0 ? p.ws.prior : p.ws.ref);
+        for (int64_t j = gtid; j < dpad; j += nthreads) {
+            float m = 0.f, iv = 0.f;
+            if (loc != nullptr && j < dim) {
+                m = loc[j];
+                const float sc = scale[j];
+                iv = 1.0f / (sc * sc);
+            }
+            out[j] = m;
+            out[dpad + j] = iv;
+        }
+        if (gtid == 0) {
+            float ln = 0.f;
+            if (loc != nullptr) {
+                for (int j = 0; j < dim; ++j) ln -= logf(scale[j]);
+                ln -= 0.5f * (float)dim * LOG_2PI;
+            }
+            out[2 * dpad] = ln;
+        }
+    }
+}
+
+void launch_prepare(const KParams& p, cudaStream_t stream) {
+    const int relayout_blocks = 16;
+    prepare_kernel<<<p.d.n_steps + relayout_blocks, 256, 0, stream>>>(p);
+}
+
+}  // namespace sdes

@@ -1,0 +1,229 @@
+"""RolloutSpec -> SdesRolloutDesc -> one call of the CUDA library.
+
+PyTorch is plumbing here: device memory for inputs/outputs/workspace, the current stream and
+one `torch.cat` that packs the caller's parameters into the flat blob the C ABI expects.
+Every arithmetic operation of the rollout happens inside `sdes_rollout_fwd`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _cabi
+from .spec import RolloutSpec
+
+_ENGINES = ("auto", "tcgen05", "simt")
+
+
+def _inf(v) -> float:
+    return math.inf if v is None else float(v)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def pack_params(spec: RolloutSpec) -> torch.Tensor:
+    """Flat fp32 parameter blob in the order documented in include/sdes_b200.h."""
+    m = spec.mlp
+    te = m["time_embed"]
+    parts = [m["in_w"], m["in_b"], te["phase"]]
+    for w, b in te["hidden"]:
+        parts += [w, b]
+    parts += [te["out_w"], te["out_b"]]
+    for w, b in m["hidden"]:
+        parts += [w, b]
+    parts += [m["out_w"], m["out_b"]]
+    if spec.gate is not None:
+        g = spec.gate
+        parts += [g["phase"]]
+        for w, b in g["hidden"]:
+            parts += [w, b]
+        parts += [g["out_w"], g["out_b"]]
+    return torch.cat([p.reshape(-1).to(torch.float32) for p in parts])
+
+
+class Workspace:
+    """Grow-only device scratch, one per loss object and device (allocations are cached across calls;
+    nothing else is)."""
+
+    def __init__(self):
+        self.buf: torch.Tensor | None = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+def fill_desc(spec: RolloutSpec, *, batch: int, engine: str = "auto") -> tuple[_cabi.RolloutDesc, list]:
+    """Everything of the descriptor except the per-call pointers x0/noise/outputs/workspace.
+    Returns (desc, keepalive tensors)."""
+    if engine not in _ENGINES:
+        raise ValueError(f"engine must be one of {_ENGINES}")
+    d = _cabi.new_desc()
+    keep = []
+    ls, cd, tg = spec.loss, spec.ctrl, spec.target
+    d.loss_kind = _cabi.LOSS[ls["kind"]]
+    d.ctrl_kind = _cabi.CTRL[cd["kind"]]
+    flags = 0
+    if ls["kind"] == "time_reversal" and ls["train"] and ls["method"] in ("kl", "kl_ito"):
+        flags |= _cabi.F_RND0_ZERO
+    if ls["compute_ito"]:
+        flags |= _cabi.F_COMPUTE_ITO
+    if ls["kind"] == "time_reversal" and not ls["train"]:
+        flags |= _cabi.F_SUB_DIV_INT
+    if ls.get("return_traj"):
+        flags |= _cabi.F_RETURN_TRAJ
+    if ls.get("reference_ctrl"):
+        flags |= _cabi.F_REFERENCE_CTRL
+    if spec.gate is not None:
+        flags |= _cabi.F_HAS_GATE
+    if engine == "simt":
+        flags |= _cabi.F_MLP_SIMT
+    d.dim = spec.dim
+    d.n_steps = int(spec.ts.shape[0]) - 1
+    d.n_hidden = len(spec.mlp["hidden"])
+    d.te_hidden = len(spec.mlp["time_embed"]["hidden"])
+    if spec.gate is not None:
+        d.gate_hidden = len(spec.gate["hidden"])
+        d.gate_dim = int(spec.gate["out_w"].shape[0])
+    d.batch = batch
+    d.clip_model = _inf(cd.get("clip_model"))
+    d.clip_score = _inf(cd.get("clip_score"))
+    d.clip_target = _inf(tg.get("clip_target"))
+    d.scale_score = float(cd.get("scale_score", 1.0))
+    d.alpha = float(ls.get("alpha", 0.0))
+    d.sigma = float(ls.get("sigma", 0.0))
+    sde = spec.sde
+    if sde is None:
+        d.sde_kind = _cabi.SDE_NONE
+    elif sde["kind"] == "vp":
+        d.sde_kind = _cabi.SDE_VP
+        d.beta_min, d.beta_max = sde["beta_min"], sde["beta_max"]
+        d.scale_diff, d.terminal_t, d.sde_sign = sde["scale"], sde["terminal_t"], sde["sign"]
+    else:
+        d.sde_kind = _cabi.SDE_CONST_OU
+        d.drift_coeff, d.diff_coeff = sde["drift_coeff"], sde["diff_coeff"]
+        d.terminal_t, d.sde_sign = sde["terminal_t"], sde["sign"]
+    d.log_norm_const = float(tg.get("log_norm_const", 0.0) or 0.0)
+    if tg["kind"] == "gmm":
+        d.target_kind = _cabi.TARGET_GMM
+        d.n_components = int(tg["loc"].shape[0])
+        d.gmm_loc, d.gmm_scale, d.gmm_weights = _ptr(tg["loc"]), _ptr(tg["scale"]), _ptr(tg["weights"])
+        keep += [tg["loc"], tg["scale"], tg["weights"]]
+    elif tg["kind"] == "gauss":  # a diagonal Gaussian target is the K=1 mixture
+        d.target_kind = _cabi.TARGET_GMM
+        d.n_components = 1
+        d.gmm_loc, d.gmm_scale, d.gmm_weights = _ptr(tg["loc"]), _ptr(tg["scale"]), None
+        keep += [tg["loc"], tg["scale"]]
+    elif tg["kind"] == "multiwell":
+        d.target_kind = _cabi.TARGET_MULTIWELL
+        d.n_double_wells = int(tg["n_dw"])
+        d.separation, d.shift = float(tg["separation"]), float(tg["shift"])
+    elif tg["kind"] == "funnel":
+        d.target_kind = _cabi.TARGET_FUNNEL
+        d.variance = float(tg["variance"])
+    else:
+        raise NotImplementedError(tg["kind"])
+    if spec.prior is not None:
+        d.prior_loc, d.prior_scale = _ptr(spec.prior["loc"]), _ptr(spec.prior["scale"])
+        keep += [spec.prior["loc"], spec.prior["scale"]]
+    if spec.ref is not None:
+        d.ref_loc, d.ref_scale = _ptr(spec.ref["loc"]), _ptr(spec.ref["scale"])
+        keep += [spec.ref["loc"], spec.ref["scale"]]
+    d.flags = flags
+    return d, keep
+
+
+def _check_device(name: str, t: torch.Tensor | None, device):
+    if t is not None and t.device != device:
+        raise ValueError(f"{name} lives on {t.device}, the rollout runs on {device}")
+
+
+def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
+            traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
+            params: torch.Tensor | None = None):
+    """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None)."""
+    lib = _cabi.lib()
+    if not x0.is_cuda:
+        raise _cabi.SdesError("the fused rollout runs on a CUDA device only (x is on %s); there is no CPU path" % x0.device)
+    if x0.ndim != 2 or x0.shape[1] != spec.dim:
+        raise ValueError(f"x must be (B, {spec.dim}), got {tuple(x0.shape)}")
+    device = x0.device
+    B, dim = x0.shape
+    T = int(spec.ts.shape[0]) - 1
+    x0c = x0.detach().to(torch.float32).contiguous()
+    ts = spec.ts.to(device=device, dtype=torch.float32).contiguous()
+    d, keep = fill_desc(spec, batch=B, engine=engine)
+    if params is None:
+        params = pack_params(spec)
+    _check_device("model parameters", params, device)
+    for k in keep:
+        _check_device("distribution parameters", k, device)
+    d.ts, d.params, d.n_params = ts.data_ptr(), params.data_ptr(), params.numel()
+    d.seed, d.traj_offset = seed & 0xFFFFFFFFFFFFFFFF, traj_offset
+    x_T = torch.empty_like(x0c)
+    rnd = torch.empty((B, 1), dtype=torch.float32, device=device)
+    xs = None
+    if d.flags & _cabi.F_RETURN_TRAJ:
+        xs = torch.empty((T + 1, B, dim), dtype=torch.float32, device=device)
+        d.xs = xs.data_ptr()
+    if noise is not None:
+        if tuple(noise.shape) != (T, B, dim):
+            raise ValueError(f"noise must be {(T, B, dim)}, got {tuple(noise.shape)}")
+        noise = noise.to(device=device, dtype=torch.float32).contiguous()
+        d.noise = noise.data_ptr()
+        d.flags |= _cabi.F_NOISE_FROM_HBM
+    d.x0, d.x_T, d.rnd = x0c.data_ptr(), x_T.data_ptr(), rnd.data_ptr()
+    with torch.cuda.device(device):
+        need = lib.sdes_workspace_bytes(C.byref(d))
+        if need == 0:
+            raise _cabi.SdesError("invalid descriptor: " + lib.sdes_last_error().decode())
+        wsbuf = (workspace or Workspace()).get(need, device)
+        d.workspace, d.workspace_bytes = wsbuf.data_ptr(), wsbuf.numel()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _cabi.check(lib.sdes_rollout_fwd(C.byref(d), C.c_void_p(stream)), "sdes_rollout_fwd")
+    return x_T, rnd, xs
+
+
+def rnd_stats(rnd: torch.Tensor, mask_mode: int, max_rnd: float = 0.0,
+              sample_mask: torch.Tensor | None = None) -> torch.Tensor:
+    """8 doubles on the device (layout: include/sdes_b200.h `sdes_rnd_stats`)."""
+    lib = _cabi.lib()
+    r = rnd.detach().reshape(-1).to(torch.float32).contiguous()
+    out = torch.empty(8, dtype=torch.float64, device=r.device)
+    m = None
+    if sample_mask is not None:
+        m = sample_mask.reshape(-1).to(torch.uint8).contiguous()
+        if m.numel() != r.numel():
+            raise ValueError("filter_samples must return one flag per sample")
+    with torch.cuda.device(r.device):
+        stream = torch.cuda.current_stream(r.device).cuda_stream
+        _cabi.check(lib.sdes_rnd_stats(r.data_ptr(), r.numel(), mask_mode, float(max_rnd), _ptr(m),
+                                       out.data_ptr(), C.c_void_p(stream)), "sdes_rnd_stats")
+    return out
+
+
+def importance_weights(rnd: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+    lib = _cabi.lib()
+    r = rnd.detach().reshape(-1).to(torch.float32).contiguous()
+    w = torch.empty_like(r)
+    with torch.cuda.device(r.device):
+        stream = torch.cuda.current_stream(r.device).cuda_stream
+        _cabi.check(lib.sdes_weights(r.data_ptr(), r.numel(), stats.data_ptr(), w.data_ptr(), C.c_void_p(stream)),
+                    "sdes_weights")
+    return w.reshape(-1, 1)
+
+
+def philox_normal(seed: int, traj_offset: int, batch: int, n_steps: int, dim: int, device) -> torch.Tensor:
+    """The in-kernel noise stream written out to HBM (test hook)."""
+    lib = _cabi.lib()
+    out = torch.empty((n_steps, batch, dim), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _cabi.check(lib.sdes_philox_normal(seed & 0xFFFFFFFFFFFFFFFF, traj_offset, batch, n_steps, dim,
+                                           out.data_ptr(), C.c_void_p(stream)), "sdes_philox_normal")
+    return out

@@ -1,0 +1,300 @@
+"""Drop-in replacements for the reference's optimal-control losses (sde_sampler/losses/oc.py).
+
+    loss._target_: sde_sampler_b200.FusedTimeReversalLoss            (conf/loss/time_reversal*.yaml:2)
+                   sde_sampler_b200.FusedReferenceSDELoss            (conf/loss/reference_sde*.yaml:2)
+                   sde_sampler_b200.FusedExponentialIntegratorSDELoss (conf/loss/exponential_sde*.yaml:2)
+
+Same constructor arguments, same `__call__` / `eval` / `simulate` / `compute_loss` /
+`compute_results` / `state_dict` surface and error behaviour as `BaseOCLoss` and its three
+subclasses (losses/oc.py:13-137, :139-278, :281-392, :395-483) — but `simulate` is ONE call
+into the CUDA library instead of a Python loop over time steps, and the reductions run in a
+CUDA kernel whose partial statistics are combined across ranks when a process group is given.
+
+What is not implemented raises (`NotImplementedError`) instead of falling back: a learned
+`inference_ctrl`, `sde_ctrl_noise` / `sde_ctrl_dropout`, targets other than GMM / Gauss /
+DoubleWell / MultiWell / Funnel, and gradients (the returned loss is a value; the backward of
+the rollout is the next row of SURVEY §8f).
+"""
+from __future__ import annotations
+
+import logging
+from collections import namedtuple
+from typing import Callable
+
+import torch
+
+from . import _cabi, engine
+from .dist import combine_stats
+from .spec import extract_spec
+
+# utils/common.py:9-13
+Results = namedtuple(
+    "Results",
+    "samples weights log_norm_const_preds expectation_preds ts xs metrics plots",
+    defaults=[{}, {}, None, None, None, None, {}, {}],
+)
+
+
+class FusedOCLoss:
+    """BaseOCLoss (losses/oc.py:13-137) on the fused kernel."""
+
+    loss_kind: str = ""
+
+    def __init__(
+        self,
+        generative_ctrl: Callable,
+        sde=None,
+        method: str = "kl",
+        traj_per_sample: int = 1,
+        filter_samples: Callable | None = None,
+        max_rnd: float | None = None,
+        sde_ctrl_dropout: float | None = None,
+        sde_ctrl_noise: float | None = None,
+        *,
+        seed: int | None = None,
+        engine: str = "auto",
+        process_group=None,
+        **kwargs,
+    ):
+        self.generative_ctrl = generative_ctrl
+        self.sde = sde
+        if method not in ["kl", "kl_ito", "lv", "lv_traj"]:
+            raise ValueError("Unknown loss method.")
+        self.method = method
+        if traj_per_sample == 1 and self.method == "lv_traj":
+            raise ValueError("Cannot compute variance over a single trajectory.")
+        self.traj_per_sample = traj_per_sample
+        self.filter_samples = filter_samples
+        self.max_rnd = max_rnd
+        self.sde_ctrl_noise = sde_ctrl_noise
+        self.sde_ctrl_dropout = sde_ctrl_dropout
+        if sde_ctrl_noise is not None or sde_ctrl_dropout is not None:
+            raise NotImplementedError("sde_ctrl_noise / sde_ctrl_dropout are not implemented in the fused rollout")
+        self.n_filtered = 0
+        # fused-path extras (keyword-only, absent from the reference signature)
+        self.engine = engine
+        self.process_group = process_group
+        self._seed = seed
+        self._calls = 0
+        self._workspace = engine_workspace()
+        _cabi.lib()  # fail now, not at the first step, if the CUDA library is missing
+
+    # ------------------------------------------------------------------ noise stream
+    def _next_seed(self) -> int:
+        """Philox key for the next rollout: low word = base seed (torch.initial_seed() unless
+        given), high word = number of rollouts this loss has run, so every call draws fresh
+        noise (the reference advances torch's global generator, losses/oc.py:214)."""
+        base = torch.initial_seed() if self._seed is None else self._seed
+        key = ((self._calls & 0xFFFFFFFF) << 32) | (base & 0xFFFFFFFF)
+        self._calls += 1
+        return key
+
+    def _rank_offset(self, batch: int) -> int:
+        """Global index of this rank's first trajectory: ranks hold contiguous shards of the
+        global batch, so the noise a trajectory sees does not depend on the number of GPUs."""
+        pg = self.process_group
+        if pg is None:
+            return 0
+        import torch.distributed as dist
+
+        return dist.get_rank(pg) * batch
+
+    # ---------------------------------------------------------------------- rollout
+    def _simulate(self, ts, x, terminal_unnorm_log_prob, second_log_prob, *, train, compute_ito_int,
+                  return_traj, noise=None):
+        spec = extract_spec(self, self.loss_kind, ts, terminal_unnorm_log_prob, second_log_prob,
+                            train=train, compute_ito=compute_ito_int, return_traj=return_traj)
+        x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=self._next_seed(),
+                                      traj_offset=self._rank_offset(x.shape[0]), engine=self.engine,
+                                      workspace=self._workspace)
+        return x_T, rnd, xs
+
+    # ------------------------------------------------------------------- reductions
+    def filter(self, rnd: torch.Tensor, samples: torch.Tensor | None = None) -> torch.Tensor:
+        """losses/oc.py:50-58 (kept for API parity; compute_loss uses the stats kernel)."""
+        mask = True
+        if samples is not None and self.filter_samples is not None:
+            mask = self.filter_samples(samples)
+        if self.max_rnd is None:
+            return mask & rnd.isfinite()
+        return mask & (rnd < self.max_rnd)
+
+    def _stats(self, rnd, samples=None, mask_mode=None):
+        smask = None
+        if samples is not None and self.filter_samples is not None:
+            smask = self.filter_samples(samples)
+        if mask_mode is None:
+            mask_mode = _cabi.MASK_ISFINITE if self.max_rnd is None else _cabi.MASK_MAX_RND
+        st = engine.rnd_stats(rnd, mask_mode, 0.0 if self.max_rnd is None else self.max_rnd, smask)
+        return combine_stats(st, self.process_group)
+
+    def compute_loss(self, rnd: torch.Tensor, samples: torch.Tensor | None = None) -> tuple[torch.Tensor, dict]:
+        """losses/oc.py:72-92.  lv: unbiased variance of the kept rnd; kl: their mean."""
+        if self.method == "lv_traj":
+            return self._compute_loss_lv_traj(rnd, samples)
+        st = self._stats(rnd, samples)
+        n, s1, s2 = st[0], st[1], st[2]
+        self.n_filtered += int((st[5] - n).item())  # the reference syncs here too (.item(), oc.py:86)
+        if self.method == "lv":
+            loss = (s2 - s1 * s1 / n) / (n - 1.0)
+        else:
+            loss = s1 / n
+        return loss.to(torch.float32), {"train/n_filtered_cumulative": self.n_filtered}
+
+    def _compute_loss_lv_traj(self, rnd, samples):
+        # variance over the traj_per_sample copies of each x0 (oc.py:78-84): a (tps, B0) view of rnd.
+        mask = self.filter(rnd, samples=samples)
+        r = rnd.reshape(self.traj_per_sample, -1, 1)
+        mask = mask.reshape(self.traj_per_sample, -1, 1).all(dim=0)
+        self.n_filtered += self.traj_per_sample * (mask.numel() - mask.sum()).item()
+        if self.process_group is not None:
+            raise NotImplementedError("lv_traj across ranks")
+        loss = r[:, mask].var(dim=0).mean()
+        return loss, {"train/n_filtered_cumulative": self.n_filtered}
+
+    def compute_results(self, rnd: torch.Tensor, compute_weights: bool = False, ts=None, samples=None, xs=None):
+        """losses/oc.py:94-123 (a staticmethod there; an instance method here because the
+        statistics may span ranks — `FusedOCLoss.compute_results_local` is the static form)."""
+        return _compute_results(rnd, compute_weights, ts, samples, xs, self.process_group)
+
+    @staticmethod
+    def compute_results_local(rnd, compute_weights=False, ts=None, samples=None, xs=None):
+        return _compute_results(rnd, compute_weights, ts, samples, xs, None)
+
+    def __call__(self, ts: torch.Tensor, x: torch.Tensor, *args, **kwargs) -> tuple[torch.Tensor, dict]:
+        raise NotImplementedError
+
+    def eval(self, ts: torch.Tensor, x: torch.Tensor, *args, **kwargs) -> Results:
+        raise NotImplementedError
+
+    def load_state_dict(self, state_dict: dict):
+        self.n_filtered = state_dict["n_filtered"]
+
+    def state_dict(self) -> dict:
+        return {"n_filtered": self.n_filtered}
+
+    def _repeat(self, x):
+        if self.traj_per_sample != 1:
+            x = x.repeat(self.traj_per_sample, 1, 1).reshape(-1, x.shape[-1])
+        return x
+
+
+def engine_workspace():
+    return engine.Workspace()
+
+
+def _compute_results(rnd, compute_weights, ts, samples, xs, process_group) -> Results:
+    metrics = {}
+    st = combine_stats(engine.rnd_stats(rnd, _cabi.MASK_ALL), process_group)
+    host = st.tolist()  # one sync; the reference does three .item() calls here
+    n, s1, s2, mx, se = host[0], host[1], host[2], host[3], host[4]
+    neg_mean = -s1 / n
+    if compute_weights:
+        weights = engine.importance_weights(rnd, st)
+        import math
+
+        log_norm_const_preds = {
+            "log_norm_const_lb_ito": neg_mean,
+            "log_norm_const_is": math.log(se / n) + mx if se > 0 else float("nan") if se != se else -math.inf,
+        }
+        metrics["eval/lv_loss"] = (s2 - s1 * s1 / n) / (n - 1.0) if n > 1 else float("nan")
+    else:
+        weights = None
+        log_norm_const_preds = {"log_norm_const_lb": neg_mean}
+    return Results(samples=samples, weights=weights, log_norm_const_preds=log_norm_const_preds, ts=ts, xs=xs,
+                   metrics=metrics)
+
+
+class FusedTimeReversalLoss(FusedOCLoss):
+    """TimeReversalLoss (losses/oc.py:139-278): DIS / Bridge without a learned inference control."""
+
+    loss_kind = "time_reversal"
+
+    def __init__(self, *args, inference_ctrl: Callable | None = None, div_estimator: str | None = None, **kwargs):
+        super().__init__(*args, **kwargs)
+        if inference_ctrl is not None:
+            raise NotImplementedError(
+                "a learned inference_ctrl needs div_x of a network (utils/autograd.py) — not on the fused path")
+        self.inference_ctrl = inference_ctrl
+        self.div_estimator = div_estimator
+        if self.div_estimator is not None and self.inference_ctrl is None:
+            logging.warning("Without inference control the divergence estimator has no effect.")
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, train=True, compute_ito_int=False,
+                 change_sde_ctrl=False, return_traj=False, noise=None):
+        # change_sde_ctrl only changes what the autograd graph sees (sde_ctrl = g.detach()), not values
+        return self._simulate(ts, x, terminal_unnorm_log_prob, initial_log_prob, train=train,
+                              compute_ito_int=compute_ito_int, return_traj=return_traj, noise=noise)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob):
+        x = self._repeat(x)
+        samples, rnd, _ = self.simulate(
+            ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, initial_log_prob=initial_log_prob,
+            compute_ito_int=self.method != "kl", change_sde_ctrl=self.method in ["lv", "lv_traj"],
+            train=True, return_traj=False)
+        return self.compute_loss(rnd, samples=samples)
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, compute_weights=True, return_traj=True):
+        samples, rnd, xs = self.simulate(
+            ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, initial_log_prob=initial_log_prob,
+            compute_ito_int=compute_weights, train=False, return_traj=return_traj)
+        return self.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
+
+
+class FusedReferenceSDELoss(FusedOCLoss):
+    """ReferenceSDELoss (losses/oc.py:281-392): PIS and Euler-DDS."""
+
+    loss_kind = "reference_sde"
+
+    def __init__(self, *args, reference_ctrl: Callable | None = None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.reference_ctrl = reference_ctrl
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, compute_ito_int=False,
+                 change_sde_ctrl=False, return_traj=False, noise=None):
+        return self._simulate(ts, x, terminal_unnorm_log_prob, reference_log_prob, train=True,
+                              compute_ito_int=compute_ito_int, return_traj=return_traj, noise=noise)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob):
+        x = self._repeat(x)
+        samples, rnd, _ = self.simulate(
+            ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, reference_log_prob=reference_log_prob,
+            compute_ito_int=self.method != "kl", change_sde_ctrl=self.method in ["lv", "lv_traj"],
+            return_traj=False)
+        return self.compute_loss(rnd, samples=samples)
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, reference_log_prob=None, compute_weights=True, return_traj=True):
+        samples, rnd, xs = self.simulate(
+            ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, reference_log_prob=reference_log_prob,
+            compute_ito_int=compute_weights, change_sde_ctrl=False, return_traj=return_traj)
+        return self.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)
+
+
+class FusedExponentialIntegratorSDELoss(FusedOCLoss):
+    """ExponentialIntegratorSDELoss (losses/oc.py:395-483): DDS."""
+
+    loss_kind = "exp_integrator"
+
+    def __init__(self, *args, alpha: float, sigma: float, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha = alpha
+        self.sigma = sigma
+
+    def simulate(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, compute_ito_int=False,
+                 change_sde_ctrl=False, return_traj=False, noise=None):
+        return self._simulate(ts, x, terminal_unnorm_log_prob, reference_log_prob, train=True,
+                              compute_ito_int=compute_ito_int, return_traj=return_traj, noise=noise)
+
+    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob):
+        x = self._repeat(x)
+        samples, rnd, _ = self.simulate(
+            ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, reference_log_prob=reference_log_prob,
+            compute_ito_int=self.method != "kl", change_sde_ctrl=self.method in ["lv", "lv_traj"],
+            return_traj=False)
+        return self.compute_loss(rnd, samples=samples)
+
+    def eval(self, ts, x, terminal_unnorm_log_prob, reference_log_prob=None, compute_weights=True, return_traj=True):
+        samples, rnd, xs = self.simulate(
+            ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, reference_log_prob=reference_log_prob,
+            compute_ito_int=compute_weights, change_sde_ctrl=False, return_traj=return_traj)
+        return self.compute_results(rnd, compute_weights=compute_weights, ts=ts, samples=samples, xs=xs)

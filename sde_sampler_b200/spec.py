@@ -14,6 +14,7 @@ the kernel's descriptor raises `NotImplementedError` — there is no fallback pa
 from __future__ import annotations
 
 import math
+import weakref
 from dataclasses import dataclass, field
 from typing import Any, Callable
 
@@ -32,9 +33,31 @@ def _np(t) -> np.ndarray:
     return np.asarray(t, dtype=np.float32)
 
 
+def _t(t) -> torch.Tensor:
+    """Parameters stay torch tensors on their device (no copy, no host sync); the kernel
+    reads them through their data pointers, the oracle through `RolloutSpec.to_dict()`."""
+    if isinstance(t, torch.Tensor):
+        return t.detach()
+    return torch.as_tensor(t, dtype=torch.float32)
+
+
+# 0-dim *buffers* (SDE coefficients, DoubleWell.shift, ...) are constants of the reference
+# objects; reading one is a device->host sync, so remember (tensor identity, version) -> value.
+_SCALAR_CACHE: dict[int, tuple] = {}
+_CHECKED_MULTIWELL: "weakref.WeakSet" = weakref.WeakSet()
+
+
 def _f(v) -> float:
     if isinstance(v, torch.Tensor):
-        return float(v.detach().cpu())
+        key = id(v)
+        hit = _SCALAR_CACHE.get(key)
+        if hit is not None and hit[0]() is v and hit[1] == v._version:
+            return hit[2]
+        val = float(v.detach().cpu())
+        if len(_SCALAR_CACHE) > 4096:
+            _SCALAR_CACHE.clear()
+        _SCALAR_CACHE[key] = (weakref.ref(v), v._version, val)
+        return val
     return float(v)
 
 
@@ -60,9 +83,11 @@ def _check_gelu(act, where):
 def _time_embed_params(te) -> dict:
     """TimeEmbed (reference models/mlp.py:43-82)."""
     _check_gelu(te.activation, "TimeEmbed")
-    hidden = [(_np(l.weight), _np(l.bias)) for l in te.hidden_layer]
-    return {"phase": _np(te.timestep_phase).reshape(-1), "hidden": hidden,
-            "out_w": _np(te.out_layer.weight), "out_b": _np(te.out_layer.bias)}
+    if int(te.channels) != 64:
+        raise NotImplementedError(f"TimeEmbed with channels={te.channels} (the fused kernel is built for 64)")
+    hidden = [(_t(l.weight), _t(l.bias)) for l in te.hidden_layer]
+    return {"phase": _t(te.timestep_phase).reshape(-1), "hidden": hidden,
+            "out_w": _t(te.out_layer.weight), "out_b": _t(te.out_layer.bias)}
 
 
 def _fourier_mlp_params(net) -> dict:
@@ -70,23 +95,39 @@ def _fourier_mlp_params(net) -> dict:
     if _cls(net) != "FourierMLP":
         raise NotImplementedError(f"base_model {_cls(net)} is not supported (FourierMLP only)")
     _check_gelu(net.activation, "FourierMLP")
-    return {"in_w": _np(net.input_embed.weight), "in_b": _np(net.input_embed.bias),
-            "hidden": [(_np(l.weight), _np(l.bias)) for l in net.hidden_layer],
-            "out_w": _np(net.out_layer.weight), "out_b": _np(net.out_layer.bias),
+    if int(net.channels) != 64:
+        raise NotImplementedError(f"FourierMLP with channels={net.channels} (the fused kernel is built for 64)")
+    return {"in_w": _t(net.input_embed.weight), "in_b": _t(net.input_embed.bias),
+            "hidden": [(_t(l.weight), _t(l.bias)) for l in net.hidden_layer],
+            "out_w": _t(net.out_layer.weight), "out_b": _t(net.out_layer.bias),
             "time_embed": _time_embed_params(net.timestep_embed)}
 
 
 # ------------------------------------------------------------------------- distributions
+def _row(t, dim) -> torch.Tensor:
+    """(1,d) / (d,) / scalar parameter -> contiguous (d,) float32 view (copy only if broadcast)."""
+    t = _t(t).reshape(-1)
+    if t.numel() == 1 and dim != 1:
+        t = t.expand(dim)
+    if t.numel() != dim:
+        raise NotImplementedError(f"parameter of {t.numel()} elements for dim={dim}")
+    return t.to(torch.float32).contiguous()
+
+
+def _same_gauss(a: dict, b: dict) -> bool:
+    if a.get("owner") is b.get("owner"):
+        return True
+    return bool(torch.equal(a["loc"], b["loc"]) and torch.equal(a["scale"], b["scale"]))
+
+
 def _diag_gauss(distr, dim) -> dict:
     """Gauss / IsotropicGauss / Delta (reference distr/gauss.py:158-242, distr/delta.py)."""
     if _cls(distr) not in ("Gauss", "IsotropicGauss", "Delta"):
         raise NotImplementedError(f"{_cls(distr)} is not a supported Gaussian prior/reference")
-    loc = np.broadcast_to(_np(distr.loc).reshape(-1), (dim,)).copy()
-    scale = np.broadcast_to(_np(distr.scale).reshape(-1), (dim,)).copy()
     lnc = getattr(distr, "log_norm_const", 0.0) or 0.0
     if abs(float(lnc)) > 0:
         raise NotImplementedError("Gaussian prior/reference with log_norm_const != 0")
-    return {"loc": loc, "scale": scale}
+    return {"loc": _row(distr.loc, dim), "scale": _row(distr.scale, dim), "owner": distr}
 
 
 def _target_params(target, dim) -> dict:
@@ -94,19 +135,18 @@ def _target_params(target, dim) -> dict:
     lnc = getattr(target, "log_norm_const", None)
     if name == "GMM":
         # distr/gauss.py:66-140
-        loc, scale = _np(target.loc), _np(target.scale)
-        if target.mixture_weights is None:
-            logw = np.zeros((1,), np.float32)
-        else:
-            w = target.mixture_weights.detach().cpu().double()
-            # Categorical(probs=w) normalises; logits = log(w / sum w)
-            logw = torch.log(w / w.sum()).float().numpy()
-        return {"kind": "gmm", "loc": loc, "scale": scale, "log_weights": logw,
+        loc, scale = _t(target.loc), _t(target.scale)
+        if loc.ndim != 2 or loc.shape != scale.shape or loc.shape[1] != dim:
+            raise NotImplementedError(f"GMM loc/scale of shape {tuple(loc.shape)}/{tuple(scale.shape)}")
+        # Categorical(probs=w) normalises (distr/gauss.py:119-128); the kernel does the same
+        w = None if target.mixture_weights is None else _t(target.mixture_weights).reshape(-1)
+        return {"kind": "gmm", "loc": loc.to(torch.float32).contiguous(),
+                "scale": scale.to(torch.float32).contiguous(),
+                "weights": None if w is None else w.to(torch.float32).contiguous(),
                 "log_norm_const": float(lnc or 0.0)}
     if name in ("Gauss", "IsotropicGauss"):
-        g = {"loc": np.broadcast_to(_np(target.loc).reshape(-1), (dim,)).copy(),
-             "scale": np.broadcast_to(_np(target.scale).reshape(-1), (dim,)).copy()}
-        return {"kind": "gauss", **g, "log_norm_const": float(lnc or 0.0)}
+        return {"kind": "gauss", "loc": _row(target.loc, dim), "scale": _row(target.scale, dim),
+                "log_norm_const": float(lnc or 0.0)}
     if name == "DoubleWell":
         # distr/double_well.py:14-45 — unnorm_log_prob has no constant
         return {"kind": "multiwell", "n_dw": 1, "separation": _f(target.separation),
@@ -114,11 +154,12 @@ def _target_params(target, dim) -> dict:
     if name == "MultiWell":
         # distr/double_well.py:103-179; Gaussian part: loc=shift, scale=1, constant folded to 0
         dw = target.double_well
-        if target.gauss is not None:
-            gs = _np(target.gauss.scale).reshape(-1)
+        if target.gauss is not None and target not in _CHECKED_MULTIWELL:
+            gs = _np(target.gauss.scale).reshape(-1)  # host read: once per target object
             gl = _np(target.gauss.loc).reshape(-1)
             if not (np.allclose(gs, 1.0) and np.allclose(gl, _f(dw.shift))):
                 raise NotImplementedError("MultiWell with a non-standard Gaussian part")
+            _CHECKED_MULTIWELL.add(target)
         return {"kind": "multiwell", "n_dw": int(target.n_double_wells),
                 "separation": _f(dw.separation), "shift": _f(dw.shift)}
     if name == "Funnel":
@@ -150,7 +191,7 @@ def _sde_params(sde) -> dict | None:
 class RolloutSpec:
     """Raw, framework-free description of one rollout call (numpy arrays + scalars)."""
     dim: int
-    ts: np.ndarray
+    ts: Any
     loss: dict
     ctrl: dict
     mlp: dict
@@ -162,9 +203,27 @@ class RolloutSpec:
     extras: dict = field(default_factory=dict)
 
     def to_dict(self) -> dict:
-        return {"dim": self.dim, "ts": self.ts, "loss": dict(self.loss), "ctrl": dict(self.ctrl),
-                "mlp": self.mlp, "gate": self.gate, "sde": self.sde, "prior": self.prior,
-                "ref": self.ref, "target": dict(self.target)}
+        """Plain numpy / scalar copy (what the oracle and the golden fixtures consume)."""
+        def conv(o):
+            if isinstance(o, torch.Tensor):
+                return _np(o)
+            if isinstance(o, dict):
+                return {k: conv(v) for k, v in o.items() if k != "owner"}
+            if isinstance(o, (list, tuple)):
+                return type(o)(conv(v) for v in o)
+            return o
+
+        target = conv(self.target)
+        if target["kind"] == "gmm":
+            w = target.pop("weights")
+            if w is None:
+                target["log_weights"] = np.zeros((1,), np.float32)
+            else:
+                w = w.astype(np.float64)
+                target["log_weights"] = np.log(w / w.sum()).astype(np.float32)
+        return {"dim": self.dim, "ts": conv(self.ts), "loss": dict(self.loss), "ctrl": dict(self.ctrl),
+                "mlp": conv(self.mlp), "gate": conv(self.gate), "sde": conv(self.sde),
+                "prior": conv(self.prior), "ref": conv(self.ref), "target": target}
 
 
 def extract_spec(loss_obj, loss_kind: str, ts: torch.Tensor, terminal_unnorm_log_prob: Callable,
@@ -239,7 +298,7 @@ def extract_spec(loss_obj, loss_kind: str, ts: torch.Tensor, terminal_unnorm_log
             raise ValueError("TimeReversalLoss needs an sde")
         if not (train and loss_obj.method in ("kl", "kl_ito")):
             p = _diag_gauss(_owner(second_log_prob, "initial_log_prob"), dim)
-            if prior is not None and not (np.array_equal(p["loc"], prior["loc"]) and np.array_equal(p["scale"], prior["scale"])):
+            if prior is not None and not _same_gauss(p, prior):
                 raise NotImplementedError("initial_log_prob and prior_score refer to different priors")
             prior = p
     else:
@@ -255,17 +314,17 @@ def extract_spec(loss_obj, loss_kind: str, ts: torch.Tensor, terminal_unnorm_log
                 if not hasattr(rc_owner, "prior"):
                     raise NotImplementedError("reference_ctrl must be EulerDDS-style (owner with .prior)")
                 p = _diag_gauss(rc_owner.prior, dim)
-                if prior is not None and not np.array_equal(p["loc"], prior["loc"]):
+                if prior is not None and not _same_gauss(p, prior):
                     raise NotImplementedError("reference_ctrl prior differs from control prior")
                 prior = p
         else:
             ld["alpha"] = float(loss_obj.alpha)
             ld["sigma"] = float(loss_obj.sigma)
 
-    ts_np = _np(ts).reshape(-1)
-    if ts_np.shape[0] < 2:
+    ts_t = _t(ts).reshape(-1).to(torch.float32)
+    if ts_t.shape[0] < 2:
         raise ValueError("need at least one time step")
-    return RolloutSpec(dim=dim, ts=ts_np, loss=ld, ctrl=cd, mlp=mlp, gate=gate, sde=sde,
+    return RolloutSpec(dim=dim, ts=ts_t, loss=ld, ctrl=cd, mlp=mlp, gate=gate, sde=sde,
                        prior=prior, ref=ref, target=target)
 
 

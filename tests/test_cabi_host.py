@@ -1,0 +1,135 @@
+"""Host-side checks that need no GPU: the C-ABI library loads, exports every symbol the header
+declares, agrees with the ctypes mirror of the descriptor, validates descriptors, and the
+plug-in introspection reproduces the golden specs."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from sde_sampler_b200 import _cabi, build as sdes_build
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+HEADER = os.path.join(ROOT, "include", "sdes_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sdes_build.build()
+    return _cabi.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(sdes_[a-z_0-9]+)\s*\(", text))
+    assert declared, "no declarations parsed"
+    assert declared == set(_cabi.SYMBOLS), (declared ^ set(_cabi.SYMBOLS))
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_desc_layout_matches_c(tmp_path, lib):
+    """sizeof / offsetof of the C struct, compiled with gcc from the header, equal the ctypes mirror."""
+    src = tmp_path / "probe.c"
+    fields = [f[0] for f in _cabi.RolloutDesc._fields_]
+    body = "\n".join(f'printf("{f} %zu\\n", offsetof(SdesRolloutDesc, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sdes_b200.h"\nint main(){'
+                   'printf("sizeof %zu\\n", sizeof(SdesRolloutDesc));' + body + "return 0;}")
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+    assert int(out["sizeof"]) == C.sizeof(_cabi.RolloutDesc)
+    for f in fields:
+        assert int(out[f]) == getattr(_cabi.RolloutDesc, f).offset, f
+    assert lib.sdes_version() == _cabi.ABI_VERSION
+
+
+def _valid_desc():
+    d = _cabi.new_desc()
+    d.loss_kind, d.ctrl_kind, d.sde_kind, d.target_kind = 0, 2, 1, 0
+    d.dim, d.n_steps, d.n_hidden, d.te_hidden, d.gate_hidden, d.gate_dim = 50, 100, 2, 1, 3, 1
+    d.n_components, d.batch = 40, 1024
+    d.flags = _cabi.F_HAS_GATE | _cabi.F_MLP_SIMT
+    c, dim = 64, 50
+    d.n_params = (c * dim + c) + (c + c * 2 * c + c + c * c + c) + 2 * (c * c + c) + (dim * c + dim) \
+        + (c + c * 2 * c + c + 2 * (c * c + c) + c + 1)
+    return d
+
+
+def test_descriptor_validation_without_gpu(lib):
+    d = _valid_desc()
+    assert lib.sdes_workspace_bytes(C.byref(d)) > 0, lib.sdes_last_error()
+    bad = _valid_desc()
+    bad.dim = 65
+    assert lib.sdes_workspace_bytes(C.byref(bad)) == 0
+    assert b"dim" in lib.sdes_last_error()
+    bad = _valid_desc()
+    bad.n_params += 1
+    assert lib.sdes_workspace_bytes(C.byref(bad)) == 0
+    assert b"n_params" in lib.sdes_last_error()
+    bad = _valid_desc()
+    bad.struct_bytes -= 8
+    assert lib.sdes_workspace_bytes(C.byref(bad)) == 0
+    # pointers are validated before anything is launched: no GPU is touched here
+    rc = lib.sdes_rollout_fwd(C.byref(d), None)
+    assert rc == -5 and b"NULL" in lib.sdes_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libsdes_b200.so")
+    with pytest.raises(_cabi.SdesError, match="no CPU or PyTorch fallback"):
+        _cabi.lib()
+
+
+def test_cpu_tensor_is_rejected(lib, golden):
+    """The product has no CPU path: a rollout on a CPU tensor raises instead of computing."""
+    from sdes_test_helpers import build_from_spec
+
+    g = golden("dis_dw1_lv")
+    b = build_from_spec(g["spec"], "cpu")
+    with pytest.raises(_cabi.SdesError, match="CUDA device only"):
+        b["loss"](b["ts"], torch.as_tensor(g["x0"]), b["terminal"], b["second"])
+
+
+@pytest.mark.parametrize("name", ["dis_gmm50_lv", "pis_funnel10_kl", "dds_funnel10_lv", "eulerdds_gmm2_lv",
+                                  "dis_lerptarget_gmmrand3_dimgate", "dis_lerpprior_multiwell4",
+                                  "dis_noscore_constou_gauss5", "dis_dw1_lv"])
+def test_introspection_roundtrip(lib, golden, name):
+    """mirror objects built from a golden spec -> extract_spec -> the same spec (the golden spec was
+    extracted from the reference's own objects by the same code, oracle/gen_golden.py)."""
+    from sde_sampler_b200.spec import extract_spec
+    from sdes_test_helpers import build_from_spec
+
+    g = golden(name)
+    spec = g["spec"]
+    b = build_from_spec(spec, "cpu")
+    ls = spec["loss"]
+    got = extract_spec(b["loss"], ls["kind"], b["ts"], b["terminal"], b["second"], train=ls["train"],
+                       compute_ito=ls["compute_ito"]).to_dict()
+
+    def cmp(a, c, path=""):
+        if isinstance(a, dict):
+            assert set(a) == set(c), (path, set(a) ^ set(c))
+            for k in a:
+                cmp(a[k], c[k], f"{path}/{k}")
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(c), path
+            for i, (u, v) in enumerate(zip(a, c)):
+                cmp(u, v, f"{path}/{i}")
+        elif isinstance(a, np.ndarray) or isinstance(c, np.ndarray):
+            np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(c, np.float64), rtol=1e-6, atol=1e-7, err_msg=path)
+        elif isinstance(a, float) or isinstance(c, float):
+            if a is None or c is None:
+                assert a == c, path
+            else:
+                assert a == pytest.approx(c, rel=1e-6), path
+        else:
+            assert a == c, (path, a, c)
+
+    cmp(spec, got)

@@ -1,0 +1,216 @@
+"""-m gpu: the CUDA path, called through the plug-in interface / C ABI, against
+  (1) the golden vectors frozen from the unmodified reference (tests/golden, oracle/gen_golden.py),
+  (2) the numpy oracle on larger / ragged batches,
+  (3) size-independent properties at BASELINE.json's full batch size.
+
+Tolerance (fp32 path, stated per the north star): |delta| <= ATOL + RTOL*|ref| elementwise with
+RTOL = ATOL = 2e-4 for terminal samples and per-trajectory rnd against the reference's fp32
+PyTorch rollout on identical x0 and noise — the same bound the numpy oracle meets against the
+reference (tests/test_oracle_golden.py; SURVEY §7 measured 7e-5 / 1.2e-4 between two fp32
+implementations); loss and log-Z estimates within 1e-3 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, rollout as oracle_rollout
+from oracle.cases import CASES, EVAL_CASES, NOISE_SEED
+from sdes_test_helpers import assert_close, build_from_spec
+
+pytestmark = pytest.mark.gpu
+
+RTOL = ATOL = 2e-4
+ENGINES = ["simt"]
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _call_kwargs(b):
+    return {"terminal_unnorm_log_prob": b["terminal"], b["second_name"]: b["second"]}
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", list(CASES))
+def test_train_rollout_matches_reference_golden(golden, name, engine):
+    g = golden(name)
+    spec, x0 = g["spec"], g["x0"]
+    T, (B, d) = g["ts"].shape[0] - 1, x0.shape
+    noise = torch.from_numpy(philox.normal_noise(NOISE_SEED, B, T, d)).to(_dev())
+    b = build_from_spec(spec, _dev(), engine=engine)
+    loss = b["loss"]
+    method = spec["loss"]["method"]
+    x_T, rnd, xs = loss.simulate(b["ts"], torch.from_numpy(x0).to(_dev()), compute_ito_int=method != "kl",
+                                 change_sde_ctrl=method in ("lv", "lv_traj"), return_traj=False, noise=noise,
+                                 **_call_kwargs(b))
+    assert xs is None and rnd.shape == (B, 1)
+    assert_close(x_T.cpu().numpy(), g["train"]["x_T"], RTOL, ATOL, "x_T")
+    assert_close(rnd.cpu().numpy(), g["train"]["rnd"], RTOL, ATOL, "rnd")
+    val, metrics = loss.compute_loss(rnd, samples=x_T)
+    ref = g["train"]["loss"]
+    assert abs(float(val) - ref) <= 1e-3 * (1 + abs(ref)), (float(val), ref)
+    assert metrics["train/n_filtered_cumulative"] == g["train"]["n_filtered"]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", list(EVAL_CASES))
+def test_eval_matches_reference_golden(golden, name, engine):
+    g = golden(name)
+    spec, x0 = g["spec"], g["x0"]
+    T, (B, d) = g["ts"].shape[0] - 1, x0.shape
+    noise = torch.from_numpy(philox.normal_noise(NOISE_SEED, B, T, d)).to(_dev())
+    for j, (cw, rt) in enumerate(EVAL_CASES[name]):
+        e = g[f"eval{j}"]
+        b = build_from_spec(spec, _dev(), engine=engine)
+        loss = b["loss"]
+        # eval() draws its own noise; inject the fixture's through simulate and reduce with compute_results
+        kw = dict(train=False) if spec["loss"]["kind"] == "time_reversal" else dict(change_sde_ctrl=False)
+        x_T, rnd, xs = loss.simulate(b["ts"], torch.from_numpy(x0).to(_dev()), compute_ito_int=cw, return_traj=rt,
+                                     noise=noise, **kw, **_call_kwargs(b))
+        res = loss.compute_results(rnd, compute_weights=cw, ts=b["ts"], samples=x_T, xs=xs)
+        assert_close(res.samples.cpu().numpy(), e["x_T"], RTOL, ATOL, "x_T")
+        assert_close(rnd.cpu().numpy(), e["rnd"], RTOL, ATOL, "rnd")
+        if rt:
+            assert res.xs.shape == (T + 1, B, d)
+            assert_close(res.xs.cpu().numpy(), e["xs"], RTOL, ATOL, "xs")
+        else:
+            assert res.xs is None
+        for k, v in e["log_norm_const_preds"].items():
+            assert abs(res.log_norm_const_preds[k] - v) <= 1e-3 * (1 + abs(v)), (k, res.log_norm_const_preds[k], v)
+        if cw:
+            ref = e["metrics"]["eval/lv_loss"]
+            assert abs(res.metrics["eval/lv_loss"] - ref) <= 1e-3 * (1 + abs(ref))
+            assert_close(res.weights.cpu().numpy(), e["weights"], 2e-3, 1e-6, "weights")
+        else:
+            assert res.weights is None
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_public_eval_and_call_run(golden, engine):
+    """loss(...) and loss.eval(...) exactly as the solver calls them (solver/oc.py:155-179): in-kernel noise."""
+    g = golden("dis_gmm2_lv")
+    b = build_from_spec(g["spec"], _dev(), engine=engine, seed=7)
+    x0 = torch.from_numpy(g["x0"]).to(_dev())
+    val, metrics = b["loss"](b["ts"], x0, b["terminal"], b["second"])
+    assert val.ndim == 0 and torch.isfinite(val) and "train/n_filtered_cumulative" in metrics
+    res = b["loss"].eval(b["ts"], x0, b["terminal"], b["second"])
+    assert res.xs.shape == (len(b["ts"]), *res.samples.shape)  # the caller's assert, solver/oc.py:85
+    assert set(res.log_norm_const_preds) == {"log_norm_const_lb_ito", "log_norm_const_is"}
+    res2 = b["loss"].eval(b["ts"], x0, b["terminal"], b["second"], compute_weights=False, return_traj=False)
+    assert res2.xs is None and res2.weights is None and set(res2.log_norm_const_preds) == {"log_norm_const_lb"}
+    assert b["loss"].state_dict() == {"n_filtered": b["loss"].n_filtered}
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name,B", [("dis_gmm50_lv", 1000), ("pis_funnel10_kl", 777), ("dds_funnel10_lv", 515),
+                                    ("dis_dw1_lv", 33), ("dis_gmm2_lv", 1)])
+def test_ragged_batches_match_oracle(golden, name, B, engine):
+    """Batches that are not multiples of the 32-row tile, down to a single trajectory."""
+    g = golden(name)
+    spec = g["spec"]
+    d, T = spec["dim"], g["ts"].shape[0] - 1
+    rng = np.random.default_rng(B)
+    x0 = rng.standard_normal((B, d)).astype(np.float32) if spec["loss"]["kind"] != "reference_sde" or spec["loss"].get("reference_ctrl") \
+        else np.zeros((B, d), np.float32)
+    noise = philox.normal_noise(NOISE_SEED + 1, B, T, d)
+    want_x, want_r, _ = oracle_rollout.rollout(spec, x0, noise=noise)
+    b = build_from_spec(spec, _dev(), engine=engine)
+    method = spec["loss"]["method"]
+    x_T, rnd, _ = b["loss"].simulate(b["ts"], torch.from_numpy(x0).to(_dev()), compute_ito_int=method != "kl",
+                                     noise=torch.from_numpy(noise).to(_dev()), **_call_kwargs(b))
+    assert_close(x_T.cpu().numpy(), want_x, RTOL, ATOL, "x_T")
+    assert_close(rnd.cpu().numpy(), want_r, RTOL, ATOL, "rnd")
+
+
+def test_noise_stream_matches_oracle_philox():
+    """Integer Philox stream is bit-exact by construction; Box-Muller through MUFU agrees to ~1e-6."""
+    from sde_sampler_b200 import engine
+
+    for (B, T, d, off) in [(70, 5, 50, 0), (33, 3, 2, 123456), (8, 4, 1, 2**31)]:
+        got = engine.philox_normal(NOISE_SEED, off, B, T, d, _dev()).cpu().numpy()
+        want = philox.normal_noise(NOISE_SEED, B, T, d, traj_offset=off)
+        assert np.abs(got - want).max() < 5e-6, np.abs(got - want).max()
+    big = engine.philox_normal(12345, 0, 4096, 16, 50, _dev()).double()
+    assert abs(big.mean().item()) < 3e-3 and abs(big.var().item() - 1) < 5e-3
+    assert abs((big ** 4).mean().item() - 3) < 0.05
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["dis_gmm50_lv", "dds_funnel10_lv"])
+def test_fused_noise_equals_staged_noise(golden, name, engine):
+    """Drawing eps in registers == reading the same stream back from HBM, bit for bit."""
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.spec import extract_spec
+
+    g = golden(name)
+    b = build_from_spec(g["spec"], _dev(), engine=engine)
+    ls = g["spec"]["loss"]
+    B, d, T = 200, g["spec"]["dim"], g["ts"].shape[0] - 1
+    x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(3))
+    spec = extract_spec(b["loss"], ls["kind"], b["ts"], b["terminal"], b["second"], train=True, compute_ito=True)
+    seed, off = 0xABCDEF0123, 1000
+    xa, ra, _ = eng.rollout(spec, x0, seed=seed, traj_offset=off, engine=engine)
+    noise = eng.philox_normal(seed, off, B, T, d, _dev())
+    xb, rb, _ = eng.rollout(spec, x0, noise=noise, engine=engine)
+    assert torch.equal(xa, xb) and torch.equal(ra, rb)
+    # and the result does not depend on how the batch is cut into shards
+    h = 96
+    x1, r1, _ = eng.rollout(spec, x0[:h], seed=seed, traj_offset=off, engine=engine)
+    x2, r2, _ = eng.rollout(spec, x0[h:], seed=seed, traj_offset=off + h, engine=engine)
+    assert torch.equal(torch.cat([x1, x2]), xa) and torch.equal(torch.cat([r1, r2]), ra)
+
+
+def test_rnd_stats_kernel_matches_numpy():
+    from sde_sampler_b200 import _cabi, engine
+
+    rng = np.random.default_rng(5)
+    r = (rng.standard_normal(100_003) * 4 + 130).astype(np.float32)
+    r[7] = np.inf
+    r[99] = np.nan
+    r[1234] = 3e8
+    t = torch.from_numpy(r).to(_dev())
+    for mode, mx in [(_cabi.MASK_ISFINITE, 0.0), (_cabi.MASK_MAX_RND, 1e8)]:
+        st = engine.rnd_stats(t, mode, mx).cpu().numpy()
+        keep = np.isfinite(r) if mode == _cabi.MASK_ISFINITE else (r < mx)
+        k = r[keep].astype(np.float64)
+        assert st[0] == k.size and st[5] == r.size
+        assert st[1] == pytest.approx(k.sum(), rel=1e-12) and st[2] == pytest.approx((k * k).sum(), rel=1e-12)
+        assert st[3] == pytest.approx((-k).max())
+        assert st[4] == pytest.approx(np.exp(-k - (-k).max()).sum(), rel=1e-5)
+    mask = torch.from_numpy((np.arange(r.size) % 3 != 0)).to(_dev())
+    st = engine.rnd_stats(t, _cabi.MASK_ISFINITE, 0.0, mask).cpu().numpy()
+    assert st[0] == (np.isfinite(r) & (np.arange(r.size) % 3 != 0)).sum()
+    st = engine.rnd_stats(t, _cabi.MASK_ALL).cpu().numpy()
+    assert np.isnan(st[1]) and np.isnan(st[3])  # NaN propagates like rnd.mean() / (-rnd).max() in the reference
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_full_size_properties_headline_config(golden, engine):
+    """BASELINE north-star size (GMM-40 d=50, B=65 536, T=100, DIS+lv): too big for the CPU oracle, so
+    check (a) a strided sample of rows against the oracle given the same Philox stream, (b) determinism,
+    (c) the cross-shard statistics identity."""
+    from sde_sampler_b200 import _cabi, engine as eng
+    from sde_sampler_b200.dist import merge_stats
+    from sde_sampler_b200.spec import extract_spec
+
+    g = golden("dis_gmm50_lv")
+    spec_d = g["spec"]
+    b = build_from_spec(spec_d, _dev(), engine=engine)
+    B, d, T = 65536, 50, 100
+    x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(11))
+    spec = extract_spec(b["loss"], "time_reversal", b["ts"], b["terminal"], b["second"], train=True, compute_ito=True)
+    seed = 2024
+    x_T, rnd, _ = eng.rollout(spec, x0, seed=seed, engine=engine)
+    x_T2, rnd2, _ = eng.rollout(spec, x0, seed=seed, engine=engine)
+    assert torch.equal(x_T, x_T2) and torch.equal(rnd, rnd2)
+    assert torch.isfinite(rnd).all() and torch.isfinite(x_T).all()
+    rows = np.arange(0, B, 1031)[:64]
+    noise = np.stack([philox.normal_block(seed, rows, i, d) for i in range(T)])
+    want_x, want_r, _ = oracle_rollout.rollout(spec_d, x0[rows].cpu().numpy(), noise=noise)
+    # noise itself differs by ~1e-6 (MUFU Box-Muller vs float64), hence the slightly wider bound
+    assert_close(x_T[rows].cpu().numpy(), want_x, 5e-4, 5e-4, "x_T sample")
+    assert_close(rnd[rows].cpu().numpy(), want_r, 5e-4, 5e-4, "rnd sample")
+    whole = eng.rnd_stats(rnd, _cabi.MASK_MAX_RND, 1e8)
+    halves = torch.stack([eng.rnd_stats(rnd[: B // 2], _cabi.MASK_MAX_RND, 1e8), eng.rnd_stats(rnd[B // 2:], _cabi.MASK_MAX_RND, 1e8)])
+    np.testing.assert_allclose(merge_stats(halves).cpu().numpy()[:6], whole.cpu().numpy()[:6], rtol=1e-9)
