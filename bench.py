@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — trajectory-steps/sec of the fused rollout on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--engine auto|tcgen05|simt]
+
+Workload (north-star headline): GMM-40 d=50, DIS + log-variance loss, T=100, 65 536 trajectories
+per GPU (weak scaling: every rank carries its own shard of the global batch; the only exchange is
+the 8-double statistics all-gather inside the loss).  One "step" = one training-mode call of the
+loss plug-in, `loss(ts, x0, clipped_target_unnorm_log_prob, prior.log_prob)`: prologue kernel +
+persistent rollout kernel over all T time steps + statistics kernel.
+
+`value`   : N*B*T / time with x0 resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`     : same call, but x0 starts in pinned host memory and the loss scalar is read back each step.
+`roofline`: MLP FLOPs (F(d) = 256 d + 16 384 per trajectory-step) of one rollout launch
+            over its CUDA-event duration, against the measured dense bf16 peak.
+`cpu_baseline` / `--impl reference`: oracle/torch_port.py — the reference's per-step op sequence in
+            torch eager on the host cores — on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+DIM, T_STEPS, BATCH_PER_GPU, N_MODES = 50, 100, 65536, 40
+METRIC = "trajectory-steps/sec"
+UNIT = "traj-steps/s"
+
+
+def flops_per_traj_step(d: int) -> int:
+    return 256 * d + 16384  # x-dependent FourierMLP layers only, C=64, 4 layers
+
+
+def workload_name(batch: int) -> str:
+    return f"GMM-40 d={DIM} solver=dis loss=lv T={T_STEPS} batch={batch}/GPU"
+
+
+# ----------------------------------------------------------------------------- the objects
+def build_objects(device, engine: str, process_group=None, seed: int = 1):
+    """conf/solver/dis.yaml with target GMM-40 d=50 (explicit loc), random-init
+    weights of the reference architecture, out layers re-randomised (the default zero init makes
+    NN == 0 and the MLP trivial)."""
+    import torch
+    from torch import nn
+    from functools import partial
+
+    from sde_sampler_b200 import FusedTimeReversalLoss, plugins
+
+    torch.manual_seed(seed)
+    loc, scale, w = plugins.fab_gmm_params(DIM)
+    target = plugins.GMM(dim=DIM, loc=loc, scale=scale, mixture_weights=w)
+    prior = plugins.IsotropicGauss(dim=DIM, truncate_quartile=1e-4)  # conf/prior/gauss_truncate.yaml
+    sde = plugins.VP(diff_coeff_sq_min=0.1, diff_coeff_sq_max=10.0, terminal_t=1.0)  # conf/sde/vp_10.yaml
+    base = plugins.FourierMLP(dim=DIM, num_layers=4, channels=64)
+    gate = plugins.TimeEmbed(dim_out=1, num_layers=4, channels=64, last_bias_init=partial(nn.init.constant_, val=1.0))
+    with torch.no_grad():
+        base.out_layer.weight.normal_(0.0, 0.15)
+        base.out_layer.bias.normal_(0.0, 0.1)
+        gate.out_layer.weight.normal_(0.0, 0.05)
+    ctrl = plugins.LerpCtrl(base_model=base, clip_model=10.0, target_score=target.score, score_model=gate,
+                            detach_score=False, scale_score=1.0, clip_score=10.0, sde=sde, prior_score=prior.score)
+    for m in (target, prior, sde, base, gate):
+        m.to(device)
+    loss = FusedTimeReversalLoss(generative_ctrl=ctrl, sde=sde, method="lv", max_rnd=1e8, engine=engine,
+                                 process_group=process_group, seed=1234)
+
+    class Solver:  # owner of clipped_target_unnorm_log_prob (solver/oc.py:48-54)
+        def __init__(self):
+            self.target, self.clip_target = target, None
+
+        def clipped_target_unnorm_log_prob(self, x):
+            raise RuntimeError("introspected, never called")
+
+    ts = plugins.get_timesteps(0.0, 1.0, steps=T_STEPS).to(device)
+    return dict(loss=loss, ts=ts, terminal=Solver().clipped_target_unnorm_log_prob, second=prior.log_prob,
+                prior=prior, target=target, sde=sde, ctrl=ctrl)
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_port_setup():
+    """Spec dict of the same workload for oracle/torch_port.py (CPU tensors)."""
+    import torch
+
+    from sde_sampler_b200.spec import extract_spec
+
+    o = build_objects_cpu()
+    spec = extract_spec(o["loss"], "time_reversal", o["ts"], o["terminal"], o["second"], train=True, compute_ito=True)
+    return spec.to_dict(), o
+
+
+def build_objects_cpu():
+    import torch
+
+    from sde_sampler_b200 import _cabi
+
+    # the mirrors hold parameters only; building them on the CPU touches no kernel
+    return build_objects(torch.device("cpu"), "simt")
+
+
+def time_cpu_port(batch: int, repeats: int = 1):
+    import torch
+
+    from oracle import torch_port
+
+    spec, o = cpu_port_setup()
+    torch.manual_seed(0)
+    x0 = o["prior"].sample((batch,))
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        torch_port.rollout(spec, x0.numpy(), generator=gen)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def reference_arm(args):
+    """--impl reference: the CPU port on all host threads, bounded sample per step."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe_b = 256
+    probe = min(time_cpu_port(probe_b, repeats=2))
+    speed = probe_b * T_STEPS / probe
+    budget_s = 150.0
+    total_steps = args.steps + args.warmup
+    sample = int(speed * budget_s / total_steps / T_STEPS)
+    sample = max(64, min(BATCH_PER_GPU, sample // 64 * 64))
+    times = time_cpu_port(sample, repeats=total_steps)[args.warmup:]
+    dt = sum(times) / len(times)
+    value = sample * T_STEPS / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(BATCH_PER_GPU), "sample": f"{sample} of {BATCH_PER_GPU} trajectories x T={T_STEPS} per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"oracle/torch_port.py (reference op sequence, torch eager fp32, no_grad) on {sample} trajectories x T={T_STEPS}, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "tcgen05", "simt"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="trajectories per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from sde_sampler_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    if args.gpus != world:
+        if rank == 0:
+            print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    lib = _cabi.lib()
+    B = args.batch
+    o = build_objects(device, args.engine, process_group=pg)
+    loss, ts = o["loss"], o["ts"]
+    torch.manual_seed(100 + rank)
+    x0 = o["prior"].sample((B,))
+    x0_host = x0.cpu().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def step(x):
+        return loss(ts, x, o["terminal"], o["second"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # which engine did the descriptor resolve to?
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.spec import extract_spec
+    spec = extract_spec(loss, "time_reversal", ts, o["terminal"], o["second"], train=True, compute_ito=True)
+    desc, _ = eng.fill_desc(spec, batch=B, engine=args.engine)
+    engine_used = "simt" if desc.flags & _cabi.F_MLP_SIMT else "tcgen05"
+
+    for _ in range(args.warmup):
+        val, _m = step(x0)
+        flush.zero_()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.sdes_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        val, _m = step(x0)
+        ev[k][1].record()
+        flush.zero_()  # L2 flush between timed iterations (inside the region; ~0.1 ms)
+    t_end.record()
+    barrier()
+    launches = lib.sdes_launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    loss_value = float(val)
+
+    # ---- rollout kernel alone (prologue + persistent kernel; CUDA events around the C-ABI call)
+    k_ms = []
+    for _ in range(min(args.steps, 5)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        a.record()
+        eng.rollout(spec, x0, seed=99, engine=args.engine, workspace=loss._workspace)
+        b.record()
+        torch.cuda.synchronize(device)
+        k_ms.append(a.elapsed_time(b))
+    kernel_ms = statistics.median(k_ms)
+
+    # ---- timed region 2: end to end through the plug-in with host buffers
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    host_loss = 0.0
+    for k in range(args.steps):
+        xd = x0_host.to(device, non_blocking=True)
+        v, _m = step(xd)
+        host_loss = v.item()  # device -> host read of the step's result
+    e_end.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_end)
+
+    times = torch.tensor([total_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kernel_ms = times.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks else "1590 TFLOP/s, of fallback"
+        traj_steps = B * T_STEPS
+        value = world * traj_steps * args.steps / (total_ms * 1e-3)
+        e2e_value = world * traj_steps * args.steps / (e2e_ms * 1e-3)
+        achieved_tf = traj_steps * flops_per_traj_step(DIM) / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if engine_used == "simt" else "tf32x3 (fp32-equivalent split) MMA, f32 elsewhere",
+            "data": "synthetic",
+            "config": {"workload": workload_name(B), "engine": engine_used, "global_batch": world * B,
+                       "l2": "flushed between timed steps (256 MiB memset inside the region)",
+                       "noise": "in-kernel Philox4x32-10", "loss_value": loss_value},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps, "loss_value": host_loss},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel_ms": kernel_ms,
+                         "flops_per_traj_step": flops_per_traj_step(DIM), "peak_source": peak_src,
+                         "traj_steps_per_s_kernel": traj_steps / (kernel_ms * 1e-3),
+                         "hbm_algorithmic_bytes": B * (8 * DIM + 4),
+                         "hbm_gbs": B * (8 * DIM + 4) / (kernel_ms * 1e-3) / 1e9},
+            "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            probe = min(time_cpu_port(256, repeats=2))
+            sample = int(256 * T_STEPS / probe * 15.0 / T_STEPS)
+            sample = max(64, min(B, sample // 64 * 64))
+            dt = min(time_cpu_port(sample, repeats=1))
+            line["cpu_baseline"] = {"value": sample * T_STEPS / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": f"oracle/torch_port.py (reference op sequence, torch eager fp32) on {sample} of {B} trajectories x T={T_STEPS}, one pass, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

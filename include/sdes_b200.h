@@ -121,6 +121,11 @@ size_t sdes_workspace_bytes(const SdesRolloutDesc* desc);
  * tables and (2) ONE persistent kernel that carries each trajectory through all T steps. */
 int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream);
 
+/* 1 if the tcgen05 (tensor-core) engine handles this descriptor, 0 if only the fp32-FFMA engine
+ * (SDES_F_MLP_SIMT) does.  sdes_rollout_fwd never switches engines by itself: asking for the
+ * tensor-core engine on an unsupported descriptor is an error. */
+int sdes_tcgen05_supported(const SdesRolloutDesc* desc);
+
 /* Statistics of rnd that BaseOCLoss.filter/compute_loss/compute_results reduce to
  * (losses/oc.py:50-123).  out_stats (device, 8 doubles):
  *   [0] n_kept  [1] sum(rnd | kept)  [2] sum(rnd^2 | kept)  [3] max(-rnd | kept)

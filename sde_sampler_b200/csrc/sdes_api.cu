@@ -247,6 +247,16 @@ size_t sdes_workspace_bytes(const SdesRolloutDesc* desc) {
     return (size_t)w.total * sizeof(float);
 }
 
+int sdes_tcgen05_supported(const SdesRolloutDesc* desc) {
+    if (validate(desc, false) != 0) return 0;
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = *desc;
+    blob_layout(p.d, p.bl);
+    ws_layout(p.d, p.ws);
+    return mma_supported(p) ? 1 : 0;
+}
+
 int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     g_err[0] = 0;
     int rc = validate(desc, true);

@@ -45,6 +45,17 @@ def pack_params(spec: RolloutSpec) -> torch.Tensor:
     return torch.cat([p.reshape(-1).to(torch.float32) for p in parts])
 
 
+def pack_params_numel(spec: RolloutSpec) -> int:
+    m = spec.mlp
+    te = m["time_embed"]
+    ts = [m["in_w"], m["in_b"], te["phase"], te["out_w"], te["out_b"], m["out_w"], m["out_b"]]
+    ts += [t for pair in te["hidden"] for t in pair] + [t for pair in m["hidden"] for t in pair]
+    if spec.gate is not None:
+        g = spec.gate
+        ts += [g["phase"], g["out_w"], g["out_b"]] + [t for pair in g["hidden"] for t in pair]
+    return sum(int(t.numel()) for t in ts)
+
+
 class Workspace:
     """Grow-only device scratch, one per loss object and device (allocations are cached across calls;
     nothing else is)."""
@@ -83,6 +94,7 @@ def fill_desc(spec: RolloutSpec, *, batch: int, engine: str = "auto") -> tuple[_
         flags |= _cabi.F_HAS_GATE
     if engine == "simt":
         flags |= _cabi.F_MLP_SIMT
+    want_auto = engine == "auto"
     d.dim = spec.dim
     d.n_steps = int(spec.ts.shape[0]) - 1
     d.n_hidden = len(spec.mlp["hidden"])
@@ -135,6 +147,12 @@ def fill_desc(spec: RolloutSpec, *, batch: int, engine: str = "auto") -> tuple[_
         d.ref_loc, d.ref_scale = _ptr(spec.ref["loc"]), _ptr(spec.ref["scale"])
         keep += [spec.ref["loc"], spec.ref["scale"]]
     d.flags = flags
+    if want_auto:
+        # same hardware, two kernels: the tensor-core engine where its tile shapes apply, else the
+        # fp32-FFMA engine.  Decided here, visibly, from the descriptor — never inside the library.
+        d.n_params = pack_params_numel(spec)
+        if not _cabi.lib().sdes_tcgen05_supported(C.byref(d)):
+            d.flags |= _cabi.F_MLP_SIMT
     return d, keep
 
 

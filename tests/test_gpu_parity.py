@@ -213,4 +213,4 @@ def test_full_size_properties_headline_config(golden, engine):
     assert_close(rnd[rows].cpu().numpy(), want_r, 5e-4, 5e-4, "rnd sample")
     whole = eng.rnd_stats(rnd, _cabi.MASK_MAX_RND, 1e8)
     halves = torch.stack([eng.rnd_stats(rnd[: B // 2], _cabi.MASK_MAX_RND, 1e8), eng.rnd_stats(rnd[B // 2:], _cabi.MASK_MAX_RND, 1e8)])
-    np.testing.assert_allclose(merge_stats(halves).cpu().numpy()[:6], whole.cpu().numpy()[:6], rtol=1e-9)
+    np.testing.assert_allclose(merge_stats(halves).cpu().numpy()[:6], whole.cpu().numpy()[:6], rtol=1e-6)  # exp-sum uses fp32 expf

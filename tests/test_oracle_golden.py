@@ -68,3 +68,17 @@ def test_oracle_fp64_close_to_fp32(golden):
     x64, r64, _ = rollout.rollout(g["spec"], x0, noise=noise, dtype=np.float64)
     _close(x32, x64)
     _close(r32, r64)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_torch_port_matches_reference_train(golden, name):
+    """oracle/torch_port.py (the CPU baseline bench.py times) is pinned to the same golden vectors."""
+    from oracle import torch_port
+
+    g = golden(name)
+    spec, x0 = g["spec"], g["x0"]
+    T, (B, d) = g["ts"].shape[0] - 1, x0.shape
+    noise = philox.normal_noise(NOISE_SEED, B, T, d)
+    x_T, rnd, _ = torch_port.rollout(spec, x0, noise=noise)
+    _close(x_T, g["train"]["x_T"])
+    _close(rnd, g["train"]["rnd"])
