@@ -14,6 +14,7 @@ cudaError_t launch_rollout_simt(const KParams& p, int sm_count, cudaStream_t str
 cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream);
 bool mma_supported(const KParams& p);
 int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad);
+cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -61,7 +62,7 @@ static bool blob_layout(const SdesRolloutDesc& d, BlobLayout& bl) {
 }
 
 static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
-    const int dpad = pad_dim(d.dim);
+    const int dpad = (d.flags & SDES_F_MLP_SIMT) ? pad_dim(d.dim) : mma_pad_dim(d.dim);
     const int64_t T = d.n_steps, K = d.target_kind == SDES_TARGET_GMM ? d.n_components : 0;
     int64_t o = 0;
     auto take = [&](int64_t n) { int64_t r = o; o = align_up(o + n, 64); return r; };
@@ -74,9 +75,10 @@ static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
     w.gmm_c = take(64);
     w.prior = take(2 * dpad + 4);
     w.ref = take(2 * dpad + 4);
-    w.w_simt_len = (int64_t)d.dim * C + C + (int64_t)d.n_hidden * (C * C + C) + (int64_t)C * dpad + dpad;
+    const bool simt = (d.flags & SDES_F_MLP_SIMT) != 0;
+    w.w_simt_len = simt ? (int64_t)d.dim * C + C + (int64_t)d.n_hidden * (C * C + C) + (int64_t)C * dpad + dpad : 0;
     w.w_simt = take(w.w_simt_len);
-    w.w_mma_len = mma_weight_image_floats(d, dpad);
+    w.w_mma_len = simt ? 0 : mma_weight_image_floats(d, dpad);
     w.w_mma = take(w.w_mma_len);
     w.counter = take(4);
     w.total = o;
@@ -307,6 +309,16 @@ int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* we
     weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, stats, weights);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, void* stream_) {
+    g_err[0] = 0;
+    if (!a || !w || !d) return fail(-5, "a/w/d NULL");
+    if (k < 8 || k > 64 || k % 8 || n < 16 || n > 64 || n % 16) return fail(-3, "k must be a multiple of 8 in [8,64], n a multiple of 16 in [16,64]");
+    cudaError_t e = launch_mma_selftest(a, w, d, k, n, reinterpret_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(-7, "selftest launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

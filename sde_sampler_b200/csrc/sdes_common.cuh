@@ -62,6 +62,9 @@ __host__ __device__ inline int pad_dim(int d) {
     return 64;
 }
 
+// padded state dimension of the tcgen05 engine: K of the input layer (multiple of 8)
+__host__ __device__ inline int mma_pad_dim(int d) { return d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : d <= 48 ? 48 : d <= 56 ? 56 : 64; }
+
 // ------------------------------------------------------------------------------------ math
 __device__ __forceinline__ float clipf(float v, float c) {
     // utils/common.py:83-84 `tensor.clip(-max_norm, max_norm)`; c = +inf means no clip. NaN propagates.

@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
         // FourierMLP.timestep_embed(s)
         time_embed_row(blob, p.bl.te_phase, p.bl.te_h_w, p.bl.te_h_b, d.te_hidden, p.bl.te_out_w,
                        p.bl.te_out_b, C, s, buf_a, buf_b, buf_out);
-        if (tid < C) ws[p.ws.emb + (int64_t)i * C + tid] = buf_out[tid];
+        // the tcgen05 engine adds the input-layer bias here, once per step, instead of once per row
+        if (tid < C) ws[p.ws.emb + (int64_t)i * C + tid] = buf_out[tid] + ((d.flags & SDES_F_MLP_SIMT) ? 0.f : blob[p.bl.in_b + tid]);
         __syncthreads();
         // gate
         float* grow = ws + p.ws.gate + (int64_t)i * dpad;
@@ -131,8 +132,41 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
         ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0u;
     }
 
+    // tcgen05 weight images (layout: sdes_tc.cuh wimg_offset_floats; order: sdes_rollout_mma.cu):
+    // every weight split into tf32 hi (truncated) and lo = w - hi, zero-padded to the MMA shapes.
+    if (!(d.flags & SDES_F_MLP_SIMT)) {
+        float* w = ws + p.ws.w_mma;
+        const int nout = (dpad + 15) / 16 * 16;
+        int64_t o = 0;
+        auto put = [&](int64_t base, int n, int k, int N, int K, float v) {
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            const int64_t off = (int64_t)(k / 4) * (N * 4) + (n / 8) * 32 + (n % 8) * 4 + (k % 4);
+            w[base + off] = hi;
+            w[base + (int64_t)N * K + off] = v - hi;
+        };
+        for (int64_t e = gtid; e < (int64_t)C * dpad; e += nthreads) {  // input layer: N=C, K=dpad
+            const int n = (int)(e / dpad), k = (int)(e % dpad);
+            put(o, n, k, C, dpad, k < dim ? blob[p.bl.in_w + (int64_t)n * dim + k] : 0.f);
+        }
+        o += 2ll * C * dpad;
+        for (int l = 0; l < nh; ++l) {
+            for (int64_t e = gtid; e < C * C; e += nthreads) put(o, (int)(e / C), (int)(e % C), C, C, blob[p.bl.h_w[l] + e]);
+            o += 2ll * C * C;
+        }
+        for (int64_t e = gtid; e < (int64_t)nout * C; e += nthreads) {  // output layer: N=nout, K=C
+            const int n = (int)(e / C), k = (int)(e % C);
+            put(o, n, k, nout, C, n < dim ? blob[p.bl.out_w + (int64_t)n * C + k] : 0.f);
+        }
+        o += 2ll * nout * C;
+        for (int l = 0; l < nh; ++l) {
+            for (int64_t e = gtid; e < C; e += nthreads) w[o + e] = blob[p.bl.h_b[l] + e];
+            o += C;
+        }
+        for (int64_t e = gtid; e < nout; e += nthreads) w[o + e] = e < dim ? blob[p.bl.out_b + e] : 0.f;
+    }
+
     // SIMT weight image: WtIn[d][C] bIn[C] {Wt[C][C] b[C]} x nh  WtOut[C][dpad] bOut[dpad]
-    {
+    if (d.flags & SDES_F_MLP_SIMT) {
         float* w = ws + p.ws.w_simt;
         int64_t o = 0;
         for (int64_t e = gtid; e < (int64_t)dim * C; e += nthreads) {

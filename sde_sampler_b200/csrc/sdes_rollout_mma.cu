@@ -1,10 +1,377 @@
 // sdes_rollout_mma.cu — persistent rollout kernel, control MLP on tcgen05 tensor cores.
-// (placeholder until the tcgen05 engine lands: reports "unsupported" so callers must ask
-// for SDES_F_MLP_SIMT explicitly; there is no silent fallback.)
-#include "sdes_common.cuh"
+//
+// One CTA per SM, resident for the whole rollout.  It holds the split (hi/lo) weight images of
+// every layer in shared memory (loaded once with TMA bulk copies), owns all 512 TMEM columns,
+// and runs GROUPS independent groups of 4 warps.  A group pulls 128-trajectory tiles from a
+// global counter and carries each tile through all T time steps: thread r owns trajectory r —
+// its state x, running cost and network activations stay in registers / TMEM lane r.  Per step
+// and layer the group writes the activations (hi, lo) into TMEM as the A operand, one thread
+// issues the 3xTF32 MMAs against the shared-memory weights and commits to the group's mbarrier,
+// and the threads read the fp32 accumulator row back with tcgen05.ld for the fused epilogue
+// (bias, exact-erf GELU, then — after the last layer — target score, control reparametrisation,
+// cost increments, Philox noise, Euler-Maruyama update: sdes_step.cuh).  While one group waits
+// on its MMAs the other group's epilogue keeps the FP32/MUFU pipes busy.
+#include "sdes_step.cuh"
+#include "sdes_tc.cuh"
 
 namespace sdes {
-bool mma_supported(const KParams&) { return false; }
-int64_t mma_weight_image_floats(const SdesRolloutDesc&, int) { return 0; }
-cudaError_t launch_rollout_mma(const KParams&, int, cudaStream_t) { return cudaErrorNotSupported; }
+
+constexpr int MMA_GROUPS = 2;
+constexpr int MMA_THREADS = MMA_GROUPS * 128;
+constexpr int TMEM_COLS = 512;
+constexpr int GROUP_COLS = 256;  // D[64] | A_hi[64] | A_lo[64] | GMM logits scratch[64]
+
+__host__ __device__ inline int mma_nout(int dpad) { return (dpad + 15) / 16 * 16; }
+
+// GMM logits of this thread, parked in spare TMEM columns of its own lane
+struct TmemLogits {
+    uint32_t addr;
+    __device__ __forceinline__ void put8(int k0, const float (&v)[8]) const {
+        uint32_t u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = __float_as_uint(v[q]);
+        tc::tmem_st8(addr + (uint32_t)k0, u);
+    }
+    __device__ __forceinline__ void get8(int k0, float (&v)[8]) const {
+        tc::wait_st();
+        tc::tmem_ld8(addr + (uint32_t)k0, v);
+        tc::wait_ld();
+    }
+};
+
+// Workspace image for the tcgen05 engine (floats), in the order the kernel keeps it in smem:
+//   L0:  hi[64*K0] lo[64*K0]      (N=64, K=K0=dpad)
+//   Lh:  { hi[64*64] lo[64*64] } x n_hidden
+//   Lo:  hi[NOUT*64] lo[NOUT*64]  (N=NOUT, K=64)
+//   bias: { b_h[64] } x n_hidden, b_out[NOUT]     (b_in is folded into the time-embedding table)
+int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad_simt) {
+    (void)dpad_simt;
+    const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad);
+    return 2ll * 64 * dpad + (int64_t)d.n_hidden * (2ll * 64 * 64) + 2ll * nout * 64 + (int64_t)d.n_hidden * 64 + nout;
+}
+
+bool mma_supported(const KParams& p) { return p.d.dim <= 64 && p.d.n_hidden <= SDES_MAX_HIDDEN; }
+
+// ------------------------------------------------------------------------------ self test
+// D[128,N] = A[128,K] * W[N,K]^T through exactly the code path the rollout uses (A via tcgen05.st
+// into TMEM, W image in smem, 3xTF32 issue, tcgen05.ld).  Exposed as sdes_tcgen05_selftest.
+__global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                              float* __restrict__ D, int K, int N) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    float* w_hi = sm;
+    float* w_lo = sm + N * K;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < N * K; e += 128) {
+        const int n = e / K, k = e % K;
+        const float w = W[e];
+        const float hi = __uint_as_float(tc::tf32_hi_bits(w));
+        w_hi[tc::wimg_offset_floats(n, k, N)] = hi;
+        w_lo[tc::wimg_offset_floats(n, k, N)] = w - hi;
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(&tmem_base_s, 256);
+        tc::tmem_relinquish();
+    }
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_proxy_async();  // generic-proxy smem writes (weights) -> visible to the tensor-core (async) proxy
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t col_d = 0, col_hi = 64, col_lo = 128;
+    for (int c = 0; c < K; c += 8) {
+        uint32_t hi[8], lo[8];
+        for (int q = 0; q < 8; ++q) {
+            const float a = A[tid * K + c + q];
+            hi[q] = tc::tf32_hi_bits(a);
+            lo[q] = __float_as_uint(a - __uint_as_float(hi[q]));
+        }
+        tc::tmem_st8(lane_addr + col_hi + c, hi);
+        tc::tmem_st8(lane_addr + col_lo + c, lo);
+    }
+    tc::wait_st();
+    tc::fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after();
+        tc::issue_layer_3xtf32(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo), K, N);
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after();
+    for (int c = 0; c < N; c += 8) {
+        float v[8];
+        tc::tmem_ld8(lane_addr + col_d + c, v);
+        tc::wait_ld();
+        for (int q = 0; q < 8; ++q) D[tid * N + c + q] = v[q];
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 256);
+}
+
+cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream) {
+    const size_t smem = 2 * (size_t)N * K * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mma_selftest_kernel<<<1, 128, smem, stream>>>(A, W, D, K, N);
+    return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------- the kernel
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+// activations (fp32) -> TMEM A operand, split into tf32 hi / lo halves
+template <int N>
+__device__ __forceinline__ void store_a_split(uint32_t addr_hi, uint32_t addr_lo, const float (&a)[N]) {
+#pragma unroll
+    for (int c = 0; c < N; c += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            hi[q] = tc::tf32_hi_bits(a[c + q]);
+            lo[q] = __float_as_uint(a[c + q] - __uint_as_float(hi[q]));
+        }
+        tc::tmem_st8(addr_hi + c, hi);
+        tc::tmem_st8(addr_lo + c, lo);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void load_acc(uint32_t addr_d, float (&acc)[N]) {
+#pragma unroll
+    for (int c = 0; c < N; c += 8) tc::tmem_ld8(addr_d + c, &acc[c]);
+    tc::wait_ld();
+}
+
+struct GroupCtx {
+    int g;               // group index
+    int gtid;            // thread index in the group = row in the tile = TMEM lane
+    uint32_t t_d, t_hi, t_lo;          // TMEM addresses, lane 0 of the tile (for the issuing thread)
+    uint32_t l_d, l_hi, l_lo;          // same, at this thread's warp lane window (for ld / st)
+    uint64_t* bar;
+    uint32_t phase;
+};
+
+// A operand is in TMEM; run one layer and leave the accumulator ready to be read.
+__device__ __forceinline__ void run_layer(GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K, int N) {
+    tc::wait_st();
+    tc::fence_before();
+    group_bar(c.g);
+    if (c.gtid == 0) {
+        tc::fence_after();
+        tc::issue_layer_3xtf32(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K, N);
+        tc::mma_commit(c.bar);
+    }
+    tc::mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    tc::fence_after();
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __grid_constant__ KParams p) {
+    constexpr int NOUT = (DPAD + 15) / 16 * 16;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t s_wbar;
+    __shared__ uint64_t s_mbar[MMA_GROUPS];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_tile[MMA_GROUPS];
+
+    const SdesRolloutDesc& d = p.d;
+    const float* ws = reinterpret_cast<const float*>(d.workspace);
+    const int dim = d.dim, T = d.n_steps, K = d.n_components, nh = d.n_hidden;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- shared memory carve-up: [weight image + biases | gmm mu | gmm h | gmm c | prior | ref]
+    float* s_w = smem;
+    float* s_mu = s_w + p.ws.w_mma_len;
+    float* s_h = s_mu + K * DPAD;
+    float* s_c = s_h + K * DPAD;
+    float* s_prior = s_c + 64;
+    float* s_ref = s_prior + 2 * DPAD + 8;
+
+    if (warp == 0) {
+        tc::tmem_alloc(&s_tmem, TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    if (tid == 0) {
+        tc::mbar_init(&s_wbar, 1);
+        for (int g = 0; g < MMA_GROUPS; ++g) tc::mbar_init(&s_mbar[g], 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    if (tid == 0) {
+        // weights: TMA bulk copies global -> shared, all counted on one mbarrier
+        const uint32_t total = (uint32_t)(p.ws.w_mma_len * sizeof(float));
+        tc::mbar_arrive_expect_tx(&s_wbar, total);
+        const char* src = reinterpret_cast<const char*>(ws + p.ws.w_mma);
+        char* dst = reinterpret_cast<char*>(s_w);
+        for (uint32_t off = 0; off < total; off += 16384u) {
+            const uint32_t n = total - off < 16384u ? total - off : 16384u;
+            tc::bulk_g2s(dst + off, src + off, n, &s_wbar);
+        }
+    }
+    for (int e = tid; e < K * DPAD; e += blockDim.x) {
+        s_mu[e] = ws[p.ws.gmm_mu + e];
+        s_h[e] = ws[p.ws.gmm_h + e];
+    }
+    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
+    for (int e = tid; e < 2 * DPAD + 8; e += blockDim.x) {
+        s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
+        s_ref[e] = e <= 2 * DPAD ? ws[p.ws.ref + e] : 0.f;
+    }
+    tc::mbar_wait(&s_wbar, 0);
+    __syncthreads();
+
+    // weight image addresses
+    const uint32_t w_base = tc::smem_u32(s_w);
+    const uint32_t l0_hi = w_base, l0_lo = w_base + 64u * DPAD * 4u;
+    const uint32_t lh_base = l0_lo + 64u * DPAD * 4u;                   // + l * 2 * 16 KB
+    const uint32_t lo_hi = lh_base + (uint32_t)nh * 2u * 16384u, lo_lo = lo_hi + (uint32_t)NOUT * 64u * 4u;
+    const float* s_bias = s_w + 2 * 64 * DPAD + nh * 2 * 64 * 64 + 2 * NOUT * 64;  // {b_h[64]} x nh, b_out[NOUT]
+
+    TargetSmem tsm{s_mu, s_h, s_c, s_prior, s_ref};
+    GroupCtx c;
+    c.g = warp >> 2;
+    c.gtid = tid & 127;
+    const uint32_t tbase = s_tmem + (uint32_t)(c.g * GROUP_COLS);
+    c.t_d = tbase;
+    c.t_hi = tbase + 64;
+    c.t_lo = tbase + 128;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    c.l_d = c.t_d + lane_off;
+    c.l_hi = c.t_hi + lane_off;
+    c.l_lo = c.t_lo + lane_off;
+    c.bar = &s_mbar[c.g];
+    c.phase = 0;
+
+    uint32_t* counter = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.counter);
+    const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
+    const bool ret_traj = (d.flags & SDES_F_RETURN_TRAJ) != 0;
+    const int64_t B = d.batch;
+    const uint32_t n_tiles = (uint32_t)((B + 127) / 128);
+    const TmemLogits lbuf{c.l_d + 192u};
+
+    for (;;) {
+        if (c.gtid == 0) s_tile[c.g] = atomicAdd(counter, 1u);
+        group_bar(c.g);
+        const uint32_t tile = s_tile[c.g];
+        if (tile >= n_tiles) break;
+        const int64_t row = (int64_t)tile * 128 + c.gtid;
+        const bool valid = row < B;
+        const int64_t rrow = valid ? row : (B - 1);
+
+        float x[DPAD];
+#pragma unroll
+        for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
+        if (ret_traj && valid) {
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j)
+                if (j < dim) d.xs[rrow * dim + j] = x[j];
+        }
+        float rnd = initial_rnd<DPAD>(d, x, tsm);
+        const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)rrow);
+
+        for (int i = 0; i < T; ++i) {
+            const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
+            float g[DPAD];
+            {
+                // ---- control MLP on the tensor cores (models/mlp.py:114-122)
+                float acc[C];
+                store_a_split<DPAD>(c.l_hi, c.l_lo, x);
+                run_layer(c, l0_hi, l0_lo, DPAD, C);
+                load_acc<C>(c.l_d, acc);
+                const float4* e4 = reinterpret_cast<const float4*>(ws + p.ws.emb + (int64_t)i * C);  // emb_t + b_in
+#pragma unroll
+                for (int q = 0; q < C / 4; ++q) {
+                    const float4 e = __ldg(e4 + q);
+                    acc[4 * q + 0] = gelu_erf(acc[4 * q + 0] + e.x);
+                    acc[4 * q + 1] = gelu_erf(acc[4 * q + 1] + e.y);
+                    acc[4 * q + 2] = gelu_erf(acc[4 * q + 2] + e.z);
+                    acc[4 * q + 3] = gelu_erf(acc[4 * q + 3] + e.w);
+                }
+                for (int l = 0; l < nh; ++l) {
+                    store_a_split<C>(c.l_hi, c.l_lo, acc);
+                    run_layer(c, lh_base + (uint32_t)l * 32768u, lh_base + (uint32_t)l * 32768u + 16384u, C, C);
+                    load_acc<C>(c.l_d, acc);
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * C);
+#pragma unroll
+                    for (int q = 0; q < C / 4; ++q) {
+                        const float4 b = b4[q];
+                        acc[4 * q + 0] = gelu_erf(acc[4 * q + 0] + b.x);
+                        acc[4 * q + 1] = gelu_erf(acc[4 * q + 1] + b.y);
+                        acc[4 * q + 2] = gelu_erf(acc[4 * q + 2] + b.z);
+                        acc[4 * q + 3] = gelu_erf(acc[4 * q + 3] + b.w);
+                    }
+                }
+                store_a_split<C>(c.l_hi, c.l_lo, acc);
+                run_layer(c, lo_hi, lo_lo, C, NOUT);
+                load_acc<DPAD>(c.l_d, g);
+                const float* bo = s_bias + nh * C;
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j) g[j] += bo[j];
+            }
+            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W], lbuf);
+            const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
+            step_update<DPAD>(d, x, g, rnd, tsm, tab, i, traj, nrow);
+            if (ret_traj && valid) {
+                float* o = d.xs + ((int64_t)(i + 1) * B + rrow) * dim;
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j)
+                    if (j < dim) o[j] = x[j];
+            }
+        }
+        rnd += terminal_rnd<DPAD>(d, x, tsm, lbuf);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j)
+                if (j < dim) d.x_T[rrow * dim + j] = x[j];
+            d.rnd[rrow] = rnd;
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(s_tmem, TMEM_COLS);
+}
+
+size_t mma_smem_bytes(const KParams& p) {
+    const int dpad = p.ws.dpad, K = p.d.n_components;
+    const size_t fl = (size_t)p.ws.w_mma_len + 2 * (size_t)K * dpad + 64 + 2 * (2 * dpad + 8);
+    return fl * sizeof(float);
+}
+
+template <int DPAD>
+static cudaError_t launch_mma_t(const KParams& p, int sm_count, cudaStream_t stream) {
+    const size_t smem = mma_smem_bytes(p);
+    cudaError_t e = cudaFuncSetAttribute(rollout_mma_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int tiles = (int)((p.d.batch + 127) / 128);
+    int grid = (tiles + MMA_GROUPS - 1) / MMA_GROUPS;
+    if (grid > sm_count) grid = sm_count;
+    if (grid < 1) grid = 1;
+    rollout_mma_kernel<DPAD><<<grid, MMA_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream) {
+    switch (p.ws.dpad) {
+        case 8: return launch_mma_t<8>(p, sm_count, stream);
+        case 16: return launch_mma_t<16>(p, sm_count, stream);
+        case 32: return launch_mma_t<32>(p, sm_count, stream);
+        case 48: return launch_mma_t<48>(p, sm_count, stream);
+        case 56: return launch_mma_t<56>(p, sm_count, stream);
+        case 64: return launch_mma_t<64>(p, sm_count, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace sdes

@@ -26,50 +26,81 @@ struct TargetSmem {
 // `lbuf` is this thread's private column of K floats (stride 32) used to hold the logits.
 // Direct (x-mu)^2 form: the expanded x^2 - 2 x mu + mu^2 form cancels catastrophically for
 // modes at |mu| ~ 40 (SURVEY §7 "GMM log-density cancellation").
-template <int DPAD, bool NEED_SCORE>
-__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts,
-                                          int K, float* lbuf) {
-    float m = -INFINITY;
-    for (int k = 0; k < K; ++k) {
-        const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
-        const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+// Per-thread scratch for the K mixture logits, written / read 8 at a time.  Two backings:
+// a shared-memory column (fp32-FFMA engine) or spare TMEM columns of the thread's own lane
+// (tcgen05 engine, sdes_rollout_mma.cu).
+struct SmemLogits {
+    float* col;  // this thread's column, stride 32 floats
+    __device__ __forceinline__ void put8(int k0, const float (&v)[8]) const {
 #pragma unroll
-        for (int q = 0; q < DPAD / 4; ++q) {
-            const float4 mu = mu4[q], h = h4[q];
-            const float d0 = x[4 * q + 0] - mu.x, d1 = x[4 * q + 1] - mu.y;
-            const float d2 = x[4 * q + 2] - mu.z, d3 = x[4 * q + 3] - mu.w;
-            a0 = fmaf(d0 * d0, h.x, a0);
-            a1 = fmaf(d1 * d1, h.y, a1);
-            a2 = fmaf(d2 * d2, h.z, a2);
-            a3 = fmaf(d3 * d3, h.w, a3);
+        for (int q = 0; q < 8; ++q) col[(k0 + q) * 32] = v[q];
+    }
+    __device__ __forceinline__ void get8(int k0, float (&v)[8]) const {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = col[(k0 + q) * 32];
+    }
+};
+
+template <int DPAD, bool NEED_SCORE, class Logits>
+__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts,
+                                          int K, const Logits& lg) {
+    float m = -INFINITY;
+    const int K8 = (K + 7) & ~7;
+    for (int k0 = 0; k0 < K8; k0 += 8) {
+        float l8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = k0 + q;
+            float l = -INFINITY;
+            if (k < K) {  // warp-uniform
+                const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
+                const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int r = 0; r < DPAD / 4; ++r) {
+                    const float4 mu = mu4[r], h = h4[r];
+                    const float d0 = x[4 * r + 0] - mu.x, d1 = x[4 * r + 1] - mu.y;
+                    const float d2 = x[4 * r + 2] - mu.z, d3 = x[4 * r + 3] - mu.w;
+                    a0 = fmaf(d0 * d0, h.x, a0);
+                    a1 = fmaf(d1 * d1, h.y, a1);
+                    a2 = fmaf(d2 * d2, h.z, a2);
+                    a3 = fmaf(d3 * d3, h.w, a3);
+                }
+                l = ts.gmm_c[k] - ((a0 + a1) + (a2 + a3));
+            }
+            l8[q] = l;
+            m = fmaxf(m, l);
         }
-        const float l = ts.gmm_c[k] - ((a0 + a1) + (a2 + a3));
-        lbuf[k * 32] = l;
-        m = fmaxf(m, l);
+        lg.put8(k0, l8);
     }
     float ssum = 0.f;
     if (NEED_SCORE) {
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) score[j] = 0.f;
     }
-    for (int k = 0; k < K; ++k) {
-        const float e = __expf(lbuf[k * 32] - m);
-        ssum += e;
-        if (NEED_SCORE) {
-            // components whose responsibility underflows to 0 contribute exactly 0: skip them
-            // when that holds for the whole warp (bit-identical result).
-            if (__any_sync(0xffffffffu, e > 0.f)) {
-                const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
-                const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
-                const float e2 = 2.0f * e;  // 1/var = 2h
+    for (int k0 = 0; k0 < K8; k0 += 8) {
+        float l8[8];
+        lg.get8(k0, l8);
 #pragma unroll
-                for (int q = 0; q < DPAD / 4; ++q) {
-                    const float4 mu = mu4[q], h = h4[q];
-                    score[4 * q + 0] = fmaf(e2 * h.x, mu.x - x[4 * q + 0], score[4 * q + 0]);
-                    score[4 * q + 1] = fmaf(e2 * h.y, mu.y - x[4 * q + 1], score[4 * q + 1]);
-                    score[4 * q + 2] = fmaf(e2 * h.z, mu.z - x[4 * q + 2], score[4 * q + 2]);
-                    score[4 * q + 3] = fmaf(e2 * h.w, mu.w - x[4 * q + 3], score[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) {
+            const int k = k0 + q;
+            const float e = __expf(l8[q] - m);  // padded components: exp(-inf) = 0
+            ssum += e;
+            if (NEED_SCORE) {
+                // components whose responsibility underflows to 0 contribute exactly 0: skip them
+                // when that holds for the whole warp (bit-identical result).
+                if (__any_sync(0xffffffffu, e > 0.f)) {
+                    const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
+                    const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
+                    const float e2 = 2.0f * e;  // 1/var = 2h
+#pragma unroll
+                    for (int r = 0; r < DPAD / 4; ++r) {
+                        const float4 mu = mu4[r], h = h4[r];
+                        score[4 * r + 0] = fmaf(e2 * h.x, mu.x - x[4 * r + 0], score[4 * r + 0]);
+                        score[4 * r + 1] = fmaf(e2 * h.y, mu.y - x[4 * r + 1], score[4 * r + 1]);
+                        score[4 * r + 2] = fmaf(e2 * h.z, mu.z - x[4 * r + 2], score[4 * r + 2]);
+                        score[4 * r + 3] = fmaf(e2 * h.w, mu.w - x[4 * r + 3], score[4 * r + 3]);
+                    }
                 }
             }
         }
@@ -123,12 +154,12 @@ __device__ __forceinline__ float funnel_eval(const float (&x)[DPAD], float (&sco
     return lp_first + lp_other;
 }
 
-template <int DPAD, bool NEED_SCORE>
+template <int DPAD, bool NEED_SCORE, class Logits>
 __device__ __forceinline__ float target_eval(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&score)[DPAD],
-                                             const TargetSmem& ts, float* lbuf) {
+                                             const TargetSmem& ts, const Logits& lbuf) {
     float lp;
     if (d.target_kind == SDES_TARGET_GMM)
-        lp = gmm_eval<DPAD, NEED_SCORE>(x, score, ts, d.n_components, lbuf);
+        lp = gmm_eval<DPAD, NEED_SCORE, Logits>(x, score, ts, d.n_components, lbuf);
     else if (d.target_kind == SDES_TARGET_MULTIWELL)
         lp = multiwell_eval<DPAD, NEED_SCORE>(x, score, d.dim, d.n_double_wells, d.separation, d.shift);
     else
@@ -152,10 +183,10 @@ __device__ __forceinline__ float diag_gauss_logp(const float (&x)[DPAD], const f
 // g = generative_ctrl(s, x) given nn = NN(s, x): ClippedCtrl reparam.py:35-36, ScoreCtrl
 // :78-83, LerpCtrl :131-162, LerpPriorCtrl :165-181, LerpTargetCtrl :184-200.
 // In: g[] holds the raw network output; out: g[] holds the control.
-template <int DPAD>
+template <int DPAD, class Logits>
 __device__ __forceinline__ void control_assemble(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&g)[DPAD],
                                                  const TargetSmem& ts, const float* __restrict__ gate_row,
-                                                 float sigma, float lerp_w, float* lbuf) {
+                                                 float sigma, float lerp_w, const Logits& lbuf) {
     const float cm = d.clip_model, cs = d.clip_score;
     if (d.ctrl_kind == SDES_CTRL_CLIPPED) {
 #pragma unroll
@@ -164,7 +195,7 @@ __device__ __forceinline__ void control_assemble(const SdesRolloutDesc& d, const
     }
     float sc[DPAD];
     if (d.ctrl_kind != SDES_CTRL_LERP_PRIOR) {
-        target_eval<DPAD, true>(d, x, sc, ts, lbuf);
+        target_eval<DPAD, true, Logits>(d, x, sc, ts, lbuf);
     } else {
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
@@ -251,11 +282,11 @@ __device__ __forceinline__ float initial_rnd(const SdesRolloutDesc& d, const flo
 }
 
 // terminal cost (losses/oc.py:225, :337, :449-450; clip: solver/oc.py:48-54)
-template <int DPAD>
+template <int DPAD, class Logits>
 __device__ __forceinline__ float terminal_rnd(const SdesRolloutDesc& d, const float (&x)[DPAD], const TargetSmem& ts,
-                                              float* lbuf) {
+                                              const Logits& lbuf) {
     float dummy[DPAD];
-    const float lp = clipf(target_eval<DPAD, false>(d, x, dummy, ts, lbuf), d.clip_target);
+    const float lp = clipf(target_eval<DPAD, false, Logits>(d, x, dummy, ts, lbuf), d.clip_target);
     if (d.loss_kind == SDES_LOSS_TIME_REVERSAL) return -lp;
     return diag_gauss_logp<DPAD>(x, ts.ref) - lp;
 }

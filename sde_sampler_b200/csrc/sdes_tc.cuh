@@ -1,0 +1,142 @@
+// sdes_tc.cuh — tcgen05 / TMEM / mbarrier / bulk-copy primitives (inline PTX, sm_100a) and the
+// "3xTF32" dense layer used by the control MLP.
+//
+// One GROUP = 4 consecutive warps = 128 trajectories = one M=128 MMA tile; thread r of the group
+// owns TMEM lane r (row r).  Per layer
+//     D[128, N] (TMEM, fp32)  =  A[128, K] (TMEM)  x  W[N, K]^T (shared memory, K-major)
+// is issued by one thread as K/8 k-steps of three kind::tf32 MMAs
+//     A_hi*W_hi + A_lo*W_hi + A_hi*W_lo          (hi = fp32 truncated to tf32, lo = fp32 - hi)
+// which recovers ~2^-21 relative accuracy from the 10-bit-mantissa tensor-core format — the
+// reference computes in true fp32 (TF32 is off by default in PyTorch), so a single tf32 pass
+// (~1e-3 per layer) would not hold the stated 2e-4 tolerance over 100 steps.
+#pragma once
+
+#include "sdes_common.cuh"
+
+namespace sdes {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------- TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 8 consecutive 32-bit columns of this thread's lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+// ----------------------------------------------------------------------------------- MMA
+// Instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format[4,6)=1 (F32),
+// a_format[7,10)=2 (TF32), b_format[10,13)=2 (TF32), a_major[15]=0 (K), b_major[16]=0 (K),
+// n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core
+// matrices; LBO = byte distance between the two 16-byte K-chunks of one MMA (K=8 tf32),
+// SBO = byte distance between consecutive 8-row groups.  version=1 (Blackwell) at bit 46.
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, one k-step (K = 8 tf32)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all previously issued MMAs of this thread -> one arrive on an mbarrier
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- weight image (B operand)
+// Byte layout of one layer's W (N rows x K cols, fp32) in shared memory / in the workspace image:
+//   offset(n, k) = (k/4) * (N*16) + (n/8) * 128 + (n%8) * 16 + (k%4) * 4
+// i.e. LBO = N*16 bytes, SBO = 128 bytes; k-step s starts at byte s * 2 * LBO.
+__host__ __device__ inline int64_t wimg_offset_floats(int n, int k, int N) {
+    return (int64_t)(k / 4) * (N * 4) + (n / 8) * 32 + (n % 8) * 4 + (k % 4);
+}
+
+__device__ __forceinline__ uint32_t tf32_hi_bits(float a) { return __float_as_uint(a) & 0xFFFFE000u; }
+
+// Issue one 3xTF32 layer: K in {8..64, multiple of 8}, N multiple of 16.  Called by ONE thread.
+//   tmem_a_hi / tmem_a_lo : TMEM addresses (lane 0 of the group) of the A operand halves
+//   w_hi / w_lo           : shared-memory addresses of the two weight images
+__device__ __forceinline__ void issue_layer_3xtf32(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
+                                                   uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K, int N) {
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t lbo = (uint32_t)N * 16u;
+    const int ksteps = K >> 3;
+    for (int s = 0; s < ksteps; ++s) {
+        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        // small terms first, the dominant hi*hi product last
+        mma_tf32_ts(tmem_d, tmem_a_lo + 8u * s, bh, idesc, s > 0 ? 1u : 0u);
+        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bl, idesc, 1u);
+        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bh, idesc, 1u);
+    }
+}
+
+}  // namespace tc
+}  // namespace sdes

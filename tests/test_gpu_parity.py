@@ -20,7 +20,7 @@ from sdes_test_helpers import assert_close, build_from_spec
 pytestmark = pytest.mark.gpu
 
 RTOL = ATOL = 2e-4
-ENGINES = ["simt"]
+ENGINES = ["simt", "tcgen05"]
 
 
 def _dev():

@@ -1,0 +1,31 @@
+"""-m gpu: the tensor-core building block on its own — one 3xTF32 tcgen05 layer (A staged in TMEM,
+W image in shared memory) against a float64 matmul.  Runs before the rollout parity tests so a
+descriptor / layout bug shows up here, in isolation."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("K,N", [(8, 16), (8, 64), (16, 64), (56, 64), (64, 64), (64, 16), (64, 48), (32, 32)])
+def test_3xtf32_layer_matches_fp64(K, N):
+    from sde_sampler_b200 import _cabi
+
+    lib = _cabi.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(K * 100 + N)
+    A = (torch.randn(128, K, generator=g) * 3).to(dev)
+    W = torch.randn(N, K, generator=g).to(dev)
+    D = torch.full((128, N), float("nan"), device=dev)
+    rc = lib.sdes_tcgen05_selftest(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.sdes_last_error()
+    torch.cuda.synchronize()
+    want = A.double() @ W.double().T
+    scale = (A.double().abs() @ W.double().abs().T)
+    err = ((D.double() - want).abs() / scale).max().item()
+    # fp32 SGEMM itself sits at ~1e-7 of sum|a||w|; single-pass TF32 would be ~5e-4
+    assert err < 2e-6, f"relative error {err:.3e} (K={K}, N={N})"
