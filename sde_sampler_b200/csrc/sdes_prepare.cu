@@ -129,7 +129,18 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
 
     if (gtid == 0) {
         uint32_t* ctr = reinterpret_cast<uint32_t*>(ws + p.ws.counter);
-        ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0u;
+        ctr[0] = ctr[2] = ctr[3] = 0u;  // [0] = dynamic tile counter
+        // [1] = GMM chunk mask: bit r set when dims 4r..4r+3 differ between components (sdes_step.cuh gmm_eval)
+        uint32_t mask = 0u;
+        if (d.target_kind == SDES_TARGET_GMM) {
+            for (int j = 0; j < dim; ++j) {
+                bool differs = false;
+                for (int k = 1; k < d.n_components && !differs; ++k)
+                    differs = d.gmm_loc[(int64_t)k * dim + j] != d.gmm_loc[j] || d.gmm_scale[(int64_t)k * dim + j] != d.gmm_scale[j];
+                if (differs) mask |= 1u << (j >> 2);
+            }
+        }
+        ctr[1] = mask;
     }
 
     // tcgen05 weight images (layout: sdes_tc.cuh wimg_offset_floats; order: sdes_rollout_mma.cu):

@@ -19,25 +19,9 @@ namespace sdes {
 constexpr int MMA_GROUPS = 2;
 constexpr int MMA_THREADS = MMA_GROUPS * 128;
 constexpr int TMEM_COLS = 512;
-constexpr int GROUP_COLS = 256;  // D[64] | A_hi[64] | A_lo[64] | GMM logits scratch[64]
+constexpr int GROUP_COLS = 256;  // D[64] | A_hi[64] | A_lo[64] | spare[64]
 
 __host__ __device__ inline int mma_nout(int dpad) { return (dpad + 15) / 16 * 16; }
-
-// GMM logits of this thread, parked in spare TMEM columns of its own lane
-struct TmemLogits {
-    uint32_t addr;
-    __device__ __forceinline__ void put8(int k0, const float (&v)[8]) const {
-        uint32_t u[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) u[q] = __float_as_uint(v[q]);
-        tc::tmem_st8(addr + (uint32_t)k0, u);
-    }
-    __device__ __forceinline__ void get8(int k0, float (&v)[8]) const {
-        tc::wait_st();
-        tc::tmem_ld8(addr + (uint32_t)k0, v);
-        tc::wait_ld();
-    }
-};
 
 // Workspace image for the tcgen05 engine (floats), in the order the kernel keeps it in smem:
 //   L0:  hi[64*K0] lo[64*K0]      (N=64, K=K0=dpad)
@@ -148,8 +132,27 @@ template <int N>
 __device__ __forceinline__ void load_acc(uint32_t addr_d, float (&acc)[N]) {
 #pragma unroll
     for (int c = 0; c < N; c += 8) tc::tmem_ld8(addr_d + c, &acc[c]);
-    tc::wait_ld();
+    tc::wait_ld_tie<N>(acc);
 }
+
+// 8 accumulator columns -> + bias -> exact GELU -> tf32 hi/lo split -> A operand of the next layer
+__device__ __forceinline__ void gelu_split_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8],
+                                                  const float* __restrict__ bias) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float a = gelu_erf(v[q] + bb[q]);
+        hi[q] = tc::tf32_hi_bits(a);
+        lo[q] = __float_as_uint(a - __uint_as_float(hi[q]));
+    }
+    tc::tmem_st8(addr_hi, hi);
+    tc::tmem_st8(addr_lo, lo);
+}
+
+struct GroupCtx;
+__device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* __restrict__ bias);
 
 struct GroupCtx {
     int g;               // group index
@@ -173,6 +176,25 @@ __device__ __forceinline__ void run_layer(GroupCtx& c, uint32_t w_hi_saddr, uint
     tc::mbar_wait(c.bar, c.phase);
     c.phase ^= 1u;
     tc::fence_after();
+}
+
+// The fused epilogue between two layers, streamed 8 columns at a time straight from the
+// accumulator (TMEM) into the next A operand (TMEM): the 64-wide activation row never sits in
+// registers, and one compact loop serves every layer (instruction-cache footprint matters: the
+// first version of this kernel spent 42% of its stall samples on instruction fetch).
+// `bias` may point to global (time-embedding row, input layer) or shared memory (hidden biases).
+__device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* __restrict__ bias) {
+    float a[8], b[8];
+    tc::tmem_ld8(c.l_d, a);
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ch += 2) {
+        tc::wait_ld_tie<8>(a);
+        tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
+        gelu_split_store8(c.l_hi + 8u * ch, c.l_lo + 8u * ch, a, bias + 8 * ch);
+        tc::wait_ld_tie<8>(b);
+        if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
+        gelu_split_store8(c.l_hi + 8u * (ch + 1), c.l_lo + 8u * (ch + 1), b, bias + 8 * (ch + 1));
+    }
 }
 
 template <int DPAD>
@@ -239,7 +261,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
     const uint32_t lo_hi = lh_base + (uint32_t)nh * 2u * 16384u, lo_lo = lo_hi + (uint32_t)NOUT * 64u * 4u;
     const float* s_bias = s_w + 2 * 64 * DPAD + nh * 2 * 64 * 64 + 2 * NOUT * 64;  // {b_h[64]} x nh, b_out[NOUT]
 
-    TargetSmem tsm{s_mu, s_h, s_c, s_prior, s_ref};
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
     GroupCtx c;
     c.g = warp >> 2;
     c.gtid = tid & 127;
@@ -259,7 +281,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
     const bool ret_traj = (d.flags & SDES_F_RETURN_TRAJ) != 0;
     const int64_t B = d.batch;
     const uint32_t n_tiles = (uint32_t)((B + 127) / 128);
-    const TmemLogits lbuf{c.l_d + 192u};
 
     for (;;) {
         if (c.gtid == 0) s_tile[c.g] = atomicAdd(counter, 1u);
@@ -286,41 +307,21 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
             float g[DPAD];
             {
                 // ---- control MLP on the tensor cores (models/mlp.py:114-122)
-                float acc[C];
                 store_a_split<DPAD>(c.l_hi, c.l_lo, x);
                 run_layer(c, l0_hi, l0_lo, DPAD, C);
-                load_acc<C>(c.l_d, acc);
-                const float4* e4 = reinterpret_cast<const float4*>(ws + p.ws.emb + (int64_t)i * C);  // emb_t + b_in
-#pragma unroll
-                for (int q = 0; q < C / 4; ++q) {
-                    const float4 e = __ldg(e4 + q);
-                    acc[4 * q + 0] = gelu_erf(acc[4 * q + 0] + e.x);
-                    acc[4 * q + 1] = gelu_erf(acc[4 * q + 1] + e.y);
-                    acc[4 * q + 2] = gelu_erf(acc[4 * q + 2] + e.z);
-                    acc[4 * q + 3] = gelu_erf(acc[4 * q + 3] + e.w);
-                }
+                layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
+#pragma unroll 1
                 for (int l = 0; l < nh; ++l) {
-                    store_a_split<C>(c.l_hi, c.l_lo, acc);
                     run_layer(c, lh_base + (uint32_t)l * 32768u, lh_base + (uint32_t)l * 32768u + 16384u, C, C);
-                    load_acc<C>(c.l_d, acc);
-                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * C);
-#pragma unroll
-                    for (int q = 0; q < C / 4; ++q) {
-                        const float4 b = b4[q];
-                        acc[4 * q + 0] = gelu_erf(acc[4 * q + 0] + b.x);
-                        acc[4 * q + 1] = gelu_erf(acc[4 * q + 1] + b.y);
-                        acc[4 * q + 2] = gelu_erf(acc[4 * q + 2] + b.z);
-                        acc[4 * q + 3] = gelu_erf(acc[4 * q + 3] + b.w);
-                    }
+                    layer_epilogue(c, s_bias + l * C);
                 }
-                store_a_split<C>(c.l_hi, c.l_lo, acc);
                 run_layer(c, lo_hi, lo_lo, C, NOUT);
                 load_acc<DPAD>(c.l_d, g);
                 const float* bo = s_bias + nh * C;
 #pragma unroll
                 for (int j = 0; j < DPAD; ++j) g[j] += bo[j];
             }
-            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W], lbuf);
+            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
             const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
             step_update<DPAD>(d, x, g, rnd, tsm, tab, i, traj, nrow);
             if (ret_traj && valid) {
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
                     if (j < dim) o[j] = x[j];
             }
         }
-        rnd += terminal_rnd<DPAD>(d, x, tsm, lbuf);
+        rnd += terminal_rnd<DPAD>(d, x, tsm);
         if (valid) {
 #pragma unroll
             for (int j = 0; j < DPAD; ++j)

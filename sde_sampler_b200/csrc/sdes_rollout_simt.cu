@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
         s_ref[e] = e <= 2 * DPAD ? ws[p.ws.ref + e] : 0.f;
     }
     __syncthreads();
-    TargetSmem tsm{s_mu, s_h, s_c, s_prior, s_ref};
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
     float* act = s_act + warp * (C * 32);
     uint32_t* counter = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.counter);
     const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
             const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
             float g[DPAD];
             mlp_simt<DPAD>(x, g, s_w, ws + p.ws.emb + (int64_t)i * C, act, dim, d.n_hidden);
-            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W], SmemLogits{act + lane});
+            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
             const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
             step_update<DPAD>(d, x, g, rnd, tsm, tab, i, traj, nrow);
             if (ret_traj && valid) {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
                     if (j < dim) o[j] = x[j];
             }
         }
-        rnd += terminal_rnd<DPAD>(d, x, tsm, SmemLogits{act + lane});
+        rnd += terminal_rnd<DPAD>(d, x, tsm);
         if (valid) {
 #pragma unroll
             for (int j = 0; j < DPAD; ++j)

@@ -16,6 +16,7 @@ struct TargetSmem {
     const float* gmm_mu;  // K * DPAD
     const float* gmm_h;   // K * DPAD
     const float* gmm_c;   // 64
+    uint32_t gmm_mask;    // bit r: dimension chunk r (4 dims) differs between components
     const float* prior;   // loc[DPAD] | inv_var[DPAD] | lognorm
     const float* ref;     // same
 };
@@ -23,94 +24,108 @@ struct TargetSmem {
 // -------------------------------------------------------------------------------- targets
 // GMM log-density and score (MixtureSameFamily log_prob distr/gauss.py:119-140; the reference
 // differentiates it with autograd, distr/base.py:130-137 — analytic form SURVEY App. A.4).
-// `lbuf` is this thread's private column of K floats (stride 32) used to hold the logits.
 // Direct (x-mu)^2 form: the expanded x^2 - 2 x mu + mu^2 form cancels catastrophically for
 // modes at |mu| ~ 40 (SURVEY §7 "GMM log-density cancellation").
-// Per-thread scratch for the K mixture logits, written / read 8 at a time.  Two backings:
-// a shared-memory column (fp32-FFMA engine) or spare TMEM columns of the thread's own lane
-// (tcgen05 engine, sdes_rollout_mma.cu).
-struct SmemLogits {
-    float* col;  // this thread's column, stride 32 floats
-    __device__ __forceinline__ void put8(int k0, const float (&v)[8]) const {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) col[(k0 + q) * 32] = v[q];
-    }
-    __device__ __forceinline__ void get8(int k0, float (&v)[8]) const {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = col[(k0 + q) * 32];
-    }
-};
-
-template <int DPAD, bool NEED_SCORE, class Logits>
-__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts,
-                                          int K, const Logits& lg) {
-    float m = -INFINITY;
-    const int K8 = (K + 7) & ~7;
-    for (int k0 = 0; k0 < K8; k0 += 8) {
-        float l8[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = k0 + q;
-            float l = -INFINITY;
-            if (k < K) {  // warp-uniform
-                const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
-                const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int r = 0; r < DPAD / 4; ++r) {
-                    const float4 mu = mu4[r], h = h4[r];
-                    const float d0 = x[4 * r + 0] - mu.x, d1 = x[4 * r + 1] - mu.y;
-                    const float d2 = x[4 * r + 2] - mu.z, d3 = x[4 * r + 3] - mu.w;
-                    a0 = fmaf(d0 * d0, h.x, a0);
-                    a1 = fmaf(d1 * d1, h.y, a1);
-                    a2 = fmaf(d2 * d2, h.z, a2);
-                    a3 = fmaf(d3 * d3, h.w, a3);
-                }
-                l = ts.gmm_c[k] - ((a0 + a1) + (a2 + a3));
-            }
-            l8[q] = l;
-            m = fmaxf(m, l);
-        }
-        lg.put8(k0, l8);
-    }
-    float ssum = 0.f;
+// One pass over the components with an online (running-max) softmax: no logits are stored.
+// Per component: phase A accumulates the logit, phase B folds its responsibility-weighted
+// score term into running sums that are rescaled whenever the running max moves.
+//
+// `ts.gmm_mask` has bit r set when dimension chunk r (4 dims) differs between components.
+// Chunks whose (mu, scale) are identical in every component factor out of the mixture exactly:
+//     log rho(x) = logsumexp_k [ c_k - sum_{j in active} h_kj (x_j - mu_kj)^2 ] - sum_{j shared} h_j (x_j - mu_j)^2
+//     score_j    = 2 h_j (mu_j - x_j)                                            for shared j
+// so they cost O(d) instead of O(K d) (e.g. the zero-padded dims of GMM-40 in d=50).
+template <int DPAD, bool NEED_SCORE>
+__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
+    constexpr int NCH = DPAD / 4;
+    const uint32_t mask = ts.gmm_mask;
+    float m = -INFINITY, ssum = 0.f;
     if (NEED_SCORE) {
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) score[j] = 0.f;
     }
-    for (int k0 = 0; k0 < K8; k0 += 8) {
-        float l8[8];
-        lg.get8(k0, l8);
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+        const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
+        const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = k0 + q;
-            const float e = __expf(l8[q] - m);  // padded components: exp(-inf) = 0
-            ssum += e;
-            if (NEED_SCORE) {
-                // components whose responsibility underflows to 0 contribute exactly 0: skip them
-                // when that holds for the whole warp (bit-identical result).
-                if (__any_sync(0xffffffffu, e > 0.f)) {
-                    const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
-                    const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
-                    const float e2 = 2.0f * e;  // 1/var = 2h
+        for (int r0 = 0; r0 < NCH; r0 += 4) {
+            if ((mask >> r0) & 0xFu) {  // warp-uniform, two-level: 4 chunks, then each chunk
 #pragma unroll
-                    for (int r = 0; r < DPAD / 4; ++r) {
+                for (int r = r0; r < r0 + 4 && r < NCH; ++r) {
+                    if ((mask >> r) & 1u) {
                         const float4 mu = mu4[r], h = h4[r];
-                        score[4 * r + 0] = fmaf(e2 * h.x, mu.x - x[4 * r + 0], score[4 * r + 0]);
-                        score[4 * r + 1] = fmaf(e2 * h.y, mu.y - x[4 * r + 1], score[4 * r + 1]);
-                        score[4 * r + 2] = fmaf(e2 * h.z, mu.z - x[4 * r + 2], score[4 * r + 2]);
-                        score[4 * r + 3] = fmaf(e2 * h.w, mu.w - x[4 * r + 3], score[4 * r + 3]);
+                        const float d0 = x[4 * r + 0] - mu.x, d1 = x[4 * r + 1] - mu.y;
+                        const float d2 = x[4 * r + 2] - mu.z, d3 = x[4 * r + 3] - mu.w;
+                        a0 = fmaf(d0 * d0, h.x, a0);
+                        a1 = fmaf(d1 * d1, h.y, a1);
+                        a2 = fmaf(d2 * d2, h.z, a2);
+                        a3 = fmaf(d3 * d3, h.w, a3);
+                    }
+                }
+            }
+        }
+        const float l = ts.gmm_c[k] - ((a0 + a1) + (a2 + a3));
+        const float m_new = fmaxf(m, l);
+        const float rescale = __expf(m - m_new);  // 1 when the max did not move, 0 on the first component
+        const float e = __expf(l - m_new);
+        m = m_new;
+        ssum = fmaf(ssum, rescale, e);
+        if (NEED_SCORE) {
+            // the rescale must be applied whenever it is != 1; the accumulation can be skipped when this
+            // component's weight underflows to exactly 0 for the whole warp (bit-identical result)
+            const bool any_rescale = __any_sync(0xffffffffu, rescale != 1.0f);
+            const bool any_weight = __any_sync(0xffffffffu, e > 0.f);
+            if (any_rescale || any_weight) {
+                const float e2 = 2.0f * e;  // 1/var = 2h
+#pragma unroll
+                for (int r0 = 0; r0 < NCH; r0 += 4) {
+                    if ((mask >> r0) & 0xFu) {
+#pragma unroll
+                        for (int r = r0; r < r0 + 4 && r < NCH; ++r) {
+                            if ((mask >> r) & 1u) {
+                                const float4 mu = mu4[r], h = h4[r];
+                                score[4 * r + 0] = fmaf(e2 * h.x, mu.x - x[4 * r + 0], score[4 * r + 0] * rescale);
+                                score[4 * r + 1] = fmaf(e2 * h.y, mu.y - x[4 * r + 1], score[4 * r + 1] * rescale);
+                                score[4 * r + 2] = fmaf(e2 * h.z, mu.z - x[4 * r + 2], score[4 * r + 2] * rescale);
+                                score[4 * r + 3] = fmaf(e2 * h.w, mu.w - x[4 * r + 3], score[4 * r + 3] * rescale);
+                            }
+                        }
                     }
                 }
             }
         }
     }
-    if (NEED_SCORE) {
-        const float inv = 1.0f / ssum;
+    // chunks shared by all components (read from component 0)
+    const float inv = 1.0f / ssum;
+    float shared = 0.f;
+    const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu);
+    const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h);
 #pragma unroll
-        for (int j = 0; j < DPAD; ++j) score[j] *= inv;
+    for (int r = 0; r < NCH; ++r) {
+        if ((mask >> r) & 1u) {
+            if (NEED_SCORE) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) score[4 * r + q] *= inv;
+            }
+        } else {
+            const float4 mu = mu4[r], h = h4[r];
+            const float d0 = mu.x - x[4 * r + 0], d1 = mu.y - x[4 * r + 1];
+            const float d2 = mu.z - x[4 * r + 2], d3 = mu.w - x[4 * r + 3];
+            shared = fmaf(d0 * d0, h.x, shared);
+            shared = fmaf(d1 * d1, h.y, shared);
+            shared = fmaf(d2 * d2, h.z, shared);
+            shared = fmaf(d3 * d3, h.w, shared);
+            if (NEED_SCORE) {
+                score[4 * r + 0] = 2.0f * h.x * d0;
+                score[4 * r + 1] = 2.0f * h.y * d1;
+                score[4 * r + 2] = 2.0f * h.z * d2;
+                score[4 * r + 3] = 2.0f * h.w * d3;
+            }
+        }
     }
-    return m + logf(ssum);
+    return m + logf(ssum) - shared;
 }
 
 // MultiWell (distr/double_well.py:165-179; DoubleWell :39-45 is n_dw = d = 1).
@@ -154,12 +169,12 @@ __device__ __forceinline__ float funnel_eval(const float (&x)[DPAD], float (&sco
     return lp_first + lp_other;
 }
 
-template <int DPAD, bool NEED_SCORE, class Logits>
+template <int DPAD, bool NEED_SCORE>
 __device__ __forceinline__ float target_eval(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&score)[DPAD],
-                                             const TargetSmem& ts, const Logits& lbuf) {
+                                             const TargetSmem& ts) {
     float lp;
     if (d.target_kind == SDES_TARGET_GMM)
-        lp = gmm_eval<DPAD, NEED_SCORE, Logits>(x, score, ts, d.n_components, lbuf);
+        lp = gmm_eval<DPAD, NEED_SCORE>(x, score, ts, d.n_components);
     else if (d.target_kind == SDES_TARGET_MULTIWELL)
         lp = multiwell_eval<DPAD, NEED_SCORE>(x, score, d.dim, d.n_double_wells, d.separation, d.shift);
     else
@@ -183,10 +198,10 @@ __device__ __forceinline__ float diag_gauss_logp(const float (&x)[DPAD], const f
 // g = generative_ctrl(s, x) given nn = NN(s, x): ClippedCtrl reparam.py:35-36, ScoreCtrl
 // :78-83, LerpCtrl :131-162, LerpPriorCtrl :165-181, LerpTargetCtrl :184-200.
 // In: g[] holds the raw network output; out: g[] holds the control.
-template <int DPAD, class Logits>
+template <int DPAD>
 __device__ __forceinline__ void control_assemble(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&g)[DPAD],
                                                  const TargetSmem& ts, const float* __restrict__ gate_row,
-                                                 float sigma, float lerp_w, const Logits& lbuf) {
+                                                 float sigma, float lerp_w) {
     const float cm = d.clip_model, cs = d.clip_score;
     if (d.ctrl_kind == SDES_CTRL_CLIPPED) {
 #pragma unroll
@@ -195,7 +210,7 @@ __device__ __forceinline__ void control_assemble(const SdesRolloutDesc& d, const
     }
     float sc[DPAD];
     if (d.ctrl_kind != SDES_CTRL_LERP_PRIOR) {
-        target_eval<DPAD, true, Logits>(d, x, sc, ts, lbuf);
+        target_eval<DPAD, true>(d, x, sc, ts);
     } else {
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
@@ -244,7 +259,8 @@ __device__ __forceinline__ void step_update(const SdesRolloutDesc& d, float (&x)
 #pragma unroll
             for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < d.dim) ? noise_row[4 * q + r] : 0.f;
         } else {
-            normal4(d.seed, traj, (uint32_t)step, (uint32_t)q, e[0], e[1], e[2], e[3]);
+            const float4 n4 = normal4_call((uint32_t)d.seed, (uint32_t)(d.seed >> 32), traj, (uint32_t)step, (uint32_t)q);
+            e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
 #pragma unroll
             for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < d.dim) ? e[r] : 0.f;
         }
@@ -282,11 +298,10 @@ __device__ __forceinline__ float initial_rnd(const SdesRolloutDesc& d, const flo
 }
 
 // terminal cost (losses/oc.py:225, :337, :449-450; clip: solver/oc.py:48-54)
-template <int DPAD, class Logits>
-__device__ __forceinline__ float terminal_rnd(const SdesRolloutDesc& d, const float (&x)[DPAD], const TargetSmem& ts,
-                                              const Logits& lbuf) {
+template <int DPAD>
+__device__ __forceinline__ float terminal_rnd(const SdesRolloutDesc& d, const float (&x)[DPAD], const TargetSmem& ts) {
     float dummy[DPAD];
-    const float lp = clipf(target_eval<DPAD, false, Logits>(d, x, dummy, ts, lbuf), d.clip_target);
+    const float lp = clipf(target_eval<DPAD, false>(d, x, dummy, ts), d.clip_target);
     if (d.loss_kind == SDES_LOSS_TIME_REVERSAL) return -lp;
     return diag_gauss_logp<DPAD>(x, ts.ref) - lp;
 }

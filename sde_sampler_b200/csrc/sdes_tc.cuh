@@ -62,6 +62,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld fills its destination registers asynchronously; they may only be read after
+// tcgen05.wait::ld.  The compiler does not know that, so tie the registers to the wait: every
+// value passes through an asm statement that is ordered after the wait (volatile asms keep
+// their order), which keeps consumers from being scheduled above it.
+__device__ __forceinline__ void tie8(float* v) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+template <int N>
+__device__ __forceinline__ void wait_ld_tie(float (&v)[N]) {
+    wait_ld();
+#pragma unroll
+    for (int c = 0; c < N; c += 8) tie8(&v[c]);
+}
 __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 8 consecutive 32-bit columns of this thread's lane
