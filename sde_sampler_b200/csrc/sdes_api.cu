@@ -70,8 +70,8 @@ static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
     w.tab = take(T * TAB_STRIDE);
     w.emb = take(T * C);
     w.gate = take(T * dpad);
-    w.gmm_mu = take(K * dpad);
-    w.gmm_h = take(K * dpad);
+    w.gmm_mu = take(((K + 1) & ~1ll) * dpad);  // padded to an even number of components
+    w.gmm_h = take(((K + 1) & ~1ll) * dpad);
     w.gmm_c = take(64);
     w.prior = take(2 * dpad + 4);
     w.ref = take(2 * dpad + 4);

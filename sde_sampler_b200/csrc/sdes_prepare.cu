@@ -206,11 +206,11 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
 
     // GMM image (distr/gauss.py:119-140): mu, h = 0.5/scale^2, c_k = log w_k - sum log scale - d/2 log 2pi
     if (d.target_kind == SDES_TARGET_GMM) {
-        const int K = d.n_components;
-        for (int64_t e = gtid; e < (int64_t)K * dpad; e += nthreads) {
+        const int K = d.n_components, K2 = (K + 1) & ~1;
+        for (int64_t e = gtid; e < (int64_t)K2 * dpad; e += nthreads) {
             const int k = (int)(e / dpad), j = (int)(e % dpad);
             float mu = 0.f, h = 0.f;
-            if (j < dim) {
+            if (j < dim && k < K) {
                 mu = d.gmm_loc[(int64_t)k * dim + j];
                 const float sc = d.gmm_scale[(int64_t)k * dim + j];
                 h = 0.5f / (sc * sc);

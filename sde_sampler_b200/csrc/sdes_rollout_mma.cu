@@ -137,13 +137,12 @@ __device__ __forceinline__ void load_acc(uint32_t addr_d, float (&acc)[N]) {
 
 // 8 accumulator columns -> + bias -> exact GELU -> tf32 hi/lo split -> A operand of the next layer
 __device__ __forceinline__ void gelu_split_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8],
-                                                  const float* __restrict__ bias) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+                                                  const float4 b0, const float4 b1) {
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float a = gelu_erf(v[q] + bb[q]);
+        const float a = gelu_fast(v[q] + bb[q]);
         hi[q] = tc::tf32_hi_bits(a);
         lo[q] = __float_as_uint(a - __uint_as_float(hi[q]));
     }
@@ -186,14 +185,17 @@ __device__ __forceinline__ void run_layer(GroupCtx& c, uint32_t w_hi_saddr, uint
 __device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* __restrict__ bias) {
     float a[8], b[8];
     tc::tmem_ld8(c.l_d, a);
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll 1
     for (int ch = 0; ch < 8; ch += 2) {
+        // bias loads are issued before the wait so their latency hides behind the TMEM load
+        const float4 p0 = b4[2 * ch], p1 = b4[2 * ch + 1], p2 = b4[2 * ch + 2], p3 = b4[2 * ch + 3];
         tc::wait_ld_tie<8>(a);
         tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
-        gelu_split_store8(c.l_hi + 8u * ch, c.l_lo + 8u * ch, a, bias + 8 * ch);
+        gelu_split_store8(c.l_hi + 8u * ch, c.l_lo + 8u * ch, a, p0, p1);
         tc::wait_ld_tie<8>(b);
         if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
-        gelu_split_store8(c.l_hi + 8u * (ch + 1), c.l_lo + 8u * (ch + 1), b, bias + 8 * (ch + 1));
+        gelu_split_store8(c.l_hi + 8u * (ch + 1), c.l_lo + 8u * (ch + 1), b, p2, p3);
     }
 }
 
@@ -213,9 +215,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
 
     // ---- shared memory carve-up: [weight image + biases | gmm mu | gmm h | gmm c | prior | ref]
     float* s_w = smem;
+    const int K2 = (K + 1) & ~1;  // GMM images are padded to an even number of components
     float* s_mu = s_w + p.ws.w_mma_len;
-    float* s_h = s_mu + K * DPAD;
-    float* s_c = s_h + K * DPAD;
+    float* s_h = s_mu + K2 * DPAD;
+    float* s_c = s_h + K2 * DPAD;
     float* s_prior = s_c + 64;
     float* s_ref = s_prior + 2 * DPAD + 8;
 
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
             tc::bulk_g2s(dst + off, src + off, n, &s_wbar);
         }
     }
-    for (int e = tid; e < K * DPAD; e += blockDim.x) {
+    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
         s_mu[e] = ws[p.ws.gmm_mu + e];
         s_h[e] = ws[p.ws.gmm_h + e];
     }
@@ -304,26 +307,46 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
 
         for (int i = 0; i < T; ++i) {
             const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
-            float g[DPAD];
-            {
-                // ---- control MLP on the tensor cores (models/mlp.py:114-122)
-                store_a_split<DPAD>(c.l_hi, c.l_lo, x);
-                run_layer(c, l0_hi, l0_lo, DPAD, C);
-                layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
+            // ---- score part of the control (needs x only): before the MLP, kept in registers
+            float sc[DPAD];
+            score_part<DPAD>(d, x, sc, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
+            // ---- control MLP on the tensor cores (models/mlp.py:114-122)
+            store_a_split<DPAD>(c.l_hi, c.l_lo, x);
+            run_layer(c, l0_hi, l0_lo, DPAD, C);
+            layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
 #pragma unroll 1
-                for (int l = 0; l < nh; ++l) {
-                    run_layer(c, lh_base + (uint32_t)l * 32768u, lh_base + (uint32_t)l * 32768u + 16384u, C, C);
-                    layer_epilogue(c, s_bias + l * C);
-                }
-                run_layer(c, lo_hi, lo_lo, C, NOUT);
-                load_acc<DPAD>(c.l_d, g);
-                const float* bo = s_bias + nh * C;
-#pragma unroll
-                for (int j = 0; j < DPAD; ++j) g[j] += bo[j];
+            for (int l = 0; l < nh; ++l) {
+                run_layer(c, lh_base + (uint32_t)l * 32768u, lh_base + (uint32_t)l * 32768u + 16384u, C, C);
+                layer_epilogue(c, s_bias + l * C);
             }
-            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
-            const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
-            step_update<DPAD>(d, x, g, rnd, tsm, tab, i, traj, nrow);
+            run_layer(c, lo_hi, lo_lo, C, NOUT);
+            // ---- network output streamed from TMEM into the control / cost / state update
+            {
+                const StepCoef sc_ = make_step_coef(d, tab);
+                const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
+                const float* bo = s_bias + nh * C;
+                float cost = 0.f, ito = 0.f;
+                float na[8], nb[8];
+                tc::tmem_ld8(c.l_d, na);
+#pragma unroll
+                for (int q = 0; q < DPAD / 8; q += 2) {
+                    tc::wait_ld_tie<8>(na);
+                    if (q + 1 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 1), nb);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) na[r] += bo[8 * q + r];
+                    update4(sc_, &x[8 * q], &na[0], &sc[8 * q], s_prior + 8 * q, s_prior + DPAD + 8 * q, 8 * q, i, traj, nrow, cost, ito);
+                    update4(sc_, &x[8 * q + 4], &na[4], &sc[8 * q + 4], s_prior + 8 * q + 4, s_prior + DPAD + 8 * q + 4, 8 * q + 4, i, traj, nrow, cost, ito);
+                    if (q + 1 < DPAD / 8) {
+                        tc::wait_ld_tie<8>(nb);
+                        if (q + 2 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 2), na);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) nb[r] += bo[8 * (q + 1) + r];
+                        update4(sc_, &x[8 * q + 8], &nb[0], &sc[8 * q + 8], s_prior + 8 * q + 8, s_prior + DPAD + 8 * q + 8, 8 * q + 8, i, traj, nrow, cost, ito);
+                        update4(sc_, &x[8 * q + 12], &nb[4], &sc[8 * q + 12], s_prior + 8 * q + 12, s_prior + DPAD + 8 * q + 12, 8 * q + 12, i, traj, nrow, cost, ito);
+                    }
+                }
+                finish_step(d, sc_, tab, cost, ito, rnd);
+            }
             if (ret_traj && valid) {
                 float* o = d.xs + ((int64_t)(i + 1) * B + rrow) * dim;
 #pragma unroll
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
 
 size_t mma_smem_bytes(const KParams& p) {
     const int dpad = p.ws.dpad, K = p.d.n_components;
-    const size_t fl = (size_t)p.ws.w_mma_len + 2 * (size_t)K * dpad + 64 + 2 * (2 * dpad + 8);
+    const size_t fl = (size_t)p.ws.w_mma_len + 2 * (size_t)((K + 1) & ~1) * dpad + 64 + 2 * (2 * dpad + 8);
     return fl * sizeof(float);
 }
 

@@ -96,14 +96,15 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
 
     // ---- shared memory carve-up
     float* s_w = smem;
+    const int K2 = (K + 1) & ~1;  // GMM images are padded to an even number of components
     float* s_mu = s_w + ((p.ws.w_simt_len + 3) & ~3ll);
-    float* s_h = s_mu + K * DPAD;
-    float* s_c = s_h + K * DPAD;
+    float* s_h = s_mu + K2 * DPAD;
+    float* s_c = s_h + K2 * DPAD;
     float* s_prior = s_c + 64;
     float* s_ref = s_prior + 2 * DPAD + 4;
     float* s_act = s_ref + 2 * DPAD + 4;
     for (int64_t e = tid; e < p.ws.w_simt_len; e += blockDim.x) s_w[e] = ws[p.ws.w_simt + e];
-    for (int e = tid; e < K * DPAD; e += blockDim.x) {
+    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
         s_mu[e] = ws[p.ws.gmm_mu + e];
         s_h[e] = ws[p.ws.gmm_h + e];
     }
@@ -142,11 +143,16 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
 
         for (int i = 0; i < T; ++i) {
             const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
-            float g[DPAD];
+            float sc[DPAD], g[DPAD];
+            score_part<DPAD>(d, x, sc, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
             mlp_simt<DPAD>(x, g, s_w, ws + p.ws.emb + (int64_t)i * C, act, dim, d.n_hidden);
-            control_assemble<DPAD>(d, x, g, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
+            const StepCoef sc_ = make_step_coef(d, tab);
             const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
-            step_update<DPAD>(d, x, g, rnd, tsm, tab, i, traj, nrow);
+            float cost = 0.f, ito = 0.f;
+#pragma unroll
+            for (int q = 0; q < DPAD / 4; ++q)
+                update4(sc_, &x[4 * q], &g[4 * q], &sc[4 * q], s_prior + 4 * q, s_prior + DPAD + 4 * q, 4 * q, i, traj, nrow, cost, ito);
+            finish_step(d, sc_, tab, cost, ito, rnd);
             if (ret_traj && valid) {
                 float* o = d.xs + ((int64_t)(i + 1) * B + rrow) * dim;
 #pragma unroll
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
 
 size_t simt_smem_bytes(const KParams& p) {
     const int dpad = p.ws.dpad, K = p.d.n_components;
-    size_t fl = ((p.ws.w_simt_len + 3) & ~3ll) + 2 * (size_t)K * dpad + 64 + 2 * (2 * dpad + 4) + (size_t)SIMT_WARPS * C * 32;
+    size_t fl = ((p.ws.w_simt_len + 3) & ~3ll) + 2 * (size_t)((K + 1) & ~1) * dpad + 64 + 2 * (2 * dpad + 4) + (size_t)SIMT_WARPS * C * 32;
     return fl * sizeof(float);
 }
 

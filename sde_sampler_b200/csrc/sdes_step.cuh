@@ -35,97 +35,110 @@ struct TargetSmem {
 //     log rho(x) = logsumexp_k [ c_k - sum_{j in active} h_kj (x_j - mu_kj)^2 ] - sum_{j shared} h_j (x_j - mu_j)^2
 //     score_j    = 2 h_j (mu_j - x_j)                                            for shared j
 // so they cost O(d) instead of O(K d) (e.g. the zero-padded dims of GMM-40 in d=50).
-template <int DPAD, bool NEED_SCORE>
-__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
+// NA = number of leading chunks handled as "active" (a compile-time prefix, chosen by the caller
+// to cover the highest set bit of the mask, so the inner loops carry no per-chunk tests).
+// Components are processed two at a time (independent accumulators) for instruction-level
+// parallelism; the images are padded to an even K with h = 0, c = -inf.
+template <int DPAD, int NA, bool NEED_SCORE, bool TWO = (NA <= 4)>
+__device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
     constexpr int NCH = DPAD / 4;
-    const uint32_t mask = ts.gmm_mask;
     float m = -INFINITY, ssum = 0.f;
     if (NEED_SCORE) {
 #pragma unroll
-        for (int j = 0; j < DPAD; ++j) score[j] = 0.f;
+        for (int j = 0; j < 4 * NA; ++j) score[j] = 0.f;
     }
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-        const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
-        const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < K; k += (TWO ? 2 : 1)) {
+        const float4* mu4a = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
+        const float4* h4a = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
+        const float4* mu4b = mu4a + NCH;
+        const float4* h4b = h4a + NCH;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-        for (int r0 = 0; r0 < NCH; r0 += 4) {
-            if ((mask >> r0) & 0xFu) {  // warp-uniform, two-level: 4 chunks, then each chunk
-#pragma unroll
-                for (int r = r0; r < r0 + 4 && r < NCH; ++r) {
-                    if ((mask >> r) & 1u) {
-                        const float4 mu = mu4[r], h = h4[r];
-                        const float d0 = x[4 * r + 0] - mu.x, d1 = x[4 * r + 1] - mu.y;
-                        const float d2 = x[4 * r + 2] - mu.z, d3 = x[4 * r + 3] - mu.w;
-                        a0 = fmaf(d0 * d0, h.x, a0);
-                        a1 = fmaf(d1 * d1, h.y, a1);
-                        a2 = fmaf(d2 * d2, h.z, a2);
-                        a3 = fmaf(d3 * d3, h.w, a3);
-                    }
-                }
+        for (int r = 0; r < NA; ++r) {
+            const float4 mu = mu4a[r], h = h4a[r];
+            const float d0 = x[4 * r + 0] - mu.x, d1 = x[4 * r + 1] - mu.y;
+            const float d2 = x[4 * r + 2] - mu.z, d3 = x[4 * r + 3] - mu.w;
+            a0 = fmaf(d0 * d0, h.x, a0);
+            a1 = fmaf(d1 * d1, h.y, a1);
+            a0 = fmaf(d2 * d2, h.z, a0);
+            a1 = fmaf(d3 * d3, h.w, a1);
+            if (TWO) {
+                const float4 nu = mu4b[r], g = h4b[r];
+                const float f0 = x[4 * r + 0] - nu.x, f1 = x[4 * r + 1] - nu.y;
+                const float f2 = x[4 * r + 2] - nu.z, f3 = x[4 * r + 3] - nu.w;
+                b0 = fmaf(f0 * f0, g.x, b0);
+                b1 = fmaf(f1 * f1, g.y, b1);
+                b0 = fmaf(f2 * f2, g.z, b0);
+                b1 = fmaf(f3 * f3, g.w, b1);
             }
         }
-        const float l = ts.gmm_c[k] - ((a0 + a1) + (a2 + a3));
-        const float m_new = fmaxf(m, l);
-        const float rescale = __expf(m - m_new);  // 1 when the max did not move, 0 on the first component
-        const float e = __expf(l - m_new);
+        const float la = ts.gmm_c[k] - (a0 + a1), lb = TWO ? ts.gmm_c[k + 1] - (b0 + b1) : -INFINITY;
+        const float m_new = fmaxf(m, fmaxf(la, lb));
+        const float rescale = __expf(m - m_new);  // 1 when the max did not move, 0 on the first pair
+        const float ea = __expf(la - m_new), eb = TWO ? __expf(lb - m_new) : 0.f;
         m = m_new;
-        ssum = fmaf(ssum, rescale, e);
+        ssum = fmaf(ssum, rescale, ea + eb);
         if (NEED_SCORE) {
-            // the rescale must be applied whenever it is != 1; the accumulation can be skipped when this
-            // component's weight underflows to exactly 0 for the whole warp (bit-identical result)
-            const bool any_rescale = __any_sync(0xffffffffu, rescale != 1.0f);
-            const bool any_weight = __any_sync(0xffffffffu, e > 0.f);
-            if (any_rescale || any_weight) {
-                const float e2 = 2.0f * e;  // 1/var = 2h
+            // the rescale must be applied whenever it is != 1; the accumulation can be skipped when both
+            // weights underflow to exactly 0 for the whole warp (bit-identical result)
+            if (__any_sync(0xffffffffu, rescale != 1.0f || ea > 0.f || eb > 0.f)) {
+                const float ea2 = 2.0f * ea, eb2 = 2.0f * eb;  // 1/var = 2h
 #pragma unroll
-                for (int r0 = 0; r0 < NCH; r0 += 4) {
-                    if ((mask >> r0) & 0xFu) {
-#pragma unroll
-                        for (int r = r0; r < r0 + 4 && r < NCH; ++r) {
-                            if ((mask >> r) & 1u) {
-                                const float4 mu = mu4[r], h = h4[r];
-                                score[4 * r + 0] = fmaf(e2 * h.x, mu.x - x[4 * r + 0], score[4 * r + 0] * rescale);
-                                score[4 * r + 1] = fmaf(e2 * h.y, mu.y - x[4 * r + 1], score[4 * r + 1] * rescale);
-                                score[4 * r + 2] = fmaf(e2 * h.z, mu.z - x[4 * r + 2], score[4 * r + 2] * rescale);
-                                score[4 * r + 3] = fmaf(e2 * h.w, mu.w - x[4 * r + 3], score[4 * r + 3] * rescale);
-                            }
-                        }
+                for (int r = 0; r < NA; ++r) {
+                    const float4 mu = mu4a[r], h = h4a[r];
+                    score[4 * r + 0] = fmaf(ea2 * h.x, mu.x - x[4 * r + 0], score[4 * r + 0] * rescale);
+                    score[4 * r + 1] = fmaf(ea2 * h.y, mu.y - x[4 * r + 1], score[4 * r + 1] * rescale);
+                    score[4 * r + 2] = fmaf(ea2 * h.z, mu.z - x[4 * r + 2], score[4 * r + 2] * rescale);
+                    score[4 * r + 3] = fmaf(ea2 * h.w, mu.w - x[4 * r + 3], score[4 * r + 3] * rescale);
+                    if (TWO) {
+                        const float4 nu = mu4b[r], g = h4b[r];
+                        score[4 * r + 0] = fmaf(eb2 * g.x, nu.x - x[4 * r + 0], score[4 * r + 0]);
+                        score[4 * r + 1] = fmaf(eb2 * g.y, nu.y - x[4 * r + 1], score[4 * r + 1]);
+                        score[4 * r + 2] = fmaf(eb2 * g.z, nu.z - x[4 * r + 2], score[4 * r + 2]);
+                        score[4 * r + 3] = fmaf(eb2 * g.w, nu.w - x[4 * r + 3], score[4 * r + 3]);
                     }
                 }
             }
         }
     }
+    if (NEED_SCORE) {
+        const float inv = 1.0f / ssum;
+#pragma unroll
+        for (int j = 0; j < 4 * NA; ++j) score[j] *= inv;
+    }
     // chunks shared by all components (read from component 0)
-    const float inv = 1.0f / ssum;
     float shared = 0.f;
     const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu);
     const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h);
 #pragma unroll
-    for (int r = 0; r < NCH; ++r) {
-        if ((mask >> r) & 1u) {
-            if (NEED_SCORE) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) score[4 * r + q] *= inv;
-            }
-        } else {
-            const float4 mu = mu4[r], h = h4[r];
-            const float d0 = mu.x - x[4 * r + 0], d1 = mu.y - x[4 * r + 1];
-            const float d2 = mu.z - x[4 * r + 2], d3 = mu.w - x[4 * r + 3];
-            shared = fmaf(d0 * d0, h.x, shared);
-            shared = fmaf(d1 * d1, h.y, shared);
-            shared = fmaf(d2 * d2, h.z, shared);
-            shared = fmaf(d3 * d3, h.w, shared);
-            if (NEED_SCORE) {
-                score[4 * r + 0] = 2.0f * h.x * d0;
-                score[4 * r + 1] = 2.0f * h.y * d1;
-                score[4 * r + 2] = 2.0f * h.z * d2;
-                score[4 * r + 3] = 2.0f * h.w * d3;
-            }
+    for (int r = NA; r < NCH; ++r) {
+        const float4 mu = mu4[r], h = h4[r];
+        const float d0 = mu.x - x[4 * r + 0], d1 = mu.y - x[4 * r + 1];
+        const float d2 = mu.z - x[4 * r + 2], d3 = mu.w - x[4 * r + 3];
+        shared = fmaf(d0 * d0, h.x, shared);
+        shared = fmaf(d1 * d1, h.y, shared);
+        shared = fmaf(d2 * d2, h.z, shared);
+        shared = fmaf(d3 * d3, h.w, shared);
+        if (NEED_SCORE) {
+            score[4 * r + 0] = 2.0f * h.x * d0;
+            score[4 * r + 1] = 2.0f * h.y * d1;
+            score[4 * r + 2] = 2.0f * h.z * d2;
+            score[4 * r + 3] = 2.0f * h.w * d3;
         }
     }
     return m + logf(ssum) - shared;
+}
+
+template <int DPAD, bool NEED_SCORE>
+__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
+    constexpr int NCH = DPAD / 4;
+    const uint32_t mask = ts.gmm_mask;  // warp-uniform
+    if (NCH > 1 && mask < 2u) return gmm_eval_na<DPAD, 1, NEED_SCORE>(x, score, ts, K);
+    if (NCH > 2 && mask < 4u) return gmm_eval_na<DPAD, (NCH > 2 ? 2 : NCH), NEED_SCORE>(x, score, ts, K);
+    if (NCH > 4 && mask < 16u) return gmm_eval_na<DPAD, (NCH > 4 ? 4 : NCH), NEED_SCORE>(x, score, ts, K);
+    if (NCH > 8 && mask < 256u) return gmm_eval_na<DPAD, (NCH > 8 ? 8 : NCH), NEED_SCORE>(x, score, ts, K);
+    return gmm_eval_na<DPAD, NCH, NEED_SCORE>(x, score, ts, K);
 }
 
 // MultiWell (distr/double_well.py:165-179; DoubleWell :39-45 is n_dw = d = 1).
@@ -195,28 +208,29 @@ __device__ __forceinline__ float diag_gauss_logp(const float (&x)[DPAD], const f
 }
 
 // ------------------------------------------------------------------------------- control
-// g = generative_ctrl(s, x) given nn = NN(s, x): ClippedCtrl reparam.py:35-36, ScoreCtrl
-// :78-83, LerpCtrl :131-162, LerpPriorCtrl :165-181, LerpTargetCtrl :184-200.
-// In: g[] holds the raw network output; out: g[] holds the control.
+// generative_ctrl(s, x) = clip(NN(s, x), clip_model) + score_part(s, x)   (models/reparam.py):
+//   ClippedCtrl :35-36     score_part = 0
+//   ScoreCtrl   :78-83     scale_score * clip(grad log rho(x), clip_score) * gate(s)
+//   LerpCtrl    :131-162   sigma(s) * scale_score * clip(lerp(grad log p_prior, grad log rho, s/T), clip_score) * gate(s)
+//   LerpPriorCtrl :165-181 / LerpTargetCtrl :184-200: only the prior / target end of the lerp.
+// score_part depends on x but not on the network, so it is evaluated BEFORE the MLP and kept in
+// registers (sc[]); the network output is then streamed out of TMEM 8 columns at a time straight
+// into the state update, and the full control vector never has to be materialised.
 template <int DPAD>
-__device__ __forceinline__ void control_assemble(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&g)[DPAD],
-                                                 const TargetSmem& ts, const float* __restrict__ gate_row,
-                                                 float sigma, float lerp_w) {
-    const float cm = d.clip_model, cs = d.clip_score;
+__device__ __forceinline__ void score_part(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&sc)[DPAD],
+                                           const TargetSmem& ts, const float* __restrict__ gate_row, float sigma,
+                                           float lerp_w) {
     if (d.ctrl_kind == SDES_CTRL_CLIPPED) {
 #pragma unroll
-        for (int j = 0; j < DPAD; ++j) g[j] = clipf(g[j], cm);
+        for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
         return;
     }
-    float sc[DPAD];
     if (d.ctrl_kind != SDES_CTRL_LERP_PRIOR) {
         target_eval<DPAD, true>(d, x, sc, ts);
     } else {
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
     }
-    const float mult = d.ctrl_kind == SDES_CTRL_SCORE ? d.scale_score : d.scale_score;
-    const float outer = d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : sigma;
     const float* pl = ts.prior;
     if (d.ctrl_kind == SDES_CTRL_LERP) {
 #pragma unroll
@@ -228,63 +242,79 @@ __device__ __forceinline__ void control_assemble(const SdesRolloutDesc& d, const
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) sc[j] = lerp_w * sc[j];
     }
+    const float cs = d.clip_score;
+    const float outer = d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : sigma;
 #pragma unroll
-    for (int j = 0; j < DPAD; ++j) {
-        const float s = mult * clipf(sc[j], cs) * gate_row[j];
-        g[j] = clipf(g[j], cm) + outer * s;
-    }
+    for (int j = 0; j < DPAD; ++j) sc[j] = outer * (d.scale_score * clipf(sc[j], cs) * gate_row[j]);
 }
 
 // ---------------------------------------------------------------------------------- step
-// Cost increments + noise + state update for one step, given the control g.
+// Per-step scalars shared by all dimensions of a trajectory.
+struct StepCoef {
+    float dt, sqrt_dt, mu, sigma, beta_k, alpha_k, bb_ss, s_bk, sg, cm;
+    bool exp_int, ref_ctrl, from_hbm;
+    uint32_t k0, k1;  // Philox key
+    int dim;
+};
+
+__device__ __forceinline__ StepCoef make_step_coef(const SdesRolloutDesc& d, const float* __restrict__ tab) {
+    StepCoef c;
+    c.dt = tab[TAB_DT]; c.sqrt_dt = tab[TAB_SQRT_DT]; c.mu = tab[TAB_MU]; c.sigma = tab[TAB_SIGMA];
+    c.beta_k = tab[TAB_BETA_K]; c.alpha_k = tab[TAB_ALPHA_K];
+    c.sg = d.sigma;
+    c.bb_ss = (c.beta_k * c.beta_k) * (c.sg * c.sg);
+    c.s_bk = c.sg * c.beta_k;
+    c.cm = d.clip_model;
+    c.exp_int = d.loss_kind == SDES_LOSS_EXP_INTEGRATOR;
+    c.ref_ctrl = (d.flags & SDES_F_REFERENCE_CTRL) != 0;
+    c.from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
+    c.k0 = (uint32_t)d.seed; c.k1 = (uint32_t)(d.seed >> 32);
+    c.dim = d.dim;
+    return c;
+}
+
+// Four dimensions j0..j0+3 of one trajectory: assemble the control from the raw network output
+// nn (bias included) and the precomputed score part, draw the noise, accumulate the cost / Ito
+// sums and advance the state.
 //   TimeReversalLoss  losses/oc.py:204-219   ReferenceSDELoss :316-331   ExponentialIntegrator :429-443
-template <int DPAD>
-__device__ __forceinline__ void step_update(const SdesRolloutDesc& d, float (&x)[DPAD], const float (&g)[DPAD],
-                                            float& rnd, const TargetSmem& ts, const float* __restrict__ tab,
-                                            int step, uint32_t traj, const float* __restrict__ noise_row) {
-    const float dt = tab[TAB_DT], sqrt_dt = tab[TAB_SQRT_DT], mu = tab[TAB_MU], sigma = tab[TAB_SIGMA];
-    const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
-    const bool exp_int = d.loss_kind == SDES_LOSS_EXP_INTEGRATOR;
-    const bool ref_ctrl = (d.flags & SDES_F_REFERENCE_CTRL) != 0;
-    const float beta_k = tab[TAB_BETA_K], alpha_k = tab[TAB_ALPHA_K];
-    const float sg = d.sigma;
-    const float bb_ss = (beta_k * beta_k) * (sg * sg);
-    const float s_bk = sg * beta_k;
-    const float* pl = ts.prior;
-    float cost = 0.f, ito = 0.f;
+__device__ __forceinline__ void update4(const StepCoef& c, float* __restrict__ x4, const float* __restrict__ nn4,
+                                        const float* __restrict__ sc4, const float* __restrict__ prior_loc4,
+                                        const float* __restrict__ prior_iv4, int j0, int step, uint32_t traj,
+                                        const float* __restrict__ noise_row, float& cost, float& ito) {
+    float e[4];
+    if (c.from_hbm) {
 #pragma unroll
-    for (int q = 0; q < DPAD / 4; ++q) {
-        float e[4];
-        if (from_hbm) {
+        for (int r = 0; r < 4; ++r) e[r] = (j0 + r < c.dim) ? noise_row[j0 + r] : 0.f;
+    } else {
+        const float4 n4 = normal4_call(c.k0, c.k1, traj, (uint32_t)step, (uint32_t)(j0 >> 2));
+        e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < d.dim) ? noise_row[4 * q + r] : 0.f;
+        for (int r = 0; r < 4; ++r) e[r] = (j0 + r < c.dim) ? e[r] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float g = clipf(nn4[r], c.cm) + sc4[r];
+        if (c.exp_int) {
+            cost = fmaf(g, g, cost);
+            ito = fmaf(c.sg * g * e[r], c.beta_k, ito);
+            x4[r] = x4[r] * c.alpha_k + c.bb_ss * g + c.s_bk * e[r];
         } else {
-            const float4 n4 = normal4_call((uint32_t)d.seed, (uint32_t)(d.seed >> 32), traj, (uint32_t)step, (uint32_t)q);
-            e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < d.dim) ? e[r] : 0.f;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int j = 4 * q + r;
-            if (exp_int) {
-                cost = fmaf(g[j], g[j], cost);
-                ito = fmaf(sg * g[j] * e[r], beta_k, ito);
-                x[j] = x[j] * alpha_k + bb_ss * g[j] + s_bk * e[r];
-            } else {
-                float gm = g[j];
-                if (ref_ctrl) gm -= sigma * ((pl[j] - x[j]) * pl[DPAD + j]);  // solver/oc.py:305-306
-                const float db = e[r] * sqrt_dt;
-                cost = fmaf(gm, gm, cost);
-                ito = fmaf(gm, db, ito);
-                x[j] = x[j] + (mu * x[j] + sigma * g[j]) * dt + sigma * db;
-            }
+            float gm = g;
+            if (c.ref_ctrl) gm -= c.sigma * ((prior_loc4[r] - x4[r]) * prior_iv4[r]);  // solver/oc.py:305-306
+            const float db = e[r] * c.sqrt_dt;
+            cost = fmaf(gm, gm, cost);
+            ito = fmaf(gm, db, ito);
+            x4[r] = x4[r] + (c.mu * x4[r] + c.sigma * g) * c.dt + c.sigma * db;
         }
     }
-    if (exp_int) {
-        rnd += bb_ss * (0.5f * cost);
+}
+
+__device__ __forceinline__ void finish_step(const SdesRolloutDesc& d, const StepCoef& c, const float* __restrict__ tab,
+                                            float cost, float ito, float& rnd) {
+    if (c.exp_int) {
+        rnd += c.bb_ss * (0.5f * cost);
     } else {
-        rnd += 0.5f * cost * dt;
+        rnd += 0.5f * cost * c.dt;
         if (d.flags & SDES_F_SUB_DIV_INT) rnd -= tab[TAB_DIV_INT];
     }
     if (d.flags & SDES_F_COMPUTE_ITO) rnd += ito;
