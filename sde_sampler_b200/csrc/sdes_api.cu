@@ -81,6 +81,9 @@ static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
     w.w_mma_len = simt ? 0 : mma_weight_image_floats(d, dpad);
     w.w_mma = take(w.w_mma_len);
     w.counter = take(4);
+    const int64_t tiles128 = simt ? 0 : (d.batch + 127) / 128;
+    w.progress = take(tiles128);
+    w.state = take(tiles128 * (dpad + 1) * 128);
     w.total = o;
 }
 
@@ -272,12 +275,23 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
         return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, (size_t)p.ws.total * sizeof(float));
     if (desc->batch == 0) return 0;
     p.n_tiles = (int)((desc->batch + 31) / 32);
+    const int sms = sm_count_cached();
+    {
+        // time-chunked scheduling of the tcgen05 engine: aim for >= 8 work items per resident group,
+        // chunks of at least 8 steps (state parks in L2 between chunks: ~29 KB per item each way)
+        const int64_t tiles128 = (desc->batch + 127) / 128, groups = 2ll * sms;
+        int64_t nc = (8 * groups + tiles128 - 1) / tiles128;
+        const int64_t nc_max = desc->n_steps / 8 > 0 ? desc->n_steps / 8 : 1;
+        if (nc > nc_max) nc = nc_max;
+        if (nc < 1) nc = 1;
+        p.chunk_steps = (int)((desc->n_steps + nc - 1) / nc);
+        p.n_chunks = (desc->n_steps + p.chunk_steps - 1) / p.chunk_steps;
+    }
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     launch_prepare(p, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "prepare kernel launch failed: %s", cudaGetErrorString(e));
     g_launches++;
-    const int sms = sm_count_cached();
     if (desc->flags & SDES_F_MLP_SIMT) {
         e = launch_rollout_simt(p, sms, stream);
     } else {

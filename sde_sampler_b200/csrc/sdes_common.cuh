@@ -32,7 +32,9 @@ struct WsLayout {
     int64_t w_simt_len;
     int64_t w_mma;     // tcgen05 operand images (see sdes_rollout_mma.cu)
     int64_t w_mma_len;
-    int64_t counter;   // 4 uint32: dynamic tile counter
+    int64_t counter;   // 4 uint32: dynamic work counter, GMM chunk mask
+    int64_t progress;  // n_tiles128 uint32: completed time chunks per tile   (tcgen05 engine)
+    int64_t state;     // n_tiles128 * (dpad+1) * 128: parked tile state between time chunks
     int64_t total;     // floats
 };
 
@@ -49,7 +51,9 @@ struct KParams {
     SdesRolloutDesc d;
     WsLayout ws;
     BlobLayout bl;
-    int n_tiles;  // warp tiles of 32 trajectories
+    int n_tiles;      // warp tiles of 32 trajectories
+    int n_chunks;     // tcgen05 engine: time chunks per tile
+    int chunk_steps;  // steps per chunk
 };
 
 __host__ __device__ inline int pad_dim(int d) {

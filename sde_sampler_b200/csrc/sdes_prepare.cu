@@ -143,6 +143,13 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
         ctr[1] = mask;
     }
 
+    // per-tile progress words of the time-chunked scheduler
+    if (!(d.flags & SDES_F_MLP_SIMT)) {
+        uint32_t* prog = reinterpret_cast<uint32_t*>(ws + p.ws.progress);
+        const int64_t tiles128 = (d.batch + 127) / 128;
+        for (int64_t e = gtid; e < tiles128; e += nthreads) prog[e] = 0u;
+    }
+
     // tcgen05 weight images (layout: sdes_tc.cuh wimg_offset_floats; order: sdes_rollout_mma.cu):
     // every weight split into tf32 hi (truncated) and lo = w - hi, zero-padded to the MMA shapes.
     if (!(d.flags & SDES_F_MLP_SIMT)) {

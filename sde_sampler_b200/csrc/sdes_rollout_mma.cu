@@ -16,7 +16,10 @@
 
 namespace sdes {
 
-constexpr int MMA_GROUPS = 2;
+#ifndef SDES_MMA_GROUPS
+#define SDES_MMA_GROUPS 2
+#endif
+constexpr int MMA_GROUPS = SDES_MMA_GROUPS;
 constexpr int MMA_THREADS = MMA_GROUPS * 128;
 constexpr int TMEM_COLS = 512;
 constexpr int GROUP_COLS = 256;  // D[64] | A_hi[64] | A_lo[64] | spare[64]
@@ -285,27 +288,55 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
     const int64_t B = d.batch;
     const uint32_t n_tiles = (uint32_t)((B + 127) / 128);
 
+    // Work items are (time chunk, tile) pairs handed out chunk-major from one counter: a tile's T steps
+    // are cut into n_chunks pieces so that 512 tiles on 296 groups do not quantise into 2 rounds with
+    // the second 73% full.  Between chunks the tile's state (x, rnd) parks in the workspace
+    // ([tile][j][128] so warps read and write whole 128-byte lines) and a per-tile progress word orders
+    // producer and consumer.  An item only ever waits on an item handed out earlier, so there is no
+    // deadlock whatever the residency.
+    const int n_chunks = p.n_chunks, chunk_steps = p.chunk_steps;
+    const uint32_t n_items = n_tiles * (uint32_t)n_chunks;
+    float* state = const_cast<float*>(ws) + p.ws.state;
+    uint32_t* progress = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.progress);
     for (;;) {
         if (c.gtid == 0) s_tile[c.g] = atomicAdd(counter, 1u);
         group_bar(c.g);
-        const uint32_t tile = s_tile[c.g];
-        if (tile >= n_tiles) break;
+        const uint32_t item = s_tile[c.g];
+        if (item >= n_items) break;
+        const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
         const int64_t row = (int64_t)tile * 128 + c.gtid;
         const bool valid = row < B;
         const int64_t rrow = valid ? row : (B - 1);
+        float* st = state + (int64_t)tile * (DPAD + 1) * 128 + c.gtid;
 
         float x[DPAD];
+        float rnd;
+        if (chunk == 0) {
 #pragma unroll
-        for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
-        if (ret_traj && valid) {
+            for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
+            if (ret_traj && valid) {
 #pragma unroll
-            for (int j = 0; j < DPAD; ++j)
-                if (j < dim) d.xs[rrow * dim + j] = x[j];
+                for (int j = 0; j < DPAD; ++j)
+                    if (j < dim) d.xs[rrow * dim + j] = x[j];
+            }
+            rnd = initial_rnd<DPAD>(d, x, tsm);
+        } else {
+            if (c.gtid == 0) {
+                uint32_t seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
+                } while (seen < chunk);
+            }
+            group_bar(c.g);
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) x[j] = __ldcg(st + j * 128);  // L2 reads: another SM wrote them
+            rnd = __ldcg(st + DPAD * 128);
         }
-        float rnd = initial_rnd<DPAD>(d, x, tsm);
         const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)rrow);
+        const int i_begin = (int)chunk * chunk_steps;
+        const int i_end = (i_begin + chunk_steps < T) ? i_begin + chunk_steps : T;
 
-        for (int i = 0; i < T; ++i) {
+        for (int i = i_begin; i < i_end; ++i) {
             const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
             // ---- score part of the control (needs x only): before the MLP, kept in registers
             float sc[DPAD];
@@ -354,12 +385,21 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
                     if (j < dim) o[j] = x[j];
             }
         }
-        rnd += terminal_rnd<DPAD>(d, x, tsm);
-        if (valid) {
+        if (i_end == T) {
+            rnd += terminal_rnd<DPAD>(d, x, tsm);
+            if (valid) {
 #pragma unroll
-            for (int j = 0; j < DPAD; ++j)
-                if (j < dim) d.x_T[rrow * dim + j] = x[j];
-            d.rnd[rrow] = rnd;
+                for (int j = 0; j < DPAD; ++j)
+                    if (j < dim) d.x_T[rrow * dim + j] = x[j];
+                d.rnd[rrow] = rnd;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) __stcg(st + j * 128, x[j]);
+            __stcg(st + DPAD * 128, rnd);
+            __threadfence();
+            group_bar(c.g);
+            if (c.gtid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(chunk + 1u) : "memory");
         }
     }
     tc::fence_before();
