@@ -148,8 +148,9 @@ int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32
 
 /* Tensor-core self test: D[128,N] = A[128,K] * W[N,K]^T through the rollout's own tcgen05 path
  * (A staged into TMEM with tcgen05.st, W image in shared memory, 3xTF32 issue, tcgen05.ld).
- * K multiple of 8 in [8,64], N multiple of 16 in [16,64].  Test hook. */
-int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, void* stream);
+ * K multiple of 8 in [8,64], N multiple of 16 in [16,64].  mode 0 = 3xTF32 split,
+ * mode 1 = tf32 hi*hi + hi*lo plus a bf16 lo*w term (the rollout's layer).  Test hook. */
+int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, int32_t mode, void* stream);
 
 /* Kernel launches performed by this process through the library since load (for bench accounting). */
 int64_t sdes_launch_count(void);

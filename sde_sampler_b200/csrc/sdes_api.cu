@@ -14,7 +14,8 @@ cudaError_t launch_rollout_simt(const KParams& p, int sm_count, cudaStream_t str
 cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream);
 bool mma_supported(const KParams& p);
 int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad);
-cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream);
+int mma_groups_per_sm();
+cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -279,7 +280,7 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     {
         // time-chunked scheduling of the tcgen05 engine: aim for >= 8 work items per resident group,
         // chunks of at least 8 steps (state parks in L2 between chunks: ~29 KB per item each way)
-        const int64_t tiles128 = (desc->batch + 127) / 128, groups = 2ll * sms;
+        const int64_t tiles128 = (desc->batch + 127) / 128, groups = (int64_t)mma_groups_per_sm() * sms;
         int64_t nc = (8 * groups + tiles128 - 1) / tiles128;
         const int64_t nc_max = desc->n_steps / 8 > 0 ? desc->n_steps / 8 : 1;
         if (nc > nc_max) nc = nc_max;
@@ -327,11 +328,12 @@ int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* we
     return 0;
 }
 
-int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, void* stream_) {
+int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, int32_t mode, void* stream_) {
     g_err[0] = 0;
     if (!a || !w || !d) return fail(-5, "a/w/d NULL");
     if (k < 8 || k > 64 || k % 8 || n < 16 || n > 64 || n % 16) return fail(-3, "k must be a multiple of 8 in [8,64], n a multiple of 16 in [16,64]");
-    cudaError_t e = launch_mma_selftest(a, w, d, k, n, reinterpret_cast<cudaStream_t>(stream_));
+    if (mode != 0 && mode != 1) return fail(-3, "mode must be 0 (3xTF32) or 1 (2xTF32 + bf16)");
+    cudaError_t e = launch_mma_selftest(a, w, d, k, n, mode, reinterpret_cast<cudaStream_t>(stream_));
     if (e != cudaSuccess) return fail(-7, "selftest launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;

@@ -9,6 +9,8 @@
 //   * kernel-ready images of the weights and of the target / prior parameters.
 //
 // Blocks [0, T) do one time step each; the remaining blocks re-lay-out parameters.
+#include <cuda_bf16.h>
+
 #include "sdes_common.cuh"
 
 namespace sdes {
@@ -150,11 +152,11 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
         for (int64_t e = gtid; e < tiles128; e += nthreads) prog[e] = 0u;
     }
 
-    // tcgen05 weight images (layout: sdes_tc.cuh wimg_offset_floats; order: sdes_rollout_mma.cu):
-    // every weight split into tf32 hi (truncated) and lo = w - hi, zero-padded to the MMA shapes.
+    // tcgen05 weight images (layouts: sdes_tc.cuh wimg_offset_floats / wimg16_offset; order: sdes_rollout_mma.cu):
+    // per layer hi = fp32 truncated to tf32, lo = w - hi, w16 = bf16(w); zero-padded to the MMA shapes.
     if (!(d.flags & SDES_F_MLP_SIMT)) {
         float* w = ws + p.ws.w_mma;
-        const int nout = (dpad + 15) / 16 * 16;
+        const int nout = (dpad + 15) / 16 * 16, k0b = (dpad + 15) & ~15;
         int64_t o = 0;
         auto put = [&](int64_t base, int n, int k, int N, int K, float v) {
             const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -162,20 +164,33 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
             w[base + off] = hi;
             w[base + (int64_t)N * K + off] = v - hi;
         };
-        for (int64_t e = gtid; e < (int64_t)C * dpad; e += nthreads) {  // input layer: N=C, K=dpad
-            const int n = (int)(e / dpad), k = (int)(e % dpad);
-            put(o, n, k, C, dpad, k < dim ? blob[p.bl.in_w + (int64_t)n * dim + k] : 0.f);
+        auto put16 = [&](int64_t base_floats, int n, int k, int N, float v) {
+            __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(w + base_floats);
+            w16[(int64_t)(k / 8) * (N * 8) + (n / 8) * 64 + (n % 8) * 8 + (k % 8)] = __float2bfloat16_rn(v);
+        };
+        for (int64_t e = gtid; e < (int64_t)C * k0b; e += nthreads) {  // input layer: N=C, K=dpad (bf16: k0b)
+            const int n = (int)(e / k0b), k = (int)(e % k0b);
+            const float v = k < dim ? blob[p.bl.in_w + (int64_t)n * dim + k] : 0.f;
+            if (k < dpad) put(o, n, k, C, dpad, v);
+            put16(o + 2ll * C * dpad, n, k, C, v);
         }
-        o += 2ll * C * dpad;
+        o += 2ll * C * dpad + 32ll * k0b;
         for (int l = 0; l < nh; ++l) {
-            for (int64_t e = gtid; e < C * C; e += nthreads) put(o, (int)(e / C), (int)(e % C), C, C, blob[p.bl.h_w[l] + e]);
-            o += 2ll * C * C;
+            for (int64_t e = gtid; e < C * C; e += nthreads) {
+                const int n = (int)(e / C), k = (int)(e % C);
+                const float v = blob[p.bl.h_w[l] + e];
+                put(o, n, k, C, C, v);
+                put16(o + 2ll * C * C, n, k, C, v);
+            }
+            o += 2ll * C * C + 32ll * C;
         }
         for (int64_t e = gtid; e < (int64_t)nout * C; e += nthreads) {  // output layer: N=nout, K=C
             const int n = (int)(e / C), k = (int)(e % C);
-            put(o, n, k, nout, C, n < dim ? blob[p.bl.out_w + (int64_t)n * C + k] : 0.f);
+            const float v = n < dim ? blob[p.bl.out_w + (int64_t)n * C + k] : 0.f;
+            put(o, n, k, nout, C, v);
+            put16(o + 2ll * nout * C, n, k, nout, v);
         }
-        o += 2ll * nout * C;
+        o += 2ll * nout * C + 32ll * nout;
         for (int l = 0; l < nh; ++l) {
             for (int64_t e = gtid; e < C; e += nthreads) w[o + e] = blob[p.bl.h_b[l] + e];
             o += C;

@@ -11,31 +11,37 @@
 // (bias, exact-erf GELU, then — after the last layer — target score, control reparametrisation,
 // cost increments, Philox noise, Euler-Maruyama update: sdes_step.cuh).  While one group waits
 // on its MMAs the other group's epilogue keeps the FP32/MUFU pipes busy.
+#include <cuda_bf16.h>
+
 #include "sdes_step.cuh"
 #include "sdes_tc.cuh"
 
 namespace sdes {
 
 #ifndef SDES_MMA_GROUPS
-#define SDES_MMA_GROUPS 2
+#define SDES_MMA_GROUPS 3
 #endif
 constexpr int MMA_GROUPS = SDES_MMA_GROUPS;
 constexpr int MMA_THREADS = MMA_GROUPS * 128;
 constexpr int TMEM_COLS = 512;
-constexpr int GROUP_COLS = 256;  // D[64] | A_hi[64] | A_lo[64] | spare[64]
+constexpr int GROUP_COLS = 160;  // D[64] | A_hi tf32 [64] | A_lo bf16x2 [32]
 
 __host__ __device__ inline int mma_nout(int dpad) { return (dpad + 15) / 16 * 16; }
 
-// Workspace image for the tcgen05 engine (floats), in the order the kernel keeps it in smem:
-//   L0:  hi[64*K0] lo[64*K0]      (N=64, K=K0=dpad)
-//   Lh:  { hi[64*64] lo[64*64] } x n_hidden
-//   Lo:  hi[NOUT*64] lo[NOUT*64]  (N=NOUT, K=64)
+// Workspace image for the tcgen05 engine (floats), in the order the kernel keeps it in smem.  Per layer:
+// hi (tf32-truncated fp32), lo = w - hi (fp32), w16 (bf16, K padded to a multiple of 16):
+//   L0:  hi[64*K0] lo[64*K0] w16[64*K0b/2]     (N=64, K=K0=dpad, K0b = round16(dpad))
+//   Lh:  { hi[64*64] lo[64*64] w16[64*64/2] } x n_hidden
+//   Lo:  hi[NOUT*64] lo[NOUT*64] w16[NOUT*64/2] (N=NOUT, K=64)
 //   bias: { b_h[64] } x n_hidden, b_out[NOUT]     (b_in is folded into the time-embedding table)
 int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad_simt) {
     (void)dpad_simt;
-    const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad);
-    return 2ll * 64 * dpad + (int64_t)d.n_hidden * (2ll * 64 * 64) + 2ll * nout * 64 + (int64_t)d.n_hidden * 64 + nout;
+    const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad), k0b = (dpad + 15) & ~15;
+    return (2ll * 64 * dpad + 32ll * k0b) + (int64_t)d.n_hidden * (2ll * 64 * 64 + 32 * 64) + (2ll * nout * 64 + nout * 32ll) +
+           (int64_t)d.n_hidden * 64 + nout;
 }
+
+int mma_groups_per_sm() { return MMA_GROUPS; }
 
 bool mma_supported(const KParams& p) { return p.d.dim <= 64 && p.d.n_hidden <= SDES_MAX_HIDDEN; }
 
@@ -43,12 +49,14 @@ bool mma_supported(const KParams& p) { return p.d.dim <= 64 && p.d.n_hidden <= S
 // D[128,N] = A[128,K] * W[N,K]^T through exactly the code path the rollout uses (A via tcgen05.st
 // into TMEM, W image in smem, 3xTF32 issue, tcgen05.ld).  Exposed as sdes_tcgen05_selftest.
 __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W,
-                                                              float* __restrict__ D, int K, int N) {
+                                                              float* __restrict__ D, int K, int N, int mode) {
     extern __shared__ __align__(128) float sm[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
+    const int K16 = (K + 15) & ~15;
     float* w_hi = sm;
     float* w_lo = sm + N * K;
+    __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(sm + 2 * N * K);
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int e = tid; e < N * K; e += 128) {
         const int n = e / K, k = e % K;
@@ -56,6 +64,10 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
         const float hi = __uint_as_float(tc::tf32_hi_bits(w));
         w_hi[tc::wimg_offset_floats(n, k, N)] = hi;
         w_lo[tc::wimg_offset_floats(n, k, N)] = w - hi;
+    }
+    for (int e = tid; e < N * K16; e += 128) {
+        const int n = e / K16, k = e % K16;
+        w16[tc::wimg16_offset(n, k, N)] = __float2bfloat16_rn(k < K ? W[n * K + k] : 0.f);
     }
     if (warp == 0) {
         tc::tmem_alloc(&tmem_base_s, 256);
@@ -72,22 +84,33 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     const uint32_t tbase = tmem_base_s;
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
     const uint32_t col_d = 0, col_hi = 64, col_lo = 128;
-    for (int c = 0; c < K; c += 8) {
-        uint32_t hi[8], lo[8];
+    for (int c = 0; c < K16; c += 8) {
+        uint32_t hi[8], lo[8], lo16[4];
+        float lof[8];
         for (int q = 0; q < 8; ++q) {
-            const float a = A[tid * K + c + q];
+            const float a = c + q < K ? A[tid * K + c + q] : 0.f;
             hi[q] = tc::tf32_hi_bits(a);
-            lo[q] = __float_as_uint(a - __uint_as_float(hi[q]));
+            lof[q] = a - __uint_as_float(hi[q]);
+            lo[q] = __float_as_uint(lof[q]);
         }
-        tc::tmem_st8(lane_addr + col_hi + c, hi);
-        tc::tmem_st8(lane_addr + col_lo + c, lo);
+        for (int q = 0; q < 4; ++q) lo16[q] = tc::pack_bf16x2(lof[2 * q], lof[2 * q + 1]);
+        if (c < K) tc::tmem_st8(lane_addr + col_hi + c, hi);
+        if (mode == 0) {
+            if (c < K) tc::tmem_st8(lane_addr + col_lo + c, lo);
+        } else {
+            tc::tmem_st4(lane_addr + col_lo + c / 2, lo16);
+        }
     }
     tc::wait_st();
     tc::fence_before();
     __syncthreads();
     if (tid == 0) {
         tc::fence_after();
-        tc::issue_layer_3xtf32(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo), K, N);
+        if (mode == 0)
+            tc::issue_layer_3xtf32(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo), K, N);
+        else
+            tc::issue_layer_mixed(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo),
+                                  tc::smem_u32(w16), K, K16, N);
         tc::mma_commit(&bar);
     }
     tc::mbar_wait(&bar, 0);
@@ -95,7 +118,7 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     for (int c = 0; c < N; c += 8) {
         float v[8];
         tc::tmem_ld8(lane_addr + col_d + c, v);
-        tc::wait_ld();
+        tc::wait_ld_tie<8>(v);
         for (int q = 0; q < 8; ++q) D[tid * N + c + q] = v[q];
     }
     tc::fence_before();
@@ -103,11 +126,11 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     if (warp == 0) tc::tmem_dealloc(tbase, 256);
 }
 
-cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream) {
-    const size_t smem = 2 * (size_t)N * K * sizeof(float);
+cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t stream) {
+    const size_t smem = 2 * (size_t)N * K * sizeof(float) + (size_t)N * ((K + 15) & ~15) * 2;
     cudaError_t e = cudaFuncSetAttribute(mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mma_selftest_kernel<<<1, 128, smem, stream>>>(A, W, D, K, N);
+    mma_selftest_kernel<<<1, 128, smem, stream>>>(A, W, D, K, N, mode);
     return cudaGetLastError();
 }
 
@@ -115,19 +138,27 @@ cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K,
 // ---------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
-// activations (fp32) -> TMEM A operand, split into tf32 hi / lo halves
+// activations (fp32) -> TMEM A operand: tf32 hi half (one column per value) and bf16 lo half (two per column).
+// ZERO_PAD: also clear the bf16 columns up to the next multiple of 16 values (input layer, K0 % 16 == 8).
 template <int N>
-__device__ __forceinline__ void store_a_split(uint32_t addr_hi, uint32_t addr_lo, const float (&a)[N]) {
+__device__ __forceinline__ void store_a_split(uint32_t addr_hi, uint32_t addr_lo16, const float (&a)[N]) {
 #pragma unroll
     for (int c = 0; c < N; c += 8) {
-        uint32_t hi[8], lo[8];
+        uint32_t hi[8], lo16[4];
+        float lo[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             hi[q] = tc::tf32_hi_bits(a[c + q]);
-            lo[q] = __float_as_uint(a[c + q] - __uint_as_float(hi[q]));
+            lo[q] = a[c + q] - __uint_as_float(hi[q]);
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lo16[q] = tc::pack_bf16x2(lo[2 * q], lo[2 * q + 1]);
         tc::tmem_st8(addr_hi + c, hi);
-        tc::tmem_st8(addr_lo + c, lo);
+        tc::tmem_st4(addr_lo16 + c / 2, lo16);
+    }
+    if (N % 16 == 8) {
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        tc::tmem_st4(addr_lo16 + N / 2, z);
     }
 }
 
@@ -142,15 +173,18 @@ __device__ __forceinline__ void load_acc(uint32_t addr_d, float (&acc)[N]) {
 __device__ __forceinline__ void gelu_split_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8],
                                                   const float4 b0, const float4 b1) {
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint32_t hi[8], lo[8];
+    uint32_t hi[8], lo16[4];
+    float lo[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float a = gelu_fast(v[q] + bb[q]);
         hi[q] = tc::tf32_hi_bits(a);
-        lo[q] = __float_as_uint(a - __uint_as_float(hi[q]));
+        lo[q] = a - __uint_as_float(hi[q]);
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lo16[q] = tc::pack_bf16x2(lo[2 * q], lo[2 * q + 1]);
     tc::tmem_st8(addr_hi, hi);
-    tc::tmem_st8(addr_lo, lo);
+    tc::tmem_st4(addr_lo, lo16);
 }
 
 struct GroupCtx;
@@ -166,13 +200,13 @@ struct GroupCtx {
 };
 
 // A operand is in TMEM; run one layer and leave the accumulator ready to be read.
-__device__ __forceinline__ void run_layer(GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K, int N) {
+__device__ __forceinline__ void run_layer(GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, uint32_t w16_saddr, int K, int N) {
     tc::wait_st();
     tc::fence_before();
     group_bar(c.g);
     if (c.gtid == 0) {
         tc::fence_after();
-        tc::issue_layer_3xtf32(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K, N);
+        tc::issue_layer_mixed(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, w16_saddr, K, (K + 15) & ~15, N);
         tc::mma_commit(c.bar);
     }
     tc::mbar_wait(c.bar, c.phase);
@@ -195,10 +229,10 @@ __device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* _
         const float4 p0 = b4[2 * ch], p1 = b4[2 * ch + 1], p2 = b4[2 * ch + 2], p3 = b4[2 * ch + 3];
         tc::wait_ld_tie<8>(a);
         tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
-        gelu_split_store8(c.l_hi + 8u * ch, c.l_lo + 8u * ch, a, p0, p1);
+        gelu_split_store8(c.l_hi + 8u * ch, c.l_lo + 4u * ch, a, p0, p1);
         tc::wait_ld_tie<8>(b);
         if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
-        gelu_split_store8(c.l_hi + 8u * (ch + 1), c.l_lo + 8u * (ch + 1), b, p2, p3);
+        gelu_split_store8(c.l_hi + 8u * (ch + 1), c.l_lo + 4u * (ch + 1), b, p2, p3);
     }
 }
 
@@ -262,10 +296,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
 
     // weight image addresses
     const uint32_t w_base = tc::smem_u32(s_w);
-    const uint32_t l0_hi = w_base, l0_lo = w_base + 64u * DPAD * 4u;
-    const uint32_t lh_base = l0_lo + 64u * DPAD * 4u;                   // + l * 2 * 16 KB
-    const uint32_t lo_hi = lh_base + (uint32_t)nh * 2u * 16384u, lo_lo = lo_hi + (uint32_t)NOUT * 64u * 4u;
-    const float* s_bias = s_w + 2 * 64 * DPAD + nh * 2 * 64 * 64 + 2 * NOUT * 64;  // {b_h[64]} x nh, b_out[NOUT]
+    constexpr uint32_t K0B = (DPAD + 15) & ~15;
+    constexpr uint32_t LH_BYTES = 16384u + 16384u + 8192u;             // one hidden layer: hi | lo | w16
+    const uint32_t l0_hi = w_base, l0_lo = l0_hi + 64u * DPAD * 4u, l0_16 = l0_lo + 64u * DPAD * 4u;
+    const uint32_t lh_base = l0_16 + 64u * K0B * 2u;
+    const uint32_t lo_hi = lh_base + (uint32_t)nh * LH_BYTES, lo_lo = lo_hi + (uint32_t)NOUT * 256u, lo_16 = lo_lo + (uint32_t)NOUT * 256u;
+    const float* s_bias = s_w + (2 * 64 * DPAD + 32 * K0B) + nh * (2 * 64 * 64 + 32 * 64) + (2 * NOUT * 64 + NOUT * 32);  // {b_h[64]} x nh, b_out[NOUT]
 
     TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
     GroupCtx c;
@@ -343,14 +379,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
             score_part<DPAD>(d, x, sc, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
             // ---- control MLP on the tensor cores (models/mlp.py:114-122)
             store_a_split<DPAD>(c.l_hi, c.l_lo, x);
-            run_layer(c, l0_hi, l0_lo, DPAD, C);
+            run_layer(c, l0_hi, l0_lo, l0_16, DPAD, C);
             layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
 #pragma unroll 1
             for (int l = 0; l < nh; ++l) {
-                run_layer(c, lh_base + (uint32_t)l * 32768u, lh_base + (uint32_t)l * 32768u + 16384u, C, C);
+                run_layer(c, lh_base + (uint32_t)l * LH_BYTES, lh_base + (uint32_t)l * LH_BYTES + 16384u, lh_base + (uint32_t)l * LH_BYTES + 32768u, C, C);
                 layer_epilogue(c, s_bias + l * C);
             }
-            run_layer(c, lo_hi, lo_lo, C, NOUT);
+            run_layer(c, lo_hi, lo_lo, lo_16, C, NOUT);
             // ---- network output streamed from TMEM into the control / cost / state update
             {
                 const StepCoef sc_ = make_step_coef(d, tab);

@@ -151,5 +151,60 @@ __device__ __forceinline__ void issue_layer_3xtf32(uint32_t tmem_d, uint32_t tme
     }
 }
 
+// ------------------------------------------------------------- mixed-precision split (v2)
+// The lo half only has to carry ~11 more bits below a 2^-11-times-smaller magnitude, so it can
+// live in bf16: the A operand shrinks from 64+64 to 64+32 TMEM columns per tile (three tiles fit
+// in the 512 columns of an SM instead of two) and its product runs as kind::f16 with K=16 per MMA:
+//     D = A_hi(tf32) * W_hi(tf32) + A_hi(tf32) * W_lo(tf32) + A_lo(bf16) * W(bf16)
+// Relative error ~2^-19 of sum|a||w| (tested < 4e-6), fp32 SGEMM-class.
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// bf16 weight image (N rows x K cols, K multiple of 16), K-major, no swizzle: core matrix = 8 rows x 16 bytes
+// = 8 rows x 8 bf16.  offset in bf16 elements: (k/8) * (N*8) + (n/8) * 64 + (n%8) * 8 + (k%8)
+//   => LBO = N*16 bytes, SBO = 128 bytes; one MMA (K=16) spans two K-chunks, k-step s starts at byte s*2*LBO.
+__host__ __device__ inline int64_t wimg16_offset(int n, int k, int N) {
+    return (int64_t)(k / 8) * (N * 8) + (n / 8) * 64 + (n % 8) * 8 + (k % 8);
+}
+// two fp32 -> packed bf16x2 (round to nearest even); `lo_k` lands in the low half (even k)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_k, float lo_k1) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(lo_k1), "f"(lo_k));
+    return r;
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3])
+                 : "memory");
+}
+
+// K8 = K of the tf32 terms (multiple of 8), K16 = K of the bf16 term (multiple of 16, >= K8; the extra
+// columns of A_lo and of the bf16 image are zero).  Called by ONE thread.
+__device__ __forceinline__ void issue_layer_mixed(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo16,
+                                                  uint32_t w_hi_saddr, uint32_t w_lo_saddr, uint32_t w16_saddr,
+                                                  int K8, int K16, int N) {
+    const uint32_t id32 = idesc_tf32(128, N), id16 = idesc_bf16(128, N);
+    const uint32_t lbo = (uint32_t)N * 16u;
+    for (int s = 0; s < (K16 >> 4); ++s) {
+        const uint64_t b16 = smem_desc_kmajor(w16_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        mma_f16_ts(tmem_d, tmem_a_lo16 + 8u * s, b16, id16, s > 0 ? 1u : 0u);
+    }
+    for (int s = 0; s < (K8 >> 3); ++s) {
+        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bl, id32, 1u);
+        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bh, id32, 1u);
+    }
+}
+
 }  // namespace tc
 }  // namespace sdes

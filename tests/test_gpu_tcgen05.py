@@ -10,8 +10,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("K,N", [(8, 16), (8, 64), (16, 64), (56, 64), (64, 64), (64, 16), (64, 48), (32, 32)])
-def test_3xtf32_layer_matches_fp64(K, N):
+def test_split_layer_matches_fp64(K, N, mode):
     from sde_sampler_b200 import _cabi
 
     lib = _cabi.lib()
@@ -20,7 +21,7 @@ def test_3xtf32_layer_matches_fp64(K, N):
     A = (torch.randn(128, K, generator=g) * 3).to(dev)
     W = torch.randn(N, K, generator=g).to(dev)
     D = torch.full((128, N), float("nan"), device=dev)
-    rc = lib.sdes_tcgen05_selftest(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N,
+    rc = lib.sdes_tcgen05_selftest(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, mode,
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.sdes_last_error()
     torch.cuda.synchronize()
@@ -28,4 +29,6 @@ def test_3xtf32_layer_matches_fp64(K, N):
     scale = (A.double().abs() @ W.double().abs().T)
     err = ((D.double() - want).abs() / scale).max().item()
     # fp32 SGEMM itself sits at ~1e-7 of sum|a||w|; single-pass TF32 would be ~5e-4
-    assert err < 2e-6, f"relative error {err:.3e} (K={K}, N={N})"
+    tol = 2e-6 if mode == 0 else 4e-6
+    print(f"mode {mode} K={K} N={N}: max relative error {err:.3e}")
+    assert err < tol, f"relative error {err:.3e} (K={K}, N={N}, mode={mode})"
