@@ -45,6 +45,17 @@ def workload_name(batch: int) -> str:
     return f"GMM-40 d={DIM} solver=dis loss=lv T={T_STEPS} batch={batch}/GPU"
 
 
+def recorded_traffic(engine: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the committed
+    `ncu --set full` capture of this same command (profiles/traffic.json), or None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = rec.get(f"{engine}:B={batch}")
+        return None if e is None else e["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- the objects
 def build_objects(device, engine: str, process_group=None, seed: int = 1):
     """conf/solver/dis.yaml with target GMM-40 d=50 (explicit loc), random-init
@@ -158,56 +169,105 @@ def reference_arm(args):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~5 ms DURING the timed region (NVML in a thread;
+    falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples = []
+        self.reasons = set()
+        self.max_clock = None
+        self._stop = False
+        self._thread = None
+        self._smi = None
+
+    def _nvml_loop(self, pynvml, handle):
+        R = {
+            getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop:
+            try:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for bit, name in R.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        import threading
+
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the local CUDA index to the NVML index via the PCI bus id
+            import torch
+
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.idx), "pci_bus_id") else None
+            handle = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        handle = h
+                        break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_clock = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self._thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self._thread = None
+            self._smi_f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self._smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                              "-i", str(self.idx)], stdout=self._smi_f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self._smi = None
 
     def stop(self) -> dict:
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().strip().splitlines():
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
-                continue
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        elif self._smi is not None:
+            self._smi.terminate()
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+                self._smi.wait(timeout=5)
+            except Exception:
+                self._smi.kill()
+            self._smi_f.flush()
+            self._smi_f.seek(0)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in self._smi_f.read().strip().splitlines():
+                parts = [x.strip() for x in ln.split(",")]
+                try:
+                    self.samples.append(float(parts[0]))
+                    self.max_clock = float(parts[1])
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            os.unlink(self._smi_f.name)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_clock, "reasons": ["no samples"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_clock, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 # -------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tcgen05", "simt"])
@@ -246,7 +306,7 @@ def main():
     torch.manual_seed(100 + rank)
     x0 = o["prior"].sample((B,))
     x0_host = x0.cpu().pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step(x):
         return loss(ts, x, o["terminal"], o["second"])
@@ -337,14 +397,14 @@ def main():
             "dtype": "f32" if engine_used == "simt" else "tf32x3 (fp32-equivalent split) MMA, f32 elsewhere",
             "data": "synthetic",
             "config": {"workload": workload_name(B), "engine": engine_used, "global_batch": world * B,
-                       "l2": "flushed between timed steps (256 MiB memset inside the region)",
+                       "l2": "flushed between timed steps (192 MiB memset inside the region)",
                        "noise": "in-kernel Philox4x32-10", "loss_value": loss_value},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps, "loss_value": host_loss},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel_ms": kernel_ms,
+                         "frac": achieved_tf / peak_tf, "traffic": recorded_traffic(engine_used, B), "kernel_ms": kernel_ms,
                          "flops_per_traj_step": flops_per_traj_step(DIM), "peak_source": peak_src,
                          "traj_steps_per_s_kernel": traj_steps / (kernel_ms * 1e-3),
                          "hbm_algorithmic_bytes": B * (8 * DIM + 4),

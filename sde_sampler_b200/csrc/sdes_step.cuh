@@ -232,20 +232,26 @@ __device__ __forceinline__ void score_part(const SdesRolloutDesc& d, const float
         for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
     }
     const float* pl = ts.prior;
-    if (d.ctrl_kind == SDES_CTRL_LERP) {
-#pragma unroll
-        for (int j = 0; j < DPAD; ++j) sc[j] = torch_lerp((pl[j] - x[j]) * pl[DPAD + j], sc[j], lerp_w);
-    } else if (d.ctrl_kind == SDES_CTRL_LERP_PRIOR) {
-#pragma unroll
-        for (int j = 0; j < DPAD; ++j) sc[j] = (1.0f - lerp_w) * ((pl[j] - x[j]) * pl[DPAD + j]);
-    } else if (d.ctrl_kind == SDES_CTRL_LERP_TARGET) {
-#pragma unroll
-        for (int j = 0; j < DPAD; ++j) sc[j] = lerp_w * sc[j];
-    }
     const float cs = d.clip_score;
-    const float outer = d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : sigma;
-#pragma unroll
-    for (int j = 0; j < DPAD; ++j) sc[j] = outer * (d.scale_score * clipf(sc[j], cs) * gate_row[j]);
+    const float outer = (d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : sigma) * d.scale_score;
+    // one fused pass per control kind; the empty asm every 8 elements is a scheduling fence that keeps the
+    // compiler from hoisting all DPAD operand loads at once (register pressure: 168 registers per thread)
+#define SDES_SCORE_LOOP(EXPR)                                                        \
+    _Pragma("unroll") for (int j = 0; j < DPAD; ++j) {                               \
+        const float inner = (EXPR);                                                  \
+        sc[j] = outer * (clipf(inner, cs) * gate_row[j]);                            \
+        if ((j & 7) == 7) asm volatile("" ::: "memory");                             \
+    }
+    if (d.ctrl_kind == SDES_CTRL_LERP) {
+        SDES_SCORE_LOOP(torch_lerp((pl[j] - x[j]) * pl[DPAD + j], sc[j], lerp_w))
+    } else if (d.ctrl_kind == SDES_CTRL_LERP_PRIOR) {
+        SDES_SCORE_LOOP((1.0f - lerp_w) * ((pl[j] - x[j]) * pl[DPAD + j]))
+    } else if (d.ctrl_kind == SDES_CTRL_LERP_TARGET) {
+        SDES_SCORE_LOOP(lerp_w * sc[j])
+    } else {
+        SDES_SCORE_LOOP(sc[j])
+    }
+#undef SDES_SCORE_LOOP
 }
 
 // ---------------------------------------------------------------------------------- step
