@@ -152,6 +152,10 @@ int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32
  * mode 1 = tf32 hi*hi + hi*lo plus a bf16 lo*w term (the rollout's layer).  Test hook. */
 int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, int32_t mode, void* stream);
 
+/* y[i] = GELU(x[i]) exactly as the tensor-core engine's epilogue evaluates it (x Phi(x), erfc by
+ * Abramowitz-Stegun 7.1.26 on MUFU.RCP / MUFU.EX2).  Test hook for the accuracy claim in DESIGN.md. */
+int sdes_gelu_probe(const float* x, float* y, int64_t n, void* stream);
+
 /* Kernel launches performed by this process through the library since load (for bench accounting). */
 int64_t sdes_launch_count(void);
 

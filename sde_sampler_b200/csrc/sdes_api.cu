@@ -222,6 +222,10 @@ __global__ void philox_normal_kernel(uint64_t seed, uint64_t traj_offset, int64_
     }
 }
 
+__global__ void gelu_probe_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = gelu_fast(x[i]);
+}
+
 static int sm_count_cached() {
     static int cached[64] = {0};
     int dev = 0;
@@ -335,6 +339,16 @@ int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, i
     if (mode != 0 && mode != 1) return fail(-3, "mode must be 0 (3xTF32) or 1 (2xTF32 + bf16)");
     cudaError_t e = launch_mma_selftest(a, w, d, k, n, mode, reinterpret_cast<cudaStream_t>(stream_));
     if (e != cudaSuccess) return fail(-7, "selftest launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_gelu_probe(const float* x, float* y, int64_t n, void* stream_) {
+    g_err[0] = 0;
+    if (!x || !y || n <= 0) return fail(-5, "x/y NULL or n <= 0");
+    gelu_probe_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, y, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "gelu probe launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

@@ -32,3 +32,25 @@ def test_split_layer_matches_fp64(K, N, mode):
     tol = 2e-6 if mode == 0 else 4e-6
     print(f"mode {mode} K={K} N={N}: max relative error {err:.3e}")
     assert err < tol, f"relative error {err:.3e} (K={K}, N={N}, mode={mode})"
+
+
+def test_fast_gelu_matches_exact_erf_gelu():
+    """The epilogue's GELU (erfc via A&S 7.1.26 on MUFU) against float64 exact-erf GELU, and against
+    torch's own fp32 GELU on the same points: it must be at least as close to the exact function."""
+    from scipy.special import erf
+
+    from sde_sampler_b200 import _cabi
+
+    lib = _cabi.lib()
+    dev = torch.device("cuda:0")
+    x = torch.cat([torch.linspace(-12, 12, 2_000_001), torch.tensor([0.0, -0.0, 1e-30, -1e-30, 40.0, -40.0])]).to(dev)
+    y = torch.empty_like(x)
+    assert lib.sdes_gelu_probe(x.data_ptr(), y.data_ptr(), x.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    torch.cuda.synchronize()
+    x64 = x.double().cpu().numpy()
+    exact = 0.5 * x64 * (1 + erf(x64 / np.sqrt(2)))
+    ours = np.abs(y.double().cpu().numpy() - exact)
+    theirs = np.abs(torch.nn.functional.gelu(x).double().cpu().numpy() - exact)
+    print(f"max |gelu_fast - exact| = {ours.max():.3e}; torch fp32 gelu: {theirs.max():.3e}")
+    assert ours.max() < 6e-7
+    assert np.isfinite(y.cpu().numpy()).all()
