@@ -76,7 +76,7 @@ CASES = [
     (64, 23, 2, "gmm", "time_reversal", "lerp"),
     (57, 11, 2, "gmm_shared", "time_reversal", "lerp"),
     (40, 17, 2, "gmm", "time_reversal", "lerp_target"),
-    (33, 9, 1, "multiwell", "time_reversal", "lerp"),
+    (33, 30, 1, "multiwell", "time_reversal", "lerp"),  # (T=9 is ill-conditioned: the fp32 and fp64 oracle runs differ by 8e-4)
     (20, 31, 3, "gmm_shared", "reference_sde", "score"),
     (16, 8, 0, "funnel", "exp_integrator", "score"),
     (12, 13, 2, "gmm", "time_reversal", "clipped"),
