@@ -54,6 +54,7 @@ class FusedOCLoss:
         seed: int | None = None,
         engine: str = "auto",
         process_group=None,
+        sync_metrics: bool = True,
         **kwargs,
     ):
         self.generative_ctrl = generative_ctrl
@@ -70,10 +71,15 @@ class FusedOCLoss:
         self.sde_ctrl_dropout = sde_ctrl_dropout
         if sde_ctrl_noise is not None or sde_ctrl_dropout is not None:
             raise NotImplementedError("sde_ctrl_noise / sde_ctrl_dropout are not implemented in the fused rollout")
-        self.n_filtered = 0
+        self._n_filtered = 0
         # fused-path extras (keyword-only, absent from the reference signature)
         self.engine = engine
         self.process_group = process_group
+        # True (default, the reference's behaviour, oc.py:86): n_filtered is a Python int updated with a host
+        # sync every call.  False: the count stays on the device and the metric is returned as a 0-dim tensor,
+        # so consecutive calls queue back to back on the stream (read `loss.n_filtered` to materialise it).
+        self.sync_metrics = sync_metrics
+        self._n_filtered_dev = None
         self._seed = seed
         self._calls = 0
         self._workspace = engine_workspace()
@@ -134,12 +140,30 @@ class FusedOCLoss:
             return self._compute_loss_lv_traj(rnd, samples)
         st = self._stats(rnd, samples)
         n, s1, s2 = st[0], st[1], st[2]
-        self.n_filtered += int((st[5] - n).item())  # the reference syncs here too (.item(), oc.py:86)
+        if self.sync_metrics:
+            self.n_filtered += int((st[5] - n).item())  # the reference syncs here too (.item(), oc.py:86)
+            count = self.n_filtered
+        else:
+            dropped = st[5] - n
+            self._n_filtered_dev = dropped if self._n_filtered_dev is None else self._n_filtered_dev + dropped
+            count = self._n_filtered_dev + self._n_filtered
         if self.method == "lv":
             loss = (s2 - s1 * s1 / n) / (n - 1.0)
         else:
             loss = s1 / n
-        return loss.to(torch.float32), {"train/n_filtered_cumulative": self.n_filtered}
+        return loss.to(torch.float32), {"train/n_filtered_cumulative": count}
+
+    @property
+    def n_filtered(self) -> int:
+        if self._n_filtered_dev is not None:
+            self._n_filtered += int(self._n_filtered_dev.item())
+            self._n_filtered_dev = None
+        return self._n_filtered
+
+    @n_filtered.setter
+    def n_filtered(self, value: int):
+        self._n_filtered = int(value)
+        self._n_filtered_dev = None
 
     def _compute_loss_lv_traj(self, rnd, samples):
         # variance over the traj_per_sample copies of each x0 (oc.py:78-84): a (tps, B0) view of rnd.
