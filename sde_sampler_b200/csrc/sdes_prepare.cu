@@ -129,20 +129,24 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
     const int64_t gtid = (int64_t)(blockIdx.x - T) * blockDim.x + tid;
     const int nh = d.n_hidden;
 
-    if (gtid == 0) {
-        uint32_t* ctr = reinterpret_cast<uint32_t*>(ws + p.ws.counter);
-        ctr[0] = ctr[2] = ctr[3] = 0u;  // [0] = dynamic tile counter
-        // [1] = GMM chunk mask: bit r set when dims 4r..4r+3 differ between components (sdes_step.cuh gmm_eval)
-        uint32_t mask = 0u;
-        if (d.target_kind == SDES_TARGET_GMM) {
-            for (int j = 0; j < dim; ++j) {
-                bool differs = false;
-                for (int k = 1; k < d.n_components && !differs; ++k)
-                    differs = d.gmm_loc[(int64_t)k * dim + j] != d.gmm_loc[j] || d.gmm_scale[(int64_t)k * dim + j] != d.gmm_scale[j];
-                if (differs) mask |= 1u << (j >> 2);
-            }
+    if ((int)blockIdx.x == T) {
+        // first re-layout block: work counter reset and the GMM chunk mask — bit r set when dims 4r..4r+3
+        // differ between components (sdes_step.cuh gmm_eval); one thread per dimension scans the components.
+        __shared__ uint32_t s_mask;
+        if (tid == 0) s_mask = 0u;
+        __syncthreads();
+        if (d.target_kind == SDES_TARGET_GMM && tid < dim) {
+            bool differs = false;
+            for (int k = 1; k < d.n_components; ++k)
+                differs |= d.gmm_loc[(int64_t)k * dim + tid] != d.gmm_loc[tid] || d.gmm_scale[(int64_t)k * dim + tid] != d.gmm_scale[tid];
+            if (differs) atomicOr(&s_mask, 1u << (tid >> 2));
         }
-        ctr[1] = mask;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t* ctr = reinterpret_cast<uint32_t*>(ws + p.ws.counter);
+            ctr[0] = ctr[2] = ctr[3] = 0u;  // [0] = dynamic work counter
+            ctr[1] = s_mask;
+        }
     }
 
     // per-tile progress words of the time-chunked scheduler
