@@ -71,8 +71,12 @@ __host__ __device__ inline int mma_pad_dim(int d) { return d <= 8 ? 8 : d <= 16 
 
 // ------------------------------------------------------------------------------------ math
 __device__ __forceinline__ float clipf(float v, float c) {
-    // utils/common.py:83-84 `tensor.clip(-max_norm, max_norm)`; c = +inf means no clip. NaN propagates.
-    return fminf(fmaxf(v, -c), c) + (v != v ? v : 0.0f);
+    // utils/common.py:83-84 `tensor.clip(-max_norm, max_norm)`; c = +inf means no clip. NaN propagates
+    // (min/max.NaN, two FMNMX instead of the five of fminf/fmaxf plus an explicit NaN fix-up).
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(-c));
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(c));
+    return r;
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -80,11 +84,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// The same function for the hot loop: x * Phi(x) with erfc from Abramowitz & Stegun 7.1.26
-// (|error| <= 1.5e-7 on erf), evaluated with MUFU.RCP / MUFU.EX2: ~17 instructions instead of
-// ~25 for erff.  Measured max |error| vs float64 over [-8, 8]: 4.2e-7 (torch's own fp32 GELU: 1.2e-6).
+// The same function for the hot loop: GELU(x) = relu(x) - |x| Phi(-|x|) with Phi(-|x|) = 0.5 erfc(|x|/sqrt 2)
+// from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf), evaluated with MUFU.RCP / MUFU.EX2:
+// 14 instructions instead of ~25 for erff and no select.  Measured max |error| vs float64 over
+// [-8, 8]: < 6e-7 (torch's own fp32 GELU: 1.2e-6).
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;
     float t, e;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
     // 0.5 * (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5)
@@ -92,11 +98,9 @@ __device__ __forceinline__ float gelu_fast(float x) {
     p = fmaf(p, t, 0.5f * 1.421413741f);
     p = fmaf(p, t, 0.5f * -0.284496736f);
     p = fmaf(p, t, 0.5f * 0.254829592f);
-    p *= t;
+    p *= t * ax;                                // |x| * 0.5 erfc-prefactor
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * -0.72134752044448170368f) * x));  // exp(-x^2/2)
-    const float q = p * e;                     // 0.5 erfc(|x|/sqrt 2) = Phi(-|x|)
-    const float phi = x >= 0.f ? 1.0f - q : q;
-    return x * phi;
+    return fmaf(-p, e, fmaxf(x, 0.0f));         // relu(x) - |x| Phi(-|x|)
 }
 
 __device__ __forceinline__ float torch_lerp(float a, float b, float w) {
