@@ -50,6 +50,21 @@ CASES = {
                                             clip_model=1e4, clip_score=5.0, gate_bias=1.0, gate_dim=3,
                                             loss="time_reversal", method="lv", max_rnd=None,
                                             clip_target=50.0, timesteps=LIN(40), batch=64, seed=7),
+    # BASELINE cfg5 family: solver/dds.yaml (ScoreCtrl, clips 10, max_rnd 1e8) + target/nice.yaml, cosine grid.
+    # NICE = 4 additive couplings (distr/nice.py); d > 64 and the coupling MLPs run on the wide (layered
+    # tcgen05 GEMM) engine.  Small widths keep the fixtures small; the arithmetic path is the same.
+    "dds_nice16_lv": dict(target="nice:24:3", dim=16, sde=None, prior="gauss", ctrl="score",
+                          clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="exp_integrator",
+                          method="lv", max_rnd=1e8, alpha=1.0, sigma=1.0,
+                          timesteps=dict(rescale_t="cosine", end=3.2, dt=0.05), batch=48, seed=8),
+    "dds_nice196_lv": dict(target="nice:72:5", dim=196, sde=None, prior="gauss", ctrl="score",
+                           clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="exp_integrator",
+                           method="lv", max_rnd=1e8, alpha=1.0, sigma=1.0,
+                           timesteps=dict(rescale_t="cosine", end=1.6, dt=0.05), batch=24, seed=9),
+    # a wide state with an analytic target: DIS+lv on a d=100 diagonal Gaussian (wide engine, Lerp control, VP)
+    "dis_gauss100_lv": dict(target="gauss", dim=100, sde="vp", prior="gauss", ctrl="lerp",
+                            clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
+                            method="lv", max_rnd=1e8, timesteps=LIN(30), batch=24, seed=10),
 }
 
 # eval-mode variants: (case, compute_weights, return_traj)  — losses/oc.py:258-278, :371-392
@@ -58,6 +73,7 @@ EVAL_CASES = {
     "dis_dw1_lv": [(True, True)],
     "pis_funnel10_kl": [(True, False)],
     "dds_funnel10_lv": [(True, True)],
+    "dds_nice16_lv": [(True, True)],
 }
 
 NOISE_SEED = 0x5DE5_0001

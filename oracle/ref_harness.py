@@ -113,6 +113,32 @@ def build_target(kind: str, dim: int):
         return Funnel(dim=dim, n_reference_samples=1000)
     if kind == "gauss":
         return IsotropicGauss(dim=dim, loc=0.7, scale=1.3)
+    if kind.startswith("nice"):
+        # "nice:<mid_dim>:<hidden>" — the reference's NiceModel (distr/nice.py:127-216) with seeded random
+        # weights wrapped exactly like Nice.unnorm_log_prob (:262-263); the shipped Nice class needs
+        # data/nice.pt (d = 196 only), which does not exist.
+        from sde_sampler.distr.base import Distribution
+        from sde_sampler.distr.nice import NiceModel, StandardLogistic
+
+        _, mid, hidden = kind.split(":")
+        torch.manual_seed(4242)
+        model = NiceModel(prior=StandardLogistic(), coupling=4, in_out_dim=dim, mid_dim=int(mid),
+                          hidden=int(hidden), mask_config=1)
+        with torch.no_grad():
+            model.scaling.scale.normal_(0.0, 0.2)
+        model.eval()
+        for p in model.parameters():
+            p.requires_grad_(False)
+
+        class Nice(Distribution):
+            def __init__(self):
+                super().__init__(dim=dim, log_norm_const=0.0, n_reference_samples=1000)
+                self.model = model
+
+            def unnorm_log_prob(self, x):
+                return self.model.log_prob(x).unsqueeze(-1) + self.log_norm_const
+
+        return Nice()
     raise ValueError(kind)
 
 

@@ -148,7 +148,54 @@ def target_log_prob_and_score(tg, x, need_score=True):
         loc, scale = tg["loc"].astype(dt), tg["scale"].astype(dt)
         logp = diag_gauss_log_prob(x, loc, scale) + dt.type(tg.get("log_norm_const", 0.0))
         return logp.astype(dt), diag_gauss_score(x, loc, scale).astype(dt) if need_score else None
+    if kind == "nice":
+        return nice_log_prob_and_score(tg, x, need_score)
     raise ValueError(f"oracle: unsupported target kind {kind!r}")
+
+
+def _softplus(z):
+    return np.logaddexp(z, z.dtype.type(0.0))
+
+
+def nice_log_prob_and_score(tg, x, need_score=True):
+    """NiceModel.log_prob (distr/nice.py:178-190) wrapped as Nice.unnorm_log_prob (:262-263), and its
+    score.  The reference differentiates log_prob with autograd (distr/base.py:130-137); here the
+    backward pass of the additive couplings is written out:
+      Coupling.forward :64-95   x.reshape(B, W/2, 2): mask_config=1 -> on = [:, :, 0], off = [:, :, 1];
+                                on <- on + out_block(relu-MLP(off))
+      Scaling.forward  :109-124 z = h * exp(scale), log|det J| = sum(scale)
+      StandardLogistic.log_prob :21-29  -(softplus(z) + softplus(-z)), d/dz = -tanh(z/2)
+    tg: {"couplings": [{"mask_config": 0|1, "layers": [(w, b), ...]}], "scale": (d,), "log_norm_const"}."""
+    dt = x.dtype
+    B, W = x.shape
+    h = x.reshape(B, W // 2, 2).copy()
+    saved = []
+    for c in tg["couplings"]:
+        on_i = 0 if int(c["mask_config"]) else 1
+        off = h[:, :, 1 - on_i]
+        a = off
+        masks = []
+        layers = c["layers"]
+        for w, b in layers[:-1]:
+            a = np.maximum(linear(a, np.asarray(w, dt), np.asarray(b, dt)), dt.type(0))
+            masks.append(a > 0)
+        w, b = layers[-1]
+        h[:, :, on_i] = h[:, :, on_i] + linear(a, np.asarray(w, dt), np.asarray(b, dt))
+        saved.append((on_i, masks))
+    scale = np.asarray(tg["scale"], dt).reshape(1, W)
+    z = h.reshape(B, W) * np.exp(scale)
+    logp = (-(_softplus(z) + _softplus(-z))).sum(-1, keepdims=True) + scale.sum() + dt.type(tg.get("log_norm_const", 0.0))
+    if not need_score:
+        return logp.astype(dt), None
+    g = (-np.tanh(z * dt.type(0.5)) * np.exp(scale)).astype(dt).reshape(B, W // 2, 2)
+    for c, (on_i, masks) in zip(reversed(tg["couplings"]), reversed(saved)):
+        layers = c["layers"]
+        delta = g[:, :, on_i] @ np.asarray(layers[-1][0], dt)           # through out_block
+        for (w, _), m in zip(reversed(layers[1:-1]), reversed(masks[1:])):
+            delta = (delta * m) @ np.asarray(w, dt)
+        delta = (delta * masks[0]) @ np.asarray(layers[0][0], dt)        # through in_block
+        g[:, :, 1 - on_i] = g[:, :, 1 - on_i] + delta
+    return logp.astype(dt), g.reshape(B, W).astype(dt)
 
 
 # --------------------------------------------------------------------------------------

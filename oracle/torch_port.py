@@ -85,8 +85,27 @@ class _Target:
             self.n, self.sep, self.shift = int(tg["n_dw"]), float(tg["separation"]), float(tg["shift"])
         elif self.kind == "funnel":
             self.var = float(tg["variance"])
+        elif self.kind == "nice":
+            self.couplings = [(int(c["mask_config"]), [(_t(w), _t(b)) for w, b in c["layers"]]) for c in tg["couplings"]]
+            self.scale = _t(tg["scale"]).reshape(1, -1)
+
+    def _nice_log_prob(self, x):
+        # NiceModel.log_prob with the reference's own op sequence (distr/nice.py:64-95, :109-124, :178-190)
+        B, W = x.shape
+        for mc, layers in self.couplings:
+            xr = x.reshape(B, W // 2, 2)
+            on, off = (xr[:, :, 0], xr[:, :, 1]) if mc else (xr[:, :, 1], xr[:, :, 0])
+            a = off
+            for w, b in layers[:-1]:
+                a = F.relu(F.linear(a, w, b))
+            on = on + F.linear(a, *layers[-1])
+            x = (torch.stack((on, off), dim=2) if mc else torch.stack((off, on), dim=2)).reshape(B, W)
+        z = x * torch.exp(self.scale)
+        return torch.sum(-(F.softplus(z) + F.softplus(-z)), dim=1) + torch.sum(self.scale)
 
     def unnorm_log_prob(self, x):
+        if self.kind == "nice":
+            return self._nice_log_prob(x).unsqueeze(-1) + self.lnc
         if self.kind == "gmm":
             return self.distr.log_prob(x).unsqueeze(-1) + self.lnc
         if self.kind == "gauss":
@@ -105,7 +124,7 @@ class _Target:
         return lp0 + lpo + self.lnc
 
     def score(self, x):
-        if self.kind == "gmm":  # Distribution.score: autograd of the log-density (distr/base.py:130-137)
+        if self.kind in ("gmm", "nice"):  # Distribution.score: autograd of the log-density (distr/base.py:130-137)
             x = x.detach().requires_grad_(True)
             with torch.enable_grad():
                 lr = self.unnorm_log_prob(x).sum()

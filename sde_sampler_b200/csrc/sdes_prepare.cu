@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
     const int nh = d.n_hidden;
 
     if ((int)blockIdx.x == T) {
-        // first re-layout block: work counter reset and the GMM chunk mask — bit r set when dims 4r..4r+3
+        // first re-layout block: work counter reset and the GMM pair mask — bit r set when dims 2r, 2r+1
         // differ between components (sdes_step.cuh gmm_eval); one thread per dimension scans the components.
         __shared__ uint32_t s_mask;
         if (tid == 0) s_mask = 0u;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
             bool differs = false;
             for (int k = 1; k < d.n_components; ++k)
                 differs |= d.gmm_loc[(int64_t)k * dim + tid] != d.gmm_loc[tid] || d.gmm_scale[(int64_t)k * dim + tid] != d.gmm_scale[tid];
-            if (differs) atomicOr(&s_mask, 1u << (tid >> 2));
+            if (differs) atomicOr(&s_mask, 1u << (tid >> 1));
         }
         __syncthreads();
         if (tid == 0) {

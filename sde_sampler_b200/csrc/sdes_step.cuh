@@ -16,7 +16,7 @@ struct TargetSmem {
     const float* gmm_mu;  // K * DPAD
     const float* gmm_h;   // K * DPAD
     const float* gmm_c;   // 64
-    uint32_t gmm_mask;    // bit r: dimension chunk r (4 dims) differs between components
+    uint32_t gmm_mask;    // bit r: dimension pair (2r, 2r+1) differs between components
     const float* prior;   // loc[DPAD] | inv_var[DPAD] | lognorm
     const float* ref;     // same
 };
@@ -30,47 +30,41 @@ struct TargetSmem {
 // Per component: phase A accumulates the logit, phase B folds its responsibility-weighted
 // score term into running sums that are rescaled whenever the running max moves.
 //
-// `ts.gmm_mask` has bit r set when dimension chunk r (4 dims) differs between components.
-// Chunks whose (mu, scale) are identical in every component factor out of the mixture exactly:
+// `ts.gmm_mask` has bit r set when the dimension pair (2r, 2r+1) differs between components.
+// Pairs whose (mu, scale) are identical in every component factor out of the mixture exactly:
 //     log rho(x) = logsumexp_k [ c_k - sum_{j in active} h_kj (x_j - mu_kj)^2 ] - sum_{j shared} h_j (x_j - mu_j)^2
 //     score_j    = 2 h_j (mu_j - x_j)                                            for shared j
 // so they cost O(d) instead of O(K d) (e.g. the zero-padded dims of GMM-40 in d=50).
-// NA = number of leading chunks handled as "active" (a compile-time prefix, chosen by the caller
-// to cover the highest set bit of the mask, so the inner loops carry no per-chunk tests).
+// NP = number of leading pairs handled as "active" (a compile-time prefix, chosen by the caller
+// to cover the highest set bit of the mask, so the inner loops carry no per-pair tests).
 // Components are processed two at a time (independent accumulators) for instruction-level
 // parallelism; the images are padded to an even K with h = 0, c = -inf.
-template <int DPAD, int NA, bool NEED_SCORE, bool TWO = (NA <= 4)>
+template <int DPAD, int NP, bool NEED_SCORE, bool TWO = (NP <= 8)>
 __device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
-    constexpr int NCH = DPAD / 4;
+    constexpr int NPAIR = DPAD / 2;
     float m = -INFINITY, ssum = 0.f;
     if (NEED_SCORE) {
 #pragma unroll
-        for (int j = 0; j < 4 * NA; ++j) score[j] = 0.f;
+        for (int j = 0; j < 2 * NP; ++j) score[j] = 0.f;
     }
 #pragma unroll 1
     for (int k = 0; k < K; k += (TWO ? 2 : 1)) {
-        const float4* mu4a = reinterpret_cast<const float4*>(ts.gmm_mu + k * DPAD);
-        const float4* h4a = reinterpret_cast<const float4*>(ts.gmm_h + k * DPAD);
-        const float4* mu4b = mu4a + NCH;
-        const float4* h4b = h4a + NCH;
+        const float2* mu2a = reinterpret_cast<const float2*>(ts.gmm_mu + k * DPAD);
+        const float2* h2a = reinterpret_cast<const float2*>(ts.gmm_h + k * DPAD);
+        const float2* mu2b = mu2a + NPAIR;
+        const float2* h2b = h2a + NPAIR;
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-        for (int r = 0; r < NA; ++r) {
-            const float4 mu = mu4a[r], h = h4a[r];
-            const float d0 = x[4 * r + 0] - mu.x, d1 = x[4 * r + 1] - mu.y;
-            const float d2 = x[4 * r + 2] - mu.z, d3 = x[4 * r + 3] - mu.w;
+        for (int r = 0; r < NP; ++r) {
+            const float2 mu = mu2a[r], h = h2a[r];
+            const float d0 = x[2 * r + 0] - mu.x, d1 = x[2 * r + 1] - mu.y;
             a0 = fmaf(d0 * d0, h.x, a0);
             a1 = fmaf(d1 * d1, h.y, a1);
-            a0 = fmaf(d2 * d2, h.z, a0);
-            a1 = fmaf(d3 * d3, h.w, a1);
             if (TWO) {
-                const float4 nu = mu4b[r], g = h4b[r];
-                const float f0 = x[4 * r + 0] - nu.x, f1 = x[4 * r + 1] - nu.y;
-                const float f2 = x[4 * r + 2] - nu.z, f3 = x[4 * r + 3] - nu.w;
+                const float2 nu = mu2b[r], g = h2b[r];
+                const float f0 = x[2 * r + 0] - nu.x, f1 = x[2 * r + 1] - nu.y;
                 b0 = fmaf(f0 * f0, g.x, b0);
                 b1 = fmaf(f1 * f1, g.y, b1);
-                b0 = fmaf(f2 * f2, g.z, b0);
-                b1 = fmaf(f3 * f3, g.w, b1);
             }
         }
         const float la = ts.gmm_c[k] - (a0 + a1), lb = TWO ? ts.gmm_c[k + 1] - (b0 + b1) : -INFINITY;
@@ -85,18 +79,14 @@ __device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&sco
             if (__any_sync(0xffffffffu, rescale != 1.0f || ea > 0.f || eb > 0.f)) {
                 const float ea2 = 2.0f * ea, eb2 = 2.0f * eb;  // 1/var = 2h
 #pragma unroll
-                for (int r = 0; r < NA; ++r) {
-                    const float4 mu = mu4a[r], h = h4a[r];
-                    score[4 * r + 0] = fmaf(ea2 * h.x, mu.x - x[4 * r + 0], score[4 * r + 0] * rescale);
-                    score[4 * r + 1] = fmaf(ea2 * h.y, mu.y - x[4 * r + 1], score[4 * r + 1] * rescale);
-                    score[4 * r + 2] = fmaf(ea2 * h.z, mu.z - x[4 * r + 2], score[4 * r + 2] * rescale);
-                    score[4 * r + 3] = fmaf(ea2 * h.w, mu.w - x[4 * r + 3], score[4 * r + 3] * rescale);
+                for (int r = 0; r < NP; ++r) {
+                    const float2 mu = mu2a[r], h = h2a[r];
+                    score[2 * r + 0] = fmaf(ea2 * h.x, mu.x - x[2 * r + 0], score[2 * r + 0] * rescale);
+                    score[2 * r + 1] = fmaf(ea2 * h.y, mu.y - x[2 * r + 1], score[2 * r + 1] * rescale);
                     if (TWO) {
-                        const float4 nu = mu4b[r], g = h4b[r];
-                        score[4 * r + 0] = fmaf(eb2 * g.x, nu.x - x[4 * r + 0], score[4 * r + 0]);
-                        score[4 * r + 1] = fmaf(eb2 * g.y, nu.y - x[4 * r + 1], score[4 * r + 1]);
-                        score[4 * r + 2] = fmaf(eb2 * g.z, nu.z - x[4 * r + 2], score[4 * r + 2]);
-                        score[4 * r + 3] = fmaf(eb2 * g.w, nu.w - x[4 * r + 3], score[4 * r + 3]);
+                        const float2 nu = mu2b[r], g = h2b[r];
+                        score[2 * r + 0] = fmaf(eb2 * g.x, nu.x - x[2 * r + 0], score[2 * r + 0]);
+                        score[2 * r + 1] = fmaf(eb2 * g.y, nu.y - x[2 * r + 1], score[2 * r + 1]);
                     }
                 }
             }
@@ -105,26 +95,21 @@ __device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&sco
     if (NEED_SCORE) {
         const float inv = 1.0f / ssum;
 #pragma unroll
-        for (int j = 0; j < 4 * NA; ++j) score[j] *= inv;
+        for (int j = 0; j < 2 * NP; ++j) score[j] *= inv;
     }
-    // chunks shared by all components (read from component 0)
+    // pairs shared by all components (read from component 0)
     float shared = 0.f;
-    const float4* mu4 = reinterpret_cast<const float4*>(ts.gmm_mu);
-    const float4* h4 = reinterpret_cast<const float4*>(ts.gmm_h);
+    const float2* mu2 = reinterpret_cast<const float2*>(ts.gmm_mu);
+    const float2* h2 = reinterpret_cast<const float2*>(ts.gmm_h);
 #pragma unroll
-    for (int r = NA; r < NCH; ++r) {
-        const float4 mu = mu4[r], h = h4[r];
-        const float d0 = mu.x - x[4 * r + 0], d1 = mu.y - x[4 * r + 1];
-        const float d2 = mu.z - x[4 * r + 2], d3 = mu.w - x[4 * r + 3];
+    for (int r = NP; r < NPAIR; ++r) {
+        const float2 mu = mu2[r], h = h2[r];
+        const float d0 = mu.x - x[2 * r + 0], d1 = mu.y - x[2 * r + 1];
         shared = fmaf(d0 * d0, h.x, shared);
         shared = fmaf(d1 * d1, h.y, shared);
-        shared = fmaf(d2 * d2, h.z, shared);
-        shared = fmaf(d3 * d3, h.w, shared);
         if (NEED_SCORE) {
-            score[4 * r + 0] = 2.0f * h.x * d0;
-            score[4 * r + 1] = 2.0f * h.y * d1;
-            score[4 * r + 2] = 2.0f * h.z * d2;
-            score[4 * r + 3] = 2.0f * h.w * d3;
+            score[2 * r + 0] = 2.0f * h.x * d0;
+            score[2 * r + 1] = 2.0f * h.y * d1;
         }
     }
     return m + logf(ssum) - shared;
@@ -132,13 +117,14 @@ __device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&sco
 
 template <int DPAD, bool NEED_SCORE>
 __device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
-    constexpr int NCH = DPAD / 4;
+    constexpr int NPAIR = DPAD / 2;
     const uint32_t mask = ts.gmm_mask;  // warp-uniform
-    if (NCH > 1 && mask < 2u) return gmm_eval_na<DPAD, 1, NEED_SCORE>(x, score, ts, K);
-    if (NCH > 2 && mask < 4u) return gmm_eval_na<DPAD, (NCH > 2 ? 2 : NCH), NEED_SCORE>(x, score, ts, K);
-    if (NCH > 4 && mask < 16u) return gmm_eval_na<DPAD, (NCH > 4 ? 4 : NCH), NEED_SCORE>(x, score, ts, K);
-    if (NCH > 8 && mask < 256u) return gmm_eval_na<DPAD, (NCH > 8 ? 8 : NCH), NEED_SCORE>(x, score, ts, K);
-    return gmm_eval_na<DPAD, NCH, NEED_SCORE>(x, score, ts, K);
+    if (NPAIR > 1 && mask < 2u) return gmm_eval_na<DPAD, 1, NEED_SCORE>(x, score, ts, K);
+    if (NPAIR > 2 && mask < 4u) return gmm_eval_na<DPAD, (NPAIR > 2 ? 2 : NPAIR), NEED_SCORE>(x, score, ts, K);
+    if (NPAIR > 4 && mask < 16u) return gmm_eval_na<DPAD, (NPAIR > 4 ? 4 : NPAIR), NEED_SCORE>(x, score, ts, K);
+    if (NPAIR > 8 && mask < 256u) return gmm_eval_na<DPAD, (NPAIR > 8 ? 8 : NPAIR), NEED_SCORE>(x, score, ts, K);
+    if (NPAIR > 16 && mask < 65536u) return gmm_eval_na<DPAD, (NPAIR > 16 ? 16 : NPAIR), NEED_SCORE>(x, score, ts, K);
+    return gmm_eval_na<DPAD, NPAIR, NEED_SCORE>(x, score, ts, K);
 }
 
 // MultiWell (distr/double_well.py:165-179; DoubleWell :39-45 is n_dw = d = 1).
@@ -287,6 +273,7 @@ __device__ __forceinline__ void update4(const StepCoef& c, float* __restrict__ x
                                         const float* __restrict__ sc4, const float* __restrict__ prior_loc4,
                                         const float* __restrict__ prior_iv4, int j0, int step, uint32_t traj,
                                         const float* __restrict__ noise_row, float& cost, float& ito) {
+    if (j0 >= c.dim) return;  // whole chunk is padding: control 0, state stays 0 (warp-uniform)
     float e[4];
     if (c.from_hbm) {
 #pragma unroll

@@ -304,6 +304,61 @@ class Funnel(_Distribution):
         self.variance = variance if variance is not None else dim - 1
 
 
+class Coupling(nn.Module):
+    """distr/nice.py:43-95 — additive coupling: `on <- on + out_block(relu-MLP(off))`."""
+
+    def __init__(self, in_out_dim: int, mid_dim: int, hidden: int, mask_config: int):
+        super().__init__()
+        self.mask_config = mask_config
+        self.in_block = nn.Sequential(nn.Linear(in_out_dim // 2, mid_dim), nn.ReLU())
+        self.mid_block = nn.ModuleList([nn.Sequential(nn.Linear(mid_dim, mid_dim), nn.ReLU()) for _ in range(hidden - 1)])
+        self.out_block = nn.Linear(mid_dim, in_out_dim // 2)
+
+    forward = _in_kernel("forward")
+
+
+class Scaling(nn.Module):
+    """distr/nice.py:98-124"""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.scale = nn.Parameter(torch.zeros((1, dim)), requires_grad=True)
+
+    forward = _in_kernel("forward")
+
+
+class StandardLogistic:
+    """distr/nice.py:17-40 (the latent prior; its log-density is evaluated in-kernel)."""
+
+
+class NiceModel(nn.Module):
+    """distr/nice.py:127-216"""
+
+    def __init__(self, prior, coupling: int, in_out_dim: int, mid_dim: int, hidden: int, mask_config: int):
+        super().__init__()
+        self.prior = prior
+        self.in_out_dim = in_out_dim
+        self.coupling = nn.ModuleList([Coupling(in_out_dim, mid_dim, hidden, (mask_config + i) % 2) for i in range(coupling)])
+        self.scaling = Scaling(in_out_dim)
+
+    log_prob = _in_kernel("log_prob")
+    forward = _in_kernel("forward")
+
+
+class Nice(_Distribution):
+    """distr/nice.py:219-263 — a NICE flow as target density.  The reference loads a checkpoint trained on
+    14x14 MNIST (dim 196); no checkpoint can travel here, so the model is always passed in (any even dim)."""
+
+    def __init__(self, model: nn.Module, dim: int | None = None, log_norm_const: float = 0.0, **kwargs):
+        dim = int(model.in_out_dim) if dim is None else dim
+        super().__init__(dim=dim, log_norm_const=log_norm_const)
+        if dim != int(model.in_out_dim):
+            raise ValueError(f"Dimension is {dim} but the model has {model.in_out_dim}.")
+        self.model = model
+        for p in self.model.parameters():
+            p.requires_grad_(False)
+
+
 # ---------------------------------------------------------------------------- time grids
 def get_timesteps(start, end, dt=None, steps: int | None = None, rescale_t: str | None = None, device=None):
     """utils/common.py:18-55 — the (T+1,) fp32 grid the caller hands to the loss."""

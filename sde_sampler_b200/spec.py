@@ -166,9 +166,33 @@ def _target_params(target, dim) -> dict:
         # distr/funnel.py:11-80
         return {"kind": "funnel", "variance": float(target.variance),
                 "log_norm_const": float(lnc or 0.0)}
+    if name == "Nice" or (hasattr(target, "model") and _cls(target.model) == "NiceModel"):
+        return _nice_params(target, dim, lnc)
     raise NotImplementedError(
         f"target {name} is not implemented in the fused rollout (supported: GMM, Gauss, "
-        "IsotropicGauss, DoubleWell, MultiWell, Funnel)")
+        "IsotropicGauss, DoubleWell, MultiWell, Funnel, Nice)")
+
+
+def _nice_params(target, dim, lnc) -> dict:
+    """Nice / NiceModel (distr/nice.py:127-263): additive couplings with ReLU MLPs, a log-scale
+    vector and a standard-logistic latent prior."""
+    model = target.model
+    if int(model.in_out_dim) != dim or dim % 2:
+        raise NotImplementedError(f"NICE with in_out_dim={model.in_out_dim} for dim={dim}")
+    if _cls(model.prior) != "StandardLogistic":
+        raise NotImplementedError(f"NICE latent prior {_cls(model.prior)} (StandardLogistic only)")
+    couplings = []
+    for c in model.coupling:
+        lins = [c.in_block[0]] + [b[0] for b in c.mid_block] + [c.out_block]
+        for blk in [c.in_block] + list(c.mid_block):
+            if _cls(blk[1]) != "ReLU":
+                raise NotImplementedError("NICE coupling with a non-ReLU activation")
+        couplings.append({"mask_config": int(c.mask_config),
+                          "layers": [(_t(l.weight), _t(l.bias)) for l in lins]})
+    if len({len(c["layers"]) for c in couplings}) != 1 or len({tuple(c["layers"][0][0].shape) for c in couplings}) != 1:
+        raise NotImplementedError("NICE couplings of different shapes")
+    return {"kind": "nice", "couplings": couplings, "scale": _t(model.scaling.scale).reshape(-1),
+            "log_norm_const": float(lnc or 0.0)}
 
 
 def _sde_params(sde) -> dict | None:
