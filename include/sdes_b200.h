@@ -30,9 +30,10 @@
 extern "C" {
 #endif
 
-#define SDES_ABI_VERSION 1
+#define SDES_ABI_VERSION 2
 #define SDES_CHANNELS 64     /* FourierMLP / TimeEmbed width (conf/model/base/fouriermlp.yaml:3) */
-#define SDES_MAX_DIM 64      /* state dimension supported by the fused kernel this round   */
+#define SDES_MAX_DIM 64      /* state dimension of the fused single-kernel engines (state in registers) */
+#define SDES_MAX_WIDE_DIM 4096 /* state dimension of the wide (layered tcgen05 GEMM) engine: d > 64 or a NICE target */
 #define SDES_MAX_HIDDEN 6    /* hidden layers per network                                    */
 #define SDES_MAX_COMPONENTS 64 /* GMM components                                           */
 
@@ -44,7 +45,8 @@ enum { SDES_CTRL_CLIPPED = 0, SDES_CTRL_SCORE = 1, SDES_CTRL_LERP = 2, SDES_CTRL
 /* sde coefficient family — eq/sdes.py */
 enum { SDES_SDE_NONE = 0, SDES_SDE_VP = 1, SDES_SDE_CONST_OU = 2 /* ConstOU and ScaledBM */ };
 /* analytic target — distr/*.py.  Gauss / IsotropicGauss targets are passed as GMM with K=1. */
-enum { SDES_TARGET_GMM = 0, SDES_TARGET_MULTIWELL = 1 /* DoubleWell = n_dw=d=1 */, SDES_TARGET_FUNNEL = 2 };
+enum { SDES_TARGET_GMM = 0, SDES_TARGET_MULTIWELL = 1 /* DoubleWell = n_dw=d=1 */, SDES_TARGET_FUNNEL = 2,
+       SDES_TARGET_NICE = 3 /* distr/nice.py:127-263, wide engine */ };
 
 /* flags */
 #define SDES_F_RND0_ZERO      (1u << 0) /* rnd starts at 0 instead of log p_prior(x0) (oc.py:168-172)   */
@@ -70,7 +72,7 @@ typedef struct SdesRolloutDesc {
     uint32_t abi_version;    /* = SDES_ABI_VERSION, checked */
     int32_t loss_kind, ctrl_kind, sde_kind, target_kind;
     uint32_t flags;
-    int32_t dim;             /* d, 1..SDES_MAX_DIM */
+    int32_t dim;             /* d: 1..SDES_MAX_DIM on the fused engines, up to SDES_MAX_WIDE_DIM on the wide engine */
     int32_t n_steps;         /* T >= 1; ts has T+1 entries */
     int32_t n_hidden;        /* FourierMLP hidden (C->C) layers = num_layers-2 */
     int32_t te_hidden;       /* hidden layers of FourierMLP.timestep_embed (>=1; reference: 1) */
@@ -105,6 +107,16 @@ typedef struct SdesRolloutDesc {
     float* xs;               /* (T+1,B,d) out with SDES_F_RETURN_TRAJ, else NULL */
     void* workspace;         /* >= sdes_workspace_bytes(desc), 256-byte aligned */
     size_t workspace_bytes;
+    /* NICE target (target_kind = SDES_TARGET_NICE; distr/nice.py): `nice_couplings` additive couplings, each a
+     * ReLU MLP  half -> mid -> ... -> mid -> half  with `nice_hidden` hidden layers (nice_hidden + 1 Linear),
+     * half = d/2; coupling c transforms the even units if (nice_mask_config + c) % 2 == 1, else the odd units
+     * (Coupling.forward :64-95); then z = h * exp(scale) with a standard-logistic latent (:21-29, :109-124).
+     * nice_params (fp32, torch (out,in) row-major):
+     *   { in_w[mid*half] in_b[mid]  { mid_w[mid*mid] mid_b[mid] } x (nice_hidden-1)  out_w[half*mid] out_b[half] } x couplings
+     *   scale[d]                                                                                                  */
+    int32_t nice_couplings, nice_mid, nice_hidden, nice_mask_config;
+    const float* nice_params;
+    int64_t n_nice_params;
 } SdesRolloutDesc;
 
 /* ABI version of the loaded library (== SDES_ABI_VERSION of the header it was built from). */
@@ -117,8 +129,11 @@ const char* sdes_last_error(void);
 size_t sdes_workspace_bytes(const SdesRolloutDesc* desc);
 
 /* The whole rollout: replaces `loss.simulate(ts, x, ...)` (losses/oc.py:156,:286,:400).
- * Enqueues (1) a small prologue kernel that hoists everything x-independent into per-step
- * tables and (2) ONE persistent kernel that carries each trajectory through all T steps. */
+ * d <= SDES_MAX_DIM with an analytic target: enqueues (1) a small prologue kernel that hoists everything
+ * x-independent into per-step tables and (2) ONE persistent kernel that carries each trajectory through all
+ * T steps.  d > SDES_MAX_DIM or a NICE target (BASELINE cfg5): the wide engine — the state lives in HBM and
+ * every Linear of the control MLP and of the NICE couplings (forward and the input-gradient backward that
+ * gives the target score) is a tcgen05 GEMM launch with a fused epilogue, one fused update kernel per step. */
 int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream);
 
 /* 1 if the tcgen05 (tensor-core) engine handles this descriptor, 0 if only the fp32-FFMA engine

@@ -10,9 +10,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libsdes_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 CHANNELS = 64
 MAX_DIM = 64
+MAX_WIDE_DIM = 4096
 MAX_HIDDEN = 6
 MAX_COMPONENTS = 64
 
@@ -20,7 +21,7 @@ LOSS_TIME_REVERSAL, LOSS_REFERENCE_SDE, LOSS_EXP_INTEGRATOR = 0, 1, 2
 CTRL = {"clipped": 0, "score": 1, "lerp": 2, "lerp_prior": 3, "lerp_target": 4}
 LOSS = {"time_reversal": 0, "reference_sde": 1, "exp_integrator": 2}
 SDE_NONE, SDE_VP, SDE_CONST_OU = 0, 1, 2
-TARGET_GMM, TARGET_MULTIWELL, TARGET_FUNNEL = 0, 1, 2
+TARGET_GMM, TARGET_MULTIWELL, TARGET_FUNNEL, TARGET_NICE = 0, 1, 2, 3
 
 F_RND0_ZERO = 1 << 0
 F_COMPUTE_ITO = 1 << 1
@@ -56,6 +57,8 @@ class RolloutDesc(C.Structure):
         ("prior_loc", _fp), ("prior_scale", _fp), ("ref_loc", _fp), ("ref_scale", _fp),
         ("x0", _fp), ("noise", _fp), ("x_T", _fp), ("rnd", _fp), ("xs", _fp),
         ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+        ("nice_couplings", C.c_int32), ("nice_mid", C.c_int32), ("nice_hidden", C.c_int32),
+        ("nice_mask_config", C.c_int32), ("nice_params", _fp), ("n_nice_params", C.c_int64),
     ]
 
 

@@ -16,6 +16,11 @@ bool mma_supported(const KParams& p);
 int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad);
 int mma_groups_per_sm();
 cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t stream);
+// wide engine (sdes_wide.cu): d > SDES_MAX_DIM or a NICE target
+bool wide_engine_needed(const SdesRolloutDesc& d);
+const char* wide_validate(const SdesRolloutDesc& d);
+size_t wide_workspace_bytes(const SdesRolloutDesc& d);
+int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t* err);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -93,7 +98,7 @@ static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
     if (d->struct_bytes != sizeof(SdesRolloutDesc))
         return fail(-2, "desc.struct_bytes=%u but this library expects %zu", d->struct_bytes, sizeof(SdesRolloutDesc));
     if (d->abi_version != SDES_ABI_VERSION) return fail(-2, "desc.abi_version=%u, library is %d", d->abi_version, SDES_ABI_VERSION);
-    if (d->dim < 1 || d->dim > SDES_MAX_DIM) return fail(-3, "dim=%d not in [1,%d]", d->dim, SDES_MAX_DIM);
+    if (d->dim < 1 || d->dim > SDES_MAX_WIDE_DIM) return fail(-3, "dim=%d not in [1,%d]", d->dim, SDES_MAX_WIDE_DIM);
     if (d->n_steps < 1) return fail(-3, "n_steps=%d < 1", d->n_steps);
     if (d->batch < 0) return fail(-3, "batch < 0");
     if (d->traj_offset + (uint64_t)d->batch > 0xFFFFFFFFull) return fail(-3, "traj_offset + batch exceeds the 32-bit Philox trajectory counter");
@@ -102,7 +107,11 @@ static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
     if (d->loss_kind < 0 || d->loss_kind > SDES_LOSS_EXP_INTEGRATOR) return fail(-3, "bad loss_kind %d", d->loss_kind);
     if (d->ctrl_kind < 0 || d->ctrl_kind > SDES_CTRL_LERP_TARGET) return fail(-3, "bad ctrl_kind %d", d->ctrl_kind);
     if (d->sde_kind < 0 || d->sde_kind > SDES_SDE_CONST_OU) return fail(-3, "bad sde_kind %d", d->sde_kind);
-    if (d->target_kind < 0 || d->target_kind > SDES_TARGET_FUNNEL) return fail(-3, "bad target_kind %d", d->target_kind);
+    if (d->target_kind < 0 || d->target_kind > SDES_TARGET_NICE) return fail(-3, "bad target_kind %d", d->target_kind);
+    if (wide_engine_needed(*d)) {
+        const char* why = wide_validate(*d);
+        if (why != nullptr) return fail(-3, "wide engine (dim=%d): %s", d->dim, why);
+    }
     if (d->loss_kind != SDES_LOSS_EXP_INTEGRATOR && d->sde_kind == SDES_SDE_NONE) return fail(-3, "this loss needs an sde");
     if (d->ctrl_kind >= SDES_CTRL_LERP && d->sde_kind == SDES_SDE_NONE) return fail(-3, "Lerp controls need an sde");
     if (d->flags & SDES_F_HAS_GATE) {
@@ -120,6 +129,7 @@ static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
     if (!need_ptrs) return 0;
     if (!d->ts || !d->params || !d->x0 || !d->x_T || !d->rnd) return fail(-5, "ts/params/x0/x_T/rnd must be non-NULL");
     if (d->target_kind == SDES_TARGET_GMM && (!d->gmm_loc || !d->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");
+    if (d->target_kind == SDES_TARGET_NICE && !d->nice_params) return fail(-5, "nice_params is NULL");
     const bool need_prior = (d->loss_kind == SDES_LOSS_TIME_REVERSAL && !(d->flags & SDES_F_RND0_ZERO)) ||
                             d->ctrl_kind == SDES_CTRL_LERP || d->ctrl_kind == SDES_CTRL_LERP_PRIOR ||
                             (d->flags & SDES_F_REFERENCE_CTRL);
@@ -252,6 +262,7 @@ int64_t sdes_launch_count(void) { return g_launches.load(); }
 
 size_t sdes_workspace_bytes(const SdesRolloutDesc* desc) {
     if (validate(desc, false) != 0) return 0;
+    if (wide_engine_needed(*desc)) return wide_workspace_bytes(*desc);
     WsLayout w;
     ws_layout(*desc, w);
     return (size_t)w.total * sizeof(float);
@@ -259,6 +270,7 @@ size_t sdes_workspace_bytes(const SdesRolloutDesc* desc) {
 
 int sdes_tcgen05_supported(const SdesRolloutDesc* desc) {
     if (validate(desc, false) != 0) return 0;
+    if (wide_engine_needed(*desc)) return 1;  // every Linear of the wide engine is a tcgen05 GEMM
     KParams p;
     memset(&p, 0, sizeof(p));
     p.d = *desc;
@@ -275,6 +287,15 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     memset(&p, 0, sizeof(p));
     p.d = *desc;
     blob_layout(p.d, p.bl);
+    if (wide_engine_needed(*desc)) {
+        const size_t need = wide_workspace_bytes(*desc);
+        if (need > desc->workspace_bytes) return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, need);
+        if (desc->batch == 0) return 0;
+        cudaError_t we = cudaSuccess;
+        g_launches += launch_rollout_wide(p, reinterpret_cast<cudaStream_t>(stream_), &we);
+        if (we != cudaSuccess) return fail(-7, "wide engine launch failed: %s", cudaGetErrorString(we));
+        return 0;
+    }
     ws_layout(p.d, p.ws);
     if ((size_t)p.ws.total * sizeof(float) > desc->workspace_bytes)
         return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, (size_t)p.ws.total * sizeof(float));

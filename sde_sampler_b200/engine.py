@@ -45,6 +45,16 @@ def pack_params(spec: RolloutSpec) -> torch.Tensor:
     return torch.cat([p.reshape(-1).to(torch.float32) for p in parts])
 
 
+def pack_nice_params(tg: dict) -> torch.Tensor:
+    """Flat fp32 NICE blob (include/sdes_b200.h): per coupling the Linear layers in order, then the log-scale."""
+    parts = []
+    for c in tg["couplings"]:
+        for w, b in c["layers"]:
+            parts += [w, b]
+    parts.append(tg["scale"])
+    return torch.cat([p.reshape(-1).to(torch.float32) for p in parts])
+
+
 def pack_params_numel(spec: RolloutSpec) -> int:
     m = spec.mlp
     te = m["time_embed"]
@@ -138,6 +148,19 @@ def fill_desc(spec: RolloutSpec, *, batch: int, engine: str = "auto") -> tuple[_
     elif tg["kind"] == "funnel":
         d.target_kind = _cabi.TARGET_FUNNEL
         d.variance = float(tg["variance"])
+    elif tg["kind"] == "nice":
+        d.target_kind = _cabi.TARGET_NICE
+        cps = tg["couplings"]
+        d.nice_couplings = len(cps)
+        d.nice_hidden = len(cps[0]["layers"]) - 1
+        d.nice_mid = int(cps[0]["layers"][0][0].shape[0])
+        d.nice_mask_config = int(cps[0]["mask_config"])
+        for i, c in enumerate(cps):
+            if int(c["mask_config"]) != (d.nice_mask_config + i) % 2:
+                raise NotImplementedError("NICE couplings must alternate their mask (distr/nice.py:146-157)")
+        blob = pack_nice_params(tg)
+        d.nice_params, d.n_nice_params = blob.data_ptr(), blob.numel()
+        keep.append(blob)
     else:
         raise NotImplementedError(tg["kind"])
     if spec.prior is not None:

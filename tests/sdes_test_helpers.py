@@ -71,6 +71,18 @@ def build_from_spec(spec: dict, device, engine: str = "simt", **loss_kw):
                                        shift=float(tg["shift"]))
     elif tg["kind"] == "funnel":
         target = plugins.Funnel(dim=dim, variance=float(tg["variance"]), log_norm_const=float(tg.get("log_norm_const", 0.0)))
+    elif tg["kind"] == "nice":
+        cps = tg["couplings"]
+        mid, half = np.asarray(cps[0]["layers"][0][0]).shape
+        model = plugins.NiceModel(plugins.StandardLogistic(), coupling=len(cps), in_out_dim=dim, mid_dim=int(mid),
+                                  hidden=len(cps[0]["layers"]) - 1, mask_config=int(cps[0]["mask_config"]))
+        for cm, c in zip(model.coupling, cps):
+            lins = [cm.in_block[0]] + [b[0] for b in cm.mid_block] + [cm.out_block]
+            for lin, (w, b) in zip(lins, c["layers"]):
+                _load_linear(lin, w, b)
+        with torch.no_grad():
+            model.scaling.scale.copy_(torch.as_tensor(tg["scale"]).reshape(1, -1))
+        target = plugins.Nice(model=model, log_norm_const=float(tg.get("log_norm_const", 0.0)))
     else:
         raise ValueError(tg["kind"])
 

@@ -65,9 +65,19 @@ def test_descriptor_validation_without_gpu(lib):
     d = _valid_desc()
     assert lib.sdes_workspace_bytes(C.byref(d)) > 0, lib.sdes_last_error()
     bad = _valid_desc()
-    bad.dim = 65
+    bad.dim = _cabi.MAX_WIDE_DIM + 1
     assert lib.sdes_workspace_bytes(C.byref(bad)) == 0
     assert b"dim" in lib.sdes_last_error()
+    # d > 64 selects the wide engine: its workspace holds the state, the operand images and the layer activations
+    wide = _valid_desc()
+    wide.dim = 100
+    wide.n_params += (100 - 50) * 2 * 64 + (100 - 50)
+    assert lib.sdes_workspace_bytes(C.byref(wide)) > lib.sdes_workspace_bytes(C.byref(d))
+    assert lib.sdes_tcgen05_supported(C.byref(wide)) == 1
+    bad = _valid_desc()
+    bad.dim, bad.target_kind = 50, _cabi.TARGET_NICE  # NICE needs its parameter blob and an even dim
+    assert lib.sdes_workspace_bytes(C.byref(bad)) == 0
+    assert b"wide engine" in lib.sdes_last_error()
     bad = _valid_desc()
     bad.n_params += 1
     assert lib.sdes_workspace_bytes(C.byref(bad)) == 0
