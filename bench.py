@@ -263,6 +263,127 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------ cfg5 (wide engine)
+def main_cfg5(args):
+    """BASELINE configs[4] on ONE GPU's shard: nice/mnist d=784, DDS + lv, T=257 (cosine grid), 4 096 trajectories
+    per GPU (32 768 over 8).  Same JSON keys as the headline line; `roofline` counts the Linear layers of the control
+    MLP and of the NICE forward + input-gradient backward (7.68e7 FLOP per trajectory-step, 2 per multiply-add; the
+    three bf16 passes of the split-precision GEMM are NOT counted) against the measured dense bf16 peak."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_wide
+
+    from sde_sampler_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B = 4096 if args.batch == BATCH_PER_GPU else args.batch
+    dim, mid, hidden = 784, 1000, 5
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import torch_port
+        from sde_sampler_b200.spec import extract_spec
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        o = bench_wide.build(torch.device("cpu"), dim, mid, hidden, "simt", steps=4)
+        spec = extract_spec(o["loss"], "exp_integrator", o["ts"], o["terminal"], o["second"], train=True, compute_ito=True).to_dict()
+        sample, T = 64, 4
+        x0 = o["prior"].sample((sample,))
+        times = []
+        for _ in range(args.steps + args.warmup):
+            t0 = time.perf_counter()
+            torch_port.rollout(spec, x0.numpy(), generator=torch.Generator().manual_seed(0))
+            times.append(time.perf_counter() - t0)
+        dt = sum(times[args.warmup:]) / max(1, len(times[args.warmup:]))
+        value = sample * T / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"NICE d={dim} mid={mid} hidden={hidden} solver=dds loss=lv T=257 batch={B}/GPU",
+                                     "sample": f"{sample} trajectories x {T} of 257 time steps per step"},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                           "sample": f"oracle/torch_port.py on {sample} trajectories x {T} time steps"},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    lib = _cabi.lib()
+    o = bench_wide.build(device, dim, mid, hidden, "auto" if args.engine == "auto" else args.engine)
+    loss, ts = o["loss"], o["ts"]
+    loss.process_group = pg
+    T = ts.shape[0] - 1
+    torch.manual_seed(100 + rank)
+    x0 = o["prior"].sample((B,))
+    x0_host = x0.cpu().pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    steps = min(args.steps, 5)
+    for _ in range(2):
+        loss(ts, x0, o["terminal"], o["second"])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = lib.sdes_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        val, _m = loss(ts, x0, o["terminal"], o["second"])
+    b.record()
+    barrier()
+    launches = lib.sdes_launch_count() - n0
+    clocks = sampler.stop()
+    total_ms = a.elapsed_time(b)
+    a.record()
+    for _ in range(steps):
+        v, _m = loss(ts, x0_host.to(device, non_blocking=True), o["terminal"], o["second"])
+        host_loss = v.item()
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = times.tolist()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        f = bench_wide.flops_per_traj_step(dim, mid, hidden)
+        ts_per_s = world * B * T * steps / (total_ms * 1e-3)
+        ach = B * T * steps * f / (total_ms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": ts_per_s, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 2,
+                "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (every Linear as 3 bf16 tcgen05 passes over hi/lo-split operands, fp32 accumulate; f32 elsewhere)",
+                "data": "synthetic",
+                "config": {"workload": f"NICE d={dim} mid={mid} hidden={hidden} solver=dds loss=lv T={T} batch={B}/GPU", "engine": "wide/tcgen05",
+                           "global_batch": world * B, "l2": "working set per step (weights 153 MB + activations) exceeds the 126 MB L2",
+                           "noise": "in-kernel Philox4x32-10", "loss_value": float(val)},
+                "clocks": clocks,
+                "e2e": {"value": world * B * T * steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms / steps, "loss_value": host_loss},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                             "flops_per_traj_step": f, "peak_source": "MEASURED_PEAKS.json bf16 dense, sustained (a step is thousands of GEMM launches)"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # -------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -273,8 +394,13 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "tcgen05", "simt"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="trajectories per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="gmm50", choices=["gmm50", "cfg5"],
+                    help="gmm50 = north-star headline (default, the driver's line); cfg5 = BASELINE configs[4] per-GPU shard "
+                         "(NICE d=784 mid=1000, DDS+lv, T=257, 4096 trajectories per GPU) on the wide engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "cfg5":
+        return main_cfg5(args)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -311,7 +437,9 @@ def main():
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step(x):
-        return loss(ts, x, o["terminal"], o["second"])
+        # the metric is the forward rollout; the training step with its backward is timed separately below
+        with torch.no_grad():
+            return loss(ts, x, o["terminal"], o["second"])
 
     def barrier():
         if world > 1:
@@ -363,6 +491,25 @@ def main():
         k_ms.append(a.elapsed_time(b))
     kernel_ms = statistics.median(k_ms)
 
+    # ---- training step: loss(...) with grad + loss.backward() (lv gradient on the tensor cores, csrc/sdes_grad.cu)
+    from sde_sampler_b200.spec import ctrl_parameters
+    train_ms = None
+    try:
+        tm = []
+        for k in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for prm in ctrl_parameters(o["ctrl"]):
+                prm.grad = None
+            a.record()
+            v, _m = loss(ts, x0, o["terminal"], o["second"])
+            v.backward()
+            b.record()
+            torch.cuda.synchronize(device)
+            tm.append(a.elapsed_time(b))
+        train_ms = statistics.median(tm[1:])
+    except Exception as exc:  # reported, never hidden
+        train_ms = f"failed: {type(exc).__name__}: {exc}"
+
     # ---- timed region 2: end to end through the plug-in with host buffers
     barrier()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -412,6 +559,9 @@ def main():
                          "hbm_algorithmic_bytes": B * (8 * DIM + 4),
                          "hbm_gbs": B * (8 * DIM + 4) / (kernel_ms * 1e-3) / 1e9},
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
+            "train_step": {"what": "loss(ts, x0, ...) with grad + loss.backward(): rollout keeping xs, then the lv gradient "
+                                   "(forward + dgrad + wgrad GEMMs over all B*T rows)", "ms": train_ms,
+                           "traj_steps_per_s": (world * traj_steps / (train_ms * 1e-3)) if isinstance(train_ms, float) else None},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -141,6 +141,31 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream);
  * tensor-core engine on an unsupported descriptor is an error. */
 int sdes_tcgen05_supported(const SdesRolloutDesc* desc);
 
+/* Gradient of the log-variance loss with respect to the control network — `loss.backward()` of
+ * `Trainable.step` (solver/base.py:404-407) for loss.method = lv.  In the lv losses the state is
+ * driven by the detached control (losses/oc.py:60-64) and the running cost has zero derivative, so
+ *     d loss / d theta = sum_b w[b] sum_s J_theta g(s, x_{b,s})^T c_{b,s},   c = eps sqrt(dt)  (DDS: sigma beta_k eps)
+ * — one backward pass of the control MLP over all B*T rows of the stored trajectory, no backpropagation through
+ * time.  `desc` is the descriptor of the forward call (same seed / traj_offset / noise so that eps is re-drawn
+ * identically; x0/x_T/rnd/xs of desc are ignored; desc->workspace must hold sdes_lv_grad_workspace_bytes).
+ * d <= SDES_MAX_DIM, analytic targets.  Outputs (overwritten):
+ *   grad_params (n_params floats, the layout of `params`): in_w, h_w/h_b, out_w/out_b; every other entry 0
+ *   grad_emb    (T, 64)        d loss / d (timestep_embed(s_i) + in_b)   -> in_b gradient = column sums; the caller
+ *   grad_gate   (T, gate_dim)  d loss / d gate(s_i)                         chains both through the TimeEmbed nets */
+typedef struct SdesLvGradDesc {
+    uint32_t struct_bytes;   /* = sizeof(SdesLvGradDesc), checked */
+    uint32_t reserved;
+    const float* xs;         /* (T+1, B, d) trajectory written by the forward call with SDES_F_RETURN_TRAJ */
+    const float* w;          /* (B) d loss / d rnd_b (0 for filtered trajectories) */
+    float* grad_params;
+    float* grad_emb;
+    float* grad_gate;        /* NULL when the control has no gate */
+    int64_t chunk_rows;      /* rows (trajectory, step) per pass; 0 = default (2^20) */
+} SdesLvGradDesc;
+
+size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);
+int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream);
+
 /* Statistics of rnd that BaseOCLoss.filter/compute_loss/compute_results reduce to
  * (losses/oc.py:50-123).  out_stats (device, 8 doubles):
  *   [0] n_kept  [1] sum(rnd | kept)  [2] sum(rnd^2 | kept)  [3] max(-rnd | kept)

@@ -67,6 +67,26 @@ def run_case(name: str, case: dict) -> dict:
     out["train"] = {"x_T": x_T.detach().numpy().copy(), "rnd": rnd.detach().numpy().copy(),
                     "loss": float(lval), "n_filtered": int(loss.n_filtered - n_before)}
 
+    # --- gradient of the lv loss w.r.t. every control parameter by the reference's own autograd
+    #     (`loss.backward()` of Trainable.step, solver/base.py:404-407), flattened in parameter-blob order
+    if method == "lv" and d <= 64 and not str(case["target"]).startswith("nice"):
+        from sde_sampler_b200.spec import ctrl_parameters
+
+        params = ctrl_parameters(built["ctrl"])
+        for q in params:
+            q.grad = None
+        n_keep = loss.n_filtered
+        with ref_harness.injected_noise(noise_t):
+            x_g, rnd_g, _ = loss.simulate(ts, x0.clone(), compute_ito_int=compute_ito, change_sde_ctrl=change,
+                                          return_traj=False, **kw, **sim_kw)
+        lg, _ = loss.compute_loss(rnd_g, samples=x_g)
+        lg.backward()
+        loss.n_filtered = n_keep
+        out["train"]["grad_blob"] = np.concatenate(
+            [(q.grad if q.grad is not None else torch.zeros_like(q)).detach().reshape(-1).numpy() for q in params]).astype(np.float32)
+        for q in params:
+            q.grad = None
+
     # target object proxy so that extract_spec sees solver-like clipped_target_unnorm_log_prob
     class _SolverShim:
         def __init__(self, target, clip_target):

@@ -62,8 +62,19 @@ class RolloutDesc(C.Structure):
     ]
 
 
+class LvGradDesc(C.Structure):
+    """struct SdesLvGradDesc (include/sdes_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("reserved", C.c_uint32),
+        ("xs", _fp), ("w", _fp), ("grad_params", _fp), ("grad_emb", _fp), ("grad_gate", _fp),
+        ("chunk_rows", C.c_int64),
+    ]
+
+
 # every symbol include/sdes_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
+    "sdes_lv_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
+    "sdes_rollout_lv_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
     "sdes_version": (C.c_int, []),
     "sdes_last_error": (C.c_char_p, []),
     "sdes_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc)]),

@@ -21,6 +21,9 @@ bool wide_engine_needed(const SdesRolloutDesc& d);
 const char* wide_validate(const SdesRolloutDesc& d);
 size_t wide_workspace_bytes(const SdesRolloutDesc& d);
 int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t* err);
+// lv gradient (sdes_grad.cu)
+size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
+int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -326,6 +329,48 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     }
     if (e != cudaSuccess) return fail(-7, "rollout kernel launch failed: %s", cudaGetErrorString(e));
     g_launches++;
+    return 0;
+}
+
+static int grad_setup(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, KParams& p, bool& simt) {
+    int rc = validate(desc, false);
+    if (rc != 0) return rc;
+    if (g == nullptr || g->struct_bytes != sizeof(SdesLvGradDesc)) return fail(-2, "SdesLvGradDesc is NULL or has the wrong struct_bytes");
+    if (wide_engine_needed(*desc)) return fail(-8, "the lv gradient is implemented for d <= %d with analytic targets", SDES_MAX_DIM);
+    memset(&p, 0, sizeof(p));
+    p.d = *desc;
+    simt = (desc->flags & SDES_F_MLP_SIMT) != 0;
+    p.d.flags = (desc->flags | SDES_F_MLP_SIMT) & ~(uint32_t)SDES_F_RETURN_TRAJ;  // fp32 tables / target images of the fused prologue
+    blob_layout(p.d, p.bl);
+    ws_layout(p.d, p.ws);
+    return 0;
+}
+
+size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g) {
+    KParams p;
+    bool simt;
+    if (grad_setup(desc, g, p, simt) != 0) return 0;
+    return lv_grad_workspace_bytes(p.d, p.ws.total * (int64_t)sizeof(float), g->chunk_rows);
+}
+
+int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream_) {
+    g_err[0] = 0;
+    KParams p;
+    bool simt;
+    int rc = grad_setup(desc, g, p, simt);
+    if (rc != 0) return rc;
+    if (!desc->ts || !desc->params || !desc->workspace) return fail(-5, "ts/params/workspace must be non-NULL");
+    if (!g->xs || !g->w || !g->grad_params || !g->grad_emb) return fail(-5, "xs/w/grad_params/grad_emb must be non-NULL");
+    if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
+    if (desc->target_kind == SDES_TARGET_GMM && (!desc->gmm_loc || !desc->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");
+    if (reinterpret_cast<uintptr_t>(desc->workspace) % 256 != 0) return fail(-5, "workspace must be 256-byte aligned");
+    const int64_t fused = p.ws.total * (int64_t)sizeof(float);
+    const size_t need = lv_grad_workspace_bytes(p.d, fused, g->chunk_rows);
+    if (need > desc->workspace_bytes) return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, need);
+    if (desc->batch == 0) return 0;
+    cudaError_t e = cudaSuccess;
+    g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e);
+    if (e != cudaSuccess) return fail(-7, "lv gradient launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -1,0 +1,581 @@
+// sdes_grad.cu — gradient of the log-variance loss with respect to the control network (SURVEY §8f-1:
+// `loss.backward()` of `Trainable.step`, solver/base.py:404-407, for loss.method = lv).
+//
+// In the lv losses the state is driven by the DETACHED control (`sde_ctrl = generative_ctrl.detach()`,
+// losses/oc.py:60-64), so x_s carries no gradient, and the running cost g.(u - g/2) dt has zero derivative at
+// u = g.  What is left is the Ito term (oc.py:218-219, :330-331, :440-443):
+//     d rnd_b / d theta = sum_s  J_theta g(s, x_{b,s})^T  c_{b,s},     c = eps sqrt(dt)   (sigma beta_k eps for DDS)
+//     d loss  / d theta = sum_b  w_b  d rnd_b / d theta,               w_b = 2 (rnd_b - mean) / (n - 1)   (kept b)
+// i.e. ONE backward pass of the control MLP over all B*T (trajectory, step) rows with the output cotangent
+// w_b c_{b,s} 1[|NN| <= clip_model] — no backpropagation through time.  The rows come from the stored trajectory
+// xs (T+1, B, d) of the forward rollout and the noise is re-drawn from the same Philox counters (or re-read from
+// HBM in parity mode).  Rows are processed in time chunks; per chunk
+//     pack x rows -> operand image | 4 forward GEMMs (GELU and GELU' images) | cotangent kernel |
+//     3 dgrad GEMMs (x GELU') | 4 wgrad GEMMs + bias / time-embedding column sums
+// all on tcgen05: forward and dgrad are `linear_mma_kernel` (sdes_linear.cuh), wgrad is `wgrad_mma_kernel` below,
+// which contracts over the ROW dimension by reading the very same activation images as MN-major operands.
+// Outputs: gradients of the x-dependent layers in the parameter-blob layout, d loss / d emb (T, 64) and
+// d loss / d gate (T, gate_dim); the caller chains the last two through the two tiny time-embedding networks.
+#include <cuda_bf16.h>
+
+#include "sdes_linear.cuh"
+#include "sdes_step.cuh"
+
+namespace sdes {
+namespace grad {
+
+using namespace wide;
+
+struct GradPlan {
+    int d, P, pc, nh, T;
+    int64_t B, Bp;
+    int chunk_steps, n_chunks;
+    int64_t chunk_rows;
+    int m_tiles;  // per full chunk
+    Lin f_in, f_h[SDES_MAX_HIDDEN], f_out;   // forward operands
+    Lin b_h[SDES_MAX_HIDDEN], b_out;         // transposed operands (dgrad)
+    int64_t embb;                            // (T, 64): timestep_embed(s) + b_in
+    int64_t ximg, a_img[SDES_MAX_HIDDEN + 1], gp_img[SDES_MAX_HIDDEN + 1], nn, dnn_img, dh_img[2], ones;
+    int64_t total;
+};
+
+static void make_plan(const SdesRolloutDesc& d, int64_t chunk_rows_req, int64_t base, GradPlan& p) {
+    p.d = d.dim;
+    p.P = round_up(d.dim, 64);
+    p.pc = p.P / 64;
+    p.nh = d.n_hidden;
+    p.T = d.n_steps;
+    p.B = d.batch;
+    p.Bp = (d.batch + 127) / 128 * 128;
+    int64_t want = chunk_rows_req > 0 ? chunk_rows_req : (1 << 20);
+    p.chunk_steps = (int)(want / p.Bp);
+    if (p.chunk_steps < 1) p.chunk_steps = 1;
+    if (p.chunk_steps > p.T) p.chunk_steps = p.T;
+    p.n_chunks = (p.T + p.chunk_steps - 1) / p.chunk_steps;
+    p.chunk_rows = (int64_t)p.chunk_steps * p.Bp;
+    p.m_tiles = (int)(p.chunk_rows / 128);
+    int64_t o = base;
+    auto take = [&](int64_t bytes) { int64_t r = o; o = align256(o + bytes); return r; };
+    auto lin = [&](Lin& l, int N, int Kin, bool bias) {
+        set_tiling(l, N, Kin);
+        l.w_off = take(lin_image_bytes(l));
+        l.b_off = bias ? take((int64_t)l.n_pad * 4) : -1;
+    };
+    lin(p.f_in, C, p.P, false);
+    for (int l = 0; l < p.nh; ++l) lin(p.f_h[l], C, C, true);
+    lin(p.f_out, p.P, C, true);
+    for (int l = 0; l < p.nh; ++l) lin(p.b_h[l], C, C, false);
+    lin(p.b_out, C, p.P, false);
+    p.embb = take((int64_t)p.T * C * 4);
+    p.ones = take(64 * 4);
+    const int64_t img1 = (int64_t)p.m_tiles * A_BLOCK, imgp = img1 * p.pc;
+    p.ximg = take(imgp);
+    for (int l = 0; l <= p.nh; ++l) {
+        p.a_img[l] = take(img1);
+        p.gp_img[l] = take(img1);
+    }
+    p.nn = take(p.chunk_rows * (int64_t)p.P * 4);
+    p.dnn_img = take(imgp);
+    p.dh_img[0] = take(img1);
+    p.dh_img[1] = take(img1);
+    p.total = o;
+}
+
+// ---------------------------------------------------------------------------- small kernels
+__global__ void embb_kernel(const float* __restrict__ emb, const float* __restrict__ in_b, float* __restrict__ out, int n, float* __restrict__ ones) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = emb[e] + in_b[e & (C - 1)];
+    if (e < 64) ones[e] = 1.0f;
+}
+
+// rows (s, b) of the stored trajectory -> A operand image of the input layer (natural feature order, K = P)
+__global__ void __launch_bounds__(128) pack_rows_kernel(const float* __restrict__ xs, int64_t B, int64_t Bp, int dim, int pc, int s0,
+                                                        uint8_t* __restrict__ ximg) {
+    const int mt = blockIdx.x, r = threadIdx.x;
+    const int64_t rr = (int64_t)mt * 128 + r;
+    const int64_t s = s0 + rr / Bp, b = rr % Bp;
+    const float* xrow = xs + (s * B + (b < B ? b : 0)) * dim;
+    for (int k0 = 0; k0 < pc * 64; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (b < B && k0 + q < dim) ? __ldg(xrow + k0 + q) : 0.f;
+        uint4 hi, lo;
+        split_pair(v[0], v[1], hi.x, lo.x);
+        split_pair(v[2], v[3], hi.y, lo.y);
+        split_pair(v[4], v[5], hi.z, lo.z);
+        split_pair(v[6], v[7], hi.w, lo.w);
+        uint8_t* o = ximg + (int64_t)mt * pc * A_BLOCK + img_group_offset(r, k0);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + A_HALF) = lo;
+    }
+}
+
+// Output cotangent of the control network for every row of the chunk, and the gate's gradient.
+//   delta_j = w_b c_j 1[|NN_j| <= clip_model],   c_j = eps_j sqrt(dt)  (DDS: sigma beta_k eps_j)
+//   d gate(s) += w_b sum_j c_j * outer * clip(inner_j)            (the score part of models/reparam.py without its gate)
+struct CotArgs {
+    KParams kp;               // descriptor + fused-engine workspace layout (tables and target images of sdes_prepare.cu)
+    const float* xs;
+    const float* w;
+    const float* nn;          // (rows, P)
+    const float* ones;
+    uint8_t* dnn_img;
+    float* grad_gate;         // (T, gate_dim) or NULL
+    int P, pc, s0;
+    int64_t Bp;
+};
+
+template <int DPAD>
+__global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ CotArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* smem = smem_f;
+    __shared__ float s_red[4];
+    const KParams& p = a.kp;
+    const SdesRolloutDesc& d = p.d;
+    const float* ws = reinterpret_cast<const float*>(d.workspace);
+    const int dim = d.dim, K = d.n_components, tid = threadIdx.x;
+    const int K2 = (K + 1) & ~1;
+    float* s_mu = smem;
+    float* s_h = s_mu + K2 * DPAD;
+    float* s_c = s_h + K2 * DPAD;
+    float* s_prior = s_c + 64;
+    float* s_gsum = s_prior + 2 * DPAD + 4;  // DPAD per-dimension gate sums
+    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
+        s_mu[e] = ws[p.ws.gmm_mu + e];
+        s_h[e] = ws[p.ws.gmm_h + e];
+    }
+    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
+    for (int e = tid; e < 2 * DPAD + 4; e += blockDim.x) s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
+    for (int e = tid; e < DPAD; e += blockDim.x) s_gsum[e] = 0.f;
+    __syncthreads();
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_prior};
+
+    const int mt = blockIdx.x;
+    const int64_t rr = (int64_t)mt * 128 + tid, B = d.batch;
+    const int s = a.s0 + (int)(rr / a.Bp);
+    const int64_t b = rr % a.Bp;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : 0;
+    float x[DPAD];
+    const float* xrow = a.xs + ((int64_t)s * B + bb) * dim;
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(xrow + j) : 0.f;
+    const float* tab = ws + p.ws.tab + (int64_t)s * TAB_STRIDE;
+    const StepCoef c = make_step_coef(d, tab);
+    const float wb = valid ? a.w[bb] : 0.f;
+    const float cscale = wb * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
+    const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
+    const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
+    const float* nnrow = a.nn + rr * a.P;
+    const bool want_gate = a.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
+    float sc[DPAD];
+    if (want_gate) {
+        score_part<DPAD>(d, x, sc, tsm, a.ones, tab[TAB_SIGMA], tab[TAB_LERP_W]);  // gate = 1: outer * clip(inner)
+    } else {
+#pragma unroll
+        for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
+    }
+    float gsum = 0.f;
+    float cot[DPAD];
+#pragma unroll
+    for (int q = 0; q < DPAD / 4; ++q) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * q < dim) {
+            if (c.from_hbm) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < dim) ? nrow[4 * q + r] : 0.f;
+            } else {
+                const float4 n4 = normal4_call(c.k0, c.k1, traj, (uint32_t)s, (uint32_t)q);
+                e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = 4 * q + r;
+            const float cj = (j < dim) ? cscale * e[r] : 0.f;
+            const float nnj = (j < dim) ? nnrow[j] : 0.f;
+            cot[j] = (fabsf(nnj) <= c.cm) ? cj : 0.f;  // d clip(NN) / d NN (torch.clip passes the gradient on [-c, c])
+            if (d.gate_dim == 1) gsum = fmaf(cj, sc[j], gsum);
+            else if (want_gate && cj != 0.f) atomicAdd(&s_gsum[j], cj * sc[j]);
+        }
+    }
+    // delta image (K = P = 64, natural feature order; this path serves d <= 64)
+#pragma unroll
+    for (int k0 = 0; k0 < 64; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (k0 + q < DPAD) ? cot[(k0 + q < DPAD) ? k0 + q : 0] : 0.f;
+        uint4 hi, lo;
+        split_pair(v[0], v[1], hi.x, lo.x);
+        split_pair(v[2], v[3], hi.y, lo.y);
+        split_pair(v[4], v[5], hi.z, lo.z);
+        split_pair(v[6], v[7], hi.w, lo.w);
+        uint8_t* o = a.dnn_img + (int64_t)mt * a.pc * A_BLOCK + img_group_offset(tid, k0);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + A_HALF) = lo;
+    }
+    if (!want_gate) return;
+    const float gmask = fabsf(ws[p.ws.gate + (int64_t)s * p.ws.dpad]) < c.cm ? 1.0f : 0.f;  // d clip(gate) / d gate (scalar gate)
+    if (d.gate_dim == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = gsum;
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.grad_gate + s, gmask * (s_red[0] + s_red[1] + s_red[2] + s_red[3]));
+    } else {
+        __syncthreads();
+        for (int j = tid; j < dim; j += blockDim.x) {
+            const float gm = fabsf(ws[p.ws.gate + (int64_t)s * p.ws.dpad + j]) < c.cm ? 1.0f : 0.f;
+            atomicAdd(a.grad_gate + (int64_t)s * dim + j, gm * s_gsum[j]);
+        }
+    }
+}
+
+// column sums of a delta image: bias gradients, and per-time-step sums for d loss / d emb
+__global__ void __launch_bounds__(128) colsum_kernel(const uint8_t* __restrict__ img, int n_chunks, int n_valid, float* __restrict__ out,
+                                                     int mt_div, int64_t mt_stride) {
+    __shared__ float s_part[16][64];
+    const int mt = blockIdx.x, tid = threadIdx.x, kg = tid & 7, rs = tid >> 3;
+    float* dst = out + (mt_div > 0 ? (int64_t)(mt / mt_div) * mt_stride : 0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const uint8_t* blk = img + ((int64_t)mt * n_chunks + ch) * A_BLOCK;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = rs; r < 128; r += 16) {
+            float h[8], l[8];
+            unpack8(*reinterpret_cast<const uint4*>(blk + (kg * 128 + r) * 16), h);
+            unpack8(*reinterpret_cast<const uint4*>(blk + A_HALF + (kg * 128 + r) * 16), l);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += h[q] + l[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_part[rs][kg * 8 + q] = acc[q];
+        __syncthreads();
+        if (tid < 64) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s += s_part[i][tid];
+            const int f = ch * 64 + tid;
+            if (f < n_valid && s != 0.f) atomicAdd(dst + f, s);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ wgrad GEMM
+// dW[n][k] += sum_rows delta[row][n] a[row][k] for one 64 x 64 block (delta chunk cd, activation chunk ca): the
+// contraction runs over the ROWS, so the activation images are read as MN-major operands (inside a block the
+// element (row r, feature f) sits at ((f/8)*128 + r)*16 + (f%8)*2 bytes: 8 features contiguous, rows 16 B apart,
+// row groups 128 B apart (LBO), feature groups 2048 B apart (SBO)).  A = [delta_hi ; delta_lo] spans the whole
+// 32 KB block as M = 128 "features", so D rows 0-63 and 64-127 are the hi and lo parts of the same gradient block;
+// B = a_hi, then a_lo.  Each CTA sums its share of the row tiles in TMEM and adds the block to global memory once.
+struct WgradArgs {
+    const uint8_t* d_img; int d_chunks;   // delta image, [m_tile][d_chunks] blocks
+    const uint8_t* a_img; int a_chunks;   // activation image
+    int m_tiles;
+    float* dw; int ldw;                   // row-major (out, in) gradient, += via atomics
+    int n_valid, k_valid;
+};
+
+__device__ __forceinline__ uint32_t idesc_bf16_mn(int M, int N) {
+    return tc::idesc_bf16(M, N) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+}
+
+__global__ void __launch_bounds__(LIN_THREADS, 1) wgrad_mma_kernel(const __grid_constant__ WgradArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_b[];
+    uint8_t* smem = smem_b;
+    __shared__ uint64_t s_full[3], s_empty[3], s_acc;
+    __shared__ uint32_t s_tmem;
+    constexpr int STAGES = 3;
+    constexpr uint32_t STAGE_BYTES = 2u * A_BLOCK;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pair = blockIdx.x, cd = pair / a.a_chunks, ca = pair % a.a_chunks;
+    const int split = blockIdx.y, n_split = gridDim.y;
+    const int n_my = a.m_tiles > split ? (a.m_tiles - split + n_split - 1) / n_split : 0;
+
+    if (warp == 1) {
+        tc::tmem_alloc(&s_tmem, 64);
+        tc::tmem_relinquish();
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&s_full[s], 1);
+            tc::mbar_init(&s_empty[s], 1);
+        }
+        tc::mbar_init(&s_acc, 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_d = s_tmem;
+    if (n_my > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int i = 0; i < n_my; ++i) {
+                    const int s = i % STAGES, it = i / STAGES;
+                    const int64_t mt = split + (int64_t)i * n_split;
+                    if (it > 0) tc::mbar_wait(&s_empty[s], (uint32_t)((it - 1) & 1));
+                    tc::mbar_arrive_expect_tx(&s_full[s], STAGE_BYTES);
+                    uint8_t* dst = smem + (size_t)s * STAGE_BYTES;
+                    const uint8_t* dp = a.d_img + (mt * a.d_chunks + cd) * A_BLOCK;
+                    const uint8_t* ap = a.a_img + (mt * a.a_chunks + ca) * A_BLOCK;
+                    tc::bulk_g2s(dst, dp, A_HALF, &s_full[s]);
+                    tc::bulk_g2s(dst + A_HALF, dp + A_HALF, A_HALF, &s_full[s]);
+                    tc::bulk_g2s(dst + A_BLOCK, ap, A_HALF, &s_full[s]);
+                    tc::bulk_g2s(dst + A_BLOCK + A_HALF, ap + A_HALF, A_HALF, &s_full[s]);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = idesc_bf16_mn(128, 64);
+                for (int i = 0; i < n_my; ++i) {
+                    const int s = i % STAGES, it = i / STAGES;
+                    tc::mbar_wait(&s_full[s], (uint32_t)(it & 1));
+                    tc::fence_after();
+                    const uint32_t dl = tc::smem_u32(smem + (size_t)s * STAGE_BYTES), ah = dl + A_BLOCK, al = ah + A_HALF;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
+                        const uint64_t da = tc::smem_desc_kmajor(dl + (uint32_t)ks * 256u, 128u, 2048u);
+                        const uint64_t dbh = tc::smem_desc_kmajor(ah + (uint32_t)ks * 256u, 128u, 2048u);
+                        const uint64_t dbl = tc::smem_desc_kmajor(al + (uint32_t)ks * 256u, 128u, 2048u);
+                        mma_f16_ss(tmem_d, da, dbl, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                        mma_f16_ss(tmem_d, da, dbh, idesc, 1u);
+                    }
+                    tc::mma_commit(&s_empty[s]);
+                }
+                tc::mma_commit(&s_acc);
+            }
+        } else {
+            const int q = warp & 3, r = q * 32 + lane;  // D row = feature (hi part for r < 64, lo part above)
+            tc::mbar_wait(&s_acc, 0);
+            tc::fence_after();
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+            const int n = cd * 64 + (r & 63);
+            for (int c0 = 0; c0 < 64; c0 += 8) {
+                float v[8];
+                tc::tmem_ld8(taddr + (uint32_t)c0, v);
+                tc::wait_ld_tie<8>(v);
+                if (n < a.n_valid) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = ca * 64 + c0 + e;
+                        if (k < a.k_valid && v[e] != 0.f) atomicAdd(a.dw + (int64_t)n * a.ldw + k, v[e]);
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_d, 64);
+}
+
+// the same contraction on the CUDA cores (SDES_F_MLP_SIMT cross-check)
+__global__ void __launch_bounds__(64) wgrad_simt_kernel(const WgradArgs a) {
+    const int pair = blockIdx.x, cd = pair / a.a_chunks, ca = pair % a.a_chunks;
+    const int nl = threadIdx.x, n = cd * 64 + nl;
+    for (int k0 = 0; k0 < 64; k0 += 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int64_t mt = blockIdx.y; mt < a.m_tiles; mt += gridDim.y) {
+            const uint8_t* dp = a.d_img + (mt * a.d_chunks + cd) * A_BLOCK + (nl >> 3) * 2048 + (nl & 7) * 2;
+            const uint8_t* ap = a.a_img + (mt * a.a_chunks + ca) * A_BLOCK + (k0 >> 3) * 2048;
+            for (int r = 0; r < 128; ++r) {
+                const uint16_t dh = *reinterpret_cast<const uint16_t*>(dp + r * 16), dl = *reinterpret_cast<const uint16_t*>(dp + A_HALF + r * 16);
+                const float dv = __uint_as_float((uint32_t)dh << 16) + __uint_as_float((uint32_t)dl << 16);
+                float ah[8], al[8];
+                unpack8(*reinterpret_cast<const uint4*>(ap + r * 16), ah);
+                unpack8(*reinterpret_cast<const uint4*>(ap + A_HALF + r * 16), al);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(dv, ah[e] + al[e], acc[e]);
+            }
+        }
+        if (n < a.n_valid) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = ca * 64 + k0 + e;
+                if (k < a.k_valid && acc[e] != 0.f) atomicAdd(a.dw + (int64_t)n * a.ldw + k, acc[e]);
+            }
+        }
+    }
+}
+
+template <int DPAD>
+static cudaError_t launch_cot_t(const CotArgs& a, int m_tiles, cudaStream_t stream) {
+    const int K2 = (a.kp.d.n_components + 1) & ~1;
+    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * DPAD + 4 + DPAD) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(cotangent_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cotangent_kernel<DPAD><<<m_tiles, 128, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_cot(const CotArgs& a, int m_tiles, cudaStream_t stream) {
+    switch (a.kp.ws.dpad) {
+        case 4: return launch_cot_t<4>(a, m_tiles, stream);
+        case 8: return launch_cot_t<8>(a, m_tiles, stream);
+        case 12: return launch_cot_t<12>(a, m_tiles, stream);
+        case 16: return launch_cot_t<16>(a, m_tiles, stream);
+        case 32: return launch_cot_t<32>(a, m_tiles, stream);
+        case 52: return launch_cot_t<52>(a, m_tiles, stream);
+        case 64: return launch_cot_t<64>(a, m_tiles, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace grad
+
+// ------------------------------------------------------------------------------ host side
+using namespace grad;
+
+void launch_prepare(const KParams& p, cudaStream_t stream);
+
+size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows) {
+    GradPlan p;
+    make_plan(d, chunk_rows, align256(fused_bytes), p);
+    return (size_t)p.total;
+}
+
+// kp: descriptor with SDES_F_MLP_SIMT set (fp32 tables / target images of the fused prologue at the start of the
+// workspace), its blob and workspace layouts.  Returns the number of kernel launches.
+int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err) {
+    const SdesRolloutDesc& d = kp.d;
+    GradPlan p;
+    make_plan(d, g.chunk_rows, align256(fused_bytes), p);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
+    auto F = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+    int64_t launches = 0;
+    *err = cudaSuccess;
+#define GRAD_CHECK(expr)                          \
+    do {                                          \
+        *err = (expr);                            \
+        if (*err != cudaSuccess) return launches; \
+    } while (0)
+    // ---- prologue: per-step tables and target images (fused prologue), operand images of W and W^T
+    launch_prepare(kp, stream);
+    ++launches;
+    GRAD_CHECK(cudaGetLastError());
+    const float* blob = d.params;
+    const float* fws = reinterpret_cast<const float*>(d.workspace);
+    embb_kernel<<<(p.T * C + 255) / 256, 256, 0, stream>>>(fws + kp.ws.emb, blob + kp.bl.in_b, F(p.embb), p.T * C, F(p.ones));
+    ++launches;
+    GRAD_CHECK(cudaGetLastError());
+    auto image = [&](const Lin& l, const float* src, int src_ld, int N, int K, int transpose) {
+        ImgArgs ia;
+        ia.src = src; ia.src_ld = src_ld; ia.N = N; ia.K = K; ia.transpose = transpose; ia.n_planar = 0; ia.k_planar = 0; ia.Hp = 64;
+        ia.out = ws + l.w_off; ia.n_pad = l.n_pad; ia.tile_n = l.tile_n; ia.k_chunks = l.k_chunks;
+        const int64_t groups = (int64_t)l.n_pad * l.k_chunks * 8;
+        weight_image_kernel<<<(int)((groups + 255) / 256), 256, 0, stream>>>(ia);
+        ++launches;
+        return cudaGetLastError();
+    };
+    auto bias = [&](const Lin& l, const float* src, int n) {
+        pad_bias_kernel<<<(l.n_pad + 255) / 256, 256, 0, stream>>>(src, n, F(l.b_off), l.n_pad);
+        ++launches;
+        return cudaGetLastError();
+    };
+    GRAD_CHECK(image(p.f_in, blob + kp.bl.in_w, d.dim, C, d.dim, 0));
+    for (int l = 0; l < p.nh; ++l) {
+        GRAD_CHECK(image(p.f_h[l], blob + kp.bl.h_w[l], C, C, C, 0));
+        GRAD_CHECK(bias(p.f_h[l], blob + kp.bl.h_b[l], C));
+        GRAD_CHECK(image(p.b_h[l], blob + kp.bl.h_w[l], C, C, C, 1));
+    }
+    GRAD_CHECK(image(p.f_out, blob + kp.bl.out_w, C, d.dim, C, 0));
+    GRAD_CHECK(bias(p.f_out, blob + kp.bl.out_b, d.dim));
+    GRAD_CHECK(image(p.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));
+    GRAD_CHECK(cudaMemsetAsync(g.grad_params, 0, (size_t)d.n_params * 4, stream));
+    GRAD_CHECK(cudaMemsetAsync(g.grad_emb, 0, (size_t)p.T * C * 4, stream));
+    if (g.grad_gate != nullptr) GRAD_CHECK(cudaMemsetAsync(g.grad_gate, 0, (size_t)p.T * (d.gate_dim > 0 ? d.gate_dim : 1) * 4, stream));
+
+    auto base_args = [&](const Lin& l) {
+        LinArgs a;
+        a.a_img = nullptr; a.a_mt_stride = A_BLOCK; a.w_img = ws + l.w_off; a.k_chunks = l.k_chunks; a.n_tiles = l.n_tiles; a.tile_n = l.tile_n;
+        a.bias = l.b_off >= 0 ? F(l.b_off) : nullptr; a.bias_mt_div = 0; a.bias_mt_stride = 0; a.act = ACT_NONE;
+        a.mask_img = nullptr; a.mask_mt_stride = 0; a.mul_img = nullptr; a.mul_mt_stride = 0; a.aux_img = nullptr; a.resid = nullptr;
+        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = A_BLOCK;
+        return a;
+    };
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRAD_CHECK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * (int)A_BLOCK));
+        attr_set = true;
+    }
+    auto wgrad = [&](const uint8_t* d_img, int d_chunks, const uint8_t* a_img, int a_chunks, int m_tiles, float* dw, int ldw, int n_valid, int k_valid) {
+        WgradArgs wa;
+        wa.d_img = d_img; wa.d_chunks = d_chunks; wa.a_img = a_img; wa.a_chunks = a_chunks; wa.m_tiles = m_tiles; wa.dw = dw; wa.ldw = ldw;
+        wa.n_valid = n_valid; wa.k_valid = k_valid;
+        const int pairs = d_chunks * a_chunks;
+        int splits = 296 / pairs;
+        if (splits > m_tiles) splits = m_tiles;
+        if (splits < 1) splits = 1;
+        ++launches;
+        if (simt) wgrad_simt_kernel<<<dim3(pairs, splits), 64, 0, stream>>>(wa);
+        else wgrad_mma_kernel<<<dim3(pairs, splits), LIN_THREADS, 3 * 2 * A_BLOCK, stream>>>(wa);
+        return cudaGetLastError();
+    };
+    auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride) {
+        colsum_kernel<<<m_tiles, 128, 0, stream>>>(img, n_chunks, n_valid, out, mt_div, mt_stride);
+        ++launches;
+        return cudaGetLastError();
+    };
+
+    const int tiles_per_step = (int)(p.Bp / 128);
+    for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const int s0 = ch * p.chunk_steps;
+        const int ns = (s0 + p.chunk_steps <= p.T) ? p.chunk_steps : p.T - s0;
+        const int m_tiles = ns * tiles_per_step;
+        pack_rows_kernel<<<m_tiles, 128, 0, stream>>>(g.xs, p.B, p.Bp, d.dim, p.pc, s0, ws + p.ximg);
+        ++launches;
+        GRAD_CHECK(cudaGetLastError());
+        // ---- forward (models/mlp.py:114-122), keeping GELU(h) and GELU'(h) of every layer
+        {
+            LinArgs a = base_args(p.f_in);
+            a.a_img = ws + p.ximg; a.a_mt_stride = (int64_t)p.pc * A_BLOCK;
+            a.bias = F(p.embb) + (int64_t)s0 * C; a.bias_mt_div = tiles_per_step; a.bias_mt_stride = C;
+            a.act = ACT_GELU_GRAD; a.out_img = ws + p.a_img[0]; a.aux_img = ws + p.gp_img[0];
+            GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+            for (int l = 0; l < p.nh; ++l) {
+                a = base_args(p.f_h[l]);
+                a.a_img = ws + p.a_img[l]; a.act = ACT_GELU_GRAD; a.out_img = ws + p.a_img[l + 1]; a.aux_img = ws + p.gp_img[l + 1];
+                GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+            }
+            a = base_args(p.f_out);
+            a.a_img = ws + p.a_img[p.nh]; a.out_f32 = F(p.nn);
+            GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+        }
+        // ---- output cotangent and gate gradient
+        {
+            CotArgs ca;
+            ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.dnn_img = ws + p.dnn_img;
+            ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = s0; ca.Bp = p.Bp;
+            GRAD_CHECK(launch_cot(ca, m_tiles, stream));
+            ++launches;
+        }
+        // ---- out layer: dW_out += delta_nn^T a_nh, db_out += colsum(delta_nn); delta_h[nh] = (delta_nn W_out) * GELU'(h_nh)
+        float* gp = g.grad_params;
+        GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C));
+        GRAD_CHECK(colsum(ws + p.dnn_img, p.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0));
+        int cur = 0;
+        {
+            LinArgs a = base_args(p.b_out);
+            a.a_img = ws + p.dnn_img; a.a_mt_stride = (int64_t)p.pc * A_BLOCK; a.mul_img = ws + p.gp_img[p.nh]; a.mul_mt_stride = A_BLOCK;
+            a.out_img = ws + p.dh_img[cur];
+            GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+        }
+        for (int l = p.nh - 1; l >= 0; --l) {
+            // delta_h[l+1] is in dh_img[cur]: gradients of hidden layer l, then delta_h[l]
+            GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C));
+            GRAD_CHECK(colsum(ws + p.dh_img[cur], 1, C, gp + kp.bl.h_b[l], m_tiles, 0, 0));
+            LinArgs a = base_args(p.b_h[l]);
+            a.a_img = ws + p.dh_img[cur]; a.mul_img = ws + p.gp_img[l]; a.mul_mt_stride = A_BLOCK; a.out_img = ws + p.dh_img[1 - cur];
+            GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+            cur = 1 - cur;
+        }
+        // ---- input layer: dW_in += delta_h0^T x ; d emb[s] += per-step column sums of delta_h0
+        GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim));
+        GRAD_CHECK(colsum(ws + p.dh_img[cur], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, tiles_per_step, C));
+    }
+#undef GRAD_CHECK
+    return launches;
+}
+
+}  // namespace sdes

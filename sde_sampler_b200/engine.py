@@ -230,6 +230,55 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
     return x_T, rnd, xs
 
 
+def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
+            traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
+            params: torch.Tensor | None = None, chunk_rows: int = 0):
+    """d loss / d theta of the log-variance loss for the rollout that produced `xs` (same spec / seed / traj_offset /
+    noise).  Returns (grad_params blob, grad_emb (T,64), grad_gate (T,gate_dim) | None) — see include/sdes_b200.h
+    `sdes_rollout_lv_grad`."""
+    lib = _cabi.lib()
+    if not xs.is_cuda:
+        raise _cabi.SdesError("the fused gradient runs on a CUDA device only; there is no CPU path")
+    device = xs.device
+    T1, B, dim = xs.shape
+    T = int(spec.ts.shape[0]) - 1
+    if T1 != T + 1 or dim != spec.dim:
+        raise ValueError(f"xs must be {(T + 1, 'B', spec.dim)}, got {tuple(xs.shape)}")
+    xs = xs.detach().to(torch.float32).contiguous()
+    w = w.detach().reshape(-1).to(torch.float32).contiguous()
+    if w.numel() != B:
+        raise ValueError("w must hold one weight per trajectory")
+    ts = spec.ts.to(device=device, dtype=torch.float32).contiguous()
+    d, keep = fill_desc(spec, batch=B, engine=engine)
+    d.flags &= ~_cabi.F_RETURN_TRAJ
+    if params is None:
+        params = pack_params(spec)
+    d.ts, d.params, d.n_params = ts.data_ptr(), params.data_ptr(), params.numel()
+    d.seed, d.traj_offset = seed & 0xFFFFFFFFFFFFFFFF, traj_offset
+    if noise is not None:
+        noise = noise.to(device=device, dtype=torch.float32).contiguous()
+        d.noise = noise.data_ptr()
+        d.flags |= _cabi.F_NOISE_FROM_HBM
+    g = _cabi.LvGradDesc()
+    g.struct_bytes = C.sizeof(_cabi.LvGradDesc)
+    grad_params = torch.empty_like(params)
+    grad_emb = torch.empty((T, _cabi.CHANNELS), dtype=torch.float32, device=device)
+    grad_gate = None
+    if spec.gate is not None:
+        grad_gate = torch.empty((T, int(spec.gate["out_w"].shape[0])), dtype=torch.float32, device=device)
+    g.xs, g.w, g.grad_params, g.grad_emb, g.grad_gate = xs.data_ptr(), w.data_ptr(), grad_params.data_ptr(), grad_emb.data_ptr(), _ptr(grad_gate)
+    g.chunk_rows = chunk_rows
+    with torch.cuda.device(device):
+        need = lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g))
+        if need == 0:
+            raise _cabi.SdesError("lv gradient: " + lib.sdes_last_error().decode())
+        wsbuf = (workspace or Workspace()).get(need, device)
+        d.workspace, d.workspace_bytes = wsbuf.data_ptr(), wsbuf.numel()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _cabi.check(lib.sdes_rollout_lv_grad(C.byref(d), C.byref(g), C.c_void_p(stream)), "sdes_rollout_lv_grad")
+    return grad_params, grad_emb, grad_gate
+
+
 def rnd_stats(rnd: torch.Tensor, mask_mode: int, max_rnd: float = 0.0,
               sample_mask: torch.Tensor | None = None) -> torch.Tensor:
     """8 doubles on the device (layout: include/sdes_b200.h `sdes_rnd_stats`)."""

@@ -12,8 +12,9 @@ CUDA kernel whose partial statistics are combined across ranks when a process gr
 
 What is not implemented raises (`NotImplementedError`) instead of falling back: a learned
 `inference_ctrl`, `sde_ctrl_noise` / `sde_ctrl_dropout`, targets other than GMM / Gauss /
-DoubleWell / MultiWell / Funnel, and gradients (the returned loss is a value; the backward of
-the rollout is the next row of SURVEY §8f).
+DoubleWell / MultiWell / Funnel / Nice.  Gradients: `loss.method = "lv"` with trainable control
+parameters returns a loss whose `.backward()` runs on the tensor cores (autograd.py, csrc/sdes_grad.cu; d <= 64,
+analytic targets); the kl losses need backpropagation through time and return a plain value.
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ from typing import Callable
 import torch
 
 from . import _cabi, engine
+from .autograd import wants_grad
 from .dist import combine_stats
 from .spec import extract_spec
 
@@ -83,6 +85,7 @@ class FusedOCLoss:
         self._seed = seed
         self._calls = 0
         self._workspace = engine_workspace()
+        self._grad_workspace = engine_workspace()
         _cabi.lib()  # fail now, not at the first step, if the CUDA library is missing
 
     # ------------------------------------------------------------------ noise stream
@@ -138,7 +141,9 @@ class FusedOCLoss:
         """losses/oc.py:72-92.  lv: unbiased variance of the kept rnd; kl: their mean."""
         if self.method == "lv_traj":
             return self._compute_loss_lv_traj(rnd, samples)
-        st = self._stats(rnd, samples)
+        return self._loss_from_stats(self._stats(rnd, samples))
+
+    def _loss_from_stats(self, st) -> tuple[torch.Tensor, dict]:
         n, s1, s2 = st[0], st[1], st[2]
         if self.sync_metrics:
             self.n_filtered += int((st[5] - n).item())  # the reference syncs here too (.item(), oc.py:86)
@@ -152,6 +157,35 @@ class FusedOCLoss:
         else:
             loss = s1 / n
         return loss.to(torch.float32), {"train/n_filtered_cumulative": count}
+
+    def _call_with_grad(self, ts, x, terminal_unnorm_log_prob, second_log_prob, noise=None):
+        """Training call whose result carries a gradient: value by the fused rollout (trajectory kept), gradient by
+        `sdes_rollout_lv_grad` (sde_sampler_b200/autograd.py).  Log-variance loss only: the kl losses need
+        backpropagation through time and return a value without grad_fn."""
+        from .autograd import LvLoss
+        from .spec import ctrl_parameters
+
+        params = ctrl_parameters(self.generative_ctrl)
+        net = self.generative_ctrl.base_model
+        gate = getattr(self.generative_ctrl, "score_model", None)
+        out = {}
+
+        def run():
+            spec = extract_spec(self, self.loss_kind, ts, terminal_unnorm_log_prob, second_log_prob, train=True,
+                                compute_ito=True, return_traj=True)
+            seed, off = self._next_seed(), self._rank_offset(x.shape[0])
+            x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
+                                          workspace=self._workspace)
+            st = self._stats(rnd, x_T)
+            loss, metrics = self._loss_from_stats(st)
+            keep = rnd.isfinite() if self.max_rnd is None else rnd < self.max_rnd
+            out.update(loss=loss, metrics=metrics, stats=st, rnd=rnd, keep=keep, xs=xs, spec=spec, seed=seed,
+                       traj_offset=off, noise=noise, samples=x_T)
+            return out
+
+        loss = LvLoss.apply(self, run, len(net.timestep_embed.hidden_layer), len(net.hidden_layer),
+                            0 if gate is None else len(gate.hidden_layer), *params)
+        return loss, out["metrics"]
 
     @property
     def n_filtered(self) -> int:
@@ -250,12 +284,14 @@ class FusedTimeReversalLoss(FusedOCLoss):
         return self._simulate(ts, x, terminal_unnorm_log_prob, initial_log_prob, train=train,
                               compute_ito_int=compute_ito_int, return_traj=return_traj, noise=noise)
 
-    def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob):
+    def __call__(self, ts, x, terminal_unnorm_log_prob, initial_log_prob, *, noise=None):
         x = self._repeat(x)
+        if wants_grad(self):
+            return self._call_with_grad(ts, x, terminal_unnorm_log_prob, initial_log_prob, noise=noise)
         samples, rnd, _ = self.simulate(
             ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, initial_log_prob=initial_log_prob,
             compute_ito_int=self.method != "kl", change_sde_ctrl=self.method in ["lv", "lv_traj"],
-            train=True, return_traj=False)
+            train=True, return_traj=False, noise=noise)
         return self.compute_loss(rnd, samples=samples)
 
     def eval(self, ts, x, terminal_unnorm_log_prob, initial_log_prob=None, compute_weights=True, return_traj=True):
@@ -279,12 +315,14 @@ class FusedReferenceSDELoss(FusedOCLoss):
         return self._simulate(ts, x, terminal_unnorm_log_prob, reference_log_prob, train=True,
                               compute_ito_int=compute_ito_int, return_traj=return_traj, noise=noise)
 
-    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob):
+    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, *, noise=None):
         x = self._repeat(x)
+        if wants_grad(self):
+            return self._call_with_grad(ts, x, terminal_unnorm_log_prob, reference_log_prob, noise=noise)
         samples, rnd, _ = self.simulate(
             ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, reference_log_prob=reference_log_prob,
             compute_ito_int=self.method != "kl", change_sde_ctrl=self.method in ["lv", "lv_traj"],
-            return_traj=False)
+            return_traj=False, noise=noise)
         return self.compute_loss(rnd, samples=samples)
 
     def eval(self, ts, x, terminal_unnorm_log_prob, reference_log_prob=None, compute_weights=True, return_traj=True):
@@ -309,12 +347,14 @@ class FusedExponentialIntegratorSDELoss(FusedOCLoss):
         return self._simulate(ts, x, terminal_unnorm_log_prob, reference_log_prob, train=True,
                               compute_ito_int=compute_ito_int, return_traj=return_traj, noise=noise)
 
-    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob):
+    def __call__(self, ts, x, terminal_unnorm_log_prob, reference_log_prob, *, noise=None):
         x = self._repeat(x)
+        if wants_grad(self):
+            return self._call_with_grad(ts, x, terminal_unnorm_log_prob, reference_log_prob, noise=noise)
         samples, rnd, _ = self.simulate(
             ts, x, terminal_unnorm_log_prob=terminal_unnorm_log_prob, reference_log_prob=reference_log_prob,
             compute_ito_int=self.method != "kl", change_sde_ctrl=self.method in ["lv", "lv_traj"],
-            return_traj=False)
+            return_traj=False, noise=noise)
         return self.compute_loss(rnd, samples=samples)
 
     def eval(self, ts, x, terminal_unnorm_log_prob, reference_log_prob=None, compute_weights=True, return_traj=True):

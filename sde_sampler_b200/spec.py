@@ -103,6 +103,27 @@ def _fourier_mlp_params(net) -> dict:
             "time_embed": _time_embed_params(net.timestep_embed)}
 
 
+def ctrl_parameters(ctrl) -> list:
+    """The control's trainable tensors in the order of the parameter blob (include/sdes_b200.h) — the live
+    nn.Parameters, not detached copies: inputs of the autograd node of the lv loss (sde_sampler_b200/autograd.py)."""
+    net = ctrl.base_model
+    te = net.timestep_embed
+    ps = [net.input_embed.weight, net.input_embed.bias, te.timestep_phase]
+    for l in te.hidden_layer:
+        ps += [l.weight, l.bias]
+    ps += [te.out_layer.weight, te.out_layer.bias]
+    for l in net.hidden_layer:
+        ps += [l.weight, l.bias]
+    ps += [net.out_layer.weight, net.out_layer.bias]
+    gate = getattr(ctrl, "score_model", None)
+    if gate is not None:
+        ps += [gate.timestep_phase]
+        for l in gate.hidden_layer:
+            ps += [l.weight, l.bias]
+        ps += [gate.out_layer.weight, gate.out_layer.bias]
+    return ps
+
+
 # ------------------------------------------------------------------------- distributions
 def _row(t, dim) -> torch.Tensor:
     """(1,d) / (d,) / scalar parameter -> contiguous (d,) float32 view (copy only if broadcast)."""

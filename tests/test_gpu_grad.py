@@ -1,0 +1,97 @@
+"""-m gpu: `loss.backward()` of the log-variance losses — the tensor-core gradient path
+(csrc/sdes_grad.cu through sde_sampler_b200/autograd.py) against the gradients the UNMODIFIED reference produces with
+its own autograd on the same x0 / noise (`train/grad_blob` in tests/golden, frozen by oracle/gen_golden.py:
+`loss.simulate(...)`, `loss.compute_loss(rnd)`, `.backward()`; parameters flattened in blob order).
+
+Tolerance: per parameter tensor, max |delta| <= 2e-3 * max |ref| of that tensor (+1e-7): the gradient is a sum over
+B*T rows of products evaluated with 16-bit-split operands and fp32 accumulation; the reference sums the same terms
+in a different order in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox
+from oracle.cases import CASES, NOISE_SEED
+from sde_sampler_b200.spec import ctrl_parameters
+from sdes_test_helpers import build_from_spec
+
+pytestmark = pytest.mark.gpu
+ENGINES = ["simt", "tcgen05"]
+GRAD_CASES = [n for n, c in CASES.items() if c["method"] == "lv" and c["dim"] <= 64 and not str(c["target"]).startswith("nice")]
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _grads(b, x0, noise):
+    params = ctrl_parameters(b["ctrl"])
+    for p in params:
+        p.grad = None
+    val, metrics = b["loss"](b["ts"], x0, b["terminal"], b["second"], noise=noise)
+    assert val.requires_grad
+    val.backward()
+    return val, params, [torch.zeros_like(p) if p.grad is None else p.grad.detach().clone() for p in params]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_lv_gradient_matches_reference_autograd(golden, name, engine):
+    g = golden(name)
+    spec, x0 = g["spec"], g["x0"]
+    T, (B, d) = g["ts"].shape[0] - 1, x0.shape
+    noise = torch.from_numpy(philox.normal_noise(NOISE_SEED, B, T, d)).to(_dev())
+    b = build_from_spec(spec, _dev(), engine=engine)
+    val, params, grads = _grads(b, torch.from_numpy(x0).to(_dev()), noise)
+    ref_loss = g["train"]["loss"]
+    assert abs(float(val) - ref_loss) <= 1e-3 * (1 + abs(ref_loss))
+    ref = np.asarray(g["train"]["grad_blob"], np.float64)
+    o = 0
+    worst = 0.0
+    for i, (p, gr) in enumerate(zip(params, grads)):
+        r = ref[o:o + p.numel()].reshape(tuple(p.shape))
+        o += p.numel()
+        got = gr.double().cpu().numpy()
+        scale = np.abs(r).max()
+        err = np.abs(got - r).max()
+        worst = max(worst, err / (scale + 1e-30) if scale > 0 else err)
+        assert err <= 2e-3 * scale + 1e-7, f"parameter {i} {tuple(p.shape)}: max|delta|={err:.3e}, max|ref|={scale:.3e}"
+    assert o == ref.size
+
+
+def test_lv_gradient_engines_agree_and_chunking_is_invariant(golden):
+    """1 000 trajectories of the headline configuration: tcgen05 GEMMs vs CUDA-core GEMMs on the same operand images,
+    and the result must not depend on how the (trajectory, step) rows are cut into chunks."""
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.spec import extract_spec
+
+    g = golden("dis_gmm50_lv")
+    outs = []
+    for engine, chunk in (("tcgen05", 0), ("tcgen05", 3000), ("simt", 0)):
+        b = build_from_spec(g["spec"], _dev(), engine=engine)
+        B, d, T = 1000, 50, g["ts"].shape[0] - 1
+        x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(2))
+        spec = extract_spec(b["loss"], "time_reversal", b["ts"], b["terminal"], b["second"], train=True, compute_ito=True,
+                            return_traj=True)
+        x_T, rnd, xs = eng.rollout(spec, x0, seed=5, engine=engine)
+        r = rnd.reshape(-1).double()
+        w = (2.0 * (r - r.mean()) / (B - 1)).float()
+        outs.append(eng.lv_grad(spec, xs, w, seed=5, engine=engine, chunk_rows=chunk))
+    for other in outs[1:]:
+        for a, c in zip(outs[0], other):
+            if a is None:
+                assert c is None
+                continue
+            scale = a.abs().max().item()
+            assert (a - c).abs().max().item() <= 2e-3 * scale + 1e-7
+
+
+def test_no_grad_call_returns_plain_value(golden):
+    g = golden("dis_gmm2_lv")
+    b = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    x0 = torch.from_numpy(g["x0"]).to(_dev())
+    with torch.no_grad():
+        val, _ = b["loss"](b["ts"], x0, b["terminal"], b["second"])
+    assert not val.requires_grad
+    val2, _ = b["loss"](b["ts"], x0, b["terminal"], b["second"])
+    assert val2.requires_grad and val2.grad_fn is not None
