@@ -217,21 +217,29 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
         : "memory");
 }
 
-// D[128, tile_n] = A[128, K] W[tile_n, K]^T for one (n_tile, m_tile); grid (n_tiles, m_tiles): the CTAs that share
-// an A tile run together so A is read from HBM once and from L2 afterwards.
-static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const __grid_constant__ LinArgs a, const int stages) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// D[128, tile_n] = A[128, K] W[tile_n, K]^T per (n_tile, m_tile).  PERSISTENT: at most one CTA per SM, each walks
+// the tile list (n fastest, so the CTAs that share an A tile run together and A is read from HBM once); the TMA ring
+// runs ahead across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile i
+// overlaps the MMAs of tile i+1 and per-CTA setup (TMEM allocation, barriers) is paid once per launch instead of
+// once per tile (the gradient path runs 8 192 row tiles of K = 64 per launch).
+static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const __grid_constant__ LinArgs a, const int stages, const int m_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t s_full[4], s_empty[4], s_acc;
+    __shared__ uint64_t s_full[4], s_empty[4], s_acc_full[2], s_acc_empty[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = blockIdx.x, mt = blockIdx.y;
     const uint32_t b_half = (uint32_t)a.tile_n * 128u;           // bytes of one bf16 half of a weight block
     const uint32_t stage_bytes = A_BLOCK + 2u * b_half;
     uint32_t ncols = 32;
     while ((int)ncols < a.tile_n) ncols <<= 1;
+    const int n_total = a.n_tiles * m_tiles;
+    const int n_my = (int)blockIdx.x < n_total ? (n_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 1) {
-        tc::tmem_alloc(&s_tmem, ncols);
+        tc::tmem_alloc(&s_tmem, 2u * ncols);
         tc::tmem_relinquish();
     }
     if (tid == 0) {
@@ -239,30 +247,37 @@ static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const
             tc::mbar_init(&s_full[s], 1);
             tc::mbar_init(&s_empty[s], 1);
         }
-        tc::mbar_init(&s_acc, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&s_acc_full[s], 1);
+            tc::mbar_init(&s_acc_empty[s], 128);
+        }
         tc::fence_mbar_init();
     }
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
-    const uint32_t tmem_d = s_tmem;
+    const uint32_t tmem_base = s_tmem;
 
     if (warp == 0) {
         if (lane == 0) {  // ---- producer: one elected thread drives the TMA bulk copies
-            const uint8_t* a_src = a.a_img + (int64_t)mt * a.a_mt_stride;
-            const uint8_t* w_src = a.w_img + (int64_t)nt * a.k_chunks * (2ll * b_half);
-            for (int kc = 0; kc < a.k_chunks; ++kc) {
-                const int s = kc % stages, it = kc / stages;
-                if (it > 0) tc::mbar_wait(&s_empty[s], (uint32_t)((it - 1) & 1));
-                tc::mbar_arrive_expect_tx(&s_full[s], stage_bytes);
-                uint8_t* dst = smem + (size_t)s * stage_bytes;
-                const uint8_t* ap = a_src + (int64_t)kc * A_BLOCK;
-                tc::bulk_g2s(dst, ap, A_HALF, &s_full[s]);
-                tc::bulk_g2s(dst + A_HALF, ap + A_HALF, A_HALF, &s_full[s]);
-                const uint8_t* wp = w_src + (int64_t)kc * (2ll * b_half);
-                for (uint32_t off = 0; off < 2u * b_half; off += 16384u) {
-                    const uint32_t n = 2u * b_half - off < 16384u ? 2u * b_half - off : 16384u;
-                    tc::bulk_g2s(dst + A_BLOCK + off, wp + off, n, &s_full[s]);
+            int iter = 0;
+            for (int i = 0; i < n_my; ++i) {
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x, nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+                const uint8_t* a_src = a.a_img + (int64_t)mt * a.a_mt_stride;
+                const uint8_t* w_src = a.w_img + (int64_t)nt * a.k_chunks * (2ll * b_half);
+                for (int kc = 0; kc < a.k_chunks; ++kc, ++iter) {
+                    const int s = iter % stages, it = iter / stages;
+                    if (it > 0) tc::mbar_wait(&s_empty[s], (uint32_t)((it - 1) & 1));
+                    tc::mbar_arrive_expect_tx(&s_full[s], stage_bytes);
+                    uint8_t* dst = smem + (size_t)s * stage_bytes;
+                    const uint8_t* ap = a_src + (int64_t)kc * A_BLOCK;
+                    tc::bulk_g2s(dst, ap, A_HALF, &s_full[s]);
+                    tc::bulk_g2s(dst + A_HALF, ap + A_HALF, A_HALF, &s_full[s]);
+                    const uint8_t* wp = w_src + (int64_t)kc * (2ll * b_half);
+                    for (uint32_t off = 0; off < 2u * b_half; off += 16384u) {
+                        const uint32_t n = 2u * b_half - off < 16384u ? 2u * b_half - off : 16384u;
+                        tc::bulk_g2s(dst + A_BLOCK + off, wp + off, n, &s_full[s]);
+                    }
                 }
             }
         }
@@ -270,45 +285,60 @@ static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const
         if (lane == 0) {  // ---- MMA issuer
             const uint32_t idesc = tc::idesc_bf16(128, a.tile_n);
             const uint32_t lbo_b = (uint32_t)a.tile_n * 16u;
-            for (int kc = 0; kc < a.k_chunks; ++kc) {
-                const int s = kc % stages, it = kc / stages;
-                tc::mbar_wait(&s_full[s], (uint32_t)(it & 1));
-                tc::fence_after();
-                const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + A_HALF;
-                const uint32_t b_hi = a_hi + A_BLOCK, b_lo = b_hi + b_half;
-#pragma unroll
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                    const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
-                    const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
-                    const uint64_t dbh = tc::smem_desc_kmajor(b_hi + (uint32_t)ks * 2u * lbo_b, lbo_b, 128u);
-                    const uint64_t dbl = tc::smem_desc_kmajor(b_lo + (uint32_t)ks * 2u * lbo_b, lbo_b, 128u);
-                    mma_f16_ss(tmem_d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);  // small terms first
-                    mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
-                    mma_f16_ss(tmem_d, dah, dbh, idesc, 1u);
+            int iter = 0;
+            for (int i = 0; i < n_my; ++i) {
+                const int buf = i & 1, use = i >> 1;
+                if (use > 0) {  // the epilogue must have drained this accumulator buffer
+                    tc::mbar_wait(&s_acc_empty[buf], (uint32_t)((use - 1) & 1));
+                    tc::fence_after();
                 }
-                tc::mma_commit(&s_empty[s]);  // the stage is free once these MMAs have read it
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * ncols;
+                for (int kc = 0; kc < a.k_chunks; ++kc, ++iter) {
+                    const int s = iter % stages, it = iter / stages;
+                    tc::mbar_wait(&s_full[s], (uint32_t)(it & 1));
+                    tc::fence_after();
+                    const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + A_HALF;
+                    const uint32_t b_hi = a_hi + A_BLOCK, b_lo = b_hi + b_half;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
+                        const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
+                        const uint64_t dbh = tc::smem_desc_kmajor(b_hi + (uint32_t)ks * 2u * lbo_b, lbo_b, 128u);
+                        const uint64_t dbl = tc::smem_desc_kmajor(b_lo + (uint32_t)ks * 2u * lbo_b, lbo_b, 128u);
+                        mma_f16_ss(tmem_d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);  // small terms first
+                        mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
+                        mma_f16_ss(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    tc::mma_commit(&s_empty[s]);  // the stage is free once these MMAs have read it
+                }
+                tc::mma_commit(&s_acc_full[buf]);
             }
-            tc::mma_commit(&s_acc);
         }
     } else {  // ---- epilogue warps: TMEM lane quadrant = warp % 4
         const int q = warp & 3, r = q * 32 + lane;
-        tc::mbar_wait(&s_acc, 0);
-        tc::fence_after();
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-        float v[8], w[8];
-        tc::tmem_ld8(taddr, v);
-        for (int c0 = 0; c0 < a.tile_n; c0 += 16) {
-            tc::wait_ld_tie<8>(v);
-            tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, w);
-            epilogue8(a, mt, r, nt * a.tile_n + c0, v);
-            tc::wait_ld_tie<8>(w);
-            if (c0 + 16 < a.tile_n) tc::tmem_ld8(taddr + (uint32_t)c0 + 16u, v);
-            epilogue8(a, mt, r, nt * a.tile_n + c0 + 8, w);
+        for (int i = 0; i < n_my; ++i) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x, nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+            const int buf = i & 1, use = i >> 1;
+            tc::mbar_wait(&s_acc_full[buf], (uint32_t)(use & 1));
+            tc::fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)buf * ncols + ((uint32_t)(q * 32) << 16);
+            float v[8], w[8];
+            tc::tmem_ld8(taddr, v);
+            for (int c0 = 0; c0 < a.tile_n; c0 += 16) {
+                tc::wait_ld_tie<8>(v);
+                tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, w);
+                epilogue8(a, mt, r, nt * a.tile_n + c0, v);
+                tc::wait_ld_tie<8>(w);
+                if (c0 + 16 < a.tile_n) tc::tmem_ld8(taddr + (uint32_t)c0 + 16u, v);
+                epilogue8(a, mt, r, nt * a.tile_n + c0 + 8, w);
+            }
+            tc::fence_before();
+            mbar_arrive(&s_acc_empty[buf]);  // 128 arrivals: every epilogue thread has read its TMEM lane
         }
     }
     tc::fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_d, ncols);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 2u * ncols);
 }
 
 // The same layer on the CUDA cores, reading the same operand images: the cross-check engine (SDES_F_MLP_SIMT).
@@ -355,10 +385,21 @@ static cudaError_t launch_linear(const LinArgs& a, int m_tiles, bool simt, cudaS
         attr_set = true;
     }
     const uint32_t stage_bytes = A_BLOCK + 2u * (uint32_t)a.tile_n * 128u;
-    int stages = (int)(200u * 1024u / stage_bytes);
+    // Skinny layers (K <= 128, N <= 64: the control MLP over millions of rows) are bound by the epilogue's CUDA-core
+    // work, not by the tensor pipe: give them three co-resident CTAs per SM (12 epilogue warps) with a one-stage ring
+    // each; wide layers keep the SM to themselves and use the shared memory for a deep ring.
+    const int ctas_per_sm = (a.k_chunks <= 2 && stage_bytes <= 64u * 1024u) ? 3 : 1;
+    int stages = (int)(200u * 1024u / (uint32_t)ctas_per_sm / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 1) stages = 1;
-    linear_mma_kernel<<<dim3(a.n_tiles, m_tiles), LIN_THREADS, (size_t)stages * stage_bytes, stream>>>(a, stages);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int64_t total = (int64_t)a.n_tiles * m_tiles;
+    const int grid = (int)(total < (int64_t)sms * ctas_per_sm ? total : (int64_t)sms * ctas_per_sm);
+    linear_mma_kernel<<<grid, LIN_THREADS, (size_t)stages * stage_bytes, stream>>>(a, stages, m_tiles);
     return cudaGetLastError();
 }
 

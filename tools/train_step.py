@@ -1,0 +1,29 @@
+"""One or more lv training steps (forward rollout keeping xs + tensor-core backward) of the headline workload — for
+launch lists / profiles:  ncu --metrics gpu__time_duration.sum ... python tools/train_step.py [--batch B] [--reps N]"""
+import argparse, os, sys, statistics
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import torch
+import bench
+from sde_sampler_b200.spec import ctrl_parameters
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=65536)
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+o = bench.build_objects(dev, "auto", sync_metrics=False)
+x0 = o["prior"].sample((args.batch,))
+ms = []
+for k in range(args.reps):
+    for p in ctrl_parameters(o["ctrl"]):
+        p.grad = None
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    v, _ = o["loss"](o["ts"], x0, o["terminal"], o["second"])
+    m = torch.cuda.Event(enable_timing=True); m.record()
+    v.backward()
+    b.record()
+    torch.cuda.synchronize()
+    ms.append((a.elapsed_time(m), m.elapsed_time(b)))
+print("forward ms, backward ms:", ms)
