@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sdes_common.cuh"
@@ -14,7 +15,10 @@ cudaError_t launch_rollout_simt(const KParams& p, int sm_count, cudaStream_t str
 cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream);
 bool mma_supported(const KParams& p);
 int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad);
-int mma_groups_per_sm();
+int64_t mma4_weight_image_floats(const SdesRolloutDesc& d);
+int mma_groups_per_sm(int variant);
+bool mma4_supported(const KParams& p);
+cudaError_t launch_rollout_mma4(const KParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t stream);
 // wide engine (sdes_wide.cu): d > SDES_MAX_DIM or a NICE target
 bool wide_engine_needed(const SdesRolloutDesc& d);
@@ -89,6 +93,8 @@ static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
     w.w_simt = take(w.w_simt_len);
     w.w_mma_len = simt ? 0 : mma_weight_image_floats(d, dpad);
     w.w_mma = take(w.w_mma_len);
+    w.w_mma4_len = simt ? 0 : mma4_weight_image_floats(d);
+    w.w_mma4 = take(w.w_mma4_len);
     w.counter = take(4);
     const int64_t tiles128 = simt ? 0 : (d.batch + 127) / 128;
     w.progress = take(tiles128);
@@ -305,10 +311,21 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     if (desc->batch == 0) return 0;
     p.n_tiles = (int)((desc->batch + 31) / 32);
     const int sms = sm_count_cached();
+    // tcgen05 engine variant: 4 groups per SM (bf16 hi/lo operands, state in shared memory) where it fits, else the
+    // 3-group tf32+bf16 kernel.  SDES_MMA_VARIANT=0|1 pins one of them (profiling / A-B measurements).
+    if (!(desc->flags & SDES_F_MLP_SIMT)) {
+        static int forced = -2;
+        if (forced == -2) {
+            const char* e = getenv("SDES_MMA_VARIANT");
+            forced = e ? atoi(e) : -1;
+        }
+        p.mma_variant = 1;
+        if (!mma4_supported(p) || forced == 0) p.mma_variant = 0;
+    }
     {
         // time-chunked scheduling of the tcgen05 engine: aim for >= 8 work items per resident group,
         // chunks of at least 8 steps (state parks in L2 between chunks: ~29 KB per item each way)
-        const int64_t tiles128 = (desc->batch + 127) / 128, groups = (int64_t)mma_groups_per_sm() * sms;
+        const int64_t tiles128 = (desc->batch + 127) / 128, groups = (int64_t)mma_groups_per_sm(p.mma_variant) * sms;
         int64_t nc = (8 * groups + tiles128 - 1) / tiles128;
         const int64_t nc_max = desc->n_steps / 8 > 0 ? desc->n_steps / 8 : 1;
         if (nc > nc_max) nc = nc_max;
@@ -325,7 +342,7 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
         e = launch_rollout_simt(p, sms, stream);
     } else {
         if (!mma_supported(p)) return fail(-8, "the tcgen05 engine does not support this descriptor (dim=%d, n_hidden=%d); set SDES_F_MLP_SIMT", desc->dim, desc->n_hidden);
-        e = launch_rollout_mma(p, sms, stream);
+        e = p.mma_variant == 1 ? launch_rollout_mma4(p, sms, stream) : launch_rollout_mma(p, sms, stream);
     }
     if (e != cudaSuccess) return fail(-7, "rollout kernel launch failed: %s", cudaGetErrorString(e));
     g_launches++;

@@ -32,6 +32,8 @@ struct WsLayout {
     int64_t w_simt_len;
     int64_t w_mma;     // tcgen05 operand images (see sdes_rollout_mma.cu)
     int64_t w_mma_len;
+    int64_t w_mma4;    // bf16 hi/lo operand images of the 4-group tcgen05 engine
+    int64_t w_mma4_len;
     int64_t counter;   // 4 uint32: dynamic work counter, GMM chunk mask
     int64_t progress;  // n_tiles128 uint32: completed time chunks per tile   (tcgen05 engine)
     int64_t state;     // n_tiles128 * (dpad+1) * 128: parked tile state between time chunks
@@ -54,6 +56,7 @@ struct KParams {
     int n_tiles;      // warp tiles of 32 trajectories
     int n_chunks;     // tcgen05 engine: time chunks per tile
     int chunk_steps;  // steps per chunk
+    int mma_variant;  // 0: 3 groups/SM, tf32+bf16 split; 1: 4 groups/SM, bf16 hi/lo split, state in shared memory
 };
 
 __host__ __device__ inline int pad_dim(int d) {

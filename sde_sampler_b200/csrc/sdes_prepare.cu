@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
 
     // tcgen05 weight images (layouts: sdes_tc.cuh wimg_offset_floats / wimg16_offset; order: sdes_rollout_mma.cu):
     // per layer hi = fp32 truncated to tf32, lo = w - hi, w16 = bf16(w); zero-padded to the MMA shapes.
-    if (!(d.flags & SDES_F_MLP_SIMT)) {
+    if (!(d.flags & SDES_F_MLP_SIMT) && p.mma_variant == 0) {
         float* w = ws + p.ws.w_mma;
         const int nout = (dpad + 15) / 16 * 16, k0b = (dpad + 15) & ~15;
         int64_t o = 0;
@@ -156,6 +156,38 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
             o += C;
         }
         for (int64_t e = gtid; e < nout; e += nthreads) w[o + e] = e < dim ? blob[p.bl.out_b + e] : 0.f;
+    }
+
+    // bf16 hi/lo operand images of the 4-group tcgen05 engine (sdes_rollout_mma.cu): per layer hi[N x K16] then
+    // lo[N x K16] in the wimg16 layout, then the fp32 biases {b_h[64]} x nh, b_out[NOUT]
+    if (!(d.flags & SDES_F_MLP_SIMT) && p.mma_variant == 1) {
+        __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(ws + p.ws.w_mma4);
+        const int nout = (dpad + 15) / 16 * 16, k0b = (dpad + 15) & ~15;
+        auto put = [&](int64_t base, int64_t half, int n, int k, int N, float v) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const int64_t off = (int64_t)(k / 8) * (N * 8) + (int64_t)n * 8 + (k % 8);
+            w16[base + off] = hi;
+            w16[base + half + off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        };
+        int64_t o = 0;
+        for (int64_t e = gtid; e < (int64_t)C * k0b; e += nthreads) {
+            const int n = (int)(e / k0b), k = (int)(e % k0b);
+            put(o, (int64_t)C * k0b, n, k, C, k < dim ? blob[p.bl.in_w + (int64_t)n * dim + k] : 0.f);
+        }
+        o += 2ll * C * k0b;
+        for (int l = 0; l < nh; ++l) {
+            for (int64_t e = gtid; e < C * C; e += nthreads) put(o, C * C, (int)(e / C), (int)(e % C), C, blob[p.bl.h_w[l] + e]);
+            o += 2ll * C * C;
+        }
+        for (int64_t e = gtid; e < (int64_t)nout * C; e += nthreads) {
+            const int n = (int)(e / C), k = (int)(e % C);
+            put(o, (int64_t)nout * C, n, k, nout, n < dim ? blob[p.bl.out_w + (int64_t)n * C + k] : 0.f);
+        }
+        o += 2ll * nout * C;
+        float* wb = ws + p.ws.w_mma4 + o / 2;
+        for (int l = 0; l < nh; ++l)
+            for (int64_t e = gtid; e < C; e += nthreads) wb[l * C + e] = blob[p.bl.h_b[l] + e];
+        for (int64_t e = gtid; e < nout; e += nthreads) wb[nh * C + e] = e < dim ? blob[p.bl.out_b + e] : 0.f;
     }
 
     // SIMT weight image: WtIn[d][C] bIn[C] {Wt[C][C] b[C]} x nh  WtOut[C][dpad] bOut[dpad]

@@ -41,7 +41,7 @@ int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad_simt) {
            (int64_t)d.n_hidden * 64 + nout;
 }
 
-int mma_groups_per_sm() { return MMA_GROUPS; }
+int mma_groups_per_sm(int variant) { return variant == 1 ? 4 : MMA_GROUPS; }
 
 bool mma_supported(const KParams& p) { return p.d.dim <= 64 && p.d.n_hidden <= SDES_MAX_HIDDEN; }
 
@@ -441,6 +441,334 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
     tc::fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(s_tmem, TMEM_COLS);
+}
+
+// =========================================================================== 4-group engine
+// Same work decomposition (items = (time chunk, 128-trajectory tile), one trajectory per thread, MLP on tcgen05
+// with the A operand in TMEM), but FOUR groups per SM instead of three: one more warp per scheduler to hide the
+// epilogue's dependency stalls, which is what bounds this kernel (issue slots ~58 % busy with three).  What makes
+// the fourth group fit:
+//   * TMEM: both operand halves are bf16 (hi = bf16(v), lo = bf16(v - hi), 16 significant bits — the wide engine's
+//     split, parity-tested there): D 64 | A_hi 32 | A_lo 32 = 128 columns per group, 4 x 128 = 512;
+//   * registers (128 per thread at 512 threads): the state x lives in shared memory ([j][128] per group, conflict
+//     free) and is read where it is needed; only the score part sc[DPAD] stays in registers across the MLP;
+//   * shared memory: bf16 hi/lo weights are 4 bytes per element instead of 10 (65 KB instead of 160 KB at d = 50),
+//     which pays for the 112 KB of state.
+// The layer is three kind::f16 MMAs per K=16 step (tc::issue_layer_bf16x3): 12 per 64x64 layer instead of 20.
+constexpr int MMA4_GROUPS = 4;
+constexpr int MMA4_THREADS = MMA4_GROUPS * 128;
+constexpr int GROUP4_COLS = 128;  // D[64] | A_hi bf16x2 [32] | A_lo bf16x2 [32]
+
+// bytes of the bf16 operand image: per layer hi then lo (wimg16 layout), then the fp32 biases
+int64_t mma4_weight_image_floats(const SdesRolloutDesc& d) {
+    const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad), k0b = (dpad + 15) & ~15;
+    const int64_t bf16_elems = 2ll * 64 * k0b + (int64_t)d.n_hidden * 2 * 64 * 64 + 2ll * nout * 64;
+    return bf16_elems / 2 + (int64_t)d.n_hidden * 64 + nout;
+}
+
+struct XSmem {  // the state of one trajectory in shared memory: element j at p[j * 128]
+    float* p;
+    __device__ __forceinline__ float operator[](int j) const { return p[j * 128]; }
+};
+
+template <int DPAD>
+__device__ __forceinline__ void store_a_split16(uint32_t addr_hi, uint32_t addr_lo, const XSmem& x) {
+#pragma unroll
+    for (int c = 0; c < DPAD; c += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tc::split_bf16_pair(x[c + 2 * q], x[c + 2 * q + 1], hi[q], lo[q]);
+        tc::tmem_st4(addr_hi + c / 2, hi);
+        tc::tmem_st4(addr_lo + c / 2, lo);
+    }
+    if (DPAD % 16 == 8) {
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        tc::tmem_st4(addr_hi + DPAD / 2, z);
+        tc::tmem_st4(addr_lo + DPAD / 2, z);
+    }
+}
+
+__device__ __forceinline__ void gelu_split16_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8], const float4 b0, const float4 b1) {
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float a[8];
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = gelu_fast(v[q] + bb[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc::split_bf16_pair(a[2 * q], a[2 * q + 1], hi[q], lo[q]);
+    tc::tmem_st4(addr_hi, hi);
+    tc::tmem_st4(addr_lo, lo);
+}
+
+__device__ __forceinline__ void group_bar4(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+__device__ __forceinline__ void run_layer4(GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K16, int N) {
+    tc::wait_st();
+    tc::fence_before();
+    group_bar4(c.g);
+    if (c.gtid == 0) {
+        tc::fence_after();
+        tc::issue_layer_bf16x3(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K16, N);
+        tc::mma_commit(c.bar);
+    }
+    tc::mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    tc::fence_after();
+}
+
+__device__ __forceinline__ void layer_epilogue4(const GroupCtx& c, const float* __restrict__ bias) {
+    float a[8], b[8];
+    tc::tmem_ld8(c.l_d, a);
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ch += 2) {
+        const float4 p0 = b4[2 * ch], p1 = b4[2 * ch + 1], p2 = b4[2 * ch + 2], p3 = b4[2 * ch + 3];
+        tc::wait_ld_tie<8>(a);
+        tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
+        gelu_split16_store8(c.l_hi + 4u * ch, c.l_lo + 4u * ch, a, p0, p1);
+        tc::wait_ld_tie<8>(b);
+        if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
+        gelu_split16_store8(c.l_hi + 4u * (ch + 1), c.l_lo + 4u * (ch + 1), b, p2, p3);
+    }
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __grid_constant__ KParams p) {
+    constexpr int NOUT = (DPAD + 15) / 16 * 16;
+    constexpr uint32_t K0B = (DPAD + 15) & ~15;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t s_wbar;
+    __shared__ uint64_t s_mbar[MMA4_GROUPS];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_tile[MMA4_GROUPS];
+
+    const SdesRolloutDesc& d = p.d;
+    const float* ws = reinterpret_cast<const float*>(d.workspace);
+    const int dim = d.dim, T = d.n_steps, K = d.n_components, nh = d.n_hidden;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- shared memory: [bf16 weight image + biases | gmm mu | gmm h | gmm c | prior | ref | state x]
+    float* s_w = smem;
+    const int K2 = (K + 1) & ~1;
+    float* s_mu = s_w + ((p.ws.w_mma4_len + 31) & ~31ll);
+    float* s_h = s_mu + K2 * DPAD;
+    float* s_c = s_h + K2 * DPAD;
+    float* s_prior = s_c + 64;
+    float* s_ref = s_prior + 2 * DPAD + 8;
+    float* s_x = s_ref + 2 * DPAD + 8;
+
+    if (warp == 0) {
+        tc::tmem_alloc(&s_tmem, TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    if (tid == 0) {
+        tc::mbar_init(&s_wbar, 1);
+        for (int g = 0; g < MMA4_GROUPS; ++g) tc::mbar_init(&s_mbar[g], 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    if (tid == 0) {
+        const uint32_t total = (uint32_t)(p.ws.w_mma4_len * sizeof(float));
+        tc::mbar_arrive_expect_tx(&s_wbar, total);
+        const char* src = reinterpret_cast<const char*>(ws + p.ws.w_mma4);
+        char* dst = reinterpret_cast<char*>(s_w);
+        for (uint32_t off = 0; off < total; off += 16384u) {
+            const uint32_t n = total - off < 16384u ? total - off : 16384u;
+            tc::bulk_g2s(dst + off, src + off, n, &s_wbar);
+        }
+    }
+    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
+        s_mu[e] = ws[p.ws.gmm_mu + e];
+        s_h[e] = ws[p.ws.gmm_h + e];
+    }
+    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
+    for (int e = tid; e < 2 * DPAD + 8; e += blockDim.x) {
+        s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
+        s_ref[e] = e <= 2 * DPAD ? ws[p.ws.ref + e] : 0.f;
+    }
+    tc::mbar_wait(&s_wbar, 0);
+    __syncthreads();
+
+    // weight image addresses (bytes): per layer hi then lo
+    const uint32_t w_base = tc::smem_u32(s_w);
+    constexpr uint32_t L0_HALF = 64u * K0B * 2u, LH_HALF = 64u * 64u * 2u, LO_HALF = (uint32_t)NOUT * 64u * 2u;
+    const uint32_t l0_hi = w_base, l0_lo = l0_hi + L0_HALF;
+    const uint32_t lh_base = l0_lo + L0_HALF;
+    const uint32_t lo_hi = lh_base + (uint32_t)nh * 2u * LH_HALF, lo_lo = lo_hi + LO_HALF;
+    const float* s_bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_w) + 2 * L0_HALF + (size_t)nh * 2 * LH_HALF + 2 * LO_HALF);
+
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
+    GroupCtx c;
+    c.g = warp >> 2;
+    c.gtid = tid & 127;
+    const uint32_t tbase = s_tmem + (uint32_t)(c.g * GROUP4_COLS);
+    c.t_d = tbase;
+    c.t_hi = tbase + 64;
+    c.t_lo = tbase + 96;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    c.l_d = c.t_d + lane_off;
+    c.l_hi = c.t_hi + lane_off;
+    c.l_lo = c.t_lo + lane_off;
+    c.bar = &s_mbar[c.g];
+    c.phase = 0;
+    const XSmem xs{s_x + c.g * (DPAD * 128) + c.gtid};
+
+    uint32_t* counter = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.counter);
+    const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
+    const bool ret_traj = (d.flags & SDES_F_RETURN_TRAJ) != 0;
+    const int64_t B = d.batch;
+    const uint32_t n_tiles = (uint32_t)((B + 127) / 128);
+    const int n_chunks = p.n_chunks, chunk_steps = p.chunk_steps;
+    const uint32_t n_items = n_tiles * (uint32_t)n_chunks;
+    float* state = const_cast<float*>(ws) + p.ws.state;
+    uint32_t* progress = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.progress);
+    for (;;) {
+        if (c.gtid == 0) s_tile[c.g] = atomicAdd(counter, 1u);
+        group_bar4(c.g);
+        const uint32_t item = s_tile[c.g];
+        if (item >= n_items) break;
+        const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
+        const int64_t row = (int64_t)tile * 128 + c.gtid;
+        const bool valid = row < B;
+        const int64_t rrow = valid ? row : (B - 1);
+        float* st = state + (int64_t)tile * (DPAD + 1) * 128 + c.gtid;
+
+        float rnd;
+        if (chunk == 0) {
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) {
+                const float v = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
+                xs.p[j * 128] = v;
+                if (ret_traj && valid && j < dim) d.xs[rrow * dim + j] = v;
+            }
+            rnd = initial_rnd<DPAD>(d, xs, tsm);
+        } else {
+            if (c.gtid == 0) {
+                uint32_t seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
+                } while (seen < chunk);
+            }
+            group_bar4(c.g);
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) xs.p[j * 128] = __ldcg(st + j * 128);
+            rnd = __ldcg(st + DPAD * 128);
+        }
+        const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)rrow);
+        const int i_begin = (int)chunk * chunk_steps;
+        const int i_end = (i_begin + chunk_steps < T) ? i_begin + chunk_steps : T;
+
+        for (int i = i_begin; i < i_end; ++i) {
+            const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
+            float sc[DPAD];
+            score_part<DPAD>(d, xs, sc, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
+            store_a_split16<DPAD>(c.l_hi, c.l_lo, xs);
+            run_layer4(c, l0_hi, l0_lo, (int)K0B, C);
+            layer_epilogue4(c, ws + p.ws.emb + (int64_t)i * C);
+#pragma unroll 1
+            for (int l = 0; l < nh; ++l) {
+                run_layer4(c, lh_base + (uint32_t)l * 2u * LH_HALF, lh_base + (uint32_t)l * 2u * LH_HALF + LH_HALF, C, C);
+                layer_epilogue4(c, s_bias + l * C);
+            }
+            run_layer4(c, lo_hi, lo_lo, C, NOUT);
+            {
+                const StepCoef sc_ = make_step_coef(d, tab);
+                const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
+                const float* bo = s_bias + nh * C;
+                float* xo = (ret_traj && valid) ? d.xs + ((int64_t)(i + 1) * B + rrow) * dim : nullptr;
+                float cost = 0.f, ito = 0.f;
+                float na[8], nb[8];
+                tc::tmem_ld8(c.l_d, na);
+#pragma unroll
+                for (int q = 0; q < DPAD / 8; q += 2) {
+                    tc::wait_ld_tie<8>(na);
+                    if (q + 1 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 1), nb);
+                    {
+                        float xv[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) { na[r] += bo[8 * q + r]; xv[r] = xs[8 * q + r]; }
+                        update4(sc_, &xv[0], &na[0], &sc[8 * q], s_prior + 8 * q, s_prior + DPAD + 8 * q, 8 * q, i, traj, nrow, cost, ito);
+                        update4(sc_, &xv[4], &na[4], &sc[8 * q + 4], s_prior + 8 * q + 4, s_prior + DPAD + 8 * q + 4, 8 * q + 4, i, traj, nrow, cost, ito);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            xs.p[(8 * q + r) * 128] = xv[r];
+                            if (xo != nullptr && 8 * q + r < dim) xo[8 * q + r] = xv[r];
+                        }
+                    }
+                    if (q + 1 < DPAD / 8) {
+                        tc::wait_ld_tie<8>(nb);
+                        if (q + 2 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 2), na);
+                        float xv[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) { nb[r] += bo[8 * (q + 1) + r]; xv[r] = xs[8 * (q + 1) + r]; }
+                        update4(sc_, &xv[0], &nb[0], &sc[8 * q + 8], s_prior + 8 * q + 8, s_prior + DPAD + 8 * q + 8, 8 * q + 8, i, traj, nrow, cost, ito);
+                        update4(sc_, &xv[4], &nb[4], &sc[8 * q + 12], s_prior + 8 * q + 12, s_prior + DPAD + 8 * q + 12, 8 * q + 12, i, traj, nrow, cost, ito);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            xs.p[(8 * (q + 1) + r) * 128] = xv[r];
+                            if (xo != nullptr && 8 * (q + 1) + r < dim) xo[8 * (q + 1) + r] = xv[r];
+                        }
+                    }
+                }
+                finish_step(d, sc_, tab, cost, ito, rnd);
+            }
+        }
+        if (i_end == T) {
+            rnd += terminal_rnd<DPAD>(d, xs, tsm);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j)
+                    if (j < dim) d.x_T[rrow * dim + j] = xs[j];
+                d.rnd[rrow] = rnd;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) __stcg(st + j * 128, xs[j]);
+            __stcg(st + DPAD * 128, rnd);
+            __threadfence();
+            group_bar4(c.g);
+            if (c.gtid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(chunk + 1u) : "memory");
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(s_tmem, TMEM_COLS);
+}
+
+size_t mma4_smem_bytes(const KParams& p) {
+    const int dpad = p.ws.dpad, K = p.d.n_components;
+    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * dpad + 64 + 2 * (2 * dpad + 8) +
+                      (size_t)MMA4_GROUPS * dpad * 128;
+    return fl * sizeof(float);
+}
+
+bool mma4_supported(const KParams& p) { return mma_supported(p) && mma4_smem_bytes(p) <= 226u * 1024u; }
+
+template <int DPAD>
+static cudaError_t launch_mma4_t(const KParams& p, int sm_count, cudaStream_t stream) {
+    const size_t smem = mma4_smem_bytes(p);
+    cudaError_t e = cudaFuncSetAttribute(rollout_mma4_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int tiles = (int)((p.d.batch + 127) / 128);
+    int grid = (tiles + MMA4_GROUPS - 1) / MMA4_GROUPS;
+    if (grid > sm_count) grid = sm_count;
+    if (grid < 1) grid = 1;
+    rollout_mma4_kernel<DPAD><<<grid, MMA4_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_mma4(const KParams& p, int sm_count, cudaStream_t stream) {
+    switch (p.ws.dpad) {
+        case 8: return launch_mma4_t<8>(p, sm_count, stream);
+        case 16: return launch_mma4_t<16>(p, sm_count, stream);
+        case 32: return launch_mma4_t<32>(p, sm_count, stream);
+        case 48: return launch_mma4_t<48>(p, sm_count, stream);
+        case 56: return launch_mma4_t<56>(p, sm_count, stream);
+        case 64: return launch_mma4_t<64>(p, sm_count, stream);
+    }
+    return cudaErrorInvalidValue;
 }
 
 size_t mma_smem_bytes(const KParams& p) {

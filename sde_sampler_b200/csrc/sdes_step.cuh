@@ -39,8 +39,8 @@ struct TargetSmem {
 // to cover the highest set bit of the mask, so the inner loops carry no per-pair tests).
 // Components are processed two at a time (independent accumulators) for instruction-level
 // parallelism; the images are padded to an even K with h = 0, c = -inf.
-template <int DPAD, int NP, bool NEED_SCORE, bool TWO = (NP <= 8)>
-__device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
+template <int DPAD, int NP, bool NEED_SCORE, bool TWO = (NP <= 8), class X>
+__device__ __forceinline__ float gmm_eval_na(const X& x, float (&score)[DPAD], const TargetSmem& ts, int K) {
     constexpr int NPAIR = DPAD / 2;
     float m = -INFINITY, ssum = 0.f;
     if (NEED_SCORE) {
@@ -115,8 +115,8 @@ __device__ __forceinline__ float gmm_eval_na(const float (&x)[DPAD], float (&sco
     return m + logf(ssum) - shared;
 }
 
-template <int DPAD, bool NEED_SCORE>
-__device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)[DPAD], const TargetSmem& ts, int K) {
+template <int DPAD, bool NEED_SCORE, class X>
+__device__ __forceinline__ float gmm_eval(const X& x, float (&score)[DPAD], const TargetSmem& ts, int K) {
     constexpr int NPAIR = DPAD / 2;
     const uint32_t mask = ts.gmm_mask;  // warp-uniform
     if (NPAIR > 1 && mask < 2u) return gmm_eval_na<DPAD, 1, NEED_SCORE>(x, score, ts, K);
@@ -128,8 +128,8 @@ __device__ __forceinline__ float gmm_eval(const float (&x)[DPAD], float (&score)
 }
 
 // MultiWell (distr/double_well.py:165-179; DoubleWell :39-45 is n_dw = d = 1).
-template <int DPAD, bool NEED_SCORE>
-__device__ __forceinline__ float multiwell_eval(const float (&x)[DPAD], float (&score)[DPAD], int dim, int n_dw,
+template <int DPAD, bool NEED_SCORE, class X>
+__device__ __forceinline__ float multiwell_eval(const X& x, float (&score)[DPAD], int dim, int n_dw,
                                                 float sep, float shift) {
     float lp = 0.f;
 #pragma unroll
@@ -150,8 +150,8 @@ __device__ __forceinline__ float multiwell_eval(const float (&x)[DPAD], float (&
 }
 
 // Funnel (distr/funnel.py:57-80): x_0 ~ N(0, var), x_{1:} | x_0 ~ N(0, exp(x_0) I).
-template <int DPAD, bool NEED_SCORE>
-__device__ __forceinline__ float funnel_eval(const float (&x)[DPAD], float (&score)[DPAD], int dim, float var) {
+template <int DPAD, bool NEED_SCORE, class X>
+__device__ __forceinline__ float funnel_eval(const X& x, float (&score)[DPAD], int dim, float var) {
     float sq = 0.f;
 #pragma unroll
     for (int j = 1; j < DPAD; ++j) sq = fmaf(x[j], x[j], sq);  // padded dims are 0
@@ -168,8 +168,8 @@ __device__ __forceinline__ float funnel_eval(const float (&x)[DPAD], float (&sco
     return lp_first + lp_other;
 }
 
-template <int DPAD, bool NEED_SCORE>
-__device__ __forceinline__ float target_eval(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&score)[DPAD],
+template <int DPAD, bool NEED_SCORE, class X>
+__device__ __forceinline__ float target_eval(const SdesRolloutDesc& d, const X& x, float (&score)[DPAD],
                                              const TargetSmem& ts) {
     float lp;
     if (d.target_kind == SDES_TARGET_GMM)
@@ -182,8 +182,8 @@ __device__ __forceinline__ float target_eval(const SdesRolloutDesc& d, const flo
 }
 
 // log N(x; loc, diag scale^2) from the image loc | inv_var | lognorm
-template <int DPAD>
-__device__ __forceinline__ float diag_gauss_logp(const float (&x)[DPAD], const float* img) {
+template <int DPAD, class X>
+__device__ __forceinline__ float diag_gauss_logp(const X& x, const float* img) {
     float a = 0.f;
 #pragma unroll
     for (int j = 0; j < DPAD; ++j) {
@@ -202,8 +202,8 @@ __device__ __forceinline__ float diag_gauss_logp(const float (&x)[DPAD], const f
 // score_part depends on x but not on the network, so it is evaluated BEFORE the MLP and kept in
 // registers (sc[]); the network output is then streamed out of TMEM 8 columns at a time straight
 // into the state update, and the full control vector never has to be materialised.
-template <int DPAD>
-__device__ __forceinline__ void score_part(const SdesRolloutDesc& d, const float (&x)[DPAD], float (&sc)[DPAD],
+template <int DPAD, class X>
+__device__ __forceinline__ void score_part(const SdesRolloutDesc& d, const X& x, float (&sc)[DPAD],
                                            const TargetSmem& ts, const float* __restrict__ gate_row, float sigma,
                                            float lerp_w) {
     if (d.ctrl_kind == SDES_CTRL_CLIPPED) {
@@ -314,15 +314,15 @@ __device__ __forceinline__ void finish_step(const SdesRolloutDesc& d, const Step
 }
 
 // initial cost (losses/oc.py:168-172, :296, :410)
-template <int DPAD>
-__device__ __forceinline__ float initial_rnd(const SdesRolloutDesc& d, const float (&x)[DPAD], const TargetSmem& ts) {
+template <int DPAD, class X>
+__device__ __forceinline__ float initial_rnd(const SdesRolloutDesc& d, const X& x, const TargetSmem& ts) {
     if (d.loss_kind == SDES_LOSS_TIME_REVERSAL && !(d.flags & SDES_F_RND0_ZERO)) return diag_gauss_logp<DPAD>(x, ts.prior);
     return 0.f;
 }
 
 // terminal cost (losses/oc.py:225, :337, :449-450; clip: solver/oc.py:48-54)
-template <int DPAD>
-__device__ __forceinline__ float terminal_rnd(const SdesRolloutDesc& d, const float (&x)[DPAD], const TargetSmem& ts) {
+template <int DPAD, class X>
+__device__ __forceinline__ float terminal_rnd(const SdesRolloutDesc& d, const X& x, const TargetSmem& ts) {
     float dummy[DPAD];
     const float lp = clipf(target_eval<DPAD, false>(d, x, dummy, ts), d.clip_target);
     if (d.loss_kind == SDES_LOSS_TIME_REVERSAL) return -lp;

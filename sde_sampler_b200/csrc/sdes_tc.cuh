@@ -187,6 +187,29 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
                  : "memory");
 }
 
+// v = hi + lo with hi = bf16(v), lo = bf16(v - hi), two values at a time (a lands in the low half)
+__device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+    lo = pack_bf16x2(a - ha, b - hb);
+}
+
+// bf16x3 layer (4-group engine): A = A_hi + A_lo and W = W_hi + W_lo, both halves bf16 (16 significant bits per
+// operand), D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in fp32 — the wide engine's scheme with A in TMEM.  A halves are
+// packed two values per 32-bit column (8 columns per K=16 step).  Called by ONE thread.
+__device__ __forceinline__ void issue_layer_bf16x3(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
+                                                   uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K16, int N) {
+    const uint32_t id16 = idesc_bf16(128, N);
+    const uint32_t lbo = (uint32_t)N * 16u;
+    for (int s = 0; s < (K16 >> 4); ++s) {
+        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        mma_f16_ts(tmem_d, tmem_a_lo + 8u * s, bh, id16, s > 0 ? 1u : 0u);
+        mma_f16_ts(tmem_d, tmem_a_hi + 8u * s, bl, id16, 1u);
+        mma_f16_ts(tmem_d, tmem_a_hi + 8u * s, bh, id16, 1u);
+    }
+}
+
 // K8 = K of the tf32 terms (multiple of 8), K16 = K of the bf16 term (multiple of 16, >= K8; the extra
 // columns of A_lo and of the bf16 image are zero).  Called by ONE thread.
 __device__ __forceinline__ void issue_layer_mixed(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo16,
