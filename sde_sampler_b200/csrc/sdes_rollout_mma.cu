@@ -751,8 +751,10 @@ static cudaError_t launch_mma4_t(const KParams& p, int sm_count, cudaStream_t st
     const size_t smem = mma4_smem_bytes(p);
     cudaError_t e = cudaFuncSetAttribute(rollout_mma4_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int tiles = (int)((p.d.batch + 127) / 128);
-    int grid = (tiles + MMA4_GROUPS - 1) / MMA4_GROUPS;
+    // work items = tiles x time chunks: a group that finds no first-chunk tile left starts on a second chunk and waits
+    // for its predecessor, so every SM is used even when there are fewer tiles than resident groups
+    const int64_t items = ((p.d.batch + 127) / 128) * (int64_t)(p.n_chunks > 0 ? p.n_chunks : 1);
+    int grid = (int)((items + MMA4_GROUPS - 1) / MMA4_GROUPS);
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
     rollout_mma4_kernel<DPAD><<<grid, MMA4_THREADS, smem, stream>>>(p);
@@ -782,8 +784,8 @@ static cudaError_t launch_mma_t(const KParams& p, int sm_count, cudaStream_t str
     const size_t smem = mma_smem_bytes(p);
     cudaError_t e = cudaFuncSetAttribute(rollout_mma_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int tiles = (int)((p.d.batch + 127) / 128);
-    int grid = (tiles + MMA_GROUPS - 1) / MMA_GROUPS;
+    const int64_t items = ((p.d.batch + 127) / 128) * (int64_t)(p.n_chunks > 0 ? p.n_chunks : 1);
+    int grid = (int)((items + MMA_GROUPS - 1) / MMA_GROUPS);
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
     rollout_mma_kernel<DPAD><<<grid, MMA_THREADS, smem, stream>>>(p);
