@@ -27,6 +27,9 @@ import sys
 import tempfile
 import time
 
+# NCCL prints its version banner on stdout; the contract is ONE JSON line there
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
@@ -543,7 +546,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if engine_used == "simt" else "f32 (MLP as split tf32+bf16 tcgen05 MMA with fp32 accumulate, fp32-equivalent; f32 elsewhere)",
+            "dtype": "f32" if engine_used == "simt" else "f32 (MLP as 3 bf16 tcgen05 MMA passes over hi/lo-split operands with fp32 accumulate, fp32-equivalent; f32 elsewhere)",
             "data": "synthetic",
             "config": {"workload": workload_name(B), "engine": engine_used, "global_batch": world * B,
                        "l2": "flushed between timed steps (192 MiB memset inside the region)",
