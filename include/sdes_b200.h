@@ -57,6 +57,10 @@ enum { SDES_TARGET_GMM = 0, SDES_TARGET_MULTIWELL = 1 /* DoubleWell = n_dw=d=1 *
 #define SDES_F_REFERENCE_CTRL (1u << 5) /* Euler-DDS reference_ctrl = sigma * prior score (solver/oc.py:305-306) */
 #define SDES_F_HAS_GATE       (1u << 6) /* ctrl.score_model (a TimeEmbed gate) is present                */
 #define SDES_F_MLP_SIMT       (1u << 7) /* evaluate the control MLP with fp32 FFMA instead of tcgen05    */
+#define SDES_F_TRAJ_TILED     (1u << 8) /* with RETURN_TRAJ (d <= SDES_MAX_DIM): xs is written row-tiled,
+                                           [T+1][ceil(B/128)][jdim][128] floats with jdim = 8/16/32/48/56/64 >= d
+                                           (coalesced for thread-per-trajectory kernels); the layout
+                                           sdes_rollout_lv_grad reads when the same flag is set on its descriptor */
 
 /* Layout of the flat fp32 parameter blob `params` (torch (out,in) row-major weights, C = 64):
  *   FourierMLP (models/mlp.py:85-122)

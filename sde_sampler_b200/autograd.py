@@ -42,6 +42,9 @@ class LvLoss(torch.autograd.Function):
     def backward(ctx, grad_out):
         m, lo = ctx.meta, ctx.loss_obj
         params = ctx.params
+        if m["traj_version"] != lo._traj_version:
+            raise RuntimeError("the trajectory of this loss value was overwritten by a later training call of the same "
+                               "loss object; call backward() before the next forward (as Trainable.step does)")
         st = m["stats"]
         n, mean = st[0], st[1] / st[0]
         rnd = m["rnd"].reshape(-1).double()

@@ -117,6 +117,7 @@ static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
     if (d->ctrl_kind < 0 || d->ctrl_kind > SDES_CTRL_LERP_TARGET) return fail(-3, "bad ctrl_kind %d", d->ctrl_kind);
     if (d->sde_kind < 0 || d->sde_kind > SDES_SDE_CONST_OU) return fail(-3, "bad sde_kind %d", d->sde_kind);
     if (d->target_kind < 0 || d->target_kind > SDES_TARGET_NICE) return fail(-3, "bad target_kind %d", d->target_kind);
+    if ((d->flags & SDES_F_TRAJ_TILED) && wide_engine_needed(*d)) return fail(-3, "SDES_F_TRAJ_TILED is a fused-engine layout (d <= %d)", SDES_MAX_DIM);
     if (wide_engine_needed(*d)) {
         const char* why = wide_validate(*d);
         if (why != nullptr) return fail(-3, "wide engine (dim=%d): %s", d->dim, why);

@@ -72,6 +72,21 @@ __host__ __device__ inline int pad_dim(int d) {
 // padded state dimension of the tcgen05 engine: K of the input layer (multiple of 8)
 __host__ __device__ inline int mma_pad_dim(int d) { return d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : d <= 48 ? 48 : d <= 56 ? 56 : 64; }
 
+// Where trajectory point (step, row) lives in `xs`: element j at p[j * stride].  Reference layout (T+1, B, d), or the
+// row-tiled layout of SDES_F_TRAJ_TILED, [step][row / 128][j][row % 128], that thread-per-trajectory kernels read
+// and write with fully coalesced 128-byte lines.
+struct TrajRef {
+    float* p;
+    int stride;
+};
+__device__ __forceinline__ TrajRef traj_ref(const SdesRolloutDesc& d, float* xs, int step, int64_t row) {
+    if (d.flags & SDES_F_TRAJ_TILED) {
+        const int64_t nt = (d.batch + 127) / 128;
+        return TrajRef{xs + (((int64_t)step * nt + (row >> 7)) * mma_pad_dim(d.dim)) * 128 + (row & 127), 128};
+    }
+    return TrajRef{xs + ((int64_t)step * d.batch + row) * d.dim, 1};
+}
+
 // ------------------------------------------------------------------------------------ math
 __device__ __forceinline__ float clipf(float v, float c) {
     // utils/common.py:83-84 `tensor.clip(-max_norm, max_norm)`; c = +inf means no clip. NaN propagates

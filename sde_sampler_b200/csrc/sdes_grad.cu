@@ -89,16 +89,16 @@ __global__ void embb_kernel(const float* __restrict__ emb, const float* __restri
 }
 
 // rows (s, b) of the stored trajectory -> A operand image of the input layer (natural feature order, K = P)
-__global__ void __launch_bounds__(128) pack_rows_kernel(const float* __restrict__ xs, int64_t B, int64_t Bp, int dim, int pc, int s0,
+__global__ void __launch_bounds__(128) pack_rows_kernel(const SdesRolloutDesc d, const float* __restrict__ xs, int64_t Bp, int pc, int s0,
                                                         uint8_t* __restrict__ ximg) {
-    const int mt = blockIdx.x, r = threadIdx.x;
-    const int64_t rr = (int64_t)mt * 128 + r;
+    const int mt = blockIdx.x, r = threadIdx.x, dim = d.dim;
+    const int64_t rr = (int64_t)mt * 128 + r, B = d.batch;
     const int64_t s = s0 + rr / Bp, b = rr % Bp;
-    const float* xrow = xs + (s * B + (b < B ? b : 0)) * dim;
+    const TrajRef x = traj_ref(d, const_cast<float*>(xs), (int)s, b < B ? b : 0);
     for (int k0 = 0; k0 < pc * 64; k0 += 8) {
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (b < B && k0 + q < dim) ? __ldg(xrow + k0 + q) : 0.f;
+        for (int q = 0; q < 8; ++q) v[q] = (b < B && k0 + q < dim) ? __ldg(x.p + (k0 + q) * x.stride) : 0.f;
         uint4 hi, lo;
         split_pair(v[0], v[1], hi.x, lo.x);
         split_pair(v[2], v[3], hi.y, lo.y);
@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     const bool valid = b < B;
     const int64_t bb = valid ? b : 0;
     float x[DPAD];
-    const float* xrow = a.xs + ((int64_t)s * B + bb) * dim;
+    const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
 #pragma unroll
-    for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(xrow + j) : 0.f;
+    for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(xr.p + j * xr.stride) : 0.f;
     const float* tab = ws + p.ws.tab + (int64_t)s * TAB_STRIDE;
     const StepCoef c = make_step_coef(d, tab);
     const float wb = valid ? a.w[bb] : 0.f;
@@ -523,7 +523,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         const int s0 = ch * p.chunk_steps;
         const int ns = (s0 + p.chunk_steps <= p.T) ? p.chunk_steps : p.T - s0;
         const int m_tiles = ns * tiles_per_step;
-        pack_rows_kernel<<<m_tiles, 128, 0, stream>>>(g.xs, p.B, p.Bp, d.dim, p.pc, s0, ws + p.ximg);
+        pack_rows_kernel<<<m_tiles, 128, 0, stream>>>(d, g.xs, p.Bp, p.pc, s0, ws + p.ximg);
         ++launches;
         GRAD_CHECK(cudaGetLastError());
         // ---- forward (models/mlp.py:114-122), keeping GELU(h) and GELU'(h) of every layer

@@ -351,9 +351,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
             if (ret_traj && valid) {
+                const TrajRef o = traj_ref(d, d.xs, 0, rrow);
 #pragma unroll
                 for (int j = 0; j < DPAD; ++j)
-                    if (j < dim) d.xs[rrow * dim + j] = x[j];
+                    if (j < dim) o.p[j * o.stride] = x[j];
             }
             rnd = initial_rnd<DPAD>(d, x, tsm);
         } else {
@@ -415,10 +416,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __gri
                 finish_step(d, sc_, tab, cost, ito, rnd);
             }
             if (ret_traj && valid) {
-                float* o = d.xs + ((int64_t)(i + 1) * B + rrow) * dim;
+                const TrajRef o = traj_ref(d, d.xs, i + 1, rrow);
 #pragma unroll
                 for (int j = 0; j < DPAD; ++j)
-                    if (j < dim) o[j] = x[j];
+                    if (j < dim) o.p[j * o.stride] = x[j];
             }
         }
         if (i_end == T) {
@@ -637,11 +638,12 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
 
         float rnd;
         if (chunk == 0) {
+            const TrajRef o0 = traj_ref(d, d.xs, 0, rrow);
 #pragma unroll
             for (int j = 0; j < DPAD; ++j) {
                 const float v = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
                 xs.p[j * 128] = v;
-                if (ret_traj && valid && j < dim) d.xs[rrow * dim + j] = v;
+                if (ret_traj && valid && j < dim) o0.p[j * o0.stride] = v;
             }
             rnd = initial_rnd<DPAD>(d, xs, tsm);
         } else {
@@ -677,7 +679,9 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
                 const StepCoef sc_ = make_step_coef(d, tab);
                 const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
                 const float* bo = s_bias + nh * C;
-                float* xo = (ret_traj && valid) ? d.xs + ((int64_t)(i + 1) * B + rrow) * dim : nullptr;
+                const TrajRef xo_ref = traj_ref(d, d.xs, i + 1, rrow);
+                float* xo = (ret_traj && valid) ? xo_ref.p : nullptr;
+                const int xo_st = xo_ref.stride;
                 float cost = 0.f, ito = 0.f;
                 float na[8], nb[8];
                 tc::tmem_ld8(c.l_d, na);
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
                             xs.p[(8 * q + r) * 128] = xv[r];
-                            if (xo != nullptr && 8 * q + r < dim) xo[8 * q + r] = xv[r];
+                            if (xo != nullptr && 8 * q + r < dim) xo[(8 * q + r) * xo_st] = xv[r];
                         }
                     }
                     if (q + 1 < DPAD / 8) {
@@ -708,7 +712,7 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
                             xs.p[(8 * (q + 1) + r) * 128] = xv[r];
-                            if (xo != nullptr && 8 * (q + 1) + r < dim) xo[8 * (q + 1) + r] = xv[r];
+                            if (xo != nullptr && 8 * (q + 1) + r < dim) xo[(8 * (q + 1) + r) * xo_st] = xv[r];
                         }
                     }
                 }

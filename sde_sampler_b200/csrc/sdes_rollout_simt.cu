@@ -134,9 +134,10 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
 #pragma unroll
         for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
         if (ret_traj && valid) {
+            const TrajRef o = traj_ref(d, d.xs, 0, rrow);
 #pragma unroll
             for (int j = 0; j < DPAD; ++j)
-                if (j < dim) d.xs[rrow * dim + j] = x[j];
+                if (j < dim) o.p[j * o.stride] = x[j];
         }
         float rnd = initial_rnd<DPAD>(d, x, tsm);
         const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)rrow);
@@ -154,10 +155,10 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32, 1) rollout_simt_kernel(const 
                 update4(sc_, &x[4 * q], &g[4 * q], &sc[4 * q], s_prior + 4 * q, s_prior + DPAD + 4 * q, 4 * q, i, traj, nrow, cost, ito);
             finish_step(d, sc_, tab, cost, ito, rnd);
             if (ret_traj && valid) {
-                float* o = d.xs + ((int64_t)(i + 1) * B + rrow) * dim;
+                const TrajRef o = traj_ref(d, d.xs, i + 1, rrow);
 #pragma unroll
                 for (int j = 0; j < DPAD; ++j)
-                    if (j < dim) o[j] = x[j];
+                    if (j < dim) o.p[j * o.stride] = x[j];
             }
         }
         rnd += terminal_rnd<DPAD>(d, x, tsm);

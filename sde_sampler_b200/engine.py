@@ -184,10 +184,20 @@ def _check_device(name: str, t: torch.Tensor | None, device):
         raise ValueError(f"{name} lives on {t.device}, the rollout runs on {device}")
 
 
+def _mma_pad_dim(d: int) -> int:
+    return 8 if d <= 8 else 16 if d <= 16 else 32 if d <= 32 else 48 if d <= 48 else 56 if d <= 56 else 64
+
+
+def tiled_traj_numel(T: int, B: int, dim: int) -> int:
+    """Floats of the row-tiled trajectory layout (SDES_F_TRAJ_TILED, include/sdes_b200.h)."""
+    return (T + 1) * ((B + 127) // 128) * _mma_pad_dim(dim) * 128
+
+
 def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
-            params: torch.Tensor | None = None):
-    """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None)."""
+            params: torch.Tensor | None = None, traj_tiled: bool = False, traj_buffer: Workspace | None = None):
+    """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None); with `traj_tiled`
+    the trajectory comes back as a flat buffer in the row-tiled layout that `lv_grad` consumes."""
     lib = _cabi.lib()
     if not x0.is_cuda:
         raise _cabi.SdesError("the fused rollout runs on a CUDA device only (x is on %s); there is no CPU path" % x0.device)
@@ -210,7 +220,15 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
     rnd = torch.empty((B, 1), dtype=torch.float32, device=device)
     xs = None
     if d.flags & _cabi.F_RETURN_TRAJ:
-        xs = torch.empty((T + 1, B, dim), dtype=torch.float32, device=device)
+        if traj_tiled and dim <= _cabi.MAX_DIM and spec.target["kind"] != "nice":
+            d.flags |= _cabi.F_TRAJ_TILED
+            n = tiled_traj_numel(T, B, dim)
+            if traj_buffer is not None:  # grow-only buffer owned by the loss: no 1.5 GB allocation per training step
+                xs = traj_buffer.get(4 * n, device)[: 4 * n].view(torch.float32)
+            else:
+                xs = torch.empty(n, dtype=torch.float32, device=device)
+        else:
+            xs = torch.empty((T + 1, B, dim), dtype=torch.float32, device=device)
         d.xs = xs.data_ptr()
     if noise is not None:
         if tuple(noise.shape) != (T, B, dim):
@@ -240,17 +258,21 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
     if not xs.is_cuda:
         raise _cabi.SdesError("the fused gradient runs on a CUDA device only; there is no CPU path")
     device = xs.device
-    T1, B, dim = xs.shape
     T = int(spec.ts.shape[0]) - 1
-    if T1 != T + 1 or dim != spec.dim:
-        raise ValueError(f"xs must be {(T + 1, 'B', spec.dim)}, got {tuple(xs.shape)}")
-    xs = xs.detach().to(torch.float32).contiguous()
     w = w.detach().reshape(-1).to(torch.float32).contiguous()
-    if w.numel() != B:
-        raise ValueError("w must hold one weight per trajectory")
+    B = w.numel()
+    tiled = xs.ndim == 1  # the flat row-tiled buffer of rollout(..., traj_tiled=True)
+    if tiled:
+        if xs.numel() != tiled_traj_numel(T, B, spec.dim):
+            raise ValueError("tiled xs does not match (T, B, dim)")
+    elif tuple(xs.shape) != (T + 1, B, spec.dim):
+        raise ValueError(f"xs must be {(T + 1, B, spec.dim)}, got {tuple(xs.shape)}")
+    xs = xs.detach().to(torch.float32).contiguous()
     ts = spec.ts.to(device=device, dtype=torch.float32).contiguous()
     d, keep = fill_desc(spec, batch=B, engine=engine)
     d.flags &= ~_cabi.F_RETURN_TRAJ
+    if tiled:
+        d.flags |= _cabi.F_TRAJ_TILED
     if params is None:
         params = pack_params(spec)
     d.ts, d.params, d.n_params = ts.data_ptr(), params.data_ptr(), params.numel()

@@ -86,6 +86,8 @@ class FusedOCLoss:
         self._calls = 0
         self._workspace = engine_workspace()
         self._grad_workspace = engine_workspace()
+        self._traj_buffer = engine_workspace()  # trajectory of the last training forward (row-tiled), reused across steps
+        self._traj_version = 0
         _cabi.lib()  # fail now, not at the first step, if the CUDA library is missing
 
     # ------------------------------------------------------------------ noise stream
@@ -175,12 +177,13 @@ class FusedOCLoss:
                                 compute_ito=True, return_traj=True)
             seed, off = self._next_seed(), self._rank_offset(x.shape[0])
             x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
-                                          workspace=self._workspace)
+                                          workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer)
+            self._traj_version += 1
             st = self._stats(rnd, x_T)
             loss, metrics = self._loss_from_stats(st)
             keep = rnd.isfinite() if self.max_rnd is None else rnd < self.max_rnd
             out.update(loss=loss, metrics=metrics, stats=st, rnd=rnd, keep=keep, xs=xs, spec=spec, seed=seed,
-                       traj_offset=off, noise=noise, samples=x_T)
+                       traj_offset=off, noise=noise, samples=x_T, traj_version=self._traj_version)
             return out
 
         loss = LvLoss.apply(self, run, len(net.timestep_embed.hidden_layer), len(net.hidden_layer),
