@@ -170,6 +170,27 @@ typedef struct SdesLvGradDesc {
 size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);
 int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream);
 
+/* EulerIntegrator.integrate (eq/integrator.py:79-127) for a LangevinSDE (eq/sdes.py:38-65) — the unadjusted
+ * Langevin sampler of LangevinSolver.run (solver/langevin.py:34-63), SURVEY §8f-3:
+ *   x <- x + clip(score(x) diff_coeff^2 / 2, clip_score) (t - s) + diff_coeff eps sqrt(t - s)   over `timesteps`,
+ * output at the times `out_ts` by linear interpolation inside the step that covers them (interpolate(), :66-77).
+ * The target is described by the rollout descriptor's target fields (target_kind, gmm_*, separation, ...), plus dim,
+ * batch, seed, traj_offset, flags & SDES_F_NOISE_FROM_HBM with noise (n_steps, B, d), workspace (>=
+ * sdes_integrate_workspace_bytes).  d <= SDES_MAX_DIM, analytic targets.  One launch for the whole chain. */
+typedef struct SdesIntegrateDesc {
+    uint32_t struct_bytes;   /* = sizeof(SdesIntegrateDesc), checked */
+    int32_t n_steps;         /* integration steps; timesteps has n_steps + 1 entries */
+    int32_t n_out;           /* output times */
+    float diff_coeff, clip_score /* +inf = none */, eps /* EulerIntegrator.eps, 1e-8 */;
+    const float* timesteps;
+    const float* out_ts;
+    const float* x_init;     /* (B, d) */
+    float* xs_out;           /* (n_out, B, d) */
+} SdesIntegrateDesc;
+
+size_t sdes_integrate_workspace_bytes(const SdesRolloutDesc* target_desc);
+int sdes_langevin_integrate(const SdesRolloutDesc* target_desc, const SdesIntegrateDesc* g, void* stream);
+
 /* Statistics of rnd that BaseOCLoss.filter/compute_loss/compute_results reduce to
  * (losses/oc.py:50-123).  out_stats (device, 8 doubles):
  *   [0] n_kept  [1] sum(rnd | kept)  [2] sum(rnd^2 | kept)  [3] max(-rnd | kept)

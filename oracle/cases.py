@@ -76,4 +76,12 @@ EVAL_CASES = {
     "dds_nice16_lv": [(True, True)],
 }
 
+# Langevin dynamics (conf/solver/langevin.yaml: LangevinSDE diff_coeff 1, clip_score 1e5, EulerIntegrator dt 0.01) at
+# small sizes; `eval_steps` output times — 7 is not a divisor of the step count, so outputs are interpolated
+ULA_CASES = {
+    "ula_gmm2": dict(target="gmm40", dim=2, terminal_t=2.0, dt=0.01, eval_steps=20, diff_coeff=1.0, clip_score=1e5, batch=64),
+    "ula_funnel10": dict(target="funnel", dim=10, terminal_t=1.0, dt=0.01, eval_steps=7, diff_coeff=0.8, clip_score=3.0, batch=48),
+    "ula_multiwell4": dict(target="multiwell", dim=4, terminal_t=0.5, dt=0.005, eval_steps=10, diff_coeff=1.0, clip_score=1e5, batch=32),
+}
+
 NOISE_SEED = 0x5DE5_0001

@@ -128,13 +128,67 @@ def run_case(name: str, case: dict) -> dict:
     return out
 
 
+def run_ula_case(name: str, case: dict) -> dict:
+    """EulerIntegrator.integrate on a LangevinSDE of the unmodified reference (solver/langevin.py:34-63) with the
+    Philox stream injected through `torch.randn` (eq/integrator.py:116 draws with torch.randn, not randn_like)."""
+    import torch
+
+    from sde_sampler_b200.spec import _target_params
+
+    ref_harness.import_reference()
+    from sde_sampler.eq.integrator import EulerIntegrator
+    from sde_sampler.eq.sdes import LangevinSDE
+    from sde_sampler.utils.common import get_timesteps
+
+    d, B = case["dim"], case["batch"]
+    target = ref_harness.build_target(case["target"], d)
+    sde = LangevinSDE(target_score=target.score, diff_coeff=case["diff_coeff"], clip_score=case["clip_score"],
+                      terminal_t=case["terminal_t"])
+    integ = EulerIntegrator(dt=case["dt"])
+    ts = get_timesteps(0.0, case["terminal_t"], steps=case["eval_steps"])
+    timesteps = get_timesteps(ts[0], ts[-1], dt=case["dt"])
+    n_steps = timesteps.shape[0] - 1
+    torch.manual_seed(77)
+    x0 = torch.randn(B, d)
+    noise = philox.normal_noise(NOISE_SEED, B, n_steps, d)
+    it = iter(torch.from_numpy(noise))
+    orig = torch.randn
+
+    def fake(*shape, **kw):
+        n = next(it)
+        assert tuple(n.shape) == tuple(shape), (n.shape, shape)
+        return n
+
+    torch.randn = fake
+    try:
+        xs = integ.integrate(sde, ts=ts, x_init=x0.clone())
+    finally:
+        torch.randn = orig
+    tg = _target_params(target, d)
+    from sde_sampler_b200.spec import RolloutSpec
+
+    tgd = RolloutSpec(dim=d, ts=ts, loss={}, ctrl={}, mlp={}, gate=None, sde=None, prior=None, ref=None, target=tg).to_dict()["target"]
+    return {"x0": x0.numpy().copy(), "ts": ts.numpy().copy(), "timesteps": timesteps.numpy().copy(), "target": tgd,
+            "diff_coeff": float(case["diff_coeff"]), "clip_score": float(case["clip_score"]), "xs": xs.numpy().copy(),
+            "torch_version": torch.__version__}
+
+
 def main():
     if not ref_harness.available():
         raise SystemExit("reference not available; golden vectors can only be generated in the build container")
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    names = sys.argv[1:] or list(CASES)
+    from oracle.cases import ULA_CASES
+
+    names = sys.argv[1:] or list(CASES) + list(ULA_CASES)
     for name in names:
+        if name in ULA_CASES:
+            out = run_ula_case(name, ULA_CASES[name])
+            path = os.path.join(outdir, f"{name}.npz")
+            specio.save(path, out)
+            print(f"{name:36s} B={out['x0'].shape[0]:4d} d={out['x0'].shape[1]:3d} steps={out['timesteps'].shape[0]-1:5d} "
+                  f"outputs={out['xs'].shape[0]} |xs|max={np.abs(out['xs']).max():.3e} size={os.path.getsize(path)/1024:.0f} KiB")
+            continue
         out = run_case(name, CASES[name])
         path = os.path.join(outdir, f"{name}.npz")
         specio.save(path, out)

@@ -363,6 +363,31 @@ def rollout(spec, x0, noise=None, seed=None, traj_offset=0, dtype=np.float32):
 
 
 # --------------------------------------------------------------------------------------
+# Langevin dynamics  (eq/integrator.py:79-127 on eq/sdes.py:38-65; solver/langevin.py:34-63)
+# --------------------------------------------------------------------------------------
+def langevin_integrate(tg, x0, timesteps, out_ts, diff_coeff, clip_score, noise, eps=1e-8, dtype=np.float32):
+    """EulerIntegrator.integrate(LangevinSDE(target.score, diff_coeff, clip_score), ts=out_ts, x_init=x0,
+    timesteps=timesteps) with the normal draws `noise` (n_steps, B, d).  Returns xs (len(out_ts), B, d)."""
+    dtype = np.dtype(dtype).type
+    xs = np.asarray(x0, dtype=dtype).copy()
+    timesteps = np.asarray(timesteps, dtype=dtype)
+    out_ts = np.asarray(out_ts, dtype=dtype)
+    out, cnt = [], 0
+    for i, (s, t) in enumerate(zip(timesteps[:-1], timesteps[1:])):
+        _, score = target_log_prob_and_score(tg, xs)
+        drift = _clip(score * dtype(diff_coeff) ** 2 / dtype(2.0), clip_score)               # eq/sdes.py:54-61
+        nz = np.asarray(noise[i], dtype=dtype) * np.sqrt(dtype(t - s))                        # integrator.py:116
+        xt = (xs + drift * dtype(t - s) + dtype(diff_coeff) * nz).astype(dtype)              # :119
+        if cnt < out_ts.shape[0] and out_ts[cnt] <= t + dtype(eps):                           # :121-123
+            ind = int(np.searchsorted(out_ts[cnt:], t + dtype(eps), side="right"))
+            w = ((out_ts[cnt:cnt + ind].reshape(-1, 1, 1) - s) / (t - s)).astype(dtype)
+            out.append(_lerp(xs[None], xt[None], w).astype(dtype))                            # interpolate(), :66-77
+            cnt += ind
+        xs = xt
+    return np.concatenate(out, axis=0)
+
+
+# --------------------------------------------------------------------------------------
 # reductions  (losses/oc.py:50-123)
 # --------------------------------------------------------------------------------------
 def loss_from_rnd(rnd, method, max_rnd=None, traj_per_sample=1, sample_mask=None):

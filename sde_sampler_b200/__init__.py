@@ -4,8 +4,9 @@ Public surface = the reference's loss plug-in interface (sde_sampler/losses/oc.p
 `FusedTimeReversalLoss`, `FusedReferenceSDELoss`, `FusedExponentialIntegratorSDELoss`, `Results`.
 Importing the losses requires the in-tree CUDA library (`python -m sde_sampler_b200.build`).
 """
+from .integrator import FusedEulerIntegrator  # noqa: F401
 from .losses import (FusedExponentialIntegratorSDELoss, FusedOCLoss, FusedReferenceSDELoss,  # noqa: F401
                      FusedTimeReversalLoss, Results)
 
 __all__ = ["FusedTimeReversalLoss", "FusedReferenceSDELoss", "FusedExponentialIntegratorSDELoss",
-           "FusedOCLoss", "Results"]
+           "FusedOCLoss", "Results", "FusedEulerIntegrator"]

@@ -72,8 +72,19 @@ class LvGradDesc(C.Structure):
     ]
 
 
+class IntegrateDesc(C.Structure):
+    """struct SdesIntegrateDesc (include/sdes_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("n_steps", C.c_int32), ("n_out", C.c_int32),
+        ("diff_coeff", C.c_float), ("clip_score", C.c_float), ("eps", C.c_float),
+        ("timesteps", _fp), ("out_ts", _fp), ("x_init", _fp), ("xs_out", _fp),
+    ]
+
+
 # every symbol include/sdes_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
+    "sdes_integrate_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc)]),
+    "sdes_langevin_integrate": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(IntegrateDesc), C.c_void_p]),
     "sdes_lv_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
     "sdes_rollout_lv_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
     "sdes_version": (C.c_int, []),

@@ -25,6 +25,8 @@ bool wide_engine_needed(const SdesRolloutDesc& d);
 const char* wide_validate(const SdesRolloutDesc& d);
 size_t wide_workspace_bytes(const SdesRolloutDesc& d);
 int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t* err);
+// Langevin / Euler integrator (sdes_integrate.cu)
+cudaError_t launch_langevin(const IntegrateParams& a, cudaStream_t stream);
 // lv gradient (sdes_grad.cu)
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
 int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err);
@@ -350,6 +352,78 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     return 0;
 }
 
+// ---- Langevin / Euler integrator (sdes_integrate.cu)
+
+// The integrator only reads the target part of the descriptor: complete the rest with a valid dummy configuration so
+// that the common validation, the fused prologue (target images) and the workspace layout can be reused.
+static int integrate_setup(const SdesRolloutDesc* desc, KParams& p) {
+    if (desc == nullptr) return fail(-1, "desc is NULL");
+    if (desc->struct_bytes != sizeof(SdesRolloutDesc)) return fail(-2, "desc.struct_bytes mismatch");
+    memset(&p, 0, sizeof(p));
+    p.d = *desc;
+    p.d.loss_kind = SDES_LOSS_EXP_INTEGRATOR;
+    p.d.ctrl_kind = SDES_CTRL_CLIPPED;
+    p.d.sde_kind = SDES_SDE_NONE;
+    p.d.flags = (desc->flags & SDES_F_NOISE_FROM_HBM) | SDES_F_MLP_SIMT;
+    p.d.n_steps = 1;
+    p.d.n_hidden = 0;
+    p.d.te_hidden = 1;
+    blob_layout(p.d, p.bl);
+    p.d.n_params = p.bl.total;
+    if (wide_engine_needed(p.d)) return fail(-8, "the Langevin integrator is implemented for d <= %d with analytic targets", SDES_MAX_DIM);
+    int rc = validate(&p.d, false);
+    if (rc != 0) return rc;
+    ws_layout(p.d, p.ws);
+    return 0;
+}
+
+static __global__ void langevin_images_kernel(const KParams p) {
+    // the target images of the fused prologue (GMM mu / h / c and the pair mask) without the network tables
+    const SdesRolloutDesc& d = p.d;
+    float* ws = reinterpret_cast<float*>(d.workspace);
+    const int dim = d.dim, dpad = p.ws.dpad, tid = threadIdx.x;
+    __shared__ uint32_t s_mask;
+    if (tid == 0) s_mask = 0u;
+    __syncthreads();
+    if (d.target_kind == SDES_TARGET_GMM) {
+        const int K = d.n_components, K2 = (K + 1) & ~1;
+        if (tid < dim) {
+            bool differs = false;
+            for (int k = 1; k < K; ++k)
+                differs |= d.gmm_loc[(int64_t)k * dim + tid] != d.gmm_loc[tid] || d.gmm_scale[(int64_t)k * dim + tid] != d.gmm_scale[tid];
+            if (differs) atomicOr(&s_mask, 1u << (tid >> 1));
+        }
+        for (int e = tid; e < K2 * dpad; e += blockDim.x) {
+            const int k = e / dpad, j = e % dpad;
+            float mu = 0.f, h = 0.f;
+            if (j < dim && k < K) {
+                mu = d.gmm_loc[(int64_t)k * dim + j];
+                const float sc = d.gmm_scale[(int64_t)k * dim + j];
+                h = 0.5f / (sc * sc);
+            }
+            ws[p.ws.gmm_mu + e] = mu;
+            ws[p.ws.gmm_h + e] = h;
+        }
+        for (int k = tid; k < 64; k += blockDim.x) {
+            float c = -INFINITY;
+            if (k < K) {
+                float logw = 0.f;
+                if (d.gmm_weights != nullptr) {
+                    float tot = 0.f;
+                    for (int q = 0; q < K; ++q) tot += d.gmm_weights[q];
+                    logw = logf(d.gmm_weights[k] / tot);
+                }
+                float sl = 0.f;
+                for (int j = 0; j < dim; ++j) sl += logf(d.gmm_scale[k * dim + j]);
+                c = logw - sl - 0.5f * (float)dim * LOG_2PI;
+            }
+            ws[p.ws.gmm_c + k] = c;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) reinterpret_cast<uint32_t*>(ws + p.ws.counter)[1] = s_mask;
+}
+
 static int grad_setup(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, KParams& p, bool& simt) {
     int rc = validate(desc, false);
     if (rc != 0) return rc;
@@ -389,6 +463,38 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
     cudaError_t e = cudaSuccess;
     g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e);
     if (e != cudaSuccess) return fail(-7, "lv gradient launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+size_t sdes_integrate_workspace_bytes(const SdesRolloutDesc* desc) {
+    KParams p;
+    if (integrate_setup(desc, p) != 0) return 0;
+    return (size_t)p.ws.total * sizeof(float);
+}
+
+int sdes_langevin_integrate(const SdesRolloutDesc* desc, const SdesIntegrateDesc* g, void* stream_) {
+    g_err[0] = 0;
+    KParams p;
+    int rc = integrate_setup(desc, p);
+    if (rc != 0) return rc;
+    if (g == nullptr || g->struct_bytes != sizeof(SdesIntegrateDesc)) return fail(-2, "SdesIntegrateDesc is NULL or has the wrong struct_bytes");
+    if (g->n_steps < 1 || g->n_out < 0) return fail(-3, "n_steps must be >= 1 and n_out >= 0");
+    if (!g->timesteps || !g->x_init || (g->n_out > 0 && (!g->out_ts || !g->xs_out))) return fail(-5, "timesteps/x_init/out_ts/xs_out must be non-NULL");
+    if (desc->target_kind == SDES_TARGET_GMM && (!desc->gmm_loc || !desc->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");
+    if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
+    if (!desc->workspace || reinterpret_cast<uintptr_t>(desc->workspace) % 256 != 0) return fail(-5, "workspace must be non-NULL and 256-byte aligned");
+    if ((size_t)p.ws.total * sizeof(float) > desc->workspace_bytes) return fail(-6, "workspace_bytes too small");
+    if (desc->batch == 0) return 0;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    langevin_images_kernel<<<1, 256, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "langevin prologue launch failed: %s", cudaGetErrorString(e));
+    IntegrateParams a;
+    a.d = p.d; a.ws = p.ws; a.timesteps = g->timesteps; a.out_ts = g->out_ts; a.n_steps = g->n_steps; a.n_out = g->n_out;
+    a.diff_coeff = g->diff_coeff; a.clip_score = g->clip_score; a.eps = g->eps; a.x_init = g->x_init; a.xs_out = g->xs_out;
+    e = launch_langevin(a, stream);
+    if (e != cudaSuccess) return fail(-7, "langevin kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches += 2;
     return 0;
 }
 

@@ -59,6 +59,18 @@ struct KParams {
     int mma_variant;  // 0: 3 groups/SM, tf32+bf16 split; 1: 4 groups/SM, bf16 hi/lo split, state in shared memory
 };
 
+// Parameters of the Langevin / Euler integrator kernel (sdes_integrate.cu)
+struct IntegrateParams {
+    SdesRolloutDesc d;       // target fields, dim, batch, seed, traj_offset, noise (optional), workspace
+    WsLayout ws;
+    const float* timesteps;  // (n_steps + 1) integration grid
+    const float* out_ts;     // (n_out) output times
+    int n_steps, n_out;
+    float diff_coeff, clip_score, eps;
+    const float* x_init;     // (B, d)
+    float* xs_out;           // (n_out, B, d)
+};
+
 __host__ __device__ inline int pad_dim(int d) {
     if (d <= 4) return 4;
     if (d <= 8) return 8;

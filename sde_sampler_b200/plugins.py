@@ -170,6 +170,20 @@ class VP(_OU):
         self.register_buffer("diff_coeff_sq_max", torch.tensor(diff_coeff_sq_max, dtype=torch.float), persistent=False)
 
 
+class LangevinSDE(nn.Module):
+    """eq/sdes.py:38-65 — drift = clip(target_score(x) * diff_coeff^2 / 2, clip_score), constant diffusion."""
+
+    def __init__(self, target_score: Callable, diff_coeff: float = 1.0, clip_score: float | None = None, terminal_t: float = 1.0):
+        super().__init__()
+        self.target_score = target_score
+        self.clip_score = clip_score
+        self.register_buffer("diff_coeff", torch.tensor(diff_coeff, dtype=torch.float), persistent=False)
+        self.register_buffer("terminal_t", torch.tensor(terminal_t, dtype=torch.float), persistent=False)
+
+    drift = _in_kernel("drift")
+    diff = _in_kernel("diff")
+
+
 # ------------------------------------------------------------------------- distributions
 class _Distribution(nn.Module):
     def __init__(self, dim: int, log_norm_const: float | None = None):

@@ -82,3 +82,16 @@ def test_torch_port_matches_reference_train(golden, name):
     x_T, rnd, _ = torch_port.rollout(spec, x0, noise=noise)
     _close(x_T, g["train"]["x_T"])
     _close(rnd, g["train"]["rnd"])
+
+
+def test_oracle_langevin_matches_reference(golden):
+    """oracle.rollout.langevin_integrate vs EulerIntegrator.integrate(LangevinSDE) of the unmodified reference."""
+    from oracle.cases import ULA_CASES
+
+    for name in ULA_CASES:
+        g = golden(name)
+        B, d = g["x0"].shape
+        noise = philox.normal_noise(NOISE_SEED, B, g["timesteps"].shape[0] - 1, d)
+        xs = rollout.langevin_integrate(g["target"], g["x0"], g["timesteps"], g["ts"], g["diff_coeff"], g["clip_score"], noise)
+        assert xs.shape == g["xs"].shape
+        _close(xs, g["xs"])
