@@ -25,6 +25,7 @@
 // "on" output a contiguous column range.  Weights of the control MLP are permuted to match when they are imaged.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "sdes_linear.cuh"
@@ -86,8 +87,9 @@ static bool make_plan(const SdesRolloutDesc& d, Plan& p) {
     p.gmm_mu = take(K * p.P * 4);
     p.gmm_h = take(K * p.P * 4);
     p.gmm_c = take(64 * 4);
+    const bool pairs_ok = !(d.flags & SDES_F_MLP_SIMT) && getenv("SDES_CTA_PAIRS") != nullptr;  // opt-in, see sdes_linear.cuh
     auto lin = [&](Lin& l, int N, int Kin, bool bias) {
-        set_tiling(l, N, Kin);
+        set_tiling(l, N, Kin, pairs_ok);
         l.w_off = take(lin_image_bytes(l));
         l.b_off = bias ? take((int64_t)l.n_pad * 4) : -1;
     };
@@ -577,7 +579,7 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
         a.a_img = nullptr; a.a_mt_stride = 0; a.w_img = ws + l.w_off; a.k_chunks = l.k_chunks; a.n_tiles = l.n_tiles; a.tile_n = l.tile_n;
         a.bias = l.b_off >= 0 ? F(l.b_off) : nullptr; a.bias_mt_div = 0; a.bias_mt_stride = 0; a.act = ACT_NONE;
         a.mask_img = nullptr; a.mask_mt_stride = 0; a.mul_img = nullptr; a.mul_mt_stride = 0; a.aux_img = nullptr; a.resid = nullptr;
-        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = 0;
+        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = 0; a.pair = l.pair;
         return a;
     };
     // NICE forward over the couplings, in place on the state image (x's image is rebuilt by update_kernel each step)
