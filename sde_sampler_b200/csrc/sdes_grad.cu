@@ -280,7 +280,9 @@ __device__ __forceinline__ uint32_t idesc_bf16_mn(int M, int N) {
     return tc::idesc_bf16(M, N) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
 }
 
-__global__ void __launch_bounds__(LIN_THREADS, 1) wgrad_mma_kernel(const __grid_constant__ WgradArgs a) {
+constexpr int WG_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: one TMEM lane quadrant each
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_b[];
     uint8_t* smem = smem_b;
     __shared__ uint64_t s_full[3], s_empty[3], s_acc;
@@ -509,7 +511,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         if (splits < 1) splits = 1;
         ++launches;
         if (simt) wgrad_simt_kernel<<<dim3(pairs, splits), 64, 0, stream>>>(wa);
-        else wgrad_mma_kernel<<<dim3(pairs, splits), LIN_THREADS, 3 * 2 * A_BLOCK, stream>>>(wa);
+        else wgrad_mma_kernel<<<dim3(pairs, splits), WG_THREADS, 3 * 2 * A_BLOCK, stream>>>(wa);
         return cudaGetLastError();
     };
     auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride) {

@@ -16,7 +16,12 @@ namespace wide {
 constexpr int KC = 64;                       // K elements per image block / pipeline stage
 constexpr uint32_t A_HALF = 128u * KC * 2u;  // bytes of one bf16 half (hi or lo) of an activation block
 constexpr uint32_t A_BLOCK = 2u * A_HALF;    // hi | lo
-constexpr int LIN_THREADS = 192;             // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue — EPI warps, EPI/4 per TMEM lane quadrant, each on its
+// share of the columns.  A single warp per scheduler runs the ~80 dependent instructions of an 8-column group at
+// ~10 cycles each, so wide layers (one CTA per SM) use 12 epilogue warps; skinny layers keep 4 and co-schedule 3 CTAs.
+constexpr int EPI_WIDE = 12, EPI_SKINNY = 4;
+constexpr int EPI_WARPS = EPI_WIDE;               // CTA-pair kernel
+constexpr int LIN_THREADS = 64 + 32 * EPI_WARPS;
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
@@ -149,18 +154,42 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
     dy = fmaf(x * 0.3989422804014327f, e, phi_cdf);
 }
 
-// 8 consecutive output columns of one row: the fused epilogue of every layer
-__device__ __forceinline__ void epilogue8(const LinArgs& a, int mt, int r, int col, float (&v)[8]) {
+// 8 consecutive output columns of one row: the fused epilogue of every layer, split into the global loads it needs
+// (issued one group ahead so their latency hides behind the previous group's arithmetic and stores — with four
+// epilogue warps per CTA nothing else would hide it) and the arithmetic + stores.
+struct EpiPre {
+    float4 b0, b1, r0, r1;
+    uint4 m, mh, ml;
+};
+
+__device__ __forceinline__ void epi_prefetch(const LinArgs& a, int mt, int r, int col, EpiPre& p) {
     const int64_t row = (int64_t)mt * 128 + r;
     if (a.bias != nullptr) {
         const float* bp = a.bias + (a.bias_mt_div > 0 ? (int64_t)(mt / a.bias_mt_div) * a.bias_mt_stride : 0) + col;
-        const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        p.b0 = __ldg(reinterpret_cast<const float4*>(bp));
+        p.b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
     }
     if (a.resid != nullptr) {
         const float4* rp = reinterpret_cast<const float4*>(a.resid + row * a.ld_f32 + col);
-        const float4 r0 = rp[0], r1 = rp[1];
-        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        p.r0 = rp[0];
+        p.r1 = rp[1];
+    }
+    const int64_t goff = img_group_offset(r, col);
+    if (a.mask_img != nullptr) p.m = *reinterpret_cast<const uint4*>(a.mask_img + (int64_t)mt * a.mask_mt_stride + goff);
+    if (a.mul_img != nullptr) {
+        const uint8_t* mp = a.mul_img + (int64_t)mt * a.mul_mt_stride + goff;
+        p.mh = *reinterpret_cast<const uint4*>(mp);
+        p.ml = *reinterpret_cast<const uint4*>(mp + A_HALF);
+    }
+}
+
+__device__ __forceinline__ void epi_finish(const LinArgs& a, int mt, int r, int col, float (&v)[8], const EpiPre& p) {
+    const int64_t row = (int64_t)mt * 128 + r;
+    if (a.bias != nullptr) {
+        v[0] += p.b0.x; v[1] += p.b0.y; v[2] += p.b0.z; v[3] += p.b0.w; v[4] += p.b1.x; v[5] += p.b1.y; v[6] += p.b1.z; v[7] += p.b1.w;
+    }
+    if (a.resid != nullptr) {
+        v[0] += p.r0.x; v[1] += p.r0.y; v[2] += p.r0.z; v[3] += p.r0.w; v[4] += p.r1.x; v[5] += p.r1.y; v[6] += p.r1.z; v[7] += p.r1.w;
     }
     if (a.act == ACT_RELU) {
 #pragma unroll
@@ -184,16 +213,14 @@ __device__ __forceinline__ void epilogue8(const LinArgs& a, int mt, int r, int c
         *reinterpret_cast<uint4*>(o + A_HALF) = lo;
     }
     if (a.mul_img != nullptr) {
-        const uint8_t* mp = a.mul_img + (int64_t)mt * a.mul_mt_stride + goff;
         float mh[8], ml[8];
-        unpack8(*reinterpret_cast<const uint4*>(mp), mh);
-        unpack8(*reinterpret_cast<const uint4*>(mp + A_HALF), ml);
+        unpack8(p.mh, mh);
+        unpack8(p.ml, ml);
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] *= mh[q] + ml[q];
     }
     if (a.mask_img != nullptr) {
-        const uint4 m = *reinterpret_cast<const uint4*>(a.mask_img + (int64_t)mt * a.mask_mt_stride + goff);
-        const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+        const uint32_t w[4] = {p.m.x, p.m.y, p.m.z, p.m.w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t bits = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;  // bf16 hi half of the forward activation
@@ -218,6 +245,48 @@ __device__ __forceinline__ void epilogue8(const LinArgs& a, int mt, int r, int c
     }
 }
 
+__device__ __forceinline__ void epilogue8(const LinArgs& a, int mt, int r, int col, float (&v)[8]) {
+    EpiPre p;
+    epi_prefetch(a, mt, r, col, p);
+    epi_finish(a, mt, r, col, v, p);
+}
+
+// the accumulator tile of one thread's row, N columns starting at global column col0: TMEM loads and the global
+// loads of group g+1 are in flight while group g is finished
+__device__ __forceinline__ void epilogue_row(const LinArgs& a, int mt, int r, int col0, int N, uint32_t taddr) {
+    float v[8], w[8];
+    EpiPre pa, pb;
+    if (N <= 0) return;
+    tc::tmem_ld8(taddr, v);
+    epi_prefetch(a, mt, r, col0, pa);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        const bool second = c0 + 8 < N;
+        tc::wait_ld_tie<8>(v);
+        if (second) {
+            tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, w);
+            epi_prefetch(a, mt, r, col0 + c0 + 8, pb);
+        }
+        epi_finish(a, mt, r, col0 + c0, v, pa);
+        if (second) {
+            tc::wait_ld_tie<8>(w);
+            if (c0 + 16 < N) {
+                tc::tmem_ld8(taddr + (uint32_t)c0 + 16u, v);
+                epi_prefetch(a, mt, r, col0 + c0 + 16, pa);
+            }
+            epi_finish(a, mt, r, col0 + c0 + 8, w, pb);
+        }
+    }
+}
+
+// columns [lo, lo + n) of an N-column tile served by epilogue warp `e` of its lane quadrant (EPI_WARPS / 4 warps share a row)
+template <int EPI>
+__device__ __forceinline__ void epi_col_range(int N, int e_in_quad, int& lo, int& n) {
+    constexpr int PER = EPI / 4;
+    const int groups = N / 8, g_lo = groups * e_in_quad / PER, g_hi = groups * (e_in_quad + 1) / PER;
+    lo = g_lo * 8;
+    n = (g_hi - g_lo) * 8;
+}
+
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -237,7 +306,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // runs ahead across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile i
 // overlaps the MMAs of tile i+1 and per-CTA setup (TMEM allocation, barriers) is paid once per launch instead of
 // once per tile (the gradient path runs 8 192 row tiles of K = 64 per launch).
-static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const __grid_constant__ LinArgs a, const int stages, const int m_tiles) {
+template <int EPI>
+static __global__ void __launch_bounds__(64 + 32 * EPI, EPI == EPI_SKINNY ? 3 : 1) linear_mma_kernel(const __grid_constant__ LinArgs a, const int stages, const int m_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t s_full[4], s_empty[4], s_acc_full[2], s_acc_empty[2];
     __shared__ uint32_t s_tmem;
@@ -260,7 +330,7 @@ static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&s_acc_full[s], 1);
-            tc::mbar_init(&s_acc_empty[s], 128);
+            tc::mbar_init(&s_acc_empty[s], 32 * EPI);
         }
         tc::fence_mbar_init();
     }
@@ -327,24 +397,17 @@ static __global__ void __launch_bounds__(LIN_THREADS, 1) linear_mma_kernel(const
         }
     } else {  // ---- epilogue warps: TMEM lane quadrant = warp % 4
         const int q = warp & 3, r = q * 32 + lane;
+        int c_lo, c_n;
+        epi_col_range<EPI>(a.tile_n, (warp - 2) >> 2, c_lo, c_n);
         for (int i = 0; i < n_my; ++i) {
             const int tile = (int)blockIdx.x + i * (int)gridDim.x, nt = tile % a.n_tiles, mt = tile / a.n_tiles;
             const int buf = i & 1, use = i >> 1;
             tc::mbar_wait(&s_acc_full[buf], (uint32_t)(use & 1));
             tc::fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * ncols + ((uint32_t)(q * 32) << 16);
-            float v[8], w[8];
-            tc::tmem_ld8(taddr, v);
-            for (int c0 = 0; c0 < a.tile_n; c0 += 16) {
-                tc::wait_ld_tie<8>(v);
-                tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, w);
-                epilogue8(a, mt, r, nt * a.tile_n + c0, v);
-                tc::wait_ld_tie<8>(w);
-                if (c0 + 16 < a.tile_n) tc::tmem_ld8(taddr + (uint32_t)c0 + 16u, v);
-                epilogue8(a, mt, r, nt * a.tile_n + c0 + 8, w);
-            }
+            epilogue_row(a, mt, r, nt * a.tile_n + c_lo, c_n, taddr + (uint32_t)c_lo);
             tc::fence_before();
-            mbar_arrive(&s_acc_empty[buf]);  // 128 arrivals: every epilogue thread has read its TMEM lane
+            mbar_arrive(&s_acc_empty[buf]);  // every epilogue thread has read its part of the accumulator
         }
     }
     tc::fence_before();
@@ -447,7 +510,7 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LIN_THREADS, 
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&s_acc_full[s], 1);
-            tc::mbar_init(&s_acc_empty[s], 256);
+            tc::mbar_init(&s_acc_empty[s], 2 * 32 * EPI_WARPS);
         }
         tc::fence_mbar_init();
     }
@@ -527,6 +590,8 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LIN_THREADS, 
         }
     } else {  // ---- epilogue warps of both CTAs: own 128 rows, all N2 columns
         const int q = warp & 3, r = q * 32 + lane;
+        int c_lo, c_n;
+        epi_col_range<EPI_WARPS>(N2, (warp - 2) >> 2, c_lo, c_n);
         const uint32_t acc_empty_leader0 = map_to_cta(tc::smem_u32(&s_acc_empty[0]), 0);
         const uint32_t acc_empty_leader1 = map_to_cta(tc::smem_u32(&s_acc_empty[1]), 0);
         for (int i = 0; i < n_my; ++i) {
@@ -537,16 +602,7 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LIN_THREADS, 
             tc::fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * ncols + ((uint32_t)(q * 32) << 16);
             if (mt < m_tiles) {
-                float v[8], w[8];
-                tc::tmem_ld8(taddr, v);
-                for (int c0 = 0; c0 < N2; c0 += 16) {
-                    tc::wait_ld_tie<8>(v);
-                    tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, w);
-                    epilogue8(a, mt, r, n2 * N2 + c0, v);
-                    tc::wait_ld_tie<8>(w);
-                    if (c0 + 16 < N2) tc::tmem_ld8(taddr + (uint32_t)c0 + 16u, v);
-                    epilogue8(a, mt, r, n2 * N2 + c0 + 8, w);
-                }
+                epilogue_row(a, mt, r, n2 * N2 + c_lo, c_n, taddr + (uint32_t)c_lo);
             }
             tc::fence_before();
             mbar_arrive_cluster(buf == 0 ? acc_empty_leader0 : acc_empty_leader1);
@@ -596,13 +652,15 @@ static cudaError_t launch_linear(const LinArgs& a, int m_tiles, bool simt, cudaS
     }
     static bool attr_set = false;  // one process per GPU (the host side is single-threaded like the reference)
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(linear_mma_kernel<EPI_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(linear_mma_kernel<EPI_SKINNY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(linear_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (a.pair) {  // CTA-pair kernel: a.tile_n is the half tile, n_tiles is even
+    if (a.pair == 1) {  // CTA-pair kernel: a.tile_n is the half tile, n_tiles is even
         static int sms2 = 0;
         if (sms2 == 0) {
             int dev = 0;
@@ -630,7 +688,8 @@ static cudaError_t launch_linear(const LinArgs& a, int m_tiles, bool simt, cudaS
     }
     const int64_t total = (int64_t)a.n_tiles * m_tiles;
     const int grid = (int)(total < (int64_t)sms * ctas_per_sm ? total : (int64_t)sms * ctas_per_sm);
-    linear_mma_kernel<<<grid, LIN_THREADS, (size_t)stages * stage_bytes, stream>>>(a, stages, m_tiles);
+    if (ctas_per_sm > 1) linear_mma_kernel<EPI_SKINNY><<<grid, 64 + 32 * EPI_SKINNY, (size_t)stages * stage_bytes, stream>>>(a, stages, m_tiles);
+    else linear_mma_kernel<EPI_WIDE><<<grid, 64 + 32 * EPI_WIDE, (size_t)stages * stage_bytes, stream>>>(a, stages, m_tiles);
     return cudaGetLastError();
 }
 
