@@ -62,6 +62,10 @@ enum { SDES_TARGET_GMM = 0, SDES_TARGET_MULTIWELL = 1 /* DoubleWell = n_dw=d=1 *
                                            (coalesced for thread-per-trajectory kernels); the layout
                                            sdes_rollout_lv_grad reads when the same flag is set on its descriptor */
 
+#define SDES_F_KEEP_FOR_GRAD  (1u << 9) /* wide engine: keep what sdes_rollout_lv_grad needs INSIDE the workspace (the
+                                           operand image of the state at every step, the per-step gate cotangent
+                                           sums); the gradient call must then be given the same workspace */
+
 /* Layout of the flat fp32 parameter blob `params` (torch (out,in) row-major weights, C = 64):
  *   FourierMLP (models/mlp.py:85-122)
  *     in_w[C*d] in_b[C]

@@ -69,7 +69,7 @@ def run_case(name: str, case: dict) -> dict:
 
     # --- gradient of the lv loss w.r.t. every control parameter by the reference's own autograd
     #     (`loss.backward()` of Trainable.step, solver/base.py:404-407), flattened in parameter-blob order
-    if method == "lv" and d <= 64 and not str(case["target"]).startswith("nice"):
+    if method == "lv":
         from sde_sampler_b200.spec import ctrl_parameters
 
         params = ctrl_parameters(built["ctrl"])

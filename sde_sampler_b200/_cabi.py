@@ -32,6 +32,7 @@ F_REFERENCE_CTRL = 1 << 5
 F_HAS_GATE = 1 << 6
 F_MLP_SIMT = 1 << 7
 F_TRAJ_TILED = 1 << 8
+F_KEEP_FOR_GRAD = 1 << 9
 
 MASK_ISFINITE, MASK_MAX_RND, MASK_ALL = 0, 1, 2
 

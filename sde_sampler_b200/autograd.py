@@ -50,9 +50,10 @@ class LvLoss(torch.autograd.Function):
         rnd = m["rnd"].reshape(-1).double()
         w = torch.where(m["keep"].reshape(-1), 2.0 * (rnd - mean) / (n - 1.0), torch.zeros_like(rnd)) * grad_out.double()
         blob = torch.cat([p.detach().reshape(-1).float() for p in params])
+        wide = engine.is_wide(m["spec"])  # wide engine: the forward kept what is needed inside its own workspace
         g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w.float(), noise=m["noise"], seed=m["seed"],
-                                               traj_offset=m["traj_offset"], engine=lo.engine, workspace=lo._grad_workspace,
-                                               params=blob)
+                                               traj_offset=m["traj_offset"], engine=lo.engine,
+                                               workspace=lo._workspace if wide else lo._grad_workspace, params=blob)
         n_te, n_h, n_g = ctx.counts
         grads, o = [], 0
         for p in params:
@@ -92,7 +93,7 @@ class LvLoss(torch.autograd.Function):
 
 def wants_grad(loss_obj) -> bool:
     """True when the training call should return a loss with a grad_fn: grad mode on, log-variance loss, trainable
-    control parameters, and a configuration `sdes_rollout_lv_grad` covers (d <= 64, analytic target)."""
+    control parameters, and a configuration `sdes_rollout_lv_grad` covers."""
     if not torch.is_grad_enabled() or loss_obj.method != "lv":
         return False
     ctrl = loss_obj.generative_ctrl
@@ -100,9 +101,10 @@ def wants_grad(loss_obj) -> bool:
         params = ctrl_parameters(ctrl)
     except AttributeError:
         return False
-    if int(ctrl.base_model.input_embed.weight.shape[1]) > _cabi.MAX_DIM:
-        return False
+    dim = int(ctrl.base_model.input_embed.weight.shape[1])
     target = getattr(getattr(ctrl, "target_score", None), "__self__", None)
-    if target is not None and hasattr(target, "model"):  # NICE: wide engine, no gradient path yet
-        return False
+    wide = dim > _cabi.MAX_DIM or (target is not None and hasattr(target, "model"))
+    gate = getattr(ctrl, "score_model", None)
+    if wide and gate is not None and int(gate.out_layer.weight.shape[0]) != 1:
+        return False  # the wide engine has a scalar gate only
     return any(p.requires_grad for p in params)

@@ -30,6 +30,7 @@ cudaError_t launch_langevin(const IntegrateParams& a, cudaStream_t stream);
 // lv gradient (sdes_grad.cu)
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
 int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err);
+int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -428,10 +429,14 @@ static int grad_setup(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, KPar
     int rc = validate(desc, false);
     if (rc != 0) return rc;
     if (g == nullptr || g->struct_bytes != sizeof(SdesLvGradDesc)) return fail(-2, "SdesLvGradDesc is NULL or has the wrong struct_bytes");
-    if (wide_engine_needed(*desc)) return fail(-8, "the lv gradient is implemented for d <= %d with analytic targets", SDES_MAX_DIM);
     memset(&p, 0, sizeof(p));
     p.d = *desc;
     simt = (desc->flags & SDES_F_MLP_SIMT) != 0;
+    if (wide_engine_needed(*desc)) {  // wide engine: the forward ran with SDES_F_KEEP_FOR_GRAD in the same workspace
+        if (!(desc->flags & SDES_F_KEEP_FOR_GRAD)) return fail(-8, "wide-engine gradient needs the forward's SDES_F_KEEP_FOR_GRAD workspace");
+        blob_layout(p.d, p.bl);
+        return 0;
+    }
     p.d.flags = (desc->flags | SDES_F_MLP_SIMT) & ~(uint32_t)SDES_F_RETURN_TRAJ;  // fp32 tables / target images of the fused prologue
     blob_layout(p.d, p.bl);
     ws_layout(p.d, p.ws);
@@ -442,6 +447,7 @@ size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGra
     KParams p;
     bool simt;
     if (grad_setup(desc, g, p, simt) != 0) return 0;
+    if (wide_engine_needed(*desc)) return wide_workspace_bytes(*desc);
     return lv_grad_workspace_bytes(p.d, p.ws.total * (int64_t)sizeof(float), g->chunk_rows);
 }
 
@@ -452,6 +458,16 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
     int rc = grad_setup(desc, g, p, simt);
     if (rc != 0) return rc;
     if (!desc->ts || !desc->params || !desc->workspace) return fail(-5, "ts/params/workspace must be non-NULL");
+    if (wide_engine_needed(*desc)) {
+        if (!g->w || !g->grad_params || !g->grad_emb) return fail(-5, "w/grad_params/grad_emb must be non-NULL");
+        if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
+        if (wide_workspace_bytes(*desc) > desc->workspace_bytes) return fail(-6, "workspace_bytes too small for the keep-mode wide workspace");
+        if (desc->batch == 0) return 0;
+        cudaError_t we = cudaSuccess;
+        g_launches += launch_lv_grad_wide_desc(p, *g, simt, reinterpret_cast<cudaStream_t>(stream_), &we);
+        if (we != cudaSuccess) return fail(-7, "wide lv gradient launch failed: %s", cudaGetErrorString(we));
+        return 0;
+    }
     if (!g->xs || !g->w || !g->grad_params || !g->grad_emb) return fail(-5, "xs/w/grad_params/grad_emb must be non-NULL");
     if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
     if (desc->target_kind == SDES_TARGET_GMM && (!desc->gmm_loc || !desc->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
 
 // column sums of a delta image: bias gradients, and per-time-step sums for d loss / d emb
 __global__ void __launch_bounds__(128) colsum_kernel(const uint8_t* __restrict__ img, int n_chunks, int n_valid, float* __restrict__ out,
-                                                     int mt_div, int64_t mt_stride) {
+                                                     int mt_div, int64_t mt_stride, int planar, int Hp) {
     __shared__ float s_part[16][64];
     const int mt = blockIdx.x, tid = threadIdx.x, kg = tid & 7, rs = tid >> 3;
     float* dst = out + (mt_div > 0 ? (int64_t)(mt / mt_div) * mt_stride : 0);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(128) colsum_kernel(const uint8_t* __restrict__
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) s += s_part[i][tid];
-            const int f = ch * 64 + tid;
+            const int f = to_natural(ch * 64 + tid, planar, Hp);
             if (f < n_valid && s != 0.f) atomicAdd(dst + f, s);
         }
         __syncthreads();
@@ -274,6 +274,7 @@ struct WgradArgs {
     int m_tiles;
     float* dw; int ldw;                   // row-major (out, in) gradient, += via atomics
     int n_valid, k_valid;
+    int n_planar, k_planar, Hp;           // wide engine: image feature index -> natural index (2 (p % Hp) + p / Hp)
 };
 
 __device__ __forceinline__ uint32_t idesc_bf16_mn(int M, int N) {
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
             tc::mbar_wait(&s_acc, 0);
             tc::fence_after();
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-            const int n = cd * 64 + (r & 63);
+            const int n = to_natural(cd * 64 + (r & 63), a.n_planar, a.Hp);
             for (int c0 = 0; c0 < 64; c0 += 8) {
                 float v[8];
                 tc::tmem_ld8(taddr + (uint32_t)c0, v);
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
                 if (n < a.n_valid) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int k = ca * 64 + c0 + e;
+                        const int k = to_natural(ca * 64 + c0 + e, a.k_planar, a.Hp);
                         if (k < a.k_valid && v[e] != 0.f) atomicAdd(a.dw + (int64_t)n * a.ldw + k, v[e]);
                     }
                 }
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
 // the same contraction on the CUDA cores (SDES_F_MLP_SIMT cross-check)
 __global__ void __launch_bounds__(64) wgrad_simt_kernel(const WgradArgs a) {
     const int pair = blockIdx.x, cd = pair / a.a_chunks, ca = pair % a.a_chunks;
-    const int nl = threadIdx.x, n = cd * 64 + nl;
+    const int nl = threadIdx.x, n = to_natural(cd * 64 + nl, a.n_planar, a.Hp);
     for (int k0 = 0; k0 < 64; k0 += 8) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int64_t mt = blockIdx.y; mt < a.m_tiles; mt += gridDim.y) {
@@ -394,10 +395,83 @@ __global__ void __launch_bounds__(64) wgrad_simt_kernel(const WgradArgs a) {
         if (n < a.n_valid) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int k = ca * 64 + k0 + e;
+                const int k = to_natural(ca * 64 + k0 + e, a.k_planar, a.Hp);
                 if (k < a.k_valid && acc[e] != 0.f) atomicAdd(a.dw + (int64_t)n * a.ldw + k, acc[e]);
             }
         }
+    }
+}
+
+// ---- wide engine (planar state, one warp per row): output cotangent of the control network
+struct CotWideArgs {
+    SdesRolloutDesc d;
+    const float* tab;
+    const float* w;
+    const float* nn;      // (rows, P) planar
+    uint8_t* dnn_img;     // [m_tile][pc] blocks, planar features
+    int Hp, P, pc, s0;
+    int64_t Bp;
+};
+
+__device__ __forceinline__ void img_store_pair_g(uint8_t* img, int pc, int Hp, int64_t row, int plane, int k, float v0, float v1) {
+    const int mt = (int)(row >> 7), r = (int)(row & 127), kk = plane * Hp + k;
+    uint32_t hi, lo;
+    split_pair(v0, v1, hi, lo);
+    uint8_t* o = img + (int64_t)mt * pc * A_BLOCK + img_group_offset(r, kk) + (kk & 7) * 2;
+    *reinterpret_cast<uint32_t*>(o) = hi;
+    *reinterpret_cast<uint32_t*>(o + A_HALF) = lo;
+}
+
+__global__ void __launch_bounds__(256) cotangent_wide_kernel(const CotWideArgs a) {
+    const SdesRolloutDesc& d = a.d;
+    const int lane = threadIdx.x & 31;
+    const int64_t rr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int s = a.s0 + (int)(rr / a.Bp);
+    const int64_t b = rr % a.Bp, B = d.batch;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : 0;
+    const int dim = d.dim, Hp = a.Hp;
+    const StepCoef c = make_step_coef(d, a.tab + (int64_t)s * TAB_STRIDE);
+    const float cscale = (valid ? a.w[bb] : 0.f) * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
+    const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
+    const float* noise = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
+    const float* nr = a.nn + rr * a.P;
+    for (int q = lane; q < Hp / 2; q += 32) {
+        float cot[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * q < dim) {
+            float e[4];
+            if (c.from_hbm) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < dim) ? noise[4 * q + r] : 0.f;
+            } else {
+                const float4 n4 = normal4_call(c.k0, c.k1, traj, (uint32_t)s, (uint32_t)q);
+                e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+            }
+            const float2 ne = *reinterpret_cast<const float2*>(nr + 2 * q), no = *reinterpret_cast<const float2*>(nr + Hp + 2 * q);
+            const float nn4[4] = {ne.x, no.x, ne.y, no.y};  // natural order within the quad
+#pragma unroll
+            for (int r = 0; r < 4; ++r) cot[r] = (4 * q + r < dim && fabsf(nn4[r]) <= c.cm) ? cscale * e[r] : 0.f;
+        }
+        img_store_pair_g(a.dnn_img, a.pc, Hp, rr, 0, 2 * q, cot[0], cot[2]);
+        img_store_pair_g(a.dnn_img, a.pc, Hp, rr, 1, 2 * q, cot[1], cot[3]);
+    }
+}
+
+// d loss / d gate(s) = 1[|gate| < clip] sum_b w_b q[s][b]   (q written by the wide forward in keep mode)
+__global__ void __launch_bounds__(256) qgate_reduce_kernel(const float* __restrict__ q, const float* __restrict__ w, const float* __restrict__ gate,
+                                                           int64_t B, int64_t Bp, float clip_model, float* __restrict__ out) {
+    __shared__ float s_red[8];
+    const int s = blockIdx.x;
+    float acc = 0.f;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) acc = fmaf(w[b], q[(int64_t)s * Bp + b], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_red[i];
+        out[s] = fabsf(gate[s]) < clip_model ? t : 0.f;
     }
 }
 
@@ -430,6 +504,178 @@ static cudaError_t launch_cot(const CotArgs& a, int m_tiles, cudaStream_t stream
 using namespace grad;
 
 void launch_prepare(const KParams& p, cudaStream_t stream);
+
+// ---- wide engine gradient: scratch layout after the forward plan (WideGradView::grad_base)
+struct WideGradScratch {
+    Lin b_h[SDES_MAX_HIDDEN], b_out;
+    int chunk_steps;
+    int64_t a_img[SDES_MAX_HIDDEN + 1], gp_img[SDES_MAX_HIDDEN + 1], nn, dnn_img, dh_img[2], total;
+};
+
+static void wide_scratch(const WideGradView& v, WideGradScratch& sc) {
+    int64_t rows = ((int64_t)1 << 27) / v.P;          // keep nn (rows x P fp32) at <= 512 MB
+    sc.chunk_steps = (int)(rows / v.Bp);
+    if (sc.chunk_steps < 1) sc.chunk_steps = 1;
+    if (sc.chunk_steps > v.T) sc.chunk_steps = v.T;
+    const int64_t m_tiles = (int64_t)sc.chunk_steps * v.m_tiles;
+    int64_t o = v.grad_base;
+    auto take = [&](int64_t bytes) { int64_t r = o; o = align256(o + bytes); return r; };
+    for (int l = 0; l < v.nh; ++l) {
+        set_tiling(sc.b_h[l], C, C);
+        sc.b_h[l].w_off = take(lin_image_bytes(sc.b_h[l]));
+        sc.b_h[l].b_off = -1;
+    }
+    set_tiling(sc.b_out, C, v.P);
+    sc.b_out.w_off = take(lin_image_bytes(sc.b_out));
+    sc.b_out.b_off = -1;
+    const int64_t img1 = m_tiles * A_BLOCK, imgp = img1 * v.pc;
+    for (int l = 0; l <= v.nh; ++l) {
+        sc.a_img[l] = take(img1);
+        sc.gp_img[l] = take(img1);
+    }
+    sc.nn = take(m_tiles * 128 * (int64_t)v.P * 4);
+    sc.dnn_img = take(imgp);
+    sc.dh_img[0] = take(img1);
+    sc.dh_img[1] = take(img1);
+    sc.total = o;
+}
+
+int64_t lv_grad_wide_scratch_bytes(const WideGradView& v) {
+    WideGradScratch sc;
+    wide_scratch(v, sc);
+    return sc.total - v.grad_base;
+}
+
+// Gradient for a wide-engine rollout that ran with SDES_F_KEEP_FOR_GRAD in the SAME workspace: the per-step state images
+// are already tensor-core operands, the forward's weight images are still there; only W^T images are added.
+int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const WideGradView& v, bool simt, cudaStream_t stream, cudaError_t* err) {
+    const SdesRolloutDesc& d = kp.d;
+    WideGradScratch sc;
+    wide_scratch(v, sc);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
+    auto F = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+    int64_t launches = 0;
+    *err = cudaSuccess;
+#define GRADW_CHECK(expr)                         \
+    do {                                          \
+        *err = (expr);                            \
+        if (*err != cudaSuccess) return launches; \
+    } while (0)
+    const float* blob = d.params;
+    auto image_t = [&](const Lin& l, const float* src, int src_ld, int N, int K, int k_planar) {
+        ImgArgs ia;
+        ia.src = src; ia.src_ld = src_ld; ia.N = N; ia.K = K; ia.transpose = 1; ia.n_planar = 0; ia.k_planar = k_planar; ia.Hp = v.Hp;
+        ia.out = ws + l.w_off; ia.n_pad = l.n_pad; ia.tile_n = l.tile_n; ia.k_chunks = l.k_chunks;
+        const int64_t groups = (int64_t)l.n_pad * l.k_chunks * 8;
+        weight_image_kernel<<<(int)((groups + 255) / 256), 256, 0, stream>>>(ia);
+        ++launches;
+        return cudaGetLastError();
+    };
+    for (int l = 0; l < v.nh; ++l) GRADW_CHECK(image_t(sc.b_h[l], blob + kp.bl.h_w[l], C, C, C, 0));
+    GRADW_CHECK(image_t(sc.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));   // out[n][k = planar dim] = W_out[natural(k)][n]
+    GRADW_CHECK(cudaMemsetAsync(g.grad_params, 0, (size_t)d.n_params * 4, stream));
+    GRADW_CHECK(cudaMemsetAsync(g.grad_emb, 0, (size_t)v.T * C * 4, stream));
+    auto base_args = [&](const Lin& l) {
+        LinArgs a;
+        a.a_img = nullptr; a.a_mt_stride = A_BLOCK; a.w_img = ws + l.w_off; a.k_chunks = l.k_chunks; a.n_tiles = l.n_tiles; a.tile_n = l.tile_n;
+        a.bias = l.b_off >= 0 ? F(l.b_off) : nullptr; a.bias_mt_div = 0; a.bias_mt_stride = 0; a.act = ACT_NONE;
+        a.mask_img = nullptr; a.mask_mt_stride = 0; a.mul_img = nullptr; a.mul_mt_stride = 0; a.aux_img = nullptr; a.resid = nullptr;
+        a.out_f32 = nullptr; a.ld_f32 = v.P; a.out_img = nullptr; a.out_mt_stride = A_BLOCK; a.pair = 0;
+        return a;
+    };
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRADW_CHECK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * (int)A_BLOCK));
+        attr_set = true;
+    }
+    auto wgrad = [&](const uint8_t* d_img, int d_chunks, const uint8_t* a_img, int a_chunks, int m_tiles, float* dw, int ldw, int n_valid,
+                     int k_valid, int n_planar, int k_planar) {
+        WgradArgs wa;
+        wa.d_img = d_img; wa.d_chunks = d_chunks; wa.a_img = a_img; wa.a_chunks = a_chunks; wa.m_tiles = m_tiles; wa.dw = dw; wa.ldw = ldw;
+        wa.n_valid = n_valid; wa.k_valid = k_valid; wa.n_planar = n_planar; wa.k_planar = k_planar; wa.Hp = v.Hp;
+        const int pairs = d_chunks * a_chunks;
+        int splits = 296 / pairs;
+        if (splits > m_tiles) splits = m_tiles;
+        if (splits < 1) splits = 1;
+        ++launches;
+        if (simt) wgrad_simt_kernel<<<dim3(pairs, splits), 64, 0, stream>>>(wa);
+        else wgrad_mma_kernel<<<dim3(pairs, splits), WG_THREADS, 3 * 2 * A_BLOCK, stream>>>(wa);
+        return cudaGetLastError();
+    };
+    auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride, int planar) {
+        colsum_kernel<<<m_tiles, 128, 0, stream>>>(img, n_chunks, n_valid, out, mt_div, mt_stride, planar, v.Hp);
+        ++launches;
+        return cudaGetLastError();
+    };
+    float* gp = g.grad_params;
+    const int x_stride_blocks = v.pc;
+    for (int s0 = 0; s0 < v.T; s0 += sc.chunk_steps) {
+        const int ns = (s0 + sc.chunk_steps <= v.T) ? sc.chunk_steps : v.T - s0;
+        const int m_tiles = ns * v.m_tiles;
+        const uint8_t* ximg = ws + v.ximg + (int64_t)s0 * v.ximg_slot;   // the chunk's state images are contiguous
+        {
+            LinArgs a = base_args(v.mlp_in);
+            a.a_img = ximg; a.a_mt_stride = (int64_t)x_stride_blocks * A_BLOCK;
+            a.bias = F(v.emb) + (int64_t)s0 * C; a.bias_mt_div = v.m_tiles; a.bias_mt_stride = C;
+            a.act = ACT_GELU_GRAD; a.out_img = ws + sc.a_img[0]; a.aux_img = ws + sc.gp_img[0];
+            GRADW_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+            for (int l = 0; l < v.nh; ++l) {
+                a = base_args(v.mlp_h[l]);
+                a.a_img = ws + sc.a_img[l]; a.act = ACT_GELU_GRAD; a.out_img = ws + sc.a_img[l + 1]; a.aux_img = ws + sc.gp_img[l + 1];
+                GRADW_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+            }
+            a = base_args(v.mlp_out);
+            a.a_img = ws + sc.a_img[v.nh]; a.out_f32 = F(sc.nn);
+            GRADW_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+        }
+        {
+            CotWideArgs ca;
+            ca.d = d; ca.tab = F(v.tab); ca.w = g.w; ca.nn = F(sc.nn); ca.dnn_img = ws + sc.dnn_img; ca.Hp = v.Hp; ca.P = v.P; ca.pc = v.pc;
+            ca.s0 = s0; ca.Bp = v.Bp;
+            cotangent_wide_kernel<<<m_tiles * 16, 256, 0, stream>>>(ca);
+            ++launches;
+            GRADW_CHECK(cudaGetLastError());
+        }
+        GRADW_CHECK(wgrad(ws + sc.dnn_img, v.pc, ws + sc.a_img[v.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C, 1, 0));
+        GRADW_CHECK(colsum(ws + sc.dnn_img, v.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0, 1));
+        int cur = 0;
+        {
+            LinArgs a = base_args(sc.b_out);
+            a.a_img = ws + sc.dnn_img; a.a_mt_stride = (int64_t)v.pc * A_BLOCK; a.mul_img = ws + sc.gp_img[v.nh]; a.mul_mt_stride = A_BLOCK;
+            a.out_img = ws + sc.dh_img[cur];
+            GRADW_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+        }
+        for (int l = v.nh - 1; l >= 0; --l) {
+            GRADW_CHECK(wgrad(ws + sc.dh_img[cur], 1, ws + sc.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C, 0, 0));
+            GRADW_CHECK(colsum(ws + sc.dh_img[cur], 1, C, gp + kp.bl.h_b[l], m_tiles, 0, 0, 0));
+            LinArgs a = base_args(sc.b_h[l]);
+            a.a_img = ws + sc.dh_img[cur]; a.mul_img = ws + sc.gp_img[l]; a.mul_mt_stride = A_BLOCK; a.out_img = ws + sc.dh_img[1 - cur];
+            GRADW_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
+            cur = 1 - cur;
+        }
+        GRADW_CHECK(wgrad(ws + sc.dh_img[cur], 1, ximg, v.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim, 0, 1));
+        GRADW_CHECK(colsum(ws + sc.dh_img[cur], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, v.m_tiles, C, 0));
+    }
+    if (g.grad_gate != nullptr) {
+        if ((d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED) {
+            qgate_reduce_kernel<<<v.T, 256, 0, stream>>>(F(v.qgate), g.w, F(v.gate), v.B, v.Bp, d.clip_model, g.grad_gate);
+            ++launches;
+            GRADW_CHECK(cudaGetLastError());
+        } else {
+            GRADW_CHECK(cudaMemsetAsync(g.grad_gate, 0, (size_t)v.T * 4, stream));
+        }
+    }
+#undef GRADW_CHECK
+    return launches;
+}
+
+void wide_grad_view(const SdesRolloutDesc& d, wide::WideGradView& v);  // sdes_wide.cu
+
+int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err) {
+    WideGradView v;
+    wide_grad_view(kp.d, v);
+    return launch_lv_grad_wide(kp, g, v, simt, stream, err);
+}
 
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows) {
     GradPlan p;
@@ -504,7 +750,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     auto wgrad = [&](const uint8_t* d_img, int d_chunks, const uint8_t* a_img, int a_chunks, int m_tiles, float* dw, int ldw, int n_valid, int k_valid) {
         WgradArgs wa;
         wa.d_img = d_img; wa.d_chunks = d_chunks; wa.a_img = a_img; wa.a_chunks = a_chunks; wa.m_tiles = m_tiles; wa.dw = dw; wa.ldw = ldw;
-        wa.n_valid = n_valid; wa.k_valid = k_valid;
+        wa.n_valid = n_valid; wa.k_valid = k_valid; wa.n_planar = 0; wa.k_planar = 0; wa.Hp = 64;
         const int pairs = d_chunks * a_chunks;
         int splits = 296 / pairs;
         if (splits > m_tiles) splits = m_tiles;
@@ -515,7 +761,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         return cudaGetLastError();
     };
     auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride) {
-        colsum_kernel<<<m_tiles, 128, 0, stream>>>(img, n_chunks, n_valid, out, mt_div, mt_stride);
+        colsum_kernel<<<m_tiles, 128, 0, stream>>>(img, n_chunks, n_valid, out, mt_div, mt_stride, 0, 64);
         ++launches;
         return cudaGetLastError();
     };

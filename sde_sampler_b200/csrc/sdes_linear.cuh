@@ -54,6 +54,14 @@ static void set_tiling(Lin& l, int N, int K, bool allow_pair = false) {
 }
 static int64_t lin_image_bytes(const Lin& l) { return (int64_t)l.n_pad * l.k_chunks * 64 * 4; }
 
+// What the lv-gradient pass (sdes_grad.cu) needs to know about a wide-engine workspace written in keep mode
+struct WideGradView {
+    int d, Hp, P, pc, T, nh, m_tiles;
+    int64_t B, Bp;
+    int64_t tab, emb, gate, ximg, ximg_slot, qgate, grad_base;
+    Lin mlp_in, mlp_h[SDES_MAX_HIDDEN], mlp_out;
+};
+
 // ---------------------------------------------------------------------------- bf16 split
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     hi = tc::pack_bf16x2(a, b);  // a in the low half

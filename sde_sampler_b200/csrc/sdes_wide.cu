@@ -54,6 +54,11 @@ struct Plan {
     int64_t xst, nn, h, g, rnd, logp;                      // fp32 state arrays
     int64_t ximg, gimg, m_img[2], act_img, d_img[2];       // operand images
     int64_t act_stride_layer, act_stride_coup;
+    // keep mode (SDES_F_KEEP_FOR_GRAD): one state image per time step, a separate image for the NICE running state,
+    // per-(step, trajectory) gate cotangent sums, and the scratch of the gradient pass (sdes_grad.cu)
+    bool keep;
+    int64_t ximg_slot;     // bytes between the state images of consecutive steps (0 = one shared slot)
+    int64_t himg, qgate, grad_base;
     int64_t total;
 };
 
@@ -110,7 +115,11 @@ static bool make_plan(const SdesRolloutDesc& d, Plan& p) {
     p.rnd = take(p.Bp * 4);
     p.logp = take(p.Bp * 4);
     const int64_t img_p = (int64_t)p.m_tiles * p.pc * A_BLOCK;
-    p.ximg = take(img_p);
+    p.keep = (d.flags & SDES_F_KEEP_FOR_GRAD) != 0;
+    p.ximg_slot = p.keep ? img_p : 0;
+    p.ximg = take(p.keep ? img_p * (p.T + 1) : img_p);
+    p.himg = (p.keep && p.nice) ? take(img_p) : p.ximg;  // without keep the couplings work in place on the state image
+    p.qgate = take(p.keep ? (int64_t)p.T * p.Bp * 4 : 0);
     p.gimg = take(p.nice ? img_p : 0);
     p.m_img[0] = take((int64_t)p.m_tiles * A_BLOCK);
     p.m_img[1] = take((int64_t)p.m_tiles * A_BLOCK);
@@ -119,6 +128,7 @@ static bool make_plan(const SdesRolloutDesc& d, Plan& p) {
     p.act_img = take(p.act_stride_coup * p.n_coup);
     p.d_img[0] = take(p.act_stride_layer);
     p.d_img[1] = take(p.act_stride_layer);
+    p.grad_base = o;
     p.total = o;
     return true;
 }
@@ -239,7 +249,8 @@ struct RowArgs {
     int64_t Bp;
     const float *tab, *gate, *vec_prior, *vec_ref, *vec_es, *scalars, *gmm_mu, *gmm_h, *gmm_c;
     float *xst, *nn, *h, *g, *rnd, *logp;
-    uint8_t *ximg, *gimg;
+    uint8_t *ximg, *gimg;   // ximg: where this kernel WRITES the state image (init: step 0; update: step + 1)
+    float* qgate;           // keep mode: (T, Bp) gate cotangent sums, else NULL
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) update_kernel(const RowArgs
     const float* gr = a.g + row * P;
     const float* noise = c.from_hbm ? d.noise + ((int64_t)step * d.batch + row) * dim : nullptr;
     float* xs_out = (d.flags & SDES_F_RETURN_TRAJ) ? d.xs + ((int64_t)(step + 1) * d.batch + row) * dim : nullptr;
-    float cost = 0.f, ito = 0.f;
+    float cost = 0.f, ito = 0.f, qsum = 0.f;
     for (int q = lane; 4 * q < dim; q += 32) {
         float e[4];
         if (c.from_hbm) {
@@ -416,6 +427,8 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) update_kernel(const RowArgs
             else if (d.ctrl_kind == SDES_CTRL_LERP_PRIOR) part = outer * (clipf((1.0f - lerp_w) * pscore, cs) * gate);
             else if (d.ctrl_kind == SDES_CTRL_LERP_TARGET) part = outer * (clipf(lerp_w * sc4[r], cs) * gate);
             const float g = clipf(nn4[r], c.cm) + part;
+            // d rnd / d gate: the Ito coefficient times the un-gated score part (sdes_grad.cu); gate != 0 assumed
+            if (a.qgate != nullptr) qsum = fmaf((c.exp_int ? c.sg * c.beta_k : c.sqrt_dt) * e[r], part / gate, qsum);
             if (c.exp_int) {
                 cost = fmaf(g, g, cost);
                 ito = fmaf(c.sg * g * e[r], c.beta_k, ito);
@@ -437,6 +450,10 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) update_kernel(const RowArgs
     }
     cost = warp_sum(cost);
     ito = warp_sum(ito);
+    if (a.qgate != nullptr) {
+        qsum = warp_sum(qsum);
+        if (lane == 0) a.qgate[(int64_t)step * a.Bp + row] = qsum;
+    }
     if (lane == 0) {
         float rnd = a.rnd[row];
         finish_step(d, c, tab, cost, ito, rnd);
@@ -497,9 +514,25 @@ const char* wide_validate(const SdesRolloutDesc& d) {
     return nullptr;
 }
 
+void wide_grad_view(const SdesRolloutDesc& d, wide::WideGradView& v) {
+    Plan p;
+    make_plan(d, p);
+    v.d = p.d; v.Hp = p.Hp; v.P = p.P; v.pc = p.pc; v.T = p.T; v.nh = p.nh; v.m_tiles = p.m_tiles; v.B = p.B; v.Bp = p.Bp;
+    v.tab = p.tab; v.emb = p.emb; v.gate = p.gate; v.ximg = p.ximg; v.ximg_slot = p.ximg_slot; v.qgate = p.qgate; v.grad_base = p.grad_base;
+    v.mlp_in = p.mlp_in; v.mlp_out = p.mlp_out;
+    for (int l = 0; l < SDES_MAX_HIDDEN; ++l) v.mlp_h[l] = p.mlp_h[l];
+}
+
+int64_t lv_grad_wide_scratch_bytes(const wide::WideGradView& v);  // sdes_grad.cu
+
 size_t wide_workspace_bytes(const SdesRolloutDesc& d) {
     Plan p;
     make_plan(d, p);
+    if (p.keep) {
+        wide::WideGradView v;
+        wide_grad_view(d, v);
+        return (size_t)(p.grad_base + lv_grad_wide_scratch_bytes(v));
+    }
     return (size_t)p.total;
 }
 
@@ -567,8 +600,12 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
     ra.scalars = F(p.scalars); ra.gmm_mu = F(p.gmm_mu); ra.gmm_h = F(p.gmm_h); ra.gmm_c = F(p.gmm_c);
     ra.xst = F(p.xst); ra.nn = F(p.nn); ra.h = F(p.h); ra.g = F(p.g); ra.rnd = F(p.rnd); ra.logp = F(p.logp);
     ra.ximg = ws + p.ximg; ra.gimg = ws + p.gimg;
+    ra.qgate = (p.keep && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED) ? F(p.qgate) : nullptr;
     const int row_blocks_pad = (int)((p.Bp + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
     const int row_blocks = (int)((p.B + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+    // keep mode: every step has its own state image; padding rows / columns of the later slots must be finite zeros
+    // (the gradient's wgrad GEMMs contract over ALL rows of a tile)
+    if (p.keep) WIDE_CHECK(cudaMemsetAsync(ws + p.ximg + p.ximg_slot, 0, (size_t)p.ximg_slot * p.T, stream));
     init_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra);
     ++launches;
     WIDE_CHECK(cudaGetLastError());
@@ -583,20 +620,21 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
         return a;
     };
     // NICE forward over the couplings, in place on the state image (x's image is rebuilt by update_kernel each step)
-    auto nice_forward = [&]() -> cudaError_t {
+    auto nice_forward = [&](const uint8_t* x_img) -> cudaError_t {
+        uint8_t* h_img = p.keep ? ws + p.himg : const_cast<uint8_t*>(x_img);
         for (int c = 0; c < p.n_coup; ++c) {
             const int on = ((p.mc + c) % 2) ? 0 : 1, off = 1 - on;  // plane index: 0 = even units (distr/nice.py:79-82)
             for (int l = 0; l < p.n_lin; ++l) {
                 LinArgs a = base_args(p.nf[c][l]);
                 uint8_t* act_out = ws + p.act_img + c * p.act_stride_coup + l * p.act_stride_layer;
-                if (l == 0) { a.a_img = ws + p.ximg + (int64_t)off * (p.Hp / 64) * A_BLOCK; a.a_mt_stride = x_stride; }
+                if (l == 0) { a.a_img = (c == 0 ? x_img : h_img) + (int64_t)off * (p.Hp / 64) * A_BLOCK; a.a_mt_stride = x_stride; }
                 else { a.a_img = act_out - p.act_stride_layer; a.a_mt_stride = act_stride; }
                 if (l < p.n_lin - 1) { a.act = ACT_RELU; a.out_img = act_out; a.out_mt_stride = act_stride; }
                 else {
                     // on <- on + shift: the first two couplings still read x's planes, later ones the running state h
                     a.resid = (c < 2 ? F(p.xst) : F(p.h)) + on * p.Hp;
                     a.out_f32 = F(p.h) + on * p.Hp;
-                    a.out_img = ws + p.ximg + (int64_t)on * (p.Hp / 64) * A_BLOCK;
+                    a.out_img = h_img + (int64_t)on * (p.Hp / 64) * A_BLOCK;
                     a.out_mt_stride = x_stride;
                 }
                 cudaError_t e = launch_linear(a, p.m_tiles, simt, stream, launches);
@@ -608,10 +646,12 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
     const bool need_score = d.ctrl_kind != SDES_CTRL_CLIPPED && d.ctrl_kind != SDES_CTRL_LERP_PRIOR;
 
     for (int i = 0; i < p.T; ++i) {
+        const uint8_t* x_img = ws + p.ximg + (int64_t)i * p.ximg_slot;   // image of the state at step i
+        ra.ximg = ws + p.ximg + (int64_t)(i + 1) * p.ximg_slot;           // where update_kernel writes step i + 1
         // ---- control MLP (models/mlp.py:114-122): x image -> 64 -> ... -> 64 -> nn (fp32, planar)
         {
             LinArgs a = base_args(p.mlp_in);
-            a.a_img = ws + p.ximg; a.a_mt_stride = x_stride; a.bias = F(p.emb) + (int64_t)i * C; a.act = ACT_GELU;
+            a.a_img = x_img; a.a_mt_stride = x_stride; a.bias = F(p.emb) + (int64_t)i * C; a.act = ACT_GELU;
             a.out_img = ws + p.m_img[0]; a.out_mt_stride = m_stride;
             WIDE_CHECK(launch_linear(a, p.m_tiles, simt, stream, launches));
             int cur = 0;
@@ -630,8 +670,7 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
         if (need_score) {
             if (p.nice) {
                 if (p.n_coup == 1) WIDE_CHECK(cudaMemcpyAsync(F(p.h), F(p.xst), p.Bp * (int64_t)p.P * 4, cudaMemcpyDeviceToDevice, stream));
-                WIDE_CHECK(nice_forward());
-                if (p.n_coup == 1) {}  // (single coupling: the untouched plane of h was copied above)
+                WIDE_CHECK(nice_forward(x_img));
                 latent_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
                 ++launches;
                 WIDE_CHECK(cudaGetLastError());
@@ -666,7 +705,7 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
     // ---- terminal cost
     if (p.nice) {
         if (p.n_coup == 1) WIDE_CHECK(cudaMemcpyAsync(F(p.h), F(p.xst), p.Bp * (int64_t)p.P * 4, cudaMemcpyDeviceToDevice, stream));
-        WIDE_CHECK(nice_forward());
+        WIDE_CHECK(nice_forward(ws + p.ximg + (int64_t)p.T * p.ximg_slot));
         latent_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
     } else {
         gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);

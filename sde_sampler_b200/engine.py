@@ -184,6 +184,11 @@ def _check_device(name: str, t: torch.Tensor | None, device):
         raise ValueError(f"{name} lives on {t.device}, the rollout runs on {device}")
 
 
+def is_wide(spec: RolloutSpec) -> bool:
+    """Served by the wide engine (csrc/sdes_wide.cu): state wider than the fused kernels hold, or a NICE target."""
+    return spec.dim > _cabi.MAX_DIM or spec.target["kind"] == "nice"
+
+
 def _mma_pad_dim(d: int) -> int:
     return 8 if d <= 8 else 16 if d <= 16 else 32 if d <= 32 else 48 if d <= 48 else 56 if d <= 56 else 64
 
@@ -195,7 +200,8 @@ def tiled_traj_numel(T: int, B: int, dim: int) -> int:
 
 def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
-            params: torch.Tensor | None = None, traj_tiled: bool = False, traj_buffer: Workspace | None = None):
+            params: torch.Tensor | None = None, traj_tiled: bool = False, traj_buffer: Workspace | None = None,
+            keep_for_grad: bool = False):
     """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None); with `traj_tiled`
     the trajectory comes back as a flat buffer in the row-tiled layout that `lv_grad` consumes."""
     lib = _cabi.lib()
@@ -216,6 +222,10 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
         _check_device("distribution parameters", k, device)
     d.ts, d.params, d.n_params = ts.data_ptr(), params.data_ptr(), params.numel()
     d.seed, d.traj_offset = seed & 0xFFFFFFFFFFFFFFFF, traj_offset
+    if keep_for_grad and is_wide(spec):
+        # wide engine: what the gradient needs stays inside the workspace (state image per step, gate cotangent sums)
+        d.flags |= _cabi.F_KEEP_FOR_GRAD
+        d.flags &= ~_cabi.F_RETURN_TRAJ
     x_T = torch.empty_like(x0c)
     rnd = torch.empty((B, 1), dtype=torch.float32, device=device)
     xs = None
@@ -255,24 +265,32 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
     noise).  Returns (grad_params blob, grad_emb (T,64), grad_gate (T,gate_dim) | None) — see include/sdes_b200.h
     `sdes_rollout_lv_grad`."""
     lib = _cabi.lib()
-    if not xs.is_cuda:
+    wide = is_wide(spec)
+    if not w.is_cuda:
         raise _cabi.SdesError("the fused gradient runs on a CUDA device only; there is no CPU path")
-    device = xs.device
+    device = w.device
     T = int(spec.ts.shape[0]) - 1
     w = w.detach().reshape(-1).to(torch.float32).contiguous()
     B = w.numel()
-    tiled = xs.ndim == 1  # the flat row-tiled buffer of rollout(..., traj_tiled=True)
-    if tiled:
-        if xs.numel() != tiled_traj_numel(T, B, spec.dim):
-            raise ValueError("tiled xs does not match (T, B, dim)")
-    elif tuple(xs.shape) != (T + 1, B, spec.dim):
-        raise ValueError(f"xs must be {(T + 1, B, spec.dim)}, got {tuple(xs.shape)}")
-    xs = xs.detach().to(torch.float32).contiguous()
+    tiled = False
+    if wide:
+        if workspace is None or workspace.buf is None:
+            raise ValueError("the wide-engine gradient needs the workspace of the forward call (keep_for_grad=True)")
+    else:
+        tiled = xs.ndim == 1  # the flat row-tiled buffer of rollout(..., traj_tiled=True)
+        if tiled:
+            if xs.numel() != tiled_traj_numel(T, B, spec.dim):
+                raise ValueError("tiled xs does not match (T, B, dim)")
+        elif tuple(xs.shape) != (T + 1, B, spec.dim):
+            raise ValueError(f"xs must be {(T + 1, B, spec.dim)}, got {tuple(xs.shape)}")
+        xs = xs.detach().to(torch.float32).contiguous()
     ts = spec.ts.to(device=device, dtype=torch.float32).contiguous()
     d, keep = fill_desc(spec, batch=B, engine=engine)
     d.flags &= ~_cabi.F_RETURN_TRAJ
     if tiled:
         d.flags |= _cabi.F_TRAJ_TILED
+    if wide:
+        d.flags |= _cabi.F_KEEP_FOR_GRAD
     if params is None:
         params = pack_params(spec)
     d.ts, d.params, d.n_params = ts.data_ptr(), params.data_ptr(), params.numel()
@@ -288,13 +306,18 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
     grad_gate = None
     if spec.gate is not None:
         grad_gate = torch.empty((T, int(spec.gate["out_w"].shape[0])), dtype=torch.float32, device=device)
-    g.xs, g.w, g.grad_params, g.grad_emb, g.grad_gate = xs.data_ptr(), w.data_ptr(), grad_params.data_ptr(), grad_emb.data_ptr(), _ptr(grad_gate)
+    g.xs, g.w, g.grad_params, g.grad_emb, g.grad_gate = _ptr(None if wide else xs), w.data_ptr(), grad_params.data_ptr(), grad_emb.data_ptr(), _ptr(grad_gate)
     g.chunk_rows = chunk_rows
     with torch.cuda.device(device):
         need = lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g))
         if need == 0:
             raise _cabi.SdesError("lv gradient: " + lib.sdes_last_error().decode())
-        wsbuf = (workspace or Workspace()).get(need, device)
+        if wide:
+            wsbuf = workspace.buf  # must be the buffer the keep-mode forward wrote (never re-allocated here)
+            if wsbuf.numel() < need or wsbuf.device != device:
+                raise _cabi.SdesError("the workspace does not hold a keep-mode wide rollout of this configuration")
+        else:
+            wsbuf = (workspace or Workspace()).get(need, device)
         d.workspace, d.workspace_bytes = wsbuf.data_ptr(), wsbuf.numel()
         stream = torch.cuda.current_stream(device).cuda_stream
         _cabi.check(lib.sdes_rollout_lv_grad(C.byref(d), C.byref(g), C.c_void_p(stream)), "sdes_rollout_lv_grad")

@@ -177,7 +177,8 @@ class FusedOCLoss:
                                 compute_ito=True, return_traj=True)
             seed, off = self._next_seed(), self._rank_offset(x.shape[0])
             x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
-                                          workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer)
+                                          workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer,
+                                          keep_for_grad=True)
             self._traj_version += 1
             st = self._stats(rnd, x_T)
             loss, metrics = self._loss_from_stats(st)
