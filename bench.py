@@ -333,6 +333,7 @@ def main_cfg5(args):
         torch.cuda.synchronize(device)
 
     steps = min(args.steps, 5)
+    torch.set_grad_enabled(False)  # the metric is the forward rollout; with grad the loss keeps per-step state images
     for _ in range(2):
         loss(ts, x0, o["terminal"], o["second"])
     barrier()

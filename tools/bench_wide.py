@@ -63,30 +63,48 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="truncate the T=257 grid (profiling)")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--engine", default="tcgen05")
+    ap.add_argument("--train", action="store_true", help="also time loss(...) with grad + loss.backward()")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     o = build(dev, args.dim, args.mid, args.hidden, args.engine, steps=args.steps)
     T = o["ts"].shape[0] - 1
     x0 = o["prior"].sample((args.batch,))
     lib = _cabi.lib()
-    val, _ = o["loss"](o["ts"], x0, o["terminal"], o["second"])  # warm-up
+    with torch.no_grad():
+        val, _ = o["loss"](o["ts"], x0, o["terminal"], o["second"])  # warm-up
     torch.cuda.synchronize()
     n0 = lib.sdes_launch_count()
     ms = []
     for _ in range(args.reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        val, _ = o["loss"](o["ts"], x0, o["terminal"], o["second"])
+        with torch.no_grad():
+            val, _ = o["loss"](o["ts"], x0, o["terminal"], o["second"])
         b.record()
         torch.cuda.synchronize()
         ms.append(a.elapsed_time(b))
     launches = (lib.sdes_launch_count() - n0) // args.reps
+    train_ms = None
+    if args.train:
+        from sde_sampler_b200.spec import ctrl_parameters
+        tm = []
+        for _ in range(3):
+            for p_ in ctrl_parameters(o["loss"].generative_ctrl):
+                p_.grad = None
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            v, _ = o["loss"](o["ts"], x0, o["terminal"], o["second"])
+            v.backward()
+            b.record()
+            torch.cuda.synchronize()
+            tm.append(a.elapsed_time(b))
+        train_ms = sorted(tm)[1]
     t = statistics.median(ms) * 1e-3
     f = flops_per_traj_step(args.dim, args.mid, args.hidden)
     print(json.dumps({"workload": f"NICE d={args.dim} mid={args.mid} hidden={args.hidden} DDS lv T={T} batch={args.batch}",
                       "engine": args.engine, "traj_steps_per_s": args.batch * T / t, "ms_per_rollout": t * 1e3,
                       "ms_per_time_step": t * 1e3 / T, "algorithmic_tflops": args.batch * T * f / t / 1e12,
-                      "flops_per_traj_step": f, "launches_per_rollout": int(launches), "loss": float(val)}))
+                      "flops_per_traj_step": f, "launches_per_rollout": int(launches), "loss": float(val), "train_step_ms": train_ms}))
 
 
 if __name__ == "__main__":
