@@ -27,8 +27,28 @@ import sys
 import tempfile
 import time
 
-# NCCL prints its version banner on stdout; the contract is ONE JSON line there
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# NCCL prints its version banner on stdout (C-level write at the first communicator); the contract is ONE JSON line
+# there, so file descriptor 1 points at stderr until the line is printed.
+_SAVED_STDOUT = None
+
+
+def _stdout_to_stderr():
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is None:
+        sys.stdout.flush()
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    global _SAVED_STDOUT
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1)
+        os.close(_SAVED_STDOUT)
+        _SAVED_STDOUT = None
+    print(json.dumps(line), flush=True)
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
@@ -167,7 +187,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -303,14 +323,14 @@ def main_cfg5(args):
             times.append(time.perf_counter() - t0)
         dt = sum(times[args.warmup:]) / max(1, len(times[args.warmup:]))
         value = sample * T / dt
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"NICE d={dim} mid={mid} hidden={hidden} solver=dds loss=lv T=257 batch={B}/GPU",
                                      "sample": f"{sample} trajectories x {T} of 257 time steps per step"},
                           "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                            "sample": f"oracle/torch_port.py on {sample} trajectories x {T} time steps"},
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         return
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -383,7 +403,7 @@ def main_cfg5(args):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                              "flops_per_traj_step": f, "peak_source": "MEASURED_PEAKS.json bf16 dense, sustained (a step is thousands of GEMM launches)"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -402,6 +422,7 @@ def main():
                     help="gmm50 = north-star headline (default, the driver's line); cfg5 = BASELINE configs[4] per-GPU shard "
                          "(NICE d=784 mid=1000, DDS+lv, T=257, 4096 trajectories per GPU) on the wide engine")
     args = ap.parse_args()
+    _stdout_to_stderr()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "cfg5":
         return main_cfg5(args)
@@ -577,7 +598,7 @@ def main():
             line["cpu_baseline"] = {"value": sample * T_STEPS / dt, "unit": UNIT, "cores": torch.get_num_threads(),
                                     "kind": "port",
                                     "sample": f"oracle/torch_port.py (reference op sequence, torch eager fp32) on {sample} of {B} trajectories x T={T_STEPS}, one pass, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

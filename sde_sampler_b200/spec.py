@@ -331,8 +331,8 @@ def extract_spec(loss_obj, loss_kind: str, ts: torch.Tensor, terminal_unnorm_log
         raise NotImplementedError("control's target_score and terminal_unnorm_log_prob refer to different targets")
     target = _target_params(term_obj, dim)
     target["clip_target"] = clip_target
-    if getattr(loss_obj, "filter_samples", None) is not None:
-        raise NotImplementedError("filter_samples (target.filter) is not implemented")
+    # filter_samples (target.filter, solver/oc.py:152) acts on x_T after the rollout: applied by the statistics kernel's
+    # sample mask in compute_loss (losses/oc.py:50-58), nothing for the descriptor to carry
 
     ld: dict[str, Any] = {"kind": loss_kind, "method": loss_obj.method, "train": bool(train),
                           "compute_ito": bool(compute_ito), "return_traj": bool(return_traj),

@@ -214,3 +214,21 @@ def test_full_size_properties_headline_config(golden, engine):
     whole = eng.rnd_stats(rnd, _cabi.MASK_MAX_RND, 1e8)
     halves = torch.stack([eng.rnd_stats(rnd[: B // 2], _cabi.MASK_MAX_RND, 1e8), eng.rnd_stats(rnd[B // 2:], _cabi.MASK_MAX_RND, 1e8)])
     np.testing.assert_allclose(merge_stats(halves).cpu().numpy()[:6], whole.cpu().numpy()[:6], rtol=1e-6)  # exp-sum uses fp32 expf
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_filter_samples_is_applied_like_the_reference(golden, engine):
+    """filter_samples (target.filter in the solver, solver/oc.py:152): mask = filter(x_T) & (rnd < max_rnd), the loss is
+    the variance of the kept rnd and n_filtered counts the dropped ones (losses/oc.py:50-92)."""
+    g = golden("dis_gmm50_lv")
+    spec, x0 = g["spec"], g["x0"]
+    T, (B, d) = g["ts"].shape[0] - 1, x0.shape
+    noise = torch.from_numpy(philox.normal_noise(NOISE_SEED, B, T, d)).to(_dev())
+    keep_fn = lambda x: x[:, 0] > 0.0  # noqa: E731
+    b = build_from_spec(spec, _dev(), engine=engine, filter_samples=keep_fn)
+    with torch.no_grad():
+        val, metrics = b["loss"](b["ts"], torch.from_numpy(x0).to(_dev()), b["terminal"], b["second"], noise=noise)
+    m = g["train"]["x_T"][:, 0] > 0.0
+    want, n_f = oracle_rollout.loss_from_rnd(g["train"]["rnd"], "lv", spec["loss"]["max_rnd"], 1, sample_mask=m)
+    assert abs(float(val) - want) <= 1e-3 * (1 + abs(want))
+    assert metrics["train/n_filtered_cumulative"] == n_f == int((~m).sum())
