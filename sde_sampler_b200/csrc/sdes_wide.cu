@@ -95,6 +95,12 @@ static bool make_plan(const SdesRolloutDesc& d, Plan& p) {
     const bool pairs_ok = !(d.flags & SDES_F_MLP_SIMT) && getenv("SDES_CTA_PAIRS") != nullptr;  // opt-in, see sdes_linear.cuh
     auto lin = [&](Lin& l, int N, int Kin, bool bias) {
         set_tiling(l, N, Kin, pairs_ok);
+        // fewer tiles than half the SMs (e.g. the N = d/2 = 392 layers of cfg 5's 4 096-row shard: 2 x 32): halve the
+        // column tile so the layer spreads over twice as many CTAs
+        while (!l.pair && (int64_t)l.n_tiles * p.m_tiles <= 74 && l.tile_n >= 128 && l.tile_n % 32 == 0) {
+            l.tile_n /= 2;
+            l.n_tiles *= 2;
+        }
         l.w_off = take(lin_image_bytes(l));
         l.b_off = bias ? take((int64_t)l.n_pad * 4) : -1;
     };
