@@ -198,7 +198,9 @@ int sdes_langevin_integrate(const SdesRolloutDesc* target_desc, const SdesIntegr
 /* Statistics of rnd that BaseOCLoss.filter/compute_loss/compute_results reduce to
  * (losses/oc.py:50-123).  out_stats (device, 8 doubles):
  *   [0] n_kept  [1] sum(rnd | kept)  [2] sum(rnd^2 | kept)  [3] max(-rnd | kept)
- *   [4] sum(exp(-rnd - [3]) | kept)  [5] n_total  [6],[7] reserved (0)
+ *   [4] sum(exp(-rnd - [3]) | kept)  [5] n_total
+ *   [6] unbiased variance of the kept rnd = the lv loss, [7] their mean = the kl loss — of THIS call's shard (a
+ *       multi-rank caller recomputes both from the combined [0..2])
  * keep-mask by mask_mode: 0 = isfinite(rnd), 1 = rnd < max_rnd (oc.py:50-58), 2 = keep all
  * (compute_results applies no mask, oc.py:94-123); `sample_mask` (B bytes, 0 = drop; may be
  * NULL) is the result of the caller's filter_samples(x_T) (oc.py:53-55), AND-ed in.

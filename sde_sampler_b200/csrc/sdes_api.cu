@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(1024) rnd_stats_kernel(const float* __restrict
             mx = (mx != mx || om != om) ? NAN : fmaxf(mx, om);
         }
         if (lane == 0) {
-            out[0] = n; out[1] = s1; out[2] = s2; out[3] = (double)mx; out[5] = (double)B; out[6] = 0.0; out[7] = 0.0;
+            out[0] = n; out[1] = s1; out[2] = s2; out[3] = (double)mx; out[5] = (double)B;
+            out[6] = (s2 - s1 * s1 / n) / (n - 1.0);  // unbiased variance of the kept rnd (lv loss of THIS shard)
+            out[7] = s1 / n;                          // their mean (kl loss)
             s_max = mx;
         }
     }

@@ -35,6 +35,9 @@ def merge_stats(gathered: torch.Tensor) -> torch.Tensor:
     scale = torch.where(has, torch.exp(mx - gmx), torch.zeros_like(mx))
     out[3] = gmx
     out[4] = (gathered[:, 4] * scale).sum()
+    n, s1, s2 = out[0], out[1], out[2]
+    out[6] = (s2 - s1 * s1 / n) / (n - 1.0)  # the derived slots of the combined statistics
+    out[7] = s1 / n
     return out
 
 

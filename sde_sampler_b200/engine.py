@@ -26,7 +26,11 @@ def _ptr(t: torch.Tensor | None) -> int | None:
 
 
 def pack_params(spec: RolloutSpec) -> torch.Tensor:
-    """Flat fp32 parameter blob in the order documented in include/sdes_b200.h."""
+    """Flat fp32 parameter blob in the order documented in include/sdes_b200.h (values re-read on every call; the list
+    of flat VIEWS of the live parameters is kept with the spec)."""
+    views = spec.extras.get("flat_views")
+    if views is not None:
+        return torch.cat(views)
     m = spec.mlp
     te = m["time_embed"]
     parts = [m["in_w"], m["in_b"], te["phase"]]
@@ -42,7 +46,10 @@ def pack_params(spec: RolloutSpec) -> torch.Tensor:
         for w, b in g["hidden"]:
             parts += [w, b]
         parts += [g["out_w"], g["out_b"]]
-    return torch.cat([p.reshape(-1).to(torch.float32) for p in parts])
+    flat = [p.reshape(-1).to(torch.float32) for p in parts]
+    if all(f.data_ptr() == p.data_ptr() for f, p in zip(flat, parts)):  # views, not copies: safe to reuse
+        spec.extras["flat_views"] = flat
+    return torch.cat(flat)
 
 
 def pack_nice_params(tg: dict) -> torch.Tensor:

@@ -27,7 +27,7 @@ import torch
 from . import _cabi, engine
 from .autograd import wants_grad
 from .dist import combine_stats
-from .spec import extract_spec
+from .spec import ctrl_parameters, extract_spec
 
 # utils/common.py:9-13
 Results = namedtuple(
@@ -88,6 +88,7 @@ class FusedOCLoss:
         self._grad_workspace = engine_workspace()
         self._traj_buffer = engine_workspace()  # trajectory of the last training forward (row-tiled), reused across steps
         self._traj_version = 0
+        self._spec_cache: dict = {}
         _cabi.lib()  # fail now, not at the first step, if the CUDA library is missing
 
     # ------------------------------------------------------------------ noise stream
@@ -111,10 +112,45 @@ class FusedOCLoss:
         return dist.get_rank(pg) * batch
 
     # ---------------------------------------------------------------------- rollout
+    def _spec(self, ts, terminal_unnorm_log_prob, second_log_prob, *, train, compute_ito, return_traj):
+        """`extract_spec` with its object introspection cached: the spec only holds REFERENCES to the caller's live
+        tensors (values are re-read by the kernels every call), so it stays valid as long as the same objects and the
+        same parameter tensors are handed in; the scalars a scheduler may change between calls (clip values, ts) are
+        refreshed here on every call."""
+        ctrl = self.generative_ctrl
+        live = ctrl_parameters(ctrl)
+        key = (train, compute_ito, return_traj, int(ts.shape[0]), id(ctrl), id(self.sde),
+               id(getattr(terminal_unnorm_log_prob, "__self__", terminal_unnorm_log_prob)),
+               id(getattr(second_log_prob, "__self__", second_log_prob)), self.method, self.traj_per_sample)
+        # storage fingerprint: parameters / distribution buffers that were re-allocated (Module.to, p.data = ...) miss
+        fp = tuple(p.data_ptr() for p in live) + _buffer_ptrs(getattr(terminal_unnorm_log_prob, "__self__", None)) + \
+            _buffer_ptrs(getattr(second_log_prob, "__self__", None)) + _buffer_ptrs(self.sde)
+        hit = self._spec_cache.get(key)
+        if hit is not None and hit[1] == fp:
+            spec = hit[0]
+            spec.ts = ts.detach().reshape(-1).to(torch.float32)
+            spec.ctrl["clip_model"] = ctrl.clip_model
+            if spec.ctrl["kind"] != "clipped":
+                spec.ctrl["scale_score"] = float(ctrl.scale_score)
+                spec.ctrl["clip_score"] = ctrl.clip_score
+            owner = getattr(terminal_unnorm_log_prob, "__self__", None)
+            if hasattr(owner, "clip_target"):
+                spec.target["clip_target"] = owner.clip_target
+            spec.loss["max_rnd"] = self.max_rnd
+            if self.loss_kind == "exp_integrator":
+                spec.loss["alpha"], spec.loss["sigma"] = float(self.alpha), float(self.sigma)
+            return spec
+        spec = extract_spec(self, self.loss_kind, ts, terminal_unnorm_log_prob, second_log_prob,
+                            train=train, compute_ito=compute_ito, return_traj=return_traj)
+        if len(self._spec_cache) > 16:
+            self._spec_cache.clear()
+        self._spec_cache[key] = (spec, fp)
+        return spec
+
     def _simulate(self, ts, x, terminal_unnorm_log_prob, second_log_prob, *, train, compute_ito_int,
                   return_traj, noise=None):
-        spec = extract_spec(self, self.loss_kind, ts, terminal_unnorm_log_prob, second_log_prob,
-                            train=train, compute_ito=compute_ito_int, return_traj=return_traj)
+        spec = self._spec(ts, terminal_unnorm_log_prob, second_log_prob, train=train, compute_ito=compute_ito_int,
+                          return_traj=return_traj)
         x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=self._next_seed(),
                                       traj_offset=self._rank_offset(x.shape[0]), engine=self.engine,
                                       workspace=self._workspace)
@@ -146,18 +182,15 @@ class FusedOCLoss:
         return self._loss_from_stats(self._stats(rnd, samples))
 
     def _loss_from_stats(self, st) -> tuple[torch.Tensor, dict]:
-        n, s1, s2 = st[0], st[1], st[2]
+        # st[6] / st[7]: lv / kl loss of the kept entries, computed by the statistics kernel (or by merge_stats)
         if self.sync_metrics:
-            self.n_filtered += int((st[5] - n).item())  # the reference syncs here too (.item(), oc.py:86)
+            self.n_filtered += int((st[5] - st[0]).item())  # the reference syncs here too (.item(), oc.py:86)
             count = self.n_filtered
         else:
-            dropped = st[5] - n
+            dropped = st[5] - st[0]
             self._n_filtered_dev = dropped if self._n_filtered_dev is None else self._n_filtered_dev + dropped
             count = self._n_filtered_dev + self._n_filtered
-        if self.method == "lv":
-            loss = (s2 - s1 * s1 / n) / (n - 1.0)
-        else:
-            loss = s1 / n
+        loss = st[6] if self.method == "lv" else st[7]
         return loss.to(torch.float32), {"train/n_filtered_cumulative": count}
 
     def _call_with_grad(self, ts, x, terminal_unnorm_log_prob, second_log_prob, noise=None):
@@ -165,7 +198,6 @@ class FusedOCLoss:
         `sdes_rollout_lv_grad` (sde_sampler_b200/autograd.py).  Log-variance loss only: the kl losses need
         backpropagation through time and return a value without grad_fn."""
         from .autograd import LvLoss
-        from .spec import ctrl_parameters
 
         params = ctrl_parameters(self.generative_ctrl)
         net = self.generative_ctrl.base_model
@@ -173,8 +205,7 @@ class FusedOCLoss:
         out = {}
 
         def run():
-            spec = extract_spec(self, self.loss_kind, ts, terminal_unnorm_log_prob, second_log_prob, train=True,
-                                compute_ito=True, return_traj=True)
+            spec = self._spec(ts, terminal_unnorm_log_prob, second_log_prob, train=True, compute_ito=True, return_traj=True)
             seed, off = self._next_seed(), self._rank_offset(x.shape[0])
             x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
                                           workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer,
@@ -241,6 +272,17 @@ class FusedOCLoss:
         if self.traj_per_sample != 1:
             x = x.repeat(self.traj_per_sample, 1, 1).reshape(-1, x.shape[-1])
         return x
+
+
+def _buffer_ptrs(obj) -> tuple:
+    """data pointers of the tensors an introspected owner (solver shim -> target, prior, reference, sde) holds"""
+    if obj is None:
+        return ()
+    out = []
+    for o in (obj, getattr(obj, "target", None), getattr(obj, "prior", None)):
+        if isinstance(o, torch.nn.Module):
+            out += [t.data_ptr() for t in o.buffers()]
+    return tuple(out)
 
 
 def engine_workspace():
