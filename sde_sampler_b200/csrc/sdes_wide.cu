@@ -158,34 +158,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepArgs a) {
     if ((int)blockIdx.x < T) {
         __shared__ float buf_a[2 * C], buf_b[2 * C], buf_out[C];
         const int i = blockIdx.x;
-        const float s = d.ts[i], t = d.ts[i + 1];
-        const float dt = __fsub_rn(t, s);
-        if (tid == 0) {  // identical to the fused engines' table (sdes_prepare.cu)
-            float mu = 0.f, sigma = 0.f, div_int = 0.f, lerp_w = 0.f;
-            if (d.sde_kind == SDES_SDE_VP) {
-                const float ws_ = __fdiv_rn(s, d.terminal_t), wt_ = __fdiv_rn(t, d.terminal_t);
-                const float b0 = d.sde_sign > 0.f ? d.beta_max : d.beta_min;
-                const float b1 = d.sde_sign > 0.f ? d.beta_min : d.beta_max;
-                const float beta_s = torch_lerp(b0, b1, ws_), beta_t = torch_lerp(b0, b1, wt_);
-                mu = d.sde_sign * 0.5f * beta_s;
-                sigma = d.scale_diff * sqrtf(beta_s);
-                div_int = d.sde_sign * 0.25f * (beta_t + beta_s) * dt * (float)dim;
-                lerp_w = ws_;
-            } else if (d.sde_kind == SDES_SDE_CONST_OU) {
-                mu = d.sde_sign * d.drift_coeff;
-                sigma = d.diff_coeff;
-                div_int = d.sde_sign * d.drift_coeff * dt * (float)dim;
-                lerp_w = __fdiv_rn(s, d.terminal_t);
-            }
-            float beta_k = 0.f, alpha_k = 0.f;
-            if (d.loss_kind == SDES_LOSS_EXP_INTEGRATOR) {
-                beta_k = fminf(fmaxf(d.alpha * sqrtf(dt), 0.f), 1.f);
-                alpha_k = sqrtf(1.0f - beta_k * beta_k);
-            }
-            float* row = a.tab + (int64_t)i * TAB_STRIDE;
-            row[TAB_DT] = dt; row[TAB_SQRT_DT] = sqrtf(dt); row[TAB_MU] = mu; row[TAB_SIGMA] = sigma;
-            row[TAB_DIV_INT] = div_int; row[TAB_LERP_W] = lerp_w; row[TAB_BETA_K] = beta_k; row[TAB_ALPHA_K] = alpha_k;
-        }
+        const float s = d.ts[i];
+        if (tid == 0) write_step_table_row(d, i, a.tab + (int64_t)i * TAB_STRIDE);
         time_embed_row(blob, a.bl.te_phase, a.bl.te_h_w, a.bl.te_h_b, d.te_hidden, a.bl.te_out_w, a.bl.te_out_b, C, s,
                        buf_a, buf_b, buf_out);
         if (tid < C) a.emb[(int64_t)i * C + tid] = buf_out[tid] + blob[a.bl.in_b + tid];

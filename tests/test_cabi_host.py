@@ -143,3 +143,38 @@ def test_introspection_roundtrip(lib, golden, name):
             assert a == c, (path, a, c)
 
     cmp(spec, got)
+
+
+def test_aux_desc_layouts_match_c(tmp_path):
+    """SdesLvGradDesc / SdesIntegrateDesc: sizeof and offsets of the C structs equal the ctypes mirrors."""
+    for cname, cls in (("SdesLvGradDesc", _cabi.LvGradDesc), ("SdesIntegrateDesc", _cabi.IntegrateDesc)):
+        fields = [f[0] for f in cls._fields_]
+        body = "\n".join(f'printf("{f} %zu\\n", offsetof({cname}, {f}));' for f in fields)
+        src = tmp_path / f"probe_{cname}.c"
+        src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sdes_b200.h"\nint main(){'
+                       f'printf("sizeof %zu\\n", sizeof({cname}));' + body + "return 0;}")
+        exe = tmp_path / f"probe_{cname}"
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+        out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+        assert int(out["sizeof"]) == C.sizeof(cls), cname
+        for f in fields:
+            assert int(out[f]) == getattr(cls, f).offset, (cname, f)
+
+
+def test_gradient_and_integrator_entry_points_validate_without_gpu(lib):
+    d = _valid_desc()
+    g = _cabi.LvGradDesc()
+    g.struct_bytes = C.sizeof(_cabi.LvGradDesc)
+    assert lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g)) > lib.sdes_workspace_bytes(C.byref(d))
+    assert lib.sdes_rollout_lv_grad(C.byref(d), C.byref(g), None) == -5 and b"NULL" in lib.sdes_last_error()
+    g.struct_bytes -= 4
+    assert lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g)) == 0
+    t = _cabi.new_desc()   # the integrator reads only the target part of the descriptor
+    t.target_kind, t.dim, t.batch, t.variance = _cabi.TARGET_FUNNEL, 10, 64, 9.0
+    assert lib.sdes_integrate_workspace_bytes(C.byref(t)) > 0, lib.sdes_last_error()
+    ig = _cabi.IntegrateDesc()
+    ig.struct_bytes = C.sizeof(_cabi.IntegrateDesc)
+    ig.n_steps, ig.n_out = 10, 3
+    assert lib.sdes_langevin_integrate(C.byref(t), C.byref(ig), None) == -5
+    t.dim = 100
+    assert lib.sdes_integrate_workspace_bytes(C.byref(t)) == 0 and b"Langevin" in lib.sdes_last_error()
