@@ -156,10 +156,13 @@ int sdes_tcgen05_supported(const SdesRolloutDesc* desc);
  * — one backward pass of the control MLP over all B*T rows of the stored trajectory, no backpropagation through
  * time.  `desc` is the descriptor of the forward call (same seed / traj_offset / noise so that eps is re-drawn
  * identically; x0/x_T/rnd/xs of desc are ignored; desc->workspace must hold sdes_lv_grad_workspace_bytes).
- * d <= SDES_MAX_DIM, analytic targets.  Outputs (overwritten):
- *   grad_params (n_params floats, the layout of `params`): in_w, h_w/h_b, out_w/out_b; every other entry 0
- *   grad_emb    (T, 64)        d loss / d (timestep_embed(s_i) + in_b)   -> in_b gradient = column sums; the caller
- *   grad_gate   (T, gate_dim)  d loss / d gate(s_i)                         chains both through the TimeEmbed nets */
+ * Fused engines: `xs` is the stored trajectory; wide engine (d > SDES_MAX_DIM or NICE): the forward ran with
+ * SDES_F_KEEP_FOR_GRAD and desc->workspace is that same workspace.  Outputs (overwritten):
+ *   grad_params (n_params floats, the layout of `params`): the gradient of EVERY control parameter — the x-dependent
+ *               layers (in_w, h_w/h_b, out_w/out_b) from the B*T-row passes, in_b and the two TimeEmbed networks
+ *               (timestep embedding, gate) from the per-step cotangents below
+ *   grad_emb    (T, 64)        d loss / d (timestep_embed(s_i) + in_b)        (intermediate, also returned)
+ *   grad_gate   (T, gate_dim)  d loss / d gate(s_i)                           (intermediate, also returned) */
 typedef struct SdesLvGradDesc {
     uint32_t struct_bytes;   /* = sizeof(SdesLvGradDesc), checked */
     uint32_t reserved;

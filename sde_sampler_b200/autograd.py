@@ -1,29 +1,16 @@
 """`loss.backward()` for the log-variance losses (reference: `Trainable.step`, solver/base.py:404-407).
 
-The forward is the fused rollout (with the trajectory kept), the backward is `sdes_rollout_lv_grad`: one pass of
-the control MLP's backward over all (trajectory, step) rows on the tensor cores — see csrc/sdes_grad.cu for why
-no backpropagation through time is needed (losses/oc.py:60-64: the state is driven by the detached control).
-
-What stays in PyTorch is plumbing on T rows: the CUDA call returns d loss / d emb (T, 64) and d loss / d gate
-(T, gate_dim) for the two x-independent TimeEmbed networks (models/mlp.py:43-82); their few thousand parameters
-receive their gradient by chaining those cotangents through `_time_embed` below (T = 100 rows, autograd)."""
+The forward is the fused rollout (with the trajectory kept), the backward is ONE C-ABI call, `sdes_rollout_lv_grad`:
+a pass of the control MLP's backward over all (trajectory, step) rows on the tensor cores plus the backward of the two
+x-independent TimeEmbed networks (csrc/sdes_grad.cu explains why no backpropagation through time is needed —
+losses/oc.py:60-64: the state is driven by the detached control).  It returns the gradient of every control parameter
+in the layout of the parameter blob; this module only slices that blob back onto the caller's `nn.Parameter`s."""
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import _cabi, engine
 from .spec import ctrl_parameters
-
-
-def _time_embed(t, phase, hidden, out_w, out_b):
-    """TimeEmbed.forward (models/mlp.py:71-82) on the (T, 1) grid — used only to chain cotangents to its parameters."""
-    coeff = torch.linspace(0.1, 100, _cabi.CHANNELS, device=t.device).unsqueeze(0)
-    arg = coeff * t + phase.reshape(1, -1)
-    h = torch.cat([arg.sin(), arg.cos()], dim=1)
-    for w, b in hidden:
-        h = F.gelu(F.linear(h, w, b))
-    return F.linear(h, out_w, out_b)
 
 
 class LvLoss(torch.autograd.Function):
@@ -54,30 +41,10 @@ class LvLoss(torch.autograd.Function):
         g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w.float(), noise=m["noise"], seed=m["seed"],
                                                traj_offset=m["traj_offset"], engine=lo.engine,
                                                workspace=lo._workspace if wide else lo._grad_workspace, params=blob)
-        n_te, n_h, n_g = ctx.counts
         grads, o = [], 0
-        for p in params:
+        for p in params:  # blob order (include/sdes_b200.h) == ctrl_parameters order
             grads.append(g_blob[o:o + p.numel()].reshape(p.shape))
             o += p.numel()
-        # blob order (include/sdes_b200.h): in_w, in_b, te_phase, te hidden (w,b)*, te out (w,b), hidden (w,b)*, out (w,b), gate...
-        grads[1] = g_emb.sum(dim=0)  # in_b enters through emb = timestep_embed(s) + in_b
-        ts = m["spec"].ts.to(g_emb.device).float()[:-1].reshape(-1, 1)
-        te_idx = list(range(2, 2 + 1 + 2 * n_te + 2))
-        with torch.enable_grad():
-            te_p = [params[i] for i in te_idx]
-            emb = _time_embed(ts, te_p[0], [(te_p[1 + 2 * k], te_p[2 + 2 * k]) for k in range(n_te)], te_p[-2], te_p[-1])
-            te_g = torch.autograd.grad(emb, te_p, grad_outputs=g_emb, allow_unused=True)
-        for i, g in zip(te_idx, te_g):
-            grads[i] = g if g is not None else torch.zeros_like(params[i])
-        if g_gate is not None:
-            g0 = 2 + 1 + 2 * n_te + 2 + 2 * n_h + 2
-            g_idx = list(range(g0, g0 + 1 + 2 * n_g + 2))
-            with torch.enable_grad():
-                gp = [params[i] for i in g_idx]
-                gate = _time_embed(ts, gp[0], [(gp[1 + 2 * k], gp[2 + 2 * k]) for k in range(n_g)], gp[-2], gp[-1])
-                gg = torch.autograd.grad(gate, gp, grad_outputs=g_gate, allow_unused=True)
-            for i, g in zip(g_idx, gg):
-                grads[i] = g if g is not None else torch.zeros_like(params[i])
         if lo.process_group is not None:  # every rank holds the gradient of the global loss w.r.t. its shard's rows
             import torch.distributed as dist
 

@@ -20,6 +20,7 @@
 
 #include "sdes_linear.cuh"
 #include "sdes_step.cuh"
+#include "sdes_timeembed.cuh"
 
 namespace sdes {
 namespace grad {
@@ -475,6 +476,120 @@ __global__ void __launch_bounds__(256) qgate_reduce_kernel(const float* __restri
     }
 }
 
+// ---- the two x-independent TimeEmbed networks (models/mlp.py:43-82): parameter gradients from the per-step
+// cotangents d loss / d emb (T, 64) and d loss / d gate (T, gate_dim).  One block per time step re-evaluates the tiny
+// network for its s_i keeping the pre-activations in shared memory, walks it backwards and adds into the gradient
+// blob (T rows x ~17 k parameters of atomics: negligible next to the B*T-row passes above).
+struct TeGradArgs {
+    const float* blob;       // parameters
+    float* grad;             // gradient blob (same layout)
+    const float* ts;         // (T+1)
+    const float* cot;        // (T, n_out) cotangent of the network output
+    int64_t o_phase, o_hw[SDES_MAX_HIDDEN], o_hb[SDES_MAX_HIDDEN], o_ow, o_ob;
+    int n_hidden, n_out;
+    int64_t o_extra_bias;    // >= 0: also add the cotangent row to this bias (FourierMLP.input_embed.bias), n_out = C
+};
+
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+
+__global__ void __launch_bounds__(256) time_embed_grad_kernel(const TeGradArgs a) {
+    __shared__ float feat[2 * C], arg_s[C], pre[SDES_MAX_HIDDEN][C], act[SDES_MAX_HIDDEN][C], delta[2 * C], delta2[2 * C];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float s = a.ts[i];
+    const float* blob = a.blob;
+    if (tid < C) {
+        const float arg = __fadd_rn(__fmul_rn(linspace_coeff(tid), s), blob[a.o_phase + tid]);
+        arg_s[tid] = arg;
+        feat[tid] = sinf(arg);
+        feat[C + tid] = cosf(arg);
+    }
+    __syncthreads();
+    // forward, keeping pre-activations
+    for (int l = 0; l < a.n_hidden; ++l) {
+        const int k_in = l == 0 ? 2 * C : C;
+        const float* in = l == 0 ? feat : act[l - 1];
+        if (tid < C) {
+            const float* w = blob + a.o_hw[l] + (int64_t)tid * k_in;
+            float acc = blob[a.o_hb[l] + tid];
+            for (int k = 0; k < k_in; ++k) acc = fmaf(w[k], in[k], acc);
+            pre[l][tid] = acc;
+            act[l][tid] = gelu_erf(acc);
+        }
+        __syncthreads();
+    }
+    const float* h_last = act[a.n_hidden - 1];
+    const float* cot = a.cot + (int64_t)i * a.n_out;
+    // output layer: dW[n][k] += cot[n] h[k], db[n] += cot[n], delta[k] = sum_n cot[n] W[n][k]
+    for (int e = tid; e < a.n_out * C; e += blockDim.x) {
+        const int n = e / C, k = e % C;
+        const float g = cot[n] * h_last[k];
+        if (g != 0.f) atomicAdd(a.grad + a.o_ow + e, g);
+    }
+    for (int n = tid; n < a.n_out; n += blockDim.x) {
+        if (cot[n] != 0.f) {
+            atomicAdd(a.grad + a.o_ob + n, cot[n]);
+            if (a.o_extra_bias >= 0) atomicAdd(a.grad + a.o_extra_bias + n, cot[n]);
+        }
+    }
+    if (tid < C) {
+        float acc = 0.f;
+        for (int n = 0; n < a.n_out; ++n) acc = fmaf(cot[n], blob[a.o_ow + (int64_t)n * C + tid], acc);
+        delta[tid] = acc;
+    }
+    __syncthreads();
+    // hidden layers, last to first
+    for (int l = a.n_hidden - 1; l >= 0; --l) {
+        const int k_in = l == 0 ? 2 * C : C;
+        const float* in = l == 0 ? feat : act[l - 1];
+        if (tid < C) delta[tid] *= gelu_erf_grad(pre[l][tid]);
+        __syncthreads();
+        for (int e = tid; e < C * k_in; e += blockDim.x) {
+            const int n = e / k_in, k = e % k_in;
+            const float g = delta[n] * in[k];
+            if (g != 0.f) atomicAdd(a.grad + a.o_hw[l] + e, g);
+        }
+        if (tid < C && delta[tid] != 0.f) atomicAdd(a.grad + a.o_hb[l] + tid, delta[tid]);
+        if (tid < k_in) {
+            float acc = 0.f;
+            for (int n = 0; n < C; ++n) acc = fmaf(delta[n], blob[a.o_hw[l] + (int64_t)n * k_in + tid], acc);
+            delta2[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < k_in) delta[tid] = delta2[tid];
+        __syncthreads();
+    }
+    // features: [sin(arg), cos(arg)], arg = coeff * t + phase
+    if (tid < C) {
+        const float g = delta[tid] * cosf(arg_s[tid]) - delta[C + tid] * sinf(arg_s[tid]);
+        if (g != 0.f) atomicAdd(a.grad + a.o_phase + tid, g);
+    }
+}
+
+static cudaError_t launch_time_embed_grads(const KParams& kp, const SdesLvGradDesc& g, cudaStream_t stream, int64_t& launches) {
+    const SdesRolloutDesc& d = kp.d;
+    TeGradArgs a;
+    a.blob = d.params; a.grad = g.grad_params; a.ts = d.ts;
+    a.cot = g.grad_emb; a.o_phase = kp.bl.te_phase; a.o_ow = kp.bl.te_out_w; a.o_ob = kp.bl.te_out_b;
+    for (int l = 0; l < SDES_MAX_HIDDEN; ++l) { a.o_hw[l] = kp.bl.te_h_w[l]; a.o_hb[l] = kp.bl.te_h_b[l]; }
+    a.n_hidden = d.te_hidden; a.n_out = C; a.o_extra_bias = kp.bl.in_b;
+    time_embed_grad_kernel<<<d.n_steps, 256, 0, stream>>>(a);
+    ++launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if ((d.flags & SDES_F_HAS_GATE) && g.grad_gate != nullptr && d.ctrl_kind != SDES_CTRL_CLIPPED) {
+        a.cot = g.grad_gate; a.o_phase = kp.bl.g_phase; a.o_ow = kp.bl.g_out_w; a.o_ob = kp.bl.g_out_b;
+        for (int l = 0; l < SDES_MAX_HIDDEN; ++l) { a.o_hw[l] = kp.bl.g_h_w[l]; a.o_hb[l] = kp.bl.g_h_b[l]; }
+        a.n_hidden = d.gate_hidden; a.n_out = d.gate_dim; a.o_extra_bias = -1;
+        time_embed_grad_kernel<<<d.n_steps, 256, 0, stream>>>(a);
+        ++launches;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
 template <int DPAD>
 static cudaError_t launch_cot_t(const CotArgs& a, int m_tiles, cudaStream_t stream) {
     const int K2 = (a.kp.d.n_components + 1) & ~1;
@@ -665,6 +780,7 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
             GRADW_CHECK(cudaMemsetAsync(g.grad_gate, 0, (size_t)v.T * 4, stream));
         }
     }
+    GRADW_CHECK(launch_time_embed_grads(kp, g, stream, launches));
 #undef GRADW_CHECK
     return launches;
 }
@@ -822,6 +938,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim));
         GRAD_CHECK(colsum(ws + p.dh_img[cur], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, tiles_per_step, C));
     }
+    GRAD_CHECK(launch_time_embed_grads(kp, g, stream, launches));
 #undef GRAD_CHECK
     return launches;
 }
