@@ -215,6 +215,12 @@ int sdes_rnd_stats(const float* rnd, int64_t batch, int mask_mode, float max_rnd
 /* Importance weights exp(-rnd - max(-rnd)) (losses/oc.py:104-105); the shift is stats[3], read on device. */
 int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* weights, void* stream);
 
+/* Cotangent of the log-variance loss with respect to rnd: w[b] = upstream * 2 (rnd_b - mean) / (n - 1) for kept b (the
+ * mask of sdes_rnd_stats), 0 otherwise; `stats` are the (rank-combined) statistics, `upstream` a device scalar
+ * (d objective / d loss, e.g. scale_loss; NULL = 1).  Input `w` of sdes_rollout_lv_grad. */
+int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,
+                    const double* stats, const float* upstream, float* w, void* stream);
+
 /* The noise stream on its own: eps (T,B,d) exactly as the fused kernel draws it in registers
  * (Philox4x32-10 keyed by seed, counter (traj_offset+b, step, dim/4) + Box-Muller).  Test hook. */
 int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32_t n_steps,

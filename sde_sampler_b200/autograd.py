@@ -32,13 +32,11 @@ class LvLoss(torch.autograd.Function):
         if m["traj_version"] != lo._traj_version:
             raise RuntimeError("the trajectory of this loss value was overwritten by a later training call of the same "
                                "loss object; call backward() before the next forward (as Trainable.step does)")
-        st = m["stats"]
-        n, mean = st[0], st[1] / st[0]
-        rnd = m["rnd"].reshape(-1).double()
-        w = torch.where(m["keep"].reshape(-1), 2.0 * (rnd - mean) / (n - 1.0), torch.zeros_like(rnd)) * grad_out.double()
+        mode = _cabi.MASK_ISFINITE if lo.max_rnd is None else _cabi.MASK_MAX_RND
+        w = engine.lv_weights(m["rnd"], m["stats"], mode, 0.0 if lo.max_rnd is None else lo.max_rnd, m["smask"], grad_out)
         blob = torch.cat([p.detach().reshape(-1).float() for p in params])
         wide = engine.is_wide(m["spec"])  # wide engine: the forward kept what is needed inside its own workspace
-        g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w.float(), noise=m["noise"], seed=m["seed"],
+        g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w, noise=m["noise"], seed=m["seed"],
                                                traj_offset=m["traj_offset"], engine=lo.engine,
                                                workspace=lo._workspace if wide else lo._grad_workspace, params=blob)
         grads, o = [], 0

@@ -233,6 +233,19 @@ __global__ void weights_kernel(const float* __restrict__ rnd, int64_t B, const d
         w[i] = expf(-rnd[i] - mx);  // losses/oc.py:104-105
 }
 
+// d (lv loss) / d rnd_b = 2 (rnd_b - mean) / (n - 1) for kept b, 0 otherwise, times the upstream scalar
+__global__ void lv_weights_kernel(const float* __restrict__ rnd, int64_t B, int mode, float max_rnd, const uint8_t* __restrict__ smask,
+                                  const double* __restrict__ stats, const float* __restrict__ upstream, float* __restrict__ w) {
+    const double n = stats[0], mean = stats[1] / stats[0];
+    const double up = upstream != nullptr ? (double)upstream[0] : 1.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const float r = rnd[i];
+        bool keep = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
+        if (smask != nullptr) keep = keep && smask[i] != 0;
+        w[i] = keep ? (float)(2.0 * ((double)r - mean) / (n - 1.0) * up) : 0.f;
+    }
+}
+
 __global__ void philox_normal_kernel(uint64_t seed, uint64_t traj_offset, int64_t B, int T, int dim, float* __restrict__ out) {
     const int nchunk = (dim + 3) / 4;
     const int64_t total = (int64_t)T * B * nchunk;
@@ -536,6 +549,20 @@ int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* we
     weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, stats, weights);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask, const double* stats,
+                    const float* upstream, float* w, void* stream_) {
+    g_err[0] = 0;
+    if (!rnd || !stats || !w) return fail(-5, "rnd/stats/w NULL");
+    if (mask_mode < 0 || mask_mode > 2) return fail(-3, "mask_mode must be 0, 1 or 2");
+    if (batch == 0) return 0;
+    const int blocks = (int)((batch + 255) / 256 < 1184 ? (batch + 255) / 256 : 1184);
+    lv_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, stats, upstream, w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "lv weights launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

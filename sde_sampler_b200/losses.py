@@ -213,10 +213,8 @@ class FusedOCLoss:
             self._traj_version += 1
             st = self._stats(rnd, x_T)
             loss, metrics = self._loss_from_stats(st)
-            keep = rnd.isfinite() if self.max_rnd is None else rnd < self.max_rnd
-            if self.filter_samples is not None:
-                keep = keep & self.filter_samples(x_T).reshape(keep.shape)
-            out.update(loss=loss, metrics=metrics, stats=st, rnd=rnd, keep=keep, xs=xs, spec=spec, seed=seed,
+            smask = None if self.filter_samples is None else self.filter_samples(x_T)
+            out.update(loss=loss, metrics=metrics, stats=st, rnd=rnd, smask=smask, xs=xs, spec=spec, seed=seed,
                        traj_offset=off, noise=noise, samples=x_T, traj_version=self._traj_version)
             return out
 
