@@ -215,6 +215,13 @@ int sdes_rnd_stats(const float* rnd, int64_t batch, int mask_mode, float max_rnd
 /* Importance weights exp(-rnd - max(-rnd)) (losses/oc.py:104-105); the shift is stats[3], read on device. */
 int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* weights, void* stream);
 
+/* lv_traj (losses/oc.py:78-84): rnd holds traj_per_sample trajectories for each of n_samples initial points, laid out
+ * (traj_per_sample, n_samples) as `x.repeat(traj_per_sample, 1, 1)` produces (:240-241).  A sample is kept when every one
+ * of its trajectories passes the mask; out3 (device, 3 doubles) = [sum over kept samples of the unbiased variance across
+ * their trajectories, kept samples, all samples].  loss = [0] / [1]; ranks add the three numbers. */
+int sdes_lv_traj_stats(const float* rnd, int64_t n_samples, int32_t traj_per_sample, int mask_mode, float max_rnd,
+                       const uint8_t* sample_mask, double* out3, void* stream);
+
 /* Cotangent of the log-variance loss with respect to rnd: w[b] = upstream * 2 (rnd_b - mean) / (n - 1) for kept b (the
  * mask of sdes_rnd_stats), 0 otherwise; `stats` are the (rank-combined) statistics, `upstream` a device scalar
  * (d objective / d loss, e.g. scale_loss; NULL = 1).  Input `w` of sdes_rollout_lv_grad. */

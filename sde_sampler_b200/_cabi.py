@@ -95,6 +95,7 @@ SYMBOLS = {
     "sdes_tcgen05_supported": (C.c_int, [C.POINTER(RolloutDesc)]),
     "sdes_rnd_stats": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, C.c_void_p]),
     "sdes_weights": (C.c_int, [_fp, C.c_int64, _fp, _fp, C.c_void_p]),
+    "sdes_lv_traj_stats": (C.c_int, [_fp, C.c_int64, C.c_int32, C.c_int, C.c_float, _fp, _fp, C.c_void_p]),
     "sdes_lv_weights": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
     "sdes_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, _fp, C.c_void_p]),
     "sdes_tcgen05_selftest": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

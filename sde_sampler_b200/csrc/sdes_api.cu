@@ -246,6 +246,45 @@ __global__ void lv_weights_kernel(const float* __restrict__ rnd, int64_t B, int 
     }
 }
 
+// lv_traj (losses/oc.py:78-84): rnd is (tps, B0) — tps trajectories per initial sample; a sample is kept when all its
+// copies pass the mask; the loss is the mean over kept samples of the unbiased variance across the copies.
+// out: [0] sum of per-sample variances (kept), [1] kept samples, [2] all samples.
+__global__ void __launch_bounds__(256) lv_traj_stats_kernel(const float* __restrict__ rnd, int64_t B0, int tps, int mode, float max_rnd,
+                                                            const uint8_t* __restrict__ smask, double* __restrict__ out) {
+    __shared__ double s_v[8], s_n[8];
+    double vsum = 0.0, nk = 0.0;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B0; b += (int64_t)gridDim.x * blockDim.x) {
+        bool keep = true;
+        double s1 = 0.0, s2 = 0.0;
+        for (int t = 0; t < tps; ++t) {
+            const int64_t i = (int64_t)t * B0 + b;
+            const float r = rnd[i];
+            bool k = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
+            if (smask != nullptr) k = k && smask[i] != 0;
+            keep = keep && k;
+            s1 += (double)r;
+            s2 += (double)r * (double)r;
+        }
+        if (keep) {
+            vsum += (s2 - s1 * s1 / tps) / (tps - 1.0);
+            nk += 1.0;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        nk += __shfl_xor_sync(0xffffffffu, nk, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = vsum; s_n[threadIdx.x >> 5] = nk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0, n = 0.0;
+        for (int i = 0; i < 8; ++i) { v += s_v[i]; n += s_n[i]; }
+        atomicAdd(out + 0, v);
+        atomicAdd(out + 1, n);
+        if (blockIdx.x == 0) out[2] = (double)B0;
+    }
+}
+
 __global__ void philox_normal_kernel(uint64_t seed, uint64_t traj_offset, int64_t B, int T, int dim, float* __restrict__ out) {
     const int nchunk = (dim + 3) / 4;
     const int64_t total = (int64_t)T * B * nchunk;
@@ -563,6 +602,24 @@ int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rn
     lv_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, stats, upstream, w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "lv weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_lv_traj_stats(const float* rnd, int64_t n_samples, int32_t traj_per_sample, int mask_mode, float max_rnd,
+                       const uint8_t* sample_mask, double* out3, void* stream_) {
+    g_err[0] = 0;
+    if (!rnd || !out3) return fail(-5, "rnd/out NULL");
+    if (traj_per_sample < 2) return fail(-3, "Cannot compute variance over a single trajectory.");
+    if (mask_mode < 0 || mask_mode > 2) return fail(-3, "mask_mode must be 0, 1 or 2");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaMemsetAsync(out3, 0, 3 * sizeof(double), stream);
+    if (e != cudaSuccess) return fail(-7, "memset failed: %s", cudaGetErrorString(e));
+    if (n_samples == 0) return 0;
+    const int blocks = (int)((n_samples + 255) / 256 < 592 ? (n_samples + 255) / 256 : 592);
+    lv_traj_stats_kernel<<<blocks, 256, 0, stream>>>(rnd, n_samples, traj_per_sample, mask_mode, max_rnd, sample_mask, out3);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "lv_traj stats launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

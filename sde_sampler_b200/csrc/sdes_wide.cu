@@ -354,6 +354,55 @@ __global__ void __launch_bounds__(32 * ROWS_PER_CTA) gmm_kernel(const RowArgs a,
     }
 }
 
+// MultiWell (distr/double_well.py:165-179) and Funnel (distr/funnel.py:57-80) on a wide state: log-density and score in
+// planar order, one warp per trajectory (the d <= 64 forms are sdes_step.cuh::multiwell_eval / funnel_eval).
+__global__ void __launch_bounds__(32 * ROWS_PER_CTA) analytic_target_kernel(const RowArgs a, const int want_score) {
+    const SdesRolloutDesc& d = a.d;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= a.Bp) return;
+    const int P = a.P, Hp = a.Hp, dim = d.dim;
+    const float* xr = a.xst + row * P;
+    float* gr = a.g + row * P;
+    float lp = 0.f;
+    if (d.target_kind == SDES_TARGET_MULTIWELL) {
+        for (int p = lane; p < P; p += 32) {
+            const int j = to_natural(p, 1, Hp);
+            const float y = xr[p] - d.shift;
+            float sc = 0.f;
+            if (j < d.n_double_wells) {
+                const float w = y * y - d.separation;
+                lp -= w * w;
+                sc = -4.0f * w * y;
+            } else if (j < dim) {
+                lp -= 0.5f * y * y;
+                sc = -y;
+            }
+            if (want_score) gr[p] = sc;
+        }
+        lp = warp_sum(lp);
+    } else {  // funnel: x_0 ~ N(0, var), x_j | x_0 ~ N(0, exp(x_0))
+        float sq = 0.f;
+        for (int p = lane; p < P; p += 32) {
+            const int j = to_natural(p, 1, Hp);
+            if (j >= 1 && j < dim) sq = fmaf(xr[p], xr[p], sq);
+        }
+        sq = warp_sum(sq);
+        const float x0 = xr[0], inv = expf(-x0), dm1 = (float)(dim - 1);
+        lp = -0.5f * logf(2.0f * 3.14159265358979323846f * d.variance) - 0.5f * x0 * x0 / d.variance - dm1 * (x0 + LOG_2PI) * 0.5f - 0.5f * sq * inv;
+        if (want_score) {
+            for (int p = lane; p < P; p += 32) {
+                const int j = to_natural(p, 1, Hp);
+                float sc = 0.f;
+                if (j == 0) sc = -x0 / d.variance - 0.5f * dm1 + 0.5f * sq * inv;
+                else if (j < dim) sc = -xr[p] * inv;
+                gr[p] = sc;
+            }
+        }
+    }
+    if (lane == 0) a.logp[row] = lp + d.log_norm_const;
+}
+
 // One time step for every trajectory: control assembly (models/reparam.py), noise, running cost / Ito sums and
 // the Euler-Maruyama / exponential-integrator update (losses/oc.py:204-219, :316-331, :429-443) — the wide-state
 // form of sdes_step.cuh::update4.  One warp per trajectory; a lane handles natural dims 4q..4q+3 (= one Philox
@@ -482,8 +531,6 @@ int64_t wide_nice_param_count(const SdesRolloutDesc& d) {
 const char* wide_validate(const SdesRolloutDesc& d) {
     if (d.dim > SDES_MAX_WIDE_DIM) return "dim exceeds SDES_MAX_WIDE_DIM";
     if ((d.flags & SDES_F_HAS_GATE) && d.gate_dim != 1) return "the wide engine supports a scalar gate only (gate_dim = 1)";
-    if (d.target_kind == SDES_TARGET_MULTIWELL || d.target_kind == SDES_TARGET_FUNNEL)
-        return "MultiWell / Funnel targets are implemented on the fused engines only (d <= 64)";
     if (d.target_kind == SDES_TARGET_NICE) {
         if (d.dim % 2) return "NICE needs an even dim";
         if (d.nice_couplings < 1 || d.nice_couplings > MAX_COUP) return "nice_couplings not in [1,8]";
@@ -673,7 +720,8 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
                     }
                 }
             } else {
-                gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
+                if (d.target_kind == SDES_TARGET_GMM) gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
+                else analytic_target_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
                 ++launches;
                 WIDE_CHECK(cudaGetLastError());
             }
@@ -687,8 +735,10 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
         if (p.n_coup == 1) WIDE_CHECK(cudaMemcpyAsync(F(p.h), F(p.xst), p.Bp * (int64_t)p.P * 4, cudaMemcpyDeviceToDevice, stream));
         WIDE_CHECK(nice_forward(ws + p.ximg + (int64_t)p.T * p.ximg_slot));
         latent_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
-    } else {
+    } else if (d.target_kind == SDES_TARGET_GMM) {
         gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
+    } else {
+        analytic_target_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
     }
     ++launches;
     WIDE_CHECK(cudaGetLastError());

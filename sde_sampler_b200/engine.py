@@ -349,6 +349,22 @@ def rnd_stats(rnd: torch.Tensor, mask_mode: int, max_rnd: float = 0.0,
     return out
 
 
+def lv_traj_stats(rnd: torch.Tensor, traj_per_sample: int, mask_mode: int, max_rnd: float = 0.0,
+                  sample_mask: torch.Tensor | None = None) -> torch.Tensor:
+    """[sum of per-sample variances, kept samples, samples] on the device (`sdes_lv_traj_stats`)."""
+    lib = _cabi.lib()
+    r = rnd.detach().reshape(-1).to(torch.float32).contiguous()
+    if r.numel() % traj_per_sample:
+        raise ValueError("rnd does not hold traj_per_sample trajectories per sample")
+    out = torch.empty(3, dtype=torch.float64, device=r.device)
+    m = None if sample_mask is None else sample_mask.reshape(-1).to(torch.uint8).contiguous()
+    with torch.cuda.device(r.device):
+        stream = torch.cuda.current_stream(r.device).cuda_stream
+        _cabi.check(lib.sdes_lv_traj_stats(r.data_ptr(), r.numel() // traj_per_sample, traj_per_sample, mask_mode, float(max_rnd),
+                                           _ptr(m), out.data_ptr(), C.c_void_p(stream)), "sdes_lv_traj_stats")
+    return out
+
+
 def lv_weights(rnd: torch.Tensor, stats: torch.Tensor, mask_mode: int, max_rnd: float = 0.0,
                sample_mask: torch.Tensor | None = None, upstream: torch.Tensor | None = None) -> torch.Tensor:
     """d (lv loss) / d rnd on the device (include/sdes_b200.h `sdes_lv_weights`)."""

@@ -235,15 +235,19 @@ class FusedOCLoss:
         self._n_filtered_dev = None
 
     def _compute_loss_lv_traj(self, rnd, samples):
-        # variance over the traj_per_sample copies of each x0 (oc.py:78-84): a (tps, B0) view of rnd.
-        mask = self.filter(rnd, samples=samples)
-        r = rnd.reshape(self.traj_per_sample, -1, 1)
-        mask = mask.reshape(self.traj_per_sample, -1, 1).all(dim=0)
-        self.n_filtered += self.traj_per_sample * (mask.numel() - mask.sum()).item()
+        # variance over the traj_per_sample copies of each x0 (oc.py:78-84), reduced by `sdes_lv_traj_stats`; every rank
+        # holds all copies of its own samples, so ranks only add three numbers
+        smask = None
+        if samples is not None and self.filter_samples is not None:
+            smask = self.filter_samples(samples)
+        mode = _cabi.MASK_ISFINITE if self.max_rnd is None else _cabi.MASK_MAX_RND
+        st = engine.lv_traj_stats(rnd, self.traj_per_sample, mode, 0.0 if self.max_rnd is None else self.max_rnd, smask)
         if self.process_group is not None:
-            raise NotImplementedError("lv_traj across ranks")
-        loss = r[:, mask].var(dim=0).mean()
-        return loss, {"train/n_filtered_cumulative": self.n_filtered}
+            import torch.distributed as dist
+
+            dist.all_reduce(st, group=self.process_group)
+        self.n_filtered += self.traj_per_sample * int((st[2] - st[1]).item())
+        return (st[0] / st[1]).to(torch.float32), {"train/n_filtered_cumulative": self.n_filtered}
 
     def compute_results(self, rnd: torch.Tensor, compute_weights: bool = False, ts=None, samples=None, xs=None):
         """losses/oc.py:94-123 (a staticmethod there; an instance method here because the

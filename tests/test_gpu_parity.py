@@ -232,3 +232,19 @@ def test_filter_samples_is_applied_like_the_reference(golden, engine):
     want, n_f = oracle_rollout.loss_from_rnd(g["train"]["rnd"], "lv", spec["loss"]["max_rnd"], 1, sample_mask=m)
     assert abs(float(val) - want) <= 1e-3 * (1 + abs(want))
     assert metrics["train/n_filtered_cumulative"] == n_f == int((~m).sum())
+
+
+def test_lv_traj_statistics_match_numpy():
+    """lv_traj (losses/oc.py:78-84) through `sdes_lv_traj_stats`: (tps, B0) layout, a sample is dropped when any of its
+    trajectories is filtered, n_filtered counts tps per dropped sample."""
+    from sde_sampler_b200 import _cabi, engine
+
+    rng = np.random.default_rng(3)
+    tps, B0 = 4, 1001
+    r = (rng.standard_normal((tps, B0)) * 3 + 50).astype(np.float32)
+    r[1, 7] = 5e8
+    r[3, 500] = np.inf
+    st = engine.lv_traj_stats(torch.from_numpy(r).to(_dev()).reshape(-1, 1), tps, _cabi.MASK_MAX_RND, 1e8).cpu().numpy()
+    want, n_f = oracle_rollout.loss_from_rnd(r.reshape(-1), "lv_traj", 1e8, tps)
+    assert st[2] == B0 and st[1] == B0 - 2 and tps * (st[2] - st[1]) == n_f
+    assert st[0] / st[1] == pytest.approx(want, rel=1e-9)

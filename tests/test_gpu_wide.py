@@ -59,7 +59,8 @@ def _variant(spec, **changes):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("variant", ["tr_eval_traj", "lerp_prior", "lerp_target", "clipped", "gmm3", "ref_sde_nice", "tr_kl"])
+@pytest.mark.parametrize("variant", ["tr_eval_traj", "lerp_prior", "lerp_target", "clipped", "gmm3", "ref_sde_nice", "tr_kl",
+                                     "multiwell", "funnel"])
 def test_wide_loss_and_control_kinds_match_oracle(golden, variant, engine):
     """Every loss / control family on a wide state (the goldens pin DDS+ScoreCtrl on NICE and DIS+LerpCtrl on a Gaussian)."""
     g = golden("dis_gauss100_lv")
@@ -85,6 +86,13 @@ def test_wide_loss_and_control_kinds_match_oracle(golden, variant, engine):
                           "scale": rng.uniform(0.7, 1.5, (3, d)).astype(np.float32),
                           "log_weights": np.log(np.array([0.2, 0.5, 0.3], np.float32)), "log_norm_const": 0.0,
                           "clip_target": None}
+    elif variant == "multiwell":     # MultiWell on a wide state: 5 double wells + 95 Gaussian dims
+        spec = copy.deepcopy(spec)
+        spec["target"] = {"kind": "multiwell", "n_dw": 5, "separation": 2.0, "shift": 0.5, "clip_target": None}
+    elif variant == "funnel":        # Funnel in d = 100 (variance 9).  Two steps only: in d = 100 the funnel score drives
+        spec = copy.deepcopy(spec)   # x_0 to large negative values where clip(-x_j exp(-x_0)) acts like sign(x_j) with
+        spec["target"] = {"kind": "funnel", "variance": 9.0, "log_norm_const": 0.0, "clip_target": None}  # slope 1e4 —
+        spec["ts"] = np.asarray(spec["ts"], np.float32)[:3]  # round-off then decides trajectories in ANY fp32 code
     elif variant == "ref_sde_nice":  # ReferenceSDELoss (PIS-style, ScoreCtrl, ScaledBM) with a NICE target
         gn = golden("dds_nice196_lv")["spec"]
         spec = copy.deepcopy(gn)
