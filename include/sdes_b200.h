@@ -163,9 +163,15 @@ int sdes_tcgen05_supported(const SdesRolloutDesc* desc);
  *               (timestep embedding, gate) from the per-step cotangents below
  *   grad_emb    (T, 64)        d loss / d (timestep_embed(s_i) + in_b)        (intermediate, also returned)
  *   grad_gate   (T, gate_dim)  d loss / d gate(s_i)                           (intermediate, also returned) */
+#define SDES_GRAD_TARGET_SCORE_CONST (1u << 0) /* kl gradient: the target score inside the control is a constant of the
+                                                  graph — the reference's autograd score without create_graph
+                                                  (Distribution.score distr/base.py:130-137 called from
+                                                  models/reparam.py:60,:135): GMM targets */
+#define SDES_GRAD_SCORE_DETACHED     (1u << 1) /* kl gradient: ctrl.detach_score=True — the whole score part (target and
+                                                  prior score) is evaluated on x.detach() (models/reparam.py:58,:134) */
 typedef struct SdesLvGradDesc {
     uint32_t struct_bytes;   /* = sizeof(SdesLvGradDesc), checked */
-    uint32_t reserved;
+    uint32_t flags;          /* SDES_GRAD_* (sdes_rollout_kl_grad only; 0 for the lv gradient) */
     const float* xs;         /* (T+1, B, d) trajectory written by the forward call with SDES_F_RETURN_TRAJ */
     const float* w;          /* (B) d loss / d rnd_b (0 for filtered trajectories) */
     float* grad_params;
@@ -176,6 +182,19 @@ typedef struct SdesLvGradDesc {
 
 size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);
 int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream);
+
+/* Gradient of the kl / kl_ito losses with respect to the control network — `loss.backward()` of `Trainable.step`
+ * (solver/base.py:404-407) for loss.method = kl | kl_ito.  Here the state is driven by the control WITH
+ * its graph (`sde_ctrl = generative_ctrl`, losses/oc.py:180,:305,:421): backpropagation through time, done as a
+ * discrete adjoint over the stored trajectory.  One reverse-sweep kernel (thread per trajectory, T steps, replayed
+ * control + its input-gradient + the score part's analytic x-derivatives) writes the cotangent of the control at
+ * every (trajectory, step) into the workspace; the parameter gradient is then the same batched tcgen05 pass as
+ * sdes_rollout_lv_grad.  Same descriptors and outputs as sdes_rollout_lv_grad; `w` = d loss / d rnd_b
+ * (sdes_kl_weights); g->flags = SDES_GRAD_*.  Fused engines only (d <= SDES_MAX_DIM, analytic target); a GMM target
+ * with more than one component requires SDES_GRAD_TARGET_SCORE_CONST (the reference's semantics) or
+ * SDES_GRAD_SCORE_DETACHED. */
+size_t sdes_kl_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);
+int sdes_rollout_kl_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream);
 
 /* EulerIntegrator.integrate (eq/integrator.py:79-127) for a LangevinSDE (eq/sdes.py:38-65) — the unadjusted
  * Langevin sampler of LangevinSolver.run (solver/langevin.py:34-63), SURVEY §8f-3:
@@ -226,6 +245,11 @@ int sdes_lv_traj_stats(const float* rnd, int64_t n_samples, int32_t traj_per_sam
  * mask of sdes_rnd_stats), 0 otherwise; `stats` are the (rank-combined) statistics, `upstream` a device scalar
  * (d objective / d loss, e.g. scale_loss; NULL = 1).  Input `w` of sdes_rollout_lv_grad. */
 int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,
+                    const double* stats, const float* upstream, float* w, void* stream);
+
+/* Cotangent of the kl loss (mean of the kept rnd, losses/oc.py:90) with respect to rnd: w[b] = upstream / n_kept for kept b,
+ * 0 otherwise.  Input `w` of sdes_rollout_kl_grad. */
+int sdes_kl_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,
                     const double* stats, const float* upstream, float* w, void* stream);
 
 /* The noise stream on its own: eps (T,B,d) exactly as the fused kernel draws it in registers

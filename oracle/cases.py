@@ -65,6 +65,23 @@ CASES = {
     "dis_gauss100_lv": dict(target="gauss", dim=100, sde="vp", prior="gauss", ctrl="lerp",
                             clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
                             method="lv", max_rnd=1e8, timesteps=LIN(30), batch=24, seed=10),
+    # ---- kl / kl_ito training gradients (backpropagation through time).  Together with dis_gmm2_kl,
+    # pis_funnel10_kl and dis_lerpprior_multiwell4 above these cover every loss kind, the reference control of Euler-DDS,
+    # active clips, and each target's second derivative (funnel, multiwell, Gauss; the GMM score is an autograd score
+    # WITHOUT create_graph in the reference, distr/base.py:130-137, so it enters the adjoint as a constant).
+    "dds_funnel10_kl": dict(target="funnel", dim=10, sde=None, prior="gauss", ctrl="score",
+                            clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="exp_integrator",
+                            method="kl", max_rnd=1e8, alpha=1.0, sigma=1.0,
+                            timesteps=dict(rescale_t="cosine", end=3.2, dt=0.05), batch=48, seed=11),
+    "eulerdds_gauss3_kl": dict(target="gauss", dim=3, sde="vp", prior="gauss", ctrl="score",
+                               clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="reference_sde",
+                               method="kl", euler_dds=True, max_rnd=1e8, timesteps=LIN(40), batch=48, seed=12),
+    "dis_gmm50_kl": dict(target="gmm40", dim=50, sde="vp", prior="gauss", ctrl="lerp",
+                         clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
+                         method="kl", max_rnd=1e8, timesteps=LIN(40), batch=32, seed=13),
+    "dis_lerp_multiwell5_klito": dict(target="multiwell", dim=5, sde="vp", prior="gauss", ctrl="lerp",
+                                      clip_model=2.0, clip_score=3.0, gate_bias=1.0, gate_dim=5, loss="time_reversal",
+                                      method="kl_ito", max_rnd=None, clip_target=30.0, timesteps=LIN(40), batch=48, seed=14),
 }
 
 # eval-mode variants: (case, compute_weights, return_traj)  — losses/oc.py:258-278, :371-392

@@ -67,9 +67,10 @@ def run_case(name: str, case: dict) -> dict:
     out["train"] = {"x_T": x_T.detach().numpy().copy(), "rnd": rnd.detach().numpy().copy(),
                     "loss": float(lval), "n_filtered": int(loss.n_filtered - n_before)}
 
-    # --- gradient of the lv loss w.r.t. every control parameter by the reference's own autograd
-    #     (`loss.backward()` of Trainable.step, solver/base.py:404-407), flattened in parameter-blob order
-    if method == "lv":
+    # --- gradient of the loss w.r.t. every control parameter by the reference's own autograd
+    #     (`loss.backward()` of Trainable.step, solver/base.py:404-407), flattened in parameter-blob order.
+    #     lv: the state is detached (one MLP backward over all rows); kl / kl_ito: backpropagation through time.
+    if method in ("lv", "kl", "kl_ito"):
         from sde_sampler_b200.spec import ctrl_parameters
 
         params = ctrl_parameters(built["ctrl"])

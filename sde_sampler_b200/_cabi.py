@@ -34,6 +34,9 @@ F_MLP_SIMT = 1 << 7
 F_TRAJ_TILED = 1 << 8
 F_KEEP_FOR_GRAD = 1 << 9
 
+GRAD_TARGET_SCORE_CONST = 1 << 0
+GRAD_SCORE_DETACHED = 1 << 1
+
 MASK_ISFINITE, MASK_MAX_RND, MASK_ALL = 0, 1, 2
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -67,7 +70,7 @@ class RolloutDesc(C.Structure):
 class LvGradDesc(C.Structure):
     """struct SdesLvGradDesc (include/sdes_b200.h)."""
     _fields_ = [
-        ("struct_bytes", C.c_uint32), ("reserved", C.c_uint32),
+        ("struct_bytes", C.c_uint32), ("flags", C.c_uint32),
         ("xs", _fp), ("w", _fp), ("grad_params", _fp), ("grad_emb", _fp), ("grad_gate", _fp),
         ("chunk_rows", C.c_int64),
     ]
@@ -88,6 +91,9 @@ SYMBOLS = {
     "sdes_langevin_integrate": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(IntegrateDesc), C.c_void_p]),
     "sdes_lv_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
     "sdes_rollout_lv_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
+    "sdes_kl_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
+    "sdes_rollout_kl_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
+    "sdes_kl_weights": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
     "sdes_version": (C.c_int, []),
     "sdes_last_error": (C.c_char_p, []),
     "sdes_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc)]),

@@ -1,10 +1,15 @@
-"""`loss.backward()` for the log-variance losses (reference: `Trainable.step`, solver/base.py:404-407).
+"""`loss.backward()` for the log-variance losses and the kl / kl_ito losses (reference:
+`Trainable.step`, solver/base.py:404-407).
 
 The forward is the fused rollout (with the trajectory kept), the backward is ONE C-ABI call, `sdes_rollout_lv_grad`:
 a pass of the control MLP's backward over all (trajectory, step) rows on the tensor cores plus the backward of the two
 x-independent TimeEmbed networks (csrc/sdes_grad.cu explains why no backpropagation through time is needed —
 losses/oc.py:60-64: the state is driven by the detached control).  It returns the gradient of every control parameter
-in the layout of the parameter blob; this module only slices that blob back onto the caller's `nn.Parameter`s."""
+in the layout of the parameter blob; this module only slices that blob back onto the caller's `nn.Parameter`s.
+
+kl / kl_ito: the state carries the graph, so `sdes_rollout_kl_grad` first runs a reverse sweep over the stored
+trajectory (csrc/sdes_adjoint.cu: discrete adjoint, control cotangent per (trajectory, step)) and then the same batched
+tensor-core pass."""
 from __future__ import annotations
 
 import torch
@@ -33,12 +38,15 @@ class LvLoss(torch.autograd.Function):
             raise RuntimeError("the trajectory of this loss value was overwritten by a later training call of the same "
                                "loss object; call backward() before the next forward (as Trainable.step does)")
         mode = _cabi.MASK_ISFINITE if lo.max_rnd is None else _cabi.MASK_MAX_RND
-        w = engine.lv_weights(m["rnd"], m["stats"], mode, 0.0 if lo.max_rnd is None else lo.max_rnd, m["smask"], grad_out)
+        bptt = lo.method != "lv"  # kl / kl_ito: the state carries the graph -> reverse sweep first (sdes_rollout_kl_grad)
+        weights = engine.kl_weights if bptt else engine.lv_weights
+        w = weights(m["rnd"], m["stats"], mode, 0.0 if lo.max_rnd is None else lo.max_rnd, m["smask"], grad_out)
         blob = torch.cat([p.detach().reshape(-1).float() for p in params])
         wide = engine.is_wide(m["spec"])  # wide engine: the forward kept what is needed inside its own workspace
         g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w, noise=m["noise"], seed=m["seed"],
                                                traj_offset=m["traj_offset"], engine=lo.engine,
-                                               workspace=lo._workspace if wide else lo._grad_workspace, params=blob)
+                                               workspace=lo._workspace if wide else lo._grad_workspace, params=blob,
+                                               bptt=bptt)
         grads, o = [], 0
         for p in params:  # blob order (include/sdes_b200.h) == ctrl_parameters order
             grads.append(g_blob[o:o + p.numel()].reshape(p.shape))
@@ -57,9 +65,10 @@ class LvLoss(torch.autograd.Function):
 
 
 def wants_grad(loss_obj) -> bool:
-    """True when the training call should return a loss with a grad_fn: grad mode on, log-variance loss, trainable
-    control parameters, and a configuration `sdes_rollout_lv_grad` covers."""
-    if not torch.is_grad_enabled() or loss_obj.method != "lv":
+    """True when the training call should return a loss with a grad_fn: grad mode on, trainable control parameters, and a
+    configuration the gradient kernels cover — lv: `sdes_rollout_lv_grad` (every engine); kl / kl_ito:
+    `sdes_rollout_kl_grad` (fused engines: d <= 64, analytic target)."""
+    if not torch.is_grad_enabled() or loss_obj.method not in ("lv", "kl", "kl_ito"):
         return False
     ctrl = loss_obj.generative_ctrl
     try:
@@ -69,6 +78,8 @@ def wants_grad(loss_obj) -> bool:
     dim = int(ctrl.base_model.input_embed.weight.shape[1])
     target = getattr(getattr(ctrl, "target_score", None), "__self__", None)
     wide = dim > _cabi.MAX_DIM or (target is not None and hasattr(target, "model"))
+    if wide and loss_obj.method != "lv":
+        return False  # backpropagation through time on the wide engine is not built: plain value, no grad_fn
     gate = getattr(ctrl, "score_model", None)
     if wide and gate is not None and int(gate.out_layer.weight.shape[0]) != 1:
         return False  # the wide engine has a scalar gate only

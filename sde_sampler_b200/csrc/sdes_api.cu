@@ -29,7 +29,9 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
 cudaError_t launch_langevin(const IntegrateParams& a, cudaStream_t stream);
 // lv gradient (sdes_grad.cu)
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
-int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err);
+int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err,
+                       bool bptt, int sm_count);
+size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
 int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err);
 
 static thread_local char g_err[512] = "";
@@ -243,6 +245,19 @@ __global__ void lv_weights_kernel(const float* __restrict__ rnd, int64_t B, int 
         bool keep = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
         if (smask != nullptr) keep = keep && smask[i] != 0;
         w[i] = keep ? (float)(2.0 * ((double)r - mean) / (n - 1.0) * up) : 0.f;
+    }
+}
+
+// d (kl loss) / d rnd_b = 1 / n_kept for kept b (mean of the kept entries, losses/oc.py:90), times the upstream scalar
+__global__ void kl_weights_kernel(const float* __restrict__ rnd, int64_t B, int mode, float max_rnd, const uint8_t* __restrict__ smask,
+                                  const double* __restrict__ stats, const float* __restrict__ upstream, float* __restrict__ w) {
+    const double up = upstream != nullptr ? (double)upstream[0] : 1.0;
+    const float wk = (float)(up / stats[0]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const float r = rnd[i];
+        bool keep = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
+        if (smask != nullptr) keep = keep && smask[i] != 0;
+        w[i] = keep ? wk : 0.f;
     }
 }
 
@@ -531,8 +546,49 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
     if (need > desc->workspace_bytes) return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, need);
     if (desc->batch == 0) return 0;
     cudaError_t e = cudaSuccess;
-    g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e);
+    g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e, false, 0);
     if (e != cudaSuccess) return fail(-7, "lv gradient launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- kl / kl_ito gradient (sdes_adjoint.cu + the GEMM passes of sdes_grad.cu)
+static int kl_grad_setup(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, KParams& p, bool& simt) {
+    int rc = grad_setup(desc, g, p, simt);
+    if (rc != 0) return rc;
+    if (wide_engine_needed(*desc))
+        return fail(-8, "the kl gradient (backpropagation through time) is implemented on the fused engines: d <= %d, analytic target", SDES_MAX_DIM);
+    if (desc->target_kind == SDES_TARGET_GMM && desc->n_components > 1 && desc->ctrl_kind != SDES_CTRL_CLIPPED &&
+        desc->ctrl_kind != SDES_CTRL_LERP_PRIOR && !(g->flags & (SDES_GRAD_TARGET_SCORE_CONST | SDES_GRAD_SCORE_DETACHED)))
+        return fail(-8, "kl gradient with a %d-component GMM score inside the control needs SDES_GRAD_TARGET_SCORE_CONST "
+                        "(the reference differentiates an autograd score without create_graph)", desc->n_components);
+    return 0;
+}
+
+size_t sdes_kl_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g) {
+    KParams p;
+    bool simt;
+    if (kl_grad_setup(desc, g, p, simt) != 0) return 0;
+    return kl_grad_workspace_bytes(p.d, p.ws.total * (int64_t)sizeof(float), g->chunk_rows);
+}
+
+int sdes_rollout_kl_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream_) {
+    g_err[0] = 0;
+    KParams p;
+    bool simt;
+    int rc = kl_grad_setup(desc, g, p, simt);
+    if (rc != 0) return rc;
+    if (!desc->ts || !desc->params || !desc->workspace) return fail(-5, "ts/params/workspace must be non-NULL");
+    if (!g->xs || !g->w || !g->grad_params || !g->grad_emb) return fail(-5, "xs/w/grad_params/grad_emb must be non-NULL");
+    if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
+    if (desc->target_kind == SDES_TARGET_GMM && (!desc->gmm_loc || !desc->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");
+    if (reinterpret_cast<uintptr_t>(desc->workspace) % 256 != 0) return fail(-5, "workspace must be 256-byte aligned");
+    const int64_t fused = p.ws.total * (int64_t)sizeof(float);
+    const size_t need = kl_grad_workspace_bytes(p.d, fused, g->chunk_rows);
+    if (need > desc->workspace_bytes) return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, need);
+    if (desc->batch == 0) return 0;
+    cudaError_t e = cudaSuccess;
+    g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e, true, sm_count_cached());
+    if (e != cudaSuccess) return fail(-7, "kl gradient launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -602,6 +658,20 @@ int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rn
     lv_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, stats, upstream, w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "lv weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_kl_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask, const double* stats,
+                    const float* upstream, float* w, void* stream_) {
+    g_err[0] = 0;
+    if (!rnd || !stats || !w) return fail(-5, "rnd/stats/w NULL");
+    if (mask_mode < 0 || mask_mode > 2) return fail(-3, "mask_mode must be 0, 1 or 2");
+    if (batch == 0) return 0;
+    const int blocks = (int)((batch + 255) / 256 < 1184 ? (batch + 255) / 256 : 1184);
+    kl_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, stats, upstream, w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "kl weights launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

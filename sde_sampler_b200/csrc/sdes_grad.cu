@@ -120,6 +120,7 @@ struct CotArgs {
     const float* w;
     const float* nn;          // (rows, P)
     const float* ones;
+    const float* delta;       // kl / kl_ito: control cotangent (T, B, d) of the adjoint sweep (sdes_adjoint.cu); NULL = lv
     uint8_t* dnn_img;
     float* grad_gate;         // (T, gate_dim) or NULL
     int P, pc, s0;
@@ -165,6 +166,8 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     const StepCoef c = make_step_coef(d, tab);
     const float wb = valid ? a.w[bb] : 0.f;
     const float cscale = wb * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
+    const bool bptt = a.delta != nullptr;
+    const TrajRef dref = traj_ref(d, const_cast<float*>(bptt ? a.delta : a.xs), s, bb);
     const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
     const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
     const float* nnrow = a.nn + rr * a.P;
@@ -181,7 +184,11 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
 #pragma unroll
     for (int q = 0; q < DPAD / 4; ++q) {
         float e[4] = {0.f, 0.f, 0.f, 0.f};
-        if (4 * q < dim) {
+        if (bptt) {
+            // the cotangent of the control was produced by the reverse sweep; cscale * e below reproduces it
+#pragma unroll
+            for (int r = 0; r < 4; ++r) e[r] = (valid && 4 * q + r < dim) ? __ldg(dref.p + (4 * q + r) * dref.stride) : 0.f;
+        } else if (4 * q < dim) {
             if (c.from_hbm) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < dim) ? nrow[4 * q + r] : 0.f;
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int j = 4 * q + r;
-            const float cj = (j < dim) ? cscale * e[r] : 0.f;
+            const float cj = (j < dim) ? (bptt ? e[r] : cscale * e[r]) : 0.f;
             const float nnj = (j < dim) ? nnrow[j] : 0.f;
             cot[j] = (fabsf(nnj) <= c.cm) ? cj : 0.f;  // d clip(NN) / d NN (torch.clip passes the gradient on [-c, c])
             if (d.gate_dim == 1) gsum = fmaf(cj, sc[j], gsum);
@@ -801,7 +808,24 @@ size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, in
 
 // kp: descriptor with SDES_F_MLP_SIMT set (fp32 tables / target images of the fused prologue at the start of the
 // workspace), its blob and workspace layouts.  Returns the number of kernel launches.
-int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err) {
+cudaError_t launch_kl_adjoint(const KParams& kp, const float* xs, const float* w, float* delta, uint32_t gflags, int sm_count,
+                              cudaStream_t stream);  // sdes_adjoint.cu
+
+static int64_t delta_floats(const SdesRolloutDesc& d) {
+    if (d.flags & SDES_F_TRAJ_TILED) return (int64_t)d.n_steps * ((d.batch + 127) / 128) * mma_pad_dim(d.dim) * 128;
+    return (int64_t)d.n_steps * d.batch * d.dim;
+}
+
+size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows) {
+    GradPlan p;
+    make_plan(d, chunk_rows, align256(fused_bytes), p);
+    return (size_t)(align256(p.total) + delta_floats(d) * 4);
+}
+
+// bptt = false: lv (closed-form cotangent).  bptt = true: kl / kl_ito — the reverse sweep of sdes_adjoint.cu first writes
+// the control cotangent of every (trajectory, step) after the plan's scratch, then the same GEMM passes consume it.
+int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err,
+                       bool bptt, int sm_count) {
     const SdesRolloutDesc& d = kp.d;
     GradPlan p;
     make_plan(d, g.chunk_rows, align256(fused_bytes), p);
@@ -818,6 +842,13 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     launch_prepare(kp, stream);
     ++launches;
     GRAD_CHECK(cudaGetLastError());
+    const float* delta = nullptr;
+    if (bptt) {
+        float* dl = F(align256(p.total));
+        GRAD_CHECK(launch_kl_adjoint(kp, g.xs, g.w, dl, g.flags, sm_count, stream));
+        ++launches;
+        delta = dl;
+    }
     const float* blob = d.params;
     const float* fws = reinterpret_cast<const float*>(d.workspace);
     embb_kernel<<<(p.T * C + 255) / 256, 256, 0, stream>>>(fws + kp.ws.emb, blob + kp.bl.in_b, F(p.embb), p.T * C, F(p.ones));
@@ -909,7 +940,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         // ---- output cotangent and gate gradient
         {
             CotArgs ca;
-            ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.dnn_img = ws + p.dnn_img;
+            ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.delta = delta; ca.dnn_img = ws + p.dnn_img;
             ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = s0; ca.Bp = p.Bp;
             GRAD_CHECK(launch_cot(ca, m_tiles, stream));
             ++launches;

@@ -265,14 +265,37 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
     return x_T, rnd, xs
 
 
+def kl_grad_flags(spec: RolloutSpec) -> int:
+    """SDES_GRAD_* for `sdes_rollout_kl_grad`: which parts of the control's score term carry a graph in the reference.
+    A `GMM` target's score is `Distribution.score` — autograd WITHOUT create_graph (distr/base.py:130-137, called with
+    create_graph=detach_score=False from models/reparam.py:60,:135) — a constant of the graph; Gauss / DoubleWell /
+    MultiWell / Funnel scores are analytic functions of x; `detach_score=True` detaches the whole score term."""
+    flags = 0
+    if spec.target["kind"] == "gmm":
+        flags |= _cabi.GRAD_TARGET_SCORE_CONST
+    if spec.extras.get("detach_score"):
+        flags |= _cabi.GRAD_SCORE_DETACHED
+    return flags
+
+
+def kl_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, **kw):
+    """d loss / d theta of the kl / kl_ito loss (backpropagation through time, `sdes_rollout_kl_grad`); arguments and
+    results as `lv_grad`."""
+    return lv_grad(spec, xs, w, bptt=True, **kw)
+
+
 def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
-            params: torch.Tensor | None = None, chunk_rows: int = 0):
+            params: torch.Tensor | None = None, chunk_rows: int = 0, bptt: bool = False):
     """d loss / d theta of the log-variance loss for the rollout that produced `xs` (same spec / seed / traj_offset /
     noise).  Returns (grad_params blob, grad_emb (T,64), grad_gate (T,gate_dim) | None) — see include/sdes_b200.h
-    `sdes_rollout_lv_grad`."""
+    `sdes_rollout_lv_grad`.  `bptt=True`: the kl / kl_ito gradient (`sdes_rollout_kl_grad`)."""
     lib = _cabi.lib()
     wide = is_wide(spec)
+    if bptt and wide:
+        raise NotImplementedError("the kl gradient (backpropagation through time) covers d <= 64 with analytic targets")
+    fn_bytes, fn_grad, what = ((lib.sdes_kl_grad_workspace_bytes, lib.sdes_rollout_kl_grad, "sdes_rollout_kl_grad") if bptt else
+                               (lib.sdes_lv_grad_workspace_bytes, lib.sdes_rollout_lv_grad, "sdes_rollout_lv_grad"))
     if not w.is_cuda:
         raise _cabi.SdesError("the fused gradient runs on a CUDA device only; there is no CPU path")
     device = w.device
@@ -308,6 +331,7 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
         d.flags |= _cabi.F_NOISE_FROM_HBM
     g = _cabi.LvGradDesc()
     g.struct_bytes = C.sizeof(_cabi.LvGradDesc)
+    g.flags = kl_grad_flags(spec) if bptt else 0
     grad_params = torch.empty_like(params)
     grad_emb = torch.empty((T, _cabi.CHANNELS), dtype=torch.float32, device=device)
     grad_gate = None
@@ -316,9 +340,9 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
     g.xs, g.w, g.grad_params, g.grad_emb, g.grad_gate = _ptr(None if wide else xs), w.data_ptr(), grad_params.data_ptr(), grad_emb.data_ptr(), _ptr(grad_gate)
     g.chunk_rows = chunk_rows
     with torch.cuda.device(device):
-        need = lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g))
+        need = fn_bytes(C.byref(d), C.byref(g))
         if need == 0:
-            raise _cabi.SdesError("lv gradient: " + lib.sdes_last_error().decode())
+            raise _cabi.SdesError(what + ": " + lib.sdes_last_error().decode())
         if wide:
             wsbuf = workspace.buf  # must be the buffer the keep-mode forward wrote (never re-allocated here)
             if wsbuf.numel() < need or wsbuf.device != device:
@@ -327,7 +351,7 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
             wsbuf = (workspace or Workspace()).get(need, device)
         d.workspace, d.workspace_bytes = wsbuf.data_ptr(), wsbuf.numel()
         stream = torch.cuda.current_stream(device).cuda_stream
-        _cabi.check(lib.sdes_rollout_lv_grad(C.byref(d), C.byref(g), C.c_void_p(stream)), "sdes_rollout_lv_grad")
+        _cabi.check(fn_grad(C.byref(d), C.byref(g), C.c_void_p(stream)), what)
     return grad_params, grad_emb, grad_gate
 
 
@@ -377,6 +401,21 @@ def lv_weights(rnd: torch.Tensor, stats: torch.Tensor, mask_mode: int, max_rnd: 
         stream = torch.cuda.current_stream(r.device).cuda_stream
         _cabi.check(lib.sdes_lv_weights(r.data_ptr(), r.numel(), mask_mode, float(max_rnd), _ptr(m), stats.data_ptr(), _ptr(up),
                                         w.data_ptr(), C.c_void_p(stream)), "sdes_lv_weights")
+    return w
+
+
+def kl_weights(rnd: torch.Tensor, stats: torch.Tensor, mask_mode: int, max_rnd: float = 0.0,
+               sample_mask: torch.Tensor | None = None, upstream: torch.Tensor | None = None) -> torch.Tensor:
+    """d (kl loss) / d rnd on the device (include/sdes_b200.h `sdes_kl_weights`)."""
+    lib = _cabi.lib()
+    r = rnd.detach().reshape(-1).to(torch.float32).contiguous()
+    w = torch.empty_like(r)
+    m = None if sample_mask is None else sample_mask.reshape(-1).to(torch.uint8).contiguous()
+    up = None if upstream is None else upstream.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+    with torch.cuda.device(r.device):
+        stream = torch.cuda.current_stream(r.device).cuda_stream
+        _cabi.check(lib.sdes_kl_weights(r.data_ptr(), r.numel(), mask_mode, float(max_rnd), _ptr(m), stats.data_ptr(), _ptr(up),
+                                        w.data_ptr(), C.c_void_p(stream)), "sdes_kl_weights")
     return w
 
 

@@ -13,8 +13,9 @@ CUDA kernel whose partial statistics are combined across ranks when a process gr
 What is not implemented raises (`NotImplementedError`) instead of falling back: a learned
 `inference_ctrl`, `sde_ctrl_noise` / `sde_ctrl_dropout`, targets other than GMM / Gauss /
 DoubleWell / MultiWell / Funnel / Nice.  Gradients: `loss.method = "lv"` with trainable control
-parameters returns a loss whose `.backward()` runs on the tensor cores (autograd.py, csrc/sdes_grad.cu; d <= 64,
-analytic targets); the kl losses need backpropagation through time and return a plain value.
+parameters returns a loss whose `.backward()` runs on the tensor cores (autograd.py, csrc/sdes_grad.cu); `"kl"` /
+`"kl_ito"` do the same after a reverse sweep over the stored trajectory (csrc/sdes_adjoint.cu; d <= 64, analytic
+targets — on the wide engine the kl losses return a plain value).
 """
 from __future__ import annotations
 
@@ -133,6 +134,7 @@ class FusedOCLoss:
             if spec.ctrl["kind"] != "clipped":
                 spec.ctrl["scale_score"] = float(ctrl.scale_score)
                 spec.ctrl["clip_score"] = ctrl.clip_score
+                spec.extras["detach_score"] = bool(getattr(ctrl, "detach_score", False))
             owner = getattr(terminal_unnorm_log_prob, "__self__", None)
             if hasattr(owner, "clip_target"):
                 spec.target["clip_target"] = owner.clip_target
@@ -195,8 +197,8 @@ class FusedOCLoss:
 
     def _call_with_grad(self, ts, x, terminal_unnorm_log_prob, second_log_prob, noise=None):
         """Training call whose result carries a gradient: value by the fused rollout (trajectory kept), gradient by
-        `sdes_rollout_lv_grad` (sde_sampler_b200/autograd.py).  Log-variance loss only: the kl losses need
-        backpropagation through time and return a value without grad_fn."""
+        `sdes_rollout_lv_grad` (lv) or `sdes_rollout_kl_grad` (kl / kl_ito: backpropagation through time as a discrete
+        adjoint) — sde_sampler_b200/autograd.py."""
         from .autograd import LvLoss
 
         params = ctrl_parameters(self.generative_ctrl)
@@ -205,7 +207,8 @@ class FusedOCLoss:
         out = {}
 
         def run():
-            spec = self._spec(ts, terminal_unnorm_log_prob, second_log_prob, train=True, compute_ito=True, return_traj=True)
+            spec = self._spec(ts, terminal_unnorm_log_prob, second_log_prob, train=True, compute_ito=self.method != "kl",
+                              return_traj=True)
             seed, off = self._next_seed(), self._rank_offset(x.shape[0])
             x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
                                           workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer,

@@ -369,8 +369,10 @@ def extract_spec(loss_obj, loss_kind: str, ts: torch.Tensor, terminal_unnorm_log
     ts_t = _t(ts).reshape(-1).to(torch.float32)
     if ts_t.shape[0] < 2:
         raise ValueError("need at least one time step")
+    # only the kl gradient looks at this: with detach_score the score term is evaluated on x.detach() (reparam.py:58,:134)
+    extras = {"detach_score": kind != "clipped" and bool(getattr(ctrl, "detach_score", False))}
     return RolloutSpec(dim=dim, ts=ts_t, loss=ld, ctrl=cd, mlp=mlp, gate=gate, sde=sde,
-                       prior=prior, ref=ref, target=target)
+                       prior=prior, ref=ref, target=target, extras=extras)
 
 
 def inf_if_none(v) -> float:

@@ -1,4 +1,6 @@
-"""-m gpu: `loss.backward()` of the log-variance losses — the tensor-core gradient path
+"""-m gpu: `loss.backward()` of the log-variance losses and of the kl / kl_ito losses (SURVEY §8f-2:
+backpropagation through time — reverse sweep csrc/sdes_adjoint.cu + the same tensor-core passes; the goldens hold the
+reference's autograd gradients for those too) — the tensor-core gradient path
 (csrc/sdes_grad.cu through sde_sampler_b200/autograd.py) against the gradients the UNMODIFIED reference produces with
 its own autograd on the same x0 / noise (`train/grad_blob` in tests/golden, frozen by oracle/gen_golden.py:
 `loss.simulate(...)`, `loss.compute_loss(rnd)`, `.backward()`; parameters flattened in blob order).
@@ -18,6 +20,7 @@ from sdes_test_helpers import build_from_spec
 pytestmark = pytest.mark.gpu
 ENGINES = ["simt", "tcgen05"]
 GRAD_CASES = [n for n, c in CASES.items() if c["method"] == "lv"]  # incl. the wide engine: NICE targets, d = 100 / 196
+KL_GRAD_CASES = [n for n, c in CASES.items() if c["method"] in ("kl", "kl_ito")]
 
 
 def _dev():
@@ -32,6 +35,45 @@ def _grads(b, x0, noise):
     assert val.requires_grad
     val.backward()
     return val, params, [torch.zeros_like(p) if p.grad is None else p.grad.detach().clone() for p in params]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", KL_GRAD_CASES)
+def test_kl_gradient_matches_reference_autograd(golden, name, engine):
+    """Backpropagation through time: every loss kind (time reversal, reference SDE with and without the Euler-DDS
+    reference control, exponential integrator), kl and kl_ito, active clips, per-dimension gate, and each target's
+    second derivative; the GMM score enters as a constant exactly as in the reference (engine.kl_grad_flags)."""
+    test_lv_gradient_matches_reference_autograd(golden, name, engine)
+
+
+def test_kl_gradient_ignores_filtered_trajectories_and_detach_score(golden):
+    """rnd[mask].mean(): a filtered trajectory contributes nothing, whatever its state holds; detach_score=True removes the
+    score term's x-dependence from the adjoint (models/reparam.py:58) and must change the gradient."""
+    g = golden("pis_funnel10_kl")
+    x0 = torch.from_numpy(g["x0"]).to(_dev())
+    T, (B, d) = g["ts"].shape[0] - 1, x0.shape
+    noise = torch.from_numpy(philox.normal_noise(NOISE_SEED, B, T, d)).to(_dev())
+    b = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    _, params, ref = _grads(b, x0, noise)
+    # (1) max_rnd below the largest rnd: those trajectories are dropped from value and gradient
+    with torch.no_grad():
+        _, rnd, _ = b["loss"].simulate(b["ts"], x0, b["terminal"], b["second"], noise=noise)
+    thr = float(rnd.reshape(-1).sort().values[-8])
+    b2 = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    b2["loss"].max_rnd = thr
+    keep = (rnd.reshape(-1) < thr)
+    val2, _, got2 = _grads(b2, x0, noise)
+    b3 = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    val3, _, got3 = _grads(b3, x0[keep], noise[:, keep])
+    assert abs(float(val2) - float(val3)) <= 1e-5 * (1 + abs(float(val3)))
+    for u, v in zip(got2, got3):
+        assert (u - v).abs().max().item() <= 2e-3 * v.abs().max().item() + 1e-7
+    # (2) detach_score
+    b4 = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    b4["ctrl"].detach_score = True
+    _, _, got4 = _grads(b4, x0, noise)
+    diff = max((u - v).abs().max().item() / (v.abs().max().item() + 1e-30) for u, v in zip(got4, ref))
+    assert diff > 1e-2
 
 
 @pytest.mark.parametrize("engine", ENGINES)
