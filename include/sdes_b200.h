@@ -252,6 +252,53 @@ int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rn
 int sdes_kl_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,
                     const double* stats, const float* upstream, float* w, void* stream);
 
+/* ---- the caller's side of the rollout ------------------------------------------------------------ */
+
+/* x0 ~ prior: IsotropicGauss.sample (distr/gauss.py:228-242) — `loc + scale * randn` or, with truncate_quartile,
+ * nn.init.trunc_normal_(mean, std, a, b) (uniform on [2 Phi(a')-1, 2 Phi(b')-1], erfinv, scale, shift, clamp) — drawn from
+ * the Philox stream keyed by `seed` with counter (traj_offset + b, 0xFFFFFFFF, dim/4), so shards of a batch draw what the
+ * whole batch would.  `uniforms` (B,d in [0,1), may be NULL) replaces the Philox uniforms of the truncated path (parity
+ * hook).  out (B,d). */
+int sdes_sample_gauss_prior(float* out, int64_t batch, int32_t dim, float mean, float std, int32_t truncated, float a, float b,
+                            uint64_t seed, uint64_t traj_offset, const float* uniforms, void* stream);
+
+/* The tail of Trainable.step (solver/base.py:409-439) on flat fp32 buffers of n parameters, without a host sync:
+ *   loss_ok = isfinite(loss) or |loss| <= max_loss;  grad_ok = all-finite or inf-norm <= max_grad      (:410-421)
+ *   if both: clip_grad_norm_(max_norm = grad_clip_norm, L2; conf/utils/grad_clip.yaml), torch.optim.Adam step
+ *   (lr, betas, eps, L2 weight_decay; conf/solver/oc_base.yaml:26-29), EMA.update (solver/base.py:620-684: copy until
+ *   update_after_step, then every update_every calls shadow -= (1 - decay_t)(shadow - param) with the warm-up decay of
+ *   get_current_decay);  else: skipped-step counter += 1.
+ * +inf for max_loss / max_grad / grad_clip_norm = not set; ema_shadow NULL = no EMA; loss NULL = no loss check.
+ * state: 8 doubles on the device, zero-initialised by the caller, carried from call to call:
+ *   [0] optimizer steps taken  [1] skipped steps  [2] EMA num_updates  [3] gradient L2 norm of this call
+ *   [4] gradient inf-norm  [5] 1 if this call stepped  [6] EMA decay used (-1: no EMA update)  [7] clip coefficient
+ * The learning-rate / parameter schedulers stay with the caller (they are Python objects); `lr` is read per call. */
+typedef struct SdesTrainerStepDesc {
+    uint32_t struct_bytes;   /* = sizeof(SdesTrainerStepDesc), checked */
+    uint32_t reserved;
+    int64_t n;
+    float* params;
+    const float* grads;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float* ema_shadow;
+    const float* loss;
+    float lr, beta1, beta2, eps, weight_decay;
+    float max_loss, max_grad, grad_clip_norm;
+    double ema_decay, ema_inv_gamma, ema_power, ema_min_value;   /* doubles: the reference evaluates the decay with Python floats */
+    int32_t ema_update_after_step, ema_update_every;
+    double* state;
+    void* workspace;         /* >= sdes_trainer_workspace_bytes() */
+    size_t workspace_bytes;
+} SdesTrainerStepDesc;
+size_t sdes_trainer_workspace_bytes(void);
+int sdes_trainer_step(const SdesTrainerStepDesc* desc, void* stream);
+
+/* Sample statistics of get_metrics (eval/metrics.py:120-131) in one pass: out (device, 4 + 2 d doubles) =
+ *   [0] sum w  [1] sum w^2  [2] B  [3] 0  [4 + j] sum_b x_bj  [4 + d + j] sum_b x_bj^2
+ * (ESS = [0]^2 / [1]; stddev_j, avg_j from the moments).  weights may be NULL. */
+int sdes_eval_moments(const float* samples, const float* weights, int64_t batch, int32_t dim, double* out, void* stream);
+
 /* The noise stream on its own: eps (T,B,d) exactly as the fused kernel draws it in registers
  * (Philox4x32-10 keyed by seed, counter (traj_offset+b, step, dim/4) + Box-Muller).  Test hook. */
 int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32_t n_steps,

@@ -76,6 +76,19 @@ class LvGradDesc(C.Structure):
     ]
 
 
+class TrainerStepDesc(C.Structure):
+    """struct SdesTrainerStepDesc (include/sdes_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("reserved", C.c_uint32), ("n", C.c_int64),
+        ("params", _fp), ("grads", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("ema_shadow", _fp), ("loss", _fp),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("max_loss", C.c_float), ("max_grad", C.c_float), ("grad_clip_norm", C.c_float),
+        ("ema_decay", C.c_double), ("ema_inv_gamma", C.c_double), ("ema_power", C.c_double), ("ema_min_value", C.c_double),
+        ("ema_update_after_step", C.c_int32), ("ema_update_every", C.c_int32),
+        ("state", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class IntegrateDesc(C.Structure):
     """struct SdesIntegrateDesc (include/sdes_b200.h)."""
     _fields_ = [
@@ -94,6 +107,11 @@ SYMBOLS = {
     "sdes_kl_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
     "sdes_rollout_kl_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
     "sdes_kl_weights": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "sdes_sample_gauss_prior": (C.c_int, [_fp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
+                                          C.c_uint64, C.c_uint64, _fp, C.c_void_p]),
+    "sdes_trainer_workspace_bytes": (C.c_size_t, []),
+    "sdes_trainer_step": (C.c_int, [C.POINTER(TrainerStepDesc), C.c_void_p]),
+    "sdes_eval_moments": (C.c_int, [_fp, _fp, C.c_int64, C.c_int32, _fp, C.c_void_p]),
     "sdes_version": (C.c_int, []),
     "sdes_last_error": (C.c_char_p, []),
     "sdes_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc)]),

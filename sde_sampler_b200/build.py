@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libsdes_b200.so")
 OBJ_DIR = os.path.join(CSRC, "_obj")
-SOURCES = ["sdes_api.cu", "sdes_prepare.cu", "sdes_rollout_simt.cu", "sdes_rollout_mma.cu", "sdes_wide.cu", "sdes_grad.cu", "sdes_adjoint.cu", "sdes_integrate.cu"]
+SOURCES = ["sdes_api.cu", "sdes_prepare.cu", "sdes_rollout_simt.cu", "sdes_rollout_mma.cu", "sdes_wide.cu", "sdes_grad.cu", "sdes_adjoint.cu", "sdes_integrate.cu", "sdes_trainer.cu"]
 HEADERS = ["sdes_common.cuh", "sdes_step.cuh", "sdes_tc.cuh", "sdes_timeembed.cuh", "sdes_linear.cuh", os.path.join("..", "..", "include", "sdes_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -38,12 +38,6 @@ struct AdjArgs {
     int warps;           // warps per CTA
 };
 
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-    // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    return fmaf(x * 0.3989422804014327f, expf(-0.5f * x * x), cdf);
-}
-
 __device__ __forceinline__ float dot64(const float* __restrict__ wrow, const float (&v)[C]) {
     const float4* w4 = reinterpret_cast<const float4*>(wrow);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -88,8 +82,10 @@ __device__ __forceinline__ void mlp_fwd_keep(const float (&x)[DPAD], float (&out
     for (int l = 0; l < nh; ++l) {
 #pragma unroll
         for (int n = 0; n < C; ++n) {
-            act[n * 32 + lane] = gelu_erf(acc[n]);
-            gp[(l * C + n) * 32 + lane] = gelu_erf_grad(acc[n]);
+            float y, dy;
+            gelu_and_grad(acc[n], y, dy);  // one erfc / exp evaluation for both (|error| < 6e-7, sdes_common.cuh)
+            act[n * 32 + lane] = y;
+            gp[(l * C + n) * 32 + lane] = dy;
         }
         const float* b = w + C * C;
 #pragma unroll
@@ -111,8 +107,10 @@ __device__ __forceinline__ void mlp_fwd_keep(const float (&x)[DPAD], float (&out
     }
 #pragma unroll
     for (int n = 0; n < C; ++n) {
-        act[n * 32 + lane] = gelu_erf(acc[n]);
-        gp[(nh * C + n) * 32 + lane] = gelu_erf_grad(acc[n]);
+        float y, dy;
+        gelu_and_grad(acc[n], y, dy);
+        act[n * 32 + lane] = y;
+        gp[(nh * C + n) * 32 + lane] = dy;
     }
     {
         const float* b = w + C * DPAD;

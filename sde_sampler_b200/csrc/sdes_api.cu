@@ -34,6 +34,13 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
 size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
 int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err);
 
+// caller-side kernels (sdes_trainer.cu)
+cudaError_t launch_sample_prior(float* out, const float* uniforms, int64_t batch, int dim, float mean, float std, int truncated, float a,
+                                float b, uint64_t seed, uint64_t traj_offset, cudaStream_t stream);
+size_t trainer_workspace_bytes();
+cudaError_t launch_trainer_step(const SdesTrainerStepDesc& d, cudaStream_t stream);
+cudaError_t launch_eval_moments(const float* x, const float* w, int64_t B, int dim, double* out, cudaStream_t stream);
+
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 
@@ -553,10 +560,12 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
 
 // ---- kl / kl_ito gradient (sdes_adjoint.cu + the GEMM passes of sdes_grad.cu)
 static int kl_grad_setup(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, KParams& p, bool& simt) {
-    int rc = grad_setup(desc, g, p, simt);
+    int rc = validate(desc, false);
     if (rc != 0) return rc;
     if (wide_engine_needed(*desc))
         return fail(-8, "the kl gradient (backpropagation through time) is implemented on the fused engines: d <= %d, analytic target", SDES_MAX_DIM);
+    rc = grad_setup(desc, g, p, simt);
+    if (rc != 0) return rc;
     if (desc->target_kind == SDES_TARGET_GMM && desc->n_components > 1 && desc->ctrl_kind != SDES_CTRL_CLIPPED &&
         desc->ctrl_kind != SDES_CTRL_LERP_PRIOR && !(g->flags & (SDES_GRAD_TARGET_SCORE_CONST | SDES_GRAD_SCORE_DETACHED)))
         return fail(-8, "kl gradient with a %d-component GMM score inside the control needs SDES_GRAD_TARGET_SCORE_CONST "
@@ -672,6 +681,51 @@ int sdes_kl_weights(const float* rnd, int64_t batch, int mask_mode, float max_rn
     kl_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, stats, upstream, w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "kl weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_sample_gauss_prior(float* out, int64_t batch, int32_t dim, float mean, float std, int32_t truncated, float a, float b,
+                            uint64_t seed, uint64_t traj_offset, const float* uniforms, void* stream_) {
+    g_err[0] = 0;
+    if (!out) return fail(-5, "out is NULL");
+    if (batch < 0 || dim < 1) return fail(-3, "batch must be >= 0 and dim >= 1");
+    if (!(std > 0.f)) return fail(-3, "std must be positive");
+    if (truncated && !(a < b)) return fail(-3, "truncation bounds must satisfy a < b");
+    if (traj_offset + (uint64_t)batch > 0xFFFFFFFFull) return fail(-3, "traj_offset + batch exceeds the 32-bit Philox trajectory counter");
+    if (batch == 0) return 0;
+    cudaError_t e = launch_sample_prior(out, uniforms, batch, dim, mean, std, truncated, a, b, seed, traj_offset, reinterpret_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(-7, "prior sampling launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+size_t sdes_trainer_workspace_bytes(void) { return trainer_workspace_bytes(); }
+
+int sdes_trainer_step(const SdesTrainerStepDesc* d, void* stream_) {
+    g_err[0] = 0;
+    if (d == nullptr || d->struct_bytes != sizeof(SdesTrainerStepDesc)) return fail(-2, "SdesTrainerStepDesc is NULL or has the wrong struct_bytes");
+    if (d->n < 0) return fail(-3, "n < 0");
+    if (!d->params || !d->grads || !d->exp_avg || !d->exp_avg_sq || !d->state || !d->workspace) return fail(-5, "params/grads/exp_avg/exp_avg_sq/state/workspace must be non-NULL");
+    if (d->workspace_bytes < trainer_workspace_bytes()) return fail(-6, "workspace_bytes=%zu < required %zu", d->workspace_bytes, trainer_workspace_bytes());
+    if (!(d->beta1 >= 0.f && d->beta1 < 1.f) || !(d->beta2 >= 0.f && d->beta2 < 1.f)) return fail(-3, "Invalid beta parameter");
+    if (!(d->lr >= 0.f) || !(d->eps >= 0.f) || !(d->weight_decay >= 0.f)) return fail(-3, "Invalid lr / eps / weight_decay");
+    if (d->ema_shadow != nullptr && d->ema_update_every < 1) return fail(-3, "ema_update_every must be >= 1");
+    if (d->n == 0) return 0;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(d->workspace) + trainer_workspace_bytes() - 256, 0, 256, stream);
+    if (e == cudaSuccess) e = launch_trainer_step(*d, stream);
+    if (e != cudaSuccess) return fail(-7, "trainer step launch failed: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    return 0;
+}
+
+int sdes_eval_moments(const float* samples, const float* weights, int64_t batch, int32_t dim, double* out, void* stream_) {
+    g_err[0] = 0;
+    if (!samples || !out) return fail(-5, "samples/out NULL");
+    if (batch < 0 || dim < 1) return fail(-3, "batch must be >= 0 and dim >= 1");
+    cudaError_t e = launch_eval_moments(samples, weights, batch, dim, out, reinterpret_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(-7, "eval moments launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

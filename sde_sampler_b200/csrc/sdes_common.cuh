@@ -134,6 +134,24 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(-p, e, fmaxf(x, 0.0f));         // relu(x) - |x| Phi(-|x|)
 }
 
+// exact-erf GELU and its derivative Phi(x) + x phi(x) (autograd of torch.nn.GELU()), from the same A&S erfc
+__device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
+    const float ax = fabsf(x);
+    const float z = ax * 0.8493218002880191f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, z, 1.0f)));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    p *= t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z));  // exp(-x^2/2)
+    const float q = p * e;                                       // Phi(-|x|)
+    const float phi_cdf = x >= 0.f ? 1.0f - q : q;
+    y = x * phi_cdf;
+    dy = fmaf(x * 0.3989422804014327f, e, phi_cdf);
+}
+
 __device__ __forceinline__ float torch_lerp(float a, float b, float w) {
     // torch.lerp: w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)
     const float diff = b - a;

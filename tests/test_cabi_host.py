@@ -178,3 +178,57 @@ def test_gradient_and_integrator_entry_points_validate_without_gpu(lib):
     assert lib.sdes_langevin_integrate(C.byref(t), C.byref(ig), None) == -5
     t.dim = 100
     assert lib.sdes_integrate_workspace_bytes(C.byref(t)) == 0 and b"Langevin" in lib.sdes_last_error()
+
+
+def test_aux_struct_layouts_match_c_trainer_and_grad(tmp_path, lib):
+    """SdesTrainerStepDesc / SdesLvGradDesc: sizeof and offsetof from gcc equal the ctypes mirrors."""
+    src = tmp_path / "probe2.c"
+    lines = []
+    for cname, cls in (("SdesTrainerStepDesc", _cabi.TrainerStepDesc), ("SdesLvGradDesc", _cabi.LvGradDesc)):
+        lines.append(f'printf("{cname}.sizeof %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sdes_b200.h"\nint main(){' + "\n".join(lines) + "return 0;}")
+    exe = tmp_path / "probe2"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+    for cname, cls in (("SdesTrainerStepDesc", _cabi.TrainerStepDesc), ("SdesLvGradDesc", _cabi.LvGradDesc)):
+        assert int(out[f"{cname}.sizeof"]) == C.sizeof(cls)
+        for f, _ in cls._fields_:
+            assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
+
+
+def test_kl_grad_and_trainer_entry_points_validate(lib):
+    d = _valid_desc()
+    g = _cabi.LvGradDesc()
+    g.struct_bytes = C.sizeof(_cabi.LvGradDesc)
+    # a 40-component GMM score inside a Lerp control: the reference treats it as a constant of the graph
+    assert lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g)) == 0
+    assert b"SDES_GRAD_TARGET_SCORE_CONST" in lib.sdes_last_error()
+    g.flags = _cabi.GRAD_TARGET_SCORE_CONST
+    need_kl = lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g))
+    need_lv = lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g))
+    assert need_kl >= need_lv + 4 * d.n_steps * d.batch * d.dim   # the control cotangent of every (trajectory, step)
+    d.dim = 100  # wide engine: no backpropagation through time there
+    d.n_params += 2 * 64 * 50 + 50
+    assert lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g)) == 0
+    assert b"fused engines" in lib.sdes_last_error()
+    t = _cabi.TrainerStepDesc()
+    assert lib.sdes_trainer_step(C.byref(t), None) == -2
+    t.struct_bytes = C.sizeof(_cabi.TrainerStepDesc)
+    t.n = 8
+    assert lib.sdes_trainer_step(C.byref(t), None) == -5
+    assert lib.sdes_trainer_workspace_bytes() > 0
+    assert lib.sdes_sample_gauss_prior(None, 4, 2, 0.0, 1.0, 0, 0.0, 0.0, 0, 0, None, None) == -5
+    assert lib.sdes_eval_moments(None, None, 4, 2, None, None) == -5
+
+
+def test_trainer_has_no_cpu_path(lib):
+    from sde_sampler_b200 import FusedAdamEMA, eval_moments, sample_gauss_prior
+
+    with pytest.raises(_cabi.SdesError, match="CUDA device only"):
+        FusedAdamEMA([torch.nn.Parameter(torch.zeros(3))])
+    with pytest.raises(_cabi.SdesError, match="CUDA device only"):
+        sample_gauss_prior(4, 2, device="cpu")
+    with pytest.raises(_cabi.SdesError, match="CUDA device only"):
+        eval_moments(torch.zeros(4, 2))
