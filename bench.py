@@ -548,6 +548,48 @@ def main():
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
 
+    # ---- after the headline regions (the optimizer below changes the weights): the same workload with loss.method = kl
+    #      (backpropagation through time: reverse sweep csrc/sdes_adjoint.cu + the GEMM passes), and the complete training
+    #      iteration of Trainable.step (solver/base.py:399-454) with the fused optimizer tail (csrc/sdes_trainer.cu)
+    kl_ms, full_ms = None, None
+    try:
+        loss.method = "kl"
+        tm = []
+        for k in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for prm in ctrl_parameters(o["ctrl"]):
+                prm.grad = None
+            a.record()
+            v, _m = loss(ts, x0, o["terminal"], o["second"])
+            v.backward()
+            b.record()
+            torch.cuda.synchronize(device)
+            tm.append(a.elapsed_time(b))
+        kl_ms = statistics.median(tm[1:])
+    except Exception as exc:
+        kl_ms = f"failed: {type(exc).__name__}: {exc}"
+    finally:
+        loss.method = "lv"
+    try:
+        from sde_sampler_b200 import FusedAdamEMA
+        opt = FusedAdamEMA(ctrl_parameters(o["ctrl"]), lr=0.005, weight_decay=1e-7, grad_clip_norm=1.0,
+                           ema=dict(decay=0.9999, inv_gamma=1.0, power=0.9, update_after_step=2, update_every=1))
+        tm = []
+        for k in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            opt.zero_grad()
+            v, _m = loss(ts, x0, o["terminal"], o["second"])
+            v = v * (1.0 / DIM)  # scale_loss (conf/solver/oc_base.yaml:22)
+            v.backward()
+            opt.step(loss=v)
+            b.record()
+            torch.cuda.synchronize(device)
+            tm.append(a.elapsed_time(b))
+        full_ms = statistics.median(tm[1:])
+    except Exception as exc:
+        full_ms = f"failed: {type(exc).__name__}: {exc}"
+
     times = torch.tensor([total_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -586,7 +628,12 @@ def main():
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "train_step": {"what": "loss(ts, x0, ...) with grad + loss.backward(): rollout keeping xs, then the lv gradient "
                                    "(forward + dgrad + wgrad GEMMs over all B*T rows)", "ms": train_ms,
-                           "traj_steps_per_s": (world * traj_steps / (train_ms * 1e-3)) if isinstance(train_ms, float) else None},
+                           "traj_steps_per_s": (world * traj_steps / (train_ms * 1e-3)) if isinstance(train_ms, float) else None,
+                           "kl_ms": kl_ms, "kl_what": "same workload with loss.method=kl: rollout keeping xs, reverse sweep (discrete "
+                                                      "adjoint, fp32 FFMA) and the same GEMM passes",
+                           "full_iteration_ms": full_ms,
+                           "full_iteration_what": "zero_grad + lv loss + backward + sdes_trainer_step (grad check, clip_grad_norm_, "
+                                                  "Adam, EMA), no host sync inside"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
