@@ -116,7 +116,8 @@ def test_trainer_step_loss_check_and_state_roundtrip():
 
 
 def test_truncated_prior_matches_trunc_normal_transform():
-    """Same uniforms through nn.init.trunc_normal_'s op sequence (torch/nn/init.py) — tolerance 2e-6 (erfinv round-off)."""
+    """Same uniforms through nn.init.trunc_normal_'s op sequence (torch/nn/init.py) — tolerance 1e-4 absolute: erfinv is
+    ill-conditioned in the tails (the bounds sit at +-3.89 sigma); measured max |delta| 3.8e-5, 1e-6 in the bulk."""
     B, d, mean, std, q = 4096, 50, 0.0, 1.0, 1e-4
     a, b = torch.distributions.Normal(mean, std).icdf(torch.tensor([q / 2, 1 - q / 2])).tolist()   # distr/gauss.py:206-213
     u = torch.rand(B, d, generator=torch.Generator().manual_seed(5))
@@ -124,7 +125,9 @@ def test_truncated_prior_matches_trunc_normal_transform():
     ncdf = lambda x: (1.0 + math.erf(x / math.sqrt(2.0))) / 2.0  # noqa: E731
     lo, hi = ncdf((a - mean) / std), ncdf((b - mean) / std)
     ref = (u * (2 * hi - 1 - (2 * lo - 1)) + (2 * lo - 1)).erfinv().mul(std * math.sqrt(2.0)).add(mean).clamp(a, b)
-    assert (got - ref).abs().max().item() <= 2e-6 * (1 + ref.abs().max().item()) * 4
+    assert (got - ref).abs().max().item() <= 1e-4
+    bulk = ref.abs() < 2.5
+    assert (got - ref)[bulk].abs().max().item() <= 5e-6
     assert got.min().item() >= a and got.max().item() <= b
 
 
