@@ -247,6 +247,12 @@ int sdes_lv_traj_stats(const float* rnd, int64_t n_samples, int32_t traj_per_sam
 int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,
                     const double* stats, const float* upstream, float* w, void* stream);
 
+/* Cotangent of the lv_traj loss (losses/oc.py:78-84) with respect to rnd, layout as sdes_lv_traj_stats:
+ * w[t, i] = upstream * 2 (rnd[t, i] - mean_t rnd[., i]) / (traj_per_sample - 1) / kept_samples for kept samples i, else 0;
+ * `out3` are the (rank-combined) numbers of sdes_lv_traj_stats.  Input `w` of sdes_rollout_lv_grad. */
+int sdes_lv_traj_weights(const float* rnd, int64_t n_samples, int32_t traj_per_sample, int mask_mode, float max_rnd,
+                         const uint8_t* sample_mask, const double* out3, const float* upstream, float* w, void* stream);
+
 /* Cotangent of the kl loss (mean of the kept rnd, losses/oc.py:90) with respect to rnd: w[b] = upstream / n_kept for kept b,
  * 0 otherwise.  Input `w` of sdes_rollout_kl_grad. */
 int sdes_kl_weights(const float* rnd, int64_t batch, int mask_mode, float max_rnd, const uint8_t* sample_mask,

@@ -82,6 +82,11 @@ CASES = {
     "dis_lerp_multiwell5_klito": dict(target="multiwell", dim=5, sde="vp", prior="gauss", ctrl="lerp",
                                       clip_model=2.0, clip_score=3.0, gate_bias=1.0, gate_dim=5, loss="time_reversal",
                                       method="kl_ito", max_rnd=None, clip_target=30.0, timesteps=LIN(40), batch=48, seed=14),
+    # lv_traj (losses/oc.py:78-84): variance across the traj_per_sample trajectories of each initial point.  The fixture's x0
+    # is the repeated batch (3 stacked copies of 24 points); the training call is given the 24 points.
+    "dis_gmm2_lvtraj": dict(target="gmm40", dim=2, sde="vp", prior="gauss", ctrl="lerp",
+                            clip_model=1e4, clip_score=1e4, gate_bias=1.0, loss="time_reversal",
+                            method="lv_traj", traj_per_sample=3, max_rnd=None, timesteps=LIN(60), batch=72, seed=15),
 }
 
 # eval-mode variants: (case, compute_weights, return_traj)  — losses/oc.py:258-278, :371-392

@@ -39,7 +39,12 @@ def run_case(name: str, case: dict) -> dict:
     B, d = case["batch"], case["dim"]
     T = ts.shape[0] - 1
     torch.manual_seed(1000 + case.get("seed", 1))
-    x0 = built["prior"].sample((B,)).float()
+    tps = case.get("traj_per_sample", 1)
+    x0 = built["prior"].sample((B // tps,)).float()
+    if tps != 1:
+        # lv_traj: the fixture holds the batch as `__call__` repeats it (losses/oc.py:240-241): tps stacked copies of B / tps
+        # initial points, so that `simulate` / `compute_loss` see exactly what the reference's training call sees
+        x0 = x0.repeat(tps, 1, 1).reshape(-1, x0.shape[-1])
     # spread the initial points a little for Delta priors? No: keep the reference semantics.
     noise = philox.normal_noise(NOISE_SEED, B, T, d)
     noise_t = torch.from_numpy(noise)
@@ -70,7 +75,7 @@ def run_case(name: str, case: dict) -> dict:
     # --- gradient of the loss w.r.t. every control parameter by the reference's own autograd
     #     (`loss.backward()` of Trainable.step, solver/base.py:404-407), flattened in parameter-blob order.
     #     lv: the state is detached (one MLP backward over all rows); kl / kl_ito: backpropagation through time.
-    if method in ("lv", "kl", "kl_ito"):
+    if method in ("lv", "lv_traj", "kl", "kl_ito"):
         from sde_sampler_b200.spec import ctrl_parameters
 
         params = ctrl_parameters(built["ctrl"])

@@ -106,6 +106,7 @@ SYMBOLS = {
     "sdes_rollout_lv_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
     "sdes_kl_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
     "sdes_rollout_kl_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
+    "sdes_lv_traj_weights": (C.c_int, [_fp, C.c_int64, C.c_int32, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
     "sdes_kl_weights": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
     "sdes_sample_gauss_prior": (C.c_int, [_fp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
                                           C.c_uint64, C.c_uint64, _fp, C.c_void_p]),

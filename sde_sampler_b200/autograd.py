@@ -38,9 +38,13 @@ class LvLoss(torch.autograd.Function):
             raise RuntimeError("the trajectory of this loss value was overwritten by a later training call of the same "
                                "loss object; call backward() before the next forward (as Trainable.step does)")
         mode = _cabi.MASK_ISFINITE if lo.max_rnd is None else _cabi.MASK_MAX_RND
-        bptt = lo.method != "lv"  # kl / kl_ito: the state carries the graph -> reverse sweep first (sdes_rollout_kl_grad)
-        weights = engine.kl_weights if bptt else engine.lv_weights
-        w = weights(m["rnd"], m["stats"], mode, 0.0 if lo.max_rnd is None else lo.max_rnd, m["smask"], grad_out)
+        bptt = lo.method in ("kl", "kl_ito")  # the state carries the graph -> reverse sweep first (sdes_rollout_kl_grad)
+        max_rnd = 0.0 if lo.max_rnd is None else lo.max_rnd
+        if lo.method == "lv_traj":  # variance across each sample's trajectories (losses/oc.py:78-84); state detached like lv
+            w = engine.lv_traj_weights(m["rnd"], m["stats"], lo.traj_per_sample, mode, max_rnd, m["smask"], grad_out)
+        else:
+            weights = engine.kl_weights if bptt else engine.lv_weights
+            w = weights(m["rnd"], m["stats"], mode, max_rnd, m["smask"], grad_out)
         blob = torch.cat([p.detach().reshape(-1).float() for p in params])
         wide = engine.is_wide(m["spec"])  # wide engine: the forward kept what is needed inside its own workspace
         g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w, noise=m["noise"], seed=m["seed"],
@@ -66,9 +70,9 @@ class LvLoss(torch.autograd.Function):
 
 def wants_grad(loss_obj) -> bool:
     """True when the training call should return a loss with a grad_fn: grad mode on, trainable control parameters, and a
-    configuration the gradient kernels cover — lv: `sdes_rollout_lv_grad` (every engine); kl / kl_ito:
+    configuration the gradient kernels cover — lv / lv_traj: `sdes_rollout_lv_grad` (every engine); kl / kl_ito:
     `sdes_rollout_kl_grad` (fused engines: d <= 64, analytic target)."""
-    if not torch.is_grad_enabled() or loss_obj.method not in ("lv", "kl", "kl_ito"):
+    if not torch.is_grad_enabled():
         return False
     ctrl = loss_obj.generative_ctrl
     try:
@@ -78,7 +82,7 @@ def wants_grad(loss_obj) -> bool:
     dim = int(ctrl.base_model.input_embed.weight.shape[1])
     target = getattr(getattr(ctrl, "target_score", None), "__self__", None)
     wide = dim > _cabi.MAX_DIM or (target is not None and hasattr(target, "model"))
-    if wide and loss_obj.method != "lv":
+    if wide and loss_obj.method in ("kl", "kl_ito"):
         return False  # backpropagation through time on the wide engine is not built: plain value, no grad_fn
     gate = getattr(ctrl, "score_model", None)
     if wide and gate is not None and int(gate.out_layer.weight.shape[0]) != 1:

@@ -255,6 +255,32 @@ __global__ void lv_weights_kernel(const float* __restrict__ rnd, int64_t B, int 
     }
 }
 
+// d (lv_traj loss) / d rnd[t, i] (losses/oc.py:78-84): the loss is the mean over kept samples of the unbiased variance across
+// each sample's traj_per_sample trajectories
+__global__ void __launch_bounds__(256) lv_traj_weights_kernel(const float* __restrict__ rnd, int64_t B0, int tps, int mode, float max_rnd,
+                                                              const uint8_t* __restrict__ smask, const double* __restrict__ st3,
+                                                              const float* __restrict__ upstream, float* __restrict__ w) {
+    const double up = upstream != nullptr ? (double)upstream[0] : 1.0;
+    const double scale = up * 2.0 / ((double)tps - 1.0) / st3[1];
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B0; b += (int64_t)gridDim.x * blockDim.x) {
+        bool keep = true;
+        double s1 = 0.0;
+        for (int t = 0; t < tps; ++t) {
+            const int64_t i = (int64_t)t * B0 + b;
+            const float r = rnd[i];
+            bool k = mode == 2 ? true : (mode == 1 ? (r < max_rnd) : isfinite(r));
+            if (smask != nullptr) k = k && smask[i] != 0;
+            keep = keep && k;
+            s1 += (double)r;
+        }
+        const double mean = s1 / tps;
+        for (int t = 0; t < tps; ++t) {
+            const int64_t i = (int64_t)t * B0 + b;
+            w[i] = keep ? (float)(((double)rnd[i] - mean) * scale) : 0.f;
+        }
+    }
+}
+
 // d (kl loss) / d rnd_b = 1 / n_kept for kept b (mean of the kept entries, losses/oc.py:90), times the upstream scalar
 __global__ void kl_weights_kernel(const float* __restrict__ rnd, int64_t B, int mode, float max_rnd, const uint8_t* __restrict__ smask,
                                   const double* __restrict__ stats, const float* __restrict__ upstream, float* __restrict__ w) {
@@ -667,6 +693,22 @@ int sdes_lv_weights(const float* rnd, int64_t batch, int mask_mode, float max_rn
     lv_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, stats, upstream, w);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "lv weights launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_lv_traj_weights(const float* rnd, int64_t n_samples, int32_t traj_per_sample, int mask_mode, float max_rnd,
+                         const uint8_t* sample_mask, const double* out3, const float* upstream, float* w, void* stream_) {
+    g_err[0] = 0;
+    if (!rnd || !out3 || !w) return fail(-5, "rnd/out3/w NULL");
+    if (traj_per_sample < 2) return fail(-3, "Cannot compute variance over a single trajectory.");
+    if (mask_mode < 0 || mask_mode > 2) return fail(-3, "mask_mode must be 0, 1 or 2");
+    if (n_samples == 0) return 0;
+    const int blocks = (int)((n_samples + 255) / 256 < 592 ? (n_samples + 255) / 256 : 592);
+    lv_traj_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, n_samples, traj_per_sample, mask_mode, max_rnd,
+                                                                                        sample_mask, out3, upstream, w);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "lv_traj weights launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

@@ -404,6 +404,22 @@ def lv_weights(rnd: torch.Tensor, stats: torch.Tensor, mask_mode: int, max_rnd: 
     return w
 
 
+def lv_traj_weights(rnd: torch.Tensor, stats3: torch.Tensor, traj_per_sample: int, mask_mode: int, max_rnd: float = 0.0,
+                    sample_mask: torch.Tensor | None = None, upstream: torch.Tensor | None = None) -> torch.Tensor:
+    """d (lv_traj loss) / d rnd on the device (include/sdes_b200.h `sdes_lv_traj_weights`)."""
+    lib = _cabi.lib()
+    r = rnd.detach().reshape(-1).to(torch.float32).contiguous()
+    w = torch.empty_like(r)
+    m = None if sample_mask is None else sample_mask.reshape(-1).to(torch.uint8).contiguous()
+    up = None if upstream is None else upstream.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+    with torch.cuda.device(r.device):
+        stream = torch.cuda.current_stream(r.device).cuda_stream
+        _cabi.check(lib.sdes_lv_traj_weights(r.data_ptr(), r.numel() // traj_per_sample, traj_per_sample, mask_mode, float(max_rnd),
+                                             _ptr(m), stats3.data_ptr(), _ptr(up), w.data_ptr(), C.c_void_p(stream)),
+                    "sdes_lv_traj_weights")
+    return w
+
+
 def kl_weights(rnd: torch.Tensor, stats: torch.Tensor, mask_mode: int, max_rnd: float = 0.0,
                sample_mask: torch.Tensor | None = None, upstream: torch.Tensor | None = None) -> torch.Tensor:
     """d (kl loss) / d rnd on the device (include/sdes_b200.h `sdes_kl_weights`)."""

@@ -214,8 +214,12 @@ class FusedOCLoss:
                                           workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer,
                                           keep_for_grad=True)
             self._traj_version += 1
-            st = self._stats(rnd, x_T)
-            loss, metrics = self._loss_from_stats(st)
+            if self.method == "lv_traj":
+                loss, metrics = self._compute_loss_lv_traj(rnd, x_T)
+                st = self._lv_traj_stats
+            else:
+                st = self._stats(rnd, x_T)
+                loss, metrics = self._loss_from_stats(st)
             smask = None if self.filter_samples is None else self.filter_samples(x_T)
             out.update(loss=loss, metrics=metrics, stats=st, rnd=rnd, smask=smask, xs=xs, spec=spec, seed=seed,
                        traj_offset=off, noise=noise, samples=x_T, traj_version=self._traj_version)
@@ -249,6 +253,7 @@ class FusedOCLoss:
             import torch.distributed as dist
 
             dist.all_reduce(st, group=self.process_group)
+        self._lv_traj_stats = st  # (rank-combined) [sum of variances, kept samples, samples]: the backward's weights need [1]
         self.n_filtered += self.traj_per_sample * int((st[2] - st[1]).item())
         return (st[0] / st[1]).to(torch.float32), {"train/n_filtered_cumulative": self.n_filtered}
 
