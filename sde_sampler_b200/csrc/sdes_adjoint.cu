@@ -170,37 +170,6 @@ __device__ __forceinline__ void mlp_bwd_input(const float (&dnn)[DPAD], float (&
         if (k < dim) a[k] += dot64(w_in + k * C, v);
 }
 
-// a += H v with H the Hessian of the target log-density at x (the Jacobian of its analytic score).
-template <int DPAD>
-__device__ __forceinline__ void target_hvp_add(const SdesRolloutDesc& d, const float (&x)[DPAD], const float (&v)[DPAD],
-                                               float (&a)[DPAD], const TargetSmem& ts) {
-    if (d.target_kind == SDES_TARGET_GMM) {
-        // one component (Gauss / IsotropicGauss, distr/gauss.py:182-183, :222-223): score = (loc - x) / scale^2
-#pragma unroll
-        for (int j = 0; j < DPAD; ++j) a[j] = fmaf(-2.0f * ts.gmm_h[j], v[j], a[j]);
-    } else if (d.target_kind == SDES_TARGET_MULTIWELL) {
-        // distr/double_well.py:43-45, :174-179: -4 (y^2 - sep) y  ->  4 sep - 12 y^2;  Gaussian part: -1
-#pragma unroll
-        for (int j = 0; j < DPAD; ++j) {
-            const float y = x[j] - d.shift;
-            if (j < d.n_double_wells) a[j] = fmaf(4.0f * d.separation - 12.0f * y * y, v[j], a[j]);
-            else if (j < d.dim) a[j] -= v[j];
-        }
-    } else {
-        // distr/funnel.py:71-80
-        float sq = 0.f, xv = 0.f;
-#pragma unroll
-        for (int j = 1; j < DPAD; ++j) {
-            sq = fmaf(x[j], x[j], sq);
-            xv = fmaf(x[j], v[j], xv);
-        }
-        const float inv = expf(-x[0]);
-        a[0] += v[0] * (-1.0f / d.variance - 0.5f * sq * inv) + inv * xv;
-#pragma unroll
-        for (int j = 1; j < DPAD; ++j) a[j] += inv * (x[j] * v[0] - v[j]);
-    }
-}
-
 template <int DPAD>
 __global__ void __launch_bounds__(256, 1) kl_adjoint_kernel(const __grid_constant__ AdjArgs a_) {
     extern __shared__ __align__(16) float smem[];

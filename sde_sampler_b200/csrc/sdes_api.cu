@@ -31,7 +31,7 @@ cudaError_t launch_langevin(const IntegrateParams& a, cudaStream_t stream);
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
 int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err,
                        bool bptt, int sm_count);
-size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
+size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows, bool simt);
 int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err);
 
 // caller-side kernels (sdes_trainer.cu)
@@ -603,7 +603,7 @@ size_t sdes_kl_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGra
     KParams p;
     bool simt;
     if (kl_grad_setup(desc, g, p, simt) != 0) return 0;
-    return kl_grad_workspace_bytes(p.d, p.ws.total * (int64_t)sizeof(float), g->chunk_rows);
+    return kl_grad_workspace_bytes(p.d, p.ws.total * (int64_t)sizeof(float), g->chunk_rows, simt);
 }
 
 int sdes_rollout_kl_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream_) {
@@ -618,7 +618,7 @@ int sdes_rollout_kl_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
     if (desc->target_kind == SDES_TARGET_GMM && (!desc->gmm_loc || !desc->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");
     if (reinterpret_cast<uintptr_t>(desc->workspace) % 256 != 0) return fail(-5, "workspace must be 256-byte aligned");
     const int64_t fused = p.ws.total * (int64_t)sizeof(float);
-    const size_t need = kl_grad_workspace_bytes(p.d, fused, g->chunk_rows);
+    const size_t need = kl_grad_workspace_bytes(p.d, fused, g->chunk_rows, simt);
     if (need > desc->workspace_bytes) return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, need);
     if (desc->batch == 0) return 0;
     cudaError_t e = cudaSuccess;

@@ -35,12 +35,15 @@ struct GradPlan {
     int m_tiles;  // per full chunk
     Lin f_in, f_h[SDES_MAX_HIDDEN], f_out;   // forward operands
     Lin b_h[SDES_MAX_HIDDEN], b_out;         // transposed operands (dgrad)
+    Lin b_in;                                // kl sweep: transposed input layer (dgrad down to x)
+    int64_t adj;                             // kl sweep: the adjoint a_s = d loss / d x_s, fp32 (Bp, P)
+    int64_t dh_all[SDES_MAX_HIDDEN + 1];     // kl sweep: one delta_h image per layer for the whole chunk
     int64_t embb;                            // (T, 64): timestep_embed(s) + b_in
     int64_t ximg, a_img[SDES_MAX_HIDDEN + 1], gp_img[SDES_MAX_HIDDEN + 1], nn, dnn_img, dh_img[2], ones;
     int64_t total;
 };
 
-static void make_plan(const SdesRolloutDesc& d, int64_t chunk_rows_req, int64_t base, GradPlan& p) {
+static void make_plan(const SdesRolloutDesc& d, int64_t chunk_rows_req, int64_t base, GradPlan& p, bool bptt_tc = false) {
     p.d = d.dim;
     p.P = round_up(d.dim, 64);
     p.pc = p.P / 64;
@@ -79,6 +82,14 @@ static void make_plan(const SdesRolloutDesc& d, int64_t chunk_rows_req, int64_t 
     p.dnn_img = take(imgp);
     p.dh_img[0] = take(img1);
     p.dh_img[1] = take(img1);
+    p.adj = -1;
+    if (bptt_tc) {
+        lin(p.b_in, p.P, C, false);
+        p.adj = take(p.Bp * (int64_t)p.P * 4);
+        p.dh_all[0] = p.dh_img[0];
+        p.dh_all[1] = p.dh_img[1];
+        for (int l = 2; l <= p.nh; ++l) p.dh_all[l] = take(img1);
+    }
     p.total = o;
 }
 
@@ -121,6 +132,9 @@ struct CotArgs {
     const float* nn;          // (rows, P)
     const float* ones;
     const float* delta;       // kl / kl_ito: control cotangent (T, B, d) of the adjoint sweep (sdes_adjoint.cu); NULL = lv
+    float* adj;               // kl sweep on the tensor cores: adjoint (Bp, P) fp32, updated in place per step
+    uint32_t gflags;          // SDES_GRAD_*
+    int step;                 // kl sweep: the time step this launch handles
     uint8_t* dnn_img;
     float* grad_gate;         // (T, gate_dim) or NULL
     int P, pc, s0;
@@ -224,6 +238,231 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     }
     if (!want_gate) return;
     const float gmask = fabsf(ws[p.ws.gate + (int64_t)s * p.ws.dpad]) < c.cm ? 1.0f : 0.f;  // d clip(gate) / d gate (scalar gate)
+    if (d.gate_dim == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = gsum;
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.grad_gate + s, gmask * (s_red[0] + s_red[1] + s_red[2] + s_red[3]));
+    } else {
+        __syncthreads();
+        for (int j = tid; j < dim; j += blockDim.x) {
+            const float gm = fabsf(ws[p.ws.gate + (int64_t)s * p.ws.dpad + j]) < c.cm ? 1.0f : 0.f;
+            atomicAdd(a.grad_gate + (int64_t)s * dim + j, gm * s_gsum[j]);
+        }
+    }
+}
+
+// ---- kl / kl_ito reverse sweep with the control MLP on the tensor cores.  The math is that of sdes_adjoint.cu; here the
+// replayed forward of the chunk (a_img / gp_img / nn) already exists, so one step of the sweep is
+//     adj_step_kernel (thread per trajectory): control cotangent delta_s from a_{s+1}, w and the stored NN output -> the
+//         masked delta image of this step's row tiles, the gate gradient, and a <- a * (1 + mu dt | alpha_k) + the score
+//         term's own x-derivatives (+ reference-control term)
+//     nh + 2 dgrad GEMMs on this step's row tiles (x GELU'), the last one accumulating J_x NN^T delta into a (resid)
+// and the weight gradients are taken once per chunk from the per-layer delta images the sweep leaves behind.
+template <int DPAD>
+__global__ void __launch_bounds__(128) adj_init_kernel(const __grid_constant__ CotArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* smem = smem_f;
+    const KParams& p = a.kp;
+    const SdesRolloutDesc& d = p.d;
+    const float* ws = reinterpret_cast<const float*>(d.workspace);
+    const int dim = d.dim, K = d.n_components, tid = threadIdx.x;
+    const int K2 = (K + 1) & ~1;
+    float* s_mu = smem;
+    float* s_h = s_mu + K2 * DPAD;
+    float* s_c = s_h + K2 * DPAD;
+    float* s_prior = s_c + 64;
+    float* s_ref = s_prior + 2 * DPAD + 4;
+    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
+        s_mu[e] = ws[p.ws.gmm_mu + e];
+        s_h[e] = ws[p.ws.gmm_h + e];
+    }
+    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
+    for (int e = tid; e < 2 * DPAD + 4; e += blockDim.x) {
+        s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
+        s_ref[e] = e <= 2 * DPAD ? ws[p.ws.ref + e] : 0.f;
+    }
+    __syncthreads();
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
+    const int64_t b = (int64_t)blockIdx.x * 128 + tid, B = d.batch;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : 0;
+    const float wb = valid ? a.w[bb] : 0.f;
+    const bool dead = !(wb != 0.f);
+    float x[DPAD], tsc[DPAD];
+    const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), d.n_steps, bb);
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(xr.p + j * xr.stride) : 0.f;
+    const float lp = target_eval<DPAD, true>(d, x, tsc, tsm);
+    const float keep = fabsf(lp) <= d.clip_target ? 1.0f : 0.f;
+    float* arow = a.adj + b * a.P;
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j) {
+        float v = -keep * tsc[j];
+        if (d.loss_kind != SDES_LOSS_TIME_REVERSAL) v += (s_ref[j] - x[j]) * s_ref[DPAD + j];
+        arow[j] = (j < dim && !dead) ? wb * v : 0.f;
+    }
+    for (int j = DPAD; j < a.P; ++j) arow[j] = 0.f;
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(128) adj_step_kernel(const __grid_constant__ CotArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* smem = smem_f;
+    __shared__ float s_red[4];
+    const KParams& p = a.kp;
+    const SdesRolloutDesc& d = p.d;
+    const float* ws = reinterpret_cast<const float*>(d.workspace);
+    const int dim = d.dim, K = d.n_components, tid = threadIdx.x;
+    const int K2 = (K + 1) & ~1;
+    float* s_mu = smem;
+    float* s_h = s_mu + K2 * DPAD;
+    float* s_c = s_h + K2 * DPAD;
+    float* s_prior = s_c + 64;
+    float* s_gsum = s_prior + 2 * DPAD + 4;
+    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
+        s_mu[e] = ws[p.ws.gmm_mu + e];
+        s_h[e] = ws[p.ws.gmm_h + e];
+    }
+    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
+    for (int e = tid; e < 2 * DPAD + 4; e += blockDim.x) s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
+    for (int e = tid; e < DPAD; e += blockDim.x) s_gsum[e] = 0.f;
+    __syncthreads();
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_prior};
+
+    const int s = a.step, mt_step = blockIdx.x;
+    const int tiles_per_step = (int)(a.Bp / 128);
+    const int mt = (s - a.s0) * tiles_per_step + mt_step;  // row tile inside the chunk's images
+    const int64_t b = (int64_t)mt_step * 128 + tid, B = d.batch;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : 0;
+    const float wb = valid ? a.w[bb] : 0.f;
+    const bool dead = !(wb != 0.f);
+    const float* tab = ws + p.ws.tab + (int64_t)s * TAB_STRIDE;
+    const StepCoef c = make_step_coef(d, tab);
+    const float* gate_row = ws + p.ws.gate + (int64_t)s * p.ws.dpad;
+    const float lerp_w = tab[TAB_LERP_W];
+    const int ck = d.ctrl_kind;
+    const bool ito = (d.flags & SDES_F_COMPUTE_ITO) != 0;
+    const bool score_detached = (a.gflags & SDES_GRAD_SCORE_DETACHED) != 0 || ck == SDES_CTRL_CLIPPED;
+    const bool target_in_ctrl = ck == SDES_CTRL_SCORE || ck == SDES_CTRL_LERP || ck == SDES_CTRL_LERP_TARGET;
+    const bool target_hvp = target_in_ctrl && !score_detached && !(a.gflags & SDES_GRAD_TARGET_SCORE_CONST);
+    const bool prior_in_ctrl = ck == SDES_CTRL_LERP || ck == SDES_CTRL_LERP_PRIOR;
+    const bool want_gate = a.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && ck != SDES_CTRL_CLIPPED;
+
+    float x[DPAD];
+    const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(xr.p + j * xr.stride) : 0.f;
+    // score part: base = outer * clip(inner) (the gate's cotangent multiplies it), sc = base * gate, fac maps d g to d inner
+    float sc[DPAD], fac[DPAD], base[DPAD];
+    if (ck == SDES_CTRL_CLIPPED) {
+#pragma unroll
+        for (int j = 0; j < DPAD; ++j) sc[j] = fac[j] = base[j] = 0.f;
+    } else {
+        if (target_in_ctrl) {
+            target_eval<DPAD, true>(d, x, sc, tsm);
+        } else {
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) sc[j] = 0.f;
+        }
+        const float outer = (ck == SDES_CTRL_SCORE ? 1.0f : c.sigma) * d.scale_score;
+#pragma unroll
+        for (int j = 0; j < DPAD; ++j) {
+            const float ps = (s_prior[j] - x[j]) * s_prior[DPAD + j];
+            float inner;
+            if (ck == SDES_CTRL_LERP) inner = torch_lerp(ps, sc[j], lerp_w);
+            else if (ck == SDES_CTRL_LERP_PRIOR) inner = (1.0f - lerp_w) * ps;
+            else if (ck == SDES_CTRL_LERP_TARGET) inner = lerp_w * sc[j];
+            else inner = sc[j];
+            base[j] = outer * clipf(inner, d.clip_score);
+            sc[j] = base[j] * gate_row[j];
+            fac[j] = fabsf(inner) <= d.clip_score ? outer * gate_row[j] : 0.f;
+        }
+    }
+    const int64_t rr = (int64_t)mt * 128 + tid;
+    const float* nnrow = a.nn + rr * a.P;
+    float* arow = a.adj + b * a.P;
+    const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
+    const float* nrow = (ito && c.from_hbm) ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
+    const float a_mul = c.exp_int ? c.alpha_k : fmaf(c.mu, c.dt, 1.0f);
+    float cot[DPAD], an[DPAD];
+    float gsum = 0.f;
+#pragma unroll
+    for (int q = 0; q < DPAD / 4; ++q) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ito && 4 * q < dim) {
+            if (c.from_hbm) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < dim) ? nrow[4 * q + r] : 0.f;
+            } else {
+                const float4 n4 = normal4_call(c.k0, c.k1, traj, (uint32_t)s, (uint32_t)q);
+                e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = 4 * q + r;
+            const float nnj = (j < dim) ? nnrow[j] : 0.f;
+            const float ap = (j < dim) ? arow[j] : 0.f;
+            const float g = clipf(nnj, c.cm) + sc[j];
+            float dg, nx;
+            if (c.exp_int) {
+                dg = wb * (c.bb_ss * g + c.s_bk * e[r]) + ap * c.bb_ss;
+                nx = ap * a_mul;
+            } else {
+                const float iv = s_prior[DPAD + j];
+                const float gm = c.ref_ctrl ? g - c.sigma * ((s_prior[j] - x[j]) * iv) : g;
+                const float qj = wb * (gm * c.dt + e[r] * c.sqrt_dt);
+                dg = fmaf(ap, c.sigma * c.dt, qj);
+                nx = ap * a_mul;
+                if (c.ref_ctrl) nx = fmaf(qj, c.sigma * iv, nx);
+            }
+            if (dead || j >= dim) dg = 0.f;
+            an[j] = nx;
+            cot[j] = fabsf(nnj) <= c.cm ? dg : 0.f;  // d clip(NN) / d NN
+            if (d.gate_dim == 1) gsum = fmaf(dg, base[j], gsum);
+            else if (want_gate && dg != 0.f) atomicAdd(&s_gsum[j], dg * base[j]);
+            fac[j] *= dg;  // cotangent of inner_j
+        }
+    }
+    if (!score_detached) {
+        if (prior_in_ctrl) {
+            const float wp = 1.0f - lerp_w;
+#pragma unroll
+            for (int j = 0; j < DPAD; ++j) an[j] = fmaf(-wp * s_prior[DPAD + j], fac[j], an[j]);
+        }
+        if (target_hvp) {
+            if (ck != SDES_CTRL_SCORE) {
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j) fac[j] *= lerp_w;
+            }
+            target_hvp_add<DPAD>(d, x, fac, an, tsm);
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < DPAD; ++j)
+            if (j < dim) arow[j] = dead ? 0.f : an[j];
+    }
+    // masked delta image of this step's rows (K = P = 64, natural feature order)
+#pragma unroll
+    for (int k0 = 0; k0 < 64; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (k0 + q < DPAD) ? cot[(k0 + q < DPAD) ? k0 + q : 0] : 0.f;
+        uint4 hi, lo;
+        split_pair(v[0], v[1], hi.x, lo.x);
+        split_pair(v[2], v[3], hi.y, lo.y);
+        split_pair(v[4], v[5], hi.z, lo.z);
+        split_pair(v[6], v[7], hi.w, lo.w);
+        uint8_t* o = a.dnn_img + (int64_t)mt * a.pc * A_BLOCK + img_group_offset(tid, k0);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + A_HALF) = lo;
+    }
+    if (!want_gate) return;
+    const float gmask = fabsf(ws[p.ws.gate + (int64_t)s * p.ws.dpad]) < c.cm ? 1.0f : 0.f;
     if (d.gate_dim == 1) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
@@ -607,6 +846,35 @@ static cudaError_t launch_cot_t(const CotArgs& a, int m_tiles, cudaStream_t stre
     return cudaGetLastError();
 }
 
+template <int DPAD>
+static cudaError_t launch_adj_t(const CotArgs& a, int tiles_per_step, bool init, cudaStream_t stream) {
+    const int K2 = (a.kp.d.n_components + 1) & ~1;
+    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * (2 * DPAD + 4) + DPAD) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(adj_init_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(adj_step_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = smem <= 48 * 1024;  // above the default limit the attribute depends on K: set it every time
+    }
+    if (init) adj_init_kernel<DPAD><<<tiles_per_step, 128, smem, stream>>>(a);
+    else adj_step_kernel<DPAD><<<tiles_per_step, 128, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_adj(const CotArgs& a, int tiles_per_step, bool init, cudaStream_t stream) {
+    switch (a.kp.ws.dpad) {
+        case 4: return launch_adj_t<4>(a, tiles_per_step, init, stream);
+        case 8: return launch_adj_t<8>(a, tiles_per_step, init, stream);
+        case 12: return launch_adj_t<12>(a, tiles_per_step, init, stream);
+        case 16: return launch_adj_t<16>(a, tiles_per_step, init, stream);
+        case 32: return launch_adj_t<32>(a, tiles_per_step, init, stream);
+        case 52: return launch_adj_t<52>(a, tiles_per_step, init, stream);
+        case 64: return launch_adj_t<64>(a, tiles_per_step, init, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
 static cudaError_t launch_cot(const CotArgs& a, int m_tiles, cudaStream_t stream) {
     switch (a.kp.ws.dpad) {
         case 4: return launch_cot_t<4>(a, m_tiles, stream);
@@ -816,19 +1084,24 @@ static int64_t delta_floats(const SdesRolloutDesc& d) {
     return (int64_t)d.n_steps * d.batch * d.dim;
 }
 
-size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows) {
+// simt: the thread-per-trajectory sweep of sdes_adjoint.cu (needs the delta buffer); otherwise the sweep runs on the
+// tensor cores inside the chunk loop (needs the adjoint, W_in^T and one delta_h image per layer)
+size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows, bool simt) {
     GradPlan p;
-    make_plan(d, chunk_rows, align256(fused_bytes), p);
-    return (size_t)(align256(p.total) + delta_floats(d) * 4);
+    make_plan(d, chunk_rows, align256(fused_bytes), p, !simt);
+    return (size_t)(align256(p.total) + (simt ? delta_floats(d) * 4 : 0));
 }
 
-// bptt = false: lv (closed-form cotangent).  bptt = true: kl / kl_ito — the reverse sweep of sdes_adjoint.cu first writes
-// the control cotangent of every (trajectory, step) after the plan's scratch, then the same GEMM passes consume it.
+// bptt = false: lv (closed-form cotangent).  bptt = true: kl / kl_ito.  With simt the reverse sweep of sdes_adjoint.cu first
+// writes the control cotangent of every (trajectory, step) after the plan's scratch, then the same GEMM passes consume it;
+// otherwise the sweep is part of the chunk loop (chunks in reverse time order): per step adj_step_kernel + the dgrad GEMMs
+// on that step's row tiles, the weight gradients once per chunk.
 int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err,
                        bool bptt, int sm_count) {
     const SdesRolloutDesc& d = kp.d;
     GradPlan p;
-    make_plan(d, g.chunk_rows, align256(fused_bytes), p);
+    const bool bptt_tc = bptt && !simt;
+    make_plan(d, g.chunk_rows, align256(fused_bytes), p, bptt_tc);
     uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
     auto F = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
     int64_t launches = 0;
@@ -843,7 +1116,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     ++launches;
     GRAD_CHECK(cudaGetLastError());
     const float* delta = nullptr;
-    if (bptt) {
+    if (bptt && simt) {
         float* dl = F(align256(p.total));
         GRAD_CHECK(launch_kl_adjoint(kp, g.xs, g.w, dl, g.flags, sm_count, stream));
         ++launches;
@@ -877,6 +1150,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     GRAD_CHECK(image(p.f_out, blob + kp.bl.out_w, C, d.dim, C, 0));
     GRAD_CHECK(bias(p.f_out, blob + kp.bl.out_b, d.dim));
     GRAD_CHECK(image(p.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));
+    if (bptt_tc) GRAD_CHECK(image(p.b_in, blob + kp.bl.in_w, d.dim, d.dim, C, 1));
     GRAD_CHECK(cudaMemsetAsync(g.grad_params, 0, (size_t)d.n_params * 4, stream));
     GRAD_CHECK(cudaMemsetAsync(g.grad_emb, 0, (size_t)p.T * C * 4, stream));
     if (g.grad_gate != nullptr) GRAD_CHECK(cudaMemsetAsync(g.grad_gate, 0, (size_t)p.T * (d.gate_dim > 0 ? d.gate_dim : 1) * 4, stream));
@@ -914,7 +1188,16 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     };
 
     const int tiles_per_step = (int)(p.Bp / 128);
-    for (int ch = 0; ch < p.n_chunks; ++ch) {
+    CotArgs ca;
+    ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.delta = delta; ca.dnn_img = ws + p.dnn_img;
+    ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = 0; ca.Bp = p.Bp;
+    ca.adj = bptt_tc ? F(p.adj) : nullptr; ca.gflags = g.flags; ca.step = 0;
+    if (bptt_tc) {  // a_T: the terminal cost's gradient
+        GRAD_CHECK(launch_adj(ca, tiles_per_step, true, stream));
+        ++launches;
+    }
+    for (int chi = 0; chi < p.n_chunks; ++chi) {
+        const int ch = bptt_tc ? p.n_chunks - 1 - chi : chi;  // the sweep walks the chunks backwards in time
         const int s0 = ch * p.chunk_steps;
         const int ns = (s0 + p.chunk_steps <= p.T) ? p.chunk_steps : p.T - s0;
         const int m_tiles = ns * tiles_per_step;
@@ -937,16 +1220,45 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
             a.a_img = ws + p.a_img[p.nh]; a.out_f32 = F(p.nn);
             GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
         }
-        // ---- output cotangent and gate gradient
-        {
-            CotArgs ca;
-            ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.delta = delta; ca.dnn_img = ws + p.dnn_img;
-            ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = s0; ca.Bp = p.Bp;
-            GRAD_CHECK(launch_cot(ca, m_tiles, stream));
-            ++launches;
-        }
-        // ---- out layer: dW_out += delta_nn^T a_nh, db_out += colsum(delta_nn); delta_h[nh] = (delta_nn W_out) * GELU'(h_nh)
         float* gp = g.grad_params;
+        ca.s0 = s0;
+        if (bptt_tc) {
+            // ---- reverse sweep over the chunk's steps: delta_s, then the dgrad chain on this step's row tiles down to x
+            for (int s = s0 + ns - 1; s >= s0; --s) {
+                ca.step = s;
+                GRAD_CHECK(launch_adj(ca, tiles_per_step, false, stream));
+                ++launches;
+                const int64_t t0 = (int64_t)(s - s0) * tiles_per_step;
+                LinArgs a = base_args(p.b_out);
+                a.a_img = ws + p.dnn_img + t0 * p.pc * A_BLOCK; a.a_mt_stride = (int64_t)p.pc * A_BLOCK;
+                a.mul_img = ws + p.gp_img[p.nh] + t0 * A_BLOCK; a.mul_mt_stride = A_BLOCK;
+                a.out_img = ws + p.dh_all[p.nh] + t0 * A_BLOCK;
+                GRAD_CHECK(launch_linear(a, tiles_per_step, simt, stream, launches));
+                for (int l = p.nh - 1; l >= 0; --l) {
+                    a = base_args(p.b_h[l]);
+                    a.a_img = ws + p.dh_all[l + 1] + t0 * A_BLOCK; a.mul_img = ws + p.gp_img[l] + t0 * A_BLOCK; a.mul_mt_stride = A_BLOCK;
+                    a.out_img = ws + p.dh_all[l] + t0 * A_BLOCK;
+                    GRAD_CHECK(launch_linear(a, tiles_per_step, simt, stream, launches));
+                }
+                a = base_args(p.b_in);  // a_s += delta_h0 W_in: fp32 accumulation into the adjoint
+                a.a_img = ws + p.dh_all[0] + t0 * A_BLOCK; a.out_f32 = F(p.adj); a.resid = F(p.adj); a.ld_f32 = p.P;
+                GRAD_CHECK(launch_linear(a, tiles_per_step, simt, stream, launches));
+            }
+            // ---- weight gradients of the chunk from the delta images the sweep left behind
+            GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C));
+            GRAD_CHECK(colsum(ws + p.dnn_img, p.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0));
+            for (int l = p.nh - 1; l >= 0; --l) {
+                GRAD_CHECK(wgrad(ws + p.dh_all[l + 1], 1, ws + p.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C));
+                GRAD_CHECK(colsum(ws + p.dh_all[l + 1], 1, C, gp + kp.bl.h_b[l], m_tiles, 0, 0));
+            }
+            GRAD_CHECK(wgrad(ws + p.dh_all[0], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim));
+            GRAD_CHECK(colsum(ws + p.dh_all[0], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, tiles_per_step, C));
+            continue;
+        }
+        // ---- output cotangent and gate gradient
+        GRAD_CHECK(launch_cot(ca, m_tiles, stream));
+        ++launches;
+        // ---- out layer: dW_out += delta_nn^T a_nh, db_out += colsum(delta_nn); delta_h[nh] = (delta_nn W_out) * GELU'(h_nh)
         GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C));
         GRAD_CHECK(colsum(ws + p.dnn_img, p.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0));
         int cur = 0;
