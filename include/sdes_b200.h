@@ -186,10 +186,11 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
 /* Gradient of the kl / kl_ito losses with respect to the control network — `loss.backward()` of `Trainable.step`
  * (solver/base.py:404-407) for loss.method = kl | kl_ito.  Here the state is driven by the control WITH
  * its graph (`sde_ctrl = generative_ctrl`, losses/oc.py:180,:305,:421): backpropagation through time, done as a
- * discrete adjoint over the stored trajectory.  One reverse-sweep kernel (thread per trajectory, T steps, replayed
- * control + its input-gradient + the score part's analytic x-derivatives) writes the cotangent of the control at
- * every (trajectory, step) into the workspace; the parameter gradient is then the same batched tcgen05 pass as
- * sdes_rollout_lv_grad.  Same descriptors and outputs as sdes_rollout_lv_grad; `w` = d loss / d rnd_b
+ * discrete adjoint over the stored trajectory.  tcgen05 engine: the sweep runs inside the gradient's chunk loop (chunks
+ * in reverse time order) — per step one elementwise kernel (control cotangent, score-term x-derivatives) and the dgrad
+ * GEMM chain on that step's row tiles, accumulating into the fp32 adjoint; weight gradients once per chunk.  With
+ * SDES_F_MLP_SIMT: one thread-per-trajectory reverse-sweep kernel (fp32 FFMA) writes the cotangent of the control at
+ * every (trajectory, step) into the workspace and the batched pass of sdes_rollout_lv_grad consumes it.  Same descriptors and outputs as sdes_rollout_lv_grad; `w` = d loss / d rnd_b
  * (sdes_kl_weights); g->flags = SDES_GRAD_*.  Fused engines only (d <= SDES_MAX_DIM, analytic target); a GMM target
  * with more than one component requires SDES_GRAD_TARGET_SCORE_CONST (the reference's semantics) or
  * SDES_GRAD_SCORE_DETACHED. */

@@ -17,6 +17,8 @@
 // target's score is an autograd score evaluated WITHOUT create_graph (GMM: distr/base.py:130-137 as called from
 // reparam.py:60, :135), which the reference's autograd treats as a constant (SDES_GRAD_TARGET_SCORE_CONST).
 //
+// This is the sweep of the fp32-FFMA engine (SDES_F_MLP_SIMT) and the cross-check of the tensor-core sweep in sdes_grad.cu
+// (adj_step_kernel + per-step dgrad GEMMs), which is what the tcgen05 engine runs.
 // This kernel only produces delta (T, B, d) — the cotangent of the control at every (trajectory, step).  The
 // parameter gradient is then the SAME batched pass as for the lv loss (sdes_grad.cu: replayed forward, dgrad and
 // wgrad GEMMs on tcgen05 over all B*T rows) with delta in place of the closed-form lv cotangent.
