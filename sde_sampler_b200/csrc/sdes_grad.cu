@@ -18,6 +18,8 @@
 // d loss / d gate (T, gate_dim); the caller chains the last two through the two tiny time-embedding networks.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "sdes_linear.cuh"
 #include "sdes_step.cuh"
 #include "sdes_timeembed.cuh"
@@ -476,6 +478,180 @@ __global__ void __launch_bounds__(128) adj_step_kernel(const __grid_constant__ C
             atomicAdd(a.grad_gate + (int64_t)s * dim + j, gm * s_gsum[j]);
         }
     }
+}
+
+// ---- fused dgrad chain of the kl sweep: all n_hidden + 2 transposed layers of one step's row tile in ONE kernel.
+// Per 128-row tile: TMA brings the masked delta image in as the first A operand; every layer is 12 bf16 tcgen05 MMAs
+// (hi/lo split, K = 64) against its weight image, all of which stay resident in shared memory; the epilogue warps
+// multiply the accumulator by GELU'(h) (stored image), write the delta_h image the weight gradients need AND the same
+// 16-byte groups straight into the shared-memory A buffer of the next layer (the image layout is the canonical
+// no-swizzle K-major operand layout), so no delta_h is ever read back; the last layer (W_in^T) accumulates into the
+// fp32 adjoint.  One launch per time step instead of n_hidden + 2, no operand re-reads.  Layers are a dependency chain
+// per tile, so two CTAs share an SM and overlap each other's MMA / epilogue phases.
+struct ChainArgs {
+    const uint8_t* dnn_img;                       // [m_tile] blocks of A_BLOCK (K = P = 64)
+    const uint8_t* w_img[SDES_MAX_HIDDEN + 2];    // W_out^T, W_h[nh-1]^T, ..., W_h[0]^T, W_in^T: 16 KB each (hi | lo)
+    const uint8_t* gp_img[SDES_MAX_HIDDEN + 1];   // GELU'(h) image multiplying the output of layer i < L - 1
+    uint8_t* dh_img[SDES_MAX_HIDDEN + 1];         // delta_h image written by layer i < L - 1
+    float* adj;                                   // (rows, 64) fp32: += output of the last layer
+    int n_layers, m_tiles;
+};
+constexpr int CHAIN_THREADS = 192;
+constexpr uint32_t CHAIN_W_BYTES = 16384u;        // one 64 x 64 weight image
+
+static __global__ void __launch_bounds__(CHAIN_THREADS, 2) dgrad_chain_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t s_wfull, s_afull, s_acc, s_aready;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = a.n_layers;
+    uint8_t* s_a = smem;                  // A operand: hi | lo (32 KB)
+    uint8_t* s_w = smem + A_BLOCK;        // L weight images
+    if (warp == 1) {
+        tc::tmem_alloc(&s_tmem, 64u);
+        tc::tmem_relinquish();
+    }
+    if (tid == 0) {
+        tc::mbar_init(&s_wfull, 1);
+        tc::mbar_init(&s_afull, 1);
+        tc::mbar_init(&s_acc, 1);
+        tc::mbar_init(&s_aready, 128);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- control thread: TMA loads and MMA issue (the chain is sequential per tile anyway)
+            tc::mbar_arrive_expect_tx(&s_wfull, (uint32_t)L * CHAIN_W_BYTES);
+            for (int l = 0; l < L; ++l) tc::bulk_g2s(s_w + (size_t)l * CHAIN_W_BYTES, a.w_img[l], CHAIN_W_BYTES, &s_wfull);
+            tc::mbar_wait(&s_wfull, 0u);
+            const uint32_t idesc = tc::idesc_bf16(128, 64);
+            const uint32_t a_hi = tc::smem_u32(s_a), a_lo = a_hi + A_HALF;
+            uint32_t ph_a = 0u, ph_ready = 0u;
+            for (int tile = (int)blockIdx.x; tile < a.m_tiles; tile += (int)gridDim.x) {
+                tc::mbar_arrive_expect_tx(&s_afull, A_BLOCK);
+                const uint8_t* src = a.dnn_img + (int64_t)tile * A_BLOCK;
+                tc::bulk_g2s(s_a, src, A_HALF, &s_afull);
+                tc::bulk_g2s(s_a + A_HALF, src + A_HALF, A_HALF, &s_afull);
+                tc::mbar_wait(&s_afull, ph_a);
+                ph_a ^= 1u;
+                for (int l = 0; l < L; ++l) {
+                    if (l > 0) {  // the epilogue has drained the accumulator and written this layer's A operand
+                        tc::mbar_wait(&s_aready, ph_ready);
+                        ph_ready ^= 1u;
+                    }
+                    tc::fence_after();
+                    const uint32_t b_hi = tc::smem_u32(s_w + (size_t)l * CHAIN_W_BYTES), b_lo = b_hi + 8192u;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
+                        const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
+                        const uint64_t dbh = tc::smem_desc_kmajor(b_hi + (uint32_t)ks * 2048u, 1024u, 128u);
+                        const uint64_t dbl = tc::smem_desc_kmajor(b_lo + (uint32_t)ks * 2048u, 1024u, 128u);
+                        mma_f16_ss(tmem_base, dal, dbh, idesc, ks > 0 ? 1u : 0u);  // small terms first
+                        mma_f16_ss(tmem_base, dah, dbl, idesc, 1u);
+                        mma_f16_ss(tmem_base, dah, dbh, idesc, 1u);
+                    }
+                    tc::mma_commit(&s_acc);
+                }
+                // the last epilogue has read the accumulator (and the last MMAs have read A): the next tile may start
+                tc::mbar_wait(&s_aready, ph_ready);
+                ph_ready ^= 1u;
+            }
+        }
+    } else if (warp >= 2) {  // ---- epilogue warps: TMEM lane quadrant = warp % 4, thread = row
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t ph_acc = 0u;
+        for (int tile = (int)blockIdx.x; tile < a.m_tiles; tile += (int)gridDim.x) {
+            for (int l = 0; l < L; ++l) {
+                tc::mbar_wait(&s_acc, ph_acc);
+                ph_acc ^= 1u;
+                tc::fence_after();
+                if (l < L - 1) {
+                    const uint8_t* gpp = a.gp_img[l] + (int64_t)tile * A_BLOCK;
+                    uint8_t* dhp = a.dh_img[l] + (int64_t)tile * A_BLOCK;
+                    float v[8];
+                    uint4 mh, ml;
+                    tc::tmem_ld8(taddr, v);
+                    {
+                        const int64_t g0 = img_group_offset(r, 0);
+                        mh = *reinterpret_cast<const uint4*>(gpp + g0);
+                        ml = *reinterpret_cast<const uint4*>(gpp + g0 + A_HALF);
+                    }
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 8) {
+                        tc::wait_ld_tie<8>(v);
+                        float w[8], fh[8], fl[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] = v[e];
+                        unpack8(mh, fh);
+                        unpack8(ml, fl);
+                        if (c0 + 8 < 64) {  // next group's accumulator and GELU' loads are in flight during this group's math
+                            tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, v);
+                            const int64_t g1 = img_group_offset(r, c0 + 8);
+                            mh = *reinterpret_cast<const uint4*>(gpp + g1);
+                            ml = *reinterpret_cast<const uint4*>(gpp + g1 + A_HALF);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] *= fh[e] + fl[e];
+                        uint4 hi, lo;
+                        split_pair(w[0], w[1], hi.x, lo.x);
+                        split_pair(w[2], w[3], hi.y, lo.y);
+                        split_pair(w[4], w[5], hi.z, lo.z);
+                        split_pair(w[6], w[7], hi.w, lo.w);
+                        const int64_t goff = img_group_offset(r, c0);
+                        *reinterpret_cast<uint4*>(dhp + goff) = hi;
+                        *reinterpret_cast<uint4*>(dhp + goff + A_HALF) = lo;
+                        *reinterpret_cast<uint4*>(s_a + goff) = hi;          // next layer's A operand, same layout
+                        *reinterpret_cast<uint4*>(s_a + goff + A_HALF) = lo;
+                    }
+                    tc::fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor-core (async) proxy
+                } else {
+                    float* arow = a.adj + ((int64_t)tile * 128 + r) * 64;
+                    float v[8];
+                    tc::tmem_ld8(taddr, v);
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 8) {
+                        tc::wait_ld_tie<8>(v);
+                        float w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] = v[e];
+                        if (c0 + 8 < 64) tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, v);
+                        float4* op = reinterpret_cast<float4*>(arow + c0);
+                        float4 r0 = op[0], r1 = op[1];
+                        r0.x += w[0]; r0.y += w[1]; r0.z += w[2]; r0.w += w[3];
+                        r1.x += w[4]; r1.y += w[5]; r1.z += w[6]; r1.w += w[7];
+                        op[0] = r0;
+                        op[1] = r1;
+                    }
+                }
+                tc::fence_before();
+                mbar_arrive(&s_aready);
+            }
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 64u);
+}
+
+static cudaError_t launch_dgrad_chain(const ChainArgs& a, int sm_count, cudaStream_t stream) {
+    const size_t smem = A_BLOCK + (size_t)a.n_layers * CHAIN_W_BYTES;
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    int grid = a.m_tiles < sm_count * per_sm ? a.m_tiles : sm_count * per_sm;
+    if (grid < 1) grid = 1;
+    dgrad_chain_kernel<<<grid, CHAIN_THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 // column sums of a delta image: bias gradients, and per-time-step sums for d loss / d emb
@@ -1192,6 +1368,14 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.delta = delta; ca.dnn_img = ws + p.dnn_img;
     ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = 0; ca.Bp = p.Bp;
     ca.adj = bptt_tc ? F(p.adj) : nullptr; ca.gflags = g.flags; ca.step = 0;
+    // the fused dgrad chain serves the fused engines' shapes (P = 64: every transposed layer is one 64 x 64 block);
+    // SDES_KL_CHAIN=0 keeps the layer-by-layer launches (A/B measurements, cross-check)
+    static int chain_env = -1;
+    if (chain_env < 0) {
+        const char* e = getenv("SDES_KL_CHAIN");
+        chain_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const bool use_chain = bptt_tc && chain_env == 1 && p.pc == 1 && p.P == 64;
     if (bptt_tc) {  // a_T: the terminal cost's gradient
         GRAD_CHECK(launch_adj(ca, tiles_per_step, true, stream));
         ++launches;
@@ -1229,6 +1413,23 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
                 GRAD_CHECK(launch_adj(ca, tiles_per_step, false, stream));
                 ++launches;
                 const int64_t t0 = (int64_t)(s - s0) * tiles_per_step;
+                if (use_chain) {  // the whole dgrad chain of this step in one launch
+                    ChainArgs c;
+                    c.dnn_img = ws + p.dnn_img + t0 * A_BLOCK;
+                    c.n_layers = p.nh + 2;
+                    c.m_tiles = tiles_per_step;
+                    c.adj = F(p.adj);
+                    c.w_img[0] = ws + p.b_out.w_off;
+                    for (int l = p.nh - 1, i = 1; l >= 0; --l, ++i) c.w_img[i] = ws + p.b_h[l].w_off;
+                    c.w_img[p.nh + 1] = ws + p.b_in.w_off;
+                    for (int l = p.nh, i = 0; l >= 0; --l, ++i) {
+                        c.gp_img[i] = ws + p.gp_img[l] + t0 * A_BLOCK;
+                        c.dh_img[i] = ws + p.dh_all[l] + t0 * A_BLOCK;
+                    }
+                    GRAD_CHECK(launch_dgrad_chain(c, sm_count > 0 ? sm_count : 148, stream));
+                    ++launches;
+                    continue;
+                }
                 LinArgs a = base_args(p.b_out);
                 a.a_img = ws + p.dnn_img + t0 * p.pc * A_BLOCK; a.a_mt_stride = (int64_t)p.pc * A_BLOCK;
                 a.mul_img = ws + p.gp_img[p.nh] + t0 * A_BLOCK; a.mul_mt_stride = A_BLOCK;
