@@ -487,7 +487,8 @@ __global__ void __launch_bounds__(128) adj_step_kernel(const __grid_constant__ C
 // 16-byte groups straight into the shared-memory A buffer of the next layer (the image layout is the canonical
 // no-swizzle K-major operand layout), so no delta_h is ever read back; the last layer (W_in^T) accumulates into the
 // fp32 adjoint.  One launch per time step instead of n_hidden + 2, no operand re-reads.  Layers are a dependency chain
-// per tile, so two CTAs share an SM and overlap each other's MMA / epilogue phases.
+// per tile, so two CTAs share an SM and overlap each other's MMA / epilogue phases, and each row's 64 accumulator columns
+// are split over CHAIN_EPW epilogue warps to shorten every hop of the chain.
 struct ChainArgs {
     const uint8_t* dnn_img;                       // [m_tile] blocks of A_BLOCK (K = P = 64)
     const uint8_t* w_img[SDES_MAX_HIDDEN + 2];    // W_out^T, W_h[nh-1]^T, ..., W_h[0]^T, W_in^T: 16 KB each (hi | lo)
@@ -496,7 +497,11 @@ struct ChainArgs {
     float* adj;                                   // (rows, 64) fp32: += output of the last layer
     int n_layers, m_tiles;
 };
-constexpr int CHAIN_THREADS = 192;
+// epilogue warps per TMEM lane quadrant: a single warp runs an 8-column group's ~100 dependent instructions at ~6-10 cycles
+// each, so a row's 64 columns are shared by CHAIN_EPW warps (16 columns each) to shorten the per-layer hop of the chain
+constexpr int CHAIN_EPW = 4;
+constexpr int CHAIN_THREADS = 64 + 128 * CHAIN_EPW;
+constexpr int CHAIN_COLS = 64 / CHAIN_EPW, CHAIN_GROUPS = CHAIN_COLS / 8;
 constexpr uint32_t CHAIN_W_BYTES = 16384u;        // one 64 x 64 weight image
 
 static __global__ void __launch_bounds__(CHAIN_THREADS, 2) dgrad_chain_kernel(const __grid_constant__ ChainArgs a) {
@@ -515,7 +520,7 @@ static __global__ void __launch_bounds__(CHAIN_THREADS, 2) dgrad_chain_kernel(co
         tc::mbar_init(&s_wfull, 1);
         tc::mbar_init(&s_afull, 1);
         tc::mbar_init(&s_acc, 1);
-        tc::mbar_init(&s_aready, 128);
+        tc::mbar_init(&s_aready, 128 * CHAIN_EPW);
         tc::fence_mbar_init();
     }
     tc::fence_before();
@@ -564,38 +569,37 @@ static __global__ void __launch_bounds__(CHAIN_THREADS, 2) dgrad_chain_kernel(co
         }
     } else if (warp >= 2) {  // ---- epilogue warps: TMEM lane quadrant = warp % 4, thread = row
         const int q = warp & 3, r = q * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int c_lo = ((warp - 2) >> 2) * CHAIN_COLS;  // this warp's share of the row's columns
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c_lo;
         uint32_t ph_acc = 0u;
         for (int tile = (int)blockIdx.x; tile < a.m_tiles; tile += (int)gridDim.x) {
             for (int l = 0; l < L; ++l) {
-                tc::mbar_wait(&s_acc, ph_acc);
-                ph_acc ^= 1u;
-                tc::fence_after();
                 if (l < L - 1) {
+                    // this layer's GELU' row does not depend on the accumulator: all 16 loads are issued BEFORE waiting for
+                    // the MMAs, so their latency hides behind the tensor-core phase of the chain
                     const uint8_t* gpp = a.gp_img[l] + (int64_t)tile * A_BLOCK;
                     uint8_t* dhp = a.dh_img[l] + (int64_t)tile * A_BLOCK;
-                    float v[8];
-                    uint4 mh, ml;
-                    tc::tmem_ld8(taddr, v);
-                    {
-                        const int64_t g0 = img_group_offset(r, 0);
-                        mh = *reinterpret_cast<const uint4*>(gpp + g0);
-                        ml = *reinterpret_cast<const uint4*>(gpp + g0 + A_HALF);
-                    }
+                    uint4 mh[CHAIN_GROUPS], ml[CHAIN_GROUPS];
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 8) {
+                    for (int g = 0; g < CHAIN_GROUPS; ++g) {
+                        const int64_t go = img_group_offset(r, c_lo + 8 * g);
+                        mh[g] = *reinterpret_cast<const uint4*>(gpp + go);
+                        ml[g] = *reinterpret_cast<const uint4*>(gpp + go + A_HALF);
+                    }
+                    tc::mbar_wait(&s_acc, ph_acc);
+                    ph_acc ^= 1u;
+                    tc::fence_after();
+                    float v[8];
+                    tc::tmem_ld8(taddr, v);
+#pragma unroll
+                    for (int g = 0; g < CHAIN_GROUPS; ++g) {
                         tc::wait_ld_tie<8>(v);
                         float w[8], fh[8], fl[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) w[e] = v[e];
-                        unpack8(mh, fh);
-                        unpack8(ml, fl);
-                        if (c0 + 8 < 64) {  // next group's accumulator and GELU' loads are in flight during this group's math
-                            tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, v);
-                            const int64_t g1 = img_group_offset(r, c0 + 8);
-                            mh = *reinterpret_cast<const uint4*>(gpp + g1);
-                            ml = *reinterpret_cast<const uint4*>(gpp + g1 + A_HALF);
-                        }
+                        if (g < CHAIN_GROUPS - 1) tc::tmem_ld8(taddr + (uint32_t)(8 * g + 8), v);
+                        unpack8(mh[g], fh);
+                        unpack8(ml[g], fl);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) w[e] *= fh[e] + fl[e];
                         uint4 hi, lo;
@@ -603,30 +607,35 @@ static __global__ void __launch_bounds__(CHAIN_THREADS, 2) dgrad_chain_kernel(co
                         split_pair(w[2], w[3], hi.y, lo.y);
                         split_pair(w[4], w[5], hi.z, lo.z);
                         split_pair(w[6], w[7], hi.w, lo.w);
-                        const int64_t goff = img_group_offset(r, c0);
-                        *reinterpret_cast<uint4*>(dhp + goff) = hi;
-                        *reinterpret_cast<uint4*>(dhp + goff + A_HALF) = lo;
+                        const int64_t goff = img_group_offset(r, c_lo + 8 * g);
                         *reinterpret_cast<uint4*>(s_a + goff) = hi;          // next layer's A operand, same layout
                         *reinterpret_cast<uint4*>(s_a + goff + A_HALF) = lo;
+                        *reinterpret_cast<uint4*>(dhp + goff) = hi;
+                        *reinterpret_cast<uint4*>(dhp + goff + A_HALF) = lo;
                     }
                     tc::fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor-core (async) proxy
                 } else {
-                    float* arow = a.adj + ((int64_t)tile * 128 + r) * 64;
+                    float* arow = a.adj + ((int64_t)tile * 128 + r) * 64 + c_lo;
+                    float4 acc[2 * CHAIN_GROUPS];  // this warp's part of the adjoint row, fetched while the last layer's MMAs run
+#pragma unroll
+                    for (int g = 0; g < 2 * CHAIN_GROUPS; ++g) acc[g] = reinterpret_cast<const float4*>(arow)[g];
+                    tc::mbar_wait(&s_acc, ph_acc);
+                    ph_acc ^= 1u;
+                    tc::fence_after();
                     float v[8];
                     tc::tmem_ld8(taddr, v);
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 8) {
+                    for (int g = 0; g < CHAIN_GROUPS; ++g) {
                         tc::wait_ld_tie<8>(v);
                         float w[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) w[e] = v[e];
-                        if (c0 + 8 < 64) tc::tmem_ld8(taddr + (uint32_t)c0 + 8u, v);
-                        float4* op = reinterpret_cast<float4*>(arow + c0);
-                        float4 r0 = op[0], r1 = op[1];
+                        if (g < CHAIN_GROUPS - 1) tc::tmem_ld8(taddr + (uint32_t)(8 * g + 8), v);
+                        float4 r0 = acc[2 * g], r1 = acc[2 * g + 1];
                         r0.x += w[0]; r0.y += w[1]; r0.z += w[2]; r0.w += w[3];
                         r1.x += w[4]; r1.y += w[5]; r1.z += w[6]; r1.w += w[7];
-                        op[0] = r0;
-                        op[1] = r1;
+                        reinterpret_cast<float4*>(arow)[2 * g] = r0;
+                        reinterpret_cast<float4*>(arow)[2 * g + 1] = r1;
                     }
                 }
                 tc::fence_before();
