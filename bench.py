@@ -629,8 +629,9 @@ def main():
             "train_step": {"what": "loss(ts, x0, ...) with grad + loss.backward(): rollout keeping xs, then the lv gradient "
                                    "(forward + dgrad + wgrad GEMMs over all B*T rows)", "ms": train_ms,
                            "traj_steps_per_s": (world * traj_steps / (train_ms * 1e-3)) if isinstance(train_ms, float) else None,
-                           "kl_ms": kl_ms, "kl_what": "same workload with loss.method=kl: rollout keeping xs, reverse sweep (discrete "
-                                                      "adjoint, fp32 FFMA) and the same GEMM passes",
+                           "kl_ms": kl_ms, "kl_what": "same workload with loss.method=kl: rollout keeping xs, backpropagation through time as a "
+                                                      "discrete adjoint (per-step cotangent kernel + fused tcgen05 dgrad chain) "
+                                                      "inside the gradient's GEMM passes",
                            "full_iteration_ms": full_ms,
                            "full_iteration_what": "zero_grad + lv loss + backward + sdes_trainer_step (grad check, clip_grad_norm_, "
                                                   "Adam, EMA), no host sync inside"},
