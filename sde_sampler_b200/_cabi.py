@@ -36,6 +36,7 @@ F_KEEP_FOR_GRAD = 1 << 9
 
 GRAD_TARGET_SCORE_CONST = 1 << 0
 GRAD_SCORE_DETACHED = 1 << 1
+GRAD_LAYERWISE_SWEEP = 1 << 2
 
 MASK_ISFINITE, MASK_MAX_RND, MASK_ALL = 0, 1, 2
 

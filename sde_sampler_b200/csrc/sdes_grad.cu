@@ -1378,13 +1378,8 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = 0; ca.Bp = p.Bp;
     ca.adj = bptt_tc ? F(p.adj) : nullptr; ca.gflags = g.flags; ca.step = 0;
     // the fused dgrad chain serves the fused engines' shapes (P = 64: every transposed layer is one 64 x 64 block);
-    // SDES_KL_CHAIN=0 keeps the layer-by-layer launches (A/B measurements, cross-check)
-    static int chain_env = -1;
-    if (chain_env < 0) {
-        const char* e = getenv("SDES_KL_CHAIN");
-        chain_env = (e != nullptr && e[0] == '0') ? 0 : 1;
-    }
-    const bool use_chain = bptt_tc && chain_env == 1 && p.pc == 1 && p.P == 64;
+    // SDES_GRAD_LAYERWISE_SWEEP keeps the layer-by-layer launches (A/B measurements, cross-check)
+    const bool use_chain = bptt_tc && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && p.pc == 1 && p.P == 64;
     if (bptt_tc) {  // a_T: the terminal cost's gradient
         GRAD_CHECK(launch_adj(ca, tiles_per_step, true, stream));
         ++launches;

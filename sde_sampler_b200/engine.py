@@ -286,7 +286,7 @@ def kl_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, **kw):
 
 def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
-            params: torch.Tensor | None = None, chunk_rows: int = 0, bptt: bool = False):
+            params: torch.Tensor | None = None, chunk_rows: int = 0, bptt: bool = False, grad_flags: int = 0):
     """d loss / d theta of the log-variance loss for the rollout that produced `xs` (same spec / seed / traj_offset /
     noise).  Returns (grad_params blob, grad_emb (T,64), grad_gate (T,gate_dim) | None) — see include/sdes_b200.h
     `sdes_rollout_lv_grad`.  `bptt=True`: the kl / kl_ito gradient (`sdes_rollout_kl_grad`)."""
@@ -331,7 +331,7 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
         d.flags |= _cabi.F_NOISE_FROM_HBM
     g = _cabi.LvGradDesc()
     g.struct_bytes = C.sizeof(_cabi.LvGradDesc)
-    g.flags = kl_grad_flags(spec) if bptt else 0
+    g.flags = (kl_grad_flags(spec) | grad_flags) if bptt else 0
     grad_params = torch.empty_like(params)
     grad_emb = torch.empty((T, _cabi.CHANNELS), dtype=torch.float32, device=device)
     grad_gate = None

@@ -14,6 +14,7 @@ import torch
 
 from oracle import philox
 from oracle.cases import CASES, NOISE_SEED
+from sde_sampler_b200 import _cabi
 from sde_sampler_b200.spec import ctrl_parameters
 from sdes_test_helpers import build_from_spec
 
@@ -133,8 +134,8 @@ def test_lv_gradient_engines_agree_and_chunking_is_invariant(golden):
 def test_kl_gradient_is_additive_over_shards_and_engine_independent(golden):
     """Size-independent properties of the BPTT gradient at 4 096 trajectories of the cfg-3 configuration (funnel d=10, PIS,
     kl): the gradient is linear in the per-trajectory weights, so two half-batch calls (global Philox counters via
-    traj_offset) add up to the full-batch call; the tcgen05 and CUDA-core GEMM passes agree; the row chunking of the GEMM
-    passes does not matter."""
+    traj_offset) add up to the full-batch call; the tensor-core sweep (fused dgrad chain, or one GEMM launch per layer) and
+    the thread-per-trajectory fp32 sweep agree; the row chunking of the GEMM passes does not matter."""
     from sde_sampler_b200 import engine as eng
     from sde_sampler_b200.spec import extract_spec
 
@@ -151,6 +152,7 @@ def test_kl_gradient_is_additive_over_shards_and_engine_independent(golden):
         outs[engine] = eng.kl_grad(spec, xs, w, seed=11, engine=engine)
         if engine == "tcgen05":
             outs["chunked"] = eng.kl_grad(spec, xs, w, seed=11, engine=engine, chunk_rows=50000)
+            outs["layerwise"] = eng.kl_grad(spec, xs, w, seed=11, engine=engine, grad_flags=_cabi.GRAD_LAYERWISE_SWEEP)
             parts = []
             for h in range(2):
                 sl = slice(h * B // 2, (h + 1) * B // 2)
@@ -158,7 +160,7 @@ def test_kl_gradient_is_additive_over_shards_and_engine_independent(golden):
                 parts.append(eng.kl_grad(spec, xs_h, w[sl], seed=11, traj_offset=h * B // 2, engine=engine))
             outs["shards"] = tuple(None if a is None else a + c for a, c in zip(*parts))
     ref = outs["tcgen05"]
-    for key in ("simt", "chunked", "shards"):
+    for key in ("simt", "chunked", "layerwise", "shards"):
         for a, c in zip(ref, outs[key]):
             if a is None:
                 assert c is None
