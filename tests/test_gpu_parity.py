@@ -217,6 +217,41 @@ def test_full_size_properties_headline_config(golden, engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name,kind,ito", [("dis_gmm2_lv", "time_reversal", True), ("pis_funnel10_kl", "reference_sde", False)])
+def test_baseline_cfg2_cfg3_full_size(golden, name, kind, ito, engine):
+    """BASELINE configs[1] (GMM-40 d=2, basic_dis, lv, T=100, B=65 536) and configs[2] (funnel d=10, basic_pis, kl, T=200,
+    B=65 536) at full size: a strided sample of rows against the oracle on the same Philox stream, determinism, and the
+    two engines against each other on every row."""
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.spec import extract_spec
+
+    g = golden(name)
+    spec_d = g["spec"]
+    b = build_from_spec(spec_d, _dev(), engine=engine)
+    B, d, T = 65536, int(spec_d["dim"]), g["ts"].shape[0] - 1
+    assert (d, T) in ((2, 100), (10, 200))
+    if spec_d["prior"] is None:  # PIS: Delta prior at the origin (distr/delta.py:25-28)
+        x0 = torch.zeros(B, d, device=_dev())
+    else:
+        x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(12))
+    spec = extract_spec(b["loss"], kind, b["ts"], b["terminal"], b["second"], train=True, compute_ito=ito)
+    seed = 777
+    x_T, rnd, _ = eng.rollout(spec, x0, seed=seed, engine=engine)
+    x_T2, rnd2, _ = eng.rollout(spec, x0, seed=seed, engine=engine)
+    assert torch.equal(x_T, x_T2) and torch.equal(rnd, rnd2)
+    assert torch.isfinite(rnd).all() and torch.isfinite(x_T).all()
+    rows = np.arange(0, B, 1031)[:64]
+    noise = np.stack([philox.normal_block(seed, rows, i, d) for i in range(T)])
+    want_x, want_r, _ = oracle_rollout.rollout(spec_d, x0[rows].cpu().numpy(), noise=noise)
+    assert_close(x_T[rows].cpu().numpy(), want_x, 5e-4, 5e-4, "x_T sample")
+    assert_close(rnd[rows].cpu().numpy(), want_r, 5e-4, 5e-4, "rnd sample")
+    other = "simt" if engine == "tcgen05" else "tcgen05"
+    x_o, rnd_o, _ = eng.rollout(spec, x0, seed=seed, engine=other)
+    assert_close(x_T.cpu().numpy(), x_o.cpu().numpy(), 5e-4, 5e-4, "x_T engines")
+    assert_close(rnd.cpu().numpy(), rnd_o.cpu().numpy(), 5e-4, 5e-4, "rnd engines")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_filter_samples_is_applied_like_the_reference(golden, engine):
     """filter_samples (target.filter in the solver, solver/oc.py:152): mask = filter(x_T) & (rnd < max_rnd), the loss is
     the variance of the kept rnd and n_filtered counts the dropped ones (losses/oc.py:50-92)."""
