@@ -165,6 +165,16 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
     for (int e = tid; e < 2 * DPAD + 4; e += blockDim.x) s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
     for (int e = tid; e < DPAD; e += blockDim.x) s_gsum[e] = 0.f;
+    // this tile's rows of the network output, read with coalesced segments and transposed through shared memory (a thread
+    // reading its own 256-byte-strided row touches 32 sectors per load); row stride DPAD + 1 keeps the banks distinct
+    float* s_nn = s_gsum + DPAD;
+    {
+        const float* src = a.nn + (int64_t)blockIdx.x * 128 * a.P;
+        for (int e = tid; e < 128 * dim; e += blockDim.x) {
+            const int r = e / dim, j = e - r * dim;
+            s_nn[r * (DPAD + 1) + j] = src[(int64_t)r * a.P + j];
+        }
+    }
     __syncthreads();
     TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_prior};
 
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     const TrajRef dref = traj_ref(d, const_cast<float*>(bptt ? a.delta : a.xs), s, bb);
     const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
     const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
-    const float* nnrow = a.nn + rr * a.P;
+    const float* nnrow = s_nn + tid * (DPAD + 1);
     const bool want_gate = a.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
     float sc[DPAD];
     if (want_gate) {
@@ -330,12 +340,25 @@ __global__ void __launch_bounds__(128) adj_step_kernel(const __grid_constant__ C
     for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
     for (int e = tid; e < 2 * DPAD + 4; e += blockDim.x) s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
     for (int e = tid; e < DPAD; e += blockDim.x) s_gsum[e] = 0.f;
-    __syncthreads();
-    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_prior};
-
     const int s = a.step, mt_step = blockIdx.x;
     const int tiles_per_step = (int)(a.Bp / 128);
     const int mt = (s - a.s0) * tiles_per_step + mt_step;  // row tile inside the chunk's images
+    // this tile's rows of the network output and of the adjoint, transposed through shared memory (coalesced segments in,
+    // conflict-free rows out: stride DPAD + 1); the updated adjoint goes back the same way
+    float* s_nn = s_gsum + DPAD;
+    float* s_adj = s_nn + 128 * (DPAD + 1);
+    {
+        const float* src = a.nn + (int64_t)mt * 128 * a.P;
+        const float* asrc = a.adj + (int64_t)mt_step * 128 * a.P;
+        for (int e = tid; e < 128 * dim; e += blockDim.x) {
+            const int r = e / dim, j = e - r * dim;
+            s_nn[r * (DPAD + 1) + j] = src[(int64_t)r * a.P + j];
+            s_adj[r * (DPAD + 1) + j] = asrc[(int64_t)r * a.P + j];
+        }
+    }
+    __syncthreads();
+    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_prior};
+
     const int64_t b = (int64_t)mt_step * 128 + tid, B = d.batch;
     const bool valid = b < B;
     const int64_t bb = valid ? b : 0;
@@ -383,9 +406,8 @@ __global__ void __launch_bounds__(128) adj_step_kernel(const __grid_constant__ C
             fac[j] = fabsf(inner) <= d.clip_score ? outer * gate_row[j] : 0.f;
         }
     }
-    const int64_t rr = (int64_t)mt * 128 + tid;
-    const float* nnrow = a.nn + rr * a.P;
-    float* arow = a.adj + b * a.P;
+    const float* nnrow = s_nn + tid * (DPAD + 1);
+    float* arow = s_adj + tid * (DPAD + 1);
     const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
     const float* nrow = (ito && c.from_hbm) ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
     const float a_mul = c.exp_int ? c.alpha_k : fmaf(c.mu, c.dt, 1.0f);
@@ -443,10 +465,16 @@ __global__ void __launch_bounds__(128) adj_step_kernel(const __grid_constant__ C
             target_hvp_add<DPAD>(d, x, fac, an, tsm);
         }
     }
-    if (valid) {
 #pragma unroll
-        for (int j = 0; j < DPAD; ++j)
-            if (j < dim) arow[j] = dead ? 0.f : an[j];
+    for (int j = 0; j < DPAD; ++j)
+        if (j < dim) arow[j] = (dead || !valid) ? 0.f : an[j];
+    __syncthreads();
+    {
+        float* adst = a.adj + (int64_t)mt_step * 128 * a.P;
+        for (int e = tid; e < 128 * dim; e += blockDim.x) {
+            const int r = e / dim, j = e - r * dim;
+            adst[(int64_t)r * a.P + j] = s_adj[r * (DPAD + 1) + j];
+        }
     }
     // masked delta image of this step's rows (K = P = 64, natural feature order)
 #pragma unroll
@@ -1024,7 +1052,7 @@ static cudaError_t launch_time_embed_grads(const KParams& kp, const SdesLvGradDe
 template <int DPAD>
 static cudaError_t launch_cot_t(const CotArgs& a, int m_tiles, cudaStream_t stream) {
     const int K2 = (a.kp.d.n_components + 1) & ~1;
-    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * DPAD + 4 + DPAD) * sizeof(float);
+    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * DPAD + 4 + DPAD + 128 * (DPAD + 1)) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cotangent_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cotangent_kernel<DPAD><<<m_tiles, 128, smem, stream>>>(a);
@@ -1034,13 +1062,13 @@ static cudaError_t launch_cot_t(const CotArgs& a, int m_tiles, cudaStream_t stre
 template <int DPAD>
 static cudaError_t launch_adj_t(const CotArgs& a, int tiles_per_step, bool init, cudaStream_t stream) {
     const int K2 = (a.kp.d.n_components + 1) & ~1;
-    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * (2 * DPAD + 4) + DPAD) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * (2 * DPAD + 4) + DPAD + 2 * 128 * (DPAD + 1)) * sizeof(float);
+    static size_t attr_bytes = 0;  // per DPAD instantiation; the footprint also depends on the number of GMM components
+    if (smem > attr_bytes) {
         cudaError_t e = cudaFuncSetAttribute(adj_init_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(adj_step_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = smem <= 48 * 1024;  // above the default limit the attribute depends on K: set it every time
+        attr_bytes = smem;
     }
     if (init) adj_init_kernel<DPAD><<<tiles_per_step, 128, smem, stream>>>(a);
     else adj_step_kernel<DPAD><<<tiles_per_step, 128, smem, stream>>>(a);
