@@ -733,6 +733,8 @@ struct WgradArgs {
     const uint8_t* a_img; int a_chunks;   // activation image
     int m_tiles;
     float* dw; int ldw;                   // row-major (out, in) gradient, += via atomics
+    float* db;                            // bias gradient (column sums of delta), += via atomics; NULL = not wanted.  Comes
+                                          // out of the same pass as one extra N = 16 MMA per k-step against a block of ones
     int n_valid, k_valid;
     int n_planar, k_planar, Hp;           // wide engine: image feature index -> natural index (2 (p % Hp) + p / Hp)
 };
@@ -742,6 +744,8 @@ __device__ __forceinline__ uint32_t idesc_bf16_mn(int M, int N) {
 }
 
 constexpr int WG_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: one TMEM lane quadrant each
+constexpr uint32_t WG_ONES_BYTES = 4096u;  // MN-major B operand of ones: 2 feature groups x 2048 B
+constexpr size_t WG_SMEM = 3 * 2 * (size_t)A_BLOCK + WG_ONES_BYTES;
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_b[];
@@ -754,9 +758,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
     const int pair = blockIdx.x, cd = pair / a.a_chunks, ca = pair % a.a_chunks;
     const int split = blockIdx.y, n_split = gridDim.y;
     const int n_my = a.m_tiles > split ? (a.m_tiles - split + n_split - 1) / n_split : 0;
+    const bool want_db = a.db != nullptr && ca == 0;
+    uint8_t* s_ones = smem + (size_t)STAGES * STAGE_BYTES;
+    if (want_db) {
+        for (int e = tid; e < (int)(WG_ONES_BYTES / 4); e += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[e] = 0x3F803F80u;  // bf16 1.0 pairs
+        tc::fence_proxy_async();
+    }
 
     if (warp == 1) {
-        tc::tmem_alloc(&s_tmem, 64);
+        tc::tmem_alloc(&s_tmem, 128);
         tc::tmem_relinquish();
     }
     if (tid == 0) {
@@ -790,7 +800,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
             }
         } else if (warp == 1) {
             if (lane == 0) {
-                const uint32_t idesc = idesc_bf16_mn(128, 64);
+                const uint32_t idesc = idesc_bf16_mn(128, 64), idesc1 = idesc_bf16_mn(128, 16);
+                const uint32_t ones = tc::smem_u32(s_ones);
                 for (int i = 0; i < n_my; ++i) {
                     const int s = i % STAGES, it = i / STAGES;
                     tc::mbar_wait(&s_full[s], (uint32_t)(it & 1));
@@ -803,6 +814,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
                         const uint64_t dbl = tc::smem_desc_kmajor(al + (uint32_t)ks * 256u, 128u, 2048u);
                         mma_f16_ss(tmem_d, da, dbl, idesc, (i > 0 || ks > 0) ? 1u : 0u);
                         mma_f16_ss(tmem_d, da, dbh, idesc, 1u);
+                        if (want_db)  // column sums of delta over these 16 rows: every column of the extra tile holds them
+                            mma_f16_ss(tmem_d + 64u, da, tc::smem_desc_kmajor(ones, 128u, 2048u), idesc1, (i > 0 || ks > 0) ? 1u : 0u);
                     }
                     tc::mma_commit(&s_empty[s]);
                 }
@@ -826,11 +839,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_mma_kernel(const __grid_c
                     }
                 }
             }
+            if (want_db) {
+                float v[8];
+                tc::tmem_ld8(taddr + 64u, v);
+                tc::wait_ld_tie<8>(v);
+                if (n < a.n_valid && v[0] != 0.f) atomicAdd(a.db + n, v[0]);  // hi row (r < 64) and lo row (r >= 64) both add
+            }
         }
     }
     tc::fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_d, 64);
+    if (warp == 1) tc::tmem_dealloc(tmem_d, 128);
 }
 
 // the same contraction on the CUDA cores (SDES_F_MLP_SIMT cross-check)
@@ -1188,13 +1207,14 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
     };
     static bool attr_set = false;
     if (!attr_set) {
-        GRADW_CHECK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * (int)A_BLOCK));
+        GRADW_CHECK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
         attr_set = true;
     }
     auto wgrad = [&](const uint8_t* d_img, int d_chunks, const uint8_t* a_img, int a_chunks, int m_tiles, float* dw, int ldw, int n_valid,
                      int k_valid, int n_planar, int k_planar) {
         WgradArgs wa;
         wa.d_img = d_img; wa.d_chunks = d_chunks; wa.a_img = a_img; wa.a_chunks = a_chunks; wa.m_tiles = m_tiles; wa.dw = dw; wa.ldw = ldw;
+        wa.db = nullptr;
         wa.n_valid = n_valid; wa.k_valid = k_valid; wa.n_planar = n_planar; wa.k_planar = k_planar; wa.Hp = v.Hp;
         const int pairs = d_chunks * a_chunks;
         int splits = 296 / pairs;
@@ -1202,7 +1222,7 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
         if (splits < 1) splits = 1;
         ++launches;
         if (simt) wgrad_simt_kernel<<<dim3(pairs, splits), 64, 0, stream>>>(wa);
-        else wgrad_mma_kernel<<<dim3(pairs, splits), WG_THREADS, 3 * 2 * A_BLOCK, stream>>>(wa);
+        else wgrad_mma_kernel<<<dim3(pairs, splits), WG_THREADS, WG_SMEM, stream>>>(wa);
         return cudaGetLastError();
     };
     auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride, int planar) {
@@ -1378,12 +1398,21 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     };
     static bool attr_set = false;
     if (!attr_set) {
-        GRAD_CHECK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * (int)A_BLOCK));
+        GRAD_CHECK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
         attr_set = true;
     }
-    auto wgrad = [&](const uint8_t* d_img, int d_chunks, const uint8_t* a_img, int a_chunks, int m_tiles, float* dw, int ldw, int n_valid, int k_valid) {
+    auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride) {
+        colsum_kernel<<<m_tiles, 128, 0, stream>>>(img, n_chunks, n_valid, out, mt_div, mt_stride, 0, 64);
+        ++launches;
+        return cudaGetLastError();
+    };
+    // dW += delta^T a over the chunk's rows; db (may be NULL) += column sums of delta — on the tensor cores inside the same
+    // kernel (one extra N = 16 MMA per k-step against a block of ones), as a separate pass on the CUDA-core engine
+    auto wgrad = [&](const uint8_t* d_img, int d_chunks, const uint8_t* a_img, int a_chunks, int m_tiles, float* dw, int ldw, int n_valid,
+                     int k_valid, float* db) {
         WgradArgs wa;
         wa.d_img = d_img; wa.d_chunks = d_chunks; wa.a_img = a_img; wa.a_chunks = a_chunks; wa.m_tiles = m_tiles; wa.dw = dw; wa.ldw = ldw;
+        wa.db = simt ? nullptr : db;
         wa.n_valid = n_valid; wa.k_valid = k_valid; wa.n_planar = 0; wa.k_planar = 0; wa.Hp = 64;
         const int pairs = d_chunks * a_chunks;
         int splits = 296 / pairs;
@@ -1391,13 +1420,10 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         if (splits < 1) splits = 1;
         ++launches;
         if (simt) wgrad_simt_kernel<<<dim3(pairs, splits), 64, 0, stream>>>(wa);
-        else wgrad_mma_kernel<<<dim3(pairs, splits), WG_THREADS, 3 * 2 * A_BLOCK, stream>>>(wa);
-        return cudaGetLastError();
-    };
-    auto colsum = [&](const uint8_t* img, int n_chunks, int n_valid, float* out, int m_tiles, int mt_div, int64_t mt_stride) {
-        colsum_kernel<<<m_tiles, 128, 0, stream>>>(img, n_chunks, n_valid, out, mt_div, mt_stride, 0, 64);
-        ++launches;
-        return cudaGetLastError();
+        else wgrad_mma_kernel<<<dim3(pairs, splits), WG_THREADS, WG_SMEM, stream>>>(wa);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess && simt && db != nullptr) e = colsum(d_img, d_chunks, n_valid, db, m_tiles, 0, 0);
+        return e;
     };
 
     const int tiles_per_step = (int)(p.Bp / 128);
@@ -1478,13 +1504,10 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
                 GRAD_CHECK(launch_linear(a, tiles_per_step, simt, stream, launches));
             }
             // ---- weight gradients of the chunk from the delta images the sweep left behind
-            GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C));
-            GRAD_CHECK(colsum(ws + p.dnn_img, p.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0));
-            for (int l = p.nh - 1; l >= 0; --l) {
-                GRAD_CHECK(wgrad(ws + p.dh_all[l + 1], 1, ws + p.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C));
-                GRAD_CHECK(colsum(ws + p.dh_all[l + 1], 1, C, gp + kp.bl.h_b[l], m_tiles, 0, 0));
-            }
-            GRAD_CHECK(wgrad(ws + p.dh_all[0], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim));
+            GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C, gp + kp.bl.out_b));
+            for (int l = p.nh - 1; l >= 0; --l)
+                GRAD_CHECK(wgrad(ws + p.dh_all[l + 1], 1, ws + p.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C, gp + kp.bl.h_b[l]));
+            GRAD_CHECK(wgrad(ws + p.dh_all[0], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim, nullptr));
             GRAD_CHECK(colsum(ws + p.dh_all[0], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, tiles_per_step, C));
             continue;
         }
@@ -1492,8 +1515,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         GRAD_CHECK(launch_cot(ca, m_tiles, stream));
         ++launches;
         // ---- out layer: dW_out += delta_nn^T a_nh, db_out += colsum(delta_nn); delta_h[nh] = (delta_nn W_out) * GELU'(h_nh)
-        GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C));
-        GRAD_CHECK(colsum(ws + p.dnn_img, p.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0));
+        GRAD_CHECK(wgrad(ws + p.dnn_img, p.pc, ws + p.a_img[p.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C, gp + kp.bl.out_b));
         int cur = 0;
         {
             LinArgs a = base_args(p.b_out);
@@ -1503,15 +1525,14 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         }
         for (int l = p.nh - 1; l >= 0; --l) {
             // delta_h[l+1] is in dh_img[cur]: gradients of hidden layer l, then delta_h[l]
-            GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C));
-            GRAD_CHECK(colsum(ws + p.dh_img[cur], 1, C, gp + kp.bl.h_b[l], m_tiles, 0, 0));
+            GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C, gp + kp.bl.h_b[l]));
             LinArgs a = base_args(p.b_h[l]);
             a.a_img = ws + p.dh_img[cur]; a.mul_img = ws + p.gp_img[l]; a.mul_mt_stride = A_BLOCK; a.out_img = ws + p.dh_img[1 - cur];
             GRAD_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
             cur = 1 - cur;
         }
         // ---- input layer: dW_in += delta_h0^T x ; d emb[s] += per-step column sums of delta_h0
-        GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim));
+        GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim, nullptr));
         GRAD_CHECK(colsum(ws + p.dh_img[cur], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, tiles_per_step, C));
     }
     GRAD_CHECK(launch_time_embed_grads(kp, g, stream, launches));
