@@ -165,16 +165,6 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
     for (int e = tid; e < 2 * DPAD + 4; e += blockDim.x) s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
     for (int e = tid; e < DPAD; e += blockDim.x) s_gsum[e] = 0.f;
-    // this tile's rows of the network output, read with coalesced segments and transposed through shared memory (a thread
-    // reading its own 256-byte-strided row touches 32 sectors per load); row stride DPAD + 1 keeps the banks distinct
-    float* s_nn = s_gsum + DPAD;
-    {
-        const float* src = a.nn + (int64_t)blockIdx.x * 128 * a.P;
-        for (int e = tid; e < 128 * dim; e += blockDim.x) {
-            const int r = e / dim, j = e - r * dim;
-            s_nn[r * (DPAD + 1) + j] = src[(int64_t)r * a.P + j];
-        }
-    }
     __syncthreads();
     TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_prior};
 
@@ -196,7 +186,7 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     const TrajRef dref = traj_ref(d, const_cast<float*>(bptt ? a.delta : a.xs), s, bb);
     const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
     const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
-    const float* nnrow = s_nn + tid * (DPAD + 1);
+    const float* nnrow = a.nn + rr * a.P;  // (staging this tile through shared memory was measured slower here: 637 vs 457 us)
     const bool want_gate = a.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
     float sc[DPAD];
     if (want_gate) {
@@ -1071,7 +1061,7 @@ static cudaError_t launch_time_embed_grads(const KParams& kp, const SdesLvGradDe
 template <int DPAD>
 static cudaError_t launch_cot_t(const CotArgs& a, int m_tiles, cudaStream_t stream) {
     const int K2 = (a.kp.d.n_components + 1) & ~1;
-    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * DPAD + 4 + DPAD + 128 * (DPAD + 1)) * sizeof(float);
+    const size_t smem = (2 * (size_t)K2 * DPAD + 64 + 2 * DPAD + 4 + DPAD) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cotangent_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cotangent_kernel<DPAD><<<m_tiles, 128, smem, stream>>>(a);
