@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SDES_ABI_VERSION 2
+#define SDES_ABI_VERSION 3
 #define SDES_CHANNELS 64     /* FourierMLP / TimeEmbed width (conf/model/base/fouriermlp.yaml:3) */
 #define SDES_MAX_DIM 64      /* state dimension of the fused single-kernel engines (state in registers) */
 #define SDES_MAX_WIDE_DIM 4096 /* state dimension of the wide (layered tcgen05 GEMM) engine: d > 64 or a NICE target */
@@ -315,14 +315,18 @@ int sdes_philox_normal(uint64_t seed, uint64_t traj_offset, int64_t batch, int32
                        int32_t dim, float* out, void* stream);
 
 /* Tensor-core self test: D[128,N] = A[128,K] * W[N,K]^T through the rollout's own tcgen05 path
- * (A staged into TMEM with tcgen05.st, W image in shared memory, 3xTF32 issue, tcgen05.ld).
- * K multiple of 8 in [8,64], N multiple of 16 in [16,64].  mode 0 = 3xTF32 split,
- * mode 1 = tf32 hi*hi + hi*lo plus a bf16 lo*w term (the rollout's layer).  Test hook. */
+ * (A split into bf16 hi / lo and staged into TMEM with tcgen05.st, W hi / lo images in shared memory,
+ * three kind::f16 passes per k-step, tcgen05.ld).  K multiple of 8 in [8,64], N multiple of 16 in
+ * [16,64].  mode must be 0 (the one split the rollout uses).  Test hook. */
 int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, int32_t n, int32_t mode, void* stream);
 
-/* y[i] = GELU(x[i]) exactly as the tensor-core engine's epilogue evaluates it (x Phi(x), erfc by
- * Abramowitz-Stegun 7.1.26 on MUFU.RCP / MUFU.EX2).  Test hook for the accuracy claim in DESIGN.md. */
+/* y[i] = GELU(x[i]) as the layered GEMM epilogues evaluate it (x Phi(x), erfc by Abramowitz-Stegun 7.1.26
+ * on MUFU.RCP / MUFU.EX2).  Test hook for the accuracy claim in DESIGN.md. */
 int sdes_gelu_probe(const float* x, float* y, int64_t n, void* stream);
+
+/* The same for the packed two-lane GELU of the persistent rollout kernel's epilogue (logistic form
+ * x / (1 + 2^(-x P(x^2))), all FP32 work as f32x2 instructions).  n must be even. */
+int sdes_gelu_pair_probe(const float* x, float* y, int64_t n, void* stream);
 
 /* Kernel launches performed by this process through the library since load (for bench accounting). */
 int64_t sdes_launch_count(void);

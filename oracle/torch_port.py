@@ -23,8 +23,14 @@ import torch.nn.functional as F
 from torch import distributions
 
 
+_DEVICE = [torch.device("cpu")]  # set by rollout(..., device=...): the same op sequence runs on the host cores or, as
+                                  # bench.py's `gpu_eager_baseline`, as stock eager PyTorch kernels on the GPU
+
+
 def _t(a):
-    return torch.as_tensor(np.asarray(a, dtype=np.float32))
+    if isinstance(a, torch.Tensor):
+        return a.to(device=_DEVICE[0], dtype=torch.float32)
+    return torch.as_tensor(np.asarray(a, dtype=np.float32), device=_DEVICE[0])
 
 
 class _TimeEmbed:
@@ -33,7 +39,7 @@ class _TimeEmbed:
     def __init__(self, p):
         self.phase = _t(p["phase"]).reshape(1, -1)
         c = self.phase.shape[1]
-        self.coeff = torch.linspace(start=0.1, end=100, steps=c).unsqueeze(0)
+        self.coeff = torch.linspace(start=0.1, end=100, steps=c).unsqueeze(0).to(_DEVICE[0])
         self.hidden = [(_t(w), _t(b)) for w, b in p["hidden"]]
         self.out_w, self.out_b = _t(p["out_w"]), _t(p["out_b"])
 
@@ -154,22 +160,33 @@ def _gauss_score(x, g):
 def _sde(sde, s, t, dim):
     """mu coefficient, sigma, int div — eq/sdes.py (scalar tensors, computed per step like the reference)."""
     if sde is None:
-        z = torch.zeros(())
+        z = torch.zeros((), device=_DEVICE[0])
         return z, z, z
     dt = t - s
     if sde["kind"] == "vp":
-        bmin, bmax, T_end = torch.tensor(sde["beta_min"]), torch.tensor(sde["beta_max"]), sde["terminal_t"]
+        bmin, bmax, T_end = torch.tensor(sde["beta_min"], device=_DEVICE[0]), torch.tensor(sde["beta_max"], device=_DEVICE[0]), sde["terminal_t"]
         sign = float(sde.get("sign", 1.0))
         a, b = (bmax, bmin) if sign > 0 else (bmin, bmax)
         beta_s, beta_t = torch.lerp(a, b, s / T_end), torch.lerp(a, b, t / T_end)
         return sign * 0.5 * beta_s, float(sde.get("scale", 1.0)) * torch.sqrt(beta_s), sign * 0.25 * (beta_t + beta_s) * dt * dim
     sign = float(sde.get("sign", 1.0))
-    return torch.tensor(sign * sde["drift_coeff"]), torch.tensor(float(sde["diff_coeff"])), sign * sde["drift_coeff"] * dt * dim
+    return (torch.tensor(sign * sde["drift_coeff"], device=_DEVICE[0]), torch.tensor(float(sde["diff_coeff"]), device=_DEVICE[0]),
+            sign * sde["drift_coeff"] * dt * dim)
 
 
 @torch.no_grad()
-def rollout(spec, x0, noise=None, generator=None):
-    """Same contract as oracle.rollout.rollout (noise (T,B,d) injected, or drawn with torch.randn)."""
+def rollout(spec, x0, noise=None, generator=None, device="cpu", as_numpy=True):
+    """Same contract as oracle.rollout.rollout (noise (T,B,d) injected, or drawn with torch.randn).
+    `device="cuda"` runs the identical eager op sequence on the GPU (the "existing Blackwell path": stock PyTorch
+    kernels, ~370 launches per time step, fp32 with TF32 off); `as_numpy=False` leaves the results on the device."""
+    _DEVICE[0] = torch.device(device)
+    try:
+        return _rollout(spec, x0, noise, generator, as_numpy)
+    finally:
+        _DEVICE[0] = torch.device("cpu")
+
+
+def _rollout(spec, x0, noise, generator, as_numpy):
     ls, cd = spec["loss"], spec["ctrl"]
     ts = _t(spec["ts"])
     x = _t(x0).clone()
@@ -183,7 +200,7 @@ def rollout(spec, x0, noise=None, generator=None):
     if kind == "time_reversal" and not (train and method in ("kl", "kl_ito")):
         rnd = _gauss_logp(x, spec["prior"])
     else:
-        rnd = torch.zeros(B, 1)
+        rnd = torch.zeros(B, 1, device=_DEVICE[0])
     xs = [x] if ls.get("return_traj") else None
     for i, (s, t) in enumerate(zip(ts[:-1], ts[1:])):
         dt = t - s
@@ -205,7 +222,7 @@ def rollout(spec, x0, noise=None, generator=None):
             if gate is not None:
                 sc = sc * _clip(gate(s), cm)
             g = g + (sc if ck == "score" else sigma * sc)
-        eps = _t(noise[i]) if noise is not None else torch.randn(x.shape, generator=generator)
+        eps = _t(noise[i]) if noise is not None else torch.randn(x.shape, generator=generator, device=_DEVICE[0])
         if kind == "exp_integrator":
             alpha, sg = float(ls["alpha"]), float(ls["sigma"])
             bk = (alpha * dt.sqrt()).clip(0, 1)
@@ -234,4 +251,6 @@ def rollout(spec, x0, noise=None, generator=None):
         rnd = rnd - lp
     else:
         rnd = rnd + _gauss_logp(x, spec["ref"]) - lp
-    return x.numpy(), rnd.numpy(), (torch.stack(xs).numpy() if xs is not None else None)
+    if not as_numpy:
+        return x, rnd, (torch.stack(xs) if xs is not None else None)
+    return x.cpu().numpy(), rnd.cpu().numpy(), (torch.stack(xs).cpu().numpy() if xs is not None else None)

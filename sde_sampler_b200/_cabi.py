@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libsdes_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 CHANNELS = 64
 MAX_DIM = 64
 MAX_WIDE_DIM = 4096
@@ -126,6 +126,7 @@ SYMBOLS = {
     "sdes_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, _fp, C.c_void_p]),
     "sdes_tcgen05_selftest": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "sdes_gelu_probe": (C.c_int, [_fp, _fp, C.c_int64, C.c_void_p]),
+    "sdes_gelu_pair_probe": (C.c_int, [_fp, _fp, C.c_int64, C.c_void_p]),
     "sdes_launch_count": (C.c_int64, []),
 }
 

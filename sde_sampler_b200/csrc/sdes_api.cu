@@ -12,14 +12,11 @@
 namespace sdes {
 void launch_prepare(const KParams& p, cudaStream_t stream);
 cudaError_t launch_rollout_simt(const KParams& p, int sm_count, cudaStream_t stream);
-cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream);
 bool mma_supported(const KParams& p);
-int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad);
 int64_t mma4_weight_image_floats(const SdesRolloutDesc& d);
-int mma_groups_per_sm(int variant);
-bool mma4_supported(const KParams& p);
-cudaError_t launch_rollout_mma4(const KParams& p, int sm_count, cudaStream_t stream);
-cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t stream);
+int mma_groups_per_sm();
+cudaError_t launch_rollout_tc(const KParams& p, int sm_count, cudaStream_t stream, int* n_launches);
+cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream);
 // wide engine (sdes_wide.cu): d > SDES_MAX_DIM or a NICE target
 bool wide_engine_needed(const SdesRolloutDesc& d);
 const char* wide_validate(const SdesRolloutDesc& d);
@@ -103,8 +100,6 @@ static void ws_layout(const SdesRolloutDesc& d, WsLayout& w) {
     const bool simt = (d.flags & SDES_F_MLP_SIMT) != 0;
     w.w_simt_len = simt ? (int64_t)d.dim * C + C + (int64_t)d.n_hidden * (C * C + C) + (int64_t)C * dpad + dpad : 0;
     w.w_simt = take(w.w_simt_len);
-    w.w_mma_len = simt ? 0 : mma_weight_image_floats(d, dpad);
-    w.w_mma = take(w.w_mma_len);
     w.w_mma4_len = simt ? 0 : mma4_weight_image_floats(d);
     w.w_mma4 = take(w.w_mma4_len);
     w.counter = take(4);
@@ -351,6 +346,10 @@ __global__ void gelu_probe_kernel(const float* __restrict__ x, float* __restrict
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = gelu_fast(x[i]);
 }
 
+__global__ void gelu_pair_probe_kernel(const float2* __restrict__ x, float2* __restrict__ y, int64_t n2) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) y[i] = gelu_fast2(x[i]);
+}
+
 static int sm_count_cached() {
     static int cached[64] = {0};
     int dev = 0;
@@ -417,27 +416,20 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
     if (desc->batch == 0) return 0;
     p.n_tiles = (int)((desc->batch + 31) / 32);
     const int sms = sm_count_cached();
-    // tcgen05 engine variant: 4 groups per SM (bf16 hi/lo operands, state in shared memory) where it fits, else the
-    // 3-group tf32+bf16 kernel.  SDES_MMA_VARIANT=0|1 pins one of them (profiling / A-B measurements).
-    if (!(desc->flags & SDES_F_MLP_SIMT)) {
-        static int forced = -2;
-        if (forced == -2) {
-            const char* e = getenv("SDES_MMA_VARIANT");
-            forced = e ? atoi(e) : -1;
-        }
-        p.mma_variant = 1;
-        if (!mma4_supported(p) || forced == 0) p.mma_variant = 0;
-    }
     {
         // time-chunked scheduling of the tcgen05 engine: aim for >= 8 work items per resident group,
         // chunks of at least 8 steps (state parks in L2 between chunks: ~29 KB per item each way)
-        const int64_t tiles128 = (desc->batch + 127) / 128, groups = (int64_t)mma_groups_per_sm(p.mma_variant) * sms;
+        const int64_t tiles128 = (desc->batch + 127) / 128, groups = (int64_t)mma_groups_per_sm() * sms;
         int64_t nc = (8 * groups + tiles128 - 1) / tiles128;
         const int64_t nc_max = desc->n_steps / 8 > 0 ? desc->n_steps / 8 : 1;
         if (nc > nc_max) nc = nc_max;
         if (nc < 1) nc = 1;
         p.chunk_steps = (int)((desc->n_steps + nc - 1) / nc);
         p.n_chunks = (desc->n_steps + p.chunk_steps - 1) / p.chunk_steps;
+    }
+    for (int r = 0; r < 10; ++r) {  // Philox4x32-10 key schedule of this call's seed (sdes_common.cuh philox4x32_10)
+        p.philox_rk[2 * r] = (uint32_t)desc->seed + (uint32_t)r * PHILOX_W0;
+        p.philox_rk[2 * r + 1] = (uint32_t)(desc->seed >> 32) + (uint32_t)r * PHILOX_W1;
     }
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     launch_prepare(p, stream);
@@ -448,7 +440,9 @@ int sdes_rollout_fwd(const SdesRolloutDesc* desc, void* stream_) {
         e = launch_rollout_simt(p, sms, stream);
     } else {
         if (!mma_supported(p)) return fail(-8, "the tcgen05 engine does not support this descriptor (dim=%d, n_hidden=%d); set SDES_F_MLP_SIMT", desc->dim, desc->n_hidden);
-        e = p.mma_variant == 1 ? launch_rollout_mma4(p, sms, stream) : launch_rollout_mma(p, sms, stream);
+        int n = 1;
+        e = launch_rollout_tc(p, sms, stream, &n);
+        g_launches += n - 1;
     }
     if (e != cudaSuccess) return fail(-7, "rollout kernel launch failed: %s", cudaGetErrorString(e));
     g_launches++;
@@ -794,8 +788,8 @@ int sdes_tcgen05_selftest(const float* a, const float* w, float* d, int32_t k, i
     g_err[0] = 0;
     if (!a || !w || !d) return fail(-5, "a/w/d NULL");
     if (k < 8 || k > 64 || k % 8 || n < 16 || n > 64 || n % 16) return fail(-3, "k must be a multiple of 8 in [8,64], n a multiple of 16 in [16,64]");
-    if (mode != 0 && mode != 1) return fail(-3, "mode must be 0 (3xTF32) or 1 (2xTF32 + bf16)");
-    cudaError_t e = launch_mma_selftest(a, w, d, k, n, mode, reinterpret_cast<cudaStream_t>(stream_));
+    if (mode != 0) return fail(-3, "mode must be 0 (bf16 hi/lo split, three kind::f16 passes: the rollout's layer)");
+    cudaError_t e = launch_mma_selftest(a, w, d, k, n, reinterpret_cast<cudaStream_t>(stream_));
     if (e != cudaSuccess) return fail(-7, "selftest launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
@@ -807,6 +801,17 @@ int sdes_gelu_probe(const float* x, float* y, int64_t n, void* stream_) {
     gelu_probe_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, y, n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "gelu probe launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_gelu_pair_probe(const float* x, float* y, int64_t n, void* stream_) {
+    g_err[0] = 0;
+    if (!x || !y || n <= 0 || (n & 1)) return fail(-5, "x/y NULL or n not a positive even number");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 7) return fail(-5, "x/y must be 8-byte aligned");
+    gelu_pair_probe_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(y), n / 2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "gelu pair probe launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

@@ -79,55 +79,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(const KParams p) {
         for (int64_t e = gtid; e < tiles128; e += nthreads) prog[e] = 0u;
     }
 
-    // tcgen05 weight images (layouts: sdes_tc.cuh wimg_offset_floats / wimg16_offset; order: sdes_rollout_mma.cu):
-    // per layer hi = fp32 truncated to tf32, lo = w - hi, w16 = bf16(w); zero-padded to the MMA shapes.
-    if (!(d.flags & SDES_F_MLP_SIMT) && p.mma_variant == 0) {
-        float* w = ws + p.ws.w_mma;
-        const int nout = (dpad + 15) / 16 * 16, k0b = (dpad + 15) & ~15;
-        int64_t o = 0;
-        auto put = [&](int64_t base, int n, int k, int N, int K, float v) {
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-            const int64_t off = (int64_t)(k / 4) * (N * 4) + (n / 8) * 32 + (n % 8) * 4 + (k % 4);
-            w[base + off] = hi;
-            w[base + (int64_t)N * K + off] = v - hi;
-        };
-        auto put16 = [&](int64_t base_floats, int n, int k, int N, float v) {
-            __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(w + base_floats);
-            w16[(int64_t)(k / 8) * (N * 8) + (n / 8) * 64 + (n % 8) * 8 + (k % 8)] = __float2bfloat16_rn(v);
-        };
-        for (int64_t e = gtid; e < (int64_t)C * k0b; e += nthreads) {  // input layer: N=C, K=dpad (bf16: k0b)
-            const int n = (int)(e / k0b), k = (int)(e % k0b);
-            const float v = k < dim ? blob[p.bl.in_w + (int64_t)n * dim + k] : 0.f;
-            if (k < dpad) put(o, n, k, C, dpad, v);
-            put16(o + 2ll * C * dpad, n, k, C, v);
-        }
-        o += 2ll * C * dpad + 32ll * k0b;
-        for (int l = 0; l < nh; ++l) {
-            for (int64_t e = gtid; e < C * C; e += nthreads) {
-                const int n = (int)(e / C), k = (int)(e % C);
-                const float v = blob[p.bl.h_w[l] + e];
-                put(o, n, k, C, C, v);
-                put16(o + 2ll * C * C, n, k, C, v);
-            }
-            o += 2ll * C * C + 32ll * C;
-        }
-        for (int64_t e = gtid; e < (int64_t)nout * C; e += nthreads) {  // output layer: N=nout, K=C
-            const int n = (int)(e / C), k = (int)(e % C);
-            const float v = n < dim ? blob[p.bl.out_w + (int64_t)n * C + k] : 0.f;
-            put(o, n, k, nout, C, v);
-            put16(o + 2ll * nout * C, n, k, nout, v);
-        }
-        o += 2ll * nout * C + 32ll * nout;
-        for (int l = 0; l < nh; ++l) {
-            for (int64_t e = gtid; e < C; e += nthreads) w[o + e] = blob[p.bl.h_b[l] + e];
-            o += C;
-        }
-        for (int64_t e = gtid; e < nout; e += nthreads) w[o + e] = e < dim ? blob[p.bl.out_b + e] : 0.f;
-    }
-
     // bf16 hi/lo operand images of the 4-group tcgen05 engine (sdes_rollout_mma.cu): per layer hi[N x K16] then
     // lo[N x K16] in the wimg16 layout, then the fp32 biases {b_h[64]} x nh, b_out[NOUT]
-    if (!(d.flags & SDES_F_MLP_SIMT) && p.mma_variant == 1) {
+    if (!(d.flags & SDES_F_MLP_SIMT)) {
         __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(ws + p.ws.w_mma4);
         const int nout = (dpad + 15) / 16 * 16, k0b = (dpad + 15) & ~15;
         auto put = [&](int64_t base, int64_t half, int n, int k, int N, float v) {

@@ -1,16 +1,32 @@
 // sdes_rollout_mma.cu — persistent rollout kernel, control MLP on tcgen05 tensor cores.
 //
-// One CTA per SM, resident for the whole rollout.  It holds the split (hi/lo) weight images of
-// every layer in shared memory (loaded once with TMA bulk copies), owns all 512 TMEM columns,
-// and runs GROUPS independent groups of 4 warps.  A group pulls 128-trajectory tiles from a
-// global counter and carries each tile through all T time steps: thread r owns trajectory r —
-// its state x, running cost and network activations stay in registers / TMEM lane r.  Per step
-// and layer the group writes the activations (hi, lo) into TMEM as the A operand, one thread
-// issues the 3xTF32 MMAs against the shared-memory weights and commits to the group's mbarrier,
-// and the threads read the fp32 accumulator row back with tcgen05.ld for the fused epilogue
-// (bias, exact-erf GELU, then — after the last layer — target score, control reparametrisation,
-// cost increments, Philox noise, Euler-Maruyama update: sdes_step.cuh).  While one group waits
-// on its MMAs the other group's epilogue keeps the FP32/MUFU pipes busy.
+// One CTA per SM, resident for the whole rollout.  It holds the bf16 hi/lo weight images of every
+// layer in shared memory (loaded once with TMA bulk copies), owns all 512 TMEM columns, and runs
+// FOUR independent groups of 4 warps.  A group pulls work items (time chunk, 128-trajectory tile) from
+// a global counter and carries the tile through the chunk's time steps: thread r owns trajectory r —
+// its state x lives in shared memory as dimension pairs ([pair][128] float2, conflict free), its
+// network activations in TMEM lane r.  Per step and layer the group writes the activations (bf16 hi, lo)
+// into TMEM as the A operand, one thread issues the layer's 3 x K/16 kind::f16 MMAs against the
+// shared-memory weights and commits to the group's mbarrier, and the threads stream the fp32 accumulator
+// back with tcgen05.ld, 8 columns at a time, through the fused epilogue (bias, exact-erf GELU, hi/lo split)
+// into the next layer's A operand.  The last accumulator (the network output) streams 8 columns at a time
+// into the control / noise / cost / state update (one pass over the state per step).
+//
+// Round-2 rewrite ("lean" step).  The kernel is bound by FP32-pipe ISSUE slots and MUFU throughput, not by the
+// tensor pipe, so the step is written to minimise issued instructions:
+//   * every elementwise FP32 operation works on a register pair (packed FFMA2 / FMUL2 / FADD2: one issue slot
+//     for two lanes), the GELU in its logistic form (sdes_common.cuh gelu_fast2);
+//   * the score part of the control is evaluated inside the update loop from the pair of x it is about to
+//     advance (no sc[DPAD] array held across the MLP, no spills), the only pre-pass being the target's
+//     "global" quantities: the softmax over mixture components on the dimensions that differ between
+//     components (<= 8 leading dims, else the DENSE kernel below), the funnel's two sums;
+//   * Philox round keys are kernel parameters (constant-bank operands), the generator is inlined;
+//   * control kind x target kind are compile-time arguments of the update loop, selected by one
+//     warp-uniform switch per step;
+//   * the Euler-Maruyama and exponential-integrator updates share one form x' = A x + Bc g + Cc eps.
+// DENSE = true is the same kernel with the target score of ALL dimensions precomputed into registers per step
+// (a GMM whose components differ beyond the first 8 dims); the host launches both instantiations and the
+// one that does not match the prologue's dimension mask returns at once.
 #include <cuda_bf16.h>
 
 #include "sdes_step.cuh"
@@ -18,59 +34,46 @@
 
 namespace sdes {
 
-#ifndef SDES_MMA_GROUPS
-#define SDES_MMA_GROUPS 3
-#endif
-constexpr int MMA_GROUPS = SDES_MMA_GROUPS;
-constexpr int MMA_THREADS = MMA_GROUPS * 128;
+constexpr int TC_GROUPS = 4;
+constexpr int TC_THREADS = TC_GROUPS * 128;
 constexpr int TMEM_COLS = 512;
-constexpr int GROUP_COLS = 160;  // D[64] | A_hi tf32 [64] | A_lo bf16x2 [32]
+constexpr int GROUP_COLS = 128;  // D[64] | A_hi bf16x2 [32] | A_lo bf16x2 [32]
+constexpr int GMM_ACT = 8;       // leading dimensions of every mixture component kept in shared memory (lean kernel)
+constexpr float LOG2E = 1.4426950408889634f;
 
 __host__ __device__ inline int mma_nout(int dpad) { return (dpad + 15) / 16 * 16; }
 
-// Workspace image for the tcgen05 engine (floats), in the order the kernel keeps it in smem.  Per layer:
-// hi (tf32-truncated fp32), lo = w - hi (fp32), w16 (bf16, K padded to a multiple of 16):
-//   L0:  hi[64*K0] lo[64*K0] w16[64*K0b/2]     (N=64, K=K0=dpad, K0b = round16(dpad))
-//   Lh:  { hi[64*64] lo[64*64] w16[64*64/2] } x n_hidden
-//   Lo:  hi[NOUT*64] lo[NOUT*64] w16[NOUT*64/2] (N=NOUT, K=64)
-//   bias: { b_h[64] } x n_hidden, b_out[NOUT]     (b_in is folded into the time-embedding table)
-int64_t mma_weight_image_floats(const SdesRolloutDesc& d, int dpad_simt) {
-    (void)dpad_simt;
+// floats of the bf16 operand image: per layer hi[N x K16] then lo[N x K16] (tc::wimg16_offset layout), then the fp32
+// biases {b_h[64]} x n_hidden, b_out[NOUT]   (b_in is folded into the time-embedding table)
+int64_t mma4_weight_image_floats(const SdesRolloutDesc& d) {
     const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad), k0b = (dpad + 15) & ~15;
-    return (2ll * 64 * dpad + 32ll * k0b) + (int64_t)d.n_hidden * (2ll * 64 * 64 + 32 * 64) + (2ll * nout * 64 + nout * 32ll) +
-           (int64_t)d.n_hidden * 64 + nout;
+    const int64_t bf16_elems = 2ll * 64 * k0b + (int64_t)d.n_hidden * 2 * 64 * 64 + 2ll * nout * 64;
+    return bf16_elems / 2 + (int64_t)d.n_hidden * 64 + nout;
 }
 
-int mma_groups_per_sm(int variant) { return variant == 1 ? 4 : MMA_GROUPS; }
-
-bool mma_supported(const KParams& p) { return p.d.dim <= 64 && p.d.n_hidden <= SDES_MAX_HIDDEN; }
+int mma_groups_per_sm() { return TC_GROUPS; }
 
 // ------------------------------------------------------------------------------ self test
-// D[128,N] = A[128,K] * W[N,K]^T through exactly the code path the rollout uses (A via tcgen05.st
-// into TMEM, W image in smem, 3xTF32 issue, tcgen05.ld).  Exposed as sdes_tcgen05_selftest.
+// D[128,N] = A[128,K] * W[N,K]^T through exactly the code path the rollout uses (A split into bf16 hi/lo and written
+// with tcgen05.st into TMEM, W hi/lo images in shared memory, the bf16x3 issue, tcgen05.ld).  sdes_tcgen05_selftest.
 __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W,
-                                                              float* __restrict__ D, int K, int N, int mode) {
+                                                              float* __restrict__ D, int K, int N) {
     extern __shared__ __align__(128) float sm[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int K16 = (K + 15) & ~15;
-    float* w_hi = sm;
-    float* w_lo = sm + N * K;
-    __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(sm + 2 * N * K);
+    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(sm);
+    __nv_bfloat16* w_lo = w_hi + N * K16;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int e = tid; e < N * K; e += 128) {
-        const int n = e / K, k = e % K;
-        const float w = W[e];
-        const float hi = __uint_as_float(tc::tf32_hi_bits(w));
-        w_hi[tc::wimg_offset_floats(n, k, N)] = hi;
-        w_lo[tc::wimg_offset_floats(n, k, N)] = w - hi;
-    }
     for (int e = tid; e < N * K16; e += 128) {
         const int n = e / K16, k = e % K16;
-        w16[tc::wimg16_offset(n, k, N)] = __float2bfloat16_rn(k < K ? W[n * K + k] : 0.f);
+        const float w = k < K ? W[n * K + k] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        w_hi[tc::wimg16_offset(n, k, N)] = hi;
+        w_lo[tc::wimg16_offset(n, k, N)] = __float2bfloat16_rn(w - __bfloat162float(hi));
     }
     if (warp == 0) {
-        tc::tmem_alloc(&tmem_base_s, 256);
+        tc::tmem_alloc(&tmem_base_s, 128);
         tc::tmem_relinquish();
     }
     if (tid == 0) {
@@ -83,34 +86,23 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     tc::fence_after();
     const uint32_t tbase = tmem_base_s;
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
-    const uint32_t col_d = 0, col_hi = 64, col_lo = 128;
+    const uint32_t col_d = 0, col_hi = 64, col_lo = 96;
     for (int c = 0; c < K16; c += 8) {
-        uint32_t hi[8], lo[8], lo16[4];
-        float lof[8];
-        for (int q = 0; q < 8; ++q) {
-            const float a = c + q < K ? A[tid * K + c + q] : 0.f;
-            hi[q] = tc::tf32_hi_bits(a);
-            lof[q] = a - __uint_as_float(hi[q]);
-            lo[q] = __float_as_uint(lof[q]);
+        uint32_t hi[4], lo[4];
+        for (int q = 0; q < 4; ++q) {
+            const int k = c + 2 * q;
+            const float2 a = make_float2(k < K ? A[tid * K + k] : 0.f, k + 1 < K ? A[tid * K + k + 1] : 0.f);
+            tc::split_bf16_pair2(a, hi[q], lo[q]);
         }
-        for (int q = 0; q < 4; ++q) lo16[q] = tc::pack_bf16x2(lof[2 * q], lof[2 * q + 1]);
-        if (c < K) tc::tmem_st8(lane_addr + col_hi + c, hi);
-        if (mode == 0) {
-            if (c < K) tc::tmem_st8(lane_addr + col_lo + c, lo);
-        } else {
-            tc::tmem_st4(lane_addr + col_lo + c / 2, lo16);
-        }
+        tc::tmem_st4(lane_addr + col_hi + c / 2, hi);
+        tc::tmem_st4(lane_addr + col_lo + c / 2, lo);
     }
     tc::wait_st();
     tc::fence_before();
     __syncthreads();
     if (tid == 0) {
         tc::fence_after();
-        if (mode == 0)
-            tc::issue_layer_3xtf32(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo), K, N);
-        else
-            tc::issue_layer_mixed(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo),
-                                  tc::smem_u32(w16), K, K16, N);
+        tc::issue_layer_bf16x3(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo), K16, N);
         tc::mma_commit(&bar);
     }
     tc::mbar_wait(&bar, 0);
@@ -123,101 +115,89 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     }
     tc::fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, 256);
+    if (warp == 0) tc::tmem_dealloc(tbase, 128);
 }
 
-cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t stream) {
-    const size_t smem = 2 * (size_t)N * K * sizeof(float) + (size_t)N * ((K + 15) & ~15) * 2;
+cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream) {
+    const size_t smem = 2 * (size_t)N * ((K + 15) & ~15) * 2;
     cudaError_t e = cudaFuncSetAttribute(mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mma_selftest_kernel<<<1, 128, smem, stream>>>(A, W, D, K, N, mode);
+    mma_selftest_kernel<<<1, 128, smem, stream>>>(A, W, D, K, N);
     return cudaGetLastError();
 }
-
 
 // ---------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
-// activations (fp32) -> TMEM A operand: tf32 hi half (one column per value) and bf16 lo half (two per column).
-// ZERO_PAD: also clear the bf16 columns up to the next multiple of 16 values (input layer, K0 % 16 == 8).
-template <int N>
-__device__ __forceinline__ void store_a_split(uint32_t addr_hi, uint32_t addr_lo16, const float (&a)[N]) {
-#pragma unroll
-    for (int c = 0; c < N; c += 8) {
-        uint32_t hi[8], lo16[4];
-        float lo[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            hi[q] = tc::tf32_hi_bits(a[c + q]);
-            lo[q] = a[c + q] - __uint_as_float(hi[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) lo16[q] = tc::pack_bf16x2(lo[2 * q], lo[2 * q + 1]);
-        tc::tmem_st8(addr_hi + c, hi);
-        tc::tmem_st4(addr_lo16 + c / 2, lo16);
-    }
-    if (N % 16 == 8) {
-        const uint32_t z[4] = {0u, 0u, 0u, 0u};
-        tc::tmem_st4(addr_lo16 + N / 2, z);
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void load_acc(uint32_t addr_d, float (&acc)[N]) {
-#pragma unroll
-    for (int c = 0; c < N; c += 8) tc::tmem_ld8(addr_d + c, &acc[c]);
-    tc::wait_ld_tie<N>(acc);
-}
-
-// 8 accumulator columns -> + bias -> exact GELU -> tf32 hi/lo split -> A operand of the next layer
-__device__ __forceinline__ void gelu_split_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8],
-                                                  const float4 b0, const float4 b1) {
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint32_t hi[8], lo16[4];
-    float lo[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float a = gelu_fast(v[q] + bb[q]);
-        hi[q] = tc::tf32_hi_bits(a);
-        lo[q] = a - __uint_as_float(hi[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) lo16[q] = tc::pack_bf16x2(lo[2 * q], lo[2 * q + 1]);
-    tc::tmem_st8(addr_hi, hi);
-    tc::tmem_st4(addr_lo, lo16);
-}
-
-struct GroupCtx;
-__device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* __restrict__ bias);
-
 struct GroupCtx {
-    int g;               // group index
-    int gtid;            // thread index in the group = row in the tile = TMEM lane
-    uint32_t t_d, t_hi, t_lo;          // TMEM addresses, lane 0 of the tile (for the issuing thread)
-    uint32_t l_d, l_hi, l_lo;          // same, at this thread's warp lane window (for ld / st)
+    int g;                     // group index
+    int gtid;                  // thread index in the group = row in the tile = TMEM lane
+    uint32_t t_d, t_hi, t_lo;  // TMEM addresses, lane 0 of the tile (for the issuing thread)
+    uint32_t l_d, l_hi, l_lo;  // same, at this thread's warp lane window (for ld / st)
     uint64_t* bar;
     uint32_t phase;
 };
 
-// A operand is in TMEM; run one layer and leave the accumulator ready to be read.
-__device__ __forceinline__ void run_layer(GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, uint32_t w16_saddr, int K, int N) {
+// The state of one trajectory in shared memory: dimensions (2r, 2r+1) as one float2 at p[r * 128] (the 128 threads of
+// a group read / write consecutive 8-byte words: conflict free, and a pair is one LDS.64 into an aligned register pair).
+struct XPair {
+    float2* p;
+    __device__ __forceinline__ float operator[](int j) const { return reinterpret_cast<const float*>(p + (j >> 1) * 128)[j & 1]; }
+    __device__ __forceinline__ float2 pair(int r) const { return p[r * 128]; }
+    __device__ __forceinline__ void set_pair(int r, float2 v) const { p[r * 128] = v; }
+};
+
+// state -> A operand of the input layer (bf16 hi / lo, two values per TMEM column)
+template <int DPAD>
+__device__ __forceinline__ void store_a_from_x(uint32_t addr_hi, uint32_t addr_lo, const XPair& x) {
+#pragma unroll
+    for (int c = 0; c < DPAD / 8; ++c) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tc::split_bf16_pair2(x.pair(4 * c + q), hi[q], lo[q]);
+        tc::tmem_st4(addr_hi + 4 * c, hi);
+        tc::tmem_st4(addr_lo + 4 * c, lo);
+    }
+    if (DPAD % 16 == 8) {  // K of the MMA is a multiple of 16: clear the upper half of the last k-step
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        tc::tmem_st4(addr_hi + DPAD / 2, z);
+        tc::tmem_st4(addr_lo + DPAD / 2, z);
+    }
+}
+
+// 8 accumulator columns -> + bias -> exact GELU -> bf16 hi/lo split -> A operand of the next layer
+__device__ __forceinline__ void gelu_split_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8], const float4 b0, const float4 b1) {
+    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 a = gelu_fast2(__fadd2_rn(make_float2(v[2 * q], v[2 * q + 1]), bb[q]));
+        tc::split_bf16_pair2(a, hi[q], lo[q]);
+    }
+    tc::tmem_st4(addr_hi, hi);
+    tc::tmem_st4(addr_lo, lo);
+}
+
+// A operand is in TMEM: hand the layer to the tensor core (one thread issues, commit -> the group's mbarrier) ...
+__device__ __forceinline__ void issue_layer(const GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K16, int N) {
     tc::wait_st();
     tc::fence_before();
     group_bar(c.g);
     if (c.gtid == 0) {
         tc::fence_after();
-        tc::issue_layer_mixed(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, w16_saddr, K, (K + 15) & ~15, N);
+        tc::issue_layer_bf16x3(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K16, N);
         tc::mma_commit(c.bar);
     }
+}
+// ... and wait until the accumulator can be read
+__device__ __forceinline__ void wait_layer(GroupCtx& c) {
     tc::mbar_wait(c.bar, c.phase);
     c.phase ^= 1u;
     tc::fence_after();
 }
 
-// The fused epilogue between two layers, streamed 8 columns at a time straight from the
-// accumulator (TMEM) into the next A operand (TMEM): the 64-wide activation row never sits in
-// registers, and one compact loop serves every layer (instruction-cache footprint matters: the
-// first version of this kernel spent 42% of its stall samples on instruction fetch).
+// The fused epilogue between two layers, streamed 8 columns at a time straight from the accumulator (TMEM) into the
+// next A operand (TMEM): the 64-wide activation row never sits in registers, and one compact loop serves every layer.
 // `bias` may point to global (time-embedding row, input layer) or shared memory (hidden biases).
 __device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* __restrict__ bias) {
     float a[8], b[8];
@@ -229,332 +209,336 @@ __device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* _
         const float4 p0 = b4[2 * ch], p1 = b4[2 * ch + 1], p2 = b4[2 * ch + 2], p3 = b4[2 * ch + 3];
         tc::wait_ld_tie<8>(a);
         tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
-        gelu_split_store8(c.l_hi + 8u * ch, c.l_lo + 4u * ch, a, p0, p1);
+        gelu_split_store8(c.l_hi + 4u * ch, c.l_lo + 4u * ch, a, p0, p1);
         tc::wait_ld_tie<8>(b);
         if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
-        gelu_split_store8(c.l_hi + 8u * (ch + 1), c.l_lo + 4u * (ch + 1), b, p2, p3);
+        gelu_split_store8(c.l_hi + 4u * (ch + 1), c.l_lo + 4u * (ch + 1), b, p2, p3);
     }
 }
 
-template <int DPAD>
-__global__ void __launch_bounds__(MMA_THREADS, 1) rollout_mma_kernel(const __grid_constant__ KParams p) {
-    constexpr int NOUT = (DPAD + 15) / 16 * 16;
-    extern __shared__ __align__(128) float smem[];
-    __shared__ uint64_t s_wbar;
-    __shared__ uint64_t s_mbar[MMA_GROUPS];
-    __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_tile[MMA_GROUPS];
-
-    const SdesRolloutDesc& d = p.d;
-    const float* ws = reinterpret_cast<const float*>(d.workspace);
-    const int dim = d.dim, T = d.n_steps, K = d.n_components, nh = d.n_hidden;
-    const int tid = threadIdx.x, warp = tid >> 5;
-
-    // ---- shared memory carve-up: [weight image + biases | gmm mu | gmm h | gmm c | prior | ref]
-    float* s_w = smem;
-    const int K2 = (K + 1) & ~1;  // GMM images are padded to an even number of components
-    float* s_mu = s_w + p.ws.w_mma_len;
-    float* s_h = s_mu + K2 * DPAD;
-    float* s_c = s_h + K2 * DPAD;
-    float* s_prior = s_c + 64;
-    float* s_ref = s_prior + 2 * DPAD + 8;
-
-    if (warp == 0) {
-        tc::tmem_alloc(&s_tmem, TMEM_COLS);
-        tc::tmem_relinquish();
-    }
-    if (tid == 0) {
-        tc::mbar_init(&s_wbar, 1);
-        for (int g = 0; g < MMA_GROUPS; ++g) tc::mbar_init(&s_mbar[g], 1);
-        tc::fence_mbar_init();
-    }
-    tc::fence_before();
-    __syncthreads();
-    tc::fence_after();
-    if (tid == 0) {
-        // weights: TMA bulk copies global -> shared, all counted on one mbarrier
-        const uint32_t total = (uint32_t)(p.ws.w_mma_len * sizeof(float));
-        tc::mbar_arrive_expect_tx(&s_wbar, total);
-        const char* src = reinterpret_cast<const char*>(ws + p.ws.w_mma);
-        char* dst = reinterpret_cast<char*>(s_w);
-        for (uint32_t off = 0; off < total; off += 16384u) {
-            const uint32_t n = total - off < 16384u ? total - off : 16384u;
-            tc::bulk_g2s(dst + off, src + off, n, &s_wbar);
-        }
-    }
-    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
-        s_mu[e] = ws[p.ws.gmm_mu + e];
-        s_h[e] = ws[p.ws.gmm_h + e];
-    }
-    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
-    for (int e = tid; e < 2 * DPAD + 8; e += blockDim.x) {
-        s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
-        s_ref[e] = e <= 2 * DPAD ? ws[p.ws.ref + e] : 0.f;
-    }
-    tc::mbar_wait(&s_wbar, 0);
-    __syncthreads();
-
-    // weight image addresses
-    const uint32_t w_base = tc::smem_u32(s_w);
-    constexpr uint32_t K0B = (DPAD + 15) & ~15;
-    constexpr uint32_t LH_BYTES = 16384u + 16384u + 8192u;             // one hidden layer: hi | lo | w16
-    const uint32_t l0_hi = w_base, l0_lo = l0_hi + 64u * DPAD * 4u, l0_16 = l0_lo + 64u * DPAD * 4u;
-    const uint32_t lh_base = l0_16 + 64u * K0B * 2u;
-    const uint32_t lo_hi = lh_base + (uint32_t)nh * LH_BYTES, lo_lo = lo_hi + (uint32_t)NOUT * 256u, lo_16 = lo_lo + (uint32_t)NOUT * 256u;
-    const float* s_bias = s_w + (2 * 64 * DPAD + 32 * K0B) + nh * (2 * 64 * 64 + 32 * 64) + (2 * NOUT * 64 + NOUT * 32);  // {b_h[64]} x nh, b_out[NOUT]
-
-    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
-    GroupCtx c;
-    c.g = warp >> 2;
-    c.gtid = tid & 127;
-    const uint32_t tbase = s_tmem + (uint32_t)(c.g * GROUP_COLS);
-    c.t_d = tbase;
-    c.t_hi = tbase + 64;
-    c.t_lo = tbase + 128;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    c.l_d = c.t_d + lane_off;
-    c.l_hi = c.t_hi + lane_off;
-    c.l_lo = c.t_lo + lane_off;
-    c.bar = &s_mbar[c.g];
-    c.phase = 0;
-
-    uint32_t* counter = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.counter);
-    const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
-    const bool ret_traj = (d.flags & SDES_F_RETURN_TRAJ) != 0;
-    const int64_t B = d.batch;
-    const uint32_t n_tiles = (uint32_t)((B + 127) / 128);
-
-    // Work items are (time chunk, tile) pairs handed out chunk-major from one counter: a tile's T steps
-    // are cut into n_chunks pieces so that 512 tiles on 296 groups do not quantise into 2 rounds with
-    // the second 73% full.  Between chunks the tile's state (x, rnd) parks in the workspace
-    // ([tile][j][128] so warps read and write whole 128-byte lines) and a per-tile progress word orders
-    // producer and consumer.  An item only ever waits on an item handed out earlier, so there is no
-    // deadlock whatever the residency.
-    const int n_chunks = p.n_chunks, chunk_steps = p.chunk_steps;
-    const uint32_t n_items = n_tiles * (uint32_t)n_chunks;
-    float* state = const_cast<float*>(ws) + p.ws.state;
-    uint32_t* progress = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.progress);
-    for (;;) {
-        if (c.gtid == 0) s_tile[c.g] = atomicAdd(counter, 1u);
-        group_bar(c.g);
-        const uint32_t item = s_tile[c.g];
-        if (item >= n_items) break;
-        const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
-        const int64_t row = (int64_t)tile * 128 + c.gtid;
-        const bool valid = row < B;
-        const int64_t rrow = valid ? row : (B - 1);
-        float* st = state + (int64_t)tile * (DPAD + 1) * 128 + c.gtid;
-
-        float x[DPAD];
-        float rnd;
-        if (chunk == 0) {
-#pragma unroll
-            for (int j = 0; j < DPAD; ++j) x[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
-            if (ret_traj && valid) {
-                const TrajRef o = traj_ref(d, d.xs, 0, rrow);
-#pragma unroll
-                for (int j = 0; j < DPAD; ++j)
-                    if (j < dim) o.p[j * o.stride] = x[j];
-            }
-            rnd = initial_rnd<DPAD>(d, x, tsm);
-        } else {
-            if (c.gtid == 0) {
-                uint32_t seen;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
-                } while (seen < chunk);
-            }
-            group_bar(c.g);
-#pragma unroll
-            for (int j = 0; j < DPAD; ++j) x[j] = __ldcg(st + j * 128);  // L2 reads: another SM wrote them
-            rnd = __ldcg(st + DPAD * 128);
-        }
-        const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)rrow);
-        const int i_begin = (int)chunk * chunk_steps;
-        const int i_end = (i_begin + chunk_steps < T) ? i_begin + chunk_steps : T;
-
-        for (int i = i_begin; i < i_end; ++i) {
-            const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
-            // ---- score part of the control (needs x only): before the MLP, kept in registers
-            float sc[DPAD];
-            score_part<DPAD>(d, x, sc, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
-            // ---- control MLP on the tensor cores (models/mlp.py:114-122)
-            store_a_split<DPAD>(c.l_hi, c.l_lo, x);
-            run_layer(c, l0_hi, l0_lo, l0_16, DPAD, C);
-            layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
-#pragma unroll 1
-            for (int l = 0; l < nh; ++l) {
-                run_layer(c, lh_base + (uint32_t)l * LH_BYTES, lh_base + (uint32_t)l * LH_BYTES + 16384u, lh_base + (uint32_t)l * LH_BYTES + 32768u, C, C);
-                layer_epilogue(c, s_bias + l * C);
-            }
-            run_layer(c, lo_hi, lo_lo, lo_16, C, NOUT);
-            // ---- network output streamed from TMEM into the control / cost / state update
-            {
-                const StepCoef sc_ = make_step_coef(d, tab);
-                const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
-                const float* bo = s_bias + nh * C;
-                float cost = 0.f, ito = 0.f;
-                float na[8], nb[8];
-                tc::tmem_ld8(c.l_d, na);
-#pragma unroll
-                for (int q = 0; q < DPAD / 8; q += 2) {
-                    tc::wait_ld_tie<8>(na);
-                    if (q + 1 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 1), nb);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) na[r] += bo[8 * q + r];
-                    update4(sc_, &x[8 * q], &na[0], &sc[8 * q], s_prior + 8 * q, s_prior + DPAD + 8 * q, 8 * q, i, traj, nrow, cost, ito);
-                    update4(sc_, &x[8 * q + 4], &na[4], &sc[8 * q + 4], s_prior + 8 * q + 4, s_prior + DPAD + 8 * q + 4, 8 * q + 4, i, traj, nrow, cost, ito);
-                    if (q + 1 < DPAD / 8) {
-                        tc::wait_ld_tie<8>(nb);
-                        if (q + 2 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 2), na);
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) nb[r] += bo[8 * (q + 1) + r];
-                        update4(sc_, &x[8 * q + 8], &nb[0], &sc[8 * q + 8], s_prior + 8 * q + 8, s_prior + DPAD + 8 * q + 8, 8 * q + 8, i, traj, nrow, cost, ito);
-                        update4(sc_, &x[8 * q + 12], &nb[4], &sc[8 * q + 12], s_prior + 8 * q + 12, s_prior + DPAD + 8 * q + 12, 8 * q + 12, i, traj, nrow, cost, ito);
-                    }
-                }
-                finish_step(d, sc_, tab, cost, ito, rnd);
-            }
-            if (ret_traj && valid) {
-                const TrajRef o = traj_ref(d, d.xs, i + 1, rrow);
-#pragma unroll
-                for (int j = 0; j < DPAD; ++j)
-                    if (j < dim) o.p[j * o.stride] = x[j];
-            }
-        }
-        if (i_end == T) {
-            rnd += terminal_rnd<DPAD>(d, x, tsm);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < DPAD; ++j)
-                    if (j < dim) d.x_T[rrow * dim + j] = x[j];
-                d.rnd[rrow] = rnd;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < DPAD; ++j) __stcg(st + j * 128, x[j]);
-            __stcg(st + DPAD * 128, rnd);
-            __threadfence();
-            group_bar(c.g);
-            if (c.gtid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(chunk + 1u) : "memory");
-        }
-    }
-    tc::fence_before();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(s_tmem, TMEM_COLS);
-}
-
-// =========================================================================== 4-group engine
-// Same work decomposition (items = (time chunk, 128-trajectory tile), one trajectory per thread, MLP on tcgen05
-// with the A operand in TMEM), but FOUR groups per SM instead of three: one more warp per scheduler to hide the
-// epilogue's dependency stalls, which is what bounds this kernel (issue slots ~58 % busy with three).  What makes
-// the fourth group fit:
-//   * TMEM: both operand halves are bf16 (hi = bf16(v), lo = bf16(v - hi), 16 significant bits — the wide engine's
-//     split, parity-tested there): D 64 | A_hi 32 | A_lo 32 = 128 columns per group, 4 x 128 = 512;
-//   * registers (128 per thread at 512 threads): the state x lives in shared memory ([j][128] per group, conflict
-//     free) and is read where it is needed; only the score part sc[DPAD] stays in registers across the MLP;
-//   * shared memory: bf16 hi/lo weights are 4 bytes per element instead of 10 (65 KB instead of 160 KB at d = 50),
-//     which pays for the 112 KB of state.
-// The layer is three kind::f16 MMAs per K=16 step (tc::issue_layer_bf16x3): 12 per 64x64 layer instead of 20.
-constexpr int MMA4_GROUPS = 4;
-constexpr int MMA4_THREADS = MMA4_GROUPS * 128;
-constexpr int GROUP4_COLS = 128;  // D[64] | A_hi bf16x2 [32] | A_lo bf16x2 [32]
-
-// bytes of the bf16 operand image: per layer hi then lo (wimg16 layout), then the fp32 biases
-int64_t mma4_weight_image_floats(const SdesRolloutDesc& d) {
-    const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad), k0b = (dpad + 15) & ~15;
-    const int64_t bf16_elems = 2ll * 64 * k0b + (int64_t)d.n_hidden * 2 * 64 * 64 + 2ll * nout * 64;
-    return bf16_elems / 2 + (int64_t)d.n_hidden * 64 + nout;
-}
-
-struct XSmem {  // the state of one trajectory in shared memory: element j at p[j * 128]
-    float* p;
-    __device__ __forceinline__ float operator[](int j) const { return p[j * 128]; }
+// ------------------------------------------------------------------- per-step scalars
+// Both integrators advance the state as x' = A x + Bc g + Cc eps and accumulate sum gm^2 and sum gm eps:
+//   Euler-Maruyama (losses/oc.py:204-219, :316-331):  A = 1 + mu dt, Bc = sigma dt, Cc = sigma sqrt(dt);
+//       rnd += 1/2 dt sum gm^2 (+ sqrt(dt) sum gm eps)
+//   exponential integrator (:429-443):                A = alpha_k, Bc = beta_k^2 sigma^2, Cc = sigma beta_k;
+//       rnd += 1/2 beta_k^2 sigma^2 sum g^2 (+ sigma beta_k sum g eps)
+struct StepK {
+    float A, Bc, Cc, cost_scale, ito_scale;
+    float sigma, lerp_w, one_m_w, gate_outer, outer, cm, cs;
+    bool w_lt_half, gate_scalar, ref_ctrl, from_hbm;
+    int dim;
 };
 
-template <int DPAD>
-__device__ __forceinline__ void store_a_split16(uint32_t addr_hi, uint32_t addr_lo, const XSmem& x) {
-#pragma unroll
-    for (int c = 0; c < DPAD; c += 8) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tc::split_bf16_pair(x[c + 2 * q], x[c + 2 * q + 1], hi[q], lo[q]);
-        tc::tmem_st4(addr_hi + c / 2, hi);
-        tc::tmem_st4(addr_lo + c / 2, lo);
+__device__ __forceinline__ StepK make_step_k(const SdesRolloutDesc& d, const float* __restrict__ tab, const float* __restrict__ gate_row) {
+    StepK k;
+    const float dt = tab[TAB_DT], sqrt_dt = tab[TAB_SQRT_DT], mu = tab[TAB_MU], sigma = tab[TAB_SIGMA];
+    k.sigma = sigma;
+    if (d.loss_kind == SDES_LOSS_EXP_INTEGRATOR) {
+        const float beta_k = tab[TAB_BETA_K], sg = d.sigma;
+        const float bb_ss = (beta_k * beta_k) * (sg * sg);
+        k.A = tab[TAB_ALPHA_K];
+        k.Bc = bb_ss;
+        k.Cc = sg * beta_k;
+        k.cost_scale = 0.5f * bb_ss;
+        k.ito_scale = sg * beta_k;
+    } else {
+        k.A = fmaf(mu, dt, 1.0f);
+        k.Bc = sigma * dt;
+        k.Cc = sigma * sqrt_dt;
+        k.cost_scale = 0.5f * dt;
+        k.ito_scale = sqrt_dt;
     }
-    if (DPAD % 16 == 8) {
-        const uint32_t z[4] = {0u, 0u, 0u, 0u};
-        tc::tmem_st4(addr_hi + DPAD / 2, z);
-        tc::tmem_st4(addr_lo + DPAD / 2, z);
-    }
+    k.lerp_w = tab[TAB_LERP_W];
+    k.one_m_w = 1.0f - k.lerp_w;
+    k.w_lt_half = k.lerp_w < 0.5f;
+    k.outer = (d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : sigma) * d.scale_score;
+    k.gate_scalar = !(d.flags & SDES_F_HAS_GATE) || d.gate_dim == 1;
+    k.gate_outer = k.outer * gate_row[0];
+    k.cm = d.clip_model;
+    k.cs = d.clip_score;
+    k.ref_ctrl = (d.flags & SDES_F_REFERENCE_CTRL) != 0;
+    k.from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
+    k.dim = d.dim;
+    return k;
 }
 
-__device__ __forceinline__ void gelu_split16_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8], const float4 b0, const float4 b1) {
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float a[8];
-    uint32_t hi[4], lo[4];
+// ------------------------------------------------------------------- noise
+// Four standard normals for (trajectory, step, dim chunk): Philox4x32-10 with the round keys read from the kernel
+// parameters, then two Box-Muller pairs.  Same stream as normal4_call / oracle/philox.py.
+__device__ __forceinline__ float4 normal4_rk(const uint32_t (&rk)[20], uint32_t traj, uint32_t step, uint32_t chunk) {
+    uint32_t c0 = traj, c1 = step, c2 = chunk, c3 = PHILOX_STREAM;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = gelu_fast(v[q] + bb[q]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) tc::split_bf16_pair(a[2 * q], a[2 * q + 1], hi[q], lo[q]);
-    tc::tmem_st4(addr_hi, hi);
-    tc::tmem_st4(addr_lo, lo);
-}
-
-__device__ __forceinline__ void group_bar4(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-
-__device__ __forceinline__ void run_layer4(GroupCtx& c, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K16, int N) {
-    tc::wait_st();
-    tc::fence_before();
-    group_bar4(c.g);
-    if (c.gtid == 0) {
-        tc::fence_after();
-        tc::issue_layer_bf16x3(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K16, N);
-        tc::mma_commit(c.bar);
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c3 = lo0;
     }
-    tc::mbar_wait(c.bar, c.phase);
-    c.phase ^= 1u;
-    tc::fence_after();
+    float4 e;
+    box_muller(c0, c1, e.x, e.y);
+    box_muller(c2, c3, e.z, e.w);
+    return e;
 }
 
-__device__ __forceinline__ void layer_epilogue4(const GroupCtx& c, const float* __restrict__ bias) {
-    float a[8], b[8];
-    tc::tmem_ld8(c.l_d, a);
-    const float4* b4 = reinterpret_cast<const float4*>(bias);
+// ------------------------------------------------------------------- target "globals"
+// What the per-dimension score of the target needs from the WHOLE state, evaluated once per step before the MLP
+// (in the shadow of the input layer's MMAs).
+struct TgtGlobals {
+    float2 gs[GMM_ACT / 2];  // GMM: score on the leading dimension pairs that differ between components
+    int np;                  // GMM: number of such pairs (1, 2 or 4)
+    float f_ninv, f_s0;      // funnel: -exp(-x_0), score of dimension 0
+};
+
+// Shared-memory parameter images of the lean kernel
+struct LeanSmem {
+    const float* gmu;    // [K2][GMM_ACT]  -mu_k on the leading dims
+    const float* gh;     // [K2][GMM_ACT]  h_k = 1/2 sigma_k^-2
+    const float* c2;     // [K2]           log2(e) (log w_k - sum_j log sigma_kj - d/2 log 2 pi)
+    const float* nmu0;   // [DPAD]         -mu of component 0 (dims shared by all components)
+    const float* nh20;   // [DPAD]         -2 h of component 0
+    const float* prior;  // loc[DPAD] | inv_var[DPAD] | lognorm
+    const float* bo;     // output-layer bias [NOUT]
+    int K2;
+};
+
+// Responsibility-weighted score on the first 2 NP dims (distr/gauss.py:119-140 through autograd, distr/base.py:130-137;
+// analytic form SURVEY App. A.4): online softmax over the components, two per iteration, logits in log2 units,
+// direct (x - mu)^2 form (the expanded form cancels catastrophically for modes at |mu| ~ 40).
+template <int NP>
+__device__ __forceinline__ void gmm_active_score(const XPair& xs, const LeanSmem& sm, float2 (&gs)[GMM_ACT / 2]) {
+    float2 xv[NP], acc[NP];
+#pragma unroll
+    for (int r = 0; r < NP; ++r) {
+        xv[r] = xs.pair(r);
+        acc[r] = make_float2(0.f, 0.f);
+    }
+    float m = -INFINITY, ssum = 0.f;
 #pragma unroll 1
-    for (int ch = 0; ch < 8; ch += 2) {
-        const float4 p0 = b4[2 * ch], p1 = b4[2 * ch + 1], p2 = b4[2 * ch + 2], p3 = b4[2 * ch + 3];
-        tc::wait_ld_tie<8>(a);
-        tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
-        gelu_split16_store8(c.l_hi + 4u * ch, c.l_lo + 4u * ch, a, p0, p1);
-        tc::wait_ld_tie<8>(b);
-        if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
-        gelu_split16_store8(c.l_hi + 4u * (ch + 1), c.l_lo + 4u * (ch + 1), b, p2, p3);
+    for (int k = 0; k < sm.K2; k += 2) {
+        const float2* mua = reinterpret_cast<const float2*>(sm.gmu + k * GMM_ACT);
+        const float2* ha = reinterpret_cast<const float2*>(sm.gh + k * GMM_ACT);
+        float qa = 0.f, qb = 0.f;
+        float2 ta[NP], tb[NP];
+#pragma unroll
+        for (int r = 0; r < NP; ++r) {
+            const float2 da = __fadd2_rn(xv[r], mua[r]), db = __fadd2_rn(xv[r], mua[r + GMM_ACT / 2]);
+            ta[r] = __fmul2_rn(da, ha[r]);
+            tb[r] = __fmul2_rn(db, ha[r + GMM_ACT / 2]);
+            qa = fmaf(da.x, ta[r].x, qa);
+            qb = fmaf(db.x, tb[r].x, qb);
+            qa = fmaf(da.y, ta[r].y, qa);
+            qb = fmaf(db.y, tb[r].y, qb);
+        }
+        const float2 c2 = *reinterpret_cast<const float2*>(sm.c2 + k);
+        const float la = fmaf(qa, -LOG2E, c2.x), lb = fmaf(qb, -LOG2E, c2.y);
+        const float m_new = fmaxf(m, fmaxf(la, lb));
+        float resc, ea, eb;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(resc) : "f"(m - m_new));  // 1 when the max did not move, 0 on the first pair
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(la - m_new));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(lb - m_new));
+        m = m_new;
+        ssum = fmaf(ssum, resc, ea + eb);
+#pragma unroll
+        for (int r = 0; r < NP; ++r) {
+            acc[r] = __fmul2_rn(acc[r], make_float2(resc, resc));
+            acc[r] = __ffma2_rn(make_float2(ea, ea), ta[r], acc[r]);
+            acc[r] = __ffma2_rn(make_float2(eb, eb), tb[r], acc[r]);
+        }
     }
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ssum));
+    inv *= -2.0f;  // score_j = -sum_k p_k (x_j - mu_kj) / sigma_kj^2 = -2 sum_k p_k h_kj (x_j - mu_kj)
+#pragma unroll
+    for (int r = 0; r < NP; ++r) gs[r] = __fmul2_rn(acc[r], make_float2(inv, inv));
 }
 
 template <int DPAD>
-__global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __grid_constant__ KParams p) {
+__device__ __forceinline__ void target_globals(const SdesRolloutDesc& d, const XPair& xs, const LeanSmem& sm, uint32_t gmm_mask, TgtGlobals& tg) {
+    if (d.target_kind == SDES_TARGET_GMM) {
+        if (gmm_mask < 2u) {
+            tg.np = 1;
+            gmm_active_score<1>(xs, sm, tg.gs);
+        } else if (gmm_mask < 4u) {
+            tg.np = 2;
+            gmm_active_score<2>(xs, sm, tg.gs);
+        } else {
+            tg.np = 4;
+            gmm_active_score<4>(xs, sm, tg.gs);
+        }
+    } else if (d.target_kind == SDES_TARGET_FUNNEL) {
+        // distr/funnel.py:71-80
+        float2 sq2 = make_float2(0.f, 0.f);
+        const float2 x01 = xs.pair(0);
+        sq2.y = x01.y * x01.y;
+#pragma unroll
+        for (int r = 1; r < DPAD / 2; ++r) {
+            const float2 v = xs.pair(r);
+            sq2 = __ffma2_rn(v, v, sq2);
+        }
+        const float inv = expf(-x01.x);
+        tg.f_ninv = -inv;
+        tg.f_s0 = -x01.x / d.variance - 0.5f * (float)(d.dim - 1) + 0.5f * (sq2.x + sq2.y) * inv;
+    }
+}
+
+constexpr bool ctrl_needs_target(int ctrl) { return ctrl == SDES_CTRL_SCORE || ctrl == SDES_CTRL_LERP || ctrl == SDES_CTRL_LERP_TARGET; }
+constexpr bool ctrl_needs_prior(int ctrl) { return ctrl == SDES_CTRL_LERP || ctrl == SDES_CTRL_LERP_PRIOR; }
+
+// ------------------------------------------------------------------- the update loop
+// Eight dimensions (four pairs) of one trajectory: network output chunk from TMEM, control = clip(NN) + score part
+// (models/reparam.py: ClippedCtrl :35-36, ScoreCtrl :78-83, LerpCtrl :131-162, LerpPriorCtrl :165-181, LerpTargetCtrl :184-200),
+// noise, cost / Ito sums, state update.  MODE 0: first chunk (may hold the GMM's active pairs and the funnel's
+// dimension 0), MODE 1: any later chunk, MODE 2: DENSE (target score of every dimension in scd[]).
+template <int DPAD, int CTRL, int TGT, int MODE>
+__device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int q, const int step,
+                                             const uint32_t traj, const LeanSmem& sm, const TgtGlobals& tg, const float* scd,
+                                             const float* __restrict__ gate_row, const float* __restrict__ noise_row, float* xo,
+                                             const int xo_st, float2& cost2, float2& ito2) {
+    const SdesRolloutDesc& d = p.d;
+    float nn[8];
+    tc::tmem_ld8(c.l_d + 8u * q, nn);
+    const int j0 = 8 * q;
+    float e[8];
+    if (k.from_hbm) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) e[r] = (j0 + r < k.dim) ? noise_row[j0 + r] : 0.f;
+    } else {
+        const float4 n0 = normal4_rk(p.philox_rk, traj, (uint32_t)step, (uint32_t)(2 * q));
+        e[0] = n0.x; e[1] = n0.y; e[2] = n0.z; e[3] = n0.w;
+        if (j0 + 4 < k.dim) {
+            const float4 n1 = normal4_rk(p.philox_rk, traj, (uint32_t)step, (uint32_t)(2 * q + 1));
+            e[4] = n1.x; e[5] = n1.y; e[6] = n1.z; e[7] = n1.w;
+        } else {
+            e[4] = e[5] = e[6] = e[7] = 0.f;
+        }
+        if (j0 + 8 > k.dim) {  // the chunk that holds the last dimension: padded dimensions get no noise (their state stays 0)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) e[r] = (j0 + r < k.dim) ? e[r] : 0.f;
+        }
+    }
+    tc::wait_ld_tie<8>(nn);
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+        const int r = 4 * q + pp;  // pair index
+        float2 x2 = xs.pair(r);
+        const float2 b2 = *reinterpret_cast<const float2*>(sm.bo + 2 * r);
+        float2 g2 = __fadd2_rn(make_float2(nn[2 * pp], nn[2 * pp + 1]), b2);
+        g2.x = clipf(g2.x, k.cm);
+        g2.y = clipf(g2.y, k.cm);
+        float2 ps2 = make_float2(0.f, 0.f);
+        if (ctrl_needs_prior(CTRL) || k.ref_ctrl) {  // (loc - x) / scale^2   distr/gauss.py:222-223
+            const float2 pl = *reinterpret_cast<const float2*>(sm.prior + 2 * r), iv = *reinterpret_cast<const float2*>(sm.prior + DPAD + 2 * r);
+            ps2 = __fmul2_rn(__ffma2_rn(x2, make_float2(-1.f, -1.f), pl), iv);
+        }
+        if (CTRL != SDES_CTRL_CLIPPED) {
+            float2 ts2 = make_float2(0.f, 0.f);
+            if (ctrl_needs_target(CTRL)) {
+                if (TGT == SDES_TARGET_GMM) {
+                    if (MODE == 2) {
+                        ts2 = make_float2(scd[2 * r], scd[2 * r + 1]);
+                    } else {
+                        // dimensions shared by all components factor out of the mixture: Gaussian score 2 h (mu - x)
+                        const float2 nmu = *reinterpret_cast<const float2*>(sm.nmu0 + 2 * r), nh2 = *reinterpret_cast<const float2*>(sm.nh20 + 2 * r);
+                        ts2 = __fmul2_rn(__fadd2_rn(x2, nmu), nh2);
+                        if (MODE == 0 && pp < tg.np) ts2 = tg.gs[pp];
+                    }
+                } else if (TGT == SDES_TARGET_MULTIWELL) {
+                    // distr/double_well.py:39-45, :165-179
+                    const float2 y = __fadd2_rn(x2, make_float2(-d.shift, -d.shift));
+                    const float2 a = __ffma2_rn(y, y, make_float2(-d.separation, -d.separation));
+                    const float2 dw = __fmul2_rn(__fmul2_rn(a, y), make_float2(-4.f, -4.f));
+                    ts2.x = (2 * r < d.n_double_wells) ? dw.x : (2 * r < k.dim ? -y.x : 0.f);
+                    ts2.y = (2 * r + 1 < d.n_double_wells) ? dw.y : (2 * r + 1 < k.dim ? -y.y : 0.f);
+                } else {
+                    // distr/funnel.py:71-80: -x_j exp(-x_0) for j >= 1
+                    ts2 = __fmul2_rn(x2, make_float2(tg.f_ninv, tg.f_ninv));
+                    if (MODE == 0 && pp == 0) ts2.x = tg.f_s0;
+                }
+            }
+            float2 inner;
+            if (CTRL == SDES_CTRL_LERP) {
+                // torch.lerp: w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)
+                const float2 diff = __ffma2_rn(ps2, make_float2(-1.f, -1.f), ts2);
+                if (k.w_lt_half) inner = __ffma2_rn(make_float2(k.lerp_w, k.lerp_w), diff, ps2);
+                else inner = __ffma2_rn(diff, make_float2(-k.one_m_w, -k.one_m_w), ts2);
+            } else if (CTRL == SDES_CTRL_LERP_PRIOR) {
+                inner = __fmul2_rn(ps2, make_float2(k.one_m_w, k.one_m_w));
+            } else if (CTRL == SDES_CTRL_LERP_TARGET) {
+                inner = __fmul2_rn(ts2, make_float2(k.lerp_w, k.lerp_w));
+            } else {
+                inner = ts2;
+            }
+            inner.x = clipf(inner.x, k.cs);
+            inner.y = clipf(inner.y, k.cs);
+            if (k.gate_scalar) {
+                g2 = __ffma2_rn(inner, make_float2(k.gate_outer, k.gate_outer), g2);
+            } else {
+                const float2 gt = *reinterpret_cast<const float2*>(gate_row + 2 * r);
+                g2 = __ffma2_rn(__fmul2_rn(inner, gt), make_float2(k.outer, k.outer), g2);
+            }
+        }
+        float2 gm2 = g2;
+        if (k.ref_ctrl) gm2 = __ffma2_rn(ps2, make_float2(-k.sigma, -k.sigma), g2);  // g - sigma * prior score  (solver/oc.py:305-306)
+        const float2 e2 = make_float2(e[2 * pp], e[2 * pp + 1]);
+        cost2 = __ffma2_rn(gm2, gm2, cost2);
+        ito2 = __ffma2_rn(gm2, e2, ito2);
+        x2 = __ffma2_rn(make_float2(k.A, k.A), x2, __ffma2_rn(make_float2(k.Bc, k.Bc), g2, __fmul2_rn(e2, make_float2(k.Cc, k.Cc))));
+        xs.set_pair(r, x2);
+        if (xo != nullptr) {
+            if (2 * r < k.dim) xo[(2 * r) * xo_st] = x2.x;
+            if (2 * r + 1 < k.dim) xo[(2 * r + 1) * xo_st] = x2.y;
+        }
+    }
+}
+
+template <int DPAD, int CTRL, int TGT, bool DENSE>
+__device__ __forceinline__ void update_phase(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int step, const uint32_t traj,
+                                             const LeanSmem& sm, const TgtGlobals& tg, const float* scd, const float* __restrict__ gate_row,
+                                             const float* __restrict__ noise_row, float* xo, const int xo_st, float2& cost2, float2& ito2) {
+    if (DENSE) {
+#pragma unroll
+        for (int q = 0; q < DPAD / 8; ++q)
+            if (8 * q < k.dim) chunk_update<DPAD, CTRL, TGT, 2>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2);
+    } else {
+        chunk_update<DPAD, CTRL, TGT, 0>(p, k, c, xs, 0, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2);
+        const int nq = (k.dim + 7) >> 3;
+#pragma unroll 1
+        for (int q = 1; q < nq; ++q) chunk_update<DPAD, CTRL, TGT, 1>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2);
+    }
+}
+
+template <int DPAD, bool DENSE>
+__global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams p) {
     constexpr int NOUT = (DPAD + 15) / 16 * 16;
     constexpr uint32_t K0B = (DPAD + 15) & ~15;
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t s_wbar;
-    __shared__ uint64_t s_mbar[MMA4_GROUPS];
+    __shared__ uint64_t s_mbar[TC_GROUPS];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_tile[MMA4_GROUPS];
+    __shared__ uint32_t s_tile[TC_GROUPS];
 
     const SdesRolloutDesc& d = p.d;
     const float* ws = reinterpret_cast<const float*>(d.workspace);
-    const int dim = d.dim, T = d.n_steps, K = d.n_components, nh = d.n_hidden;
+    const int dim = d.dim, T = d.n_steps, K = d.target_kind == SDES_TARGET_GMM ? d.n_components : 0, nh = d.n_hidden;
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    // ---- shared memory: [bf16 weight image + biases | gmm mu | gmm h | gmm c | prior | ref | state x]
+    // Which instantiation runs: the prologue kernel left the GMM's dimension-pair mask in the workspace.  A mixture
+    // whose components differ beyond the first GMM_ACT dims needs the per-step score of every dimension (DENSE).
+    const uint32_t gmm_mask = reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1];
+    const bool want_dense = d.target_kind == SDES_TARGET_GMM && gmm_mask >= (1u << (GMM_ACT / 2)) && ctrl_needs_target(d.ctrl_kind);
+    if (want_dense != DENSE) return;
+
+    // ---- shared memory: [bf16 weight image + biases | gmm -mu, h (leading dims) | c2 | -mu0 | -2 h0 | prior | ref | state x]
     float* s_w = smem;
     const int K2 = (K + 1) & ~1;
-    float* s_mu = s_w + ((p.ws.w_mma4_len + 31) & ~31ll);
-    float* s_h = s_mu + K2 * DPAD;
-    float* s_c = s_h + K2 * DPAD;
-    float* s_prior = s_c + 64;
+    float* s_gmu = s_w + ((p.ws.w_mma4_len + 31) & ~31ll);
+    float* s_gh = s_gmu + K2 * GMM_ACT;
+    float* s_c2 = s_gh + K2 * GMM_ACT;
+    float* s_nmu0 = s_c2 + 64;
+    float* s_nh20 = s_nmu0 + DPAD;
+    float* s_prior = s_nh20 + DPAD;
     float* s_ref = s_prior + 2 * DPAD + 8;
     float* s_x = s_ref + 2 * DPAD + 8;
 
@@ -564,13 +548,14 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
     }
     if (tid == 0) {
         tc::mbar_init(&s_wbar, 1);
-        for (int g = 0; g < MMA4_GROUPS; ++g) tc::mbar_init(&s_mbar[g], 1);
+        for (int g = 0; g < TC_GROUPS; ++g) tc::mbar_init(&s_mbar[g], 1);
         tc::fence_mbar_init();
     }
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     if (tid == 0) {
+        // weights: TMA bulk copies global -> shared, all counted on one mbarrier
         const uint32_t total = (uint32_t)(p.ws.w_mma4_len * sizeof(float));
         tc::mbar_arrive_expect_tx(&s_wbar, total);
         const char* src = reinterpret_cast<const char*>(ws + p.ws.w_mma4);
@@ -580,11 +565,16 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
             tc::bulk_g2s(dst + off, src + off, n, &s_wbar);
         }
     }
-    for (int e = tid; e < K2 * DPAD; e += blockDim.x) {
-        s_mu[e] = ws[p.ws.gmm_mu + e];
-        s_h[e] = ws[p.ws.gmm_h + e];
+    for (int e = tid; e < K2 * GMM_ACT; e += blockDim.x) {
+        const int k = e / GMM_ACT, j = e % GMM_ACT;
+        s_gmu[e] = j < DPAD ? -ws[p.ws.gmm_mu + k * DPAD + j] : 0.f;
+        s_gh[e] = j < DPAD ? ws[p.ws.gmm_h + k * DPAD + j] : 0.f;
     }
-    for (int e = tid; e < 64; e += blockDim.x) s_c[e] = ws[p.ws.gmm_c + e];
+    for (int e = tid; e < 64; e += blockDim.x) s_c2[e] = (e < K2 ? ws[p.ws.gmm_c + e] : -INFINITY) * LOG2E;
+    for (int e = tid; e < DPAD; e += blockDim.x) {
+        s_nmu0[e] = K > 0 ? -ws[p.ws.gmm_mu + e] : 0.f;
+        s_nh20[e] = K > 0 ? -2.0f * ws[p.ws.gmm_h + e] : 0.f;
+    }
     for (int e = tid; e < 2 * DPAD + 8; e += blockDim.x) {
         s_prior[e] = e <= 2 * DPAD ? ws[p.ws.prior + e] : 0.f;
         s_ref[e] = e <= 2 * DPAD ? ws[p.ws.ref + e] : 0.f;
@@ -600,11 +590,13 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
     const uint32_t lo_hi = lh_base + (uint32_t)nh * 2u * LH_HALF, lo_lo = lo_hi + LO_HALF;
     const float* s_bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_w) + 2 * L0_HALF + (size_t)nh * 2 * LH_HALF + 2 * LO_HALF);
 
-    TargetSmem tsm{s_mu, s_h, s_c, reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1], s_prior, s_ref};
+    // generic (once-per-tile) evaluations read the full-width target images in the workspace
+    const TargetSmem tsm{ws + p.ws.gmm_mu, ws + p.ws.gmm_h, ws + p.ws.gmm_c, gmm_mask, s_prior, s_ref};
+    const LeanSmem lsm{s_gmu, s_gh, s_c2, s_nmu0, s_nh20, s_prior, s_bias + nh * C, K2};
     GroupCtx c;
     c.g = warp >> 2;
     c.gtid = tid & 127;
-    const uint32_t tbase = s_tmem + (uint32_t)(c.g * GROUP4_COLS);
+    const uint32_t tbase = s_tmem + (uint32_t)(c.g * GROUP_COLS);
     c.t_d = tbase;
     c.t_hi = tbase + 64;
     c.t_lo = tbase + 96;
@@ -614,20 +606,26 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
     c.l_lo = c.t_lo + lane_off;
     c.bar = &s_mbar[c.g];
     c.phase = 0;
-    const XSmem xs{s_x + c.g * (DPAD * 128) + c.gtid};
+    const XPair xs{reinterpret_cast<float2*>(s_x + c.g * (DPAD * 128)) + c.gtid};
 
     uint32_t* counter = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.counter);
     const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
     const bool ret_traj = (d.flags & SDES_F_RETURN_TRAJ) != 0;
     const int64_t B = d.batch;
     const uint32_t n_tiles = (uint32_t)((B + 127) / 128);
+
+    // Work items are (time chunk, tile) pairs handed out chunk-major from one counter: a tile's T steps are cut into
+    // n_chunks pieces so that the tiles do not quantise into rounds with a mostly idle last one.  Between chunks the
+    // tile's state (x, rnd) parks in the workspace ([tile][j][128] so warps read and write whole 128-byte lines, L2
+    // resident) and a per-tile progress word orders producer and consumer.  An item only ever waits on an item handed
+    // out earlier, so there is no deadlock whatever the residency.
     const int n_chunks = p.n_chunks, chunk_steps = p.chunk_steps;
     const uint32_t n_items = n_tiles * (uint32_t)n_chunks;
     float* state = const_cast<float*>(ws) + p.ws.state;
     uint32_t* progress = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.progress);
     for (;;) {
         if (c.gtid == 0) s_tile[c.g] = atomicAdd(counter, 1u);
-        group_bar4(c.g);
+        group_bar(c.g);
         const uint32_t item = s_tile[c.g];
         if (item >= n_items) break;
         const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
@@ -640,10 +638,15 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
         if (chunk == 0) {
             const TrajRef o0 = traj_ref(d, d.xs, 0, rrow);
 #pragma unroll
-            for (int j = 0; j < DPAD; ++j) {
-                const float v = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
-                xs.p[j * 128] = v;
-                if (ret_traj && valid && j < dim) o0.p[j * o0.stride] = v;
+            for (int r = 0; r < DPAD / 2; ++r) {
+                float2 v;
+                v.x = (2 * r < dim) ? __ldg(d.x0 + rrow * dim + 2 * r) : 0.f;
+                v.y = (2 * r + 1 < dim) ? __ldg(d.x0 + rrow * dim + 2 * r + 1) : 0.f;
+                xs.set_pair(r, v);
+                if (ret_traj && valid) {
+                    if (2 * r < dim) o0.p[(2 * r) * o0.stride] = v.x;
+                    if (2 * r + 1 < dim) o0.p[(2 * r + 1) * o0.stride] = v.y;
+                }
             }
             rnd = initial_rnd<DPAD>(d, xs, tsm);
         } else {
@@ -653,9 +656,9 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
                 } while (seen < chunk);
             }
-            group_bar4(c.g);
+            group_bar(c.g);
 #pragma unroll
-            for (int j = 0; j < DPAD; ++j) xs.p[j * 128] = __ldcg(st + j * 128);
+            for (int r = 0; r < DPAD / 2; ++r) xs.set_pair(r, make_float2(__ldcg(st + (2 * r) * 128), __ldcg(st + (2 * r + 1) * 128)));  // L2 reads: another SM wrote them
             rnd = __ldcg(st + DPAD * 128);
         }
         const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)rrow);
@@ -664,60 +667,58 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
 
         for (int i = i_begin; i < i_end; ++i) {
             const float* tab = ws + p.ws.tab + (int64_t)i * TAB_STRIDE;
-            float sc[DPAD];
-            score_part<DPAD>(d, xs, sc, tsm, ws + p.ws.gate + (int64_t)i * DPAD, tab[TAB_SIGMA], tab[TAB_LERP_W]);
-            store_a_split16<DPAD>(c.l_hi, c.l_lo, xs);
-            run_layer4(c, l0_hi, l0_lo, (int)K0B, C);
-            layer_epilogue4(c, ws + p.ws.emb + (int64_t)i * C);
+            const float* gate_row = ws + p.ws.gate + (int64_t)i * DPAD;
+            // ---- control MLP on the tensor cores (models/mlp.py:114-122): input layer first, so that the target's global
+            //      quantities are evaluated while its MMAs run
+            store_a_from_x<DPAD>(c.l_hi, c.l_lo, xs);
+            issue_layer(c, l0_hi, l0_lo, (int)K0B, C);
+            TgtGlobals tg;
+            float scd[DENSE ? DPAD : 1];
+            if constexpr (DENSE) {
+                // score of every dimension, components differing on the first 8 / 16 / all dimension pairs (sdes_step.cuh)
+                constexpr int NPAIR = DPAD / 2;
+                if (NPAIR > 8 && gmm_mask < 256u) gmm_eval_na<DPAD, (NPAIR > 8 ? 8 : NPAIR), true>(xs, scd, tsm, K);
+                else if (NPAIR > 16 && gmm_mask < 65536u) gmm_eval_na<DPAD, (NPAIR > 16 ? 16 : NPAIR), true>(xs, scd, tsm, K);
+                else gmm_eval_na<DPAD, NPAIR, true>(xs, scd, tsm, K);
+            } else if (ctrl_needs_target(d.ctrl_kind)) {
+                target_globals<DPAD>(d, xs, lsm, gmm_mask, tg);
+            }
+            wait_layer(c);
+            layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
 #pragma unroll 1
             for (int l = 0; l < nh; ++l) {
-                run_layer4(c, lh_base + (uint32_t)l * 2u * LH_HALF, lh_base + (uint32_t)l * 2u * LH_HALF + LH_HALF, C, C);
-                layer_epilogue4(c, s_bias + l * C);
+                issue_layer(c, lh_base + (uint32_t)l * 2u * LH_HALF, lh_base + (uint32_t)l * 2u * LH_HALF + LH_HALF, C, C);
+                wait_layer(c);
+                layer_epilogue(c, s_bias + l * C);
             }
-            run_layer4(c, lo_hi, lo_lo, C, NOUT);
-            {
-                const StepCoef sc_ = make_step_coef(d, tab);
-                const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
-                const float* bo = s_bias + nh * C;
-                const TrajRef xo_ref = traj_ref(d, d.xs, i + 1, rrow);
-                float* xo = (ret_traj && valid) ? xo_ref.p : nullptr;
-                const int xo_st = xo_ref.stride;
-                float cost = 0.f, ito = 0.f;
-                float na[8], nb[8];
-                tc::tmem_ld8(c.l_d, na);
-#pragma unroll
-                for (int q = 0; q < DPAD / 8; q += 2) {
-                    tc::wait_ld_tie<8>(na);
-                    if (q + 1 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 1), nb);
-                    {
-                        float xv[8];
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) { na[r] += bo[8 * q + r]; xv[r] = xs[8 * q + r]; }
-                        update4(sc_, &xv[0], &na[0], &sc[8 * q], s_prior + 8 * q, s_prior + DPAD + 8 * q, 8 * q, i, traj, nrow, cost, ito);
-                        update4(sc_, &xv[4], &na[4], &sc[8 * q + 4], s_prior + 8 * q + 4, s_prior + DPAD + 8 * q + 4, 8 * q + 4, i, traj, nrow, cost, ito);
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            xs.p[(8 * q + r) * 128] = xv[r];
-                            if (xo != nullptr && 8 * q + r < dim) xo[(8 * q + r) * xo_st] = xv[r];
-                        }
-                    }
-                    if (q + 1 < DPAD / 8) {
-                        tc::wait_ld_tie<8>(nb);
-                        if (q + 2 < DPAD / 8) tc::tmem_ld8(c.l_d + 8u * (q + 2), na);
-                        float xv[8];
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) { nb[r] += bo[8 * (q + 1) + r]; xv[r] = xs[8 * (q + 1) + r]; }
-                        update4(sc_, &xv[0], &nb[0], &sc[8 * q + 8], s_prior + 8 * q + 8, s_prior + DPAD + 8 * q + 8, 8 * q + 8, i, traj, nrow, cost, ito);
-                        update4(sc_, &xv[4], &nb[4], &sc[8 * q + 12], s_prior + 8 * q + 12, s_prior + DPAD + 8 * q + 12, 8 * q + 12, i, traj, nrow, cost, ito);
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            xs.p[(8 * (q + 1) + r) * 128] = xv[r];
-                            if (xo != nullptr && 8 * (q + 1) + r < dim) xo[(8 * (q + 1) + r) * xo_st] = xv[r];
-                        }
-                    }
-                }
-                finish_step(d, sc_, tab, cost, ito, rnd);
+            issue_layer(c, lo_hi, lo_lo, C, NOUT);
+            const StepK k = make_step_k(d, tab, gate_row);
+            const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
+            const TrajRef xo_ref = traj_ref(d, d.xs, i + 1, rrow);
+            float* xo = (ret_traj && valid) ? xo_ref.p : nullptr;
+            float2 cost2 = make_float2(0.f, 0.f), ito2 = make_float2(0.f, 0.f);
+            wait_layer(c);
+            // ---- network output streamed from TMEM into the control / cost / state update
+#define SDES_UPD(CTRL, TGT) update_phase<DPAD, CTRL, TGT, DENSE>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2)
+#define SDES_UPD_T(CTRL)                                                              \
+    if (DENSE || d.target_kind == SDES_TARGET_GMM) SDES_UPD(CTRL, SDES_TARGET_GMM);    \
+    else if (d.target_kind == SDES_TARGET_MULTIWELL) SDES_UPD(CTRL, SDES_TARGET_MULTIWELL); \
+    else SDES_UPD(CTRL, SDES_TARGET_FUNNEL);
+            if (d.ctrl_kind == SDES_CTRL_LERP) {
+                SDES_UPD_T(SDES_CTRL_LERP)
+            } else if (d.ctrl_kind == SDES_CTRL_SCORE) {
+                SDES_UPD_T(SDES_CTRL_SCORE)
+            } else if (d.ctrl_kind == SDES_CTRL_LERP_TARGET) {
+                SDES_UPD_T(SDES_CTRL_LERP_TARGET)
+            } else if (!DENSE) {
+                if (d.ctrl_kind == SDES_CTRL_LERP_PRIOR) SDES_UPD(SDES_CTRL_LERP_PRIOR, SDES_TARGET_GMM);
+                else SDES_UPD(SDES_CTRL_CLIPPED, SDES_TARGET_GMM);
             }
+#undef SDES_UPD_T
+#undef SDES_UPD
+            rnd = fmaf(k.cost_scale, cost2.x + cost2.y, rnd);
+            if (d.flags & SDES_F_SUB_DIV_INT) rnd -= tab[TAB_DIV_INT];
+            if (d.flags & SDES_F_COMPUTE_ITO) rnd = fmaf(k.ito_scale, ito2.x + ito2.y, rnd);
         }
         if (i_end == T) {
             rnd += terminal_rnd<DPAD>(d, xs, tsm);
@@ -729,10 +730,14 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < DPAD; ++j) __stcg(st + j * 128, xs[j]);
+            for (int r = 0; r < DPAD / 2; ++r) {
+                const float2 v = xs.pair(r);
+                __stcg(st + (2 * r) * 128, v.x);
+                __stcg(st + (2 * r + 1) * 128, v.y);
+            }
             __stcg(st + DPAD * 128, rnd);
             __threadfence();
-            group_bar4(c.g);
+            group_bar(c.g);
             if (c.gtid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(chunk + 1u) : "memory");
         }
     }
@@ -741,71 +746,53 @@ __global__ void __launch_bounds__(MMA4_THREADS, 1) rollout_mma4_kernel(const __g
     if (warp == 0) tc::tmem_dealloc(s_tmem, TMEM_COLS);
 }
 
-size_t mma4_smem_bytes(const KParams& p) {
-    const int dpad = p.ws.dpad, K = p.d.n_components;
-    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * dpad + 64 + 2 * (2 * dpad + 8) +
-                      (size_t)MMA4_GROUPS * dpad * 128;
+size_t tc_smem_bytes(const KParams& p) {
+    const int dpad = p.ws.dpad, K = p.d.target_kind == SDES_TARGET_GMM ? p.d.n_components : 0;
+    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
+                      (size_t)TC_GROUPS * dpad * 128;
     return fl * sizeof(float);
 }
 
-bool mma4_supported(const KParams& p) { return mma_supported(p) && mma4_smem_bytes(p) <= 226u * 1024u; }
+bool mma_supported(const KParams& p) {
+    return p.d.dim <= 64 && p.d.n_hidden <= SDES_MAX_HIDDEN && tc_smem_bytes(p) <= 226u * 1024u;
+}
 
-template <int DPAD>
-static cudaError_t launch_mma4_t(const KParams& p, int sm_count, cudaStream_t stream) {
-    const size_t smem = mma4_smem_bytes(p);
-    cudaError_t e = cudaFuncSetAttribute(rollout_mma4_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int DPAD, bool DENSE>
+static cudaError_t launch_tc_t(const KParams& p, int sm_count, cudaStream_t stream) {
+    const size_t smem = tc_smem_bytes(p);
+    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<DPAD, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // work items = tiles x time chunks: a group that finds no first-chunk tile left starts on a second chunk and waits
     // for its predecessor, so every SM is used even when there are fewer tiles than resident groups
     const int64_t items = ((p.d.batch + 127) / 128) * (int64_t)(p.n_chunks > 0 ? p.n_chunks : 1);
-    int grid = (int)((items + MMA4_GROUPS - 1) / MMA4_GROUPS);
+    int grid = (int)((items + TC_GROUPS - 1) / TC_GROUPS);
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
-    rollout_mma4_kernel<DPAD><<<grid, MMA4_THREADS, smem, stream>>>(p);
+    rollout_tc_kernel<DPAD, DENSE><<<grid, TC_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_mma4(const KParams& p, int sm_count, cudaStream_t stream) {
+// Launches the lean kernel and, when the descriptor can need it (a multi-component GMM whose score enters the
+// control, d > GMM_ACT), the DENSE one as well: whichever does not match the prologue's dimension mask exits at once.
+cudaError_t launch_rollout_tc(const KParams& p, int sm_count, cudaStream_t stream, int* n_launches) {
+    const bool maybe_dense = p.d.target_kind == SDES_TARGET_GMM && p.d.n_components > 1 && p.d.dim > GMM_ACT && ctrl_needs_target(p.d.ctrl_kind);
+    cudaError_t e = cudaErrorInvalidValue;
+    *n_launches = maybe_dense ? 2 : 1;
     switch (p.ws.dpad) {
-        case 8: return launch_mma4_t<8>(p, sm_count, stream);
-        case 16: return launch_mma4_t<16>(p, sm_count, stream);
-        case 32: return launch_mma4_t<32>(p, sm_count, stream);
-        case 48: return launch_mma4_t<48>(p, sm_count, stream);
-        case 56: return launch_mma4_t<56>(p, sm_count, stream);
-        case 64: return launch_mma4_t<64>(p, sm_count, stream);
+        case 8: return launch_tc_t<8, false>(p, sm_count, stream);
+#define SDES_TC_CASE(DP)                                                       \
+    case DP:                                                                   \
+        e = launch_tc_t<DP, false>(p, sm_count, stream);                       \
+        if (e == cudaSuccess && maybe_dense) e = launch_tc_t<DP, true>(p, sm_count, stream); \
+        return e;
+        SDES_TC_CASE(16)
+        SDES_TC_CASE(32)
+        SDES_TC_CASE(48)
+        SDES_TC_CASE(56)
+        SDES_TC_CASE(64)
+#undef SDES_TC_CASE
     }
-    return cudaErrorInvalidValue;
-}
-
-size_t mma_smem_bytes(const KParams& p) {
-    const int dpad = p.ws.dpad, K = p.d.n_components;
-    const size_t fl = (size_t)p.ws.w_mma_len + 2 * (size_t)((K + 1) & ~1) * dpad + 64 + 2 * (2 * dpad + 8);
-    return fl * sizeof(float);
-}
-
-template <int DPAD>
-static cudaError_t launch_mma_t(const KParams& p, int sm_count, cudaStream_t stream) {
-    const size_t smem = mma_smem_bytes(p);
-    cudaError_t e = cudaFuncSetAttribute(rollout_mma_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int64_t items = ((p.d.batch + 127) / 128) * (int64_t)(p.n_chunks > 0 ? p.n_chunks : 1);
-    int grid = (int)((items + MMA_GROUPS - 1) / MMA_GROUPS);
-    if (grid > sm_count) grid = sm_count;
-    if (grid < 1) grid = 1;
-    rollout_mma_kernel<DPAD><<<grid, MMA_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_rollout_mma(const KParams& p, int sm_count, cudaStream_t stream) {
-    switch (p.ws.dpad) {
-        case 8: return launch_mma_t<8>(p, sm_count, stream);
-        case 16: return launch_mma_t<16>(p, sm_count, stream);
-        case 32: return launch_mma_t<32>(p, sm_count, stream);
-        case 48: return launch_mma_t<48>(p, sm_count, stream);
-        case 56: return launch_mma_t<56>(p, sm_count, stream);
-        case 64: return launch_mma_t<64>(p, sm_count, stream);
-    }
-    return cudaErrorInvalidValue;
+    return e;
 }
 
 }  // namespace sdes

@@ -1,14 +1,14 @@
 // sdes_tc.cuh — tcgen05 / TMEM / mbarrier / bulk-copy primitives (inline PTX, sm_100a) and the
-// "3xTF32" dense layer used by the control MLP.
+// split-precision dense layer used by the control MLP.
 //
 // One GROUP = 4 consecutive warps = 128 trajectories = one M=128 MMA tile; thread r of the group
 // owns TMEM lane r (row r).  Per layer
 //     D[128, N] (TMEM, fp32)  =  A[128, K] (TMEM)  x  W[N, K]^T (shared memory, K-major)
-// is issued by one thread as K/8 k-steps of three kind::tf32 MMAs
-//     A_hi*W_hi + A_lo*W_hi + A_hi*W_lo          (hi = fp32 truncated to tf32, lo = fp32 - hi)
-// which recovers ~2^-21 relative accuracy from the 10-bit-mantissa tensor-core format — the
-// reference computes in true fp32 (TF32 is off by default in PyTorch), so a single tf32 pass
-// (~1e-3 per layer) would not hold the stated 2e-4 tolerance over 100 steps.
+// is issued by one thread as K/16 k-steps of three kind::f16 (bf16) MMAs
+//     A_lo*W_hi + A_hi*W_lo + A_hi*W_hi          (hi = bf16(v), lo = bf16(v - hi): 16 significant bits)
+// which recovers ~2^-16 relative accuracy of sum|a||w| from the 8-bit-mantissa tensor-core format — the
+// reference computes in true fp32 (TF32 is off by default in PyTorch), so a single bf16 / tf32 pass
+// (~4e-3 / 5e-4 per layer) would not hold the stated 2e-4 tolerance over 100 steps.
 #pragma once
 
 #include "sdes_common.cuh"
@@ -94,69 +94,21 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
 
 // ----------------------------------------------------------------------------------- MMA
 // Instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format[4,6)=1 (F32),
-// a_format[7,10)=2 (TF32), b_format[10,13)=2 (TF32), a_major[15]=0 (K), b_major[16]=0 (K),
+// a_format[7,10)=1 (BF16), b_format[10,13)=1 (BF16), a_major[15]=0 (K), b_major[16]=0 (K),
 // n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
+//
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core
-// matrices; LBO = byte distance between the two 16-byte K-chunks of one MMA (K=8 tf32),
+// matrices; LBO = byte distance between the two 16-byte K-chunks of one MMA (K=16 bf16),
 // SBO = byte distance between consecutive 8-row groups.  version=1 (Blackwell) at bit 46.
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46);
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]^T, one k-step (K = 8 tf32)
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // completion of all previously issued MMAs of this thread -> one arrive on an mbarrier
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---------------------------------------------------------------- weight image (B operand)
-// Byte layout of one layer's W (N rows x K cols, fp32) in shared memory / in the workspace image:
-//   offset(n, k) = (k/4) * (N*16) + (n/8) * 128 + (n%8) * 16 + (k%4) * 4
-// i.e. LBO = N*16 bytes, SBO = 128 bytes; k-step s starts at byte s * 2 * LBO.
-__host__ __device__ inline int64_t wimg_offset_floats(int n, int k, int N) {
-    return (int64_t)(k / 4) * (N * 4) + (n / 8) * 32 + (n % 8) * 4 + (k % 4);
-}
-
-__device__ __forceinline__ uint32_t tf32_hi_bits(float a) { return __float_as_uint(a) & 0xFFFFE000u; }
-
-// Issue one 3xTF32 layer: K in {8..64, multiple of 8}, N multiple of 16.  Called by ONE thread.
-//   tmem_a_hi / tmem_a_lo : TMEM addresses (lane 0 of the group) of the A operand halves
-//   w_hi / w_lo           : shared-memory addresses of the two weight images
-__device__ __forceinline__ void issue_layer_3xtf32(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
-                                                   uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K, int N) {
-    const uint32_t idesc = idesc_tf32(128, N);
-    const uint32_t lbo = (uint32_t)N * 16u;
-    const int ksteps = K >> 3;
-    for (int s = 0; s < ksteps; ++s) {
-        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        // small terms first, the dominant hi*hi product last
-        mma_tf32_ts(tmem_d, tmem_a_lo + 8u * s, bh, idesc, s > 0 ? 1u : 0u);
-        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bl, idesc, 1u);
-        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bh, idesc, 1u);
-    }
-}
-
-// ------------------------------------------------------------- mixed-precision split (v2)
-// The lo half only has to carry ~11 more bits below a 2^-11-times-smaller magnitude, so it can
-// live in bf16: the A operand shrinks from 64+64 to 64+32 TMEM columns per tile (three tiles fit
-// in the 512 columns of an SM instead of two) and its product runs as kind::f16 with K=16 per MMA:
-//     D = A_hi(tf32) * W_hi(tf32) + A_hi(tf32) * W_lo(tf32) + A_lo(bf16) * W(bf16)
-// Relative error ~2^-19 of sum|a||w| (tested < 4e-6), fp32 SGEMM-class.
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -194,6 +146,14 @@ __device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, 
     lo = pack_bf16x2(a - ha, b - hb);
 }
 
+// the same on a register pair, the subtraction as one packed FFMA2 (v - hi = fma(hi, -1, v), exact)
+__device__ __forceinline__ void split_bf16_pair2(float2 v, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(v.x, v.y);
+    const float2 h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+    const float2 l = __ffma2_rn(h, make_float2(-1.f, -1.f), v);
+    lo = pack_bf16x2(l.x, l.y);
+}
+
 // bf16x3 layer (4-group engine): A = A_hi + A_lo and W = W_hi + W_lo, both halves bf16 (16 significant bits per
 // operand), D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in fp32 — the wide engine's scheme with A in TMEM.  A halves are
 // packed two values per 32-bit column (8 columns per K=16 step).  Called by ONE thread.
@@ -207,25 +167,6 @@ __device__ __forceinline__ void issue_layer_bf16x3(uint32_t tmem_d, uint32_t tme
         mma_f16_ts(tmem_d, tmem_a_lo + 8u * s, bh, id16, s > 0 ? 1u : 0u);
         mma_f16_ts(tmem_d, tmem_a_hi + 8u * s, bl, id16, 1u);
         mma_f16_ts(tmem_d, tmem_a_hi + 8u * s, bh, id16, 1u);
-    }
-}
-
-// K8 = K of the tf32 terms (multiple of 8), K16 = K of the bf16 term (multiple of 16, >= K8; the extra
-// columns of A_lo and of the bf16 image are zero).  Called by ONE thread.
-__device__ __forceinline__ void issue_layer_mixed(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo16,
-                                                  uint32_t w_hi_saddr, uint32_t w_lo_saddr, uint32_t w16_saddr,
-                                                  int K8, int K16, int N) {
-    const uint32_t id32 = idesc_tf32(128, N), id16 = idesc_bf16(128, N);
-    const uint32_t lbo = (uint32_t)N * 16u;
-    for (int s = 0; s < (K16 >> 4); ++s) {
-        const uint64_t b16 = smem_desc_kmajor(w16_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        mma_f16_ts(tmem_d, tmem_a_lo16 + 8u * s, b16, id16, s > 0 ? 1u : 0u);
-    }
-    for (int s = 0; s < (K8 >> 3); ++s) {
-        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bl, id32, 1u);
-        mma_tf32_ts(tmem_d, tmem_a_hi + 8u * s, bh, id32, 1u);
     }
 }
 
