@@ -16,7 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libsdes_b200.so")
 OBJ_DIR = os.path.join(CSRC, "_obj")
-SOURCES = ["sdes_api.cu", "sdes_prepare.cu", "sdes_rollout_simt.cu", "sdes_rollout_mma.cu", "sdes_wide.cu", "sdes_grad.cu", "sdes_adjoint.cu", "sdes_integrate.cu", "sdes_trainer.cu"]
+SOURCES = ["sdes_api.cu", "sdes_prepare.cu", "sdes_rollout_simt.cu", "sdes_rollout_tc_api.cu", "sdes_wide.cu", "sdes_grad.cu", "sdes_adjoint.cu", "sdes_integrate.cu", "sdes_trainer.cu"]
+# the tensor-core rollout kernel is compiled once per padded state dimension (parallel builds, one object each)
+TC_DPADS = [8, 16, 32, 48, 56, 64]
+TC_SOURCE = "sdes_rollout_mma.cu"
 HEADERS = ["sdes_common.cuh", "sdes_step.cuh", "sdes_tc.cuh", "sdes_timeembed.cuh", "sdes_linear.cuh", os.path.join("..", "..", "include", "sdes_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -31,7 +34,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for name in SOURCES + HEADERS:
+    for name in SOURCES + [TC_SOURCE] + HEADERS:
         path = os.path.join(CSRC, name)
         if os.path.exists(path):
             with open(path, "rb") as f:
@@ -48,9 +51,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
 
-    def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(job):
+        src, tag, extra = job
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", tag + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -60,8 +64,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    jobs = [(TC_SOURCE, f"_{dp}", [f"-DSDES_TC_DPAD={dp}"]) for dp in reversed(TC_DPADS)] + [(s, "", []) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(jobs))) as ex:
+        objs = list(ex.map(compile_one, jobs))
     r = subprocess.run([nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:

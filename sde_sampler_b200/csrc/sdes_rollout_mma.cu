@@ -43,87 +43,12 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 __host__ __device__ inline int mma_nout(int dpad) { return (dpad + 15) / 16 * 16; }
 
-// floats of the bf16 operand image: per layer hi[N x K16] then lo[N x K16] (tc::wimg16_offset layout), then the fp32
-// biases {b_h[64]} x n_hidden, b_out[NOUT]   (b_in is folded into the time-embedding table)
-int64_t mma4_weight_image_floats(const SdesRolloutDesc& d) {
-    const int dpad = mma_pad_dim(d.dim), nout = mma_nout(dpad), k0b = (dpad + 15) & ~15;
-    const int64_t bf16_elems = 2ll * 64 * k0b + (int64_t)d.n_hidden * 2 * 64 * 64 + 2ll * nout * 64;
-    return bf16_elems / 2 + (int64_t)d.n_hidden * 64 + nout;
-}
-
-int mma_groups_per_sm() { return TC_GROUPS; }
-
-// ------------------------------------------------------------------------------ self test
-// D[128,N] = A[128,K] * W[N,K]^T through exactly the code path the rollout uses (A split into bf16 hi/lo and written
-// with tcgen05.st into TMEM, W hi/lo images in shared memory, the bf16x3 issue, tcgen05.ld).  sdes_tcgen05_selftest.
-__global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W,
-                                                              float* __restrict__ D, int K, int N) {
-    extern __shared__ __align__(128) float sm[];
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    const int K16 = (K + 15) & ~15;
-    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(sm);
-    __nv_bfloat16* w_lo = w_hi + N * K16;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int e = tid; e < N * K16; e += 128) {
-        const int n = e / K16, k = e % K16;
-        const float w = k < K ? W[n * K + k] : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        w_hi[tc::wimg16_offset(n, k, N)] = hi;
-        w_lo[tc::wimg16_offset(n, k, N)] = __float2bfloat16_rn(w - __bfloat162float(hi));
-    }
-    if (warp == 0) {
-        tc::tmem_alloc(&tmem_base_s, 128);
-        tc::tmem_relinquish();
-    }
-    if (tid == 0) {
-        tc::mbar_init(&bar, 1);
-        tc::fence_mbar_init();
-    }
-    tc::fence_proxy_async();  // generic-proxy smem writes (weights) -> visible to the tensor-core (async) proxy
-    tc::fence_before();
-    __syncthreads();
-    tc::fence_after();
-    const uint32_t tbase = tmem_base_s;
-    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
-    const uint32_t col_d = 0, col_hi = 64, col_lo = 96;
-    for (int c = 0; c < K16; c += 8) {
-        uint32_t hi[4], lo[4];
-        for (int q = 0; q < 4; ++q) {
-            const int k = c + 2 * q;
-            const float2 a = make_float2(k < K ? A[tid * K + k] : 0.f, k + 1 < K ? A[tid * K + k + 1] : 0.f);
-            tc::split_bf16_pair2(a, hi[q], lo[q]);
-        }
-        tc::tmem_st4(lane_addr + col_hi + c / 2, hi);
-        tc::tmem_st4(lane_addr + col_lo + c / 2, lo);
-    }
-    tc::wait_st();
-    tc::fence_before();
-    __syncthreads();
-    if (tid == 0) {
-        tc::fence_after();
-        tc::issue_layer_bf16x3(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(w_hi), tc::smem_u32(w_lo), K16, N);
-        tc::mma_commit(&bar);
-    }
-    tc::mbar_wait(&bar, 0);
-    tc::fence_after();
-    for (int c = 0; c < N; c += 8) {
-        float v[8];
-        tc::tmem_ld8(lane_addr + col_d + c, v);
-        tc::wait_ld_tie<8>(v);
-        for (int q = 0; q < 8; ++q) D[tid * N + c + q] = v[q];
-    }
-    tc::fence_before();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, 128);
-}
-
-cudaError_t launch_mma_selftest(const float* A, const float* W, float* D, int K, int N, cudaStream_t stream) {
-    const size_t smem = 2 * (size_t)N * ((K + 15) & ~15) * 2;
-    cudaError_t e = cudaFuncSetAttribute(mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    mma_selftest_kernel<<<1, 128, smem, stream>>>(A, W, D, K, N);
-    return cudaGetLastError();
+// dynamic shared memory of rollout_tc_kernel (carve-up in the kernel)
+inline size_t tc_smem_bytes(const KParams& p) {
+    const int dpad = p.ws.dpad, K = p.d.target_kind == SDES_TARGET_GMM ? p.d.n_components : 0;
+    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
+                      (size_t)TC_GROUPS * dpad * 128;
+    return fl * sizeof(float);
 }
 
 // ---------------------------------------------------------------------------- the kernel
@@ -132,6 +57,8 @@ __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 12
 struct GroupCtx {
     int g;                     // group index
     int gtid;                  // thread index in the group = row in the tile = TMEM lane
+    int issuer;                // gtid of the thread that issues this group's MMAs: lane 0 of warp (g mod 4), so that each of the
+                               // SM's four schedulers hosts exactly one issuing warp
     uint32_t t_d, t_hi, t_lo;  // TMEM addresses, lane 0 of the tile (for the issuing thread)
     uint32_t l_d, l_hi, l_lo;  // same, at this thread's warp lane window (for ld / st)
     uint64_t* bar;
@@ -183,7 +110,7 @@ __device__ __forceinline__ void issue_layer(const GroupCtx& c, uint32_t w_hi_sad
     tc::wait_st();
     tc::fence_before();
     group_bar(c.g);
-    if (c.gtid == 0) {
+    if (c.gtid == c.issuer) {
         tc::fence_after();
         tc::issue_layer_bf16x3(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K16, N);
         tc::mma_commit(c.bar);
@@ -224,12 +151,13 @@ __device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* _
 //       rnd += 1/2 beta_k^2 sigma^2 sum g^2 (+ sigma beta_k sum g eps)
 struct StepK {
     float A, Bc, Cc, cost_scale, ito_scale;
-    float sigma, lerp_w, one_m_w, gate_outer, outer, cm, cs;
-    bool w_lt_half, gate_scalar, ref_ctrl, from_hbm;
+    float sigma, lerp_w, one_m_w, outer, cm, cs;
+    bool w_lt_half, ref_ctrl, from_hbm;
     int dim;
 };
 
-__device__ __forceinline__ StepK make_step_k(const SdesRolloutDesc& d, const float* __restrict__ tab, const float* __restrict__ gate_row) {
+template <int CTRL>
+__device__ __forceinline__ StepK make_step_k(const SdesRolloutDesc& d, const float* __restrict__ tab) {
     StepK k;
     const float dt = tab[TAB_DT], sqrt_dt = tab[TAB_SQRT_DT], mu = tab[TAB_MU], sigma = tab[TAB_SIGMA];
     k.sigma = sigma;
@@ -251,9 +179,7 @@ __device__ __forceinline__ StepK make_step_k(const SdesRolloutDesc& d, const flo
     k.lerp_w = tab[TAB_LERP_W];
     k.one_m_w = 1.0f - k.lerp_w;
     k.w_lt_half = k.lerp_w < 0.5f;
-    k.outer = (d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : sigma) * d.scale_score;
-    k.gate_scalar = !(d.flags & SDES_F_HAS_GATE) || d.gate_dim == 1;
-    k.gate_outer = k.outer * gate_row[0];
+    k.outer = (CTRL == SDES_CTRL_SCORE ? 1.0f : sigma) * d.scale_score;
     k.cm = d.clip_model;
     k.cs = d.clip_score;
     k.ref_ctrl = (d.flags & SDES_F_REFERENCE_CTRL) != 0;
@@ -354,9 +280,9 @@ __device__ __forceinline__ void gmm_active_score(const XPair& xs, const LeanSmem
     for (int r = 0; r < NP; ++r) gs[r] = __fmul2_rn(acc[r], make_float2(inv, inv));
 }
 
-template <int DPAD>
+template <int DPAD, int TGT>
 __device__ __forceinline__ void target_globals(const SdesRolloutDesc& d, const XPair& xs, const LeanSmem& sm, uint32_t gmm_mask, TgtGlobals& tg) {
-    if (d.target_kind == SDES_TARGET_GMM) {
+    if (TGT == SDES_TARGET_GMM) {
         if (gmm_mask < 2u) {
             tg.np = 1;
             gmm_active_score<1>(xs, sm, tg.gs);
@@ -367,7 +293,7 @@ __device__ __forceinline__ void target_globals(const SdesRolloutDesc& d, const X
             tg.np = 4;
             gmm_active_score<4>(xs, sm, tg.gs);
         }
-    } else if (d.target_kind == SDES_TARGET_FUNNEL) {
+    } else if (TGT == SDES_TARGET_FUNNEL) {
         // distr/funnel.py:71-80
         float2 sq2 = make_float2(0.f, 0.f);
         const float2 x01 = xs.pair(0);
@@ -383,14 +309,16 @@ __device__ __forceinline__ void target_globals(const SdesRolloutDesc& d, const X
     }
 }
 
-constexpr bool ctrl_needs_target(int ctrl) { return ctrl == SDES_CTRL_SCORE || ctrl == SDES_CTRL_LERP || ctrl == SDES_CTRL_LERP_TARGET; }
-constexpr bool ctrl_needs_prior(int ctrl) { return ctrl == SDES_CTRL_LERP || ctrl == SDES_CTRL_LERP_PRIOR; }
+constexpr bool ctrl_needs_target(int ctrl) { return ctrl == SDES_CTRL_SCORE || ctrl == SDES_CTRL_LERP || ctrl == SDES_CTRL_LERP_TARGET || ctrl == 100; }
+constexpr bool ctrl_needs_prior(int ctrl) { return ctrl == SDES_CTRL_LERP || ctrl == SDES_CTRL_LERP_PRIOR || ctrl == 100; }
 
 // ------------------------------------------------------------------- the update loop
 // Eight dimensions (four pairs) of one trajectory: network output chunk from TMEM, control = clip(NN) + score part
 // (models/reparam.py: ClippedCtrl :35-36, ScoreCtrl :78-83, LerpCtrl :131-162, LerpPriorCtrl :165-181, LerpTargetCtrl :184-200),
 // noise, cost / Ito sums, state update.  MODE 0: first chunk (may hold the GMM's active pairs and the funnel's
 // dimension 0), MODE 1: any later chunk, MODE 2: DENSE (target score of every dimension in scd[]).
+constexpr int CTRL_LERP_HI = 100;  // LerpCtrl with s / T >= 0.5: the other branch of torch.lerp (compile-time so that no select is issued per pair)
+
 template <int DPAD, int CTRL, int TGT, int MODE>
 __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int q, const int step,
                                              const uint32_t traj, const LeanSmem& sm, const TgtGlobals& tg, const float* scd,
@@ -458,10 +386,10 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
                 }
             }
             float2 inner;
-            if (CTRL == SDES_CTRL_LERP) {
+            if (CTRL == SDES_CTRL_LERP || CTRL == CTRL_LERP_HI) {
                 // torch.lerp: w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)
                 const float2 diff = __ffma2_rn(ps2, make_float2(-1.f, -1.f), ts2);
-                if (k.w_lt_half) inner = __ffma2_rn(make_float2(k.lerp_w, k.lerp_w), diff, ps2);
+                if (CTRL == SDES_CTRL_LERP) inner = __ffma2_rn(make_float2(k.lerp_w, k.lerp_w), diff, ps2);
                 else inner = __ffma2_rn(diff, make_float2(-k.one_m_w, -k.one_m_w), ts2);
             } else if (CTRL == SDES_CTRL_LERP_PRIOR) {
                 inner = __fmul2_rn(ps2, make_float2(k.one_m_w, k.one_m_w));
@@ -472,12 +400,9 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
             }
             inner.x = clipf(inner.x, k.cs);
             inner.y = clipf(inner.y, k.cs);
-            if (k.gate_scalar) {
-                g2 = __ffma2_rn(inner, make_float2(k.gate_outer, k.gate_outer), g2);
-            } else {
-                const float2 gt = *reinterpret_cast<const float2*>(gate_row + 2 * r);
-                g2 = __ffma2_rn(__fmul2_rn(inner, gt), make_float2(k.outer, k.outer), g2);
-            }
+            // gate row of the prologue's table: clip(score_model(s)) per dimension (a scalar gate replicated, 0 on padding)
+            const float2 gt = *reinterpret_cast<const float2*>(gate_row + 2 * r);
+            g2 = __ffma2_rn(__fmul2_rn(inner, gt), make_float2(k.outer, k.outer), g2);
         }
         float2 gm2 = g2;
         if (k.ref_ctrl) gm2 = __ffma2_rn(ps2, make_float2(-k.sigma, -k.sigma), g2);  // g - sigma * prior score  (solver/oc.py:305-306)
@@ -509,7 +434,10 @@ __device__ __forceinline__ void update_phase(const KParams& p, const StepK& k, c
     }
 }
 
-template <int DPAD, bool DENSE>
+// CTRL = the descriptor's ctrl_kind, TGT = its target_kind where the step depends on it (controls with a target score), else
+// SDES_TARGET_GMM as a placeholder: the host dispatches on both (launch_rollout_tc_dpad below), so each kernel is one
+// straight-line step with at most two update loops (the two branches of torch.lerp).
+template <int DPAD, bool DENSE, int CTRL, int TGT>
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams p) {
     constexpr int NOUT = (DPAD + 15) / 16 * 16;
     constexpr uint32_t K0B = (DPAD + 15) & ~15;
@@ -527,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     // Which instantiation runs: the prologue kernel left the GMM's dimension-pair mask in the workspace.  A mixture
     // whose components differ beyond the first GMM_ACT dims needs the per-step score of every dimension (DENSE).
     const uint32_t gmm_mask = reinterpret_cast<const uint32_t*>(ws + p.ws.counter)[1];
-    const bool want_dense = d.target_kind == SDES_TARGET_GMM && gmm_mask >= (1u << (GMM_ACT / 2)) && ctrl_needs_target(d.ctrl_kind);
+    const bool want_dense = TGT == SDES_TARGET_GMM && ctrl_needs_target(CTRL) && gmm_mask >= (1u << (GMM_ACT / 2));
     if (want_dense != DENSE) return;
 
     // ---- shared memory: [bf16 weight image + biases | gmm -mu, h (leading dims) | c2 | -mu0 | -2 h0 | prior | ref | state x]
@@ -596,6 +524,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     GroupCtx c;
     c.g = warp >> 2;
     c.gtid = tid & 127;
+    c.issuer = (c.g & 3) * 32;
     const uint32_t tbase = s_tmem + (uint32_t)(c.g * GROUP_COLS);
     c.t_d = tbase;
     c.t_hi = tbase + 64;
@@ -652,9 +581,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
         } else {
             if (c.gtid == 0) {
                 uint32_t seen;
-                do {
+                for (;;) {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
-                } while (seen < chunk);
+                    if (seen >= chunk) break;
+                    __nanosleep(256);  // the predecessor chunk runs for tens of microseconds: do not spend issue slots polling
+                }
             }
             group_bar(c.g);
 #pragma unroll
@@ -680,8 +611,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                 if (NPAIR > 8 && gmm_mask < 256u) gmm_eval_na<DPAD, (NPAIR > 8 ? 8 : NPAIR), true>(xs, scd, tsm, K);
                 else if (NPAIR > 16 && gmm_mask < 65536u) gmm_eval_na<DPAD, (NPAIR > 16 ? 16 : NPAIR), true>(xs, scd, tsm, K);
                 else gmm_eval_na<DPAD, NPAIR, true>(xs, scd, tsm, K);
-            } else if (ctrl_needs_target(d.ctrl_kind)) {
-                target_globals<DPAD>(d, xs, lsm, gmm_mask, tg);
+            } else if (ctrl_needs_target(CTRL)) {
+                target_globals<DPAD, TGT>(d, xs, lsm, gmm_mask, tg);
             }
             wait_layer(c);
             layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
@@ -692,30 +623,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                 layer_epilogue(c, s_bias + l * C);
             }
             issue_layer(c, lo_hi, lo_lo, C, NOUT);
-            const StepK k = make_step_k(d, tab, gate_row);
+            const StepK k = make_step_k<CTRL>(d, tab);
             const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
             const TrajRef xo_ref = traj_ref(d, d.xs, i + 1, rrow);
             float* xo = (ret_traj && valid) ? xo_ref.p : nullptr;
             float2 cost2 = make_float2(0.f, 0.f), ito2 = make_float2(0.f, 0.f);
             wait_layer(c);
             // ---- network output streamed from TMEM into the control / cost / state update
-#define SDES_UPD(CTRL, TGT) update_phase<DPAD, CTRL, TGT, DENSE>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2)
-#define SDES_UPD_T(CTRL)                                                              \
-    if (DENSE || d.target_kind == SDES_TARGET_GMM) SDES_UPD(CTRL, SDES_TARGET_GMM);    \
-    else if (d.target_kind == SDES_TARGET_MULTIWELL) SDES_UPD(CTRL, SDES_TARGET_MULTIWELL); \
-    else SDES_UPD(CTRL, SDES_TARGET_FUNNEL);
-            if (d.ctrl_kind == SDES_CTRL_LERP) {
-                SDES_UPD_T(SDES_CTRL_LERP)
-            } else if (d.ctrl_kind == SDES_CTRL_SCORE) {
-                SDES_UPD_T(SDES_CTRL_SCORE)
-            } else if (d.ctrl_kind == SDES_CTRL_LERP_TARGET) {
-                SDES_UPD_T(SDES_CTRL_LERP_TARGET)
-            } else if (!DENSE) {
-                if (d.ctrl_kind == SDES_CTRL_LERP_PRIOR) SDES_UPD(SDES_CTRL_LERP_PRIOR, SDES_TARGET_GMM);
-                else SDES_UPD(SDES_CTRL_CLIPPED, SDES_TARGET_GMM);
-            }
-#undef SDES_UPD_T
-#undef SDES_UPD
+            if (CTRL == SDES_CTRL_LERP && !k.w_lt_half)
+                update_phase<DPAD, CTRL_LERP_HI, TGT, DENSE>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2);
+            else
+                update_phase<DPAD, CTRL, TGT, DENSE>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2);
             rnd = fmaf(k.cost_scale, cost2.x + cost2.y, rnd);
             if (d.flags & SDES_F_SUB_DIV_INT) rnd -= tab[TAB_DIV_INT];
             if (d.flags & SDES_F_COMPUTE_ITO) rnd = fmaf(k.ito_scale, ito2.x + ito2.y, rnd);
@@ -746,21 +664,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     if (warp == 0) tc::tmem_dealloc(s_tmem, TMEM_COLS);
 }
 
-size_t tc_smem_bytes(const KParams& p) {
-    const int dpad = p.ws.dpad, K = p.d.target_kind == SDES_TARGET_GMM ? p.d.n_components : 0;
-    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
-                      (size_t)TC_GROUPS * dpad * 128;
-    return fl * sizeof(float);
-}
+// ---------------------------------------------------------------------------- launch
+// This translation unit is compiled once per padded state dimension (-DSDES_TC_DPAD=8|16|32|48|56|64, sde_sampler_b200/build.py)
+// so that the instantiations build in parallel; sdes_rollout_tc_api.cu dispatches on ws.dpad.
+#ifndef SDES_TC_DPAD
+#define SDES_TC_DPAD 56
+#endif
 
-bool mma_supported(const KParams& p) {
-    return p.d.dim <= 64 && p.d.n_hidden <= SDES_MAX_HIDDEN && tc_smem_bytes(p) <= 226u * 1024u;
-}
-
-template <int DPAD, bool DENSE>
-static cudaError_t launch_tc_t(const KParams& p, int sm_count, cudaStream_t stream) {
+template <int DPAD, bool DENSE, int CTRL, int TGT>
+static cudaError_t launch_k(const KParams& p, int sm_count, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes(p);
-    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<DPAD, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<DPAD, DENSE, CTRL, TGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // work items = tiles x time chunks: a group that finds no first-chunk tile left starts on a second chunk and waits
     // for its predecessor, so every SM is used even when there are fewer tiles than resident groups
@@ -768,31 +682,39 @@ static cudaError_t launch_tc_t(const KParams& p, int sm_count, cudaStream_t stre
     int grid = (int)((items + TC_GROUPS - 1) / TC_GROUPS);
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
-    rollout_tc_kernel<DPAD, DENSE><<<grid, TC_THREADS, smem, stream>>>(p);
+    rollout_tc_kernel<DPAD, DENSE, CTRL, TGT><<<grid, TC_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-// Launches the lean kernel and, when the descriptor can need it (a multi-component GMM whose score enters the
-// control, d > GMM_ACT), the DENSE one as well: whichever does not match the prologue's dimension mask exits at once.
-cudaError_t launch_rollout_tc(const KParams& p, int sm_count, cudaStream_t stream, int* n_launches) {
-    const bool maybe_dense = p.d.target_kind == SDES_TARGET_GMM && p.d.n_components > 1 && p.d.dim > GMM_ACT && ctrl_needs_target(p.d.ctrl_kind);
-    cudaError_t e = cudaErrorInvalidValue;
-    *n_launches = maybe_dense ? 2 : 1;
-    switch (p.ws.dpad) {
-        case 8: return launch_tc_t<8, false>(p, sm_count, stream);
-#define SDES_TC_CASE(DP)                                                       \
-    case DP:                                                                   \
-        e = launch_tc_t<DP, false>(p, sm_count, stream);                       \
-        if (e == cudaSuccess && maybe_dense) e = launch_tc_t<DP, true>(p, sm_count, stream); \
-        return e;
-        SDES_TC_CASE(16)
-        SDES_TC_CASE(32)
-        SDES_TC_CASE(48)
-        SDES_TC_CASE(56)
-        SDES_TC_CASE(64)
-#undef SDES_TC_CASE
+// a control with a target score: the lean kernel and, when the descriptor can need it (a multi-component GMM in d > GMM_ACT),
+// the DENSE one as well — whichever does not match the prologue's dimension mask exits at once
+template <int DPAD, int CTRL>
+static cudaError_t launch_target_ctrl(const KParams& p, int sm_count, cudaStream_t stream, int* n_launches) {
+    if (p.d.target_kind == SDES_TARGET_MULTIWELL) return launch_k<DPAD, false, CTRL, SDES_TARGET_MULTIWELL>(p, sm_count, stream);
+    if (p.d.target_kind == SDES_TARGET_FUNNEL) return launch_k<DPAD, false, CTRL, SDES_TARGET_FUNNEL>(p, sm_count, stream);
+    cudaError_t e = launch_k<DPAD, false, CTRL, SDES_TARGET_GMM>(p, sm_count, stream);
+    if constexpr (DPAD > GMM_ACT) {
+        if (e == cudaSuccess && p.d.n_components > 1 && p.d.dim > GMM_ACT) {
+            *n_launches = 2;
+            e = launch_k<DPAD, true, CTRL, SDES_TARGET_GMM>(p, sm_count, stream);
+        }
     }
     return e;
+}
+
+#define SDES_TC_CAT2(a, b) a##b
+#define SDES_TC_CAT(a, b) SDES_TC_CAT2(a, b)
+cudaError_t SDES_TC_CAT(launch_rollout_tc_, SDES_TC_DPAD)(const KParams& p, int sm_count, cudaStream_t stream, int* n_launches) {
+    constexpr int DPAD = SDES_TC_DPAD;
+    *n_launches = 1;
+    switch (p.d.ctrl_kind) {
+        case SDES_CTRL_CLIPPED: return launch_k<DPAD, false, SDES_CTRL_CLIPPED, SDES_TARGET_GMM>(p, sm_count, stream);
+        case SDES_CTRL_LERP_PRIOR: return launch_k<DPAD, false, SDES_CTRL_LERP_PRIOR, SDES_TARGET_GMM>(p, sm_count, stream);
+        case SDES_CTRL_SCORE: return launch_target_ctrl<DPAD, SDES_CTRL_SCORE>(p, sm_count, stream, n_launches);
+        case SDES_CTRL_LERP: return launch_target_ctrl<DPAD, SDES_CTRL_LERP>(p, sm_count, stream, n_launches);
+        case SDES_CTRL_LERP_TARGET: return launch_target_ctrl<DPAD, SDES_CTRL_LERP_TARGET>(p, sm_count, stream, n_launches);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace sdes
