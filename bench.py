@@ -88,7 +88,8 @@ def build_objects(device, engine: str, process_group=None, seed: int = 1, sync_m
     from torch import nn
     from functools import partial
 
-    from sde_sampler_b200 import FusedTimeReversalLoss, plugins
+    import ref_mirrors as plugins  # parameter-holder mirrors of the reference classes (tests/ref_mirrors.py)
+    from sde_sampler_b200 import FusedTimeReversalLoss
 
     torch.manual_seed(seed)
     loc, scale, w = plugins.fab_gmm_params(DIM)

@@ -46,7 +46,7 @@ __host__ __device__ inline int mma_nout(int dpad) { return (dpad + 15) / 16 * 16
 // dynamic shared memory of rollout_tc_kernel (carve-up in the kernel)
 inline size_t tc_smem_bytes(const KParams& p) {
     const int dpad = p.ws.dpad, K = p.d.target_kind == SDES_TARGET_GMM ? p.d.n_components : 0;
-    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
+    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 3) & ~3) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
                       (size_t)TC_GROUPS * dpad * 128;
     return fl * sizeof(float);
 }
@@ -92,17 +92,22 @@ __device__ __forceinline__ void store_a_from_x(uint32_t addr_hi, uint32_t addr_l
     }
 }
 
-// 8 accumulator columns -> + bias -> exact GELU -> bf16 hi/lo split -> A operand of the next layer
-__device__ __forceinline__ void gelu_split_store8(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[8], const float4 b0, const float4 b1) {
-    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-    uint32_t hi[4], lo[4];
+// 16 accumulator columns -> + bias -> exact GELU -> bf16 hi/lo split -> A operand of the next layer.  All eight register
+// pairs are processed in one basic block (eight independent dependency chains for the scheduler to interleave: the kernel
+// runs four warps per scheduler, so instruction-level parallelism inside the warp is what hides the FMA / MUFU latencies).
+__device__ __forceinline__ void gelu_split_store16(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[16], const float4 (&b)[4]) {
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float2 a = gelu_fast2(__fadd2_rn(make_float2(v[2 * q], v[2 * q + 1]), bb[q]));
+    for (int q = 0; q < 8; ++q) {
+        const float4 bq = b[q >> 1];
+        const float2 bb = (q & 1) ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y);
+        const float2 a = gelu_fast2(__fadd2_rn(make_float2(v[2 * q], v[2 * q + 1]), bb));
         tc::split_bf16_pair2(a, hi[q], lo[q]);
     }
-    tc::tmem_st4(addr_hi, hi);
-    tc::tmem_st4(addr_lo, lo);
+    tc::tmem_st4(addr_hi, &hi[0]);
+    tc::tmem_st4(addr_hi + 4u, &hi[4]);
+    tc::tmem_st4(addr_lo, &lo[0]);
+    tc::tmem_st4(addr_lo + 4u, &lo[4]);
 }
 
 // A operand is in TMEM: hand the layer to the tensor core (one thread issues, commit -> the group's mbarrier) ...
@@ -127,19 +132,28 @@ __device__ __forceinline__ void wait_layer(GroupCtx& c) {
 // next A operand (TMEM): the 64-wide activation row never sits in registers, and one compact loop serves every layer.
 // `bias` may point to global (time-embedding row, input layer) or shared memory (hidden biases).
 __device__ __forceinline__ void layer_epilogue(const GroupCtx& c, const float* __restrict__ bias) {
-    float a[8], b[8];
-    tc::tmem_ld8(c.l_d, a);
+    float a[16], b[16];
+    tc::tmem_ld8(c.l_d, &a[0]);
+    tc::tmem_ld8(c.l_d + 8u, &a[8]);
     const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll 1
-    for (int ch = 0; ch < 8; ch += 2) {
-        // bias loads are issued before the wait so their latency hides behind the TMEM load
-        const float4 p0 = b4[2 * ch], p1 = b4[2 * ch + 1], p2 = b4[2 * ch + 2], p3 = b4[2 * ch + 3];
-        tc::wait_ld_tie<8>(a);
-        tc::tmem_ld8(c.l_d + 8u * (ch + 1), b);
-        gelu_split_store8(c.l_hi + 4u * ch, c.l_lo + 4u * ch, a, p0, p1);
-        tc::wait_ld_tie<8>(b);
-        if (ch + 2 < 8) tc::tmem_ld8(c.l_d + 8u * (ch + 2), a);
-        gelu_split_store8(c.l_hi + 4u * (ch + 1), c.l_lo + 4u * (ch + 1), b, p2, p3);
+    for (int ch = 0; ch < 4; ch += 2) {  // 16 columns per block, two blocks per iteration (double-buffered TMEM loads)
+        float4 pa[4], pb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // bias loads are issued before the wait so their latency hides behind the TMEM load
+            pa[q] = b4[4 * ch + q];
+            pb[q] = b4[4 * ch + 4 + q];
+        }
+        tc::wait_ld_tie<16>(a);
+        tc::tmem_ld8(c.l_d + 16u * (ch + 1), &b[0]);
+        tc::tmem_ld8(c.l_d + 16u * (ch + 1) + 8u, &b[8]);
+        gelu_split_store16(c.l_hi + 8u * ch, c.l_lo + 8u * ch, a, pa);
+        tc::wait_ld_tie<16>(b);
+        if (ch + 2 < 4) {
+            tc::tmem_ld8(c.l_d + 16u * (ch + 2), &a[0]);
+            tc::tmem_ld8(c.l_d + 16u * (ch + 2) + 8u, &a[8]);
+        }
+        gelu_split_store16(c.l_hi + 8u * (ch + 1), c.l_lo + 8u * (ch + 1), b, pb);
     }
 }
 
@@ -208,6 +222,30 @@ __device__ __forceinline__ float4 normal4_rk(const uint32_t (&rk)[20], uint32_t 
     return e;
 }
 
+// Eight normals for dimension chunks (chunk, chunk + 1): the two Philox streams advance in lock step so that the
+// scheduler always has two independent multiply chains in flight.
+__device__ __forceinline__ void normal8_rk(const uint32_t (&rk)[20], uint32_t traj, uint32_t step, uint32_t chunk, float (&e)[8]) {
+    uint32_t a0 = traj, a1 = step, a2 = chunk, a3 = PHILOX_STREAM;
+    uint32_t b0 = traj, b1 = step, b2 = chunk + 1u, b3 = PHILOX_STREAM;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t ah0 = __umulhi(PHILOX_M0, a0), al0 = PHILOX_M0 * a0, ah1 = __umulhi(PHILOX_M1, a2), al1 = PHILOX_M1 * a2;
+        const uint32_t bh0 = __umulhi(PHILOX_M0, b0), bl0 = PHILOX_M0 * b0, bh1 = __umulhi(PHILOX_M1, b2), bl1 = PHILOX_M1 * b2;
+        a0 = ah1 ^ a1 ^ rk[2 * r];
+        b0 = bh1 ^ b1 ^ rk[2 * r];
+        a1 = al1;
+        b1 = bl1;
+        a2 = ah0 ^ a3 ^ rk[2 * r + 1];
+        b2 = bh0 ^ b3 ^ rk[2 * r + 1];
+        a3 = al0;
+        b3 = bl0;
+    }
+    box_muller(a0, a1, e[0], e[1]);
+    box_muller(b0, b1, e[4], e[5]);
+    box_muller(a2, a3, e[2], e[3]);
+    box_muller(b2, b3, e[6], e[7]);
+}
+
 // ------------------------------------------------------------------- target "globals"
 // What the per-dimension score of the target needs from the WHOLE state, evaluated once per step before the MLP
 // (in the shadow of the input layer's MMAs).
@@ -219,14 +257,14 @@ struct TgtGlobals {
 
 // Shared-memory parameter images of the lean kernel
 struct LeanSmem {
-    const float* gmu;    // [K2][GMM_ACT]  -mu_k on the leading dims
-    const float* gh;     // [K2][GMM_ACT]  h_k = 1/2 sigma_k^-2
-    const float* c2;     // [K2]           log2(e) (log w_k - sum_j log sigma_kj - d/2 log 2 pi)
+    const float* gmu;    // [K4][GMM_ACT]  -mu_k on the leading dims (K padded to a multiple of 4 with h = 0, c = -inf)
+    const float* gh;     // [K4][GMM_ACT]  h_k = 1/2 sigma_k^-2
+    const float* c2;     // [64]           log2(e) (log w_k - sum_j log sigma_kj - d/2 log 2 pi)
     const float* nmu0;   // [DPAD]         -mu of component 0 (dims shared by all components)
     const float* nh20;   // [DPAD]         -2 h of component 0
     const float* prior;  // loc[DPAD] | inv_var[DPAD] | lognorm
     const float* bo;     // output-layer bias [NOUT]
-    int K2;
+    int K4;
 };
 
 // Responsibility-weighted score on the first 2 NP dims (distr/gauss.py:119-140 through autograd, distr/base.py:130-137;
@@ -242,35 +280,35 @@ __device__ __forceinline__ void gmm_active_score(const XPair& xs, const LeanSmem
     }
     float m = -INFINITY, ssum = 0.f;
 #pragma unroll 1
-    for (int k = 0; k < sm.K2; k += 2) {
-        const float2* mua = reinterpret_cast<const float2*>(sm.gmu + k * GMM_ACT);
-        const float2* ha = reinterpret_cast<const float2*>(sm.gh + k * GMM_ACT);
-        float qa = 0.f, qb = 0.f;
-        float2 ta[NP], tb[NP];
+    for (int k = 0; k < sm.K4; k += 4) {  // four components per iteration: independent chains for the scheduler
+        const float2* mu = reinterpret_cast<const float2*>(sm.gmu + k * GMM_ACT);
+        const float2* hh = reinterpret_cast<const float2*>(sm.gh + k * GMM_ACT);
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 t[4][NP];
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
-            const float2 da = __fadd2_rn(xv[r], mua[r]), db = __fadd2_rn(xv[r], mua[r + GMM_ACT / 2]);
-            ta[r] = __fmul2_rn(da, ha[r]);
-            tb[r] = __fmul2_rn(db, ha[r + GMM_ACT / 2]);
-            qa = fmaf(da.x, ta[r].x, qa);
-            qb = fmaf(db.x, tb[r].x, qb);
-            qa = fmaf(da.y, ta[r].y, qa);
-            qb = fmaf(db.y, tb[r].y, qb);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 dd = __fadd2_rn(xv[r], mu[r + u * (GMM_ACT / 2)]);
+                t[u][r] = __fmul2_rn(dd, hh[r + u * (GMM_ACT / 2)]);
+                q[u] = fmaf(dd.x, t[u][r].x, q[u]);
+                q[u] = fmaf(dd.y, t[u][r].y, q[u]);
+            }
         }
-        const float2 c2 = *reinterpret_cast<const float2*>(sm.c2 + k);
-        const float la = fmaf(qa, -LOG2E, c2.x), lb = fmaf(qb, -LOG2E, c2.y);
-        const float m_new = fmaxf(m, fmaxf(la, lb));
-        float resc, ea, eb;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(resc) : "f"(m - m_new));  // 1 when the max did not move, 0 on the first pair
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(la - m_new));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(lb - m_new));
+        const float4 c4 = *reinterpret_cast<const float4*>(sm.c2 + k);
+        const float l[4] = {fmaf(q[0], -LOG2E, c4.x), fmaf(q[1], -LOG2E, c4.y), fmaf(q[2], -LOG2E, c4.z), fmaf(q[3], -LOG2E, c4.w)};
+        const float m_new = fmaxf(fmaxf(m, fmaxf(l[0], l[1])), fmaxf(l[2], l[3]));
+        float resc, e[4];
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(resc) : "f"(m - m_new));  // 1 when the max did not move, 0 on the first group
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[u]) : "f"(l[u] - m_new));
         m = m_new;
-        ssum = fmaf(ssum, resc, ea + eb);
+        ssum = fmaf(ssum, resc, (e[0] + e[1]) + (e[2] + e[3]));
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
             acc[r] = __fmul2_rn(acc[r], make_float2(resc, resc));
-            acc[r] = __ffma2_rn(make_float2(ea, ea), ta[r], acc[r]);
-            acc[r] = __ffma2_rn(make_float2(eb, eb), tb[r], acc[r]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[r] = __ffma2_rn(make_float2(e[u], e[u]), t[u][r], acc[r]);
         }
     }
     float inv;
@@ -332,6 +370,8 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
     if (k.from_hbm) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) e[r] = (j0 + r < k.dim) ? noise_row[j0 + r] : 0.f;
+    } else if (j0 + 8 <= k.dim) {
+        normal8_rk(p.philox_rk, traj, (uint32_t)step, (uint32_t)(2 * q), e);
     } else {
         const float4 n0 = normal4_rk(p.philox_rk, traj, (uint32_t)step, (uint32_t)(2 * q));
         e[0] = n0.x; e[1] = n0.y; e[2] = n0.z; e[3] = n0.w;
@@ -347,8 +387,9 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
         }
     }
     tc::wait_ld_tie<8>(nn);
+    float2 xn[4];
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
+    for (int pp = 0; pp < 4; ++pp) {  // one basic block for the four pairs (the trajectory stores follow the loop)
         const int r = 4 * q + pp;  // pair index
         float2 x2 = xs.pair(r);
         const float2 b2 = *reinterpret_cast<const float2*>(sm.bo + 2 * r);
@@ -411,9 +452,14 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
         ito2 = __ffma2_rn(gm2, e2, ito2);
         x2 = __ffma2_rn(make_float2(k.A, k.A), x2, __ffma2_rn(make_float2(k.Bc, k.Bc), g2, __fmul2_rn(e2, make_float2(k.Cc, k.Cc))));
         xs.set_pair(r, x2);
-        if (xo != nullptr) {
-            if (2 * r < k.dim) xo[(2 * r) * xo_st] = x2.x;
-            if (2 * r + 1 < k.dim) xo[(2 * r + 1) * xo_st] = x2.y;
+        xn[pp] = x2;
+    }
+    if (xo != nullptr) {
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const int r = 4 * q + pp;
+            if (2 * r < k.dim) xo[(2 * r) * xo_st] = xn[pp].x;
+            if (2 * r + 1 < k.dim) xo[(2 * r + 1) * xo_st] = xn[pp].y;
         }
     }
 }
@@ -460,10 +506,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
 
     // ---- shared memory: [bf16 weight image + biases | gmm -mu, h (leading dims) | c2 | -mu0 | -2 h0 | prior | ref | state x]
     float* s_w = smem;
-    const int K2 = (K + 1) & ~1;
+    const int K2 = (K + 1) & ~1, K4 = (K + 3) & ~3;
     float* s_gmu = s_w + ((p.ws.w_mma4_len + 31) & ~31ll);
-    float* s_gh = s_gmu + K2 * GMM_ACT;
-    float* s_c2 = s_gh + K2 * GMM_ACT;
+    float* s_gh = s_gmu + K4 * GMM_ACT;
+    float* s_c2 = s_gh + K4 * GMM_ACT;
     float* s_nmu0 = s_c2 + 64;
     float* s_nh20 = s_nmu0 + DPAD;
     float* s_prior = s_nh20 + DPAD;
@@ -493,10 +539,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             tc::bulk_g2s(dst + off, src + off, n, &s_wbar);
         }
     }
-    for (int e = tid; e < K2 * GMM_ACT; e += blockDim.x) {
+    for (int e = tid; e < K4 * GMM_ACT; e += blockDim.x) {
         const int k = e / GMM_ACT, j = e % GMM_ACT;
-        s_gmu[e] = j < DPAD ? -ws[p.ws.gmm_mu + k * DPAD + j] : 0.f;
-        s_gh[e] = j < DPAD ? ws[p.ws.gmm_h + k * DPAD + j] : 0.f;
+        s_gmu[e] = k < K2 ? -ws[p.ws.gmm_mu + k * DPAD + j] : 0.f;
+        s_gh[e] = k < K2 ? ws[p.ws.gmm_h + k * DPAD + j] : 0.f;
     }
     for (int e = tid; e < 64; e += blockDim.x) s_c2[e] = (e < K2 ? ws[p.ws.gmm_c + e] : -INFINITY) * LOG2E;
     for (int e = tid; e < DPAD; e += blockDim.x) {
@@ -520,7 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
 
     // generic (once-per-tile) evaluations read the full-width target images in the workspace
     const TargetSmem tsm{ws + p.ws.gmm_mu, ws + p.ws.gmm_h, ws + p.ws.gmm_c, gmm_mask, s_prior, s_ref};
-    const LeanSmem lsm{s_gmu, s_gh, s_c2, s_nmu0, s_nh20, s_prior, s_bias + nh * C, K2};
+    const LeanSmem lsm{s_gmu, s_gh, s_c2, s_nmu0, s_nh20, s_prior, s_bias + nh * C, K4};
     GroupCtx c;
     c.g = warp >> 2;
     c.gtid = tid & 127;

@@ -25,7 +25,7 @@ int mma_groups_per_sm() { return TC_GROUPS; }
 
 size_t tc_smem_bytes_host(const KParams& p) {  // mirrors tc_smem_bytes in sdes_rollout_mma.cu
     const int dpad = p.ws.dpad, K = p.d.target_kind == SDES_TARGET_GMM ? p.d.n_components : 0;
-    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 1) & ~1) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
+    const size_t fl = (size_t)((p.ws.w_mma4_len + 31) & ~31ll) + 2 * (size_t)((K + 3) & ~3) * GMM_ACT + 64 + 2 * (size_t)dpad + 2 * (2 * dpad + 8) +
                       (size_t)TC_GROUPS * dpad * 128;
     return fl * sizeof(float);
 }

@@ -15,7 +15,6 @@ import math
 import torch
 
 from . import _cabi, engine
-from .plugins import get_timesteps
 from .spec import _cls, _f, _owner, _target_params
 
 
@@ -40,8 +39,15 @@ class FusedEulerIntegrator:
         device = x_init.device
         B, dim = x_init.shape
         if timesteps is None:
-            timesteps = get_timesteps(float(ts[0]), float(ts[-1]), dt=self.dt, steps=self.steps, rescale_t=self.rescale_t,
-                                      device=device)
+            # eq/integrator.py:105-113 builds the integration grid with the reference's own get_timesteps; the drop-in
+            # runs next to the reference package, so that function is used as is (bit-identical grid).  Without the
+            # reference importable the caller passes `timesteps`.
+            try:
+                from sde_sampler.utils.common import get_timesteps
+            except ImportError as exc:
+                raise ValueError("FusedEulerIntegrator.integrate needs `timesteps` when sde_sampler.utils.common.get_timesteps "
+                                 "is not importable") from exc
+            timesteps = get_timesteps(ts[0], ts[-1], dt=self.dt, steps=self.steps, rescale_t=self.rescale_t, device=device)
         timesteps = timesteps.to(device=device, dtype=torch.float32).contiguous()
         out_ts = ts.to(device=device, dtype=torch.float32).contiguous()
         tg = _target_params(_owner(sde.target_score, "target_score"), dim)

@@ -1,4 +1,4 @@
-"""Test helpers: rebuild plug-in objects (the mirrors in sde_sampler_b200.plugins) from the raw
+"""Test helpers: rebuild plug-in objects (the parameter-holder mirrors in tests/ref_mirrors.py) from the raw
 spec dict stored in a golden fixture, so the -m gpu tests drive the fused losses through the
 same object/bound-method interface the reference's solver uses — without /root/reference."""
 from __future__ import annotations
@@ -7,7 +7,8 @@ import numpy as np
 import torch
 
 from sde_sampler_b200 import (FusedExponentialIntegratorSDELoss, FusedReferenceSDELoss,
-                              FusedTimeReversalLoss, plugins)
+                              FusedTimeReversalLoss)
+import ref_mirrors as plugins
 
 
 def _load_linear(layer, w, b):

@@ -7,7 +7,8 @@ import torch
 
 from oracle import philox, rollout as oracle_rollout
 from oracle.cases import NOISE_SEED, ULA_CASES
-from sde_sampler_b200 import FusedEulerIntegrator, plugins
+import ref_mirrors as plugins
+from sde_sampler_b200 import FusedEulerIntegrator
 from sdes_test_helpers import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -35,6 +36,25 @@ def _build(g, case):
     sde = plugins.LangevinSDE(target_score=target.score, diff_coeff=g["diff_coeff"], clip_score=g["clip_score"],
                               terminal_t=case["terminal_t"]).to(_dev())
     return FusedEulerIntegrator(dt=case["dt"], seed=3), sde
+
+
+@pytest.fixture(autouse=True)
+def _reference_get_timesteps(monkeypatch):
+    """`integrate(..., timesteps=None)` builds its grid with the reference's `sde_sampler.utils.common.get_timesteps`
+    (the drop-in runs next to the reference package).  On the GPU box the reference is absent: stand its module in
+    with the mirror of that one function so the default path is exercised too."""
+    import sys
+    import types
+
+    try:
+        import sde_sampler.utils.common  # noqa: F401
+    except ImportError:
+        pkg, utils, common = types.ModuleType("sde_sampler"), types.ModuleType("sde_sampler.utils"), types.ModuleType("sde_sampler.utils.common")
+        common.get_timesteps = plugins.get_timesteps
+        pkg.utils, utils.common = utils, common
+        for name, mod in (("sde_sampler", pkg), ("sde_sampler.utils", utils), ("sde_sampler.utils.common", common)):
+            monkeypatch.setitem(sys.modules, name, mod)
+    yield
 
 
 @pytest.mark.parametrize("name", list(ULA_CASES))

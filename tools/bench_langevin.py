@@ -3,9 +3,10 @@
 Prints GPU time of FusedEulerIntegrator.integrate and, with --cpu, the numpy-oracle time on a small sample."""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch
-from sde_sampler_b200 import FusedEulerIntegrator, plugins
+from sde_sampler_b200 import FusedEulerIntegrator
+import ref_mirrors as plugins  # parameter-holder mirrors of the reference classes (tests/ref_mirrors.py)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=6000)
@@ -18,13 +19,14 @@ target = plugins.GMM(dim=args.dim, loc=loc, scale=scale, mixture_weights=w).to(d
 sde = plugins.LangevinSDE(target_score=target.score, diff_coeff=1.0, clip_score=1e5, terminal_t=100.0).to(dev)
 integ = FusedEulerIntegrator(dt=0.01, seed=1)
 ts = plugins.get_timesteps(0.0, 100.0, steps=1000).to(dev)
+grid = plugins.get_timesteps(0.0, 100.0, dt=0.01).to(dev)  # eq/integrator.py:105-113
 x0 = torch.randn(args.batch, args.dim, device=dev)
-xs = integ.integrate(sde, ts=ts, x_init=x0)
+xs = integ.integrate(sde, ts=ts, x_init=x0, timesteps=grid)
 torch.cuda.synchronize()
 ms = []
 for _ in range(3):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); xs = integ.integrate(sde, ts=ts, x_init=x0); b.record(); torch.cuda.synchronize()
+    a.record(); xs = integ.integrate(sde, ts=ts, x_init=x0, timesteps=grid); b.record(); torch.cuda.synchronize()
     ms.append(a.elapsed_time(b))
 out = {"workload": f"ULA GMM-40 d={args.dim} B={args.batch} steps=10000 outputs=1001", "ms": sorted(ms)[1],
        "traj_steps_per_s": args.batch * 10000 / (sorted(ms)[1] * 1e-3), "finite": bool(torch.isfinite(xs).all())}

@@ -9,10 +9,11 @@ of the NICE forward + input-gradient backward: 2 FLOP per multiply-add, no split
 import argparse, json, os, sys, statistics
 from functools import partial
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch
 from torch import nn
-from sde_sampler_b200 import FusedExponentialIntegratorSDELoss, plugins, _cabi
+from sde_sampler_b200 import FusedExponentialIntegratorSDELoss, _cabi
+import ref_mirrors as plugins  # parameter-holder mirrors of the reference classes (tests/ref_mirrors.py)
 
 
 def build(device, dim, mid, hidden, engine, T_end=12.8, dt=0.05, steps=None):

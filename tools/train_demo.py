@@ -1,6 +1,6 @@
 """A complete training run through the drop-in pieces — what `python scripts/main.py solver=basic_dis target=gmm
 loss.method=lv` does in the reference (`Trainable.run`, solver/base.py:456-498), here without Hydra: mirror objects
-(`sde_sampler_b200.plugins`), the fused loss, `loss.backward()` on the tensor cores, the fused optimizer tail and the fused
+(`tests/ref_mirrors.py`), the fused loss, `loss.backward()` on the tensor cores, the fused optimizer tail and the fused
 prior sampler; every `--eval-every` iterations `loss.eval` (EMA weights swapped in) gives the importance-sampling estimate
 of log Z (0 for the normalised GMM) and the ESS.
 
@@ -13,11 +13,12 @@ import time
 from functools import partial
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch
 from torch import nn
 
-from sde_sampler_b200 import FusedAdamEMA, FusedTimeReversalLoss, eval_moments, plugins, sample_gauss_prior
+from sde_sampler_b200 import FusedAdamEMA, FusedTimeReversalLoss, eval_moments, sample_gauss_prior
+import ref_mirrors as plugins  # parameter-holder mirrors of the reference classes (tests/ref_mirrors.py)
 from sde_sampler_b200.spec import ctrl_parameters
 
 ap = argparse.ArgumentParser()
