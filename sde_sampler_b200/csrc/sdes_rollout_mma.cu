@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t s_wbar;
     __shared__ uint64_t s_mbar[TC_GROUPS];
+    __shared__ uint64_t s_xbar[TC_GROUPS];  // arrival of a tile's x0 rows (TMA bulk copy)
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_tile[TC_GROUPS];
 
@@ -522,7 +523,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     }
     if (tid == 0) {
         tc::mbar_init(&s_wbar, 1);
-        for (int g = 0; g < TC_GROUPS; ++g) tc::mbar_init(&s_mbar[g], 1);
+        for (int g = 0; g < TC_GROUPS; ++g) {
+            tc::mbar_init(&s_mbar[g], 1);
+            tc::mbar_init(&s_xbar[g], 1);
+        }
         tc::fence_mbar_init();
     }
     tc::fence_before();
@@ -582,6 +586,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     c.bar = &s_mbar[c.g];
     c.phase = 0;
     const XPair xs{reinterpret_cast<float2*>(s_x + c.g * (DPAD * 128)) + c.gtid};
+    // The same region, seen row-major [row][dim], stages a tile's x0 / x_T between HBM and the pair layout: a tile's rows are
+    // one contiguous span of the caller's (B, d) tensors, moved by ONE TMA bulk copy each way (cp.async.bulk, SASS UBLKCP)
+    // instead of 128 threads striding through global memory 4 bytes at a time.
+    float* xrow = s_x + c.g * (DPAD * 128);
+    uint32_t xphase = 0;
+    const bool io_aligned = ((reinterpret_cast<uintptr_t>(d.x0) | reinterpret_cast<uintptr_t>(d.x_T)) & 15) == 0;
 
     uint32_t* counter = reinterpret_cast<uint32_t*>(const_cast<float*>(ws) + p.ws.counter);
     const bool from_hbm = (d.flags & SDES_F_NOISE_FROM_HBM) != 0;
@@ -610,13 +620,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
         float* st = state + (int64_t)tile * (DPAD + 1) * 128 + c.gtid;
 
         float rnd;
+        const int tile_rows = (int)((B - (int64_t)tile * 128 < 128) ? (B - (int64_t)tile * 128) : 128);
+        const uint32_t tile_bytes = (uint32_t)tile_rows * (uint32_t)dim * 4u;
+        const bool tile_tma = io_aligned && (tile_bytes & 15u) == 0u;  // bulk copies move multiples of 16 bytes (ragged last tile: plain loads)
         if (chunk == 0) {
             const TrajRef o0 = traj_ref(d, d.xs, 0, rrow);
+            float xv[DPAD];
+            if (tile_tma) {
+                if (c.gtid == 0) {
+                    tc::fence_proxy_async();  // the region was last touched through the generic proxy (previous item of this group)
+                    tc::mbar_arrive_expect_tx(&s_xbar[c.g], tile_bytes);
+                    tc::bulk_g2s(xrow, d.x0 + (int64_t)tile * 128 * dim, tile_bytes, &s_xbar[c.g]);
+                }
+                tc::mbar_wait(&s_xbar[c.g], xphase);
+                xphase ^= 1u;
+                const float* my = xrow + (valid ? c.gtid : tile_rows - 1) * dim;
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j) xv[j] = (j < dim) ? my[j] : 0.f;
+                group_bar(c.g);  // every row is in registers before the region is rewritten in the pair layout
+            } else {
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j) xv[j] = (j < dim) ? __ldg(d.x0 + rrow * dim + j) : 0.f;
+            }
 #pragma unroll
             for (int r = 0; r < DPAD / 2; ++r) {
-                float2 v;
-                v.x = (2 * r < dim) ? __ldg(d.x0 + rrow * dim + 2 * r) : 0.f;
-                v.y = (2 * r + 1 < dim) ? __ldg(d.x0 + rrow * dim + 2 * r + 1) : 0.f;
+                const float2 v = make_float2(xv[2 * r], xv[2 * r + 1]);
                 xs.set_pair(r, v);
                 if (ret_traj && valid) {
                     if (2 * r < dim) o0.p[(2 * r) * o0.stride] = v.x;
@@ -630,7 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
                     if (seen >= chunk) break;
-                    __nanosleep(256);  // the predecessor chunk runs for tens of microseconds: do not spend issue slots polling
+                    __nanosleep(2000);  // the predecessor chunk runs for tens of microseconds: do not spend issue slots polling
                 }
             }
             group_bar(c.g);
@@ -686,7 +714,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
         }
         if (i_end == T) {
             rnd += terminal_rnd<DPAD>(d, xs, tsm);
-            if (valid) {
+            if (tile_tma) {
+                float xv[DPAD];
+#pragma unroll
+                for (int j = 0; j < DPAD; ++j) xv[j] = xs[j];
+                group_bar(c.g);  // all pair-layout reads done before the region becomes the row-major x_T tile
+                if (valid) {
+                    float* my = xrow + c.gtid * dim;
+#pragma unroll
+                    for (int j = 0; j < DPAD; ++j)
+                        if (j < dim) my[j] = xv[j];
+                    d.rnd[rrow] = rnd;
+                }
+                tc::fence_proxy_async();  // generic-proxy writes -> visible to the bulk copy (async proxy)
+                group_bar(c.g);
+                if (c.gtid == 0) {
+                    tc::bulk_s2g(d.x_T + (int64_t)tile * 128 * dim, xrow, tile_bytes);
+                    tc::bulk_wait_read();  // the region is reused by this group's next item
+                }
+            } else if (valid) {
 #pragma unroll
                 for (int j = 0; j < DPAD; ++j)
                     if (j < dim) d.x_T[rrow * dim + j] = xs[j];
