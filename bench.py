@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py — trajectory-steps/sec of the fused rollout on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--engine auto|tcgen05|simt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload gmm50|cfg2|cfg3|cfg4|cfg5|gmm50dense]
+                    [--scaling weak|strong] [--global-batch B] [--engine auto|tcgen05|simt]
 
-Workload (north-star headline): GMM-40 d=50, DIS + log-variance loss, T=100, 65 536 trajectories
-per GPU (weak scaling: every rank carries its own shard of the global batch; the only exchange is
-the 8-double statistics all-gather inside the loss).  One "step" = one training-mode call of the
-loss plug-in, `loss(ts, x0, clipped_target_unnorm_log_prob, prior.log_prob)`: prologue kernel +
-persistent rollout kernel over all T time steps + statistics kernel.
+Default workload `gmm50` (north-star headline): GMM-40 d=50, DIS + log-variance loss, T=100, 65 536 trajectories per GPU
+(weak scaling: every rank carries its own shard of the global batch; the only exchange is the 8-double statistics
+all-gather inside the loss).  One "step" = one training-mode call of the loss plug-in,
+`loss(ts, x0, clipped_target_unnorm_log_prob, prior.log_prob)`: prologue kernel + persistent rollout kernel over all T time
+steps + statistics kernel.  The other workloads are BASELINE.json's configs (cfg2, cfg3, cfg4 = gmm50 at 32 768 per GPU,
+cfg5 on the wide engine) and `gmm50dense`, the headline with a 40-mode mixture that differs in every dimension.
 
 `value`   : N*B*T / time with x0 resident in HBM (CUDA events on the launching stream, max over ranks).
-`e2e`     : same call, but x0 starts in pinned host memory and the loss scalar is read back each step.
-`roofline`: MLP FLOPs (F(d) = 256 d + 16 384 per trajectory-step) of one rollout launch
-            over its CUDA-event duration, against the measured dense bf16 peak.
-`cpu_baseline` / `--impl reference`: oracle/torch_port.py — the reference's per-step op sequence in
-            torch eager on the host cores — on a bounded sample of the same workload.
+`e2e`     : same call, but every step's x0 starts in pinned host memory and the loss scalar is read back each step.
+`roofline`: MLP FLOPs (F(d) = 256 d + 16 384 per trajectory-step) of one rollout launch over its CUDA-event
+            duration, against the measured dense bf16 peak.
+`cpu_baseline` / `--impl reference`: oracle/torch_port.py — the reference's per-step op sequence in torch eager on the
+            host cores — on a bounded sample of the same workload.  The reference arm imports NOTHING from the product
+            package: the workload's spec comes from the golden fixture frozen from the unmodified reference.
+`gpu_eager_baseline`: the same op sequence as stock eager PyTorch kernels on the same GPU (fp32, TF32 off) — the
+            "existing Blackwell path" of SURVEY §8d.
 """
 from __future__ import annotations
 
@@ -50,145 +55,127 @@ def emit(line: dict):
     print(json.dumps(line), flush=True)
 
 
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-DIM, T_STEPS, BATCH_PER_GPU, N_MODES = 50, 100, 65536, 40
 METRIC = "trajectory-steps/sec"
 UNIT = "traj-steps/s"
+
+# Every fused-engine workload is a golden fixture's spec (tests/golden/<golden>.npz: the raw parameters extracted from the
+# UNMODIFIED reference objects by oracle/gen_golden.py) run at the BASELINE batch size; both arms read the same file.
+WORKLOADS = {
+    "gmm50": dict(golden="dis_gmm50_lv", batch=65536, x0="trunc_gauss",
+                  what="GMM-40 d=50 solver=dis loss=lv T=100", note="north-star headline (BASELINE configs[3] at 65 536 per GPU)"),
+    "cfg2": dict(golden="dis_gmm2_lv", batch=65536, x0="gauss", what="GMM-40 d=2 solver=basic_dis loss=lv T=100", note="BASELINE configs[1]"),
+    "cfg3": dict(golden="pis_funnel10_kl", batch=65536, x0="zeros", what="funnel d=10 solver=basic_pis loss=kl T=200", note="BASELINE configs[2]"),
+    "cfg4": dict(golden="dis_gmm50_lv", batch=32768, x0="trunc_gauss", what="GMM-40 d=50 solver=dis loss=lv T=100",
+                 note="BASELINE configs[3] as written: 262 144 trajectories over 8 GPUs = 32 768 per GPU"),
+    "gmm50dense": dict(golden="dis_gmmdense50_lv", batch=65536, x0="trunc_gauss", what="dense GMM-40 (modes differ in all 50 dims) d=50 solver=dis loss=lv T=100",
+                       note="the headline without GMM-40's zero-padded structure: no dimension factors out of the mixture"),
+}
 
 
 def flops_per_traj_step(d: int) -> int:
     return 256 * d + 16384  # x-dependent FourierMLP layers only, C=64, 4 layers
 
 
-def workload_name(batch: int) -> str:
-    return f"GMM-40 d={DIM} solver=dis loss=lv T={T_STEPS} batch={batch}/GPU"
+def workload_name(w: dict, batch: int) -> str:
+    return f"{w['what']} batch={batch}/GPU"
 
 
-def recorded_traffic(engine: str, batch: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the committed
-    `ncu --set full` capture of this same command (profiles/traffic.json), or None."""
+def load_spec(w: dict) -> dict:
+    from oracle import specio
+
+    return specio.load(os.path.join(ROOT, "tests", "golden", w["golden"] + ".npz"))["spec"]
+
+
+def sample_x0(kind: str, batch: int, dim: int, device, seed: int):
+    """The caller-side prior draw (solver/oc.py:71): conf/prior/gauss_truncate.yaml (trunc_normal_ at the 1e-4 quantiles),
+    conf/prior/gauss.yaml, or the Delta prior of PIS (distr/delta.py:25-28)."""
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if kind == "zeros":
+        return torch.zeros(batch, dim, device=device)
+    x = torch.randn(batch, dim, generator=g)
+    if kind == "trunc_gauss":
+        x = x.clamp_(-3.7190, 3.7190)  # standard normal quantiles of 1e-4 / 1 - 1e-4: same support as trunc_normal_
+    return x.to(device)
+
+
+def recorded_traffic(workload: str, engine: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the committed `ncu --set full` capture of
+    this same command (profiles/traffic.json; one capture per (workload, engine, batch)), or None."""
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        e = rec.get(f"{engine}:B={batch}")
-        return None if e is None else e["dram_bytes_per_launch"]
+        e = rec.get(f"{workload}:{engine}:B={batch}")
+        return (None, None) if e is None else (e["dram_bytes_per_launch"], e.get("source"))
     except Exception:
-        return None
+        return None, None
 
 
-# ----------------------------------------------------------------------------- the objects
-def build_objects(device, engine: str, process_group=None, seed: int = 1, sync_metrics: bool = True):
-    """conf/solver/dis.yaml with target GMM-40 d=50 (explicit loc), random-init
-    weights of the reference architecture, out layers re-randomised (the default zero init makes
-    NN == 0 and the MLP trivial)."""
-    import torch
-    from torch import nn
-    from functools import partial
-
-    import ref_mirrors as plugins  # parameter-holder mirrors of the reference classes (tests/ref_mirrors.py)
-    from sde_sampler_b200 import FusedTimeReversalLoss
-
-    torch.manual_seed(seed)
-    loc, scale, w = plugins.fab_gmm_params(DIM)
-    target = plugins.GMM(dim=DIM, loc=loc, scale=scale, mixture_weights=w)
-    prior = plugins.IsotropicGauss(dim=DIM, truncate_quartile=1e-4)  # conf/prior/gauss_truncate.yaml
-    sde = plugins.VP(diff_coeff_sq_min=0.1, diff_coeff_sq_max=10.0, terminal_t=1.0)  # conf/sde/vp_10.yaml
-    base = plugins.FourierMLP(dim=DIM, num_layers=4, channels=64)
-    gate = plugins.TimeEmbed(dim_out=1, num_layers=4, channels=64, last_bias_init=partial(nn.init.constant_, val=1.0))
-    with torch.no_grad():
-        base.out_layer.weight.normal_(0.0, 0.15)
-        base.out_layer.bias.normal_(0.0, 0.1)
-        gate.out_layer.weight.normal_(0.0, 0.05)
-    ctrl = plugins.LerpCtrl(base_model=base, clip_model=10.0, target_score=target.score, score_model=gate,
-                            detach_score=False, scale_score=1.0, clip_score=10.0, sde=sde, prior_score=prior.score)
-    for m in (target, prior, sde, base, gate):
-        m.to(device)
-    loss = FusedTimeReversalLoss(generative_ctrl=ctrl, sde=sde, method="lv", max_rnd=1e8, engine=engine,
-                                 process_group=process_group, seed=1234, sync_metrics=sync_metrics)
-
-    class Solver:  # owner of clipped_target_unnorm_log_prob (solver/oc.py:48-54)
-        def __init__(self):
-            self.target, self.clip_target = target, None
-
-        def clipped_target_unnorm_log_prob(self, x):
-            raise RuntimeError("introspected, never called")
-
-    ts = plugins.get_timesteps(0.0, 1.0, steps=T_STEPS).to(device)
-    return dict(loss=loss, ts=ts, terminal=Solver().clipped_target_unnorm_log_prob, second=prior.log_prob,
-                prior=prior, target=target, sde=sde, ctrl=ctrl)
-
-
-# ------------------------------------------------------------------------------ CPU baseline
-def cpu_port_setup():
-    """Spec dict of the same workload for oracle/torch_port.py (CPU tensors)."""
-    import torch
-
-    from sde_sampler_b200.spec import extract_spec
-
-    o = build_objects_cpu()
-    spec = extract_spec(o["loss"], "time_reversal", o["ts"], o["terminal"], o["second"], train=True, compute_ito=True)
-    return spec.to_dict(), o
-
-
-def build_objects_cpu():
-    import torch
-
-    from sde_sampler_b200 import _cabi
-
-    # the mirrors hold parameters only; building them on the CPU touches no kernel
-    return build_objects(torch.device("cpu"), "simt")
-
-
-def time_cpu_port(batch: int, repeats: int = 1):
+# ------------------------------------------------------------------------------ CPU / eager baselines
+def time_port(spec: dict, x0, device: str, repeats: int):
+    """oracle/torch_port.py: the reference's op sequence (losses/oc.py:176-222 and what it calls) in torch eager."""
     import torch
 
     from oracle import torch_port
 
-    spec, o = cpu_port_setup()
-    torch.manual_seed(0)
-    x0 = o["prior"].sample((batch,))
-    gen = torch.Generator().manual_seed(0)
     times = []
     for _ in range(repeats):
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        torch_port.rollout(spec, x0.numpy(), generator=gen)
+        torch_port.rollout(spec, x0, device=device, as_numpy=False)
+        if device != "cpu":
+            torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     return times
 
 
-def reference_arm(args):
-    """--impl reference: the CPU port on all host threads, bounded sample per step."""
+def cpu_sample_size(spec, w, dim, budget_s: float, total_steps: int, batch_cap: int) -> int:
+    T = len(spec["ts"]) - 1
+    probe_b = 256
+    probe = min(time_port(spec, sample_x0(w["x0"], probe_b, dim, "cpu", 0), "cpu", 2))
+    speed = probe_b * T / probe
+    sample = int(speed * budget_s / max(1, total_steps) / T)
+    return max(64, min(batch_cap, sample // 64 * 64))
+
+
+def reference_arm(args, w):
+    """--impl reference: the CPU port on all host threads, bounded sample per step.  No product import."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    probe_b = 256
-    probe = min(time_cpu_port(probe_b, repeats=2))
-    speed = probe_b * T_STEPS / probe
-    budget_s = 150.0
+    assert "sde_sampler_b200" not in sys.modules
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = load_spec(w)
+    dim, T = int(spec["dim"]), len(spec["ts"]) - 1
+    B = args.batch or w["batch"]
     total_steps = args.steps + args.warmup
-    sample = int(speed * budget_s / total_steps / T_STEPS)
-    sample = max(64, min(BATCH_PER_GPU, sample // 64 * 64))
-    times = time_cpu_port(sample, repeats=total_steps)[args.warmup:]
+    sample = cpu_sample_size(spec, w, dim, 150.0, total_steps, B)
+    x0 = sample_x0(w["x0"], sample, dim, "cpu", 0)
+    times = time_port(spec, x0, "cpu", total_steps)[args.warmup:]
     dt = sum(times) / len(times)
-    value = sample * T_STEPS / dt
-    line = {
+    value = sample * T / dt
+    assert "sde_sampler_b200" not in sys.modules, "the reference arm must not import the product"
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(BATCH_PER_GPU), "sample": f"{sample} of {BATCH_PER_GPU} trajectories x T={T_STEPS} per step"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(w, B), "sample": f"{sample} of {B} trajectories x T={T} per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"oracle/torch_port.py (reference op sequence, torch eager fp32, no_grad) on {sample} trajectories x T={T_STEPS}, {args.steps} steps"},
+                         "sample": f"oracle/torch_port.py (reference op sequence incl. the autograd target score, torch eager fp32, under "
+                                   f"no_grad: faster than the reference's train-mode call, so ratios against it are conservative) on {sample} "
+                                   f"trajectories x T={T}, {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+    })
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -287,52 +274,64 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+
+
 # ------------------------------------------------------------------------------ cfg5 (wide engine)
+def cfg5_reference_spec(steps: int) -> dict:
+    """cfg5's spec for the CPU port, without the product: committed fixture + regenerated NICE weights (tools/gen_bench_specs.py)."""
+    import bench_wide
+    from oracle import specio
+
+    spec = specio.load(bench_wide.SPEC_FIXTURE)
+    spec["target"] = bench_wide.nice_target_dict(**spec["target"]["regenerate"])
+    spec["ts"] = spec["ts"][: steps + 1]
+    return spec
+
+
 def main_cfg5(args):
     """BASELINE configs[4] on ONE GPU's shard: nice/mnist d=784, DDS + lv, T=257 (cosine grid), 4 096 trajectories
     per GPU (32 768 over 8).  Same JSON keys as the headline line; `roofline` counts the Linear layers of the control
     MLP and of the NICE forward + input-gradient backward (7.68e7 FLOP per trajectory-step, 2 per multiply-add; the
     three bf16 passes of the split-precision GEMM are NOT counted) against the measured dense bf16 peak."""
     import torch
-    import torch.distributed as dist
 
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_wide
-
-    from sde_sampler_b200 import _cabi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    B = 4096 if args.batch == BATCH_PER_GPU else args.batch
+    B = args.batch or 4096
     dim, mid, hidden = 784, 1000, 5
+    name = f"NICE d={dim} mid={mid} hidden={hidden} solver=dds loss=lv T=257 batch={B}/GPU"
     if args.impl == "reference":
         if rank != 0:
             return
         from oracle import torch_port
-        from sde_sampler_b200.spec import extract_spec
 
         torch.set_num_threads(os.cpu_count() or 1)
-        o = bench_wide.build(torch.device("cpu"), dim, mid, hidden, "simt", steps=4)
-        spec = extract_spec(o["loss"], "exp_integrator", o["ts"], o["terminal"], o["second"], train=True, compute_ito=True).to_dict()
         sample, T = 64, 4
-        x0 = o["prior"].sample((sample,))
+        spec = cfg5_reference_spec(T)
+        x0 = sample_x0("gauss", sample, dim, "cpu", 0)
         times = []
         for _ in range(args.steps + args.warmup):
             t0 = time.perf_counter()
-            torch_port.rollout(spec, x0.numpy(), generator=torch.Generator().manual_seed(0))
+            torch_port.rollout(spec, x0, generator=torch.Generator().manual_seed(0))
             times.append(time.perf_counter() - t0)
         dt = sum(times[args.warmup:]) / max(1, len(times[args.warmup:]))
         value = sample * T / dt
+        assert "sde_sampler_b200" not in sys.modules, "the reference arm must not import the product"
         emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"NICE d={dim} mid={mid} hidden={hidden} solver=dds loss=lv T=257 batch={B}/GPU",
-                                     "sample": f"{sample} trajectories x {T} of 257 time steps per step"},
-                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                           "sample": f"oracle/torch_port.py on {sample} trajectories x {T} time steps"},
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+              "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+              "dtype": "f32", "data": "synthetic",
+              "config": {"workload": name, "sample": f"{sample} trajectories x {T} of 257 time steps per step"},
+              "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"oracle/torch_port.py on {sample} trajectories x {T} time steps"},
+              "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         return
+    import torch.distributed as dist
+
+    from sde_sampler_b200 import _cabi
+
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     pg = None
@@ -355,7 +354,7 @@ def main_cfg5(args):
 
     steps = min(args.steps, 5)
     torch.set_grad_enabled(False)  # the metric is the forward rollout; with grad the loss keeps per-step state images
-    for _ in range(2):
+    for _ in range(3):
         loss(ts, x0, o["terminal"], o["second"])
     barrier()
     sampler = ClockSampler(local_rank)
@@ -391,11 +390,11 @@ def main_cfg5(args):
         f = bench_wide.flops_per_traj_step(dim, mid, hidden)
         ts_per_s = world * B * T * steps / (total_ms * 1e-3)
         ach = B * T * steps * f / (total_ms * 1e-3) / 1e12
-        line = {"metric": METRIC, "value": ts_per_s, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 2,
+        line = {"metric": METRIC, "value": ts_per_s, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 3,
                 "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (every Linear as 3 bf16 tcgen05 passes over hi/lo-split operands, fp32 accumulate; f32 elsewhere)",
                 "data": "synthetic",
-                "config": {"workload": f"NICE d={dim} mid={mid} hidden={hidden} solver=dds loss=lv T={T} batch={B}/GPU", "engine": "wide/tcgen05",
+                "config": {"workload": name, "engine": "wide/tcgen05",
                            "global_batch": world * B, "l2": "working set per step (weights 153 MB + activations) exceeds the 126 MB L2",
                            "noise": "in-kernel Philox4x32-10", "loss_value": float(val)},
                 "clocks": clocks,
@@ -404,6 +403,17 @@ def main_cfg5(args):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                              "flops_per_traj_step": f, "peak_source": "MEASURED_PEAKS.json bf16 dense, sustained (a step is thousands of GEMM launches)"}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import torch_port
+
+            torch.set_num_threads(os.cpu_count() or 1)
+            sample, Tc = 64, 4
+            spec = cfg5_reference_spec(Tc)
+            t0 = time.perf_counter()
+            torch_port.rollout(spec, sample_x0("gauss", sample, dim, "cpu", 0), generator=torch.Generator().manual_seed(0))
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": sample * Tc / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"oracle/torch_port.py on {sample} trajectories x {Tc} of 257 time steps, one pass, {dt:.1f} s"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -417,25 +427,29 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "tcgen05", "simt"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="trajectories per GPU")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="gmm50", choices=["gmm50", "cfg5"],
-                    help="gmm50 = north-star headline (default, the driver's line); cfg5 = BASELINE configs[4] per-GPU shard "
-                         "(NICE d=784 mid=1000, DDS+lv, T=257, 4096 trajectories per GPU) on the wide engine")
+    ap.add_argument("--batch", type=int, default=None, help="trajectories per GPU (default: the workload's BASELINE batch)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch trajectories per GPU; strong: --global-batch trajectories split over the ranks")
+    ap.add_argument("--global-batch", type=int, default=65536, help="total trajectories with --scaling strong")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs")
+    ap.add_argument("--workload", default="gmm50", choices=list(WORKLOADS) + ["cfg5"],
+                    help="gmm50 = north-star headline (default, the driver's line); cfg2 / cfg3 / cfg4 / cfg5 = BASELINE configs[1..4] "
+                         "per-GPU shards; gmm50dense = the headline with a mixture that differs in every dimension")
     args = ap.parse_args()
     _stdout_to_stderr()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "cfg5":
         return main_cfg5(args)
-
+    w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, w)
         return
 
     import torch
     import torch.distributed as dist
 
     from sde_sampler_b200 import _cabi
+    from sdes_test_helpers import build_from_spec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -452,14 +466,20 @@ def main():
         if rank == 0:
             print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     lib = _cabi.lib()
-    B = args.batch
+    if args.scaling == "strong":
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of ranks")
+        B = args.global_batch // world
+    else:
+        B = args.batch or w["batch"]
+    spec_dict = load_spec(w)
+    dim, T = int(spec_dict["dim"]), len(spec_dict["ts"]) - 1
     # resident-input leg: the filtered-trajectory count stays on the device (no host sync per call), so calls
     # queue back to back; the e2e leg below reads the loss scalar back every step.
-    o = build_objects(device, args.engine, process_group=pg, sync_metrics=False)
+    o = build_from_spec(spec_dict, device, engine=args.engine, process_group=pg, seed=1234, sync_metrics=False)
     loss, ts = o["loss"], o["ts"]
-    torch.manual_seed(100 + rank)
-    x0 = o["prior"].sample((B,))
-    x0_host = x0.cpu().pin_memory()
+    x0 = sample_x0(w["x0"], B, dim, device, 100 + rank)
+    x0_host = [x0.cpu().pin_memory(), x0.cpu().pin_memory()]
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step(x):
@@ -475,7 +495,8 @@ def main():
     # which engine did the descriptor resolve to?
     from sde_sampler_b200 import engine as eng
     from sde_sampler_b200.spec import extract_spec
-    spec = extract_spec(loss, "time_reversal", ts, o["terminal"], o["second"], train=True, compute_ito=True)
+    method = spec_dict["loss"]["method"]
+    spec = extract_spec(loss, spec_dict["loss"]["kind"], ts, o["terminal"], o["second"], train=True, compute_ito=method != "kl")
     desc, _ = eng.fill_desc(spec, batch=B, engine=args.engine)
     engine_used = "simt" if desc.flags & _cabi.F_MLP_SIMT else "tcgen05"
 
@@ -496,7 +517,7 @@ def main():
         ev[k][0].record()
         val, _m = step(x0)
         ev[k][1].record()
-        flush.zero_()  # L2 flush between timed iterations (inside the region; ~0.1 ms)
+        flush.zero_()  # L2 flush between timed iterations (inside the region; ~0.03 ms)
     t_end.record()
     barrier()
     launches = lib.sdes_launch_count() - launches0
@@ -517,79 +538,95 @@ def main():
         k_ms.append(a.elapsed_time(b))
     kernel_ms = statistics.median(k_ms)
 
-    # ---- training step: loss(...) with grad + loss.backward() (lv gradient on the tensor cores, csrc/sdes_grad.cu)
+    # ---- training step (headline only): loss(...) with grad + loss.backward() (csrc/sdes_grad.cu)
     from sde_sampler_b200.spec import ctrl_parameters
-    train_ms = None
-    try:
-        tm = []
-        for k in range(4):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for prm in ctrl_parameters(o["ctrl"]):
-                prm.grad = None
-            a.record()
-            v, _m = loss(ts, x0, o["terminal"], o["second"])
-            v.backward()
-            b.record()
-            torch.cuda.synchronize(device)
-            tm.append(a.elapsed_time(b))
-        train_ms = statistics.median(tm[1:])
-    except Exception as exc:  # reported, never hidden
-        train_ms = f"failed: {type(exc).__name__}: {exc}"
+    train_ms = kl_ms = full_ms = None
+    headline = args.workload == "gmm50"
+    if headline:
+        try:
+            tm = []
+            for k in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for prm in ctrl_parameters(o["ctrl"]):
+                    prm.grad = None
+                a.record()
+                v, _m = loss(ts, x0, o["terminal"], o["second"])
+                v.backward()
+                b.record()
+                torch.cuda.synchronize(device)
+                tm.append(a.elapsed_time(b))
+            train_ms = statistics.median(tm[1:])
+        except Exception as exc:  # reported, never hidden
+            train_ms = f"failed: {type(exc).__name__}: {exc}"
 
-    # ---- timed region 2: end to end through the plug-in with host buffers
+    # ---- timed region 2: end to end through the plug-in with host buffers.  The loop a user writes: the NEXT step's x0 goes
+    #      host -> device on a copy stream while the current rollout runs; every step still copies its own input inside the
+    #      region and reads its own loss back.
     barrier()
+    copy_stream = torch.cuda.Stream(device)
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     host_loss = 0.0
+    with torch.cuda.stream(copy_stream):
+        xd_next = x0_host[0].to(device, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(copy_stream)
     for k in range(args.steps):
-        xd = x0_host.to(device, non_blocking=True)
+        torch.cuda.current_stream(device).wait_event(ready)
+        xd = xd_next
         v, _m = step(xd)
+        if k + 1 < args.steps:
+            with torch.cuda.stream(copy_stream):
+                xd_next = x0_host[(k + 1) & 1].to(device, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+        xd.record_stream(torch.cuda.current_stream(device))
         host_loss = v.item()  # device -> host read of the step's result
     e_end.record()
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
 
     # ---- after the headline regions (the optimizer below changes the weights): the same workload with loss.method = kl
-    #      (backpropagation through time: reverse sweep csrc/sdes_adjoint.cu + the GEMM passes), and the complete training
-    #      iteration of Trainable.step (solver/base.py:399-454) with the fused optimizer tail (csrc/sdes_trainer.cu)
-    kl_ms, full_ms = None, None
-    try:
-        loss.method = "kl"
-        tm = []
-        for k in range(3):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for prm in ctrl_parameters(o["ctrl"]):
-                prm.grad = None
-            a.record()
-            v, _m = loss(ts, x0, o["terminal"], o["second"])
-            v.backward()
-            b.record()
-            torch.cuda.synchronize(device)
-            tm.append(a.elapsed_time(b))
-        kl_ms = statistics.median(tm[1:])
-    except Exception as exc:
-        kl_ms = f"failed: {type(exc).__name__}: {exc}"
-    finally:
-        loss.method = "lv"
-    try:
-        from sde_sampler_b200 import FusedAdamEMA
-        opt = FusedAdamEMA(ctrl_parameters(o["ctrl"]), lr=0.005, weight_decay=1e-7, grad_clip_norm=1.0,
-                           ema=dict(decay=0.9999, inv_gamma=1.0, power=0.9, update_after_step=2, update_every=1))
-        tm = []
-        for k in range(4):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            opt.zero_grad()
-            v, _m = loss(ts, x0, o["terminal"], o["second"])
-            v = v * (1.0 / DIM)  # scale_loss (conf/solver/oc_base.yaml:22)
-            v.backward()
-            opt.step(loss=v)
-            b.record()
-            torch.cuda.synchronize(device)
-            tm.append(a.elapsed_time(b))
-        full_ms = statistics.median(tm[1:])
-    except Exception as exc:
-        full_ms = f"failed: {type(exc).__name__}: {exc}"
+    #      (backpropagation through time), and the complete training iteration of Trainable.step (solver/base.py:399-454)
+    #      with the fused optimizer tail (csrc/sdes_trainer.cu)
+    if headline:
+        try:
+            loss.method = "kl"
+            tm = []
+            for k in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for prm in ctrl_parameters(o["ctrl"]):
+                    prm.grad = None
+                a.record()
+                v, _m = loss(ts, x0, o["terminal"], o["second"])
+                v.backward()
+                b.record()
+                torch.cuda.synchronize(device)
+                tm.append(a.elapsed_time(b))
+            kl_ms = statistics.median(tm[1:])
+        except Exception as exc:
+            kl_ms = f"failed: {type(exc).__name__}: {exc}"
+        finally:
+            loss.method = "lv"
+        try:
+            from sde_sampler_b200 import FusedAdamEMA
+            opt = FusedAdamEMA(ctrl_parameters(o["ctrl"]), lr=0.005, weight_decay=1e-7, grad_clip_norm=1.0,
+                               ema=dict(decay=0.9999, inv_gamma=1.0, power=0.9, update_after_step=2, update_every=1))
+            tm = []
+            for k in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                opt.zero_grad()
+                v, _m = loss(ts, x0, o["terminal"], o["second"])
+                v = v * (1.0 / dim)  # scale_loss (conf/solver/oc_base.yaml:22)
+                v.backward()
+                opt.step(loss=v)
+                b.record()
+                torch.cuda.synchronize(device)
+                tm.append(a.elapsed_time(b))
+            full_ms = statistics.median(tm[1:])
+        except Exception as exc:
+            full_ms = f"failed: {type(exc).__name__}: {exc}"
 
     times = torch.tensor([total_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -604,49 +641,61 @@ def main():
             pass
         peak_tf = peaks.get("bf16_tflops", 1590.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks else "1590 TFLOP/s, of fallback"
-        traj_steps = B * T_STEPS
+        traj_steps = B * T
         value = world * traj_steps * args.steps / (total_ms * 1e-3)
         e2e_value = world * traj_steps * args.steps / (e2e_ms * 1e-3)
-        achieved_tf = traj_steps * flops_per_traj_step(DIM) / (kernel_ms * 1e-3) / 1e12
+        achieved_tf = traj_steps * flops_per_traj_step(dim) / (kernel_ms * 1e-3) / 1e12
+        traffic, traffic_src = recorded_traffic(args.workload, engine_used, B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if engine_used == "simt" else "f32 (MLP as 3 bf16 tcgen05 MMA passes over hi/lo-split operands with fp32 accumulate, fp32-equivalent; f32 elsewhere)",
             "data": "synthetic",
-            "config": {"workload": workload_name(B), "engine": engine_used, "global_batch": world * B,
+            "config": {"workload": workload_name(w, B), "note": w["note"], "engine": engine_used, "global_batch": world * B,
                        "l2": "flushed between timed steps (192 MiB memset inside the region)",
-                       "noise": "in-kernel Philox4x32-10", "loss_value": loss_value},
+                       "noise": "in-kernel Philox4x32-10", "loss_value": loss_value,
+                       "spec": f"tests/golden/{w['golden']}.npz (parameters extracted from the unmodified reference objects)"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / args.steps, "loss_value": host_loss},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps, "loss_value": host_loss,
+                    "how": "x0 of step k+1 copied from pinned host memory on a side stream while step k runs; loss.item() every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": recorded_traffic(engine_used, B), "kernel_ms": kernel_ms,
-                         "flops_per_traj_step": flops_per_traj_step(DIM), "peak_source": peak_src,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kernel_ms,
+                         "flops_per_traj_step": flops_per_traj_step(dim), "peak_source": peak_src,
                          "traj_steps_per_s_kernel": traj_steps / (kernel_ms * 1e-3),
-                         "hbm_algorithmic_bytes": B * (8 * DIM + 4),
-                         "hbm_gbs": B * (8 * DIM + 4) / (kernel_ms * 1e-3) / 1e9},
+                         "hbm_algorithmic_bytes": B * (8 * dim + 4),
+                         "hbm_gbs": B * (8 * dim + 4) / (kernel_ms * 1e-3) / 1e9},
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
-            "train_step": {"what": "loss(ts, x0, ...) with grad + loss.backward(): rollout keeping xs, then the lv gradient "
-                                   "(forward + dgrad + wgrad GEMMs over all B*T rows)", "ms": train_ms,
-                           "traj_steps_per_s": (world * traj_steps / (train_ms * 1e-3)) if isinstance(train_ms, float) else None,
-                           "kl_ms": kl_ms, "kl_what": "same workload with loss.method=kl: rollout keeping xs, backpropagation through time as a "
-                                                      "discrete adjoint (per-step cotangent kernel + fused tcgen05 dgrad chain) "
-                                                      "inside the gradient's GEMM passes",
-                           "full_iteration_ms": full_ms,
-                           "full_iteration_what": "zero_grad + lv loss + backward + sdes_trainer_step (grad check, clip_grad_norm_, "
-                                                  "Adam, EMA), no host sync inside"},
         }
+        if headline:
+            line["train_step"] = {
+                "what": "loss(ts, x0, ...) with grad + loss.backward(): rollout keeping xs, then the lv gradient", "ms": train_ms,
+                "traj_steps_per_s": (world * traj_steps / (train_ms * 1e-3)) if isinstance(train_ms, float) else None,
+                "kl_ms": kl_ms, "kl_what": "same workload with loss.method=kl: rollout keeping xs, backpropagation through time as a discrete adjoint",
+                "full_iteration_ms": full_ms,
+                "full_iteration_what": "zero_grad + lv loss + backward + sdes_trainer_step (grad check, clip_grad_norm_, Adam, EMA), no host sync inside"}
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            probe = min(time_cpu_port(256, repeats=2))
-            sample = int(256 * T_STEPS / probe * 15.0 / T_STEPS)
-            sample = max(64, min(B, sample // 64 * 64))
-            dt = min(time_cpu_port(sample, repeats=1))
-            line["cpu_baseline"] = {"value": sample * T_STEPS / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+            # the existing-Blackwell bar: the reference's op sequence as stock eager PyTorch kernels on this GPU (fp32, TF32 off)
+            try:
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = False
+                be = min(B, 65536)
+                xe = x0[:be]
+                te = time_port(spec_dict, xe, str(device), 2)
+                line["gpu_eager_baseline"] = {
+                    "value": be * T / te[-1], "unit": UNIT, "ms": te[-1] * 1e3, "batch": be,
+                    "what": "oracle/torch_port.py (losses/oc.py:176-222 op sequence incl. the autograd GMM score; torch eager, fp32, "
+                            "TF32 off, under no_grad) on the same B200, second of two passes, wall clock around a device sync"}
+            except Exception as exc:
+                line["gpu_eager_baseline"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
+            torch.set_num_threads(os.cpu_count() or 1)
+            sample = cpu_sample_size(spec_dict, w, dim, 15.0, 1, B)
+            dt = min(time_port(spec_dict, sample_x0(w["x0"], sample, dim, "cpu", 0), "cpu", 1))
+            line["cpu_baseline"] = {"value": sample * T / dt, "unit": UNIT, "cores": torch.get_num_threads(),
                                     "kind": "port",
-                                    "sample": f"oracle/torch_port.py (reference op sequence, torch eager fp32) on {sample} of {B} trajectories x T={T_STEPS}, one pass, {dt:.1f} s"}
+                                    "sample": f"oracle/torch_port.py (reference op sequence, torch eager fp32, under no_grad: a lower bound on the "
+                                              f"reference's train-mode cost) on {sample} of {B} trajectories x T={T}, one pass, {dt:.1f} s"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -65,6 +65,19 @@ CASES = {
     "dis_gauss100_lv": dict(target="gauss", dim=100, sde="vp", prior="gauss", ctrl="lerp",
                             clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
                             method="lv", max_rnd=1e8, timesteps=LIN(30), batch=24, seed=10),
+    # A mixture whose components differ in EVERY dimension (no shared-dimension factorisation): the DENSE instantiation of the
+    # tensor-core rollout kernel (per-step score of all dims).  d=20 / 7 modes for the parity suite; d=50 / 40 modes is the
+    # `gmm50dense` bench workload (bench.py) — the headline configuration without the zero-padded structure of GMM-40.
+    "dis_gmmdense20_lv": dict(target="gmm_dense:7", dim=20, sde="vp", prior="gauss", ctrl="lerp",
+                              clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
+                              method="lv", max_rnd=1e8, timesteps=LIN(40), batch=48, seed=16),
+    "dis_gmmdense50_lv": dict(target="gmm_dense:40", dim=50, sde="vp", prior="gauss", ctrl="lerp",
+                              clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
+                              method="lv", max_rnd=1e8, timesteps=LIN(100), batch=32, seed=17),
+    "dds_gmmdense20_score": dict(target="gmm_dense:7", dim=20, sde=None, prior="gauss", ctrl="score",
+                                 clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="exp_integrator",
+                                 method="lv", max_rnd=1e8, alpha=1.0, sigma=1.0,
+                                 timesteps=dict(rescale_t="cosine", end=3.2, dt=0.05), batch=48, seed=18),
     # ---- kl / kl_ito training gradients (backpropagation through time).  Together with dis_gmm2_kl,
     # pis_funnel10_kl and dis_lerpprior_multiwell4 above these cover every loss kind, the reference control of Euler-DDS,
     # active clips, and each target's second derivative (funnel, multiwell, Gauss; the GMM score is an autograd score

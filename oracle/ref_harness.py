@@ -104,6 +104,17 @@ def build_target(kind: str, dim: int):
         w = 0.2 + torch.rand((K,), generator=g)
         return GMM(dim=dim, loc=loc, scale=scale, mixture_weights=w, name=None,
                    domain_tol=None, n_reference_samples=1000)
+    if kind.startswith("gmm_dense"):
+        # "gmm_dense:<K>" — K modes that differ in EVERY dimension (random loc, per-(k, j) scale, non-uniform weights): the
+        # general MixtureSameFamily of distr/gauss.py:119-140 with no dimension shared between components
+        g = torch.Generator()
+        K = int(kind.split(":")[1])
+        g.manual_seed(1000 + K)
+        loc = (torch.rand((K, dim), generator=g) - 0.5) * (80.0 if K >= 40 else 8.0)
+        scale = 0.8 + 1.2 * torch.rand((K, dim), generator=g)
+        w = 0.5 + torch.rand((K,), generator=g)
+        return GMM(dim=dim, loc=loc, scale=scale, mixture_weights=w, name=None,
+                   domain_tol=None, n_reference_samples=1000)
     if kind == "dw_shift":
         assert dim == 1
         return DoubleWell(separation=2.0, shift=1.5)

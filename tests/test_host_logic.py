@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-import bench
+from oracle import specio
 from sde_sampler_b200 import engine
 from sde_sampler_b200.dist import merge_stats
 from sde_sampler_b200.spec import ctrl_parameters, extract_spec
@@ -12,7 +12,13 @@ from sde_sampler_b200.spec import ctrl_parameters, extract_spec
 
 @pytest.fixture(scope="module")
 def objs():
-    return bench.build_objects(torch.device("cpu"), "simt")
+    import os
+
+    from conftest import GOLDEN_DIR
+    from sdes_test_helpers import build_from_spec
+
+    # the headline workload's objects (mirrors on the CPU hold parameters only; no kernel is touched)
+    return build_from_spec(specio.load(os.path.join(GOLDEN_DIR, "dis_gmm50_lv.npz"))["spec"], torch.device("cpu"), engine="simt")
 
 
 def _spec(o, **kw):

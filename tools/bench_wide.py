@@ -12,15 +12,38 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch
 from torch import nn
-from sde_sampler_b200 import FusedExponentialIntegratorSDELoss, _cabi
 import ref_mirrors as plugins  # parameter-holder mirrors of the reference classes (tests/ref_mirrors.py)
 
+SPEC_FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_cfg5_spec.npz")
 
-def build(device, dim, mid, hidden, engine, T_end=12.8, dt=0.05, steps=None):
+
+def nice_model(dim, mid, hidden):
+    """NiceModel(coupling=4, in_out_dim, mid_dim, hidden, mask_config=1) of scripts/train_nice.py:67-78 with seeded random
+    weights (no checkpoint can travel).  Constructed FIRST after the seed, so every caller gets the same weights."""
     torch.manual_seed(1)
     model = plugins.NiceModel(plugins.StandardLogistic(), coupling=4, in_out_dim=dim, mid_dim=mid, hidden=hidden, mask_config=1)
     with torch.no_grad():
         model.scaling.scale.normal_(0.0, 0.2)
+    return model
+
+
+def nice_target_dict(dim, mid, hidden) -> dict:
+    """The `target` entry of a rollout spec dict for nice_model(...) (same layout as sde_sampler_b200.spec._nice_params),
+    built from the mirror alone: bench.py's reference arm completes the committed cfg5 spec fixture with it (the 76 MB of
+    coupling weights are regenerated from the seed instead of being committed) without importing the product."""
+    model = nice_model(dim, mid, hidden)
+    couplings = []
+    for c in model.coupling:
+        lins = [c.in_block[0]] + [b[0] for b in c.mid_block] + [c.out_block]
+        couplings.append({"mask_config": int(c.mask_config),
+                          "layers": [(l.weight.detach().numpy().copy(), l.bias.detach().numpy().copy()) for l in lins]})
+    return {"kind": "nice", "couplings": couplings, "scale": model.scaling.scale.detach().reshape(-1).numpy().copy(), "log_norm_const": 0.0}
+
+
+def build(device, dim, mid, hidden, engine, T_end=12.8, dt=0.05, steps=None):
+    from sde_sampler_b200 import FusedExponentialIntegratorSDELoss
+
+    model = nice_model(dim, mid, hidden)
     target = plugins.Nice(model=model)
     prior = plugins.IsotropicGauss(dim=dim)
     base = plugins.FourierMLP(dim=dim, num_layers=4, channels=64)
@@ -66,6 +89,8 @@ def main():
     ap.add_argument("--engine", default="tcgen05")
     ap.add_argument("--train", action="store_true", help="also time loss(...) with grad + loss.backward()")
     args = ap.parse_args()
+    from sde_sampler_b200 import _cabi
+
     dev = torch.device("cuda:0")
     o = build(dev, args.dim, args.mid, args.hidden, args.engine, steps=args.steps)
     T = o["ts"].shape[0] - 1
