@@ -235,6 +235,11 @@ int sdes_langevin_integrate(const SdesRolloutDesc* target_desc, const SdesIntegr
 int sdes_rnd_stats(const float* rnd, int64_t batch, int mask_mode, float max_rnd,
                    const uint8_t* sample_mask, double* out_stats, void* stream);
 
+/* The rank-combining step of the statistics above as ONE launch: `gathered` (device, world x 8 doubles, the output of an
+ * all-gather of every rank's out_stats) -> out_stats of the global batch (all eight slots, [6] / [7] recomputed from the
+ * combined [0..2]).  Ranks that kept nothing contribute max = -inf and an exp-sum of 0; a NaN max propagates. */
+int sdes_merge_stats(const double* gathered, int32_t world, double* out_stats, void* stream);
+
 /* Importance weights exp(-rnd - max(-rnd)) (losses/oc.py:104-105); the shift is stats[3], read on device. */
 int sdes_weights(const float* rnd, int64_t batch, const double* stats, float* weights, void* stream);
 

@@ -28,6 +28,34 @@ from oracle import philox, ref_harness, specio  # noqa: E402
 from oracle.cases import CASES, EVAL_CASES, NOISE_SEED  # noqa: E402
 
 
+def reference_spec(built: dict, case: dict, compute_ito: bool) -> dict:
+    """sde_sampler_b200.spec.extract_spec applied to the UNMODIFIED reference objects of a case, the way the solver hands
+    them to the loss: bound methods of an owner object (solver/oc.py:158-163, :213-215, :305-306)."""
+    from sde_sampler_b200.spec import extract_spec
+
+    class _SolverShim:  # owner of clipped_target_unnorm_log_prob: introspected, never called
+        def __init__(self, target, clip_target):
+            self.target = target
+            self.clip_target = clip_target
+
+        def clipped_target_unnorm_log_prob(self, x):
+            raise RuntimeError("shim is introspected, never called")
+
+    loss = built["loss"]
+    shim = _SolverShim(built["target"], case.get("clip_target"))
+    if case.get("euler_dds"):
+        class _EulerShim:
+            def __init__(self, prior, sde):
+                self.prior, self.sde = prior, sde
+
+            def reference_ctrl(self, t, x):
+                return self.sde.diff(t, x) * self.prior.score(x)
+        loss.reference_ctrl = _EulerShim(built["prior"], built["sde"]).reference_ctrl
+    spec = extract_spec(loss, case["loss"], built["ts"], shim.clipped_target_unnorm_log_prob, built["second"],
+                        train=True, compute_ito=compute_ito)
+    return spec.to_dict()
+
+
 def run_case(name: str, case: dict) -> dict:
     import torch
 
@@ -93,27 +121,7 @@ def run_case(name: str, case: dict) -> dict:
         for q in params:
             q.grad = None
 
-    # target object proxy so that extract_spec sees solver-like clipped_target_unnorm_log_prob
-    class _SolverShim:
-        def __init__(self, target, clip_target):
-            self.target = target
-            self.clip_target = clip_target
-
-        def clipped_target_unnorm_log_prob(self, x):
-            raise RuntimeError("shim is introspected, never called")
-
-    shim = _SolverShim(built["target"], case.get("clip_target"))
-    if case.get("euler_dds"):
-        class _EulerShim:
-            def __init__(self, prior, sde):
-                self.prior, self.sde = prior, sde
-
-            def reference_ctrl(self, t, x):
-                return self.sde.diff(t, x) * self.prior.score(x)
-        loss.reference_ctrl = _EulerShim(built["prior"], built["sde"]).reference_ctrl
-    spec = extract_spec(loss, kind, ts, shim.clipped_target_unnorm_log_prob, built["second"],
-                        train=True, compute_ito=compute_ito)
-    out["spec"] = spec.to_dict()
+    out["spec"] = reference_spec(built, case, compute_ito)
 
     # --- eval-mode rollouts (losses/oc.py:258-278): train=False, change_sde_ctrl=False
     for j, (cw, rt) in enumerate(EVAL_CASES.get(name, [])):

@@ -120,6 +120,7 @@ SYMBOLS = {
     "sdes_rollout_fwd": (C.c_int, [C.POINTER(RolloutDesc), C.c_void_p]),
     "sdes_tcgen05_supported": (C.c_int, [C.POINTER(RolloutDesc)]),
     "sdes_rnd_stats": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, C.c_void_p]),
+    "sdes_merge_stats": (C.c_int, [_fp, C.c_int32, _fp, C.c_void_p]),
     "sdes_weights": (C.c_int, [_fp, C.c_int64, _fp, _fp, C.c_void_p]),
     "sdes_lv_traj_stats": (C.c_int, [_fp, C.c_int64, C.c_int32, C.c_int, C.c_float, _fp, _fp, C.c_void_p]),
     "sdes_lv_weights": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),

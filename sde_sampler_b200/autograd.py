@@ -70,8 +70,9 @@ class LvLoss(torch.autograd.Function):
 
 def wants_grad(loss_obj) -> bool:
     """True when the training call should return a loss with a grad_fn: grad mode on, trainable control parameters, and a
-    configuration the gradient kernels cover — lv / lv_traj: `sdes_rollout_lv_grad` (every engine); kl / kl_ito:
-    `sdes_rollout_kl_grad` (fused engines: d <= 64, analytic target)."""
+    configuration the gradient kernels cover — lv / lv_traj: `sdes_rollout_lv_grad`; kl / kl_ito: `sdes_rollout_kl_grad`
+    (every engine).  A configuration the kernels do not cover raises `NotImplementedError` here, like every other
+    unsupported case of the package, instead of returning a value without a grad_fn."""
     if not torch.is_grad_enabled():
         return False
     ctrl = loss_obj.generative_ctrl
@@ -82,9 +83,14 @@ def wants_grad(loss_obj) -> bool:
     dim = int(ctrl.base_model.input_embed.weight.shape[1])
     target = getattr(getattr(ctrl, "target_score", None), "__self__", None)
     wide = dim > _cabi.MAX_DIM or (target is not None and hasattr(target, "model"))
+    if not any(p.requires_grad for p in params):
+        return False
     if wide and loss_obj.method in ("kl", "kl_ito"):
-        return False  # backpropagation through time on the wide engine is not built: plain value, no grad_fn
+        raise NotImplementedError("loss.method=kl / kl_ito training on the wide engine (d > 64 or a NICE target): backpropagation "
+                                  "through time is implemented on the fused engines only; use loss.method=lv or torch.no_grad()")
     gate = getattr(ctrl, "score_model", None)
     if wide and gate is not None and int(gate.out_layer.weight.shape[0]) != 1:
-        return False  # the wide engine has a scalar gate only
-    return any(p.requires_grad for p in params)
+        # a silent grad-less value would surface as an unrelated autograd error in the caller's backward()
+        raise NotImplementedError("training with a per-dimension gate (conf/model/*_dim.yaml) on the wide engine (d > 64 or a NICE "
+                                  "target) is not implemented; evaluate under torch.no_grad() or use a scalar gate")
+    return True

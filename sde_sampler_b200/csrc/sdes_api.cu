@@ -230,6 +230,39 @@ __global__ void __launch_bounds__(1024) rnd_stats_kernel(const float* __restrict
     }
 }
 
+// (world, 8) per-rank statistics -> the statistics of the global batch (include/sdes_b200.h: sdes_merge_stats); one warp
+__global__ void merge_stats_kernel(const double* __restrict__ g, int world, double* __restrict__ out) {
+    const int lane = threadIdx.x;
+    double n = 0.0, s1 = 0.0, s2 = 0.0, nt = 0.0, mx = -INFINITY;
+    bool nan_seen = false;
+    for (int r = lane; r < world; r += 32) {
+        const double* v = g + (int64_t)r * 8;
+        n += v[0]; s1 += v[1]; s2 += v[2]; nt += v[5];
+        nan_seen |= (v[3] != v[3]);
+        if (v[0] > 0.0 && v[3] > mx) mx = v[3];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        nt += __shfl_xor_sync(0xffffffffu, nt, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        nan_seen |= __shfl_xor_sync(0xffffffffu, (int)nan_seen, o) != 0;
+    }
+    double se = 0.0;
+    for (int r = lane; r < world; r += 32) {
+        const double* v = g + (int64_t)r * 8;
+        if (v[0] > 0.0) se += v[4] * exp(v[3] - mx);
+    }
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (lane == 0) {
+        const double gmx = nan_seen ? (double)NAN : mx;
+        out[0] = n; out[1] = s1; out[2] = s2; out[3] = gmx; out[4] = nan_seen ? (double)NAN : se; out[5] = nt;
+        out[6] = (s2 - s1 * s1 / n) / (n - 1.0);
+        out[7] = s1 / n;
+    }
+}
+
 __global__ void weights_kernel(const float* __restrict__ rnd, int64_t B, const double* __restrict__ stats,
                                float* __restrict__ w) {
     const float mx = (float)stats[3];
@@ -661,6 +694,17 @@ int sdes_rnd_stats(const float* rnd, int64_t batch, int mask_mode, float max_rnd
     rnd_stats_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(rnd, batch, mask_mode, max_rnd, sample_mask, out_stats);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-7, "rnd_stats launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_merge_stats(const double* gathered, int32_t world, double* out_stats, void* stream_) {
+    g_err[0] = 0;
+    if (!gathered || !out_stats) return fail(-5, "gathered/out_stats NULL");
+    if (world < 1) return fail(-3, "world must be >= 1");
+    merge_stats_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(gathered, world, out_stats);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-7, "merge_stats launch failed: %s", cudaGetErrorString(e));
     g_launches++;
     return 0;
 }

@@ -19,9 +19,22 @@ def combine_stats(stats: torch.Tensor, process_group=None) -> torch.Tensor:
     world = dist.get_world_size(process_group)
     if world == 1:
         return stats
-    parts = [torch.empty_like(stats) for _ in range(world)]
-    dist.all_gather(parts, stats.contiguous(), group=process_group)
-    return merge_stats(torch.stack(parts))
+    if not stats.is_cuda:  # gloo (CPU tests of the host logic): list all-gather + the host restatement of the merge
+        parts = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(parts, stats.contiguous(), group=process_group)
+        return merge_stats(torch.stack(parts))
+    gathered = torch.empty((world, stats.numel()), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(gathered, stats.contiguous(), group=process_group)
+    # one launch (csrc/sdes_api.cu merge_stats_kernel) instead of ~15 tiny torch kernels serialised on the stream
+    import ctypes as C
+
+    from . import _cabi
+
+    out = torch.empty_like(stats)
+    with torch.cuda.device(stats.device):
+        _cabi.check(_cabi.lib().sdes_merge_stats(gathered.data_ptr(), world, out.data_ptr(),
+                                                 C.c_void_p(torch.cuda.current_stream(stats.device).cuda_stream)), "sdes_merge_stats")
+    return out
 
 
 def merge_stats(gathered: torch.Tensor) -> torch.Tensor:
