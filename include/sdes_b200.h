@@ -216,10 +216,49 @@ typedef struct SdesIntegrateDesc {
     const float* out_ts;
     const float* x_init;     /* (B, d) */
     float* xs_out;           /* (n_out, B, d) */
+    int32_t noise_is_increment; /* with SDES_F_NOISE_FROM_HBM: 0 = `noise` holds standard normals (scaled by sqrt(t - s) here),
+                                   1 = it holds the Brownian increments themselves — the `bm(s, t)` values of
+                                   eq/integrator.py:116-119, evaluated by the caller */
+    int32_t reserved;
 } SdesIntegrateDesc;
 
 size_t sdes_integrate_workspace_bytes(const SdesRolloutDesc* target_desc);
 int sdes_langevin_integrate(const SdesRolloutDesc* target_desc, const SdesIntegrateDesc* g, void* stream);
+
+/* EulerIntegrator.integrate (eq/integrator.py:79-127) for the OU family (eq/sdes.py:66-269: VP, ConstOU, ScaledBM, generative
+ * or not) and for a ControlledSDE (eq/sdes.py:272-305) whose control is the score of a Gaussian marginal — the inference
+ * processes of TrainableDiff.compute_results (solver/oc.py:100-110, called with timesteps = ts; PIS: :204-208), SURVEY §8f-3:
+ *   x <- x + (mu_i x + sigma_i c_i(x)) (t - s) + sigma_i dW_i,
+ *   c_i(x)_j = csig_i min((cloc[i, j] - x_j) cinv_i, cmax)          (absent when cloc is NULL)
+ * with the x-independent per-step coefficients in `tab` (n_steps x 8 floats: mu, sigma, csig, cinv, 4 reserved) — the
+ * caller evaluates the reference's own coefficient functions on the grid once.  dW_i = eps sqrt(t - s) with eps from the
+ * Philox stream (counter layout of the rollout), or from `noise` (n_steps, B, d) as standard normals / increments.
+ * Output at `out_ts` by the reference's linear interpolation.  Any d; one launch for the whole chain. */
+typedef struct SdesAffineIntegrateDesc {
+    uint32_t struct_bytes;   /* = sizeof(SdesAffineIntegrateDesc), checked */
+    int32_t dim;
+    int64_t batch;
+    int32_t n_steps, n_out;
+    float eps;               /* EulerIntegrator.eps */
+    float cmax;              /* upper clip of the control's score (PIS: 1e5); +inf = none */
+    const float* timesteps;  /* (n_steps + 1) */
+    const float* out_ts;     /* (n_out) */
+    const float* tab;        /* (n_steps, 8) */
+    const float* cloc;       /* (n_steps, d) or NULL */
+    const float* x_init;     /* (B, d) */
+    const float* noise;      /* (n_steps, B, d) or NULL (in-kernel Philox) */
+    int32_t noise_is_increment;
+    int32_t reserved;
+    uint64_t seed, traj_offset;
+    float* xs_out;           /* (n_out, B, d) */
+} SdesAffineIntegrateDesc;
+
+int sdes_affine_integrate(const SdesAffineIntegrateDesc* g, void* stream);
+
+/* The expectation estimates of LangevinSolver.run (solver/langevin.py:50-54; EXPECTATION_FNS, distr/base.py:12-17) over the
+ * rows of `xs` (n_rows, d) — the caller passes xs[burn_steps:] flattened: out4 (device, 4 doubles) = means over rows of
+ * sum_j x^2, sum_j |x|, sum_j x, sum_j (x^2 - x).  One launch. */
+int sdes_expectations(const float* xs, int64_t n_rows, int32_t dim, double* out4, void* stream);
 
 /* Statistics of rnd that BaseOCLoss.filter/compute_loss/compute_results reduce to
  * (losses/oc.py:50-123).  out_stats (device, 8 doubles):

@@ -119,4 +119,16 @@ ULA_CASES = {
     "ula_multiwell4": dict(target="multiwell", dim=4, terminal_t=0.5, dt=0.005, eval_steps=10, diff_coeff=1.0, clip_score=1e5, batch=32),
 }
 
+# EulerIntegrator.integrate on the OU family / ControlledSDE — the inference processes of TrainableDiff.compute_results
+# (solver/oc.py:100-110: integrate(sde=inference_sde, ts=ts, x_init=target samples, timesteps=ts)) and a dt grid with
+# interpolated outputs.  `grid`: "ts" = timesteps=ts as the solver passes them, or a dt for the integrator's own grid.
+OU_CASES = {
+    # DIS / Euler-DDS: inference_sde = VP(generative=False), no control (solver/oc.py:130-133, :287)
+    "ou_vp_inference3": dict(sde="vp", generative=False, ctrl=None, dim=3, eval_steps=25, grid="ts", batch=64),
+    # PIS: ControlledSDE(ScaledBM(generative=False), ctrl = PIS.inference_ctrl) (solver/oc.py:200-208) — a Brownian bridge to the origin
+    "ou_pis_bridge4": dict(sde="bm_pis", generative=False, ctrl="pis", dim=4, eval_steps=40, grid="ts", batch=48),
+    # generative ConstOU on the integrator's own dt grid: outputs interpolated (7 output intervals, 0.013-wide steps)
+    "ou_const_dt2": dict(sde="const_ou", generative=True, ctrl=None, dim=2, eval_steps=7, grid=0.013, batch=32),
+}
+
 NOISE_SEED = 0x5DE5_0001

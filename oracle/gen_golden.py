@@ -187,15 +187,77 @@ def run_ula_case(name: str, case: dict) -> dict:
             "torch_version": torch.__version__}
 
 
+def run_ou_case(name: str, case: dict) -> dict:
+    """EulerIntegrator.integrate of the unmodified reference on an OU-family SDE or a ControlledSDE around one
+    (eq/integrator.py:93-127, eq/sdes.py:272-305), Philox stream injected through `torch.randn`."""
+    import torch
+
+    ref_harness.import_reference()
+    from sde_sampler.distr.delta import Delta
+    from sde_sampler.eq.integrator import EulerIntegrator
+    from sde_sampler.eq.sdes import VP, ConstOU, ControlledSDE, ScaledBM
+    from sde_sampler.utils.common import get_timesteps
+
+    d, B = case["dim"], case["batch"]
+    gen = case["generative"]
+    mk = {"vp": lambda g: VP(diff_coeff_sq_min=0.1, diff_coeff_sq_max=10.0, scale_diff_coeff=1.0, terminal_t=1.0, generative=g),
+          "bm_pis": lambda g: ScaledBM(diff_coeff=0.4472135954999579, terminal_t=5.0, generative=g),
+          "const_ou": lambda g: ConstOU(drift_coeff=4.5, diff_coeff=3.0, terminal_t=1.0, generative=g)}[case["sde"]]
+    sde = mk(gen)
+    if case["ctrl"] == "pis":
+        class _PIS:  # the two attributes and the one method of solver.oc.PIS that the inference process uses (:204-208)
+            def __init__(self):
+                self.sde, self.prior = mk(True), Delta(dim=d)
+
+            def inference_ctrl(self, t, x):
+                reference_distr = self.sde.marginal_distr(t=t, x_init=self.prior.loc)
+                return self.sde.diff(t, x) * reference_distr.score(x).clip(max=1e5)
+
+        sde = ControlledSDE(sde=sde, ctrl=_PIS().inference_ctrl)
+    T_end = float(sde.terminal_t)
+    ts = get_timesteps(0.0, T_end, steps=case["eval_steps"])
+    if case["grid"] == "ts":
+        integ, timesteps = EulerIntegrator(), ts
+    else:
+        integ = EulerIntegrator(dt=case["grid"])
+        timesteps = get_timesteps(ts[0], ts[-1], dt=case["grid"])
+    n_steps = timesteps.shape[0] - 1
+    torch.manual_seed(78)
+    x0 = torch.randn(B, d) * 1.5
+    noise = philox.normal_noise(NOISE_SEED, B, n_steps, d)
+    it = iter(torch.from_numpy(noise))
+    orig = torch.randn
+
+    def fake(*shape, **kw):
+        n = next(it)
+        assert tuple(n.shape) == tuple(shape), (n.shape, shape)
+        return n
+
+    torch.randn = fake
+    try:
+        xs = integ.integrate(sde, ts=ts, x_init=x0.clone(), timesteps=timesteps if case["grid"] == "ts" else None)
+    finally:
+        torch.randn = orig
+    return {"x0": x0.numpy().copy(), "ts": ts.numpy().copy(), "timesteps": timesteps.numpy().copy(), "xs": xs.numpy().copy(),
+            "torch_version": torch.__version__}
+
+
 def main():
     if not ref_harness.available():
         raise SystemExit("reference not available; golden vectors can only be generated in the build container")
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    from oracle.cases import ULA_CASES
+    from oracle.cases import OU_CASES, ULA_CASES
 
-    names = sys.argv[1:] or list(CASES) + list(ULA_CASES)
+    names = sys.argv[1:] or list(CASES) + list(ULA_CASES) + list(OU_CASES)
     for name in names:
+        if name in OU_CASES:
+            out = run_ou_case(name, OU_CASES[name])
+            path = os.path.join(outdir, f"{name}.npz")
+            specio.save(path, out)
+            print(f"{name:36s} B={out['x0'].shape[0]:4d} d={out['x0'].shape[1]:3d} steps={out['timesteps'].shape[0]-1:5d} "
+                  f"outputs={out['xs'].shape[0]} |xs|max={np.abs(out['xs']).max():.3e} size={os.path.getsize(path)/1024:.0f} KiB")
+            continue
         if name in ULA_CASES:
             out = run_ula_case(name, ULA_CASES[name])
             path = os.path.join(outdir, f"{name}.npz")

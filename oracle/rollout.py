@@ -387,6 +387,56 @@ def langevin_integrate(tg, x0, timesteps, out_ts, diff_coeff, clip_score, noise,
     return np.concatenate(out, axis=0)
 
 
+def ou_coefficients(case, timesteps):
+    """Per-step (mu, sigma) of the OU family (eq/sdes.py:125-269) and, for the PIS inference process (solver/oc.py:200-208;
+    ControlledSDE eq/sdes.py:296-305), the control's (diff, loc factor, 1/var) at the reversed time — fp32 like the reference."""
+    f = np.float32
+    s = np.asarray(timesteps, dtype=f)[:-1]
+    sign = f(1.0 if case["generative"] else -1.0)
+    if case["sde"] == "vp":
+        bmin, bmax, T_end = f(0.1), f(10.0), f(1.0)
+        w = (s / T_end).astype(f)
+        a, b = (bmax, bmin) if case["generative"] else (bmin, bmax)
+        beta = _lerp(np.full_like(s, a), np.full_like(s, b), w).astype(f)                      # VP._diff_coeff_sq_t :222-229
+        mu, sigma = (sign * f(0.5) * beta).astype(f), np.sqrt(beta).astype(f)
+    elif case["sde"] == "bm_pis":
+        T_end = f(5.0)
+        mu, sigma = np.zeros_like(s), np.full_like(s, f(0.4472135954999579))
+    else:
+        T_end = f(1.0)
+        mu, sigma = np.full_like(s, sign * f(4.5)), np.full_like(s, f(3.0))
+    ctrl = None
+    if case.get("ctrl") == "pis":
+        tt = s if case["generative"] else (T_end - s).astype(f)                                # eq/sdes.py:302-303
+        var = (sigma * sigma * tt).astype(f)                                                    # ScaledBM.marginal_params :179-188
+        ctrl = dict(csig=sigma.copy(), cinv=(f(1.0) / var).astype(f), cmax=f(1e5))              # Delta prior at the origin: loc = 0
+    return mu, sigma, ctrl
+
+
+def affine_integrate(mu, sigma, ctrl, x0, timesteps, out_ts, noise, eps=1e-8, increments=False, dtype=np.float32):
+    """EulerIntegrator.integrate (eq/integrator.py:93-127) for x-affine SDEs: drift mu_i x (+ sigma_i csig_i min((0 - x) cinv_i,
+    cmax) for the PIS bridge control), diffusion sigma_i; `noise` standard normals (or Brownian increments)."""
+    dtype = np.dtype(dtype).type
+    xs = np.asarray(x0, dtype=dtype).copy()
+    timesteps = np.asarray(timesteps, dtype=dtype)
+    out_ts = np.asarray(out_ts, dtype=dtype)
+    out, cnt = [], 0
+    for i, (s, t) in enumerate(zip(timesteps[:-1], timesteps[1:])):
+        drift = dtype(mu[i]) * xs
+        if ctrl is not None:
+            score = np.minimum((dtype(0.0) - xs) * dtype(ctrl["cinv"][i]), dtype(ctrl["cmax"]))
+            drift = drift + dtype(sigma[i]) * (dtype(ctrl["csig"][i]) * score)
+        nz = np.asarray(noise[i], dtype=dtype) * (dtype(1.0) if increments else np.sqrt(dtype(t - s)))
+        xt = (xs + drift * dtype(t - s) + dtype(sigma[i]) * nz).astype(dtype)
+        if cnt < out_ts.shape[0] and out_ts[cnt] <= t + dtype(eps):
+            ind = int(np.searchsorted(out_ts[cnt:], t + dtype(eps), side="right"))
+            w = ((out_ts[cnt:cnt + ind].reshape(-1, 1, 1) - s) / (t - s)).astype(dtype)
+            out.append(_lerp(xs[None], xt[None], w).astype(dtype))
+            cnt += ind
+        xs = xt
+    return np.concatenate(out, axis=0)
+
+
 # --------------------------------------------------------------------------------------
 # reductions  (losses/oc.py:50-123)
 # --------------------------------------------------------------------------------------

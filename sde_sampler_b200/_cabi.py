@@ -96,6 +96,18 @@ class IntegrateDesc(C.Structure):
         ("struct_bytes", C.c_uint32), ("n_steps", C.c_int32), ("n_out", C.c_int32),
         ("diff_coeff", C.c_float), ("clip_score", C.c_float), ("eps", C.c_float),
         ("timesteps", _fp), ("out_ts", _fp), ("x_init", _fp), ("xs_out", _fp),
+        ("noise_is_increment", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AffineIntegrateDesc(C.Structure):
+    """struct SdesAffineIntegrateDesc (include/sdes_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("dim", C.c_int32), ("batch", C.c_int64), ("n_steps", C.c_int32), ("n_out", C.c_int32),
+        ("eps", C.c_float), ("cmax", C.c_float),
+        ("timesteps", _fp), ("out_ts", _fp), ("tab", _fp), ("cloc", _fp), ("x_init", _fp), ("noise", _fp),
+        ("noise_is_increment", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64), ("traj_offset", C.c_uint64),
+        ("xs_out", _fp),
     ]
 
 
@@ -103,6 +115,8 @@ class IntegrateDesc(C.Structure):
 SYMBOLS = {
     "sdes_integrate_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc)]),
     "sdes_langevin_integrate": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(IntegrateDesc), C.c_void_p]),
+    "sdes_affine_integrate": (C.c_int, [C.POINTER(AffineIntegrateDesc), C.c_void_p]),
+    "sdes_expectations": (C.c_int, [_fp, C.c_int64, C.c_int32, _fp, C.c_void_p]),
     "sdes_lv_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),
     "sdes_rollout_lv_grad": (C.c_int, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc), C.c_void_p]),
     "sdes_kl_grad_workspace_bytes": (C.c_size_t, [C.POINTER(RolloutDesc), C.POINTER(LvGradDesc)]),

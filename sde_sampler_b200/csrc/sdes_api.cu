@@ -24,6 +24,8 @@ size_t wide_workspace_bytes(const SdesRolloutDesc& d);
 int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t* err);
 // Langevin / Euler integrator (sdes_integrate.cu)
 cudaError_t launch_langevin(const IntegrateParams& a, cudaStream_t stream);
+cudaError_t launch_affine_integrate(const SdesAffineIntegrateDesc& g, cudaStream_t stream);
+cudaError_t launch_expectations(const float* xs, int64_t n_rows, int dim, double* out4, cudaStream_t stream);
 // lv gradient (sdes_grad.cu)
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows);
 int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err,
@@ -680,9 +682,34 @@ int sdes_langevin_integrate(const SdesRolloutDesc* desc, const SdesIntegrateDesc
     IntegrateParams a;
     a.d = p.d; a.ws = p.ws; a.timesteps = g->timesteps; a.out_ts = g->out_ts; a.n_steps = g->n_steps; a.n_out = g->n_out;
     a.diff_coeff = g->diff_coeff; a.clip_score = g->clip_score; a.eps = g->eps; a.x_init = g->x_init; a.xs_out = g->xs_out;
+    a.noise_is_increment = g->noise_is_increment;
     e = launch_langevin(a, stream);
     if (e != cudaSuccess) return fail(-7, "langevin kernel launch failed: %s", cudaGetErrorString(e));
     g_launches += 2;
+    return 0;
+}
+
+int sdes_affine_integrate(const SdesAffineIntegrateDesc* g, void* stream_) {
+    g_err[0] = 0;
+    if (g == nullptr || g->struct_bytes != sizeof(SdesAffineIntegrateDesc)) return fail(-2, "SdesAffineIntegrateDesc is NULL or has the wrong struct_bytes");
+    if (g->dim < 1 || g->batch < 0 || g->n_steps < 1 || g->n_out < 0) return fail(-3, "dim >= 1, batch >= 0, n_steps >= 1, n_out >= 0 required");
+    if (g->traj_offset + (uint64_t)g->batch > 0xFFFFFFFFull) return fail(-3, "traj_offset + batch exceeds the 32-bit Philox trajectory counter");
+    if (!g->timesteps || !g->tab || !g->x_init || (g->n_out > 0 && (!g->out_ts || !g->xs_out))) return fail(-5, "timesteps/tab/x_init/out_ts/xs_out must be non-NULL");
+    if ((g->dim & 3) == 0 && g->n_out > 0 && (reinterpret_cast<uintptr_t>(g->xs_out) & 15)) return fail(-5, "xs_out must be 16-byte aligned");
+    if (g->batch == 0) return 0;
+    cudaError_t e = launch_affine_integrate(*g, reinterpret_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(-7, "affine integrator launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
+    return 0;
+}
+
+int sdes_expectations(const float* xs, int64_t n_rows, int32_t dim, double* out4, void* stream_) {
+    g_err[0] = 0;
+    if (!xs || !out4) return fail(-5, "xs/out4 NULL");
+    if (n_rows < 0 || dim < 1) return fail(-3, "n_rows >= 0 and dim >= 1 required");
+    cudaError_t e = launch_expectations(xs, n_rows, dim, out4, reinterpret_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(-7, "expectations launch failed: %s", cudaGetErrorString(e));
+    g_launches++;
     return 0;
 }
 

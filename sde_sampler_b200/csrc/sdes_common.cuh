@@ -68,6 +68,7 @@ struct IntegrateParams {
     float diff_coeff, clip_score, eps;
     const float* x_init;     // (B, d)
     float* xs_out;           // (n_out, B, d)
+    int noise_is_increment;  // noise (HBM) holds Brownian increments instead of standard normals
 };
 
 __host__ __device__ inline int pad_dim(int d) {

@@ -133,6 +133,21 @@ class _OU(nn.Module):
     drift = _in_kernel("drift")
     diff = _in_kernel("diff")
     drift_div_int = _in_kernel("drift_div_int")
+    # The x-INDEPENDENT coefficient functions stay callable: FusedEulerIntegrator evaluates them once on the whole grid
+    # (they are the caller's object's own functions there; these mirror eq/sdes.py for the tests on the GPU box).
+
+
+class ControlledSDE(nn.Module):
+    """eq/sdes.py:272-305 — holder of (sde, ctrl); drift = sde.drift + sde.diff * ctrl(t or terminal_t - t, x)."""
+
+    def __init__(self, sde, ctrl=None):
+        super().__init__()
+        self.sde, self.ctrl = sde, ctrl
+        self.register_buffer("terminal_t", sde.terminal_t.clone(), persistent=False)
+
+    drift = _in_kernel("drift")
+    diff = _in_kernel("diff")
+    f_and_g = _in_kernel("f_and_g")
 
 
 class ConstOU(_OU):
@@ -145,12 +160,32 @@ class ConstOU(_OU):
         self.register_buffer("drift_coeff", torch.tensor(drift_coeff, dtype=torch.float), persistent=False)
         self.register_buffer("diff_coeff", torch.tensor(diff_coeff, dtype=torch.float), persistent=False)
 
+    def drift_coeff_t(self, t):  # eq/sdes.py:141-142
+        return self.sign * self.drift_coeff
+
+    def diff_coeff_t(self, t):  # :144-145
+        return self.diff_coeff
+
+    def marginal_params(self, t, x_init, var_init=None):  # :157-172
+        drift_coeff = self.sign * self.drift_coeff
+        loc = torch.exp(drift_coeff * t)
+        var = -self.diff_coeff ** 2 / (2 * drift_coeff) * (1 - torch.exp(2 * drift_coeff * t))
+        if var_init is not None:
+            var = var + loc ** 2 * var_init
+        return loc * x_init, var
+
 
 class ScaledBM(ConstOU):
     """eq/sdes.py:175-188"""
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, drift_coeff=0.0, **kwargs)
+
+    def marginal_params(self, t, x_init, var_init=None):  # eq/sdes.py:179-188
+        var = self.diff_coeff ** 2 * t
+        if var_init is not None:
+            var = var + var_init
+        return x_init, var
 
     def marginal_distr(self, t, x_init, var_init=None) -> "Gauss":
         var = self.diff_coeff ** 2 * t
@@ -168,6 +203,17 @@ class VP(_OU):
         self.register_buffer("scale_diff_coeff", torch.tensor(scale_diff_coeff, dtype=torch.float), persistent=False)
         self.register_buffer("diff_coeff_sq_min", torch.tensor(diff_coeff_sq_min, dtype=torch.float), persistent=False)
         self.register_buffer("diff_coeff_sq_max", torch.tensor(diff_coeff_sq_max, dtype=torch.float), persistent=False)
+
+    def _diff_coeff_sq_t(self, t):  # eq/sdes.py:222-229
+        if self.generative:
+            return torch.lerp(self.diff_coeff_sq_max, self.diff_coeff_sq_min, t / self.terminal_t)
+        return torch.lerp(self.diff_coeff_sq_min, self.diff_coeff_sq_max, t / self.terminal_t)
+
+    def drift_coeff_t(self, t):  # :231-232
+        return self.sign * 0.5 * self._diff_coeff_sq_t(t)
+
+    def diff_coeff_t(self, t):  # :234-235
+        return self.scale_diff_coeff * torch.sqrt(self._diff_coeff_sq_t(t))
 
 
 class LangevinSDE(nn.Module):

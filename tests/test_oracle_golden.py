@@ -95,3 +95,18 @@ def test_oracle_langevin_matches_reference(golden):
         xs = rollout.langevin_integrate(g["target"], g["x0"], g["timesteps"], g["ts"], g["diff_coeff"], g["clip_score"], noise)
         assert xs.shape == g["xs"].shape
         _close(xs, g["xs"])
+
+
+def test_oracle_affine_integrate_matches_reference(golden):
+    """oracle.rollout.affine_integrate vs EulerIntegrator.integrate of the unmodified reference on VP / ScaledBM / ConstOU and
+    on the PIS ControlledSDE (tests/golden/ou_*.npz)."""
+    from oracle.cases import OU_CASES
+
+    for name, case in OU_CASES.items():
+        g = golden(name)
+        B, d = g["x0"].shape
+        noise = philox.normal_noise(NOISE_SEED, B, g["timesteps"].shape[0] - 1, d)
+        mu, sigma, ctrl = rollout.ou_coefficients(case, g["timesteps"])
+        xs = rollout.affine_integrate(mu, sigma, ctrl, g["x0"], g["timesteps"], g["ts"], noise)
+        assert xs.shape == g["xs"].shape
+        _close(xs, g["xs"])
