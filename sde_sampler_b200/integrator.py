@@ -32,6 +32,10 @@ class FusedEulerIntegrator:
         self.dt, self.steps, self.rescale_t, self.eps = dt, steps, rescale_t, eps
         self._seed = seed
         self._calls = 0
+        from .losses import _STREAM_IDS
+
+        _STREAM_IDS[0] += 1
+        self._stream_id = _STREAM_IDS[0]  # per-object noise stream: a loss and an integrator under one torch seed do not share noise
         self._workspace = engine.Workspace()
         _cabi.lib()
 
@@ -120,8 +124,9 @@ class FusedEulerIntegrator:
         return xs
 
     def _next_seed(self) -> int:
-        base = torch.initial_seed() if self._seed is None else self._seed
-        seed = (((self._calls & 0xFFFFFFFF) << 32) | (base & 0xFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+        from .losses import mix_key
+
+        seed = mix_key(torch.initial_seed() if self._seed is None else self._seed, self._stream_id, self._calls)
         self._calls += 1
         return seed
 

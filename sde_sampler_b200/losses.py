@@ -30,6 +30,21 @@ from .autograd import wants_grad
 from .dist import combine_stats
 from .spec import ctrl_parameters, extract_spec
 
+_STREAM_IDS = [0]
+
+
+def mix_key(seed: int, stream: int, call: int) -> int:
+    """splitmix64-style mix of (seed, stream id, call counter) into one 64-bit Philox key."""
+    m = 0xFFFFFFFFFFFFFFFF
+    z = (seed & m) ^ ((stream & m) * 0x9E3779B97F4A7C15 & m) ^ ((call & m) * 0xBF58476D1CE4E5B9 & m)
+    for _ in range(2):
+        z = (z + 0x9E3779B97F4A7C15) & m
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+        z ^= z >> 31
+    return z
+
+
 # utils/common.py:9-13
 Results = namedtuple(
     "Results",
@@ -85,6 +100,8 @@ class FusedOCLoss:
         self._n_filtered_dev = None
         self._seed = seed
         self._calls = 0
+        _STREAM_IDS[0] += 1
+        self._stream_id = _STREAM_IDS[0]  # per-object noise stream (see _next_seed)
         self._workspace = engine_workspace()
         self._grad_workspace = engine_workspace()
         self._traj_buffer = engine_workspace()  # trajectory of the last training forward (row-tiled), reused across steps
@@ -94,11 +111,12 @@ class FusedOCLoss:
 
     # ------------------------------------------------------------------ noise stream
     def _next_seed(self) -> int:
-        """Philox key for the next rollout: low word = base seed (torch.initial_seed() unless
-        given), high word = number of rollouts this loss has run, so every call draws fresh
-        noise (the reference advances torch's global generator, losses/oc.py:214)."""
+        """Philox key for the next rollout: a 64-bit mix of the FULL base seed (torch.initial_seed() unless given), a
+        per-object stream id and the number of rollouts this loss has run — every call draws fresh noise (the reference
+        advances torch's global generator, losses/oc.py:214), and two loss objects (train / eval, or a loss and an
+        integrator) under the same torch seed do not replay each other's stream."""
         base = torch.initial_seed() if self._seed is None else self._seed
-        key = ((self._calls & 0xFFFFFFFF) << 32) | (base & 0xFFFFFFFF)
+        key = mix_key(base, self._stream_id, self._calls)
         self._calls += 1
         return key
 
@@ -117,7 +135,9 @@ class FusedOCLoss:
         """`extract_spec` with its object introspection cached: the spec only holds REFERENCES to the caller's live
         tensors (values are re-read by the kernels every call), so it stays valid as long as the same objects and the
         same parameter tensors are handed in; the scalars a scheduler may change between calls (clip values, ts) are
-        refreshed here on every call."""
+        refreshed here on every call.  Distribution / SDE buffers and the Python scalars read from them are part of the
+        cache key (`_buffer_ptrs`: pointers, in-place version counters, scalar values), because the spec may hold converted
+        copies of those."""
         ctrl = self.generative_ctrl
         live = ctrl_parameters(ctrl)
         key = (train, compute_ito, return_traj, int(ts.shape[0]), id(ctrl), id(self.sde),
@@ -156,6 +176,10 @@ class FusedOCLoss:
         x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=self._next_seed(),
                                       traj_offset=self._rank_offset(x.shape[0]), engine=self.engine,
                                       workspace=self._workspace)
+        if engine.is_wide(spec):
+            # the wide engine's gradient reads what a training forward kept INSIDE this workspace: any later rollout
+            # through it invalidates a pending backward (LvLoss.backward checks the version)
+            self._traj_version += 1
         return x_T, rnd, xs
 
     # ------------------------------------------------------------------- reductions
@@ -274,9 +298,11 @@ class FusedOCLoss:
 
     def load_state_dict(self, state_dict: dict):
         self.n_filtered = state_dict["n_filtered"]
+        self._calls = int(state_dict.get("noise_calls", self._calls))  # absent in the reference's checkpoints
 
     def state_dict(self) -> dict:
-        return {"n_filtered": self.n_filtered}
+        # `n_filtered` is the reference's key (losses/oc.py:133-137); `noise_calls` resumes the Philox stream where it stopped
+        return {"n_filtered": self.n_filtered, "noise_calls": self._calls}
 
     def _repeat(self, x):
         if self.traj_per_sample != 1:
@@ -284,14 +310,28 @@ class FusedOCLoss:
         return x
 
 
+_SCALAR_ATTRS = ("variance", "separation", "shift", "n_double_wells", "log_norm_const", "clip_target", "dim", "sign", "generative",
+                 "truncate_quartile")
+
+
 def _buffer_ptrs(obj) -> tuple:
-    """data pointers of the tensors an introspected owner (solver shim -> target, prior, reference, sde) holds"""
+    """Fingerprint of what an introspected owner (solver shim -> target, prior, reference, sde) holds: data pointers AND
+    in-place version counters of its buffers (the spec may hold fp32 / broadcast COPIES of them), plus the Python scalars
+    the extraction reads — so an in-place edit or a changed scalar re-extracts instead of being silently ignored."""
     if obj is None:
         return ()
     out = []
     for o in (obj, getattr(obj, "target", None), getattr(obj, "prior", None)):
+        if o is None:
+            continue
         if isinstance(o, torch.nn.Module):
-            out += [t.data_ptr() for t in o.buffers()]
+            out += [(t.data_ptr(), t._version) for t in o.buffers()]
+        for name in _SCALAR_ATTRS:
+            v = getattr(o, name, None)
+            if isinstance(v, (int, float, bool)):
+                out.append((name, v))
+            elif isinstance(v, (list, tuple)) and all(isinstance(e, (int, float)) for e in v):
+                out.append((name, tuple(v)))
     return tuple(out)
 
 

@@ -8,8 +8,19 @@ each of them: `.item()`, `all(p.grad.isfinite().all() ...)`).
                          ema=dict(decay=0.9999, inv_gamma=1, power=0.9, update_after_step=..., update_every=5))
     optim.zero_grad(); loss, _ = fused_loss(ts, x0, ...); (scale_loss * loss).backward(); optim.step(loss=loss)
 
-`FusedAdamEMA` is a `torch.optim.Optimizer` (so the reference's lr schedulers attach to it unchanged); the parameters are
-re-pointed to views of one flat fp32 buffer so the kernel updates them in place.  There is no CPU path."""
+`FusedAdamEMA` is a `torch.optim.Optimizer`; the parameters are re-pointed to views of one flat fp32 buffer so the kernel
+updates them in place.  There is no CPU path.
+
+LR schedulers: the reference calls `scheduler.step()` only when the optimizer stepped (`loss_ok and grad_ok`,
+solver/base.py:423-436).  Here that decision is taken on the DEVICE, so a scheduler (or `MultiStepParams`) attached to this
+optimizer must be gated on it — `if optim.step(loss=loss, sync_skip=True): scheduler.step()` (one host read of the flag,
+the same sync the reference pays), or `optim.stepped()` later.  Stepping a scheduler unconditionally advances the
+schedule on skipped steps and drifts from the reference.
+
+Checkpoints: `state_dict()` uses the `torch.optim.Adam` layout (`state` / `param_groups`, per-parameter `step`, `exp_avg`,
+`exp_avg_sq`) plus a `fused` entry (device counters, EMA shadow); `load_state_dict` accepts that, a plain
+`torch.optim.Adam` state dict of the reference's `Trainable` checkpoint, and — through `load_ema_state_dict` — a
+`torch_ema.ExponentialMovingAverage` state dict (`shadow_params`, `num_updates`)."""
 from __future__ import annotations
 
 import contextlib
@@ -63,12 +74,23 @@ class FusedAdamEMA(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------------------------------
     def _flat_grads(self) -> torch.Tensor:
-        return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self._params])
+        missing = [i for i, p in enumerate(self._params) if p.grad is None]
+        if missing:
+            # torch.optim.Adam skips such parameters entirely (no weight decay, no moment decay); the flat kernel updates
+            # every element, so a silent zero gradient would let them drift under weight_decay
+            raise RuntimeError(f"parameters {missing} have no gradient: FusedAdamEMA updates the whole flat buffer (freeze them with "
+                               "requires_grad=False before constructing the optimizer, or pass `grads=`)")
+        return torch.cat([p.grad.reshape(-1) for p in self._params])
+
+    def stepped(self) -> bool:
+        """Did the last `step()` update the parameters (loss_ok and grad_ok, solver/base.py:423-436)?  One host read."""
+        return bool(self.dev_state[5].item())
 
     @torch.no_grad()
-    def step(self, closure=None, loss: torch.Tensor | None = None, grads: torch.Tensor | None = None):
+    def step(self, closure=None, loss: torch.Tensor | None = None, grads: torch.Tensor | None = None, sync_skip: bool = False):
         """One `Trainable.step` tail.  `loss` (0-dim device tensor, optional) feeds the max_loss / isfinite check;
-        `grads` (flat, blob order) may be passed instead of reading `p.grad`."""
+        `grads` (flat, blob order) may be passed instead of reading `p.grad`.  Returns None (no host sync), or with
+        `sync_skip=True` whether the step was applied — gate `scheduler.step()` on it (module docstring)."""
         if closure is not None:
             raise NotImplementedError("closure")
         g = self._flat_grads() if grads is None else grads.detach().reshape(-1).to(torch.float32).contiguous()
@@ -96,7 +118,7 @@ class FusedAdamEMA(torch.optim.Optimizer):
         with torch.cuda.device(self.flat.device):
             stream = torch.cuda.current_stream(self.flat.device).cuda_stream
             _cabi.check(_cabi.lib().sdes_trainer_step(C.byref(d), C.c_void_p(stream)), "sdes_trainer_step")
-        return None
+        return self.stepped() if sync_skip else None
 
     def metrics(self) -> dict:
         """One host read of the device-side counters (the reference's train/* metrics, solver/base.py:421-451)."""
@@ -123,24 +145,99 @@ class FusedAdamEMA(torch.optim.Optimizer):
         finally:
             self.flat.copy_(backup)
 
+    # ------------------------------------------------------------------------------------------ checkpoints
+    def _segments(self):
+        o = 0
+        for i, p in enumerate(self._params):
+            yield i, p, o, o + p.numel()
+            o += p.numel()
+
     def state_dict(self) -> dict:
-        return {"param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}],
-                "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "ema_shadow": None if self.ema_shadow is None else self.ema_shadow.clone(), "dev_state": self.dev_state.clone()}
+        """torch.optim.Adam layout + a `fused` entry (module docstring)."""
+        st = self.dev_state.tolist()
+        step = torch.tensor(float(st[0]))
+        state = {i: {"step": step.clone(), "exp_avg": self.exp_avg[a:b].view(p.shape).clone(),
+                     "exp_avg_sq": self.exp_avg_sq[a:b].view(p.shape).clone()} for i, p, a, b in self._segments()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self._params)))
+        return {"state": state, "param_groups": [group],
+                "fused": {"dev_state": self.dev_state.clone(), "ema_shadow": None if self.ema_shadow is None else self.ema_shadow.clone(),
+                          "ema": None if self.ema is None else dict(self.ema)}}
 
     def load_state_dict(self, sd: dict):
-        self.param_groups[0].update(sd["param_groups"][0])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        if self.ema_shadow is not None and sd.get("ema_shadow") is not None:
-            self.ema_shadow.copy_(sd["ema_shadow"])
-        self.dev_state.copy_(sd["dev_state"])
+        if "state" not in sd or "param_groups" not in sd:
+            raise KeyError("FusedAdamEMA.load_state_dict expects the torch.optim layout: keys 'state' and 'param_groups' "
+                           f"(got {sorted(sd)})")
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise ValueError(f"checkpoint has {len(groups)} parameter groups; FusedAdamEMA holds one")
+        ids = list(groups[0].get("params", range(len(self._params))))
+        if len(ids) != len(self._params):
+            raise ValueError(f"checkpoint holds {len(ids)} parameters, the optimizer {len(self._params)}")
+        self.param_groups[0].update({k: v for k, v in groups[0].items() if k != "params"})
+        steps = []
+        for (i, p, a, b), pid in zip(self._segments(), ids):
+            ent = sd["state"].get(pid, sd["state"].get(str(pid)))
+            if ent is None:  # torch.optim.Adam creates state lazily: a parameter that never stepped has none
+                self.exp_avg[a:b].zero_()
+                self.exp_avg_sq[a:b].zero_()
+                continue
+            for key, buf in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                t = ent[key]
+                if tuple(t.shape) != tuple(p.shape):
+                    raise ValueError(f"state[{pid}][{key!r}] has shape {tuple(t.shape)}, parameter {i} has {tuple(p.shape)}")
+                buf[a:b].copy_(t.reshape(-1).to(buf.dtype))
+            steps.append(float(ent["step"]))
+        if steps and max(steps) != min(steps):
+            raise ValueError("per-parameter Adam step counts differ; FusedAdamEMA keeps one step counter")
+        fused = sd.get("fused")
+        if fused is not None:
+            self.dev_state.copy_(fused["dev_state"])
+            if self.ema_shadow is not None:
+                if fused.get("ema_shadow") is not None:
+                    if fused["ema_shadow"].numel() != self.ema_shadow.numel():
+                        raise ValueError("EMA shadow size does not match the parameters")
+                    self.ema_shadow.copy_(fused["ema_shadow"])
+                else:  # no shadow in the checkpoint: restart the average from the current weights, counter at 0
+                    self.ema_shadow.copy_(self.flat)
+                    self.dev_state[2] = 0.0
+        else:  # a plain torch.optim.Adam checkpoint (the reference's Trainable): step counter from the entries, rest fresh
+            self.dev_state.zero_()
+            self.dev_state[0] = steps[0] if steps else 0.0
+            if self.ema_shadow is not None:
+                self.ema_shadow.copy_(self.flat)
+
+    def load_ema_state_dict(self, sd: dict):
+        """A `torch_ema.ExponentialMovingAverage.state_dict()` (the reference's checkpoint entry `ema`): `shadow_params`
+        (one tensor per parameter, in parameter order) and `num_updates`."""
+        if self.ema_shadow is None:
+            raise ValueError("this optimizer was built without ema=...")
+        shadow = sd["shadow_params"]
+        if len(shadow) != len(self._params):
+            raise ValueError(f"EMA checkpoint holds {len(shadow)} tensors, the optimizer {len(self._params)} parameters")
+        for (i, p, a, b), t in zip(self._segments(), shadow):
+            if tuple(t.shape) != tuple(p.shape):
+                raise ValueError(f"shadow_params[{i}] has shape {tuple(t.shape)}, parameter has {tuple(p.shape)}")
+            self.ema_shadow[a:b].copy_(t.reshape(-1).to(self.ema_shadow.dtype))
+        self.dev_state[2] = float(sd.get("num_updates") or 0)
+        if sd.get("decay") is not None:
+            self.ema["decay"] = float(sd["decay"])
+
+
+_PRIOR_CALLS = [0]
 
 
 def sample_gauss_prior(batch: int, dim: int, *, mean: float = 0.0, std: float = 1.0, truncate: tuple | None = None,
-                       seed: int = 0, traj_offset: int = 0, device="cuda", uniforms: torch.Tensor | None = None) -> torch.Tensor:
+                       seed: int | None = None, traj_offset: int = 0, device="cuda", uniforms: torch.Tensor | None = None) -> torch.Tensor:
     """x0 ~ IsotropicGauss prior on the device (`sdes_sample_gauss_prior`): `truncate=(a, b)` = the bounds
-    `IsotropicGauss.truncate_quartile` holds (distr/gauss.py:206-213)."""
+    `IsotropicGauss.truncate_quartile` holds (distr/gauss.py:206-213).  `seed=None` (default) draws a fresh stream per call
+    from torch's seed and a call counter — like `prior.sample`, repeated calls return different samples; pass `seed` for a
+    reproducible draw."""
+    if seed is None:
+        from .losses import mix_key
+
+        seed = mix_key(torch.initial_seed(), 0x9817, _PRIOR_CALLS[0])
+        _PRIOR_CALLS[0] += 1
     device = torch.device(device)
     if device.type != "cuda":
         raise _cabi.SdesError("prior sampling runs on a CUDA device only; there is no CPU path")

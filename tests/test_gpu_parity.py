@@ -99,7 +99,10 @@ def test_public_eval_and_call_run(golden, engine):
     assert set(res.log_norm_const_preds) == {"log_norm_const_lb_ito", "log_norm_const_is"}
     res2 = b["loss"].eval(b["ts"], x0, b["terminal"], b["second"], compute_weights=False, return_traj=False)
     assert res2.xs is None and res2.weights is None and set(res2.log_norm_const_preds) == {"log_norm_const_lb"}
-    assert b["loss"].state_dict() == {"n_filtered": b["loss"].n_filtered}
+    sd = b["loss"].state_dict()  # the reference's key (losses/oc.py:133-137) + the position of the Philox stream
+    assert sd["n_filtered"] == b["loss"].n_filtered and set(sd) == {"n_filtered", "noise_calls"} and sd["noise_calls"] >= 3
+    b["loss"].load_state_dict({"n_filtered": 5})  # a checkpoint written by the reference loads
+    assert b["loss"].n_filtered == 5
 
 
 @pytest.mark.parametrize("engine", ENGINES)

@@ -75,8 +75,7 @@ def test_trainer_step_matches_torch_adam_clip_ema():
             ref_ema.update(ref_p)
         else:
             skipped += 1
-        fus.step()
-        if fus.metrics()["train/stepped"]:
+        if fus.step(sync_skip=True):   # the reference steps its scheduler only when the optimizer stepped (solver/base.py:423-436)
             sched_f.step()
         for p, q in zip(ref_p, fus_p):
             assert torch.allclose(p, q, rtol=2e-6, atol=2e-7), it
@@ -113,6 +112,59 @@ def test_trainer_step_loss_check_and_state_roundtrip():
     opt2 = FusedAdamEMA(p2, lr=1e-2, max_loss=10.0)
     opt2.load_state_dict(sd)
     assert torch.equal(opt2.exp_avg, opt.exp_avg) and opt2.metrics()["train/optim_steps"] == 1
+
+
+def test_checkpoint_interop_with_torch_adam_and_torch_ema():
+    """A checkpoint written by the reference's Trainable (torch.optim.Adam + torch_ema state dicts) loads into FusedAdamEMA
+    and training continues bit-compatibly; the fused state dict has the torch.optim layout; bad shapes raise clearly."""
+    ref_p, fus_p = _make_params(4), _make_params(4)
+    ref = torch.optim.Adam(ref_p, lr=0.003, weight_decay=1e-7)
+    g = torch.Generator().manual_seed(2)
+    for _ in range(3):
+        for p in ref_p:
+            p.grad = torch.randn(*p.shape, generator=g).to(DEV) * 0.1
+        ref.step()
+    adam_sd = ref.state_dict()
+    ema_sd = {"decay": 0.999, "num_updates": 3, "shadow_params": [p.detach().clone() * 0.5 for p in ref_p], "collected_params": None}
+    with torch.no_grad():
+        for p, q in zip(ref_p, fus_p):
+            q.copy_(p)
+    fus = FusedAdamEMA(fus_p, lr=0.003, weight_decay=1e-7, ema=dict(decay=0.999, update_after_step=0, update_every=1))
+    fus.load_state_dict(adam_sd)
+    fus.load_ema_state_dict(ema_sd)
+    assert fus.metrics()["train/optim_steps"] == 3 and fus.metrics()["train/ema_num_updates"] == 3
+    assert torch.equal(fus.ema_shadow[: ref_p[0].numel()].view(ref_p[0].shape), ref_p[0].detach() * 0.5)
+    for _ in range(2):
+        grads = [torch.randn(*p.shape, generator=g).to(DEV) * 0.1 for p in ref_p]
+        for p, q, gr in zip(ref_p, fus_p, grads):
+            p.grad, q.grad = gr.clone(), gr.clone()
+        ref.step()
+        fus.step()
+        for p, q in zip(ref_p, fus_p):
+            assert torch.allclose(p, q, rtol=2e-6, atol=2e-7)
+    sd = fus.state_dict()
+    assert set(sd) >= {"state", "param_groups"} and sd["param_groups"][0]["params"] == list(range(len(fus_p)))
+    assert tuple(sd["state"][2]["exp_avg"].shape) == tuple(fus_p[2].shape) and float(sd["state"][0]["step"]) == 5
+    torch.optim.Adam(_make_params(4), lr=0.003).load_state_dict({"state": sd["state"], "param_groups": sd["param_groups"]})  # torch accepts it
+    bad = {"state": {0: {"step": torch.tensor(1.0), "exp_avg": torch.zeros(3, 3), "exp_avg_sq": torch.zeros(3, 3)}},
+           "param_groups": [{"lr": 0.1, "params": list(range(len(fus_p)))}]}
+    with pytest.raises(ValueError, match="shape"):
+        fus.load_state_dict(bad)
+    with pytest.raises(KeyError, match="torch.optim layout"):
+        fus.load_state_dict({"exp_avg": None})
+
+
+def test_missing_gradient_raises_and_prior_streams_differ():
+    p = _make_params(5)
+    opt = FusedAdamEMA(p, lr=1e-2)
+    for q in p[1:]:
+        q.grad = torch.ones_like(q)
+    with pytest.raises(RuntimeError, match="no gradient"):
+        opt.step()
+    a = sample_gauss_prior(256, 4, device=DEV)
+    b = sample_gauss_prior(256, 4, device=DEV)
+    assert not torch.equal(a, b)                                     # like prior.sample: a fresh draw per call
+    assert torch.equal(sample_gauss_prior(256, 4, seed=9, device=DEV), sample_gauss_prior(256, 4, seed=9, device=DEV))
 
 
 def test_truncated_prior_matches_trunc_normal_transform():
