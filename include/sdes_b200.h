@@ -66,6 +66,9 @@ enum { SDES_TARGET_GMM = 0, SDES_TARGET_MULTIWELL = 1 /* DoubleWell = n_dw=d=1 *
                                            operand image of the state at every step, the per-step gate cotangent
                                            sums); the gradient call must then be given the same workspace */
 
+#define SDES_F_KEEP_SCORE     (1u << 10) /* with KEEP_FOR_GRAD, for sdes_rollout_kl_grad on the wide engine: also keep the target
+                                           score of every step and of the terminal state (T + 1 planes of (B, d) fp32) */
+
 /* Layout of the flat fp32 parameter blob `params` (torch (out,in) row-major weights, C = 64):
  *   FourierMLP (models/mlp.py:85-122)
  *     in_w[C*d] in_b[C]
@@ -194,9 +197,13 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
  * GEMM chain on that step's row tiles, accumulating into the fp32 adjoint; weight gradients once per chunk.  With
  * SDES_F_MLP_SIMT: one thread-per-trajectory reverse-sweep kernel (fp32 FFMA) writes the cotangent of the control at
  * every (trajectory, step) into the workspace and the batched pass of sdes_rollout_lv_grad consumes it.  Same descriptors and outputs as sdes_rollout_lv_grad; `w` = d loss / d rnd_b
- * (sdes_kl_weights); g->flags = SDES_GRAD_*.  Fused engines only (d <= SDES_MAX_DIM, analytic target); a GMM target
- * with more than one component requires SDES_GRAD_TARGET_SCORE_CONST (the reference's semantics) or
- * SDES_GRAD_SCORE_DETACHED. */
+ * (sdes_kl_weights); g->flags = SDES_GRAD_*.  A GMM target with more than one component requires
+ * SDES_GRAD_TARGET_SCORE_CONST (the reference's semantics) or SDES_GRAD_SCORE_DETACHED.
+ * Wide engine (d > SDES_MAX_DIM or a NICE target): the forward ran with SDES_F_KEEP_FOR_GRAD | SDES_F_KEEP_SCORE in the same
+ * workspace; the sweep is one elementwise kernel + the dgrad GEMM chain (incl. W_in^T, accumulating into the fp32 adjoint)
+ * per step inside the reverse chunk loop.  A NICE / multi-component GMM score is a constant of the graph (the reference's
+ * autograd score without create_graph); a single Gaussian target is differentiated analytically; wide funnel / multi-well
+ * targets are refused. */
 size_t sdes_kl_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);
 int sdes_rollout_kl_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, void* stream);
 

@@ -95,6 +95,14 @@ CASES = {
     "dis_lerp_multiwell5_klito": dict(target="multiwell", dim=5, sde="vp", prior="gauss", ctrl="lerp",
                                       clip_model=2.0, clip_score=3.0, gate_bias=1.0, gate_dim=5, loss="time_reversal",
                                       method="kl_ito", max_rnd=None, clip_target=30.0, timesteps=LIN(40), batch=48, seed=14),
+    # kl on the WIDE engine (NICE target / d > 64): the sweep's adjoint is a (B, d) fp32 plane, the dgrad chain per step GEMM launches
+    "dds_nice16_kl": dict(target="nice:24:3", dim=16, sde=None, prior="gauss", ctrl="score",
+                          clip_model=10.0, clip_score=10.0, gate_bias=0.01, loss="exp_integrator",
+                          method="kl", max_rnd=1e8, alpha=1.0, sigma=1.0,
+                          timesteps=dict(rescale_t="cosine", end=3.2, dt=0.05), batch=48, seed=19),
+    "dis_gauss100_klito": dict(target="gauss", dim=100, sde="vp", prior="gauss", ctrl="lerp",
+                               clip_model=10.0, clip_score=10.0, gate_bias=1.0, loss="time_reversal",
+                               method="kl_ito", max_rnd=1e8, timesteps=LIN(30), batch=24, seed=20),
     # lv_traj (losses/oc.py:78-84): variance across the traj_per_sample trajectories of each initial point.  The fixture's x0
     # is the repeated batch (3 stacked copies of 24 points); the training call is given the 24 points.
     "dis_gmm2_lvtraj": dict(target="gmm40", dim=2, sde="vp", prior="gauss", ctrl="lerp",

@@ -33,6 +33,7 @@ F_HAS_GATE = 1 << 6
 F_MLP_SIMT = 1 << 7
 F_TRAJ_TILED = 1 << 8
 F_KEEP_FOR_GRAD = 1 << 9
+F_KEEP_SCORE = 1 << 10
 
 GRAD_TARGET_SCORE_CONST = 1 << 0
 GRAD_SCORE_DETACHED = 1 << 1

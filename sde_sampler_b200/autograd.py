@@ -85,9 +85,6 @@ def wants_grad(loss_obj) -> bool:
     wide = dim > _cabi.MAX_DIM or (target is not None and hasattr(target, "model"))
     if not any(p.requires_grad for p in params):
         return False
-    if wide and loss_obj.method in ("kl", "kl_ito"):
-        raise NotImplementedError("loss.method=kl / kl_ito training on the wide engine (d > 64 or a NICE target): backpropagation "
-                                  "through time is implemented on the fused engines only; use loss.method=lv or torch.no_grad()")
     gate = getattr(ctrl, "score_model", None)
     if wide and gate is not None and int(gate.out_layer.weight.shape[0]) != 1:
         # a silent grad-less value would surface as an unrelated autograd error in the caller's backward()

@@ -31,7 +31,7 @@ size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, in
 int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused_bytes, bool simt, cudaStream_t stream, cudaError_t* err,
                        bool bptt, int sm_count);
 size_t kl_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows, bool simt);
-int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err);
+int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err, bool bptt);
 
 // caller-side kernels (sdes_trainer.cu)
 cudaError_t launch_sample_prior(float* out, const float* uniforms, int64_t batch, int dim, float mean, float std, int truncated, float a,
@@ -595,7 +595,7 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
         if (wide_workspace_bytes(*desc) > desc->workspace_bytes) return fail(-6, "workspace_bytes too small for the keep-mode wide workspace");
         if (desc->batch == 0) return 0;
         cudaError_t we = cudaSuccess;
-        g_launches += launch_lv_grad_wide_desc(p, *g, simt, reinterpret_cast<cudaStream_t>(stream_), &we);
+        g_launches += launch_lv_grad_wide_desc(p, *g, simt, reinterpret_cast<cudaStream_t>(stream_), &we, false);
         if (we != cudaSuccess) return fail(-7, "wide lv gradient launch failed: %s", cudaGetErrorString(we));
         return 0;
     }
@@ -617,10 +617,17 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
 static int kl_grad_setup(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, KParams& p, bool& simt) {
     int rc = validate(desc, false);
     if (rc != 0) return rc;
-    if (wide_engine_needed(*desc))
-        return fail(-8, "the kl gradient (backpropagation through time) is implemented on the fused engines: d <= %d, analytic target", SDES_MAX_DIM);
     rc = grad_setup(desc, g, p, simt);
     if (rc != 0) return rc;
+    if (wide_engine_needed(*desc)) {
+        if (!(desc->flags & SDES_F_KEEP_SCORE)) return fail(-8, "wide-engine kl gradient needs the forward's SDES_F_KEEP_FOR_GRAD | SDES_F_KEEP_SCORE workspace");
+        if (desc->target_kind == SDES_TARGET_MULTIWELL || desc->target_kind == SDES_TARGET_FUNNEL)
+            return fail(-8, "kl gradient on the wide engine: NICE, GMM and Gaussian targets (a wide funnel / multi-well Hessian is not implemented)");
+        if (desc->target_kind == SDES_TARGET_GMM && desc->n_components > 1 && desc->ctrl_kind != SDES_CTRL_CLIPPED &&
+            desc->ctrl_kind != SDES_CTRL_LERP_PRIOR && !(g->flags & (SDES_GRAD_TARGET_SCORE_CONST | SDES_GRAD_SCORE_DETACHED)))
+            return fail(-8, "kl gradient with a %d-component GMM score inside the control needs SDES_GRAD_TARGET_SCORE_CONST", desc->n_components);
+        return 0;
+    }
     if (desc->target_kind == SDES_TARGET_GMM && desc->n_components > 1 && desc->ctrl_kind != SDES_CTRL_CLIPPED &&
         desc->ctrl_kind != SDES_CTRL_LERP_PRIOR && !(g->flags & (SDES_GRAD_TARGET_SCORE_CONST | SDES_GRAD_SCORE_DETACHED)))
         return fail(-8, "kl gradient with a %d-component GMM score inside the control needs SDES_GRAD_TARGET_SCORE_CONST "
@@ -632,6 +639,7 @@ size_t sdes_kl_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGra
     KParams p;
     bool simt;
     if (kl_grad_setup(desc, g, p, simt) != 0) return 0;
+    if (wide_engine_needed(*desc)) return wide_workspace_bytes(*desc);
     return kl_grad_workspace_bytes(p.d, p.ws.total * (int64_t)sizeof(float), g->chunk_rows, simt);
 }
 
@@ -642,6 +650,16 @@ int sdes_rollout_kl_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
     int rc = kl_grad_setup(desc, g, p, simt);
     if (rc != 0) return rc;
     if (!desc->ts || !desc->params || !desc->workspace) return fail(-5, "ts/params/workspace must be non-NULL");
+    if (wide_engine_needed(*desc)) {
+        if (!g->w || !g->grad_params || !g->grad_emb) return fail(-5, "w/grad_params/grad_emb must be non-NULL");
+        if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
+        if (wide_workspace_bytes(*desc) > desc->workspace_bytes) return fail(-6, "workspace_bytes too small for the keep-mode wide workspace");
+        if (desc->batch == 0) return 0;
+        cudaError_t we = cudaSuccess;
+        g_launches += launch_lv_grad_wide_desc(p, *g, simt, reinterpret_cast<cudaStream_t>(stream_), &we, true);
+        if (we != cudaSuccess) return fail(-7, "wide kl gradient launch failed: %s", cudaGetErrorString(we));
+        return 0;
+    }
     if (!g->xs || !g->w || !g->grad_params || !g->grad_emb) return fail(-5, "xs/w/grad_params/grad_emb must be non-NULL");
     if ((desc->flags & SDES_F_NOISE_FROM_HBM) && !desc->noise) return fail(-5, "SDES_F_NOISE_FROM_HBM set but noise is NULL");
     if (desc->target_kind == SDES_TARGET_GMM && (!desc->gmm_loc || !desc->gmm_scale)) return fail(-5, "gmm_loc/gmm_scale are NULL");

@@ -926,13 +926,156 @@ __global__ void __launch_bounds__(256) cotangent_wide_kernel(const CotWideArgs a
     }
 }
 
-// d loss / d gate(s) = 1[|gate| < clip] sum_b w_b q[s][b]   (q written by the wide forward in keep mode)
+// ---- kl / kl_ito on the wide engine: the reverse sweep's elementwise step (planar state, one warp per row).
+// With a_{s+1} = d loss / d x_{s+1}, w_b = d loss / d rnd_b, g = generative_ctrl(s, x_s) = clip(NN) + part(x_s):
+//   q = w (cq g_m + ci eps),  delta_s = q + a_{s+1} Bc  (cotangent of the control),  a_s = A a_{s+1} + (d part / d x)^T delta_s
+//   [+ q sigma / scale_prior^2 for the Euler-DDS reference control]  + J_x NN^T (delta_s 1[|NN| <= clip_model])  — the last term
+//   is added by the dgrad GEMM chain that follows this kernel (it reads the masked delta image written here).
+//   Euler-Maruyama (losses/oc.py:204-219, :316-331): A = 1 + mu dt, Bc = sigma dt, cq = dt, ci = sqrt(dt) [ito]
+//   exponential integrator (:429-443):                A = alpha_k,   Bc = beta_k^2 sigma^2, cq = Bc, ci = sigma beta_k [ito]
+// The target score inside `part` is the value the forward kept (SDES_F_KEEP_SCORE): a NICE / multi-component GMM score is an
+// autograd score without create_graph in the reference (distr/base.py:130-137) and enters as a constant; a single Gaussian is
+// differentiated (-1 / scale^2); the prior score of the Lerp controls always is.
+struct AdjWideArgs {
+    SdesRolloutDesc d;
+    const float *tab, *gate, *w, *nn, *sc, *vec_prior, *gmm_h;
+    const uint8_t* ximg;   // state image of this step
+    float* adj;            // (Bp, P) fp32 planar, in: a_{s+1}, out: A a_{s+1} + score-term part of a_s
+    uint8_t* dnn_img;      // masked delta of this step's rows: [m_tile][pc] blocks
+    float* qg;             // (Bp) sum_j delta_j part_j / gate, or NULL
+    int Hp, P, pc, step;
+    int64_t Bp;
+    uint32_t gflags;
+};
+
+__device__ __forceinline__ void img_load_pair(const uint8_t* img, int pc, int Hp, int64_t row, int plane, int k, float& v0, float& v1) {
+    const int mt = (int)(row >> 7), r = (int)(row & 127), kk = plane * Hp + k;
+    const uint8_t* o = img + (int64_t)mt * pc * A_BLOCK + img_group_offset(r, kk) + (kk & 7) * 2;
+    const uint32_t hi = *reinterpret_cast<const uint32_t*>(o), lo = *reinterpret_cast<const uint32_t*>(o + A_HALF);
+    v0 = __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+    v1 = __uint_as_float(hi & 0xFFFF0000u) + __uint_as_float(lo & 0xFFFF0000u);
+}
+
+__global__ void __launch_bounds__(256) adj_wide_step_kernel(const AdjWideArgs a) {
+    const SdesRolloutDesc& d = a.d;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= a.Bp) return;
+    const int64_t B = d.batch;
+    const bool valid = row < B;
+    const int64_t bb = valid ? row : 0;
+    const int dim = d.dim, Hp = a.Hp, P = a.P, s = a.step;
+    const float* tab = a.tab + (int64_t)s * TAB_STRIDE;
+    const StepCoef c = make_step_coef(d, tab);
+    const bool ito = (d.flags & SDES_F_COMPUTE_ITO) != 0;
+    const float wb = valid ? a.w[bb] : 0.f;
+    const float A = c.exp_int ? c.alpha_k : fmaf(c.mu, c.dt, 1.0f), Bc = c.exp_int ? c.bb_ss : c.sigma * c.dt;
+    const float cq = c.exp_int ? c.bb_ss : c.dt, ci = ito ? (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt) : 0.f;
+    const float gate = a.gate[s], lerp_w = tab[TAB_LERP_W], cs = d.clip_score;
+    const float outer = (d.ctrl_kind == SDES_CTRL_SCORE ? 1.0f : c.sigma) * d.scale_score;
+    const bool has_part = d.ctrl_kind != SDES_CTRL_CLIPPED;
+    const bool use_sc = has_part && d.ctrl_kind != SDES_CTRL_LERP_PRIOR;
+    const bool score_detached = (a.gflags & SDES_GRAD_SCORE_DETACHED) != 0;
+    const bool target_diff = !(a.gflags & SDES_GRAD_TARGET_SCORE_CONST) && d.target_kind == SDES_TARGET_GMM && d.n_components == 1;
+    const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
+    const float* noise = (c.from_hbm && ito) ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
+    const float* nr = a.nn + row * P;
+    const float* sr = use_sc ? a.sc + row * P : nullptr;
+    float* ar = a.adj + row * P;
+    float qg = 0.f;
+    for (int q = lane; q < Hp / 2; q += 32) {
+        float dm[4] = {0.f, 0.f, 0.f, 0.f}, an[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * q < dim) {
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ito) {
+                if (c.from_hbm) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) e[r] = (4 * q + r < dim) ? noise[4 * q + r] : 0.f;
+                } else {
+                    const float4 n4 = normal4_call(c.k0, c.k1, traj, (uint32_t)s, (uint32_t)q);
+                    e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+                }
+            }
+            float xe0, xe1, xo0, xo1;
+            img_load_pair(a.ximg, a.pc, Hp, row, 0, 2 * q, xe0, xe1);
+            img_load_pair(a.ximg, a.pc, Hp, row, 1, 2 * q, xo0, xo1);
+            const float2 ne = *reinterpret_cast<const float2*>(nr + 2 * q), no = *reinterpret_cast<const float2*>(nr + Hp + 2 * q);
+            float2 se = make_float2(0.f, 0.f), so = se, he = se, ho = se;
+            if (use_sc) { se = *reinterpret_cast<const float2*>(sr + 2 * q); so = *reinterpret_cast<const float2*>(sr + Hp + 2 * q); }
+            if (target_diff) { he = *reinterpret_cast<const float2*>(a.gmm_h + 2 * q); ho = *reinterpret_cast<const float2*>(a.gmm_h + Hp + 2 * q); }
+            const float2 ae = *reinterpret_cast<const float2*>(ar + 2 * q), ao = *reinterpret_cast<const float2*>(ar + Hp + 2 * q);
+            const float2 ple = *reinterpret_cast<const float2*>(a.vec_prior + 2 * q), plo = *reinterpret_cast<const float2*>(a.vec_prior + Hp + 2 * q);
+            const float2 pie = *reinterpret_cast<const float2*>(a.vec_prior + P + 2 * q), pio = *reinterpret_cast<const float2*>(a.vec_prior + P + Hp + 2 * q);
+            const float x4[4] = {xe0, xo0, xe1, xo1}, nn4[4] = {ne.x, no.x, ne.y, no.y}, sc4[4] = {se.x, so.x, se.y, so.y};
+            const float a4[4] = {ae.x, ao.x, ae.y, ao.y}, pl4[4] = {ple.x, plo.x, ple.y, plo.y}, pi4[4] = {pie.x, pio.x, pie.y, pio.y};
+            const float h4[4] = {he.x, ho.x, he.y, ho.y};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (4 * q + r >= dim) continue;
+                const float pscore = (pl4[r] - x4[r]) * pi4[r];
+                const float tsd = target_diff ? -2.0f * h4[r] : 0.f;  // d target score / d x (diagonal)
+                float inner = 0.f, dinner = 0.f;
+                if (d.ctrl_kind == SDES_CTRL_SCORE) { inner = sc4[r]; dinner = tsd; }
+                else if (d.ctrl_kind == SDES_CTRL_LERP) { inner = torch_lerp(pscore, sc4[r], lerp_w); dinner = (1.0f - lerp_w) * (-pi4[r]) + lerp_w * tsd; }
+                else if (d.ctrl_kind == SDES_CTRL_LERP_PRIOR) { inner = (1.0f - lerp_w) * pscore; dinner = (1.0f - lerp_w) * (-pi4[r]); }
+                else if (d.ctrl_kind == SDES_CTRL_LERP_TARGET) { inner = lerp_w * sc4[r]; dinner = lerp_w * tsd; }
+                const float ungated = has_part ? outer * clipf(inner, cs) : 0.f;
+                const float part = ungated * gate;
+                const float dpart = (has_part && !score_detached && fabsf(inner) <= cs) ? outer * gate * dinner : 0.f;
+                const float g = clipf(nn4[r], c.cm) + part;
+                const float gm = c.ref_ctrl ? g - c.sigma * pscore : g;
+                const float qv = wb * (cq * gm + ci * e[r]);
+                const float delta = qv + a4[r] * Bc;
+                an[r] = a4[r] * A + dpart * delta + (c.ref_ctrl ? qv * c.sigma * pi4[r] : 0.f);
+                dm[r] = fabsf(nn4[r]) <= c.cm ? delta : 0.f;
+                qg = fmaf(delta, ungated, qg);
+            }
+        }
+        *reinterpret_cast<float2*>(ar + 2 * q) = make_float2(an[0], an[2]);
+        *reinterpret_cast<float2*>(ar + Hp + 2 * q) = make_float2(an[1], an[3]);
+        img_store_pair_g(a.dnn_img, a.pc, Hp, row, 0, 2 * q, dm[0], dm[2]);
+        img_store_pair_g(a.dnn_img, a.pc, Hp, row, 1, 2 * q, dm[1], dm[3]);
+    }
+    if (a.qg != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qg += __shfl_xor_sync(0xffffffffu, qg, o);
+        if (lane == 0) a.qg[row] = valid ? qg : 0.f;
+    }
+}
+
+// terminal adjoint a_T = w (grad log p_ref(x_T) - 1[|log rho(x_T)| <= clip_target] grad log rho(x_T))   (losses/oc.py:225, :337, :449-450)
+struct AdjWideInitArgs {
+    SdesRolloutDesc d;
+    const float *w, *xst, *logp, *sc_T, *vec_ref;
+    float* adj;
+    int P;
+    int64_t Bp;
+};
+
+__global__ void __launch_bounds__(256) adj_wide_init_kernel(const AdjWideInitArgs a) {
+    const SdesRolloutDesc& d = a.d;
+    const int64_t n = a.Bp * a.P;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / a.P;
+        const int p = (int)(e - row * a.P);
+        float v = 0.f;
+        if (row < d.batch) {
+            const float lp = a.logp[row];
+            float t = fabsf(lp) <= d.clip_target ? -a.sc_T[e] : 0.f;   // padded planar dims hold score 0
+            if (d.loss_kind != SDES_LOSS_TIME_REVERSAL) t += (a.vec_ref[p] - a.xst[e]) * a.vec_ref[a.P + p];
+            v = a.w[row] * t;
+        }
+        a.adj[e] = v;
+    }
+}
+
+// d loss / d gate(s) = 1[|gate| < clip] sum_b w_b q[s][b]   (q written by the wide forward in keep mode; w = NULL: plain sum)
 __global__ void __launch_bounds__(256) qgate_reduce_kernel(const float* __restrict__ q, const float* __restrict__ w, const float* __restrict__ gate,
                                                            int64_t B, int64_t Bp, float clip_model, float* __restrict__ out) {
     __shared__ float s_red[8];
     const int s = blockIdx.x;
     float acc = 0.f;
-    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) acc = fmaf(w[b], q[(int64_t)s * Bp + b], acc);
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) acc = fmaf(w != nullptr ? w[b] : 1.0f, q[(int64_t)s * Bp + b], acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -1119,12 +1262,13 @@ void launch_prepare(const KParams& p, cudaStream_t stream);
 
 // ---- wide engine gradient: scratch layout after the forward plan (WideGradView::grad_base)
 struct WideGradScratch {
-    Lin b_h[SDES_MAX_HIDDEN], b_out;
+    Lin b_h[SDES_MAX_HIDDEN], b_out, b_in;
     int chunk_steps;
     int64_t a_img[SDES_MAX_HIDDEN + 1], gp_img[SDES_MAX_HIDDEN + 1], nn, dnn_img, dh_img[2], total;
+    int64_t dh_all[SDES_MAX_HIDDEN + 1], adj;  // kl sweep: one cotangent image per layer kept until the chunk's wgrad, fp32 adjoint
 };
 
-static void wide_scratch(const WideGradView& v, WideGradScratch& sc) {
+static void wide_scratch(const WideGradView& v, WideGradScratch& sc, bool bptt) {
     int64_t rows = ((int64_t)1 << 27) / v.P;          // keep nn (rows x P fp32) at <= 512 MB
     sc.chunk_steps = (int)(rows / v.Bp);
     if (sc.chunk_steps < 1) sc.chunk_steps = 1;
@@ -1149,21 +1293,29 @@ static void wide_scratch(const WideGradView& v, WideGradScratch& sc) {
     sc.dnn_img = take(imgp);
     sc.dh_img[0] = take(img1);
     sc.dh_img[1] = take(img1);
+    if (bptt) {
+        set_tiling(sc.b_in, v.P, C);   // W_in^T: the adjoint's share of the input layer (N = planar state width, K = 64)
+        sc.b_in.w_off = take(lin_image_bytes(sc.b_in));
+        sc.b_in.b_off = -1;
+        for (int l = 0; l <= v.nh; ++l) sc.dh_all[l] = take(img1);
+        sc.adj = take(v.Bp * (int64_t)v.P * 4);
+    }
     sc.total = o;
 }
 
-int64_t lv_grad_wide_scratch_bytes(const WideGradView& v) {
+int64_t lv_grad_wide_scratch_bytes(const WideGradView& v, bool bptt) {
     WideGradScratch sc;
-    wide_scratch(v, sc);
+    wide_scratch(v, sc, bptt);
     return sc.total - v.grad_base;
 }
 
 // Gradient for a wide-engine rollout that ran with SDES_F_KEEP_FOR_GRAD in the SAME workspace: the per-step state images
 // are already tensor-core operands, the forward's weight images are still there; only W^T images are added.
-int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const WideGradView& v, bool simt, cudaStream_t stream, cudaError_t* err) {
+int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const WideGradView& v, bool simt, cudaStream_t stream, cudaError_t* err,
+                            bool bptt) {
     const SdesRolloutDesc& d = kp.d;
     WideGradScratch sc;
-    wide_scratch(v, sc);
+    wide_scratch(v, sc, bptt);
     uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
     auto F = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
     int64_t launches = 0;
@@ -1185,6 +1337,15 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
     };
     for (int l = 0; l < v.nh; ++l) GRADW_CHECK(image_t(sc.b_h[l], blob + kp.bl.h_w[l], C, C, C, 0));
     GRADW_CHECK(image_t(sc.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));   // out[n][k = planar dim] = W_out[natural(k)][n]
+    if (bptt) {  // W_in^T: out[n = planar dim][k] = W_in[k][natural(n)]
+        ImgArgs ia;
+        ia.src = blob + kp.bl.in_w; ia.src_ld = d.dim; ia.N = d.dim; ia.K = C; ia.transpose = 1; ia.n_planar = 1; ia.k_planar = 0; ia.Hp = v.Hp;
+        ia.out = ws + sc.b_in.w_off; ia.n_pad = sc.b_in.n_pad; ia.tile_n = sc.b_in.tile_n; ia.k_chunks = sc.b_in.k_chunks;
+        const int64_t groups = (int64_t)sc.b_in.n_pad * sc.b_in.k_chunks * 8;
+        weight_image_kernel<<<(int)((groups + 255) / 256), 256, 0, stream>>>(ia);
+        ++launches;
+        GRADW_CHECK(cudaGetLastError());
+    }
     GRADW_CHECK(cudaMemsetAsync(g.grad_params, 0, (size_t)d.n_params * 4, stream));
     GRADW_CHECK(cudaMemsetAsync(g.grad_emb, 0, (size_t)v.T * C * 4, stream));
     auto base_args = [&](const Lin& l) {
@@ -1222,7 +1383,18 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
     };
     float* gp = g.grad_params;
     const int x_stride_blocks = v.pc;
-    for (int s0 = 0; s0 < v.T; s0 += sc.chunk_steps) {
+    const bool want_gate = g.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
+    if (bptt) {  // terminal adjoint
+        AdjWideInitArgs ia;
+        ia.d = d; ia.w = g.w; ia.xst = F(v.xst); ia.logp = F(v.logp); ia.sc_T = F(v.sc_keep) + (int64_t)v.T * v.Bp * v.P;
+        ia.vec_ref = F(v.vec_ref); ia.adj = F(sc.adj); ia.P = v.P; ia.Bp = v.Bp;
+        adj_wide_init_kernel<<<148 * 4, 256, 0, stream>>>(ia);
+        ++launches;
+        GRADW_CHECK(cudaGetLastError());
+    }
+    const int n_chunks = (v.T + sc.chunk_steps - 1) / sc.chunk_steps;
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int s0 = (bptt ? n_chunks - 1 - ci : ci) * sc.chunk_steps;   // the sweep walks the chunks backwards in time
         const int ns = (s0 + sc.chunk_steps <= v.T) ? sc.chunk_steps : v.T - s0;
         const int m_tiles = ns * v.m_tiles;
         const uint8_t* ximg = ws + v.ximg + (int64_t)s0 * v.ximg_slot;   // the chunk's state images are contiguous
@@ -1241,16 +1413,57 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
             a.a_img = ws + sc.a_img[v.nh]; a.out_f32 = F(sc.nn);
             GRADW_CHECK(launch_linear(a, m_tiles, simt, stream, launches));
         }
-        {
+        if (!bptt) {
             CotWideArgs ca;
             ca.d = d; ca.tab = F(v.tab); ca.w = g.w; ca.nn = F(sc.nn); ca.dnn_img = ws + sc.dnn_img; ca.Hp = v.Hp; ca.P = v.P; ca.pc = v.pc;
             ca.s0 = s0; ca.Bp = v.Bp;
             cotangent_wide_kernel<<<m_tiles * 16, 256, 0, stream>>>(ca);
             ++launches;
             GRADW_CHECK(cudaGetLastError());
+        } else {
+            // reverse sweep over the chunk's steps: cotangent of the control from the adjoint, then the dgrad chain of THIS step's
+            // row tiles (layer cotangent images kept per layer for the chunk's weight gradients), W_in^T accumulating into the adjoint
+            for (int s = s0 + ns - 1; s >= s0; --s) {
+                const int64_t t_off = (int64_t)(s - s0) * v.m_tiles;   // first row tile of this step inside the chunk buffers
+                AdjWideArgs aa;
+                aa.d = d; aa.tab = F(v.tab); aa.gate = F(v.gate); aa.w = g.w; aa.nn = F(sc.nn) + t_off * 128 * v.P;
+                aa.sc = F(v.sc_keep) + (int64_t)s * v.Bp * v.P; aa.vec_prior = F(v.vec_prior); aa.gmm_h = F(v.gmm_h);
+                aa.ximg = ws + v.ximg + (int64_t)s * v.ximg_slot; aa.adj = F(sc.adj);
+                aa.dnn_img = ws + sc.dnn_img + t_off * v.pc * A_BLOCK;
+                aa.qg = want_gate ? F(v.qgate) + (int64_t)s * v.Bp : nullptr;
+                aa.Hp = v.Hp; aa.P = v.P; aa.pc = v.pc; aa.step = s; aa.Bp = v.Bp; aa.gflags = g.flags;
+                adj_wide_step_kernel<<<(int)((v.Bp + 7) / 8), 256, 0, stream>>>(aa);
+                ++launches;
+                GRADW_CHECK(cudaGetLastError());
+                LinArgs a = base_args(sc.b_out);
+                a.a_img = aa.dnn_img; a.a_mt_stride = (int64_t)v.pc * A_BLOCK;
+                a.mul_img = ws + sc.gp_img[v.nh] + t_off * A_BLOCK; a.mul_mt_stride = A_BLOCK;
+                a.out_img = ws + sc.dh_all[v.nh] + t_off * A_BLOCK;
+                GRADW_CHECK(launch_linear(a, v.m_tiles, simt, stream, launches));
+                for (int l = v.nh - 1; l >= 0; --l) {
+                    a = base_args(sc.b_h[l]);
+                    a.a_img = ws + sc.dh_all[l + 1] + t_off * A_BLOCK;
+                    a.mul_img = ws + sc.gp_img[l] + t_off * A_BLOCK; a.mul_mt_stride = A_BLOCK;
+                    a.out_img = ws + sc.dh_all[l] + t_off * A_BLOCK;
+                    GRADW_CHECK(launch_linear(a, v.m_tiles, simt, stream, launches));
+                }
+                a = base_args(sc.b_in);
+                a.a_img = ws + sc.dh_all[0] + t_off * A_BLOCK;
+                a.resid = F(sc.adj); a.out_f32 = F(sc.adj);
+                GRADW_CHECK(launch_linear(a, v.m_tiles, simt, stream, launches));
+            }
         }
         GRADW_CHECK(wgrad(ws + sc.dnn_img, v.pc, ws + sc.a_img[v.nh], 1, m_tiles, gp + kp.bl.out_w, C, d.dim, C, 1, 0));
         GRADW_CHECK(colsum(ws + sc.dnn_img, v.pc, d.dim, gp + kp.bl.out_b, m_tiles, 0, 0, 1));
+        if (bptt) {
+            for (int l = v.nh - 1; l >= 0; --l) {
+                GRADW_CHECK(wgrad(ws + sc.dh_all[l + 1], 1, ws + sc.a_img[l], 1, m_tiles, gp + kp.bl.h_w[l], C, C, C, 0, 0));
+                GRADW_CHECK(colsum(ws + sc.dh_all[l + 1], 1, C, gp + kp.bl.h_b[l], m_tiles, 0, 0, 0));
+            }
+            GRADW_CHECK(wgrad(ws + sc.dh_all[0], 1, ximg, v.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim, 0, 1));
+            GRADW_CHECK(colsum(ws + sc.dh_all[0], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, v.m_tiles, C, 0));
+            continue;
+        }
         int cur = 0;
         {
             LinArgs a = base_args(sc.b_out);
@@ -1271,7 +1484,8 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
     }
     if (g.grad_gate != nullptr) {
         if ((d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED) {
-            qgate_reduce_kernel<<<v.T, 256, 0, stream>>>(F(v.qgate), g.w, F(v.gate), v.B, v.Bp, d.clip_model, g.grad_gate);
+            // lv: the forward left sum_j c_j part_j / gate per (step, row), weighted by w here; kl: the sweep left sum_j delta_j part_j / gate
+            qgate_reduce_kernel<<<v.T, 256, 0, stream>>>(F(v.qgate), bptt ? nullptr : g.w, F(v.gate), v.B, v.Bp, d.clip_model, g.grad_gate);
             ++launches;
             GRADW_CHECK(cudaGetLastError());
         } else {
@@ -1285,10 +1499,10 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
 
 void wide_grad_view(const SdesRolloutDesc& d, wide::WideGradView& v);  // sdes_wide.cu
 
-int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err) {
+int64_t launch_lv_grad_wide_desc(const KParams& kp, const SdesLvGradDesc& g, bool simt, cudaStream_t stream, cudaError_t* err, bool bptt) {
     WideGradView v;
     wide_grad_view(kp.d, v);
-    return launch_lv_grad_wide(kp, g, v, simt, stream, err);
+    return launch_lv_grad_wide(kp, g, v, simt, stream, err, bptt);
 }
 
 size_t lv_grad_workspace_bytes(const SdesRolloutDesc& d, int64_t fused_bytes, int64_t chunk_rows) {

@@ -59,6 +59,8 @@ struct WideGradView {
     int d, Hp, P, pc, T, nh, m_tiles;
     int64_t B, Bp;
     int64_t tab, emb, gate, ximg, ximg_slot, qgate, grad_base;
+    int64_t vec_prior, vec_ref, gmm_h, xst, logp, sc_keep;  // kl gradient: planar parameter vectors, final state / log-density, kept scores
+    bool keep_score;
     Lin mlp_in, mlp_h[SDES_MAX_HIDDEN], mlp_out;
 };
 

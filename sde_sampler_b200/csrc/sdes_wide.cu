@@ -56,9 +56,10 @@ struct Plan {
     int64_t act_stride_layer, act_stride_coup;
     // keep mode (SDES_F_KEEP_FOR_GRAD): one state image per time step, a separate image for the NICE running state,
     // per-(step, trajectory) gate cotangent sums, and the scratch of the gradient pass (sdes_grad.cu)
-    bool keep;
+    bool keep, keep_score;
     int64_t ximg_slot;     // bytes between the state images of consecutive steps (0 = one shared slot)
     int64_t himg, qgate, grad_base;
+    int64_t sc_keep;       // keep_score (kl gradient): target score of step i at sc_keep + i * plane bytes, terminal state at slot T
     int64_t total;
 };
 
@@ -126,6 +127,8 @@ static bool make_plan(const SdesRolloutDesc& d, Plan& p) {
     p.ximg = take(p.keep ? img_p * (p.T + 1) : img_p);
     p.himg = (p.keep && p.nice) ? take(img_p) : p.ximg;  // without keep the couplings work in place on the state image
     p.qgate = take(p.keep ? (int64_t)p.T * p.Bp * 4 : 0);
+    p.keep_score = p.keep && (d.flags & SDES_F_KEEP_SCORE) != 0;
+    p.sc_keep = take(p.keep_score ? plane * (p.T + 1) : 0);
     p.gimg = take(p.nice ? img_p : 0);
     p.m_img[0] = take((int64_t)p.m_tiles * A_BLOCK);
     p.m_img[1] = take((int64_t)p.m_tiles * A_BLOCK);
@@ -546,11 +549,13 @@ void wide_grad_view(const SdesRolloutDesc& d, wide::WideGradView& v) {
     make_plan(d, p);
     v.d = p.d; v.Hp = p.Hp; v.P = p.P; v.pc = p.pc; v.T = p.T; v.nh = p.nh; v.m_tiles = p.m_tiles; v.B = p.B; v.Bp = p.Bp;
     v.tab = p.tab; v.emb = p.emb; v.gate = p.gate; v.ximg = p.ximg; v.ximg_slot = p.ximg_slot; v.qgate = p.qgate; v.grad_base = p.grad_base;
+    v.vec_prior = p.vec_prior; v.vec_ref = p.vec_ref; v.gmm_h = p.gmm_h; v.xst = p.xst; v.logp = p.logp; v.sc_keep = p.sc_keep;
+    v.keep_score = p.keep_score;
     v.mlp_in = p.mlp_in; v.mlp_out = p.mlp_out;
     for (int l = 0; l < SDES_MAX_HIDDEN; ++l) v.mlp_h[l] = p.mlp_h[l];
 }
 
-int64_t lv_grad_wide_scratch_bytes(const wide::WideGradView& v);  // sdes_grad.cu
+int64_t lv_grad_wide_scratch_bytes(const wide::WideGradView& v, bool bptt);  // sdes_grad.cu
 
 size_t wide_workspace_bytes(const SdesRolloutDesc& d) {
     Plan p;
@@ -558,7 +563,7 @@ size_t wide_workspace_bytes(const SdesRolloutDesc& d) {
     if (p.keep) {
         wide::WideGradView v;
         wide_grad_view(d, v);
-        return (size_t)(p.grad_base + lv_grad_wide_scratch_bytes(v));
+        return (size_t)(p.grad_base + lv_grad_wide_scratch_bytes(v, p.keep_score));
     }
     return (size_t)p.total;
 }
@@ -670,7 +675,31 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
         }
         return cudaSuccess;
     };
+    // NICE input-gradient backward (the autograd score of distr/base.py:130-137): g = d log rho / d x, seeded by latent_kernel
+    auto nice_backward = [&]() -> cudaError_t {
+        for (int c = p.n_coup - 1; c >= 0; --c) {
+            const int on = ((p.mc + c) % 2) ? 0 : 1, off = 1 - on;
+            int cur = 0;
+            for (int l = p.n_lin - 1; l >= 0; --l) {
+                LinArgs a = base_args(p.nb[c][l]);
+                if (l == p.n_lin - 1) { a.a_img = ws + p.gimg + (int64_t)on * (p.Hp / 64) * A_BLOCK; a.a_mt_stride = x_stride; }
+                else { a.a_img = ws + p.d_img[cur]; a.a_mt_stride = act_stride; cur = 1 - cur; }
+                if (l > 0) {
+                    a.mask_img = ws + p.act_img + c * p.act_stride_coup + (l - 1) * p.act_stride_layer;
+                    a.mask_mt_stride = act_stride;
+                    a.out_img = ws + p.d_img[cur]; a.out_mt_stride = act_stride;
+                } else {
+                    a.resid = F(p.g) + off * p.Hp; a.out_f32 = F(p.g) + off * p.Hp;
+                    a.out_img = ws + p.gimg + (int64_t)off * (p.Hp / 64) * A_BLOCK; a.out_mt_stride = x_stride;
+                }
+                cudaError_t e = launch_linear(a, p.m_tiles, simt, stream, launches);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        return cudaSuccess;
+    };
     const bool need_score = d.ctrl_kind != SDES_CTRL_CLIPPED && d.ctrl_kind != SDES_CTRL_LERP_PRIOR;
+    const int64_t plane_bytes = p.Bp * (int64_t)p.P * 4;
 
     for (int i = 0; i < p.T; ++i) {
         const uint8_t* x_img = ws + p.ximg + (int64_t)i * p.ximg_slot;   // image of the state at step i
@@ -701,24 +730,7 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
                 latent_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
                 ++launches;
                 WIDE_CHECK(cudaGetLastError());
-                for (int c = p.n_coup - 1; c >= 0; --c) {
-                    const int on = ((p.mc + c) % 2) ? 0 : 1, off = 1 - on;
-                    int cur = 0;
-                    for (int l = p.n_lin - 1; l >= 0; --l) {
-                        LinArgs a = base_args(p.nb[c][l]);
-                        if (l == p.n_lin - 1) { a.a_img = ws + p.gimg + (int64_t)on * (p.Hp / 64) * A_BLOCK; a.a_mt_stride = x_stride; }
-                        else { a.a_img = ws + p.d_img[cur]; a.a_mt_stride = act_stride; cur = 1 - cur; }
-                        if (l > 0) {
-                            a.mask_img = ws + p.act_img + c * p.act_stride_coup + (l - 1) * p.act_stride_layer;
-                            a.mask_mt_stride = act_stride;
-                            a.out_img = ws + p.d_img[cur]; a.out_mt_stride = act_stride;
-                        } else {
-                            a.resid = F(p.g) + off * p.Hp; a.out_f32 = F(p.g) + off * p.Hp;
-                            a.out_img = ws + p.gimg + (int64_t)off * (p.Hp / 64) * A_BLOCK; a.out_mt_stride = x_stride;
-                        }
-                        WIDE_CHECK(launch_linear(a, p.m_tiles, simt, stream, launches));
-                    }
-                }
+                WIDE_CHECK(nice_backward());
             } else {
                 if (d.target_kind == SDES_TARGET_GMM) gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
                 else analytic_target_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 1);
@@ -726,6 +738,8 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
                 WIDE_CHECK(cudaGetLastError());
             }
         }
+        if (p.keep_score && need_score)  // kl gradient: the score enters the adjoint as a stored constant / through its mask
+            WIDE_CHECK(cudaMemcpyAsync(ws + p.sc_keep + (int64_t)i * plane_bytes, F(p.g), (size_t)plane_bytes, cudaMemcpyDeviceToDevice, stream));
         update_kernel<<<row_blocks, 32 * ROWS_PER_CTA, 0, stream>>>(ra, i);
         ++launches;
         WIDE_CHECK(cudaGetLastError());
@@ -734,14 +748,18 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
     if (p.nice) {
         if (p.n_coup == 1) WIDE_CHECK(cudaMemcpyAsync(F(p.h), F(p.xst), p.Bp * (int64_t)p.P * 4, cudaMemcpyDeviceToDevice, stream));
         WIDE_CHECK(nice_forward(ws + p.ximg + (int64_t)p.T * p.ximg_slot));
-        latent_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
+        latent_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, p.keep_score ? 1 : 0);
     } else if (d.target_kind == SDES_TARGET_GMM) {
-        gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
+        gmm_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, p.keep_score ? 1 : 0);
     } else {
-        analytic_target_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, 0);
+        analytic_target_kernel<<<row_blocks_pad, 32 * ROWS_PER_CTA, 0, stream>>>(ra, p.keep_score ? 1 : 0);
     }
     ++launches;
     WIDE_CHECK(cudaGetLastError());
+    if (p.keep_score) {  // the terminal cost -log rho(x_T) IS differentiated by the reference: keep grad log rho(x_T)
+        if (p.nice) WIDE_CHECK(nice_backward());
+        WIDE_CHECK(cudaMemcpyAsync(ws + p.sc_keep + (int64_t)p.T * plane_bytes, F(p.g), (size_t)plane_bytes, cudaMemcpyDeviceToDevice, stream));
+    }
     terminal_kernel<<<row_blocks, 32 * ROWS_PER_CTA, 0, stream>>>(ra);
     ++launches;
     WIDE_CHECK(cudaGetLastError());

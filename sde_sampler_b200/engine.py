@@ -208,7 +208,7 @@ def tiled_traj_numel(T: int, B: int, dim: int) -> int:
 def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
             params: torch.Tensor | None = None, traj_tiled: bool = False, traj_buffer: Workspace | None = None,
-            keep_for_grad: bool = False):
+            keep_for_grad: bool = False, keep_score: bool = False):
     """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None); with `traj_tiled`
     the trajectory comes back as a flat buffer in the row-tiled layout that `lv_grad` consumes."""
     lib = _cabi.lib()
@@ -232,6 +232,8 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
     if keep_for_grad and is_wide(spec):
         # wide engine: what the gradient needs stays inside the workspace (state image per step, gate cotangent sums)
         d.flags |= _cabi.F_KEEP_FOR_GRAD
+        if keep_score:  # kl / kl_ito: the reverse sweep also needs the target score of every step (sdes_rollout_kl_grad)
+            d.flags |= _cabi.F_KEEP_SCORE
         d.flags &= ~_cabi.F_RETURN_TRAJ
     x_T = torch.empty_like(x0c)
     rnd = torch.empty((B, 1), dtype=torch.float32, device=device)
@@ -271,7 +273,7 @@ def kl_grad_flags(spec: RolloutSpec) -> int:
     create_graph=detach_score=False from models/reparam.py:60,:135) — a constant of the graph; Gauss / DoubleWell /
     MultiWell / Funnel scores are analytic functions of x; `detach_score=True` detaches the whole score term."""
     flags = 0
-    if spec.target["kind"] == "gmm":
+    if spec.target["kind"] in ("gmm", "nice"):  # Distribution.score (autograd, no create_graph) — Nice inherits it too
         flags |= _cabi.GRAD_TARGET_SCORE_CONST
     if spec.extras.get("detach_score"):
         flags |= _cabi.GRAD_SCORE_DETACHED
@@ -292,8 +294,6 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
     `sdes_rollout_lv_grad`.  `bptt=True`: the kl / kl_ito gradient (`sdes_rollout_kl_grad`)."""
     lib = _cabi.lib()
     wide = is_wide(spec)
-    if bptt and wide:
-        raise NotImplementedError("the kl gradient (backpropagation through time) covers d <= 64 with analytic targets")
     fn_bytes, fn_grad, what = ((lib.sdes_kl_grad_workspace_bytes, lib.sdes_rollout_kl_grad, "sdes_rollout_kl_grad") if bptt else
                                (lib.sdes_lv_grad_workspace_bytes, lib.sdes_rollout_lv_grad, "sdes_rollout_lv_grad"))
     if not w.is_cuda:
@@ -320,7 +320,7 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
     if tiled:
         d.flags |= _cabi.F_TRAJ_TILED
     if wide:
-        d.flags |= _cabi.F_KEEP_FOR_GRAD
+        d.flags |= _cabi.F_KEEP_FOR_GRAD | (_cabi.F_KEEP_SCORE if bptt else 0)
     if params is None:
         params = pack_params(spec)
     d.ts, d.params, d.n_params = ts.data_ptr(), params.data_ptr(), params.numel()

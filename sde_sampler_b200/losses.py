@@ -236,7 +236,7 @@ class FusedOCLoss:
             seed, off = self._next_seed(), self._rank_offset(x.shape[0])
             x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
                                           workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer,
-                                          keep_for_grad=True)
+                                          keep_for_grad=True, keep_score=self.method in ("kl", "kl_ito"))
             self._traj_version += 1
             if self.method == "lv_traj":
                 loss, metrics = self._compute_loss_lv_traj(rnd, x_T)

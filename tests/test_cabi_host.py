@@ -209,10 +209,16 @@ def test_kl_grad_and_trainer_entry_points_validate(lib):
     need_kl = lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g))
     need_lv = lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g))
     assert need_kl >= need_lv + 4 * d.n_steps * d.batch * d.dim   # the control cotangent of every (trajectory, step)
-    d.dim = 100  # wide engine: no backpropagation through time there
+    d.dim = 100  # wide engine: the sweep needs what a keep-mode forward left in the workspace
     d.n_params += 2 * 64 * 50 + 50
     assert lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g)) == 0
-    assert b"fused engines" in lib.sdes_last_error()
+    assert b"SDES_F_KEEP_FOR_GRAD" in lib.sdes_last_error()
+    d.flags |= _cabi.F_KEEP_FOR_GRAD
+    assert lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g)) == 0
+    assert b"SDES_F_KEEP_SCORE" in lib.sdes_last_error()
+    need_lv_wide = lib.sdes_lv_grad_workspace_bytes(C.byref(d), C.byref(g))
+    d.flags |= _cabi.F_KEEP_SCORE  # + the kept scores of every step, the fp32 adjoint and one cotangent image per layer
+    assert lib.sdes_kl_grad_workspace_bytes(C.byref(d), C.byref(g)) > need_lv_wide > 0
     t = _cabi.TrainerStepDesc()
     assert lib.sdes_trainer_step(C.byref(t), None) == -2
     t.struct_bytes = C.sizeof(_cabi.TrainerStepDesc)
