@@ -128,6 +128,11 @@ typedef struct SdesRolloutDesc {
     int32_t nice_couplings, nice_mid, nice_hidden, nice_mask_config;
     const float* nice_params;
     int64_t n_nice_params;
+    /* Optional output of the tensor-core fused engine (d <= SDES_MAX_DIM, no SDES_F_MLP_SIMT), NULL = not wanted:
+     * gate_cot (T, B) = ito coefficient x sum_j eps_j x [scale_score (sigma) clip(inner_j)], the ungated score part of the
+     * control paired with the step's noise — what d rnd_b / d gate(s) is for the log-variance losses.  A training forward
+     * that keeps it spares sdes_rollout_lv_grad the re-evaluation of the target score (SdesLvGradDesc.gate_cot). */
+    float* gate_cot;
 } SdesRolloutDesc;
 
 /* ABI version of the loaded library (== SDES_ABI_VERSION of the header it was built from). */
@@ -184,6 +189,8 @@ typedef struct SdesLvGradDesc {
     float* grad_emb;
     float* grad_gate;        /* NULL when the control has no gate */
     int64_t chunk_rows;      /* rows (trajectory, step) per pass; 0 = default (2^20) */
+    const float* gate_cot;   /* lv, scalar gate, fused engines: (T, B) from the forward's SdesRolloutDesc.gate_cot, or NULL
+                                (the gate gradient is then recomputed from the target score) */
 } SdesLvGradDesc;
 
 size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);

@@ -158,6 +158,8 @@ static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
     if ((d->flags & SDES_F_RETURN_TRAJ) && !d->xs) return fail(-5, "SDES_F_RETURN_TRAJ set but xs is NULL");
     if (!d->workspace) return fail(-5, "workspace is NULL");
     if (reinterpret_cast<uintptr_t>(d->workspace) % 256 != 0) return fail(-5, "workspace must be 256-byte aligned");
+    if (d->gate_cot != nullptr && ((d->flags & SDES_F_MLP_SIMT) || wide_engine_needed(*d)))
+        return fail(-3, "gate_cot is an output of the tensor-core fused engine only (d <= %d, no SDES_F_MLP_SIMT)", SDES_MAX_DIM);
     return 0;
 }
 

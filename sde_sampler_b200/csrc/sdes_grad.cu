@@ -141,6 +141,7 @@ struct CotArgs {
     float* grad_gate;         // (T, gate_dim) or NULL
     int P, pc, s0;
     int64_t Bp;
+    int skip_gate;            // lv with the forward's gate_cot: the gate gradient is reduced from it, no target score here
 };
 
 template <int DPAD>
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(128) cotangent_kernel(const __grid_constant__ 
     const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
     const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
     const float* nnrow = a.nn + rr * a.P;  // (staging this tile through shared memory was measured slower here: 637 vs 457 us)
-    const bool want_gate = a.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
+    const bool want_gate = !a.skip_gate && a.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
     float sc[DPAD];
     if (want_gate) {
         score_part<DPAD>(d, x, sc, tsm, a.ones, tab[TAB_SIGMA], tab[TAB_LERP_W]);  // gate = 1: outer * clip(inner)
@@ -1071,7 +1072,7 @@ __global__ void __launch_bounds__(256) adj_wide_init_kernel(const AdjWideInitArg
 
 // d loss / d gate(s) = 1[|gate| < clip] sum_b w_b q[s][b]   (q written by the wide forward in keep mode; w = NULL: plain sum)
 __global__ void __launch_bounds__(256) qgate_reduce_kernel(const float* __restrict__ q, const float* __restrict__ w, const float* __restrict__ gate,
-                                                           int64_t B, int64_t Bp, float clip_model, float* __restrict__ out) {
+                                                           int64_t B, int64_t Bp, float clip_model, float* __restrict__ out, int gate_stride = 1) {
     __shared__ float s_red[8];
     const int s = blockIdx.x;
     float acc = 0.f;
@@ -1083,7 +1084,7 @@ __global__ void __launch_bounds__(256) qgate_reduce_kernel(const float* __restri
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int i = 0; i < 8; ++i) t += s_red[i];
-        out[s] = fabsf(gate[s]) < clip_model ? t : 0.f;
+        out[s] = fabsf(gate[(int64_t)s * gate_stride]) < clip_model ? t : 0.f;
     }
 }
 
@@ -1635,6 +1636,10 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.delta = delta; ca.dnn_img = ws + p.dnn_img;
     ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = 0; ca.Bp = p.Bp;
     ca.adj = bptt_tc ? F(p.adj) : nullptr; ca.gflags = g.flags; ca.step = 0;
+    // lv with a scalar gate and the forward's gate_cot: the gate gradient is one reduction over (T, B), no target score here
+    const bool gate_from_fwd = !bptt && g.gate_cot != nullptr && g.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) &&
+                               d.ctrl_kind != SDES_CTRL_CLIPPED && d.gate_dim == 1;
+    ca.skip_gate = gate_from_fwd ? 1 : 0;
     // the fused dgrad chain serves the fused engines' shapes (P = 64: every transposed layer is one 64 x 64 block);
     // SDES_GRAD_LAYERWISE_SWEEP keeps the layer-by-layer launches (A/B measurements, cross-check)
     const bool use_chain = bptt_tc && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && p.pc == 1 && p.P == 64;
@@ -1738,6 +1743,11 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         // ---- input layer: dW_in += delta_h0^T x ; d emb[s] += per-step column sums of delta_h0
         GRAD_CHECK(wgrad(ws + p.dh_img[cur], 1, ws + p.ximg, p.pc, m_tiles, gp + kp.bl.in_w, d.dim, C, d.dim, nullptr));
         GRAD_CHECK(colsum(ws + p.dh_img[cur], 1, C, g.grad_emb + (int64_t)s0 * C, m_tiles, tiles_per_step, C));
+    }
+    if (gate_from_fwd) {
+        qgate_reduce_kernel<<<p.T, 256, 0, stream>>>(g.gate_cot, g.w, fws + kp.ws.gate, d.batch, d.batch, d.clip_model, g.grad_gate, kp.ws.dpad);
+        ++launches;
+        GRAD_CHECK(cudaGetLastError());
     }
     GRAD_CHECK(launch_time_embed_grads(kp, g, stream, launches));
 #undef GRAD_CHECK

@@ -357,11 +357,11 @@ constexpr bool ctrl_needs_prior(int ctrl) { return ctrl == SDES_CTRL_LERP || ctr
 // dimension 0), MODE 1: any later chunk, MODE 2: DENSE (target score of every dimension in scd[]).
 constexpr int CTRL_LERP_HI = 100;  // LerpCtrl with s / T >= 0.5: the other branch of torch.lerp (compile-time so that no select is issued per pair)
 
-template <int DPAD, int CTRL, int TGT, int MODE>
+template <int DPAD, int CTRL, int TGT, int MODE, bool QG>
 __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int q, const int step,
                                              const uint32_t traj, const LeanSmem& sm, const TgtGlobals& tg, const float* scd,
                                              const float* __restrict__ gate_row, const float* __restrict__ noise_row, float* xo,
-                                             const int xo_st, float2& cost2, float2& ito2) {
+                                             const int xo_st, float2& cost2, float2& ito2, float2& qs2) {
     const SdesRolloutDesc& d = p.d;
     float nn[8];
     tc::tmem_ld8(c.l_d + 8u * q, nn);
@@ -443,7 +443,9 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
             inner.y = clipf(inner.y, k.cs);
             // gate row of the prologue's table: clip(score_model(s)) per dimension (a scalar gate replicated, 0 on padding)
             const float2 gt = *reinterpret_cast<const float2*>(gate_row + 2 * r);
-            g2 = __ffma2_rn(__fmul2_rn(inner, gt), make_float2(k.outer, k.outer), g2);
+            const float2 u2 = __fmul2_rn(inner, make_float2(k.outer, k.outer));  // the ungated score part
+            g2 = __ffma2_rn(u2, gt, g2);
+            if (QG) qs2 = __ffma2_rn(u2, make_float2(e[2 * pp], e[2 * pp + 1]), qs2);  // d rnd / d gate of the lv losses (SdesRolloutDesc.gate_cot)
         }
         float2 gm2 = g2;
         if (k.ref_ctrl) gm2 = __ffma2_rn(ps2, make_float2(-k.sigma, -k.sigma), g2);  // g - sigma * prior score  (solver/oc.py:305-306)
@@ -464,19 +466,19 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
     }
 }
 
-template <int DPAD, int CTRL, int TGT, bool DENSE>
+template <int DPAD, int CTRL, int TGT, bool DENSE, bool QG>
 __device__ __forceinline__ void update_phase(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int step, const uint32_t traj,
                                              const LeanSmem& sm, const TgtGlobals& tg, const float* scd, const float* __restrict__ gate_row,
-                                             const float* __restrict__ noise_row, float* xo, const int xo_st, float2& cost2, float2& ito2) {
+                                             const float* __restrict__ noise_row, float* xo, const int xo_st, float2& cost2, float2& ito2, float2& qs2) {
     if (DENSE) {
 #pragma unroll
         for (int q = 0; q < DPAD / 8; ++q)
-            if (8 * q < k.dim) chunk_update<DPAD, CTRL, TGT, 2>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2);
+            if (8 * q < k.dim) chunk_update<DPAD, CTRL, TGT, 2, QG>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2);
     } else {
-        chunk_update<DPAD, CTRL, TGT, 0>(p, k, c, xs, 0, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2);
+        chunk_update<DPAD, CTRL, TGT, 0, QG>(p, k, c, xs, 0, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2);
         const int nq = (k.dim + 7) >> 3;
 #pragma unroll 1
-        for (int q = 1; q < nq; ++q) chunk_update<DPAD, CTRL, TGT, 1>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2);
+        for (int q = 1; q < nq; ++q) chunk_update<DPAD, CTRL, TGT, 1, QG>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2);
     }
 }
 
@@ -704,10 +706,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             float2 cost2 = make_float2(0.f, 0.f), ito2 = make_float2(0.f, 0.f);
             wait_layer(c);
             // ---- network output streamed from TMEM into the control / cost / state update
-            if (CTRL == SDES_CTRL_LERP && !k.w_lt_half)
-                update_phase<DPAD, CTRL_LERP_HI, TGT, DENSE>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2);
-            else
-                update_phase<DPAD, CTRL, TGT, DENSE>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2);
+            float2 qs2 = make_float2(0.f, 0.f);
+            const bool want_q = CTRL != SDES_CTRL_CLIPPED && d.gate_cot != nullptr;
+#define SDES_UPD(C_, Q_) update_phase<DPAD, C_, TGT, DENSE, Q_>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2, qs2)
+            if (CTRL == SDES_CTRL_LERP && !k.w_lt_half) {
+                if (want_q) SDES_UPD(CTRL_LERP_HI, true);
+                else SDES_UPD(CTRL_LERP_HI, false);
+            } else {
+                if (want_q) SDES_UPD(CTRL, true);
+                else SDES_UPD(CTRL, false);
+            }
+#undef SDES_UPD
+            if (want_q && valid) d.gate_cot[(int64_t)i * B + rrow] = k.ito_scale * (qs2.x + qs2.y);
             rnd = fmaf(k.cost_scale, cost2.x + cost2.y, rnd);
             if (d.flags & SDES_F_SUB_DIV_INT) rnd -= tab[TAB_DIV_INT];
             if (d.flags & SDES_F_COMPUTE_ITO) rnd = fmaf(k.ito_scale, ito2.x + ito2.y, rnd);

@@ -208,7 +208,7 @@ def tiled_traj_numel(T: int, B: int, dim: int) -> int:
 def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
             params: torch.Tensor | None = None, traj_tiled: bool = False, traj_buffer: Workspace | None = None,
-            keep_for_grad: bool = False, keep_score: bool = False):
+            keep_for_grad: bool = False, keep_score: bool = False, gate_cot: Workspace | None = None, out: dict | None = None):
     """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None); with `traj_tiled`
     the trajectory comes back as a flat buffer in the row-tiled layout that `lv_grad` consumes."""
     lib = _cabi.lib()
@@ -256,6 +256,14 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
         d.noise = noise.data_ptr()
         d.flags |= _cabi.F_NOISE_FROM_HBM
     d.x0, d.x_T, d.rnd = x0c.data_ptr(), x_T.data_ptr(), rnd.data_ptr()
+    if gate_cot is not None and spec.gate is not None and int(spec.gate["out_w"].shape[0]) == 1 and not is_wide(spec) \
+            and not (d.flags & _cabi.F_MLP_SIMT) and spec.ctrl["kind"] != "clipped":
+        # training forward on the tensor-core engine: keep d rnd / d gate per (step, trajectory) so that the lv gradient
+        # does not have to re-evaluate the target score (SdesRolloutDesc.gate_cot)
+        gc = gate_cot.get(4 * T * B, device)[: 4 * T * B].view(torch.float32)
+        d.gate_cot = gc.data_ptr()
+        if out is not None:
+            out["gate_cot"] = gc
     with torch.cuda.device(device):
         need = lib.sdes_workspace_bytes(C.byref(d))
         if need == 0:
@@ -288,7 +296,8 @@ def kl_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, **kw):
 
 def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
-            params: torch.Tensor | None = None, chunk_rows: int = 0, bptt: bool = False, grad_flags: int = 0):
+            params: torch.Tensor | None = None, chunk_rows: int = 0, bptt: bool = False, grad_flags: int = 0,
+            gate_cot: torch.Tensor | None = None):
     """d loss / d theta of the log-variance loss for the rollout that produced `xs` (same spec / seed / traj_offset /
     noise).  Returns (grad_params blob, grad_emb (T,64), grad_gate (T,gate_dim) | None) — see include/sdes_b200.h
     `sdes_rollout_lv_grad`.  `bptt=True`: the kl / kl_ito gradient (`sdes_rollout_kl_grad`)."""
@@ -339,6 +348,10 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
         grad_gate = torch.empty((T, int(spec.gate["out_w"].shape[0])), dtype=torch.float32, device=device)
     g.xs, g.w, g.grad_params, g.grad_emb, g.grad_gate = _ptr(None if wide else xs), w.data_ptr(), grad_params.data_ptr(), grad_emb.data_ptr(), _ptr(grad_gate)
     g.chunk_rows = chunk_rows
+    if gate_cot is not None and not bptt and not wide:
+        if gate_cot.numel() != T * B:
+            raise ValueError("gate_cot must be (T, B)")
+        g.gate_cot = gate_cot.data_ptr()
     with torch.cuda.device(device):
         need = fn_bytes(C.byref(d), C.byref(g))
         if need == 0:

@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch
 import bench
+from sdes_test_helpers import build_from_spec
 from sde_sampler_b200.spec import ctrl_parameters
 
 ap = argparse.ArgumentParser()
@@ -12,8 +13,9 @@ ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-o = bench.build_objects(dev, "auto", sync_metrics=False)
-x0 = o["prior"].sample((args.batch,))
+W = bench.WORKLOADS["gmm50"]
+o = build_from_spec(bench.load_spec(W), dev, engine="auto", seed=1234, sync_metrics=False)
+x0 = bench.sample_x0(W["x0"], args.batch, 50, dev, 100)
 ms = []
 for k in range(args.reps):
     for p in ctrl_parameters(o["ctrl"]):
