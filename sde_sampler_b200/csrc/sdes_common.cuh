@@ -54,6 +54,7 @@ struct KParams {
     int n_tiles;      // warp tiles of 32 trajectories
     int n_chunks;     // tcgen05 engine: time chunks per tile
     int chunk_steps;  // steps per chunk
+    int dense_smem;   // tcgen05 engine, DENSE instantiation: the full mixture image sits in shared memory (set by the launcher)
     uint32_t philox_rk[20];  // Philox4x32-10 round keys (k0 + r W0, k1 + r W1), r = 0..9, of d.seed: read by the tensor-core
                              // rollout as constant-bank operands instead of being re-derived per draw
 };

@@ -50,6 +50,9 @@ inline size_t tc_smem_bytes(const KParams& p) {
                       (size_t)TC_GROUPS * dpad * 128;
     return fl * sizeof(float);
 }
+// DENSE instantiation: the full mixture image ([K4][DPAD / 2] float4 = {-mu pair, h pair}) behind everything else, where it fits
+inline size_t tc_dense_image_bytes(const KParams& p) { return (size_t)((p.d.n_components + 3) & ~3) * p.ws.dpad * 8; }
+inline bool tc_dense_image_fits(const KParams& p) { return tc_smem_bytes(p) + tc_dense_image_bytes(p) <= 227u * 1024u; }
 
 // ---------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
@@ -318,6 +321,67 @@ __device__ __forceinline__ void gmm_active_score(const XPair& xs, const LeanSmem
     for (int r = 0; r < NP; ++r) gs[r] = __fmul2_rn(acc[r], make_float2(inv, inv));
 }
 
+// DENSE mixtures: score of EVERY dimension, components in groups of four, two sweeps over the dimension pairs per group —
+// (1) the four logits, (2) after the online-softmax update, the responsibility-weighted (x - mu) h terms — with the
+// mixture image in shared memory as one float4 {-mu pair, h pair} per (component, dimension pair) and packed math:
+// 8 instructions per (component, pair).  Same direct (x - mu)^2 form and log2-unit softmax as gmm_active_score.
+template <int DPAD>
+__device__ __forceinline__ void gmm_dense_score(const XPair& xs, const float4* __restrict__ img, const float* __restrict__ c2, const int K4,
+                                                float (&sc)[DPAD]) {
+    constexpr int NPAIR = DPAD / 2;
+    float2 acc[NPAIR];
+#pragma unroll
+    for (int r = 0; r < NPAIR; ++r) acc[r] = make_float2(0.f, 0.f);
+    float m = -INFINITY, ssum = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < K4; k += 4) {
+        const float4* g = img + k * NPAIR;
+        float2 q2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int r = 0; r < NPAIR; ++r) {
+            const float2 x2 = xs.pair(r);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = g[u * NPAIR + r];
+                const float2 dd = __fadd2_rn(x2, make_float2(v.x, v.y));
+                q2[u] = __ffma2_rn(dd, __fmul2_rn(dd, make_float2(v.z, v.w)), q2[u]);
+            }
+        }
+        const float4 c4 = *reinterpret_cast<const float4*>(c2 + k);
+        const float l[4] = {fmaf(q2[0].x + q2[0].y, -LOG2E, c4.x), fmaf(q2[1].x + q2[1].y, -LOG2E, c4.y),
+                            fmaf(q2[2].x + q2[2].y, -LOG2E, c4.z), fmaf(q2[3].x + q2[3].y, -LOG2E, c4.w)};
+        const float m_new = fmaxf(fmaxf(m, fmaxf(l[0], l[1])), fmaxf(l[2], l[3]));
+        float resc, e[4];
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(resc) : "f"(m - m_new));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[u]) : "f"(l[u] - m_new));
+        m = m_new;
+        ssum = fmaf(ssum, resc, (e[0] + e[1]) + (e[2] + e[3]));
+        if (__any_sync(0xffffffffu, resc != 1.0f)) {  // the running maximum moved for some trajectory of the warp
+#pragma unroll
+            for (int r = 0; r < NPAIR; ++r) acc[r] = __fmul2_rn(acc[r], make_float2(resc, resc));
+        }
+#pragma unroll
+        for (int r = 0; r < NPAIR; ++r) {
+            const float2 x2 = xs.pair(r);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = g[u * NPAIR + r];
+                const float2 t = __fmul2_rn(__fadd2_rn(x2, make_float2(v.x, v.y)), make_float2(v.z, v.w));
+                acc[r] = __ffma2_rn(make_float2(e[u], e[u]), t, acc[r]);
+            }
+        }
+    }
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ssum));
+    inv *= -2.0f;
+#pragma unroll
+    for (int r = 0; r < NPAIR; ++r) {
+        sc[2 * r] = acc[r].x * inv;
+        sc[2 * r + 1] = acc[r].y * inv;
+    }
+}
+
 template <int DPAD, int TGT>
 __device__ __forceinline__ void target_globals(const SdesRolloutDesc& d, const XPair& xs, const LeanSmem& sm, uint32_t gmm_mask, TgtGlobals& tg) {
     if (TGT == SDES_TARGET_GMM) {
@@ -518,6 +582,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     float* s_prior = s_nh20 + DPAD;
     float* s_ref = s_prior + 2 * DPAD + 8;
     float* s_x = s_ref + 2 * DPAD + 8;
+    float4* s_gimg = reinterpret_cast<float4*>(s_x + TC_GROUPS * DPAD * 128);  // DENSE: full mixture image (when it fits)
+    const bool dense_smem = DENSE && p.dense_smem != 0;
 
     if (warp == 0) {
         tc::tmem_alloc(&s_tmem, TMEM_COLS);
@@ -551,6 +617,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
         s_gh[e] = k < K2 ? ws[p.ws.gmm_h + k * DPAD + j] : 0.f;
     }
     for (int e = tid; e < 64; e += blockDim.x) s_c2[e] = (e < K2 ? ws[p.ws.gmm_c + e] : -INFINITY) * LOG2E;
+    if (dense_smem) {
+        for (int e = tid; e < K4 * (DPAD / 2); e += blockDim.x) {
+            const int k = e / (DPAD / 2), r = e % (DPAD / 2);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < K2) v = make_float4(-ws[p.ws.gmm_mu + k * DPAD + 2 * r], -ws[p.ws.gmm_mu + k * DPAD + 2 * r + 1],
+                                        ws[p.ws.gmm_h + k * DPAD + 2 * r], ws[p.ws.gmm_h + k * DPAD + 2 * r + 1]);
+            s_gimg[e] = v;
+        }
+    }
     for (int e = tid; e < DPAD; e += blockDim.x) {
         s_nmu0[e] = K > 0 ? -ws[p.ws.gmm_mu + e] : 0.f;
         s_nh20[e] = K > 0 ? -2.0f * ws[p.ws.gmm_h + e] : 0.f;
@@ -684,7 +759,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             if constexpr (DENSE) {
                 // score of every dimension, components differing on the first 8 / 16 / all dimension pairs (sdes_step.cuh)
                 constexpr int NPAIR = DPAD / 2;
-                if (NPAIR > 8 && gmm_mask < 256u) gmm_eval_na<DPAD, (NPAIR > 8 ? 8 : NPAIR), true>(xs, scd, tsm, K);
+                if (dense_smem) gmm_dense_score<DPAD>(xs, s_gimg, s_c2, K4, scd);
+                else if (NPAIR > 8 && gmm_mask < 256u) gmm_eval_na<DPAD, (NPAIR > 8 ? 8 : NPAIR), true>(xs, scd, tsm, K);
                 else if (NPAIR > 16 && gmm_mask < 65536u) gmm_eval_na<DPAD, (NPAIR > 16 ? 16 : NPAIR), true>(xs, scd, tsm, K);
                 else gmm_eval_na<DPAD, NPAIR, true>(xs, scd, tsm, K);
             } else if (ctrl_needs_target(CTRL)) {
@@ -775,7 +851,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
 
 template <int DPAD, bool DENSE, int CTRL, int TGT>
 static cudaError_t launch_k(const KParams& p, int sm_count, cudaStream_t stream) {
-    const size_t smem = tc_smem_bytes(p);
+    KParams q = p;
+    q.dense_smem = (DENSE && tc_dense_image_fits(p)) ? 1 : 0;
+    const size_t smem = tc_smem_bytes(p) + (q.dense_smem ? tc_dense_image_bytes(p) : 0);
     cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel<DPAD, DENSE, CTRL, TGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // work items = tiles x time chunks: a group that finds no first-chunk tile left starts on a second chunk and waits
@@ -784,7 +862,7 @@ static cudaError_t launch_k(const KParams& p, int sm_count, cudaStream_t stream)
     int grid = (int)((items + TC_GROUPS - 1) / TC_GROUPS);
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
-    rollout_tc_kernel<DPAD, DENSE, CTRL, TGT><<<grid, TC_THREADS, smem, stream>>>(p);
+    rollout_tc_kernel<DPAD, DENSE, CTRL, TGT><<<grid, TC_THREADS, smem, stream>>>(q);
     return cudaGetLastError();
 }
 
