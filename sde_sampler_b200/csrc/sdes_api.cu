@@ -610,7 +610,7 @@ int sdes_rollout_lv_grad(const SdesRolloutDesc* desc, const SdesLvGradDesc* g, v
     if (need > desc->workspace_bytes) return fail(-6, "workspace_bytes=%zu < required %zu", desc->workspace_bytes, need);
     if (desc->batch == 0) return 0;
     cudaError_t e = cudaSuccess;
-    g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e, false, 0);
+    g_launches += launch_lv_grad(p, *g, fused, simt, reinterpret_cast<cudaStream_t>(stream_), &e, false, sm_count_cached());
     if (e != cudaSuccess) return fail(-7, "lv gradient launch failed: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -23,6 +23,7 @@
 #include "sdes_linear.cuh"
 #include "sdes_step.cuh"
 #include "sdes_timeembed.cuh"
+#include "sdes_grad_fused.cuh"
 
 namespace sdes {
 namespace grad {
@@ -1579,15 +1580,22 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         ++launches;
         return cudaGetLastError();
     };
+    // lv with a scalar gate and the forward's gate_cot: the gate gradient is one reduction over (T, B), no target score here
+    const bool gate_from_fwd = !bptt && g.gate_cot != nullptr && g.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) &&
+                               d.ctrl_kind != SDES_CTRL_CLIPPED && d.gate_dim == 1;
+    const bool gate_wanted = g.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) && d.ctrl_kind != SDES_CTRL_CLIPPED;
+    // the whole pass as one persistent kernel (sdes_grad_fused.cuh) whenever its shapes allow; SDES_GRAD_LAYERWISE_SWEEP keeps
+    // the layer-by-layer GEMM passes (A/B measurements, cross-check)
+    const bool fused_lv = !bptt && !simt && lv_fused_supported(d) && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && (gate_from_fwd || !gate_wanted);
     GRAD_CHECK(image(p.f_in, blob + kp.bl.in_w, d.dim, C, d.dim, 0));
     for (int l = 0; l < p.nh; ++l) {
         GRAD_CHECK(image(p.f_h[l], blob + kp.bl.h_w[l], C, C, C, 0));
         GRAD_CHECK(bias(p.f_h[l], blob + kp.bl.h_b[l], C));
-        GRAD_CHECK(image(p.b_h[l], blob + kp.bl.h_w[l], C, C, C, 1));
+        if (!fused_lv) GRAD_CHECK(image(p.b_h[l], blob + kp.bl.h_w[l], C, C, C, 1));
     }
     GRAD_CHECK(image(p.f_out, blob + kp.bl.out_w, C, d.dim, C, 0));
     GRAD_CHECK(bias(p.f_out, blob + kp.bl.out_b, d.dim));
-    GRAD_CHECK(image(p.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));
+    if (!fused_lv) GRAD_CHECK(image(p.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));
     if (bptt_tc) GRAD_CHECK(image(p.b_in, blob + kp.bl.in_w, d.dim, d.dim, C, 1));
     GRAD_CHECK(cudaMemsetAsync(g.grad_params, 0, (size_t)d.n_params * 4, stream));
     GRAD_CHECK(cudaMemsetAsync(g.grad_emb, 0, (size_t)p.T * C * 4, stream));
@@ -1636,9 +1644,6 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     ca.kp = kp; ca.xs = g.xs; ca.w = g.w; ca.nn = F(p.nn); ca.ones = F(p.ones); ca.delta = delta; ca.dnn_img = ws + p.dnn_img;
     ca.grad_gate = g.grad_gate; ca.P = p.P; ca.pc = p.pc; ca.s0 = 0; ca.Bp = p.Bp;
     ca.adj = bptt_tc ? F(p.adj) : nullptr; ca.gflags = g.flags; ca.step = 0;
-    // lv with a scalar gate and the forward's gate_cot: the gate gradient is one reduction over (T, B), no target score here
-    const bool gate_from_fwd = !bptt && g.gate_cot != nullptr && g.grad_gate != nullptr && (d.flags & SDES_F_HAS_GATE) &&
-                               d.ctrl_kind != SDES_CTRL_CLIPPED && d.gate_dim == 1;
     ca.skip_gate = gate_from_fwd ? 1 : 0;
     // the fused dgrad chain serves the fused engines' shapes (P = 64: every transposed layer is one 64 x 64 block);
     // SDES_GRAD_LAYERWISE_SWEEP keeps the layer-by-layer launches (A/B measurements, cross-check)
@@ -1647,7 +1652,26 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         GRAD_CHECK(launch_adj(ca, tiles_per_step, true, stream));
         ++launches;
     }
-    for (int chi = 0; chi < p.n_chunks; ++chi) {
+    if (fused_lv) {
+        FusedLvArgs fa;
+        fa.d = d; fa.tab = fws + kp.ws.tab; fa.xs = g.xs; fa.w = g.w; fa.embb = F(p.embb);
+        fa.nh = p.nh; fa.T = p.T; fa.tiles_per_step = tiles_per_step; fa.grad_emb = g.grad_emb;
+        float* gp = g.grad_params;
+        const int Lf = p.nh + 2;
+        for (int l = 0; l < FL_MAX_LAYERS; ++l) {
+            fa.w_img[l] = nullptr; fa.bias[l] = nullptr; fa.dw[l] = nullptr; fa.db[l] = nullptr; fa.ldw[l] = fa.n_valid[l] = fa.k_valid[l] = 0;
+        }
+        fa.w_img[0] = ws + p.f_in.w_off; fa.dw[0] = gp + kp.bl.in_w; fa.ldw[0] = d.dim; fa.n_valid[0] = C; fa.k_valid[0] = d.dim;
+        for (int l = 0; l < p.nh; ++l) {
+            fa.w_img[1 + l] = ws + p.f_h[l].w_off; fa.bias[1 + l] = F(p.f_h[l].b_off);
+            fa.dw[1 + l] = gp + kp.bl.h_w[l]; fa.db[1 + l] = gp + kp.bl.h_b[l]; fa.ldw[1 + l] = C; fa.n_valid[1 + l] = C; fa.k_valid[1 + l] = C;
+        }
+        fa.w_img[Lf - 1] = ws + p.f_out.w_off; fa.bias[Lf - 1] = F(p.f_out.b_off);
+        fa.dw[Lf - 1] = gp + kp.bl.out_w; fa.db[Lf - 1] = gp + kp.bl.out_b; fa.ldw[Lf - 1] = C; fa.n_valid[Lf - 1] = d.dim; fa.k_valid[Lf - 1] = C;
+        GRAD_CHECK(launch_lv_fused(fa, sm_count > 0 ? sm_count : 148, stream));
+        ++launches;
+    }
+    for (int chi = 0; chi < (fused_lv ? 0 : p.n_chunks); ++chi) {
         const int ch = bptt_tc ? p.n_chunks - 1 - chi : chi;  // the sweep walks the chunks backwards in time
         const int s0 = ch * p.chunk_steps;
         const int ns = (s0 + p.chunk_steps <= p.T) ? p.chunk_steps : p.T - s0;

@@ -1,0 +1,467 @@
+// sdes_grad_fused.cuh — the lv gradient of the control MLP as ONE persistent kernel (`loss.backward()` of
+// `Trainable.step`, solver/base.py:404-407, loss.method = lv): per 128-row tile of (step, trajectory) rows
+//     replayed forward (models/mlp.py:114-122)  ->  output cotangent  ->  dgrad chain  ->  weight-gradient MMAs
+// with every activation / delta operand living in shared memory only and the weight gradients accumulating in TMEM for
+// the whole launch.  Nothing but the stored trajectory (200 B per row) is read from HBM and nothing but the final
+// gradients is written — the layer-by-layer path of sdes_grad.cu moves ~45 GB of operand images per training step.
+//
+// One CTA per SM, 18 warps: warp 0 lane 0 issues every MMA, warp 1 owns the TMEM allocation, warps 2-17 are the
+// epilogue: TMEM lane quadrant = warp % 4 (thread = row), and the four warps of a quadrant share the row's 64 columns
+// (16 each) so that every hop of the per-tile dependency chain is short.  Shared memory (nh = 2, d <= 56):
+//     X (input rows, bf16 hi | lo)  28 KB     A1, A2 (hidden activations, kept for their weight gradients)  64 KB
+//     P, Q (ping-pong: last activation / cotangent / delta images)  64 KB     4 weight images  64 KB     ones  4 KB
+// All images use the canonical no-swizzle layout of sdes_linear.cuh: element (row r, feature f) of a half at
+// ((f / 8) * 128 + r) * 16 + (f % 8) * 2 bytes, which is at once
+//   - a K-major A operand  [M = 128 rows,  K = features]   (forward and dgrad GEMMs),
+//   - an MN-major operand  [MN = features, K = 128 rows]   (weight gradients: the contraction runs over the rows).
+// The 64 x 64 weight images are the forward ones; W^T for the dgrad GEMMs is the SAME image read as an MN-major B operand.
+// Per layer of the backward chain the pre-activation is recomputed by one more GEMM into a second accumulator (the
+// tensor pipe is far from busy; storing GELU' would need another 96 KB), so  delta_l = (delta_{l+1} W^T) * GELU'(z_l).
+// MMAs complete in issue order, so a commit after {wgrad, dgrad, recompute} of one hop also frees the buffers the wgrad
+// read, which is what lets two ping-pong buffers serve the whole chain.
+// TMEM: 4 x 64 columns of weight-gradient accumulators (rows 0-63 / 64-127: contributions of the hi / lo half of delta),
+// 4 x 16 columns of column sums (bias gradients; the input layer's are d loss / d emb(s), flushed whenever the step
+// changes — items are step-major, so a CTA sees at most a few steps), 2 x 64 working accumulators.
+#pragma once
+
+#include "sdes_linear.cuh"
+#include "sdes_step.cuh"
+
+namespace sdes {
+namespace grad {
+
+using namespace wide;
+
+constexpr int FL_MAX_LAYERS = 4;                 // W_in, up to two hidden layers, W_out
+constexpr int FL_EPI_WARPS = 16;
+constexpr int FL_THREADS = 64 + 32 * FL_EPI_WARPS;
+constexpr uint32_t FL_W_BYTES = 16384u;          // one 64 x 64 weight image (hi | lo)
+constexpr uint32_t FL_ONES_BYTES = 4096u;
+constexpr uint32_t FL_COL_DW = 0u, FL_COL_DB = 256u, FL_COL_D = 320u, FL_COL_D2 = 384u;
+
+struct FusedLvArgs {
+    SdesRolloutDesc d;                        // dim, batch, flags (trajectory layout, noise source), seed, traj_offset, noise, clip_model
+    const float* tab;                         // (T, TAB_STRIDE) per-step scalars of the fused prologue
+    const float* xs;                          // stored trajectory of the forward rollout
+    const float* w;                           // (B) d loss / d rnd_b
+    const float* embb;                        // (T, 64) timestep_embed(s) + b_in
+    const uint8_t* w_img[FL_MAX_LAYERS];      // forward images of W_in, W_h[0..nh-1], W_out
+    const float* bias[FL_MAX_LAYERS];         // [1..nh]: b_h, [nh+1]: b_out (padded to 64); [0] unused
+    float* dw[FL_MAX_LAYERS];                 // row-major (out, in) gradients, += via atomics
+    int ldw[FL_MAX_LAYERS], n_valid[FL_MAX_LAYERS], k_valid[FL_MAX_LAYERS];
+    float* db[FL_MAX_LAYERS];                 // bias gradients of layers 1..nh+1 ([0]: NULL — the input layer's go to grad_emb)
+    float* grad_emb;                          // (T, 64)
+    int nh, T, tiles_per_step;
+};
+
+// GELU'(x) = Phi(x) + x phi(x) of the exact-erf GELU, two values at a time: Phi from the logistic fit of gelu_fast2
+// (sdes_common.cuh), phi(x) = 2^(-x^2 log2(e) / 2) / sqrt(2 pi).
+__device__ __forceinline__ float2 gelu_grad2(float2 x) {
+    const float2 u = __fmul2_rn(x, x);
+    float2 p = __ffma2_rn(make_float2(-5.42691260e-09f, -5.42691260e-09f), u, make_float2(3.93527977e-07f, 3.93527977e-07f));
+    p = __ffma2_rn(p, u, make_float2(-1.15760618e-05f, -1.15760618e-05f));
+    p = __ffma2_rn(p, u, make_float2(1.60239457e-04f, 1.60239457e-04f));
+    p = __ffma2_rn(p, u, make_float2(9.27478302e-05f, 9.27478302e-05f));
+    p = __ffma2_rn(p, u, make_float2(-1.04834383e-01f, -1.04834383e-01f));
+    p = __ffma2_rn(p, u, make_float2(-2.30220913e+00f, -2.30220913e+00f));
+    const float2 q = __fmul2_rn(x, p);
+    const float2 t = __fmul2_rn(u, make_float2(-0.72134752044448170f, -0.72134752044448170f));
+    float2 e, r, g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.y) : "f"(t.y));
+    const float2 dn = __fadd2_rn(e, make_float2(1.f, 1.f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(dn.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(dn.y));
+    return __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), g, r);
+}
+
+// ---- MMA issue (one thread).  D[128 rows, 64] = A (row image, K-major) x W image (N = 64 out features, K-major)
+__device__ __forceinline__ void fl_mma_rows_w(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, int nks) {
+    const uint32_t idesc = tc::idesc_bf16(128, 64);
+    const uint32_t w_lo = w_hi + 8192u;
+    for (int ks = 0; ks < nks; ++ks) {
+        const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
+        const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
+        const uint64_t dbh = tc::smem_desc_kmajor(w_hi + (uint32_t)ks * 2048u, 1024u, 128u);
+        const uint64_t dbl = tc::smem_desc_kmajor(w_lo + (uint32_t)ks * 2048u, 1024u, 128u);
+        mma_f16_ss(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);  // small terms first
+        mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
+        mma_f16_ss(tmem_d, dah, dbh, idesc, 1u);
+    }
+}
+// D[128 rows, 64 in features] = A (delta image, K = out features) x W: the forward image (n = out, k = in) read as an
+// MN-major B operand — 8 in-features contiguous, out-features 16 B apart, groups of 8 out-features 128 B apart, groups of
+// 8 in-features 1024 B apart; one k-step = 16 out-features = 256 B.
+__device__ __forceinline__ void fl_mma_rows_wt(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, int nks) {
+    const uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 16);  // b_major = MN
+    const uint32_t w_lo = w_hi + 8192u;
+    for (int ks = 0; ks < nks; ++ks) {
+        const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
+        const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
+        const uint64_t dbh = tc::smem_desc_kmajor(w_hi + (uint32_t)ks * 256u, 128u, 1024u);
+        const uint64_t dbl = tc::smem_desc_kmajor(w_lo + (uint32_t)ks * 256u, 128u, 1024u);
+        mma_f16_ss(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+        mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
+        mma_f16_ss(tmem_d, dah, dbh, idesc, 1u);
+    }
+}
+// dW[(hi | lo) out features, in features] += delta^T a over the tile's 128 rows, and the column sums of delta (wgrad_mma_kernel)
+__device__ __forceinline__ void fl_mma_wgrad(uint32_t tmem_dw, uint32_t tmem_db, uint32_t delta, uint32_t act_hi, uint32_t act_lo,
+                                             uint32_t ones, bool acc_dw, bool acc_db) {
+    const uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 15) | (1u << 16), idesc1 = tc::idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
+    const uint64_t dones = tc::smem_desc_kmajor(ones, 128u, 2048u);
+    for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
+        const uint64_t da = tc::smem_desc_kmajor(delta + (uint32_t)ks * 256u, 128u, 2048u);
+        const uint64_t dbh = tc::smem_desc_kmajor(act_hi + (uint32_t)ks * 256u, 128u, 2048u);
+        const uint64_t dbl = tc::smem_desc_kmajor(act_lo + (uint32_t)ks * 256u, 128u, 2048u);
+        mma_f16_ss(tmem_dw, da, dbl, idesc, (acc_dw || ks > 0) ? 1u : 0u);
+        mma_f16_ss(tmem_dw, da, dbh, idesc, 1u);
+        mma_f16_ss(tmem_db, da, dones, idesc1, (acc_db || ks > 0) ? 1u : 0u);
+    }
+}
+
+// 16 values of one row -> the two 16-byte groups (c_lo .. c_lo + 15) of both halves of an image
+__device__ __forceinline__ void fl_store16(uint8_t* img, uint32_t half_bytes, int r, int c_lo, const float (&v)[16]) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint4 hi, lo;
+        tc::split_bf16_pair2(make_float2(v[8 * g + 0], v[8 * g + 1]), hi.x, lo.x);
+        tc::split_bf16_pair2(make_float2(v[8 * g + 2], v[8 * g + 3]), hi.y, lo.y);
+        tc::split_bf16_pair2(make_float2(v[8 * g + 4], v[8 * g + 5]), hi.z, lo.z);
+        tc::split_bf16_pair2(make_float2(v[8 * g + 6], v[8 * g + 7]), hi.w, lo.w);
+        uint8_t* o = img + (uint32_t)((((c_lo >> 3) + g) * 128 + r) * 16);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + half_bytes) = lo;
+    }
+}
+__device__ __forceinline__ void fl_ld16(uint32_t taddr, float (&v)[16]) {
+    tc::tmem_ld8(taddr, &v[0]);
+    tc::tmem_ld8(taddr + 8u, &v[8]);
+    tc::wait_ld_tie<16>(v);
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_constant__ FusedLvArgs a) {
+    extern __shared__ __align__(128) uint8_t fl_smem[];
+    __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone;
+    __shared__ uint32_t s_tmem;
+    constexpr uint32_t XHALF = (uint32_t)(DPAD / 8) * 2048u, XBYTES = 2u * XHALF;
+    constexpr int NKS_IN = (DPAD + 15) / 16;
+    const SdesRolloutDesc& d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nh = a.nh, L = nh + 2, dim = d.dim;
+    uint8_t* s_x = fl_smem;
+    uint8_t* s_act = s_x + XBYTES;                       // a_1 .. a_nh
+    uint8_t* s_p = s_act + (size_t)nh * A_BLOCK;
+    uint8_t* s_q = s_p + A_BLOCK;
+    uint8_t* s_w = s_q + A_BLOCK;                        // L weight images
+    uint8_t* s_ones = s_w + (size_t)L * FL_W_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_ones + FL_ONES_BYTES);  // [l - 1][64], l = 1 .. nh + 1
+
+    // every operand buffer starts finite: padded k-steps multiply whatever lies there by zero weights
+    for (uint32_t e = tid; e < (uint32_t)(s_w - fl_smem) / 16u; e += blockDim.x) reinterpret_cast<uint4*>(fl_smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t e = tid; e < FL_ONES_BYTES / 4u; e += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[e] = 0x3F803F80u;  // bf16 1.0 pairs
+    for (int e = tid; e < (nh + 1) * 64; e += blockDim.x) s_bias[e] = a.bias[1 + e / 64][e % 64];
+    tc::fence_proxy_async();
+    if (warp == 1) {
+        tc::tmem_alloc(&s_tmem, 512u);
+        tc::tmem_relinquish();
+    }
+    if (tid == 0) {
+        tc::mbar_init(&s_wfull, 1);
+        tc::mbar_init(&s_acc, 1);
+        tc::mbar_init(&s_aready, 32 * FL_EPI_WARPS);
+        tc::mbar_init(&s_wdone, 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int64_t n_items = (int64_t)a.T * a.tiles_per_step;
+    const int64_t i0 = (int64_t)blockIdx.x * n_items / gridDim.x, i1 = (int64_t)(blockIdx.x + 1) * n_items / gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0 && i1 > i0) {  // ---- control thread
+            tc::mbar_arrive_expect_tx(&s_wfull, (uint32_t)L * FL_W_BYTES);
+            for (int l = 0; l < L; ++l) tc::bulk_g2s(s_w + (size_t)l * FL_W_BYTES, a.w_img[l], FL_W_BYTES, &s_wfull);
+            tc::mbar_wait(&s_wfull, 0u);
+            const uint32_t x_hi = tc::smem_u32(s_x), x_lo = x_hi + XHALF;
+            const uint32_t act0 = tc::smem_u32(s_act), pb = tc::smem_u32(s_p), qb = tc::smem_u32(s_q), wb = tc::smem_u32(s_w);
+            const uint32_t ones = tc::smem_u32(s_ones);
+            const uint32_t tD = tmem_base + FL_COL_D, tD2 = tmem_base + FL_COL_D2;
+            uint32_t ph = 0u;
+            bool first = true;
+            int prev_s = -1;
+            auto ready = [&]() {
+                tc::mbar_wait(&s_aready, ph);
+                ph ^= 1u;
+                tc::fence_after();
+            };
+            for (int64_t item = i0; item < i1; ++item) {
+                const int s = (int)(item / a.tiles_per_step);
+                const bool new_step = s != prev_s;
+                prev_s = s;
+                // ---- replayed forward
+                ready();
+                fl_mma_rows_w(tD, x_hi, x_lo, wb, NKS_IN);
+                tc::mma_commit(&s_acc);
+                for (int l = 0; l < nh; ++l) {
+                    ready();
+                    const uint32_t ab = act0 + (uint32_t)l * A_BLOCK;
+                    fl_mma_rows_w(tD, ab, ab + A_HALF, wb + (uint32_t)(1 + l) * FL_W_BYTES, 4);
+                    tc::mma_commit(&s_acc);
+                }
+                ready();
+                fl_mma_rows_w(tD, pb, pb + A_HALF, wb + (uint32_t)(nh + 1) * FL_W_BYTES, 4);
+                tc::mma_commit(&s_acc);
+                // ---- backward: output layer (cotangent in Q, a_{nh+1} in P)
+                ready();
+                fl_mma_wgrad(tmem_base + FL_COL_DW + 64u * (uint32_t)(nh + 1), tmem_base + FL_COL_DB + 16u * (uint32_t)(nh + 1), qb, pb, pb + A_HALF, ones,
+                             !first, !first);
+                fl_mma_rows_wt(tD, qb, qb + A_HALF, wb + (uint32_t)(nh + 1) * FL_W_BYTES, NKS_IN);
+                {
+                    const uint32_t ab = act0 + (uint32_t)(nh - 1) * A_BLOCK;  // z_{nh+1} = a_nh W_h[nh-1]
+                    fl_mma_rows_w(tD2, ab, ab + A_HALF, wb + (uint32_t)nh * FL_W_BYTES, 4);
+                }
+                tc::mma_commit(&s_acc);
+                uint32_t cur = pb, other = qb;  // the epilogue writes delta_{nh+1} into P
+                for (int l = nh - 1; l >= 0; --l) {
+                    ready();  // delta_{l+2} is in `cur`
+                    const uint32_t ab = act0 + (uint32_t)l * A_BLOCK;  // a_{l+1}
+                    fl_mma_wgrad(tmem_base + FL_COL_DW + 64u * (uint32_t)(1 + l), tmem_base + FL_COL_DB + 16u * (uint32_t)(1 + l), cur, ab, ab + A_HALF, ones,
+                                 !first, !first);
+                    fl_mma_rows_wt(tD, cur, cur + A_HALF, wb + (uint32_t)(1 + l) * FL_W_BYTES, 4);
+                    if (l > 0) {
+                        const uint32_t pa = act0 + (uint32_t)(l - 1) * A_BLOCK;
+                        fl_mma_rows_w(tD2, pa, pa + A_HALF, wb + (uint32_t)l * FL_W_BYTES, 4);
+                    } else {
+                        fl_mma_rows_w(tD2, x_hi, x_lo, wb, NKS_IN);
+                    }
+                    tc::mma_commit(&s_acc);
+                    const uint32_t t = cur;
+                    cur = other;
+                    other = t;
+                }
+                ready();  // delta_1 is in `cur`
+                fl_mma_wgrad(tmem_base + FL_COL_DW, tmem_base + FL_COL_DB, cur, x_hi, x_lo, ones, !first, !new_step);
+                tc::mma_commit(&s_wdone);
+                first = false;
+            }
+        }
+    } else if (warp >= 2 && i1 > i0) {  // ---- epilogue warps
+        const int q = warp & 3, r = q * 32 + lane, cw = (warp - 2) >> 2, c_lo = 16 * cw;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t tD = lane_base + FL_COL_D + (uint32_t)c_lo, tD2 = lane_base + FL_COL_D2 + (uint32_t)c_lo;
+        const int64_t B = d.batch;
+        uint32_t ph_acc = 0u, ph_w = 0u;
+        int prev_s = -1;
+        auto arrive = [&]() {
+            tc::fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor-core (async) proxy
+            tc::fence_before();
+            mbar_arrive(&s_aready);
+        };
+        auto wait_acc = [&]() {
+            tc::mbar_wait(&s_acc, ph_acc);
+            ph_acc ^= 1u;
+            tc::fence_after();
+        };
+        auto flush_emb = [&](int s_prev) {  // d loss / d emb(s_prev): column sums of delta_1 over the step's tiles of this CTA
+            if (cw == 0) {
+                float v[8];
+                tc::tmem_ld8(lane_base + FL_COL_DB, v);
+                tc::wait_ld_tie<8>(v);
+                if (v[0] != 0.f) atomicAdd(a.grad_emb + (int64_t)s_prev * 64 + (r & 63), v[0]);  // hi row and lo row both add
+            }
+        };
+        for (int64_t item = i0; item < i1; ++item) {
+            const int s = (int)(item / a.tiles_per_step), tile = (int)(item - (int64_t)s * a.tiles_per_step);
+            const int64_t b = (int64_t)tile * 128 + r;
+            const bool valid = b < B;
+            const int64_t bb = valid ? b : 0;
+            // ---- this thread's 16 features of the row (loads in flight while the previous item's last MMAs drain)
+            float v[16];
+            {
+                const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = (valid && c_lo + e < dim) ? __ldg(xr.p + (int64_t)(c_lo + e) * xr.stride) : 0.f;
+            }
+            if (item > i0) {
+                tc::mbar_wait(&s_wdone, ph_w);  // X (and P / Q) are free again
+                ph_w ^= 1u;
+                tc::fence_after();
+                if (s != prev_s) flush_emb(prev_s);
+            }
+            prev_s = s;
+            if (c_lo < DPAD) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (c_lo + 8 * g < DPAD) {
+                        uint4 hi, lo;
+                        tc::split_bf16_pair2(make_float2(v[8 * g + 0], v[8 * g + 1]), hi.x, lo.x);
+                        tc::split_bf16_pair2(make_float2(v[8 * g + 2], v[8 * g + 3]), hi.y, lo.y);
+                        tc::split_bf16_pair2(make_float2(v[8 * g + 4], v[8 * g + 5]), hi.z, lo.z);
+                        tc::split_bf16_pair2(make_float2(v[8 * g + 6], v[8 * g + 7]), hi.w, lo.w);
+                        uint8_t* o = s_x + (uint32_t)((((c_lo >> 3) + g) * 128 + r) * 16);
+                        *reinterpret_cast<uint4*>(o) = hi;
+                        *reinterpret_cast<uint4*>(o + XHALF) = lo;
+                    }
+                }
+            }
+            arrive();
+            const float* embb = a.embb + (int64_t)s * 64 + c_lo;
+            // ---- replayed forward: input layer, hidden layers
+            for (int l = 0; l <= nh; ++l) {
+                float bv[16];
+                if (l == 0) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = __ldg(reinterpret_cast<const float4*>(embb + e));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = *reinterpret_cast<const float4*>(s_bias + (l - 1) * 64 + c_lo + e);
+                }
+                wait_acc();
+                fl_ld16(tD, v);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 y = gelu_fast2(__fadd2_rn(make_float2(v[e], v[e + 1]), make_float2(bv[e], bv[e + 1])));
+                    v[e] = y.x;
+                    v[e + 1] = y.y;
+                }
+                fl_store16(l < nh ? s_act + (size_t)l * A_BLOCK : s_p, A_HALF, r, c_lo, v);
+                arrive();
+            }
+            // ---- output layer -> cotangent of the network output: w_b c_j 1[|NN_j| <= clip_model], c = eps sqrt(dt) (sigma beta_k eps)
+            {
+                const float* tab = a.tab + (int64_t)s * TAB_STRIDE;
+                const StepCoef c = make_step_coef(d, tab);
+                const float wb = valid ? __ldg(a.w + bb) : 0.f;
+                const float cscale = wb * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
+                const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
+                const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
+                float eps[16];
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const int j0 = c_lo + 4 * qd;
+                    float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j0 < dim) {
+                        if (c.from_hbm) {
+                            n4.x = nrow[j0];
+                            n4.y = j0 + 1 < dim ? nrow[j0 + 1] : 0.f;
+                            n4.z = j0 + 2 < dim ? nrow[j0 + 2] : 0.f;
+                            n4.w = j0 + 3 < dim ? nrow[j0 + 3] : 0.f;
+                        } else {
+                            n4 = normal4_call(c.k0, c.k1, traj, (uint32_t)s, (uint32_t)(j0 >> 2));
+                        }
+                    }
+                    eps[4 * qd] = n4.x; eps[4 * qd + 1] = n4.y; eps[4 * qd + 2] = n4.z; eps[4 * qd + 3] = n4.w;
+                }
+                const float* bo = s_bias + nh * 64 + c_lo;
+                wait_acc();
+                fl_ld16(tD, v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float nn = v[e] + bo[e];
+                    v[e] = (c_lo + e < dim && fabsf(nn) <= c.cm) ? cscale * eps[e] : 0.f;  // d clip(NN) / d NN: 1 on [-c, c]
+                }
+                fl_store16(s_q, A_HALF, r, c_lo, v);
+                arrive();
+            }
+            // ---- backward chain: delta_l = (delta_{l+1} W^T) * GELU'(z_l), z_l recomputed into the second accumulator
+            uint8_t* dst = s_p;
+            uint8_t* nxt = s_q;
+            for (int l = nh; l >= 0; --l) {  // produces delta_{l+1}
+                float bv[16], z[16];
+                if (l == 0) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = __ldg(reinterpret_cast<const float4*>(embb + e));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = *reinterpret_cast<const float4*>(s_bias + (l - 1) * 64 + c_lo + e);
+                }
+                wait_acc();
+                tc::tmem_ld8(tD2, &z[0]);
+                tc::tmem_ld8(tD2 + 8u, &z[8]);
+                tc::tmem_ld8(tD, &v[0]);
+                tc::tmem_ld8(tD + 8u, &v[8]);
+                tc::wait_ld_tie<16>(z);
+                tc::wait_ld_tie<16>(v);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 g = gelu_grad2(__fadd2_rn(make_float2(z[e], z[e + 1]), make_float2(bv[e], bv[e + 1])));
+                    const float2 y = __fmul2_rn(make_float2(v[e], v[e + 1]), g);
+                    v[e] = y.x;
+                    v[e + 1] = y.y;
+                }
+                fl_store16(dst, A_HALF, r, c_lo, v);
+                arrive();
+                uint8_t* t = dst;
+                dst = nxt;
+                nxt = t;
+            }
+        }
+        // ---- the launch's accumulators -> global memory
+        tc::mbar_wait(&s_wdone, ph_w);
+        tc::fence_after();
+        flush_emb(prev_s);
+        for (int l = 0; l < L; ++l) {
+            float v[16];
+            fl_ld16(lane_base + FL_COL_DW + 64u * (uint32_t)l + (uint32_t)c_lo, v);
+            const int n = r & 63;  // D rows 0-63: contributions of delta_hi, 64-127: of delta_lo
+            if (n < a.n_valid[l]) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (c_lo + e < a.k_valid[l] && v[e] != 0.f) atomicAdd(a.dw[l] + (int64_t)n * a.ldw[l] + c_lo + e, v[e]);
+            }
+            if (l > 0 && cw == 0 && a.db[l] != nullptr) {
+                float u[8];
+                tc::tmem_ld8(lane_base + FL_COL_DB + 16u * (uint32_t)l, u);
+                tc::wait_ld_tie<8>(u);
+                if (n < a.n_valid[l] && u[0] != 0.f) atomicAdd(a.db[l] + n, u[0]);
+            }
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 512u);
+}
+
+static size_t lv_fused_smem_bytes(int dpad, int nh) {
+    return (size_t)2 * (dpad / 8) * 2048 + (size_t)(nh + 2) * A_BLOCK + (size_t)(nh + 2) * FL_W_BYTES + FL_ONES_BYTES + (size_t)(nh + 1) * 256;
+}
+// the shapes the fused kernel serves: d <= 56 (input image + buffers fit 227 KB), one or two hidden layers
+static bool lv_fused_supported(const SdesRolloutDesc& d) {
+    return d.dim <= 56 && d.n_hidden >= 1 && d.n_hidden <= 2 && lv_fused_smem_bytes(mma_pad_dim(d.dim), d.n_hidden) <= 232448u - 64u;
+}
+
+template <int DPAD>
+static cudaError_t launch_lv_fused_t(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
+    const size_t smem = lv_fused_smem_bytes(DPAD, a.nh);
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(lv_fused_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    const int64_t n_items = (int64_t)a.T * a.tiles_per_step;
+    int grid = (int)(n_items < sm_count ? n_items : sm_count);
+    if (grid < 1) grid = 1;
+    lv_fused_kernel<DPAD><<<grid, FL_THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_lv_fused(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
+    switch (mma_pad_dim(a.d.dim)) {
+        case 8: return launch_lv_fused_t<8>(a, sm_count, stream);
+        case 16: return launch_lv_fused_t<16>(a, sm_count, stream);
+        case 32: return launch_lv_fused_t<32>(a, sm_count, stream);
+        case 48: return launch_lv_fused_t<48>(a, sm_count, stream);
+        case 56: return launch_lv_fused_t<56>(a, sm_count, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace grad
+}  // namespace sdes

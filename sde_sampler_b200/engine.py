@@ -340,7 +340,7 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
         d.flags |= _cabi.F_NOISE_FROM_HBM
     g = _cabi.LvGradDesc()
     g.struct_bytes = C.sizeof(_cabi.LvGradDesc)
-    g.flags = (kl_grad_flags(spec) | grad_flags) if bptt else 0
+    g.flags = (kl_grad_flags(spec) if bptt else 0) | grad_flags
     grad_params = torch.empty_like(params)
     grad_emb = torch.empty((T, _cabi.CHANNELS), dtype=torch.float32, device=device)
     grad_gate = None

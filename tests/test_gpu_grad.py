@@ -131,6 +131,38 @@ def test_lv_gradient_engines_agree_and_chunking_is_invariant(golden):
             assert (a - c).abs().max().item() <= 2e-3 * scale + 1e-7
 
 
+@pytest.mark.parametrize("name,B", [("dis_gmm50_lv", 1000), ("dis_gmm50_lv", 40000), ("dds_funnel10_lv", 3000), ("eulerdds_gmm2_lv", 777), ("dis_dw1_lv", 130)])
+def test_lv_fused_kernel_matches_layerwise_passes(golden, name, B):
+    """The one-kernel lv gradient (csrc/sdes_grad_fused.cuh: replayed forward, dgrad chain and weight-gradient MMAs per row
+    tile, operands in shared memory, accumulators in TMEM) against the layer-by-layer GEMM passes on the same stored
+    trajectory: ragged last tile, several steps per CTA, all three loss kinds, in-kernel Philox noise."""
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.engine import Workspace
+    from sde_sampler_b200.spec import extract_spec
+
+    if name not in CASES:
+        pytest.skip("no such golden")
+    g = golden(name)
+    b = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    d, T = g["x0"].shape[1], g["ts"].shape[0] - 1
+    x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(4))
+    kind = CASES[name]["loss"]
+    spec = extract_spec(b["loss"], kind, b["ts"], b["terminal"], b["second"], train=True, compute_ito=True, return_traj=True)
+    out = {}
+    x_T, rnd, xs = eng.rollout(spec, x0, seed=5, engine="tcgen05", gate_cot=Workspace(), out=out)
+    r = rnd.reshape(-1).double()
+    w = (2.0 * (r - r.mean()) / (B - 1)).float()
+    gc = out.get("gate_cot")
+    fused = eng.lv_grad(spec, xs, w, seed=5, engine="tcgen05", gate_cot=gc)
+    layer = eng.lv_grad(spec, xs, w, seed=5, engine="tcgen05", gate_cot=gc, grad_flags=_cabi.GRAD_LAYERWISE_SWEEP)
+    for i, (a, c) in enumerate(zip(layer, fused)):
+        if a is None:
+            assert c is None
+            continue
+        scale = a.abs().max().item()
+        assert (a - c).abs().max().item() <= 1e-3 * scale + 1e-7, f"output {i}: {(a - c).abs().max().item():.3e} vs scale {scale:.3e}"
+
+
 def test_kl_gradient_is_additive_over_shards_and_engine_independent(golden):
     """Size-independent properties of the BPTT gradient at 4 096 trajectories of the cfg-3 configuration (funnel d=10, PIS,
     kl): the gradient is linear in the per-trajectory weights, so two half-batch calls (global Philox counters via
