@@ -20,7 +20,7 @@ SOURCES = ["sdes_api.cu", "sdes_prepare.cu", "sdes_rollout_simt.cu", "sdes_rollo
 # the tensor-core rollout kernel is compiled once per padded state dimension (parallel builds, one object each)
 TC_DPADS = [8, 16, 32, 48, 56, 64]
 TC_SOURCE = "sdes_rollout_mma.cu"
-HEADERS = ["sdes_common.cuh", "sdes_step.cuh", "sdes_tc.cuh", "sdes_timeembed.cuh", "sdes_linear.cuh", os.path.join("..", "..", "include", "sdes_b200.h")]
+HEADERS = ["sdes_common.cuh", "sdes_step.cuh", "sdes_tc.cuh", "sdes_timeembed.cuh", "sdes_linear.cuh", "sdes_grad_fused.cuh", os.path.join("..", "..", "include", "sdes_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -5,7 +5,7 @@
 // the whole launch.  Nothing but the stored trajectory (200 B per row) is read from HBM and nothing but the final
 // gradients is written — the layer-by-layer path of sdes_grad.cu moves ~45 GB of operand images per training step.
 //
-// One CTA per SM, 18 warps: warp 0 lane 0 issues every MMA, warp 1 owns the TMEM allocation, warps 2-17 are the
+// One CTA per SM, 18 warps: warp 0 issues every MMA (converged, one elected lane), warp 1 owns the TMEM allocation, warps 2-17 are the
 // epilogue: TMEM lane quadrant = warp % 4 (thread = row), and the four warps of a quadrant share the row's 64 columns
 // (16 each) so that every hop of the per-tile dependency chain is short.  Shared memory (nh = 2, d <= 56):
 //     X (input rows, bf16 hi | lo)  28 KB     A1, A2 (hidden activations, kept for their weight gradients)  64 KB
@@ -21,7 +21,8 @@
 // read, which is what lets two ping-pong buffers serve the whole chain.
 // TMEM: 4 x 64 columns of weight-gradient accumulators (rows 0-63 / 64-127: contributions of the hi / lo half of delta),
 // 4 x 16 columns of column sums (bias gradients; the input layer's are d loss / d emb(s), flushed whenever the step
-// changes — items are step-major, so a CTA sees at most a few steps), 2 x 64 working accumulators.
+// changes — items are step-major, so a CTA sees at most a few steps), 3 x 64 working accumulators (the dgrad result and
+// two alternating recomputed pre-activations, so the next hop's recompute runs under the current hop's epilogue).
 #pragma once
 
 #include "sdes_linear.cuh"
@@ -77,18 +78,42 @@ __device__ __forceinline__ float2 gelu_grad2(float2 x) {
     return __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), g, r);
 }
 
-// ---- MMA issue (one thread).  D[128 rows, 64] = A (row image, K-major) x W image (N = 64 out features, K-major)
+// ---- MMA issue by a CONVERGED warp: every lane runs the (warp-uniform) descriptor arithmetic, one elected lane issues.
+// Issued from a divergent `if (lane == 0)` the compiler wraps every tcgen05.mma in an elect / branch loop and moves each
+// descriptor through R2UR (~10 instructions and a branch per MMA); here the operands stay in uniform registers.
+__device__ __forceinline__ void fl_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void fl_commit(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(tc::smem_u32(bar))
+        : "memory");
+}
+
+// D[128 rows, 64] = A (row image, K-major) x W image (N = 64 out features, K-major)
 __device__ __forceinline__ void fl_mma_rows_w(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, int nks) {
     const uint32_t idesc = tc::idesc_bf16(128, 64);
     const uint32_t w_lo = w_hi + 8192u;
+#pragma unroll
     for (int ks = 0; ks < nks; ++ks) {
         const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
         const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
         const uint64_t dbh = tc::smem_desc_kmajor(w_hi + (uint32_t)ks * 2048u, 1024u, 128u);
         const uint64_t dbl = tc::smem_desc_kmajor(w_lo + (uint32_t)ks * 2048u, 1024u, 128u);
-        mma_f16_ss(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);  // small terms first
-        mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
-        mma_f16_ss(tmem_d, dah, dbh, idesc, 1u);
+        fl_mma(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);  // small terms first
+        fl_mma(tmem_d, dah, dbl, idesc, 1u);
+        fl_mma(tmem_d, dah, dbh, idesc, 1u);
     }
 }
 // D[128 rows, 64 in features] = A (delta image, K = out features) x W: the forward image (n = out, k = in) read as an
@@ -97,14 +122,15 @@ __device__ __forceinline__ void fl_mma_rows_w(uint32_t tmem_d, uint32_t a_hi, ui
 __device__ __forceinline__ void fl_mma_rows_wt(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, int nks) {
     const uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 16);  // b_major = MN
     const uint32_t w_lo = w_hi + 8192u;
+#pragma unroll
     for (int ks = 0; ks < nks; ++ks) {
         const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
         const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
         const uint64_t dbh = tc::smem_desc_kmajor(w_hi + (uint32_t)ks * 256u, 128u, 1024u);
         const uint64_t dbl = tc::smem_desc_kmajor(w_lo + (uint32_t)ks * 256u, 128u, 1024u);
-        mma_f16_ss(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-        mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
-        mma_f16_ss(tmem_d, dah, dbh, idesc, 1u);
+        fl_mma(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+        fl_mma(tmem_d, dah, dbl, idesc, 1u);
+        fl_mma(tmem_d, dah, dbh, idesc, 1u);
     }
 }
 // dW[(hi | lo) out features, in features] += delta^T a over the tile's 128 rows, and the column sums of delta (wgrad_mma_kernel)
@@ -112,13 +138,14 @@ __device__ __forceinline__ void fl_mma_wgrad(uint32_t tmem_dw, uint32_t tmem_db,
                                              uint32_t ones, bool acc_dw, bool acc_db) {
     const uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 15) | (1u << 16), idesc1 = tc::idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
     const uint64_t dones = tc::smem_desc_kmajor(ones, 128u, 2048u);
+#pragma unroll
     for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
         const uint64_t da = tc::smem_desc_kmajor(delta + (uint32_t)ks * 256u, 128u, 2048u);
         const uint64_t dbh = tc::smem_desc_kmajor(act_hi + (uint32_t)ks * 256u, 128u, 2048u);
         const uint64_t dbl = tc::smem_desc_kmajor(act_lo + (uint32_t)ks * 256u, 128u, 2048u);
-        mma_f16_ss(tmem_dw, da, dbl, idesc, (acc_dw || ks > 0) ? 1u : 0u);
-        mma_f16_ss(tmem_dw, da, dbh, idesc, 1u);
-        mma_f16_ss(tmem_db, da, dones, idesc1, (acc_db || ks > 0) ? 1u : 0u);
+        fl_mma(tmem_dw, da, dbl, idesc, (acc_dw || ks > 0) ? 1u : 0u);
+        fl_mma(tmem_dw, da, dbh, idesc, 1u);
+        fl_mma(tmem_db, da, dones, idesc1, (acc_db || ks > 0) ? 1u : 0u);
     }
 }
 
@@ -145,7 +172,7 @@ __device__ __forceinline__ void fl_ld16(uint32_t taddr, float (&v)[16]) {
 template <int DPAD>
 __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_constant__ FusedLvArgs a) {
     extern __shared__ __align__(128) uint8_t fl_smem[];
-    __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone;
+    __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone, s_z;
     __shared__ uint32_t s_tmem;
     constexpr uint32_t XHALF = (uint32_t)(DPAD / 8) * 2048u, XBYTES = 2u * XHALF;
     constexpr int NKS_IN = (DPAD + 15) / 16;
@@ -172,8 +199,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
     if (tid == 0) {
         tc::mbar_init(&s_wfull, 1);
         tc::mbar_init(&s_acc, 1);
-        tc::mbar_init(&s_aready, 32 * FL_EPI_WARPS);
+        tc::mbar_init(&s_aready, FL_EPI_WARPS);  // one arrive per epilogue warp
         tc::mbar_init(&s_wdone, 1);
+        tc::mbar_init(&s_z, 1);
         tc::fence_mbar_init();
     }
     tc::fence_before();
@@ -184,9 +212,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
     const int64_t i0 = (int64_t)blockIdx.x * n_items / gridDim.x, i1 = (int64_t)(blockIdx.x + 1) * n_items / gridDim.x;
 
     if (warp == 0) {
-        if (lane == 0 && i1 > i0) {  // ---- control thread
-            tc::mbar_arrive_expect_tx(&s_wfull, (uint32_t)L * FL_W_BYTES);
-            for (int l = 0; l < L; ++l) tc::bulk_g2s(s_w + (size_t)l * FL_W_BYTES, a.w_img[l], FL_W_BYTES, &s_wfull);
+        if (i1 > i0) {  // ---- control warp (converged: see fl_mma)
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(&s_wfull, (uint32_t)L * FL_W_BYTES);
+                for (int l = 0; l < L; ++l) tc::bulk_g2s(s_w + (size_t)l * FL_W_BYTES, a.w_img[l], FL_W_BYTES, &s_wfull);
+            }
+            __syncwarp();
             tc::mbar_wait(&s_wfull, 0u);
             const uint32_t x_hi = tc::smem_u32(s_x), x_lo = x_hi + XHALF;
             const uint32_t act0 = tc::smem_u32(s_act), pb = tc::smem_u32(s_p), qb = tc::smem_u32(s_q), wb = tc::smem_u32(s_w);
@@ -207,47 +238,60 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 // ---- replayed forward
                 ready();
                 fl_mma_rows_w(tD, x_hi, x_lo, wb, NKS_IN);
-                tc::mma_commit(&s_acc);
+                fl_commit(&s_acc);
                 for (int l = 0; l < nh; ++l) {
                     ready();
                     const uint32_t ab = act0 + (uint32_t)l * A_BLOCK;
                     fl_mma_rows_w(tD, ab, ab + A_HALF, wb + (uint32_t)(1 + l) * FL_W_BYTES, 4);
-                    tc::mma_commit(&s_acc);
+                    fl_commit(&s_acc);
                 }
                 ready();
                 fl_mma_rows_w(tD, pb, pb + A_HALF, wb + (uint32_t)(nh + 1) * FL_W_BYTES, 4);
-                tc::mma_commit(&s_acc);
-                // ---- backward: output layer (cotangent in Q, a_{nh+1} in P)
+                fl_commit(&s_acc);
+                // z_{nh+1} = a_nh W_h[nh-1] for the first backward hop: runs while the epilogue builds the cotangent
+                {
+                    const uint32_t ab = act0 + (uint32_t)(nh - 1) * A_BLOCK;
+                    fl_mma_rows_w(tD2, ab, ab + A_HALF, wb + (uint32_t)nh * FL_W_BYTES, 4);
+                    fl_commit(&s_z);
+                }
+                // ---- backward: output layer (cotangent in Q, a_{nh+1} in P).  Its weight gradient goes first: the epilogue
+                //      overwrites P with delta_{nh+1}, and MMAs complete in order
                 ready();
                 fl_mma_wgrad(tmem_base + FL_COL_DW + 64u * (uint32_t)(nh + 1), tmem_base + FL_COL_DB + 16u * (uint32_t)(nh + 1), qb, pb, pb + A_HALF, ones,
                              !first, !first);
                 fl_mma_rows_wt(tD, qb, qb + A_HALF, wb + (uint32_t)(nh + 1) * FL_W_BYTES, NKS_IN);
-                {
-                    const uint32_t ab = act0 + (uint32_t)(nh - 1) * A_BLOCK;  // z_{nh+1} = a_nh W_h[nh-1]
-                    fl_mma_rows_w(tD2, ab, ab + A_HALF, wb + (uint32_t)nh * FL_W_BYTES, 4);
-                }
-                tc::mma_commit(&s_acc);
-                uint32_t cur = pb, other = qb;  // the epilogue writes delta_{nh+1} into P
-                for (int l = nh - 1; l >= 0; --l) {
-                    ready();  // delta_{l+2} is in `cur`
-                    const uint32_t ab = act0 + (uint32_t)l * A_BLOCK;  // a_{l+1}
-                    fl_mma_wgrad(tmem_base + FL_COL_DW + 64u * (uint32_t)(1 + l), tmem_base + FL_COL_DB + 16u * (uint32_t)(1 + l), cur, ab, ab + A_HALF, ones,
-                                 !first, !first);
-                    fl_mma_rows_wt(tD, cur, cur + A_HALF, wb + (uint32_t)(1 + l) * FL_W_BYTES, 4);
+                fl_commit(&s_acc);
+                uint32_t z_next = 1u;  // which recompute accumulator the NEXT hop reads
+                auto recompute = [&](int l) {  // z_{l+1} for the hop that produces delta_{l+1}
+                    const uint32_t tz = tD2 + 64u * z_next;
                     if (l > 0) {
                         const uint32_t pa = act0 + (uint32_t)(l - 1) * A_BLOCK;
-                        fl_mma_rows_w(tD2, pa, pa + A_HALF, wb + (uint32_t)l * FL_W_BYTES, 4);
+                        fl_mma_rows_w(tz, pa, pa + A_HALF, wb + (uint32_t)l * FL_W_BYTES, 4);
                     } else {
-                        fl_mma_rows_w(tD2, x_hi, x_lo, wb, NKS_IN);
+                        fl_mma_rows_w(tz, x_hi, x_lo, wb, NKS_IN);
                     }
-                    tc::mma_commit(&s_acc);
+                    fl_commit(&s_z);
+                    z_next ^= 1u;
+                };
+                recompute(nh - 1);
+                uint32_t cur = pb, other = qb;  // the epilogue writes delta_{nh+1} into P
+                for (int l = nh - 1; l >= 0; --l) {
+                    ready();  // delta_{l+2} is in `cur`; `other` was last read by MMAs issued before this hop's dgrad
+                    const uint32_t ab = act0 + (uint32_t)l * A_BLOCK;  // a_{l+1}
+                    fl_mma_rows_wt(tD, cur, cur + A_HALF, wb + (uint32_t)(1 + l) * FL_W_BYTES, 4);
+                    fl_commit(&s_acc);
+                    // off the critical path (they run while the epilogue works on this hop): the weight gradient of this
+                    // layer and the next hop's pre-activation
+                    fl_mma_wgrad(tmem_base + FL_COL_DW + 64u * (uint32_t)(1 + l), tmem_base + FL_COL_DB + 16u * (uint32_t)(1 + l), cur, ab, ab + A_HALF, ones,
+                                 !first, !first);
+                    if (l > 0) recompute(l - 1);
                     const uint32_t t = cur;
                     cur = other;
                     other = t;
                 }
                 ready();  // delta_1 is in `cur`
                 fl_mma_wgrad(tmem_base + FL_COL_DW, tmem_base + FL_COL_DB, cur, x_hi, x_lo, ones, !first, !new_step);
-                tc::mma_commit(&s_wdone);
+                fl_commit(&s_wdone);
                 first = false;
             }
         }
@@ -256,12 +300,13 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t tD = lane_base + FL_COL_D + (uint32_t)c_lo, tD2 = lane_base + FL_COL_D2 + (uint32_t)c_lo;
         const int64_t B = d.batch;
-        uint32_t ph_acc = 0u, ph_w = 0u;
+        uint32_t ph_acc = 0u, ph_w = 0u, ph_z = 0u;
         int prev_s = -1;
         auto arrive = [&]() {
             tc::fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor-core (async) proxy
             tc::fence_before();
-            mbar_arrive(&s_aready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_aready);  // 16 arrivals per hop instead of 512 serialised ones
         };
         auto wait_acc = [&]() {
             tc::mbar_wait(&s_acc, ph_acc);
@@ -312,38 +357,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             }
             arrive();
             const float* embb = a.embb + (int64_t)s * 64 + c_lo;
-            // ---- replayed forward: input layer, hidden layers
-            for (int l = 0; l <= nh; ++l) {
-                float bv[16];
-                if (l == 0) {
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = __ldg(reinterpret_cast<const float4*>(embb + e));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = *reinterpret_cast<const float4*>(s_bias + (l - 1) * 64 + c_lo + e);
-                }
-                wait_acc();
-                fl_ld16(tD, v);
-#pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    const float2 y = gelu_fast2(__fadd2_rn(make_float2(v[e], v[e + 1]), make_float2(bv[e], bv[e + 1])));
-                    v[e] = y.x;
-                    v[e + 1] = y.y;
-                }
-                fl_store16(l < nh ? s_act + (size_t)l * A_BLOCK : s_p, A_HALF, r, c_lo, v);
-                arrive();
-            }
-            // ---- output layer -> cotangent of the network output: w_b c_j 1[|NN_j| <= clip_model], c = eps sqrt(dt) (sigma beta_k eps)
-            {
-                const float* tab = a.tab + (int64_t)s * TAB_STRIDE;
-                const StepCoef c = make_step_coef(d, tab);
-                const float wb = valid ? __ldg(a.w + bb) : 0.f;
-                const float cscale = wb * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
-                const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
-                const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
-                float eps[16];
+            // the noise of the cotangent is drawn one quad of dimensions per forward hop, BEFORE that hop's wait: the ~130
+            // Philox / Box-Muller instructions run while the tensor pipe works on the layer
+            const float* tab = a.tab + (int64_t)s * TAB_STRIDE;
+            const StepCoef c = make_step_coef(d, tab);
+            const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
+            const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
+            float eps[16];
+            auto draw = [&](int hop) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
+                    if (qd % (nh + 2) != hop) continue;
                     const int j0 = c_lo + 4 * qd;
                     float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (j0 < dim) {
@@ -358,7 +382,35 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                     }
                     eps[4 * qd] = n4.x; eps[4 * qd + 1] = n4.y; eps[4 * qd + 2] = n4.z; eps[4 * qd + 3] = n4.w;
                 }
+            };
+            // ---- replayed forward: input layer, hidden layers
+            for (int l = 0; l <= nh; ++l) {
+                float bv[16];
+                if (l == 0) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = __ldg(reinterpret_cast<const float4*>(embb + e));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = *reinterpret_cast<const float4*>(s_bias + (l - 1) * 64 + c_lo + e);
+                }
+                draw(l);
+                wait_acc();
+                fl_ld16(tD, v);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 y = gelu_fast2(__fadd2_rn(make_float2(v[e], v[e + 1]), make_float2(bv[e], bv[e + 1])));
+                    v[e] = y.x;
+                    v[e + 1] = y.y;
+                }
+                fl_store16(l < nh ? s_act + (size_t)l * A_BLOCK : s_p, A_HALF, r, c_lo, v);
+                arrive();
+            }
+            // ---- output layer -> cotangent of the network output: w_b c_j 1[|NN_j| <= clip_model], c = eps sqrt(dt) (sigma beta_k eps)
+            {
+                const float wb = valid ? __ldg(a.w + bb) : 0.f;
+                const float cscale = wb * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
                 const float* bo = s_bias + nh * 64 + c_lo;
+                draw(nh + 1);
                 wait_acc();
                 fl_ld16(tD, v);
 #pragma unroll
@@ -372,6 +424,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             // ---- backward chain: delta_l = (delta_{l+1} W^T) * GELU'(z_l), z_l recomputed into the second accumulator
             uint8_t* dst = s_p;
             uint8_t* nxt = s_q;
+            uint32_t zsel = 0u;  // the two recompute accumulators alternate hop by hop
             for (int l = nh; l >= 0; --l) {  // produces delta_{l+1}
                 float bv[16], z[16];
                 if (l == 0) {
@@ -381,17 +434,26 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
 #pragma unroll
                     for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&bv[e]) = *reinterpret_cast<const float4*>(s_bias + (l - 1) * 64 + c_lo + e);
                 }
-                wait_acc();
-                tc::tmem_ld8(tD2, &z[0]);
-                tc::tmem_ld8(tD2 + 8u, &z[8]);
-                tc::tmem_ld8(tD, &v[0]);
-                tc::tmem_ld8(tD + 8u, &v[8]);
+                // the recomputed pre-activation was committed a whole hop ago: GELU'(z) — most of this hop's arithmetic — is
+                // evaluated while the tensor pipe still runs the hop's dgrad GEMM
+                tc::mbar_wait(&s_z, ph_z);
+                ph_z ^= 1u;
+                tc::fence_after();
+                tc::tmem_ld8(tD2 + 64u * zsel, &z[0]);
+                tc::tmem_ld8(tD2 + 64u * zsel + 8u, &z[8]);
+                zsel ^= 1u;
                 tc::wait_ld_tie<16>(z);
-                tc::wait_ld_tie<16>(v);
 #pragma unroll
                 for (int e = 0; e < 16; e += 2) {
                     const float2 g = gelu_grad2(__fadd2_rn(make_float2(z[e], z[e + 1]), make_float2(bv[e], bv[e + 1])));
-                    const float2 y = __fmul2_rn(make_float2(v[e], v[e + 1]), g);
+                    z[e] = g.x;
+                    z[e + 1] = g.y;
+                }
+                wait_acc();
+                fl_ld16(tD, v);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 y = __fmul2_rn(make_float2(v[e], v[e + 1]), make_float2(z[e], z[e + 1]));
                     v[e] = y.x;
                     v[e + 1] = y.y;
                 }
