@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             auto draw = [&](int hop) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
-                    if (qd % (nh + 2) != hop) continue;
+                    if ((qd < nh + 2 ? qd : qd - (nh + 2)) != hop) continue;  // quad -> forward hop, round robin
                     const int j0 = c_lo + 4 * qd;
                     float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (j0 < dim) {

@@ -118,10 +118,10 @@ __device__ __forceinline__ void issue_layer(const GroupCtx& c, uint32_t w_hi_sad
     tc::wait_st();
     tc::fence_before();
     group_bar(c.g);
-    if (c.gtid == c.issuer) {
+    if ((c.gtid >> 5) == (c.issuer >> 5)) {  // the whole issuing warp, converged: one elected lane issues (sdes_tc.cuh)
         tc::fence_after();
-        tc::issue_layer_bf16x3(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K16, N);
-        tc::mma_commit(c.bar);
+        tc::issue_layer_bf16x3_warp(c.t_d, c.t_hi, c.t_lo, w_hi_saddr, w_lo_saddr, K16, N);
+        tc::mma_commit_elect(c.bar);
     }
 }
 // ... and wait until the accumulator can be read

@@ -178,5 +178,40 @@ __device__ __forceinline__ void issue_layer_bf16x3(uint32_t tmem_d, uint32_t tme
     }
 }
 
+// The same issued by a CONVERGED warp: every lane runs the warp-uniform descriptor arithmetic, one elected lane issues.
+// From a divergent `if (lane == 0)` the compiler wraps each tcgen05.mma in an elect / branch loop (~10 instructions and a
+// branch per MMA); converged, the MMAs are straight-line predicated instructions.
+__device__ __forceinline__ void mma_f16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void issue_layer_bf16x3_warp(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
+                                                        uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K16, int N) {
+    const uint32_t id16 = idesc_bf16(128, N);
+    const uint32_t lbo = (uint32_t)N * 16u;
+    for (int s = 0; s < (K16 >> 4); ++s) {
+        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
+        mma_f16_ts_elect(tmem_d, tmem_a_lo + 8u * s, bh, id16, s > 0 ? 1u : 0u);
+        mma_f16_ts_elect(tmem_d, tmem_a_hi + 8u * s, bl, id16, 1u);
+        mma_f16_ts_elect(tmem_d, tmem_a_hi + 8u * s, bh, id16, 1u);
+    }
+}
+
 }  // namespace tc
 }  // namespace sdes
