@@ -133,6 +133,11 @@ typedef struct SdesRolloutDesc {
      * control paired with the step's noise — what d rnd_b / d gate(s) is for the log-variance losses.  A training forward
      * that keeps it spares sdes_rollout_lv_grad the re-evaluation of the target score (SdesLvGradDesc.gate_cot). */
     float* gate_cot;
+    /* Optional output of the same engine for the kl / kl_ito gradient, NULL = not wanted: score_keep, in the layout of xs
+     * (steps 0 .. T-1; honours SDES_F_TRAJ_TILED), holds the UNGATED score part of the control at every (step, trajectory,
+     * dimension): scale_score (sigma) clip(inner_j, clip_score).  With it sdes_rollout_kl_grad runs its whole reverse sweep
+     * as one persistent kernel (SdesLvGradDesc.score_keep) whenever the score term's x-derivative is local per dimension. */
+    float* score_keep;
 } SdesRolloutDesc;
 
 /* ABI version of the loaded library (== SDES_ABI_VERSION of the header it was built from). */
@@ -191,6 +196,8 @@ typedef struct SdesLvGradDesc {
     int64_t chunk_rows;      /* rows (trajectory, step) per pass; 0 = default (2^20) */
     const float* gate_cot;   /* lv, scalar gate, fused engines: (T, B) from the forward's SdesRolloutDesc.gate_cot, or NULL
                                 (the gate gradient is then recomputed from the target score) */
+    const float* score_keep; /* kl / kl_ito, tensor-core fused engine: the forward's SdesRolloutDesc.score_keep, or NULL
+                                (the sweep then runs step by step and re-evaluates the target score) */
 } SdesLvGradDesc;
 
 size_t sdes_lv_grad_workspace_bytes(const SdesRolloutDesc* desc, const SdesLvGradDesc* g);

@@ -66,7 +66,7 @@ class RolloutDesc(C.Structure):
         ("workspace", _fp), ("workspace_bytes", C.c_size_t),
         ("nice_couplings", C.c_int32), ("nice_mid", C.c_int32), ("nice_hidden", C.c_int32),
         ("nice_mask_config", C.c_int32), ("nice_params", _fp), ("n_nice_params", C.c_int64),
-        ("gate_cot", _fp),
+        ("gate_cot", _fp), ("score_keep", _fp),
     ]
 
 
@@ -75,7 +75,7 @@ class LvGradDesc(C.Structure):
     _fields_ = [
         ("struct_bytes", C.c_uint32), ("flags", C.c_uint32),
         ("xs", _fp), ("w", _fp), ("grad_params", _fp), ("grad_emb", _fp), ("grad_gate", _fp),
-        ("chunk_rows", C.c_int64), ("gate_cot", _fp),
+        ("chunk_rows", C.c_int64), ("gate_cot", _fp), ("score_keep", _fp),
     ]
 
 

@@ -50,7 +50,7 @@ class LvLoss(torch.autograd.Function):
         g_blob, g_emb, g_gate = engine.lv_grad(m["spec"], m["xs"], w, noise=m["noise"], seed=m["seed"],
                                                traj_offset=m["traj_offset"], engine=lo.engine,
                                                workspace=lo._workspace if wide else lo._grad_workspace, params=blob,
-                                               bptt=bptt, gate_cot=m.get("gate_cot"))
+                                               bptt=bptt, gate_cot=m.get("gate_cot"), score_keep=m.get("score_keep"))
         grads, o = [], 0
         for p in params:  # blob order (include/sdes_b200.h) == ctrl_parameters order
             grads.append(g_blob[o:o + p.numel()].reshape(p.shape))

@@ -160,6 +160,9 @@ static int validate(const SdesRolloutDesc* d, bool need_ptrs) {
     if (reinterpret_cast<uintptr_t>(d->workspace) % 256 != 0) return fail(-5, "workspace must be 256-byte aligned");
     if (d->gate_cot != nullptr && ((d->flags & SDES_F_MLP_SIMT) || wide_engine_needed(*d)))
         return fail(-3, "gate_cot is an output of the tensor-core fused engine only (d <= %d, no SDES_F_MLP_SIMT)", SDES_MAX_DIM);
+    if (d->score_keep != nullptr && ((d->flags & SDES_F_MLP_SIMT) || wide_engine_needed(*d)))
+        return fail(-3, "score_keep is an output of the tensor-core fused engine only (d <= %d, no SDES_F_MLP_SIMT)", SDES_MAX_DIM);
+    if (d->score_keep != nullptr && d->gate_cot != nullptr) return fail(-3, "gate_cot (lv) and score_keep (kl) are alternatives");
     return 0;
 }
 

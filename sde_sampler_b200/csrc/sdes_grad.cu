@@ -1587,16 +1587,24 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     // the whole pass as one persistent kernel (sdes_grad_fused.cuh) whenever its shapes allow; SDES_GRAD_LAYERWISE_SWEEP keeps
     // the layer-by-layer GEMM passes (A/B measurements, cross-check)
     const bool fused_lv = !bptt && !simt && lv_fused_supported(d) && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && (gate_from_fwd || !gate_wanted);
+    // kl / kl_ito: the same kernel walks each row tile backwards in time with the adjoint in registers, whenever the score
+    // part's x-derivative is local per dimension (no Hessian-vector product of the target: constant / detached target score, or
+    // a control without one), the forward kept the ungated score part (score_keep) and the gate is scalar or absent
+    const bool kl_target_in_ctrl = d.ctrl_kind == SDES_CTRL_SCORE || d.ctrl_kind == SDES_CTRL_LERP || d.ctrl_kind == SDES_CTRL_LERP_TARGET;
+    const bool kl_hvp = kl_target_in_ctrl && !(g.flags & (SDES_GRAD_TARGET_SCORE_CONST | SDES_GRAD_SCORE_DETACHED));
+    const bool fused_kl = bptt_tc && lv_fused_supported(d) && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && !kl_hvp &&
+                          (d.ctrl_kind == SDES_CTRL_CLIPPED || g.score_keep != nullptr) && (!gate_wanted || d.gate_dim == 1);
+    const bool fused_any = fused_lv || fused_kl;
     GRAD_CHECK(image(p.f_in, blob + kp.bl.in_w, d.dim, C, d.dim, 0));
     for (int l = 0; l < p.nh; ++l) {
         GRAD_CHECK(image(p.f_h[l], blob + kp.bl.h_w[l], C, C, C, 0));
         GRAD_CHECK(bias(p.f_h[l], blob + kp.bl.h_b[l], C));
-        if (!fused_lv) GRAD_CHECK(image(p.b_h[l], blob + kp.bl.h_w[l], C, C, C, 1));
+        if (!fused_any) GRAD_CHECK(image(p.b_h[l], blob + kp.bl.h_w[l], C, C, C, 1));
     }
     GRAD_CHECK(image(p.f_out, blob + kp.bl.out_w, C, d.dim, C, 0));
     GRAD_CHECK(bias(p.f_out, blob + kp.bl.out_b, d.dim));
-    if (!fused_lv) GRAD_CHECK(image(p.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));
-    if (bptt_tc) GRAD_CHECK(image(p.b_in, blob + kp.bl.in_w, d.dim, d.dim, C, 1));
+    if (!fused_any) GRAD_CHECK(image(p.b_out, blob + kp.bl.out_w, C, C, d.dim, 1));
+    if (bptt_tc && !fused_kl) GRAD_CHECK(image(p.b_in, blob + kp.bl.in_w, d.dim, d.dim, C, 1));
     GRAD_CHECK(cudaMemsetAsync(g.grad_params, 0, (size_t)d.n_params * 4, stream));
     GRAD_CHECK(cudaMemsetAsync(g.grad_emb, 0, (size_t)p.T * C * 4, stream));
     if (g.grad_gate != nullptr) GRAD_CHECK(cudaMemsetAsync(g.grad_gate, 0, (size_t)p.T * (d.gate_dim > 0 ? d.gate_dim : 1) * 4, stream));
@@ -1652,8 +1660,12 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         GRAD_CHECK(launch_adj(ca, tiles_per_step, true, stream));
         ++launches;
     }
-    if (fused_lv) {
+    if (fused_any) {
         FusedLvArgs fa;
+        fa.adj_init = fused_kl ? F(p.adj) : nullptr;
+        fa.score_keep = g.score_keep; fa.gate = fws + kp.ws.gate; fa.gate_stride = kp.ws.dpad;
+        fa.prior_loc = fws + kp.ws.prior; fa.prior_iv = fws + kp.ws.prior + kp.ws.dpad;
+        fa.grad_gate = (fused_kl && gate_wanted) ? g.grad_gate : nullptr; fa.gflags = g.flags;
         fa.d = d; fa.tab = fws + kp.ws.tab; fa.xs = g.xs; fa.w = g.w; fa.embb = F(p.embb);
         fa.nh = p.nh; fa.T = p.T; fa.tiles_per_step = tiles_per_step; fa.grad_emb = g.grad_emb;
         float* gp = g.grad_params;
@@ -1668,10 +1680,10 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         }
         fa.w_img[Lf - 1] = ws + p.f_out.w_off; fa.bias[Lf - 1] = F(p.f_out.b_off);
         fa.dw[Lf - 1] = gp + kp.bl.out_w; fa.db[Lf - 1] = gp + kp.bl.out_b; fa.ldw[Lf - 1] = C; fa.n_valid[Lf - 1] = d.dim; fa.k_valid[Lf - 1] = C;
-        GRAD_CHECK(launch_lv_fused(fa, sm_count > 0 ? sm_count : 148, stream));
+        GRAD_CHECK(launch_lv_fused(fa, fused_kl, sm_count > 0 ? sm_count : 148, stream));
         ++launches;
     }
-    for (int chi = 0; chi < (fused_lv ? 0 : p.n_chunks); ++chi) {
+    for (int chi = 0; chi < (fused_any ? 0 : p.n_chunks); ++chi) {
         const int ch = bptt_tc ? p.n_chunks - 1 - chi : chi;  // the sweep walks the chunks backwards in time
         const int s0 = ch * p.chunk_steps;
         const int ns = (s0 + p.chunk_steps <= p.T) ? p.chunk_steps : p.T - s0;

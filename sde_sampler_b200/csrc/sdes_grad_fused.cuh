@@ -53,6 +53,15 @@ struct FusedLvArgs {
     float* db[FL_MAX_LAYERS];                 // bias gradients of layers 1..nh+1 ([0]: NULL — the input layer's go to grad_emb)
     float* grad_emb;                          // (T, 64)
     int nh, T, tiles_per_step;
+    // kl / kl_ito (BPTT instantiation): the reverse sweep of sdes_grad.cu's adj_step_kernel inside the same kernel
+    const float* adj_init;                    // (Bp, 64) a_T = d loss / d x_T (adj_init_kernel)
+    const float* score_keep;                  // forward's ungated score part, layout of xs (NULL: control without a score part)
+    const float* gate;                        // (T, gate_stride) clip(score_model(s)) table of the prologue
+    const float* prior_loc;                   // prior / reference Gaussian of the control: loc | 1 / scale^2
+    const float* prior_iv;
+    float* grad_gate;                         // (T) scalar gate gradient or NULL
+    int gate_stride;
+    uint32_t gflags;                          // SDES_GRAD_*
 };
 
 // GELU'(x) = Phi(x) + x phi(x) of the exact-erf GELU, two values at a time: Phi from the logistic fit of gelu_fast2
@@ -169,7 +178,7 @@ __device__ __forceinline__ void fl_ld16(uint32_t taddr, float (&v)[16]) {
     tc::wait_ld_tie<16>(v);
 }
 
-template <int DPAD>
+template <int DPAD, bool BPTT>
 __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_constant__ FusedLvArgs a) {
     extern __shared__ __align__(128) uint8_t fl_smem[];
     __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone, s_z;
@@ -208,8 +217,22 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = s_tmem;
+    // lv: the (step, tile) items are independent — each CTA takes a contiguous step-major range.  kl: a tile's steps are a
+    // chain (the adjoint lives in registers from s = T-1 down to 0) — each CTA takes whole tiles, blockIdx.x + k gridDim.x.
     const int64_t n_items = (int64_t)a.T * a.tiles_per_step;
-    const int64_t i0 = (int64_t)blockIdx.x * n_items / gridDim.x, i1 = (int64_t)(blockIdx.x + 1) * n_items / gridDim.x;
+    int64_t i0, i1;
+    if (BPTT) {
+        const int my_tiles = a.tiles_per_step > (int)blockIdx.x ? (a.tiles_per_step - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        i0 = 0;
+        i1 = (int64_t)my_tiles * a.T;
+    } else {
+        i0 = (int64_t)blockIdx.x * n_items / gridDim.x;
+        i1 = (int64_t)(blockIdx.x + 1) * n_items / gridDim.x;
+    }
+    auto item_step = [&](int64_t item) -> int { return BPTT ? a.T - 1 - (int)(item % a.T) : (int)(item / a.tiles_per_step); };
+    auto item_tile = [&](int64_t item, int s) -> int {
+        return BPTT ? (int)blockIdx.x + (int)(item / a.T) * (int)gridDim.x : (int)(item - (int64_t)s * a.tiles_per_step);
+    };
 
     if (warp == 0) {
         if (i1 > i0) {  // ---- control warp (converged: see fl_mma)
@@ -232,7 +255,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 tc::fence_after();
             };
             for (int64_t item = i0; item < i1; ++item) {
-                const int s = (int)(item / a.tiles_per_step);
+                const int s = item_step(item);
                 const bool new_step = s != prev_s;
                 prev_s = s;
                 // ---- replayed forward
@@ -290,6 +313,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                     other = t;
                 }
                 ready();  // delta_1 is in `cur`
+                if (BPTT) {  // J_x NN^T delta: one more transposed layer, added to the adjoint by the epilogue
+                    fl_mma_rows_wt(tD, cur, cur + A_HALF, wb, 4);
+                    fl_commit(&s_acc);
+                }
                 fl_mma_wgrad(tmem_base + FL_COL_DW, tmem_base + FL_COL_DB, cur, x_hi, x_lo, ones, !first, !new_step);
                 fl_commit(&s_wdone);
                 first = false;
@@ -302,6 +329,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         const int64_t B = d.batch;
         uint32_t ph_acc = 0u, ph_w = 0u, ph_z = 0u;
         int prev_s = -1;
+        float adj[16];  // kl: this thread's 16 dimensions of a_{s+1} = d loss / d x_{s+1}
+#pragma unroll
+        for (int e = 0; e < 16; ++e) adj[e] = 0.f;
         auto arrive = [&]() {
             tc::fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor-core (async) proxy
             tc::fence_before();
@@ -322,10 +352,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             }
         };
         for (int64_t item = i0; item < i1; ++item) {
-            const int s = (int)(item / a.tiles_per_step), tile = (int)(item - (int64_t)s * a.tiles_per_step);
+            const int s = item_step(item), tile = item_tile(item, s);
             const int64_t b = (int64_t)tile * 128 + r;
             const bool valid = b < B;
             const int64_t bb = valid ? b : 0;
+            if (BPTT && s == a.T - 1) {  // a new tile: its terminal adjoint
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&adj[e]) = __ldg(reinterpret_cast<const float4*>(a.adj_init + b * 64 + c_lo + e));
+            }
             // ---- this thread's 16 features of the row (loads in flight while the previous item's last MMAs drain)
             float v[16];
             {
@@ -364,9 +398,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
             const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
             float eps[16];
+            const bool need_eps = !BPTT || (d.flags & SDES_F_COMPUTE_ITO) != 0;
             auto draw = [&](int hop) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
+                    if (!need_eps) {
+                        eps[4 * qd] = eps[4 * qd + 1] = eps[4 * qd + 2] = eps[4 * qd + 3] = 0.f;
+                        continue;
+                    }
                     if ((qd < nh + 2 ? qd : qd - (nh + 2)) != hop) continue;  // quad -> forward hop, round robin
                     const int j0 = c_lo + 4 * qd;
                     float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -413,10 +452,70 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 draw(nh + 1);
                 wait_acc();
                 fl_ld16(tD, v);
+                if (!BPTT) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float nn = v[e] + bo[e];
-                    v[e] = (c_lo + e < dim && fabsf(nn) <= c.cm) ? cscale * eps[e] : 0.f;  // d clip(NN) / d NN: 1 on [-c, c]
+                    for (int e = 0; e < 16; ++e) {
+                        const float nn = v[e] + bo[e];
+                        v[e] = (c_lo + e < dim && fabsf(nn) <= c.cm) ? cscale * eps[e] : 0.f;  // d clip(NN) / d NN: 1 on [-c, c]
+                    }
+                } else {
+                    // the reverse sweep's elementwise step (adj_step_kernel of sdes_grad.cu, per dimension): with a = a_{s+1},
+                    //   g = clip(NN) + gate * base,   q = w (cq g_m + ci eps),   delta = q + a Bc   (cotangent of the control),
+                    //   a <- A a  [+ q sigma / scale_prior^2: Euler-DDS reference control]  + (d score part / d x)^T delta
+                    // (the score part's own x-derivative is local here: prior score of the Lerp controls; a target score that is a
+                    // constant of the graph or detached) and + J_x NN^T (delta 1[|NN| <= clip_model]) after the last hop.
+                    const int ck = d.ctrl_kind;
+                    const bool dead = !(wb != 0.f);
+                    const bool score_detached = (a.gflags & SDES_GRAD_SCORE_DETACHED) != 0 || ck == SDES_CTRL_CLIPPED;
+                    const bool prior_in_ctrl = ck == SDES_CTRL_LERP || ck == SDES_CTRL_LERP_PRIOR;
+                    const bool has_score = ck != SDES_CTRL_CLIPPED && a.score_keep != nullptr;
+                    const float outer = (ck == SDES_CTRL_SCORE ? 1.0f : c.sigma) * d.scale_score;
+                    const float clip_edge = fabsf(outer) * d.clip_score;  // |base| of a clipped inner value
+                    const float a_mul = c.exp_int ? c.alpha_k : fmaf(c.mu, c.dt, 1.0f);
+                    const float wp = 1.0f - tab[TAB_LERP_W];
+                    const float* grow = a.gate + (int64_t)s * a.gate_stride + c_lo;
+                    const TrajRef kr = traj_ref(d, const_cast<float*>(has_score ? a.score_keep : a.xs), s, bb);
+                    const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
+                    float gsum = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j = c_lo + e;
+                        const bool in = j < dim;
+                        const float nn = v[e] + bo[e];
+                        const float base = (in && has_score && valid) ? __ldg(kr.p + (int64_t)j * kr.stride) : 0.f;
+                        const float gt = in ? __ldg(grow + e) : 0.f;
+                        const float iv = in ? __ldg(a.prior_iv + j) : 0.f;
+                        const float g = clipf(nn, c.cm) + base * gt;
+                        const float ap = adj[e];
+                        float dg, nx;
+                        if (c.exp_int) {
+                            dg = wb * (c.bb_ss * g + c.s_bk * eps[e]) + ap * c.bb_ss;
+                            nx = ap * a_mul;
+                        } else {
+                            float gm = g;
+                            if (c.ref_ctrl) {
+                                const float xj = (in && valid) ? __ldg(xr.p + (int64_t)j * xr.stride) : 0.f;
+                                gm = g - c.sigma * ((__ldg(a.prior_loc + (in ? j : 0)) - xj) * iv);
+                            }
+                            const float qj = wb * (gm * c.dt + eps[e] * c.sqrt_dt);
+                            dg = fmaf(ap, c.sigma * c.dt, qj);
+                            nx = ap * a_mul;
+                            if (c.ref_ctrl) nx = fmaf(qj, c.sigma * iv, nx);
+                        }
+                        if (dead || !in) dg = 0.f;
+                        gsum = fmaf(dg, base, gsum);
+                        if (!score_detached && prior_in_ctrl) {
+                            const float fac = (fabsf(base) != clip_edge) ? outer * gt * dg : 0.f;  // cotangent of inner_j (1 inside the clip)
+                            nx = fmaf(-wp * iv, fac, nx);
+                        }
+                        adj[e] = (dead || !valid || !in) ? 0.f : nx;
+                        v[e] = fabsf(nn) <= c.cm ? dg : 0.f;  // d clip(NN) / d NN
+                    }
+                    if (a.grad_gate != nullptr) {  // scalar gate: d loss / d gate(s) = 1[|gate| < clip] sum_b sum_j delta_j base_j
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+                        if (lane == 0 && gsum != 0.f && fabsf(__ldg(a.gate + (int64_t)s * a.gate_stride)) < c.cm) atomicAdd(a.grad_gate + s, gsum);
+                    }
                 }
                 fl_store16(s_q, A_HALF, r, c_lo, v);
                 arrive();
@@ -463,6 +562,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 dst = nxt;
                 nxt = t;
             }
+            if (BPTT) {  // a_s += J_x NN^T delta  (dimension columns of delta_1 W_in)
+                wait_acc();
+                fl_ld16(tD, v);
+                const bool dead = !(valid && __ldg(a.w + bb) != 0.f);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) adj[e] = (dead || c_lo + e >= dim) ? 0.f : adj[e] + v[e];
+                tc::fence_before();  // the next item's first GEMM overwrites this accumulator (ordered through the X hand-off)
+            }
         }
         // ---- the launch's accumulators -> global memory
         tc::mbar_wait(&s_wdone, ph_w);
@@ -498,31 +605,35 @@ static bool lv_fused_supported(const SdesRolloutDesc& d) {
     return d.dim <= 56 && d.n_hidden >= 1 && d.n_hidden <= 2 && lv_fused_smem_bytes(mma_pad_dim(d.dim), d.n_hidden) <= 232448u - 64u;
 }
 
-template <int DPAD>
+template <int DPAD, bool BPTT>
 static cudaError_t launch_lv_fused_t(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
     const size_t smem = lv_fused_smem_bytes(DPAD, a.nh);
     static size_t attr = 0;
     if (attr < smem) {
-        cudaError_t e = cudaFuncSetAttribute(lv_fused_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(lv_fused_kernel<DPAD, BPTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    const int64_t n_items = (int64_t)a.T * a.tiles_per_step;
+    const int64_t n_items = BPTT ? (int64_t)a.tiles_per_step : (int64_t)a.T * a.tiles_per_step;
     int grid = (int)(n_items < sm_count ? n_items : sm_count);
     if (grid < 1) grid = 1;
-    lv_fused_kernel<DPAD><<<grid, FL_THREADS, smem, stream>>>(a);
+    lv_fused_kernel<DPAD, BPTT><<<grid, FL_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_lv_fused(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
+template <bool BPTT>
+static cudaError_t launch_lv_fused_b(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
     switch (mma_pad_dim(a.d.dim)) {
-        case 8: return launch_lv_fused_t<8>(a, sm_count, stream);
-        case 16: return launch_lv_fused_t<16>(a, sm_count, stream);
-        case 32: return launch_lv_fused_t<32>(a, sm_count, stream);
-        case 48: return launch_lv_fused_t<48>(a, sm_count, stream);
-        case 56: return launch_lv_fused_t<56>(a, sm_count, stream);
+        case 8: return launch_lv_fused_t<8, BPTT>(a, sm_count, stream);
+        case 16: return launch_lv_fused_t<16, BPTT>(a, sm_count, stream);
+        case 32: return launch_lv_fused_t<32, BPTT>(a, sm_count, stream);
+        case 48: return launch_lv_fused_t<48, BPTT>(a, sm_count, stream);
+        case 56: return launch_lv_fused_t<56, BPTT>(a, sm_count, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+static cudaError_t launch_lv_fused(const FusedLvArgs& a, bool bptt, int sm_count, cudaStream_t stream) {
+    return bptt ? launch_lv_fused_b<true>(a, sm_count, stream) : launch_lv_fused_b<false>(a, sm_count, stream);
 }
 
 }  // namespace grad

@@ -425,7 +425,7 @@ template <int DPAD, int CTRL, int TGT, int MODE, bool QG>
 __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int q, const int step,
                                              const uint32_t traj, const LeanSmem& sm, const TgtGlobals& tg, const float* scd,
                                              const float* __restrict__ gate_row, const float* __restrict__ noise_row, float* xo,
-                                             const int xo_st, float2& cost2, float2& ito2, float2& qs2) {
+                                             const int xo_st, float2& cost2, float2& ito2, float2& qs2, float* sko) {
     const SdesRolloutDesc& d = p.d;
     float nn[8];
     tc::tmem_ld8(c.l_d + 8u * q, nn);
@@ -509,7 +509,14 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
             const float2 gt = *reinterpret_cast<const float2*>(gate_row + 2 * r);
             const float2 u2 = __fmul2_rn(inner, make_float2(k.outer, k.outer));  // the ungated score part
             g2 = __ffma2_rn(u2, gt, g2);
-            if (QG) qs2 = __ffma2_rn(u2, make_float2(e[2 * pp], e[2 * pp + 1]), qs2);  // d rnd / d gate of the lv losses (SdesRolloutDesc.gate_cot)
+            if (QG) {
+                if (sko != nullptr) {  // kl / kl_ito training forward: the ungated score part, kept for the reverse sweep (score_keep)
+                    if (2 * r < k.dim) sko[(2 * r) * xo_st] = u2.x;
+                    if (2 * r + 1 < k.dim) sko[(2 * r + 1) * xo_st] = u2.y;
+                } else {
+                    qs2 = __ffma2_rn(u2, make_float2(e[2 * pp], e[2 * pp + 1]), qs2);  // d rnd / d gate of the lv losses (SdesRolloutDesc.gate_cot)
+                }
+            }
         }
         float2 gm2 = g2;
         if (k.ref_ctrl) gm2 = __ffma2_rn(ps2, make_float2(-k.sigma, -k.sigma), g2);  // g - sigma * prior score  (solver/oc.py:305-306)
@@ -533,16 +540,17 @@ __device__ __forceinline__ void chunk_update(const KParams& p, const StepK& k, c
 template <int DPAD, int CTRL, int TGT, bool DENSE, bool QG>
 __device__ __forceinline__ void update_phase(const KParams& p, const StepK& k, const GroupCtx& c, const XPair& xs, const int step, const uint32_t traj,
                                              const LeanSmem& sm, const TgtGlobals& tg, const float* scd, const float* __restrict__ gate_row,
-                                             const float* __restrict__ noise_row, float* xo, const int xo_st, float2& cost2, float2& ito2, float2& qs2) {
+                                             const float* __restrict__ noise_row, float* xo, const int xo_st, float2& cost2, float2& ito2, float2& qs2,
+                                             float* sko) {
     if (DENSE) {
 #pragma unroll
         for (int q = 0; q < DPAD / 8; ++q)
-            if (8 * q < k.dim) chunk_update<DPAD, CTRL, TGT, 2, QG>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2);
+            if (8 * q < k.dim) chunk_update<DPAD, CTRL, TGT, 2, QG>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2, sko);
     } else {
-        chunk_update<DPAD, CTRL, TGT, 0, QG>(p, k, c, xs, 0, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2);
+        chunk_update<DPAD, CTRL, TGT, 0, QG>(p, k, c, xs, 0, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2, sko);
         const int nq = (k.dim + 7) >> 3;
 #pragma unroll 1
-        for (int q = 1; q < nq; ++q) chunk_update<DPAD, CTRL, TGT, 1, QG>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2);
+        for (int q = 1; q < nq; ++q) chunk_update<DPAD, CTRL, TGT, 1, QG>(p, k, c, xs, q, step, traj, sm, tg, scd, gate_row, noise_row, xo, xo_st, cost2, ito2, qs2, sko);
     }
 }
 
@@ -783,8 +791,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             wait_layer(c);
             // ---- network output streamed from TMEM into the control / cost / state update
             float2 qs2 = make_float2(0.f, 0.f);
-            const bool want_q = CTRL != SDES_CTRL_CLIPPED && d.gate_cot != nullptr;
-#define SDES_UPD(C_, Q_) update_phase<DPAD, C_, TGT, DENSE, Q_>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2, qs2)
+            const bool want_q = CTRL != SDES_CTRL_CLIPPED && (d.gate_cot != nullptr || d.score_keep != nullptr);
+            float* sko = (d.score_keep != nullptr && valid) ? traj_ref(d, d.score_keep, i, rrow).p : nullptr;
+#define SDES_UPD(C_, Q_) update_phase<DPAD, C_, TGT, DENSE, Q_>(p, k, c, xs, i, traj, lsm, tg, scd, gate_row, nrow, xo, xo_ref.stride, cost2, ito2, qs2, sko)
             if (CTRL == SDES_CTRL_LERP && !k.w_lt_half) {
                 if (want_q) SDES_UPD(CTRL_LERP_HI, true);
                 else SDES_UPD(CTRL_LERP_HI, false);
@@ -793,7 +802,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                 else SDES_UPD(CTRL, false);
             }
 #undef SDES_UPD
-            if (want_q && valid) d.gate_cot[(int64_t)i * B + rrow] = k.ito_scale * (qs2.x + qs2.y);
+            if (want_q && valid && d.gate_cot != nullptr) d.gate_cot[(int64_t)i * B + rrow] = k.ito_scale * (qs2.x + qs2.y);
             rnd = fmaf(k.cost_scale, cost2.x + cost2.y, rnd);
             if (d.flags & SDES_F_SUB_DIV_INT) rnd -= tab[TAB_DIV_INT];
             if (d.flags & SDES_F_COMPUTE_ITO) rnd = fmaf(k.ito_scale, ito2.x + ito2.y, rnd);

@@ -208,7 +208,8 @@ def tiled_traj_numel(T: int, B: int, dim: int) -> int:
 def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
             params: torch.Tensor | None = None, traj_tiled: bool = False, traj_buffer: Workspace | None = None,
-            keep_for_grad: bool = False, keep_score: bool = False, gate_cot: Workspace | None = None, out: dict | None = None):
+            keep_for_grad: bool = False, keep_score: bool = False, gate_cot: Workspace | None = None, out: dict | None = None,
+            score_keep: Workspace | None = None):
     """One fused rollout on x0's device.  Returns (x_T (B,d), rnd (B,1), xs (T+1,B,d) | None); with `traj_tiled`
     the trajectory comes back as a flat buffer in the row-tiled layout that `lv_grad` consumes."""
     lib = _cabi.lib()
@@ -264,6 +265,14 @@ def rollout(spec: RolloutSpec, x0: torch.Tensor, *, noise: torch.Tensor | None =
         d.gate_cot = gc.data_ptr()
         if out is not None:
             out["gate_cot"] = gc
+    if score_keep is not None and xs is not None and not is_wide(spec) and not (d.flags & _cabi.F_MLP_SIMT) \
+            and spec.ctrl["kind"] != "clipped":
+        # kl / kl_ito training forward on the tensor-core engine: keep the ungated score part of every (step, trajectory,
+        # dimension) in the layout of xs, so that the reverse sweep runs as one kernel (SdesRolloutDesc.score_keep)
+        sk = score_keep.get(4 * xs.numel(), device)[: 4 * xs.numel()].view(torch.float32)
+        d.score_keep = sk.data_ptr()
+        if out is not None:
+            out["score_keep"] = sk
     with torch.cuda.device(device):
         need = lib.sdes_workspace_bytes(C.byref(d))
         if need == 0:
@@ -297,7 +306,7 @@ def kl_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, **kw):
 def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torch.Tensor | None = None, seed: int = 0,
             traj_offset: int = 0, engine: str = "auto", workspace: Workspace | None = None,
             params: torch.Tensor | None = None, chunk_rows: int = 0, bptt: bool = False, grad_flags: int = 0,
-            gate_cot: torch.Tensor | None = None):
+            gate_cot: torch.Tensor | None = None, score_keep: torch.Tensor | None = None):
     """d loss / d theta of the log-variance loss for the rollout that produced `xs` (same spec / seed / traj_offset /
     noise).  Returns (grad_params blob, grad_emb (T,64), grad_gate (T,gate_dim) | None) — see include/sdes_b200.h
     `sdes_rollout_lv_grad`.  `bptt=True`: the kl / kl_ito gradient (`sdes_rollout_kl_grad`)."""
@@ -352,6 +361,10 @@ def lv_grad(spec: RolloutSpec, xs: torch.Tensor, w: torch.Tensor, *, noise: torc
         if gate_cot.numel() != T * B:
             raise ValueError("gate_cot must be (T, B)")
         g.gate_cot = gate_cot.data_ptr()
+    if score_keep is not None and bptt and not wide:
+        if score_keep.numel() != xs.numel():
+            raise ValueError("score_keep must have the layout (and size) of xs")
+        g.score_keep = score_keep.data_ptr()
     with torch.cuda.device(device):
         need = fn_bytes(C.byref(d), C.byref(g))
         if need == 0:

@@ -106,6 +106,7 @@ class FusedOCLoss:
         self._grad_workspace = engine_workspace()
         self._traj_buffer = engine_workspace()  # trajectory of the last training forward (row-tiled), reused across steps
         self._gate_cot_buffer = engine_workspace()  # (T, B) gate cotangent sums of the last training forward (lv losses)
+        self._score_keep_buffer = engine_workspace()  # ungated score part per (step, trajectory, dim) of the last kl / kl_ito forward
         self._traj_version = 0
         self._spec_cache: dict = {}
         _cabi.lib()  # fail now, not at the first step, if the CUDA library is missing
@@ -239,7 +240,8 @@ class FusedOCLoss:
             x_T, rnd, xs = engine.rollout(spec, x, noise=noise, seed=seed, traj_offset=off, engine=self.engine,
                                           workspace=self._workspace, traj_tiled=True, traj_buffer=self._traj_buffer,
                                           keep_for_grad=True, keep_score=self.method in ("kl", "kl_ito"),
-                                          gate_cot=self._gate_cot_buffer if self.method in ("lv", "lv_traj") else None, out=extra)
+                                          gate_cot=self._gate_cot_buffer if self.method in ("lv", "lv_traj") else None, out=extra,
+                                          score_keep=self._score_keep_buffer if self.method in ("kl", "kl_ito") else None)
             self._traj_version += 1
             if self.method == "lv_traj":
                 loss, metrics = self._compute_loss_lv_traj(rnd, x_T)
@@ -249,7 +251,8 @@ class FusedOCLoss:
                 loss, metrics = self._loss_from_stats(st)
             smask = None if self.filter_samples is None else self.filter_samples(x_T)
             out.update(loss=loss, metrics=metrics, stats=st, rnd=rnd, smask=smask, xs=xs, spec=spec, seed=seed,
-                       traj_offset=off, noise=noise, samples=x_T, traj_version=self._traj_version, gate_cot=extra.get("gate_cot"))
+                       traj_offset=off, noise=noise, samples=x_T, traj_version=self._traj_version, gate_cot=extra.get("gate_cot"),
+                       score_keep=extra.get("score_keep"))
             return out
 
         loss = LvLoss.apply(self, run, len(net.timestep_embed.hidden_layer), len(net.hidden_layer),

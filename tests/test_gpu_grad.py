@@ -163,6 +163,36 @@ def test_lv_fused_kernel_matches_layerwise_passes(golden, name, B):
         assert (a - c).abs().max().item() <= 1e-3 * scale + 1e-7, f"output {i}: {(a - c).abs().max().item():.3e} vs scale {scale:.3e}"
 
 
+@pytest.mark.parametrize("name,B", [("dis_gmm50_kl", 1000), ("dis_gmm50_kl", 33000), ("dis_lerpprior_multiwell4", 3000), ("dis_gmm2_kl", 130)])
+def test_kl_fused_kernel_matches_stepwise_sweep(golden, name, B):
+    """kl / kl_ito with the forward's score_keep: the whole reverse sweep as one persistent kernel (adjoint in registers, a
+    tile's steps walked backwards by one CTA) against the step-by-step sweep (one elementwise kernel + dgrad chain per step)
+    on the same stored trajectory — ragged last tile, more tiles than SMs, kl and kl_ito, Lerp and LerpPrior controls."""
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.engine import Workspace
+    from sde_sampler_b200.spec import extract_spec
+
+    g = golden(name)
+    b = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    d, T = g["x0"].shape[1], g["ts"].shape[0] - 1
+    x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(4))
+    spec = extract_spec(b["loss"], CASES[name]["loss"], b["ts"], b["terminal"], b["second"], train=True,
+                        compute_ito=CASES[name]["method"] == "kl_ito", return_traj=True)
+    out = {}
+    x_T, rnd, xs = eng.rollout(spec, x0, seed=5, engine="tcgen05", traj_tiled=True, score_keep=Workspace(), out=out)
+    w = torch.full((B,), 1.0 / B, device=_dev())
+    w[::7] = 0.0  # filtered trajectories
+    assert out.get("score_keep") is not None
+    fused = eng.kl_grad(spec, xs, w, seed=5, engine="tcgen05", score_keep=out["score_keep"])
+    step = eng.kl_grad(spec, xs, w, seed=5, engine="tcgen05")
+    for i, (a, c) in enumerate(zip(step, fused)):
+        if a is None:
+            assert c is None
+            continue
+        scale = a.abs().max().item()
+        assert (a - c).abs().max().item() <= 1e-3 * scale + 1e-7, f"output {i}: {(a - c).abs().max().item():.3e} vs scale {scale:.3e}"
+
+
 def test_kl_gradient_is_additive_over_shards_and_engine_independent(golden):
     """Size-independent properties of the BPTT gradient at 4 096 trajectories of the cfg-3 configuration (funnel d=10, PIS,
     kl): the gradient is linear in the per-trajectory weights, so two half-batch calls (global Philox counters via
