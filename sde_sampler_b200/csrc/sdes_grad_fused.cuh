@@ -195,11 +195,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
     uint8_t* s_w = s_q + A_BLOCK;                        // L weight images
     uint8_t* s_ones = s_w + (size_t)L * FL_W_BYTES;
     float* s_bias = reinterpret_cast<float*>(s_ones + FL_ONES_BYTES);  // [l - 1][64], l = 1 .. nh + 1
+    float* s_prior = s_bias + (nh + 1) * 64;                           // kl: prior loc[64] | 1 / scale^2 [64]
 
     // every operand buffer starts finite: padded k-steps multiply whatever lies there by zero weights
     for (uint32_t e = tid; e < (uint32_t)(s_w - fl_smem) / 16u; e += blockDim.x) reinterpret_cast<uint4*>(fl_smem)[e] = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t e = tid; e < FL_ONES_BYTES / 4u; e += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[e] = 0x3F803F80u;  // bf16 1.0 pairs
     for (int e = tid; e < (nh + 1) * 64; e += blockDim.x) s_bias[e] = a.bias[1 + e / 64][e % 64];
+    if (BPTT)
+        for (int e = tid; e < 128; e += blockDim.x) s_prior[e] = (e & 63) < dim ? (e < 64 ? a.prior_loc[e] : a.prior_iv[e - 64]) : 0.f;
     tc::fence_proxy_async();
     if (warp == 1) {
         tc::tmem_alloc(&s_tmem, 512u);
@@ -360,6 +363,20 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
 #pragma unroll
                 for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&adj[e]) = __ldg(reinterpret_cast<const float4*>(a.adj_init + b * 64 + c_lo + e));
             }
+            // kl: the kept score part of this row and the step's (scalar) gate, fetched now — the cotangent math after the output
+            // layer sits on the item's critical path and must not wait for HBM
+            float gate0 = 0.f;
+            const bool has_score = BPTT && d.ctrl_kind != SDES_CTRL_CLIPPED && a.score_keep != nullptr;
+            const TrajRef kr = traj_ref(d, const_cast<float*>(has_score ? a.score_keep : a.xs), s, bb);
+            if (BPTT) {
+                if (has_score && valid) {  // towards L2 now, into registers only right before the output layer's wait (16 live
+                                           // registers across the forward hops would spill)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c_lo + e < dim) asm volatile("prefetch.global.L2 [%0];" ::"l"(kr.p + (int64_t)(c_lo + e) * kr.stride));
+                }
+                gate0 = __ldg(a.gate + (int64_t)s * a.gate_stride);
+            }
             // ---- this thread's 16 features of the row (loads in flight while the previous item's last MMAs drain)
             float v[16];
             {
@@ -406,7 +423,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                         eps[4 * qd] = eps[4 * qd + 1] = eps[4 * qd + 2] = eps[4 * qd + 3] = 0.f;
                         continue;
                     }
-                    if ((qd < nh + 2 ? qd : qd - (nh + 2)) != hop) continue;  // quad -> forward hop, round robin
+                    // lv: quad -> forward hop, round robin.  kl: all four at the output hop (hop < 0) — the adjoint already
+                    // occupies 16 registers across the forward hops, and only kl_ito draws noise at all
+                    if (hop >= 0 && (BPTT || (qd < nh + 2 ? qd : qd - (nh + 2)) != hop)) continue;
                     const int j0 = c_lo + 4 * qd;
                     float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (j0 < dim) {
@@ -449,7 +468,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 const float wb = valid ? __ldg(a.w + bb) : 0.f;
                 const float cscale = wb * (c.exp_int ? c.sg * c.beta_k : c.sqrt_dt);
                 const float* bo = s_bias + nh * 64 + c_lo;
-                draw(nh + 1);
+                draw(BPTT ? -1 : nh + 1);
+                float kbase[16];
+                if (BPTT) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) kbase[e] = (has_score && valid && c_lo + e < dim) ? __ldg(kr.p + (int64_t)(c_lo + e) * kr.stride) : 0.f;
+                }
                 wait_acc();
                 fl_ld16(tD, v);
                 if (!BPTT) {
@@ -468,13 +492,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                     const bool dead = !(wb != 0.f);
                     const bool score_detached = (a.gflags & SDES_GRAD_SCORE_DETACHED) != 0 || ck == SDES_CTRL_CLIPPED;
                     const bool prior_in_ctrl = ck == SDES_CTRL_LERP || ck == SDES_CTRL_LERP_PRIOR;
-                    const bool has_score = ck != SDES_CTRL_CLIPPED && a.score_keep != nullptr;
                     const float outer = (ck == SDES_CTRL_SCORE ? 1.0f : c.sigma) * d.scale_score;
                     const float clip_edge = fabsf(outer) * d.clip_score;  // |base| of a clipped inner value
                     const float a_mul = c.exp_int ? c.alpha_k : fmaf(c.mu, c.dt, 1.0f);
                     const float wp = 1.0f - tab[TAB_LERP_W];
-                    const float* grow = a.gate + (int64_t)s * a.gate_stride + c_lo;
-                    const TrajRef kr = traj_ref(d, const_cast<float*>(has_score ? a.score_keep : a.xs), s, bb);
                     const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
                     float gsum = 0.f;
 #pragma unroll
@@ -482,9 +503,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                         const int j = c_lo + e;
                         const bool in = j < dim;
                         const float nn = v[e] + bo[e];
-                        const float base = (in && has_score && valid) ? __ldg(kr.p + (int64_t)j * kr.stride) : 0.f;
-                        const float gt = in ? __ldg(grow + e) : 0.f;
-                        const float iv = in ? __ldg(a.prior_iv + j) : 0.f;
+                        const float base = kbase[e];
+                        const float gt = in ? gate0 : 0.f;  // scalar gate (or the constant 1 of a control without one), 0 on padding
+                        const float iv = s_prior[64 + j];
                         const float g = clipf(nn, c.cm) + base * gt;
                         const float ap = adj[e];
                         float dg, nx;
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                             float gm = g;
                             if (c.ref_ctrl) {
                                 const float xj = (in && valid) ? __ldg(xr.p + (int64_t)j * xr.stride) : 0.f;
-                                gm = g - c.sigma * ((__ldg(a.prior_loc + (in ? j : 0)) - xj) * iv);
+                                gm = g - c.sigma * ((s_prior[j] - xj) * iv);
                             }
                             const float qj = wb * (gm * c.dt + eps[e] * c.sqrt_dt);
                             dg = fmaf(ap, c.sigma * c.dt, qj);
@@ -514,7 +535,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                     if (a.grad_gate != nullptr) {  // scalar gate: d loss / d gate(s) = 1[|gate| < clip] sum_b sum_j delta_j base_j
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-                        if (lane == 0 && gsum != 0.f && fabsf(__ldg(a.gate + (int64_t)s * a.gate_stride)) < c.cm) atomicAdd(a.grad_gate + s, gsum);
+                        if (lane == 0 && gsum != 0.f && fabsf(gate0) < c.cm) atomicAdd(a.grad_gate + s, gsum);
                     }
                 }
                 fl_store16(s_q, A_HALF, r, c_lo, v);
@@ -598,7 +619,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
 }
 
 static size_t lv_fused_smem_bytes(int dpad, int nh) {
-    return (size_t)2 * (dpad / 8) * 2048 + (size_t)(nh + 2) * A_BLOCK + (size_t)(nh + 2) * FL_W_BYTES + FL_ONES_BYTES + (size_t)(nh + 1) * 256;
+    return (size_t)2 * (dpad / 8) * 2048 + (size_t)(nh + 2) * A_BLOCK + (size_t)(nh + 2) * FL_W_BYTES + FL_ONES_BYTES + (size_t)(nh + 1) * 256 + 512;
 }
 // the shapes the fused kernel serves: d <= 56 (input image + buffers fit 227 KB), one or two hidden layers
 static bool lv_fused_supported(const SdesRolloutDesc& d) {

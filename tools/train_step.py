@@ -11,11 +11,13 @@ from sde_sampler_b200.spec import ctrl_parameters
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--method", default="lv")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 W = bench.WORKLOADS["gmm50"]
 o = build_from_spec(bench.load_spec(W), dev, engine="auto", seed=1234, sync_metrics=False)
 x0 = bench.sample_x0(W["x0"], args.batch, 50, dev, 100)
+o["loss"].method = args.method
 ms = []
 for k in range(args.reps):
     for p in ctrl_parameters(o["ctrl"]):
