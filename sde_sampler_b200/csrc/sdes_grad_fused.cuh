@@ -178,8 +178,10 @@ __device__ __forceinline__ void fl_ld16(uint32_t taddr, float (&v)[16]) {
     tc::wait_ld_tie<16>(v);
 }
 
-template <int DPAD, bool BPTT>
+// MODE 0: lv.  MODE 1: kl (no noise in the cotangent).  MODE 2: kl_ito.
+template <int DPAD, int MODE>
 __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_constant__ FusedLvArgs a) {
+    constexpr bool BPTT = MODE != 0;
     extern __shared__ __align__(128) uint8_t fl_smem[];
     __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone, s_z;
     __shared__ uint32_t s_tmem;
@@ -354,6 +356,15 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 if (v[0] != 0.f) atomicAdd(a.grad_emb + (int64_t)s_prev * 64 + (r & 63), v[0]);  // hi row and lo row both add
             }
         };
+        float xnext[16];
+        auto load_x = [&](int64_t it, float (&xv)[16]) {
+            const int s2 = item_step(it), tile2 = item_tile(it, s2);
+            const int64_t b2 = (int64_t)tile2 * 128 + r;
+            const bool valid2 = b2 < B;
+            const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s2, valid2 ? b2 : 0);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) xv[e] = (valid2 && c_lo + e < dim) ? __ldg(xr.p + (int64_t)(c_lo + e) * xr.stride) : 0.f;
+        };
         for (int64_t item = i0; item < i1; ++item) {
             const int s = item_step(item), tile = item_tile(item, s);
             const int64_t b = (int64_t)tile * 128 + r;
@@ -369,21 +380,20 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             const bool has_score = BPTT && d.ctrl_kind != SDES_CTRL_CLIPPED && a.score_keep != nullptr;
             const TrajRef kr = traj_ref(d, const_cast<float*>(has_score ? a.score_keep : a.xs), s, bb);
             if (BPTT) {
-                if (has_score && valid) {  // towards L2 now, into registers only right before the output layer's wait (16 live
-                                           // registers across the forward hops would spill)
+                gate0 = __ldg(a.gate + (int64_t)s * a.gate_stride);
+                if (s > 0 && valid) {  // the next item of this tile: rows of x_{s-1}
+                    const TrajRef xp = traj_ref(d, const_cast<float*>(a.xs), s - 1, bb);
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (c_lo + e < dim) asm volatile("prefetch.global.L2 [%0];" ::"l"(kr.p + (int64_t)(c_lo + e) * kr.stride));
+                        if (c_lo + e < dim) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp.p + (int64_t)(c_lo + e) * xp.stride));
                 }
-                gate0 = __ldg(a.gate + (int64_t)s * a.gate_stride);
             }
-            // ---- this thread's 16 features of the row (loads in flight while the previous item's last MMAs drain)
+            // ---- this thread's 16 features of the row: fetched at the END of the previous item (load_x below), so that the HBM
+            //      latency runs under that item's last tensor phases
             float v[16];
-            {
-                const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
+            if (BPTT || item == i0) load_x(item, xnext);  // (kl: 16 more live registers across the last hop would spill — L2 prefetch instead)
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = (valid && c_lo + e < dim) ? __ldg(xr.p + (int64_t)(c_lo + e) * xr.stride) : 0.f;
-            }
+            for (int e = 0; e < 16; ++e) v[e] = xnext[e];
             if (item > i0) {
                 tc::mbar_wait(&s_wdone, ph_w);  // X (and P / Q) are free again
                 ph_w ^= 1u;
@@ -391,6 +401,19 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 if (s != prev_s) flush_emb(prev_s);
             }
             prev_s = s;
+            if (BPTT && has_score && valid) {
+                // the kept score part of this row goes global -> shared asynchronously, into the 64 bytes of Q this thread will
+                // overwrite with its cotangent anyway (its two 16-byte groups of both halves): no registers held across the
+                // forward hops, no exposed HBM latency at the cotangent
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    if (c_lo + e < dim) {
+                        const uint32_t dst = tc::smem_u32(s_q + (uint32_t)((((c_lo >> 3) + ((e >> 2) & 1)) * 128 + r) * 16) + ((e >> 3) ? A_HALF : 0u) + 4u * (e & 3));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(kr.p + (int64_t)(c_lo + e) * kr.stride) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             if (c_lo < DPAD) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
@@ -415,7 +438,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
             const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
             float eps[16];
-            const bool need_eps = !BPTT || (d.flags & SDES_F_COMPUTE_ITO) != 0;
+            constexpr bool need_eps = MODE != 1;
             auto draw = [&](int hop) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
@@ -472,7 +495,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 float kbase[16];
                 if (BPTT) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) kbase[e] = (has_score && valid && c_lo + e < dim) ? __ldg(kr.p + (int64_t)(c_lo + e) * kr.stride) : 0.f;
+                    for (int e = 0; e < 16; ++e) kbase[e] = 0.f;
+                    if (has_score && valid) {
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(s_q + (uint32_t)((((c_lo >> 3) + ((e >> 2) & 1)) * 128 + r) * 16) + ((e >> 3) ? A_HALF : 0u));
+                            kbase[e] = t4.x; kbase[e + 1] = t4.y; kbase[e + 2] = t4.z; kbase[e + 3] = t4.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) kbase[e] = (c_lo + e < dim) ? kbase[e] : 0.f;
+                    }
                 }
                 wait_acc();
                 fl_ld16(tD, v);
@@ -583,6 +616,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 dst = nxt;
                 nxt = t;
             }
+            if (!BPTT && item + 1 < i1) load_x(item + 1, xnext);
             if (BPTT) {  // a_s += J_x NN^T delta  (dimension columns of delta_1 W_in)
                 wait_acc();
                 fl_ld16(tD, v);
@@ -626,35 +660,36 @@ static bool lv_fused_supported(const SdesRolloutDesc& d) {
     return d.dim <= 56 && d.n_hidden >= 1 && d.n_hidden <= 2 && lv_fused_smem_bytes(mma_pad_dim(d.dim), d.n_hidden) <= 232448u - 64u;
 }
 
-template <int DPAD, bool BPTT>
+template <int DPAD, int MODE>
 static cudaError_t launch_lv_fused_t(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
     const size_t smem = lv_fused_smem_bytes(DPAD, a.nh);
     static size_t attr = 0;
     if (attr < smem) {
-        cudaError_t e = cudaFuncSetAttribute(lv_fused_kernel<DPAD, BPTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(lv_fused_kernel<DPAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    const int64_t n_items = BPTT ? (int64_t)a.tiles_per_step : (int64_t)a.T * a.tiles_per_step;
+    const int64_t n_items = MODE != 0 ? (int64_t)a.tiles_per_step : (int64_t)a.T * a.tiles_per_step;
     int grid = (int)(n_items < sm_count ? n_items : sm_count);
     if (grid < 1) grid = 1;
-    lv_fused_kernel<DPAD, BPTT><<<grid, FL_THREADS, smem, stream>>>(a);
+    lv_fused_kernel<DPAD, MODE><<<grid, FL_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <bool BPTT>
-static cudaError_t launch_lv_fused_b(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
+template <int MODE>
+static cudaError_t launch_lv_fused_m(const FusedLvArgs& a, int sm_count, cudaStream_t stream) {
     switch (mma_pad_dim(a.d.dim)) {
-        case 8: return launch_lv_fused_t<8, BPTT>(a, sm_count, stream);
-        case 16: return launch_lv_fused_t<16, BPTT>(a, sm_count, stream);
-        case 32: return launch_lv_fused_t<32, BPTT>(a, sm_count, stream);
-        case 48: return launch_lv_fused_t<48, BPTT>(a, sm_count, stream);
-        case 56: return launch_lv_fused_t<56, BPTT>(a, sm_count, stream);
+        case 8: return launch_lv_fused_t<8, MODE>(a, sm_count, stream);
+        case 16: return launch_lv_fused_t<16, MODE>(a, sm_count, stream);
+        case 32: return launch_lv_fused_t<32, MODE>(a, sm_count, stream);
+        case 48: return launch_lv_fused_t<48, MODE>(a, sm_count, stream);
+        case 56: return launch_lv_fused_t<56, MODE>(a, sm_count, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 static cudaError_t launch_lv_fused(const FusedLvArgs& a, bool bptt, int sm_count, cudaStream_t stream) {
-    return bptt ? launch_lv_fused_b<true>(a, sm_count, stream) : launch_lv_fused_b<false>(a, sm_count, stream);
+    if (!bptt) return launch_lv_fused_m<0>(a, sm_count, stream);
+    return (a.d.flags & SDES_F_COMPUTE_ITO) ? launch_lv_fused_m<2>(a, sm_count, stream) : launch_lv_fused_m<1>(a, sm_count, stream);
 }
 
 }  // namespace grad
