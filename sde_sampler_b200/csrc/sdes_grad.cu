@@ -19,6 +19,8 @@
 #include <cuda_bf16.h>
 
 #include <cstdlib>
+#include <cstdio>
+#include <vector>
 
 #include "sdes_linear.cuh"
 #include "sdes_step.cuh"
@@ -40,6 +42,7 @@ struct GradPlan {
     Lin b_h[SDES_MAX_HIDDEN], b_out;         // transposed operands (dgrad)
     Lin b_in;                                // kl sweep: transposed input layer (dgrad down to x)
     int64_t adj;                             // kl sweep: the adjoint a_s = d loss / d x_s, fp32 (Bp, P)
+    int64_t kl_flags;                        // one-kernel kl sweep: per-tile hand-off counters (uint32)
     int64_t dh_all[SDES_MAX_HIDDEN + 1];     // kl sweep: one delta_h image per layer for the whole chunk
     int64_t embb;                            // (T, 64): timestep_embed(s) + b_in
     int64_t ximg, a_img[SDES_MAX_HIDDEN + 1], gp_img[SDES_MAX_HIDDEN + 1], nn, dnn_img, dh_img[2], ones;
@@ -86,9 +89,11 @@ static void make_plan(const SdesRolloutDesc& d, int64_t chunk_rows_req, int64_t 
     p.dh_img[0] = take(img1);
     p.dh_img[1] = take(img1);
     p.adj = -1;
+    p.kl_flags = -1;
     if (bptt_tc) {
         lin(p.b_in, p.P, C, false);
         p.adj = take(p.Bp * (int64_t)p.P * 4);
+        p.kl_flags = take(p.Bp / 128 * 4 + 4096);  // + a small record area for the hand-off watchdog
         p.dh_all[0] = p.dh_img[0];
         p.dh_all[1] = p.dh_img[1];
         for (int l = 2; l <= p.nh; ++l) p.dh_all[l] = take(img1);
@@ -1663,6 +1668,8 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     if (fused_any) {
         FusedLvArgs fa;
         fa.adj_init = fused_kl ? F(p.adj) : nullptr;
+        fa.kl_flags = fused_kl ? reinterpret_cast<uint32_t*>(ws + p.kl_flags) : nullptr;
+        if (fused_kl) GRAD_CHECK(cudaMemsetAsync(ws + p.kl_flags, 0, (size_t)tiles_per_step * 4 + 4096, stream));
         fa.score_keep = g.score_keep; fa.gate = fws + kp.ws.gate; fa.gate_stride = kp.ws.dpad;
         fa.prior_loc = fws + kp.ws.prior; fa.prior_iv = fws + kp.ws.prior + kp.ws.dpad;
         fa.grad_gate = (fused_kl && gate_wanted) ? g.grad_gate : nullptr; fa.gflags = g.flags;
@@ -1682,6 +1689,14 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         fa.dw[Lf - 1] = gp + kp.bl.out_w; fa.db[Lf - 1] = gp + kp.bl.out_b; fa.ldw[Lf - 1] = C; fa.n_valid[Lf - 1] = d.dim; fa.k_valid[Lf - 1] = C;
         GRAD_CHECK(launch_lv_fused(fa, fused_kl, sm_count > 0 ? sm_count : 148, stream));
         ++launches;
+        if (fused_kl && getenv("SDES_FL_DEBUG")) {
+            std::vector<uint32_t> rec(1024);
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(rec.data(), ws + p.kl_flags + (size_t)tiles_per_step * 4, 4096, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "lv_fused kl watchdog records: %u\n", rec[0]);
+            for (uint32_t i = 0; i < rec[0] && i < 200; ++i)
+                    fprintf(stderr, "  REC cta %u who %u code %u item %u\n", rec[4 + 4 * i], rec[5 + 4 * i], rec[6 + 4 * i], rec[7 + 4 * i]);
+        }
     }
     for (int chi = 0; chi < (fused_any ? 0 : p.n_chunks); ++chi) {
         const int ch = bptt_tc ? p.n_chunks - 1 - chi : chi;  // the sweep walks the chunks backwards in time

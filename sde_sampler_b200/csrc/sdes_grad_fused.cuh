@@ -25,6 +25,9 @@
 // two alternating recomputed pre-activations, so the next hop's recompute runs under the current hop's epilogue).
 #pragma once
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "sdes_linear.cuh"
 #include "sdes_step.cuh"
 
@@ -54,7 +57,9 @@ struct FusedLvArgs {
     float* grad_emb;                          // (T, 64)
     int nh, T, tiles_per_step;
     // kl / kl_ito (BPTT instantiation): the reverse sweep of sdes_grad.cu's adj_step_kernel inside the same kernel
-    const float* adj_init;                    // (Bp, 64) a_T = d loss / d x_T (adj_init_kernel)
+    float* adj_init;                          // (Bp, 64) a_T = d loss / d x_T (adj_init_kernel); a tile's adjoint at the half-way step
+                                              // is handed from its late to its early half through the same rows
+    uint32_t* kl_flags;                       // (tiles) zeroed by the launcher: epilogue warps that have parked the tile's adjoint
     const float* score_keep;                  // forward's ungated score part, layout of xs (NULL: control without a score part)
     const float* gate;                        // (T, gate_stride) clip(score_model(s)) table of the prologue
     const float* prior_loc;                   // prior / reference Gaussian of the control: loc | 1 / scale^2
@@ -108,6 +113,44 @@ __device__ __forceinline__ void fl_commit(uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
         "}" ::"r"(tc::smem_u32(bar))
         : "memory");
+}
+
+// mbarrier wait with a watchdog for the kl instantiations (their CTAs wait on each other): after ~3 s of failed polls the
+// waiter records (CTA, warp, wait site, item), raises the launch-wide abort word and every wait returns at once — the kernel
+// ends with a wrong result that the host reports (SDES_FL_DEBUG) instead of hanging the device.
+__device__ __forceinline__ void fl_wait(uint64_t* bar, uint32_t parity, uint32_t* dbg, uint32_t code, uint32_t item) {
+    if (dbg == nullptr) {
+        tc::mbar_wait(bar, parity);
+        return;
+    }
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if ((spins & 255u) == 255u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            const bool aborted = *reinterpret_cast<volatile uint32_t*>(dbg + 1) != 0u;
+            if (aborted || now - t0 > 3000000000ull) {
+                if (!aborted && (threadIdx.x & 31) == 0) {
+                    const uint32_t slot = atomicAdd(dbg, 1u);
+                    if (slot < 200u) {
+                        uint32_t* rec = dbg + 4 + 4 * slot;
+                        rec[0] = blockIdx.x; rec[1] = 1000u + (threadIdx.x >> 5); rec[2] = code; rec[3] = item;
+                    }
+                    *reinterpret_cast<volatile uint32_t*>(dbg + 1) = 1u;
+                }
+                return;
+            }
+        }
+    }
 }
 
 // D[128 rows, 64] = A (row image, K-major) x W image (N = 64 out features, K-major)
@@ -183,7 +226,7 @@ template <int DPAD, int MODE>
 __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_constant__ FusedLvArgs a) {
     constexpr bool BPTT = MODE != 0;
     extern __shared__ __align__(128) uint8_t fl_smem[];
-    __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone, s_z;
+    __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone, s_z[2];
     __shared__ uint32_t s_tmem;
     constexpr uint32_t XHALF = (uint32_t)(DPAD / 8) * 2048u, XBYTES = 2u * XHALF;
     constexpr int NKS_IN = (DPAD + 15) / 16;
@@ -215,29 +258,62 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         tc::mbar_init(&s_acc, 1);
         tc::mbar_init(&s_aready, FL_EPI_WARPS);  // one arrive per epilogue warp
         tc::mbar_init(&s_wdone, 1);
-        tc::mbar_init(&s_z, 1);
+        tc::mbar_init(&s_z[0], 1);
+        tc::mbar_init(&s_z[1], 1);
         tc::fence_mbar_init();
     }
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = s_tmem;
-    // lv: the (step, tile) items are independent — each CTA takes a contiguous step-major range.  kl: a tile's steps are a
-    // chain (the adjoint lives in registers from s = T-1 down to 0) — each CTA takes whole tiles, blockIdx.x + k gridDim.x.
+    uint32_t* dbg = BPTT ? a.kl_flags + a.tiles_per_step : nullptr;  // watchdog record area (fl_wait)
+    // lv: the (step, tile) items are independent — each CTA takes a contiguous step-major range.
+    // kl: a tile's steps are a chain (the adjoint lives in registers while the tile walks backwards in time).  512 tiles do not
+    // divide by 148 CTAs, so each chain is cut in two UNITS — the late half (s = T-1 .. Th) and the early half (Th-1 .. 0) —
+    // and unit u = half * tiles + tile goes to CTA u mod gridDim.x: every CTA runs its late units first, then its early ones,
+    // which wait (flag, acquire) for the adjoint the tile's late half parked in HBM.  A late unit never waits and all CTAs are
+    // resident (grid <= SM count, one CTA per SM), so there is no deadlock.
     const int64_t n_items = (int64_t)a.T * a.tiles_per_step;
+    const int G = (int)gridDim.x, bx = (int)blockIdx.x, tiles = a.tiles_per_step;
+    const int Th = a.T / 2, L0 = a.T - Th, L1 = Th;  // steps of a late / early unit
+    const int n_units = BPTT ? (2 * tiles > bx ? (2 * tiles - bx + G - 1) / G : 0) : 0;
+    const int n_late = BPTT ? (tiles > bx ? (tiles - bx + G - 1) / G : 0) : 0;
     int64_t i0, i1;
     if (BPTT) {
-        const int my_tiles = a.tiles_per_step > (int)blockIdx.x ? (a.tiles_per_step - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         i0 = 0;
-        i1 = (int64_t)my_tiles * a.T;
+        i1 = (int64_t)n_late * L0 + (int64_t)(n_units - n_late) * L1;
     } else {
-        i0 = (int64_t)blockIdx.x * n_items / gridDim.x;
-        i1 = (int64_t)(blockIdx.x + 1) * n_items / gridDim.x;
+        i0 = (int64_t)bx * n_items / G;
+        i1 = (int64_t)(bx + 1) * n_items / G;
     }
-    auto item_step = [&](int64_t item) -> int { return BPTT ? a.T - 1 - (int)(item % a.T) : (int)(item / a.tiles_per_step); };
-    auto item_tile = [&](int64_t item, int s) -> int {
-        return BPTT ? (int)blockIdx.x + (int)(item / a.T) * (int)gridDim.x : (int)(item - (int64_t)s * a.tiles_per_step);
+    struct Item { int s, tile; bool first, last, late; };
+    auto decode = [&](int64_t item) -> Item {
+        Item it;
+        if (!BPTT) {
+            it.s = (int)(item / tiles);
+            it.tile = (int)(item - (int64_t)it.s * tiles);
+            it.first = it.last = it.late = false;
+            return it;
+        }
+        const int64_t late_items = (int64_t)n_late * L0;
+        int k, pos, len;
+        if (item < late_items) {
+            k = (int)(item / L0); pos = (int)(item - (int64_t)k * L0); len = L0; it.late = true;
+            it.s = a.T - 1 - pos;
+        } else {
+            const int64_t e = item - late_items;
+            const int ke = (int)(e / L1);
+            pos = (int)(e - (int64_t)ke * L1); len = L1; it.late = false;
+            k = n_late + ke;
+            it.s = Th - 1 - pos;
+        }
+        const int u = bx + k * G;
+        it.tile = it.late ? u : u - tiles;
+        it.first = pos == 0;
+        it.last = pos == len - 1;
+        return it;
     };
+    auto item_step = [&](int64_t item) -> int { return decode(item).s; };
 
     if (warp == 0) {
         if (i1 > i0) {  // ---- control warp (converged: see fl_mma)
@@ -254,12 +330,19 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             uint32_t ph = 0u;
             bool first = true;
             int prev_s = -1;
+            int64_t cur_ctl_item = 0;
+            // The recompute of hop h + 1 is committed while the epilogue may not have looked at hop h's commit yet: on ONE
+            // mbarrier a slow warp would then see the phase flip twice and wait for a third commit that needs its own arrival
+            // (observed as a hang under load).  Consecutive commits therefore alternate between two barriers; a barrier is
+            // reused only after a `ready()` that every warp can reach only past its wait on that barrier's previous phase.
+            uint32_t zbar = 0u;
             auto ready = [&]() {
-                tc::mbar_wait(&s_aready, ph);
+                fl_wait(&s_aready, ph, dbg, 1u, (uint32_t)cur_ctl_item);
                 ph ^= 1u;
                 tc::fence_after();
             };
             for (int64_t item = i0; item < i1; ++item) {
+                cur_ctl_item = item;
                 const int s = item_step(item);
                 const bool new_step = s != prev_s;
                 prev_s = s;
@@ -280,7 +363,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 {
                     const uint32_t ab = act0 + (uint32_t)(nh - 1) * A_BLOCK;
                     fl_mma_rows_w(tD2, ab, ab + A_HALF, wb + (uint32_t)nh * FL_W_BYTES, 4);
-                    fl_commit(&s_z);
+                    fl_commit(&s_z[zbar]);
+                    zbar ^= 1u;
                 }
                 // ---- backward: output layer (cotangent in Q, a_{nh+1} in P).  Its weight gradient goes first: the epilogue
                 //      overwrites P with delta_{nh+1}, and MMAs complete in order
@@ -298,7 +382,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                     } else {
                         fl_mma_rows_w(tz, x_hi, x_lo, wb, NKS_IN);
                     }
-                    fl_commit(&s_z);
+                    fl_commit(&s_z[zbar]);
+                    zbar ^= 1u;
                     z_next ^= 1u;
                 };
                 recompute(nh - 1);
@@ -332,7 +417,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t tD = lane_base + FL_COL_D + (uint32_t)c_lo, tD2 = lane_base + FL_COL_D2 + (uint32_t)c_lo;
         const int64_t B = d.batch;
-        uint32_t ph_acc = 0u, ph_w = 0u, ph_z = 0u;
+        uint32_t ph_acc = 0u, ph_w = 0u, ph_zbits = 0u, zbar = 0u;  // ph_zbits: one parity bit per s_z barrier
         int prev_s = -1;
         float adj[16];  // kl: this thread's 16 dimensions of a_{s+1} = d loss / d x_{s+1}
 #pragma unroll
@@ -343,8 +428,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_aready);  // 16 arrivals per hop instead of 512 serialised ones
         };
+        int64_t cur_e_item = 0;
         auto wait_acc = [&]() {
-            tc::mbar_wait(&s_acc, ph_acc);
+            fl_wait(&s_acc, ph_acc, dbg, 2u, (uint32_t)cur_e_item);
             ph_acc ^= 1u;
             tc::fence_after();
         };
@@ -358,7 +444,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         };
         float xnext[16];
         auto load_x = [&](int64_t it, float (&xv)[16]) {
-            const int s2 = item_step(it), tile2 = item_tile(it, s2);
+            const Item i2 = decode(it);
+            const int s2 = i2.s, tile2 = i2.tile;
             const int64_t b2 = (int64_t)tile2 * 128 + r;
             const bool valid2 = b2 < B;
             const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s2, valid2 ? b2 : 0);
@@ -366,13 +453,36 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             for (int e = 0; e < 16; ++e) xv[e] = (valid2 && c_lo + e < dim) ? __ldg(xr.p + (int64_t)(c_lo + e) * xr.stride) : 0.f;
         };
         for (int64_t item = i0; item < i1; ++item) {
-            const int s = item_step(item), tile = item_tile(item, s);
+            cur_e_item = item;
+            const Item cur_item = decode(item);
+            const int s = cur_item.s, tile = cur_item.tile;
             const int64_t b = (int64_t)tile * 128 + r;
             const bool valid = b < B;
             const int64_t bb = valid ? b : 0;
-            if (BPTT && s == a.T - 1) {  // a new tile: its terminal adjoint
+            if (BPTT && cur_item.first) {  // a new unit: the tile's terminal adjoint, or the one its late half parked
+                if (!cur_item.late) {
+                    if (lane == 0) {
+                        uint32_t seen;
+                        for (uint32_t spins = 0;; ++spins) {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.kl_flags + tile) : "memory");
+                            if (seen >= (uint32_t)FL_EPI_WARPS) break;
+                            __nanosleep(1000);
+                            if (spins > 2000000u || *reinterpret_cast<volatile uint32_t*>(dbg + 1) != 0u) {  // seconds: the producer is gone
+                                if (warp == 2) {
+                                    const uint32_t slot = atomicAdd(dbg, 1u);
+                                    if (slot < 200u) {
+                                        uint32_t* rec = dbg + 4 + 4 * slot;
+                                        rec[0] = (uint32_t)bx; rec[1] = (uint32_t)tile; rec[2] = 100u + seen; rec[3] = (uint32_t)item;
+                                    }
+                                }
+                                break;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
 #pragma unroll
-                for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&adj[e]) = __ldg(reinterpret_cast<const float4*>(a.adj_init + b * 64 + c_lo + e));
+                for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(&adj[e]) = __ldcg(reinterpret_cast<const float4*>(a.adj_init + b * 64 + c_lo + e));
             }
             // kl: the kept score part of this row and the step's (scalar) gate, fetched now — the cotangent math after the output
             // layer sits on the item's critical path and must not wait for HBM
@@ -395,7 +505,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = xnext[e];
             if (item > i0) {
-                tc::mbar_wait(&s_wdone, ph_w);  // X (and P / Q) are free again
+                fl_wait(&s_wdone, ph_w, dbg, 3u, (uint32_t)item);  // X (and P / Q) are free again
                 ph_w ^= 1u;
                 tc::fence_after();
                 if (s != prev_s) flush_emb(prev_s);
@@ -589,8 +699,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 }
                 // the recomputed pre-activation was committed a whole hop ago: GELU'(z) — most of this hop's arithmetic — is
                 // evaluated while the tensor pipe still runs the hop's dgrad GEMM
-                tc::mbar_wait(&s_z, ph_z);
-                ph_z ^= 1u;
+                fl_wait(&s_z[zbar], (ph_zbits >> zbar) & 1u, dbg, 4u, (uint32_t)item);
+                ph_zbits ^= 1u << zbar;
+                zbar ^= 1u;
                 tc::fence_after();
                 tc::tmem_ld8(tD2 + 64u * zsel, &z[0]);
                 tc::tmem_ld8(tD2 + 64u * zsel + 8u, &z[8]);
@@ -624,10 +735,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
 #pragma unroll
                 for (int e = 0; e < 16; ++e) adj[e] = (dead || c_lo + e >= dim) ? 0.f : adj[e] + v[e];
                 tc::fence_before();  // the next item's first GEMM overwrites this accumulator (ordered through the X hand-off)
+                if (cur_item.late && cur_item.last && L1 > 0) {  // park the adjoint for the tile's early half (another CTA, later)
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) __stcg(reinterpret_cast<float4*>(a.adj_init + b * 64 + c_lo + e), *reinterpret_cast<const float4*>(&adj[e]));
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.kl_flags + tile) : "memory");
+                }
             }
         }
         // ---- the launch's accumulators -> global memory
-        tc::mbar_wait(&s_wdone, ph_w);
+        fl_wait(&s_wdone, ph_w, dbg, 5u, 0xffffffffu);
         tc::fence_after();
         flush_emb(prev_s);
         for (int l = 0; l < L; ++l) {
@@ -669,8 +787,17 @@ static cudaError_t launch_lv_fused_t(const FusedLvArgs& a, int sm_count, cudaStr
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    const int64_t n_items = MODE != 0 ? (int64_t)a.tiles_per_step : (int64_t)a.T * a.tiles_per_step;
+    const int64_t n_items = MODE != 0 ? 2 * (int64_t)a.tiles_per_step : (int64_t)a.T * a.tiles_per_step;  // kl: units (half chains)
     int grid = (int)(n_items < sm_count ? n_items : sm_count);
+    if (MODE != 0) {
+        // the kl units wait on each other: every CTA of the grid must be resident
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lv_fused_kernel<DPAD, MODE>, FL_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        if (const char* g = getenv("SDES_FL_GRID")) grid = atoi(g) < grid ? atoi(g) : grid;  // debugging aid
+        if (getenv("SDES_FL_DEBUG")) fprintf(stderr, "lv_fused kl: occ/SM %d, sm_count %d, grid %d, units %lld\n", occ, sm_count, grid, (long long)n_items);
+    }
     if (grid < 1) grid = 1;
     lv_fused_kernel<DPAD, MODE><<<grid, FL_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
