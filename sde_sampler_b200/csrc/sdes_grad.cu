@@ -1673,6 +1673,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         fa.score_keep = g.score_keep; fa.gate = fws + kp.ws.gate; fa.gate_stride = kp.ws.dpad;
         fa.prior_loc = fws + kp.ws.prior; fa.prior_iv = fws + kp.ws.prior + kp.ws.dpad;
         fa.grad_gate = (fused_kl && gate_wanted) ? g.grad_gate : nullptr; fa.gflags = g.flags;
+        fa.watch_all = getenv("SDES_FL_DEBUG") != nullptr;
         fa.d = d; fa.tab = fws + kp.ws.tab; fa.xs = g.xs; fa.w = g.w; fa.embb = F(p.embb);
         fa.nh = p.nh; fa.T = p.T; fa.tiles_per_step = tiles_per_step; fa.grad_emb = g.grad_emb;
         float* gp = g.grad_params;

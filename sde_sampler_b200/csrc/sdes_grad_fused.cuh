@@ -67,6 +67,7 @@ struct FusedLvArgs {
     float* grad_gate;                         // (T) scalar gate gradient or NULL
     int gate_stride;
     uint32_t gflags;                          // SDES_GRAD_*
+    int watch_all;                            // debugging (SDES_FL_DEBUG): watchdog on the CTA-internal waits too (fl_wait)
 };
 
 // GELU'(x) = Phi(x) + x phi(x) of the exact-erf GELU, two values at a time: Phi from the logistic fit of gelu_fast2
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = s_tmem;
-    uint32_t* dbg = BPTT ? a.kl_flags + a.tiles_per_step : nullptr;  // watchdog record area (fl_wait)
+    uint32_t* dbg = BPTT ? a.kl_flags + a.tiles_per_step : nullptr;  // watchdog record area: always for the inter-CTA hand-off,
+    uint32_t* dbg_in = (BPTT && a.watch_all) ? dbg : nullptr;        // for the CTA-internal mbarrier waits only on request
     // lv: the (step, tile) items are independent — each CTA takes a contiguous step-major range.
     // kl: a tile's steps are a chain (the adjoint lives in registers while the tile walks backwards in time).  512 tiles do not
     // divide by 148 CTAs, so each chain is cut in two UNITS — the late half (s = T-1 .. Th) and the early half (Th-1 .. 0) —
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             // reused only after a `ready()` that every warp can reach only past its wait on that barrier's previous phase.
             uint32_t zbar = 0u;
             auto ready = [&]() {
-                fl_wait(&s_aready, ph, dbg, 1u, (uint32_t)cur_ctl_item);
+                fl_wait(&s_aready, ph, dbg_in, 1u, (uint32_t)cur_ctl_item);
                 ph ^= 1u;
                 tc::fence_after();
             };
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         };
         int64_t cur_e_item = 0;
         auto wait_acc = [&]() {
-            fl_wait(&s_acc, ph_acc, dbg, 2u, (uint32_t)cur_e_item);
+            fl_wait(&s_acc, ph_acc, dbg_in, 2u, (uint32_t)cur_e_item);
             ph_acc ^= 1u;
             tc::fence_after();
         };
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = xnext[e];
             if (item > i0) {
-                fl_wait(&s_wdone, ph_w, dbg, 3u, (uint32_t)item);  // X (and P / Q) are free again
+                fl_wait(&s_wdone, ph_w, dbg_in, 3u, (uint32_t)item);  // X (and P / Q) are free again
                 ph_w ^= 1u;
                 tc::fence_after();
                 if (s != prev_s) flush_emb(prev_s);
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                 }
                 // the recomputed pre-activation was committed a whole hop ago: GELU'(z) — most of this hop's arithmetic — is
                 // evaluated while the tensor pipe still runs the hop's dgrad GEMM
-                fl_wait(&s_z[zbar], (ph_zbits >> zbar) & 1u, dbg, 4u, (uint32_t)item);
+                fl_wait(&s_z[zbar], (ph_zbits >> zbar) & 1u, dbg_in, 4u, (uint32_t)item);
                 ph_zbits ^= 1u << zbar;
                 zbar ^= 1u;
                 tc::fence_after();
@@ -745,7 +747,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             }
         }
         // ---- the launch's accumulators -> global memory
-        fl_wait(&s_wdone, ph_w, dbg, 5u, 0xffffffffu);
+        fl_wait(&s_wdone, ph_w, dbg_in, 5u, 0xffffffffu);
         tc::fence_after();
         flush_emb(prev_s);
         for (int l = 0; l < L; ++l) {

@@ -30,3 +30,13 @@ run("traj reference layout", traj=True)
 run("traj tiled", traj=True, traj_tiled=True, traj_buffer=tb)
 run("traj tiled + gate_cot", traj=True, traj_tiled=True, traj_buffer=tb, gate_cot=gc, out={})
 run("traj tiled + score_keep", traj=True, traj_tiled=True, traj_buffer=tb, score_keep=sk, out={})
+# kl spec (no Ito term), many repetitions: every time listed (looking for outliers)
+o["loss"].method = "kl"
+spec = extract_spec(o["loss"], "time_reversal", o["ts"], o["terminal"], o["second"], train=True, compute_ito=False, return_traj=True)
+ms = []
+for _ in range(40):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.rollout(spec, x0, seed=5, engine="tcgen05", workspace=ws, traj_tiled=True, traj_buffer=tb, score_keep=sk, out={})
+    b.record(); torch.cuda.synchronize(); ms.append(round(a.elapsed_time(b), 2))
+print("kl forward with score_keep, 40 reps:", ms)

@@ -12,6 +12,8 @@ dev = torch.device("cuda:0")
 W = bench.WORKLOADS["gmm50"]
 o = build_from_spec(bench.load_spec(W), dev, engine="auto", seed=1234, sync_metrics=False)
 x0 = bench.sample_x0(W["x0"], 65536, 50, dev, 100)
+if len(sys.argv) > 1:
+    o["loss"].method = sys.argv[1]
 orig = eng.rollout
 def timed_rollout(*a, **k):
     torch.cuda.synchronize(); t = time.perf_counter()
