@@ -1360,7 +1360,7 @@ int64_t launch_lv_grad_wide(const KParams& kp, const SdesLvGradDesc& g, const Wi
         a.a_img = nullptr; a.a_mt_stride = A_BLOCK; a.w_img = ws + l.w_off; a.k_chunks = l.k_chunks; a.n_tiles = l.n_tiles; a.tile_n = l.tile_n;
         a.bias = l.b_off >= 0 ? F(l.b_off) : nullptr; a.bias_mt_div = 0; a.bias_mt_stride = 0; a.act = ACT_NONE;
         a.mask_img = nullptr; a.mask_mt_stride = 0; a.mul_img = nullptr; a.mul_mt_stride = 0; a.aux_img = nullptr; a.resid = nullptr;
-        a.out_f32 = nullptr; a.ld_f32 = v.P; a.out_img = nullptr; a.out_mt_stride = A_BLOCK; a.pair = 0;
+        a.out_f32 = nullptr; a.ld_f32 = v.P; a.out_img = nullptr; a.out_mt_stride = A_BLOCK;
         return a;
     };
     static bool attr_set = false;
@@ -1619,7 +1619,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         a.a_img = nullptr; a.a_mt_stride = A_BLOCK; a.w_img = ws + l.w_off; a.k_chunks = l.k_chunks; a.n_tiles = l.n_tiles; a.tile_n = l.tile_n;
         a.bias = l.b_off >= 0 ? F(l.b_off) : nullptr; a.bias_mt_div = 0; a.bias_mt_stride = 0; a.act = ACT_NONE;
         a.mask_img = nullptr; a.mask_mt_stride = 0; a.mul_img = nullptr; a.mul_mt_stride = 0; a.aux_img = nullptr; a.resid = nullptr;
-        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = A_BLOCK; a.pair = 0;
+        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = A_BLOCK;
         return a;
     };
     static bool attr_set = false;

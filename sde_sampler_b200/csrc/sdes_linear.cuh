@@ -20,8 +20,6 @@ constexpr uint32_t A_BLOCK = 2u * A_HALF;    // hi | lo
 // share of the columns.  A single warp per scheduler runs the ~80 dependent instructions of an 8-column group at
 // ~10 cycles each, so wide layers (one CTA per SM) use 12 epilogue warps; skinny layers keep 4 and co-schedule 3 CTAs.
 constexpr int EPI_WIDE = 12, EPI_SKINNY = 4;
-constexpr int EPI_WARPS = EPI_WIDE;               // CTA-pair kernel
-constexpr int LIN_THREADS = 64 + 32 * EPI_WARPS;
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
@@ -30,12 +28,11 @@ static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 struct Lin {           // one Linear as a B operand image: [n_tile][k_chunk] blocks of tile_n x 64 (hi | lo)
     int N, K;          // logical out / in features
     int n_pad, n_tiles, tile_n, k_chunks;
-    int pair;          // 1: imaged in half tiles for the CTA-pair kernel
     int64_t w_off;     // bytes from the workspace base
     int64_t b_off;     // bytes from the workspace base of the padded fp32 bias (n_pad), -1 = none
 };
 
-static void set_tiling(Lin& l, int N, int K, bool allow_pair = false) {
+static void set_tiling(Lin& l, int N, int K) {
     l.N = N;
     l.K = K;
     l.n_pad = round_up(N, 64);
@@ -44,13 +41,6 @@ static void set_tiling(Lin& l, int N, int K, bool allow_pair = false) {
     l.n_tiles = nt;
     l.tile_n = l.n_pad / nt;
     l.k_chunks = round_up(K, 64) / 64;
-    // wide layers (smem-fill bound) run on CTA pairs: image the weights in half tiles of a 256 x tile_n MMA tile
-    l.pair = 0;
-    if (allow_pair && l.tile_n >= 128 && l.tile_n % 32 == 0 && l.k_chunks >= 4) {
-        l.pair = 1;
-        l.tile_n /= 2;
-        l.n_tiles *= 2;
-    }
 }
 static int64_t lin_image_bytes(const Lin& l) { return (int64_t)l.n_pad * l.k_chunks * 64 * 4; }
 
@@ -142,7 +132,6 @@ struct LinArgs {
     float* out_f32; int ld_f32;                    // row-major fp32 output (same leading dimension as resid)
     uint8_t* out_img; int64_t out_mt_stride;       // next layer's A operand
     uint8_t* aux_img;                              // ACT_GELU_GRAD: image of gelu'(h), strides as out_img
-    int pair;                                      // 1: CTA-pair kernel (tile_n = half tile of a 256 x 2*tile_n MMA tile)
 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_GRAD = 3 };
 
@@ -407,204 +396,6 @@ static __global__ void __launch_bounds__(64 + 32 * EPI, EPI == EPI_SKINNY ? 3 : 
     if (warp == 1) tc::tmem_dealloc(tmem_base, 2u * ncols);
 }
 
-// ----------------------------------------------------------------------- 2-CTA (cta_group::2) variant
-// A CTA PAIR (cluster of 2, two SMs of one TPC) computes a 256 x N2 tile with tcgen05.mma.cta_group::2: each CTA stages
-// its own 128 rows of A and only HALF of the weight tile (N2/2 rows), the leader's single MMA thread drives both tensor
-// cores, each CTA's TMEM receives its own 128 x N2 accumulator half: 64 KB per stage instead of 96 and a 3-stage ring.
-// OPT-IN (SDES_CTA_PAIRS=1): parity-tested, but measured SLOWER than the single-CTA kernel on cfg 5's 1024 x 1024
-// layers (46 us vs 36.5 us; L2->SM traffic 143 MB vs 201 MB, tensor pipe 32 % vs 42 % of active cycles) — the layer is
-// not bound by the fill bandwidth the pairing saves; see DESIGN.md §4.3 for the open question this leaves for round 2.
-// Protocol per stage: every CTA's producer fills its own smem and completes its own `full`; the peer's MMA-warp thread
-// forwards that to the leader (remote mbarrier arrive on `peer_full`); the leader issues the MMAs and commits with
-// multicast to `empty` of both CTAs; `acc_full` is a multicast commit too, `acc_empty` collects 256 arrivals (the
-// epilogue threads of both CTAs) at the leader.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    __syncwarp();  // the role branches leave lanes of warps 0 / 1 diverged
-    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_saddr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP_C:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE_C;\n\t"
-        "bra WAIT_LOOP_C;\n\t"
-        "DONE_C:\n\t"
-        "}" ::"r"(tc::smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_result)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma2_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma2_commit_multicast(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-
-// a.tile_n is the HALF tile (rows of the weight image block one CTA stages); the MMA tile is 256 x (2 * a.tile_n).
-// Pair tile t: n2 = t % (n_tiles / 2), m pair = t / (n_tiles / 2); this CTA owns row tile 2 * mpair + rank and stages
-// weight block 2 * n2 + rank.
-static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LIN_THREADS, 1)
-    linear_mma2_kernel(const __grid_constant__ LinArgs a, const int m_tiles) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int STAGES = 3;
-    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_peer_full[STAGES], s_acc_full[2], s_acc_empty[2];
-    __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int N2 = 2 * a.tile_n, n2_tiles = a.n_tiles / 2, m_pairs = (m_tiles + 1) / 2;
-    const uint32_t b_half = (uint32_t)a.tile_n * 128u;  // bytes of one bf16 half of this CTA's weight block
-    const uint32_t stage_bytes = A_BLOCK + 2u * b_half;
-    uint32_t ncols = 32;
-    while ((int)ncols < N2) ncols <<= 1;
-    const int n_clusters = (int)gridDim.x / 2, cid = (int)blockIdx.x / 2;
-    const int n_total = n2_tiles * m_pairs;
-    const int n_my = cid < n_total ? (n_total - cid + n_clusters - 1) / n_clusters : 0;
-
-    if (warp == 1) {
-        tmem_alloc2(&s_tmem, 2u * ncols);
-        tmem_relinquish2();
-    }
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(&s_full[s], 1);
-            tc::mbar_init(&s_empty[s], 1);
-            tc::mbar_init(&s_peer_full[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(&s_acc_full[s], 1);
-            tc::mbar_init(&s_acc_empty[s], 2 * 32 * EPI_WARPS);
-        }
-        tc::fence_mbar_init();
-    }
-    tc::fence_before();
-    cluster_sync_all();
-    tc::fence_after();
-    const uint32_t tmem_base = s_tmem;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ---- producer (both CTAs): own A rows, own half of the weight tile
-            int iter = 0;
-            for (int i = 0; i < n_my; ++i) {
-                const int t = cid + i * n_clusters, n2 = t % n2_tiles, mp = t / n2_tiles;
-                int mt = 2 * mp + (int)rank;
-                if (mt >= m_tiles) mt = m_tiles - 1;  // odd tail: stage a valid tile, its result is never stored
-                const uint8_t* a_src = a.a_img + (int64_t)mt * a.a_mt_stride;
-                const uint8_t* w_src = a.w_img + (int64_t)(2 * n2 + (int)rank) * a.k_chunks * (2ll * b_half);
-                for (int kc = 0; kc < a.k_chunks; ++kc, ++iter) {
-                    const int s = iter % STAGES, it = iter / STAGES;
-                    if (it > 0) tc::mbar_wait(&s_empty[s], (uint32_t)((it - 1) & 1));
-                    tc::mbar_arrive_expect_tx(&s_full[s], stage_bytes);
-                    uint8_t* dst = smem + (size_t)s * stage_bytes;
-                    const uint8_t* ap = a_src + (int64_t)kc * A_BLOCK;
-                    tc::bulk_g2s(dst, ap, A_HALF, &s_full[s]);
-                    tc::bulk_g2s(dst + A_HALF, ap + A_HALF, A_HALF, &s_full[s]);
-                    const uint8_t* wp = w_src + (int64_t)kc * (2ll * b_half);
-                    for (uint32_t off = 0; off < 2u * b_half; off += 16384u) {
-                        const uint32_t n = 2u * b_half - off < 16384u ? 2u * b_half - off : 16384u;
-                        tc::bulk_g2s(dst + A_BLOCK + off, wp + off, n, &s_full[s]);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            if (!leader) {  // ---- peer: forward "my stage is full" to the leader
-                int iter = 0;
-                for (int i = 0; i < n_my; ++i)
-                    for (int kc = 0; kc < a.k_chunks; ++kc, ++iter) {
-                        const int s = iter % STAGES, it = iter / STAGES;
-                        tc::mbar_wait(&s_full[s], (uint32_t)(it & 1));
-                        mbar_arrive_cluster(map_to_cta(tc::smem_u32(&s_peer_full[s]), 0));
-                    }
-            } else {  // ---- leader: the MMA issuer of the pair
-                const uint32_t idesc = tc::idesc_bf16(256, N2);
-                const uint32_t lbo_b = (uint32_t)a.tile_n * 16u;
-                int iter = 0;
-                for (int i = 0; i < n_my; ++i) {
-                    const int buf = i & 1, use = i >> 1;
-                    if (use > 0) {
-                        mbar_wait_cluster(&s_acc_empty[buf], (uint32_t)((use - 1) & 1));
-                        tc::fence_after();
-                    }
-                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * ncols;
-                    for (int kc = 0; kc < a.k_chunks; ++kc, ++iter) {
-                        const int s = iter % STAGES, it = iter / STAGES;
-                        tc::mbar_wait(&s_full[s], (uint32_t)(it & 1));
-                        mbar_wait_cluster(&s_peer_full[s], (uint32_t)(it & 1));
-                        tc::fence_after();
-                        const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + A_HALF;
-                        const uint32_t b_hi = a_hi + A_BLOCK, b_lo = b_hi + b_half;
-#pragma unroll
-                        for (int ks = 0; ks < KC / 16; ++ks) {
-                            const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
-                            const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
-                            const uint64_t dbh = tc::smem_desc_kmajor(b_hi + (uint32_t)ks * 2u * lbo_b, lbo_b, 128u);
-                            const uint64_t dbl = tc::smem_desc_kmajor(b_lo + (uint32_t)ks * 2u * lbo_b, lbo_b, 128u);
-                            mma2_f16_ss(tmem_d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                            mma2_f16_ss(tmem_d, dah, dbl, idesc, 1u);
-                            mma2_f16_ss(tmem_d, dah, dbh, idesc, 1u);
-                        }
-                        mma2_commit_multicast(&s_empty[s]);
-                    }
-                    mma2_commit_multicast(&s_acc_full[buf]);
-                }
-            }
-        }
-    } else {  // ---- epilogue warps of both CTAs: own 128 rows, all N2 columns
-        const int q = warp & 3, r = q * 32 + lane;
-        int c_lo, c_n;
-        epi_col_range<EPI_WARPS>(N2, (warp - 2) >> 2, c_lo, c_n);
-        const uint32_t acc_empty_leader0 = map_to_cta(tc::smem_u32(&s_acc_empty[0]), 0);
-        const uint32_t acc_empty_leader1 = map_to_cta(tc::smem_u32(&s_acc_empty[1]), 0);
-        for (int i = 0; i < n_my; ++i) {
-            const int t = cid + i * n_clusters, n2 = t % n2_tiles, mp = t / n2_tiles;
-            const int mt = 2 * mp + (int)rank;
-            const int buf = i & 1, use = i >> 1;
-            tc::mbar_wait(&s_acc_full[buf], (uint32_t)(use & 1));
-            tc::fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)buf * ncols + ((uint32_t)(q * 32) << 16);
-            if (mt < m_tiles) {
-                epilogue_row(a, mt, r, n2 * N2 + c_lo, c_n, taddr + (uint32_t)c_lo);
-            }
-            tc::fence_before();
-            mbar_arrive_cluster(buf == 0 ? acc_empty_leader0 : acc_empty_leader1);
-        }
-    }
-    tc::fence_before();
-    cluster_sync_all();
-    if (warp == 1) tmem_dealloc2(tmem_base, 2u * ncols);
-}
-
 // The same layer on the CUDA cores, reading the same operand images: the cross-check engine (SDES_F_MLP_SIMT).
 static __global__ void __launch_bounds__(128) linear_simt_kernel(const LinArgs a) {
     const int nt = blockIdx.x, mt = blockIdx.y, r = threadIdx.x;
@@ -648,22 +439,7 @@ static cudaError_t launch_linear(const LinArgs& a, int m_tiles, bool simt, cudaS
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(linear_mma_kernel<EPI_SKINNY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(linear_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
         attr_set = true;
-    }
-    if (a.pair == 1) {  // CTA-pair kernel: a.tile_n is the half tile, n_tiles is even
-        static int sms2 = 0;
-        if (sms2 == 0) {
-            int dev = 0;
-            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms2 <= 0) sms2 = 148;
-        }
-        const uint32_t stage2 = A_BLOCK + 2u * (uint32_t)a.tile_n * 128u;
-        const int64_t pairs = (int64_t)(a.n_tiles / 2) * ((m_tiles + 1) / 2);
-        int clusters = (int)(pairs < sms2 / 2 ? pairs : sms2 / 2);
-        if (clusters < 1) clusters = 1;
-        linear_mma2_kernel<<<2 * clusters, LIN_THREADS, 3 * (size_t)stage2, stream>>>(a, m_tiles);
-        return cudaGetLastError();
     }
     const uint32_t stage_bytes = A_BLOCK + 2u * (uint32_t)a.tile_n * 128u;
     // Skinny layers (K <= 128, N <= 64: the control MLP over millions of rows) are bound by the epilogue's CUDA-core

@@ -93,12 +93,11 @@ static bool make_plan(const SdesRolloutDesc& d, Plan& p) {
     p.gmm_mu = take(K * p.P * 4);
     p.gmm_h = take(K * p.P * 4);
     p.gmm_c = take(64 * 4);
-    const bool pairs_ok = !(d.flags & SDES_F_MLP_SIMT) && getenv("SDES_CTA_PAIRS") != nullptr;  // opt-in, see sdes_linear.cuh
     auto lin = [&](Lin& l, int N, int Kin, bool bias) {
-        set_tiling(l, N, Kin, pairs_ok);
+        set_tiling(l, N, Kin);
         // fewer tiles than half the SMs (e.g. the N = d/2 = 392 layers of cfg 5's 4 096-row shard: 2 x 32): halve the
         // column tile so the layer spreads over twice as many CTAs
-        while (!l.pair && (int64_t)l.n_tiles * p.m_tiles <= 74 && l.tile_n >= 128 && l.tile_n % 32 == 0) {
+        while ((int64_t)l.n_tiles * p.m_tiles <= 74 && l.tile_n >= 128 && l.tile_n % 32 == 0) {
             l.tile_n /= 2;
             l.n_tiles *= 2;
         }
@@ -648,7 +647,7 @@ int64_t launch_rollout_wide(const KParams& kp, cudaStream_t stream, cudaError_t*
         a.a_img = nullptr; a.a_mt_stride = 0; a.w_img = ws + l.w_off; a.k_chunks = l.k_chunks; a.n_tiles = l.n_tiles; a.tile_n = l.tile_n;
         a.bias = l.b_off >= 0 ? F(l.b_off) : nullptr; a.bias_mt_div = 0; a.bias_mt_stride = 0; a.act = ACT_NONE;
         a.mask_img = nullptr; a.mask_mt_stride = 0; a.mul_img = nullptr; a.mul_mt_stride = 0; a.aux_img = nullptr; a.resid = nullptr;
-        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = 0; a.pair = l.pair;
+        a.out_f32 = nullptr; a.ld_f32 = p.P; a.out_img = nullptr; a.out_mt_stride = 0;
         return a;
     };
     // NICE forward over the couplings, in place on the state image (x's image is rebuilt by update_kernel each step)

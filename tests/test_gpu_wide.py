@@ -193,17 +193,3 @@ def test_wide_engines_agree_at_scale(golden):
         assert torch.isfinite(outs[engine][0]).all() and torch.isfinite(outs[engine][1]).all()
     assert_close(outs["tcgen05"][0].cpu().numpy(), outs["simt"][0].cpu().numpy(), 1e-4, 1e-4, "x_T engines")
     assert_close(outs["tcgen05"][1].cpu().numpy(), outs["simt"][1].cpu().numpy(), 1e-4, 1e-4, "rnd engines")
-
-
-def test_cta_pair_gemm_kernel_matches_oracle(golden, monkeypatch):
-    """The opt-in cta_group::2 variant of the GEMM layer (SDES_CTA_PAIRS=1: 256-row tiles on CTA pairs, multicast
-    commits, remote mbarrier arrives) must give the same rollout as the oracle on cfg 5's full layer widths."""
-    monkeypatch.setenv("SDES_CTA_PAIRS", "1")
-    spec = _cfg5_spec(golden, 784, 1000, 5, T=2)
-    B, d, T = 300, 784, 2   # 3 row tiles: an odd tail pair
-    x0 = np.random.default_rng(2).standard_normal((B, d)).astype(np.float32)
-    noise = philox.normal_noise(NOISE_SEED + 5, B, T, d)
-    want_x, want_r, _ = oracle_rollout.rollout(spec, x0, noise=noise)
-    x_T, rnd, _ = _run(spec, x0, noise, "tcgen05")
-    assert_close(x_T.cpu().numpy(), want_x, RTOL, ATOL, "x_T")
-    assert_close(rnd.cpu().numpy(), want_r, RTOL, ATOL, "rnd")
