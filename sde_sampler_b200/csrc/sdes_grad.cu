@@ -1597,8 +1597,13 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
     // a control without one), the forward kept the ungated score part (score_keep) and the gate is scalar or absent
     const bool kl_target_in_ctrl = d.ctrl_kind == SDES_CTRL_SCORE || d.ctrl_kind == SDES_CTRL_LERP || d.ctrl_kind == SDES_CTRL_LERP_TARGET;
     const bool kl_hvp = kl_target_in_ctrl && !(g.flags & (SDES_GRAD_TARGET_SCORE_CONST | SDES_GRAD_SCORE_DETACHED));
-    const bool fused_kl = bptt_tc && lv_fused_supported(d) && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && !kl_hvp &&
-                          (d.ctrl_kind == SDES_CTRL_CLIPPED || g.score_keep != nullptr) && (!gate_wanted || d.gate_dim == 1);
+    // a Hessian that is diagonal (one Gaussian, multi-well) is local per dimension too; the funnel's needs the whole row in one
+    // epilogue thread (d <= 16), and so does a per-dimension gate's reduction
+    const bool row_in_thread = mma_pad_dim(d.dim) <= 16;
+    const bool hvp_ok = !kl_hvp || (d.target_kind == SDES_TARGET_GMM && d.n_components == 1) || d.target_kind == SDES_TARGET_MULTIWELL ||
+                        (d.target_kind == SDES_TARGET_FUNNEL && row_in_thread);
+    const bool fused_kl = bptt_tc && lv_fused_supported(d) && !(g.flags & SDES_GRAD_LAYERWISE_SWEEP) && hvp_ok &&
+                          (d.ctrl_kind == SDES_CTRL_CLIPPED || g.score_keep != nullptr) && (!gate_wanted || d.gate_dim == 1 || row_in_thread);
     const bool fused_any = fused_lv || fused_kl;
     GRAD_CHECK(image(p.f_in, blob + kp.bl.in_w, d.dim, C, d.dim, 0));
     for (int l = 0; l < p.nh; ++l) {
@@ -1674,6 +1679,7 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         fa.prior_loc = fws + kp.ws.prior; fa.prior_iv = fws + kp.ws.prior + kp.ws.dpad;
         fa.grad_gate = (fused_kl && gate_wanted) ? g.grad_gate : nullptr; fa.gflags = g.flags;
         fa.watch_all = getenv("SDES_FL_DEBUG") != nullptr;
+        fa.gmm_h = fws + kp.ws.gmm_h; fa.hvp = (fused_kl && kl_hvp) ? 1 : 0;
         fa.d = d; fa.tab = fws + kp.ws.tab; fa.xs = g.xs; fa.w = g.w; fa.embb = F(p.embb);
         fa.nh = p.nh; fa.T = p.T; fa.tiles_per_step = tiles_per_step; fa.grad_emb = g.grad_emb;
         float* gp = g.grad_params;

@@ -67,6 +67,8 @@ struct FusedLvArgs {
     float* grad_gate;                         // (T) scalar gate gradient or NULL
     int gate_stride;
     uint32_t gflags;                          // SDES_GRAD_*
+    const float* gmm_h;                       // MODE 3, single-Gaussian target: 0.5 / scale^2 per dimension
+    int hvp;                                  // MODE 3: the target's Hessian enters (adj_step_kernel's target_hvp)
     int watch_all;                            // debugging (SDES_FL_DEBUG): watchdog on the CTA-internal waits too (fl_wait)
 };
 
@@ -222,10 +224,13 @@ __device__ __forceinline__ void fl_ld16(uint32_t taddr, float (&v)[16]) {
     tc::wait_ld_tie<16>(v);
 }
 
-// MODE 0: lv.  MODE 1: kl (no noise in the cotangent).  MODE 2: kl_ito.
+// MODE 0: lv.  MODE 1: kl (no noise in the cotangent).  MODE 2: kl_ito.  MODE 3: kl / kl_ito whose score term brings the target's
+// Hessian into the sweep (Gauss / multi-well: diagonal, any d; funnel: the whole row must sit in one thread, d <= 16) and / or a
+// per-dimension gate (d <= 16) — kept apart so that its extra registers do not spill the common instantiations.
 template <int DPAD, int MODE>
 __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_constant__ FusedLvArgs a) {
     constexpr bool BPTT = MODE != 0;
+    constexpr bool HVP = MODE == 3;
     extern __shared__ __align__(128) uint8_t fl_smem[];
     __shared__ uint64_t s_wfull, s_acc, s_aready, s_wdone, s_z[2];
     __shared__ uint32_t s_tmem;
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             const uint32_t traj = (uint32_t)(d.traj_offset + (uint64_t)bb);
             const float* nrow = c.from_hbm ? d.noise + ((int64_t)s * B + bb) * dim : nullptr;
             float eps[16];
-            constexpr bool need_eps = MODE != 1;
+            const bool need_eps = MODE == 0 || MODE == 2 || (MODE == 3 && (d.flags & SDES_F_COMPUTE_ITO) != 0);
             auto draw = [&](int hop) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
@@ -643,14 +648,18 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                     const float wp = 1.0f - tab[TAB_LERP_W];
                     const TrajRef xr = traj_ref(d, const_cast<float*>(a.xs), s, bb);
                     float gsum = 0.f;
+                    float xv16[HVP ? 16 : 1], facv[HVP ? 16 : 1], gdim[HVP ? 16 : 1];
+                    const bool gate_per_dim = HVP && d.gate_dim > 1;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int j = c_lo + e;
                         const bool in = j < dim;
                         const float nn = v[e] + bo[e];
                         const float base = kbase[e];
-                        const float gt = in ? gate0 : 0.f;  // scalar gate (or the constant 1 of a control without one), 0 on padding
+                        // scalar gate (or the constant 1 of a control without one), 0 on padding; MODE 3: the table's own column
+                        const float gt = in ? (gate_per_dim ? __ldg(a.gate + (int64_t)s * a.gate_stride + j) : gate0) : 0.f;
                         const float iv = s_prior[64 + j];
+                        if (HVP) xv16[e] = (in && valid) ? __ldg(xr.p + (int64_t)j * xr.stride) : 0.f;
                         const float g = clipf(nn, c.cm) + base * gt;
                         const float ap = adj[e];
                         float dg, nx;
@@ -670,14 +679,55 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                         }
                         if (dead || !in) dg = 0.f;
                         gsum = fmaf(dg, base, gsum);
-                        if (!score_detached && prior_in_ctrl) {
-                            const float fac = (fabsf(base) != clip_edge) ? outer * gt * dg : 0.f;  // cotangent of inner_j (1 inside the clip)
-                            nx = fmaf(-wp * iv, fac, nx);
+                        const float fac = (fabsf(base) != clip_edge) ? outer * gt * dg : 0.f;  // cotangent of inner_j (1 inside the clip)
+                        if (!score_detached && prior_in_ctrl) nx = fmaf(-wp * iv, fac, nx);
+                        if (HVP) {
+                            facv[e] = fac;
+                            gdim[e] = dg * base;
                         }
                         adj[e] = (dead || !valid || !in) ? 0.f : nx;
                         v[e] = fabsf(nn) <= c.cm ? dg : 0.f;  // d clip(NN) / d NN
                     }
-                    if (a.grad_gate != nullptr) {  // scalar gate: d loss / d gate(s) = 1[|gate| < clip] sum_b sum_j delta_j base_j
+                    if (HVP && a.hvp && !score_detached && !dead && valid) {
+                        // + H(x_s) (cotangent of the target score): sdes_step.cuh target_hvp_add, on this thread's 16 dimensions
+                        const float lw = (ck == SDES_CTRL_SCORE) ? 1.0f : tab[TAB_LERP_W];
+                        if (d.target_kind == SDES_TARGET_GMM) {  // one component: score = (loc - x) / scale^2
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (c_lo + e < dim) adj[e] = fmaf(-2.0f * __ldg(a.gmm_h + c_lo + e), lw * facv[e], adj[e]);
+                        } else if (d.target_kind == SDES_TARGET_MULTIWELL) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const int j = c_lo + e;
+                                const float y = xv16[e] - d.shift;
+                                if (j < d.n_double_wells) adj[e] = fmaf(4.0f * d.separation - 12.0f * y * y, lw * facv[e], adj[e]);
+                                else if (j < dim) adj[e] -= lw * facv[e];
+                            }
+                        } else if (c_lo == 0) {  // funnel (d <= 16: the whole row is here); distr/funnel.py:71-80
+                            float sq = 0.f, xf = 0.f;
+#pragma unroll
+                            for (int e = 1; e < 16; ++e) {
+                                sq = fmaf(xv16[e], xv16[e], sq);
+                                xf = fmaf(xv16[e], lw * facv[e], xf);
+                            }
+                            const float inv = expf(-xv16[0]), f0 = lw * facv[0];
+                            adj[0] += f0 * (-1.0f / d.variance - 0.5f * sq * inv) + inv * xf;
+#pragma unroll
+                            for (int e = 1; e < 16; ++e)
+                                if (e < dim) adj[e] += inv * (xv16[e] * f0 - lw * facv[e]);
+                        }
+                    }
+                    if (gate_per_dim && a.grad_gate != nullptr && c_lo < dim) {  // per-dimension gate (d <= 16): one reduction per column
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float t = gdim[e];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                            const int j = c_lo + e;
+                            if (lane == 0 && j < dim && t != 0.f && fabsf(__ldg(a.gate + (int64_t)s * a.gate_stride + j)) < c.cm)
+                                atomicAdd(a.grad_gate + (int64_t)s * dim + j, t);
+                        }
+                    } else if (a.grad_gate != nullptr) {  // scalar gate: d loss / d gate(s) = 1[|gate| < clip] sum_b sum_j delta_j base_j
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
                         if (lane == 0 && gsum != 0.f && fabsf(gate0) < c.cm) atomicAdd(a.grad_gate + s, gsum);
@@ -818,6 +868,7 @@ static cudaError_t launch_lv_fused_m(const FusedLvArgs& a, int sm_count, cudaStr
 }
 static cudaError_t launch_lv_fused(const FusedLvArgs& a, bool bptt, int sm_count, cudaStream_t stream) {
     if (!bptt) return launch_lv_fused_m<0>(a, sm_count, stream);
+    if (a.hvp || a.d.gate_dim > 1) return launch_lv_fused_m<3>(a, sm_count, stream);
     return (a.d.flags & SDES_F_COMPUTE_ITO) ? launch_lv_fused_m<2>(a, sm_count, stream) : launch_lv_fused_m<1>(a, sm_count, stream);
 }
 

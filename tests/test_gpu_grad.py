@@ -163,11 +163,14 @@ def test_lv_fused_kernel_matches_layerwise_passes(golden, name, B):
         assert (a - c).abs().max().item() <= 1e-3 * scale + 1e-7, f"output {i}: {(a - c).abs().max().item():.3e} vs scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("name,B", [("dis_gmm50_kl", 1000), ("dis_gmm50_kl", 33000), ("dis_lerpprior_multiwell4", 3000), ("dis_gmm2_kl", 130)])
+@pytest.mark.parametrize("name,B", [("dis_gmm50_kl", 1000), ("dis_gmm50_kl", 33000), ("dis_lerpprior_multiwell4", 3000), ("dis_gmm2_kl", 130),
+                                    ("pis_funnel10_kl", 20000), ("dds_funnel10_kl", 700), ("eulerdds_gauss3_kl", 2000),
+                                    ("dis_lerp_multiwell5_klito", 5000)])
 def test_kl_fused_kernel_matches_stepwise_sweep(golden, name, B):
     """kl / kl_ito with the forward's score_keep: the whole reverse sweep as one persistent kernel (adjoint in registers, a
     tile's steps walked backwards by one CTA) against the step-by-step sweep (one elementwise kernel + dgrad chain per step)
-    on the same stored trajectory — ragged last tile, more tiles than SMs, kl and kl_ito, Lerp and LerpPrior controls."""
+    on the same stored trajectory — ragged last tile, more tiles than SMs, kl and kl_ito, Lerp / LerpPrior / Score controls, all three loss kinds, targets
+    whose Hessian enters the sweep (funnel, Gauss, multi-well) and a per-dimension gate."""
     from sde_sampler_b200 import engine as eng
     from sde_sampler_b200.engine import Workspace
     from sde_sampler_b200.spec import extract_spec
