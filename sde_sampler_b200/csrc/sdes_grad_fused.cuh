@@ -120,7 +120,7 @@ __device__ __forceinline__ void fl_commit(uint64_t* bar) {
 
 // mbarrier wait with a watchdog for the kl instantiations (their CTAs wait on each other): after ~3 s of failed polls the
 // waiter records (CTA, warp, wait site, item), raises the launch-wide abort word and every wait returns at once — the kernel
-// ends with a wrong result that the host reports (SDES_FL_DEBUG) instead of hanging the device.
+// ends (gradients poisoned with NaN; details with SDES_FL_DEBUG) instead of hanging the device.
 __device__ __forceinline__ void fl_wait(uint64_t* bar, uint32_t parity, uint32_t* dbg, uint32_t code, uint32_t item) {
     if (dbg == nullptr) {
         tc::mbar_wait(bar, parity);
@@ -481,6 +481,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
                                         uint32_t* rec = dbg + 4 + 4 * slot;
                                         rec[0] = (uint32_t)bx; rec[1] = (uint32_t)tile; rec[2] = 100u + seen; rec[3] = (uint32_t)item;
                                     }
+                                    // the result is wrong from here on: poison it so that nobody can use it by accident (the
+                                    // trainer's finite check skips the step, the tests fail) — later atomic adds keep the NaN
+                                    atomicExch(reinterpret_cast<unsigned int*>(a.grad_emb), 0x7fc00000u);
+                                    atomicExch(reinterpret_cast<unsigned int*>(a.dw[0]), 0x7fc00000u);
                                 }
                                 break;
                             }

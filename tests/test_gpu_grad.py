@@ -196,6 +196,52 @@ def test_kl_fused_kernel_matches_stepwise_sweep(golden, name, B):
         assert (a - c).abs().max().item() <= 1e-3 * scale + 1e-7, f"output {i}: {(a - c).abs().max().item():.3e} vs scale {scale:.3e}"
 
 
+@pytest.mark.parametrize("bptt", [False, True])
+def test_fused_gradient_full_size_properties(golden, bptt):
+    """BASELINE's headline size (65 536 trajectories x T steps, d = 50) through the one-kernel gradient — too large for the
+    oracle, so the size-independent properties: the gradient is linear in the per-trajectory weights (w = w1 + w2 gives the
+    sum of the two gradients) and additive over shards addressed through the global Philox counters (traj_offset)."""
+    from sde_sampler_b200 import engine as eng
+    from sde_sampler_b200.engine import Workspace
+    from sde_sampler_b200.spec import extract_spec
+
+    name = "dis_gmm50_kl" if bptt else "dis_gmm50_lv"
+    g = golden(name)
+    b = build_from_spec(g["spec"], _dev(), engine="tcgen05")
+    B, d = 65536, 50
+    x0 = torch.randn(B, d, device=_dev(), generator=torch.Generator(_dev()).manual_seed(9))
+    spec = extract_spec(b["loss"], "time_reversal", b["ts"], b["terminal"], b["second"], train=True, compute_ito=not bptt, return_traj=True)
+    key = "score_keep" if bptt else "gate_cot"
+
+    def fwd(x, off):
+        out = {}
+        _, rnd, xs = eng.rollout(spec, x, seed=5, traj_offset=off, engine="tcgen05", traj_tiled=True, out=out, **{key: Workspace()})
+        return rnd.reshape(-1), xs, out[key]
+
+    def grad(xs, w, aux, off):
+        return eng.lv_grad(spec, xs, w, seed=5, traj_offset=off, engine="tcgen05", bptt=bptt, **{key: aux})
+
+    rnd, xs, aux = fwd(x0, 0)
+    r = rnd.double()
+    w = (2.0 * (r - r.mean()) / (B - 1)).float() if not bptt else torch.full((B,), 1.0 / B, device=_dev())
+    full = grad(xs, w, aux, 0)
+    gen = torch.Generator(_dev()).manual_seed(1)
+    w1 = w * torch.rand(B, device=_dev(), generator=gen)
+    parts = [grad(xs, w1, aux, 0), grad(xs, w - w1, aux, 0)]
+    halves = []
+    for h in range(2):
+        sl = slice(h * B // 2, (h + 1) * B // 2)
+        _, xs_h, aux_h = fwd(x0[sl], h * B // 2)
+        halves.append(grad(xs_h, w[sl], aux_h, h * B // 2))
+    for what, pair in (("linearity in w", parts), ("shard additivity", halves)):
+        for i, (a, p0, p1) in enumerate(zip(full, *pair)):
+            if a is None:
+                continue
+            scale = a.abs().max().item()
+            assert (a - (p0 + p1)).abs().max().item() <= 1e-3 * scale + 1e-7, f"{what}, output {i}"
+            assert torch.isfinite(a).all()
+
+
 def test_kl_gradient_is_additive_over_shards_and_engine_independent(golden):
     """Size-independent properties of the BPTT gradient at 4 096 trajectories of the cfg-3 configuration (funnel d=10, PIS,
     kl): the gradient is linear in the per-trajectory weights, so two half-batch calls (global Philox counters via
