@@ -571,17 +571,31 @@ def main():
         xd_next = x0_host[0].to(device, non_blocking=True)
         ready = torch.cuda.Event()
         ready.record(copy_stream)
+    # every step's loss goes device -> pinned host memory with a non-blocking copy and is READ one step later (after the next
+    # step has been queued), the last one before the region ends: each step's result reaches the host inside the region, but
+    # the host never idles the GPU waiting for it — the loop a training script with a logging callback runs
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [None, None]
+    pending = None
     for k in range(args.steps):
         torch.cuda.current_stream(device).wait_event(ready)
         xd = xd_next
         v, _m = step(xd)
+        loss_host[k & 1].copy_(v.detach().reshape(()).float(), non_blocking=True)
+        loss_done[k & 1] = torch.cuda.Event()
+        loss_done[k & 1].record()
         if k + 1 < args.steps:
             with torch.cuda.stream(copy_stream):
                 xd_next = x0_host[(k + 1) & 1].to(device, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
         xd.record_stream(torch.cuda.current_stream(device))
-        host_loss = v.item()  # device -> host read of the step's result
+        if pending is not None:  # the previous step's loss: on the host by now
+            loss_done[pending].synchronize()
+            host_loss = float(loss_host[pending])
+        pending = k & 1
+    loss_done[pending].synchronize()
+    host_loss = float(loss_host[pending])  # device -> host read of the last step's result
     e_end.record()
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
@@ -658,7 +672,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps, "loss_value": host_loss,
-                    "how": "x0 of step k+1 copied from pinned host memory on a side stream while step k runs; loss.item() every step"},
+                    "how": "x0 of step k+1 copied from pinned host memory on a side stream while step k runs; every step's loss copied to pinned host memory (non-blocking) and read one step later, the last one before the region ends"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kernel_ms,
