@@ -182,12 +182,13 @@ int sdes_tcgen05_supported(const SdesRolloutDesc* desc);
                                                   models/reparam.py:60,:135): GMM targets */
 #define SDES_GRAD_SCORE_DETACHED     (1u << 1) /* kl gradient: ctrl.detach_score=True — the whole score part (target and
                                                   prior score) is evaluated on x.detach() (models/reparam.py:58,:134) */
-#define SDES_GRAD_LAYERWISE_SWEEP     (1u << 2) /* kl gradient, tcgen05 engine: run the sweep's dgrad chain as one GEMM launch per
-                                                  layer instead of the fused chain kernel — same result; cross-check and
-                                                  A/B measurements */
+#define SDES_GRAD_LAYERWISE_SWEEP     (1u << 2) /* tcgen05 engine, lv and kl gradients: do NOT take the one-kernel path
+                                                  (csrc/sdes_grad_fused.cuh) — run the layer-by-layer GEMM passes, and for
+                                                  kl the step-by-step sweep with one GEMM launch per transposed layer —
+                                                  same result; cross-check and A/B measurements */
 typedef struct SdesLvGradDesc {
     uint32_t struct_bytes;   /* = sizeof(SdesLvGradDesc), checked */
-    uint32_t flags;          /* SDES_GRAD_* (sdes_rollout_kl_grad only; 0 for the lv gradient) */
+    uint32_t flags;          /* SDES_GRAD_* (the score-term flags: sdes_rollout_kl_grad only) */
     const float* xs;         /* (T+1, B, d) trajectory written by the forward call with SDES_F_RETURN_TRAJ */
     const float* w;          /* (B) d loss / d rnd_b (0 for filtered trajectories) */
     float* grad_params;
