@@ -156,52 +156,97 @@ __device__ __forceinline__ void fl_wait(uint64_t* bar, uint32_t parity, uint32_t
     }
 }
 
-// D[128 rows, 64] = A (row image, K-major) x W image (N = 64 out features, K-major)
+// ---- MMA issue, lean form.  A shared-memory matrix descriptor (sdes_tc.cuh smem_desc_kmajor) is two 32-bit words:
+//   low  = (address >> 4) | (LBO >> 4) << 16     — the only part that changes from k-step to k-step (one integer add),
+//   high = (SBO >> 4) | 1 << 14 (descriptor version) — a constant per operand kind.
+// Building the 64-bit values with shifts and masks per MMA, one elect per MMA and one R2UR per word cost ~20 instructions per
+// MMA on the single issuing warp — 216 MMAs per item made that warp, not the tensor pipe or the epilogue, the bound of the
+// kernel.  Here one asm block issues the three MMAs of a k-step behind ONE elect, from low words that are base + immediate.
+constexpr uint32_t FL_TOP_KMAJOR = (128u >> 4) | (1u << 14);      // SBO 128 B: row images as A, weight images as B (K-major)
+constexpr uint32_t FL_TOP_WT = (1024u >> 4) | (1u << 14);         // SBO 1024 B: weight image read MN-major (W^T)
+constexpr uint32_t FL_TOP_ROWS = (2048u >> 4) | (1u << 14);       // SBO 2048 B: row images read MN-major (K = rows)
+__device__ __forceinline__ uint32_t fl_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+
+// D (+)= A_lo B_hi + A_hi B_lo + A_hi B_hi for one k-step (small terms first).  The descriptors' high words and the
+// instruction descriptor are compile-time immediates of the asm block (no register moves for constants).
+template <uint32_t ATOP, uint32_t BTOP, uint32_t IDESC>
+__device__ __forceinline__ void fl_mma3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, t;\n\t"
+        ".reg .b64 dah, dal, dbh, dbl;\n\t"
+        ".reg .b32 id;\n\t"
+        "mov.b64 dah, {%1, %6};\n\t"
+        "mov.b64 dal, {%2, %6};\n\t"
+        "mov.b64 dbh, {%3, %7};\n\t"
+        "mov.b64 dbl, {%4, %7};\n\t"
+        "mov.b32 id, %8;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.u32 t, %0, %0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, id, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, id, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, id, t;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_hi), "r"(a_lo), "r"(b_hi), "r"(b_lo), "r"(accumulate), "n"(ATOP), "n"(BTOP), "n"(IDESC)
+        : "memory");
+}
+// one k-step (16 rows) of a weight gradient: dW (+)= delta^T a_lo + delta^T a_hi, column sums (+)= delta^T ones
+template <uint32_t IDESC, uint32_t IDESC1>
+__device__ __forceinline__ void fl_mma_wg3(uint32_t tmem_dw, uint32_t tmem_db, uint32_t da, uint32_t b_hi, uint32_t b_lo, uint32_t ones,
+                                           uint32_t acc_dw, uint32_t acc_db) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, r, q, t;\n\t"
+        ".reg .b64 dda, dbh, dbl, don;\n\t"
+        ".reg .b32 id, id1;\n\t"
+        "mov.b64 dda, {%2, %8};\n\t"
+        "mov.b64 dbh, {%3, %8};\n\t"
+        "mov.b64 dbl, {%4, %8};\n\t"
+        "mov.b64 don, {%5, %8};\n\t"
+        "mov.b32 id, %9;\n\t"
+        "mov.b32 id1, %10;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 r, %7, 0;\n\t"
+        "setp.eq.u32 t, %0, %0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dda, dbl, id, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dda, dbh, id, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dda, don, id1, r;\n\t"
+        "}" ::"r"(tmem_dw), "r"(tmem_db), "r"(da), "r"(b_hi), "r"(b_lo), "r"(ones), "r"(acc_dw), "r"(acc_db), "n"(FL_TOP_ROWS), "n"(IDESC), "n"(IDESC1)
+        : "memory");
+}
+
+// D[128 rows, 64] = A (row image, K-major) x W image (N = 64 out features, K-major).  Arguments are shared-memory addresses.
 __device__ __forceinline__ void fl_mma_rows_w(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, int nks) {
-    const uint32_t idesc = tc::idesc_bf16(128, 64);
-    const uint32_t w_lo = w_hi + 8192u;
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 64);
+    const uint32_t ah = fl_desc_lo(a_hi, 2048u), al = fl_desc_lo(a_lo, 2048u), bh = fl_desc_lo(w_hi, 1024u), bl = fl_desc_lo(w_hi + 8192u, 1024u);
 #pragma unroll
-    for (int ks = 0; ks < nks; ++ks) {
-        const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
-        const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
-        const uint64_t dbh = tc::smem_desc_kmajor(w_hi + (uint32_t)ks * 2048u, 1024u, 128u);
-        const uint64_t dbl = tc::smem_desc_kmajor(w_lo + (uint32_t)ks * 2048u, 1024u, 128u);
-        fl_mma(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);  // small terms first
-        fl_mma(tmem_d, dah, dbl, idesc, 1u);
-        fl_mma(tmem_d, dah, dbh, idesc, 1u);
-    }
+    for (int ks = 0; ks < 4; ++ks)
+        if (ks < nks)
+            fl_mma3<FL_TOP_KMAJOR, FL_TOP_KMAJOR, idesc>(tmem_d, ah + (uint32_t)ks * 256u, al + (uint32_t)ks * 256u, bh + (uint32_t)ks * 128u,
+                                                         bl + (uint32_t)ks * 128u, ks > 0 ? 1u : 0u);
 }
 // D[128 rows, 64 in features] = A (delta image, K = out features) x W: the forward image (n = out, k = in) read as an
 // MN-major B operand — 8 in-features contiguous, out-features 16 B apart, groups of 8 out-features 128 B apart, groups of
 // 8 in-features 1024 B apart; one k-step = 16 out-features = 256 B.
 __device__ __forceinline__ void fl_mma_rows_wt(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, int nks) {
-    const uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 16);  // b_major = MN
-    const uint32_t w_lo = w_hi + 8192u;
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 16);  // b_major = MN
+    const uint32_t ah = fl_desc_lo(a_hi, 2048u), al = fl_desc_lo(a_lo, 2048u), bh = fl_desc_lo(w_hi, 128u), bl = fl_desc_lo(w_hi + 8192u, 128u);
 #pragma unroll
-    for (int ks = 0; ks < nks; ++ks) {
-        const uint64_t dah = tc::smem_desc_kmajor(a_hi + (uint32_t)ks * 4096u, 2048u, 128u);
-        const uint64_t dal = tc::smem_desc_kmajor(a_lo + (uint32_t)ks * 4096u, 2048u, 128u);
-        const uint64_t dbh = tc::smem_desc_kmajor(w_hi + (uint32_t)ks * 256u, 128u, 1024u);
-        const uint64_t dbl = tc::smem_desc_kmajor(w_lo + (uint32_t)ks * 256u, 128u, 1024u);
-        fl_mma(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-        fl_mma(tmem_d, dah, dbl, idesc, 1u);
-        fl_mma(tmem_d, dah, dbh, idesc, 1u);
-    }
+    for (int ks = 0; ks < 4; ++ks)
+        if (ks < nks)
+            fl_mma3<FL_TOP_KMAJOR, FL_TOP_WT, idesc>(tmem_d, ah + (uint32_t)ks * 256u, al + (uint32_t)ks * 256u, bh + (uint32_t)ks * 16u,
+                                                     bl + (uint32_t)ks * 16u, ks > 0 ? 1u : 0u);
 }
 // dW[(hi | lo) out features, in features] += delta^T a over the tile's 128 rows, and the column sums of delta (wgrad_mma_kernel)
 __device__ __forceinline__ void fl_mma_wgrad(uint32_t tmem_dw, uint32_t tmem_db, uint32_t delta, uint32_t act_hi, uint32_t act_lo,
                                              uint32_t ones, bool acc_dw, bool acc_db) {
-    const uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 15) | (1u << 16), idesc1 = tc::idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
-    const uint64_t dones = tc::smem_desc_kmajor(ones, 128u, 2048u);
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 64) | (1u << 15) | (1u << 16), idesc1 = tc::idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
+    const uint32_t da = fl_desc_lo(delta, 128u), bh = fl_desc_lo(act_hi, 128u), bl = fl_desc_lo(act_lo, 128u), on = fl_desc_lo(ones, 128u);
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
-        const uint64_t da = tc::smem_desc_kmajor(delta + (uint32_t)ks * 256u, 128u, 2048u);
-        const uint64_t dbh = tc::smem_desc_kmajor(act_hi + (uint32_t)ks * 256u, 128u, 2048u);
-        const uint64_t dbl = tc::smem_desc_kmajor(act_lo + (uint32_t)ks * 256u, 128u, 2048u);
-        fl_mma(tmem_dw, da, dbl, idesc, (acc_dw || ks > 0) ? 1u : 0u);
-        fl_mma(tmem_dw, da, dbh, idesc, 1u);
-        fl_mma(tmem_db, da, dones, idesc1, (acc_db || ks > 0) ? 1u : 0u);
-    }
+    for (int ks = 0; ks < 8; ++ks)  // 16 rows per MMA
+        fl_mma_wg3<idesc, idesc1>(tmem_dw, tmem_db, da + (uint32_t)ks * 16u, bh + (uint32_t)ks * 16u, bl + (uint32_t)ks * 16u, on,
+                                  (acc_dw || ks > 0) ? 1u : 0u, (acc_db || ks > 0) ? 1u : 0u);
 }
 
 // 16 values of one row -> the two 16-byte groups (c_lo .. c_lo + 15) of both halves of an image
