@@ -1694,8 +1694,26 @@ int64_t launch_lv_grad(const KParams& kp, const SdesLvGradDesc& g, int64_t fused
         }
         fa.w_img[Lf - 1] = ws + p.f_out.w_off; fa.bias[Lf - 1] = F(p.f_out.b_off);
         fa.dw[Lf - 1] = gp + kp.bl.out_w; fa.db[Lf - 1] = gp + kp.bl.out_b; fa.ldw[Lf - 1] = C; fa.n_valid[Lf - 1] = d.dim; fa.k_valid[Lf - 1] = C;
+        fa.timeline = nullptr;
+        if (getenv("SDES_FL_TIMELINE")) {  // debugging: clock64 stamps of CTA 0 (control warp and one epilogue warp), printed per launch
+            static unsigned long long* tl = nullptr;
+            if (tl == nullptr) cudaMalloc(&tl, 1024 * sizeof(unsigned long long));
+            cudaMemsetAsync(tl, 0, 1024 * sizeof(unsigned long long), stream);
+            fa.timeline = tl;
+        }
         GRAD_CHECK(launch_lv_fused(fa, fused_kl, sm_count > 0 ? sm_count : 148, stream));
         ++launches;
+        if (fa.timeline != nullptr) {
+            std::vector<unsigned long long> h(1024);
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h.data(), fa.timeline, 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            const unsigned long long t0 = h[0];
+            fprintf(stderr, "TIMELINE control:");
+            for (int i = 0; i < 512 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - t0);
+            fprintf(stderr, "\nTIMELINE epilogue:");
+            for (int i = 512; i < 1024 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - t0);
+            fprintf(stderr, "\n");
+        }
         if (fused_kl && getenv("SDES_FL_DEBUG")) {
             std::vector<uint32_t> rec(1024);
             cudaStreamSynchronize(stream);

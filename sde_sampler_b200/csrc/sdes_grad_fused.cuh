@@ -69,6 +69,7 @@ struct FusedLvArgs {
     uint32_t gflags;                          // SDES_GRAD_*
     const float* gmm_h;                       // MODE 3, single-Gaussian target: 0.5 / scale^2 per dimension
     int hvp;                                  // MODE 3: the target's Hessian enters (adj_step_kernel's target_hvp)
+    unsigned long long* timeline;             // debugging (build -DSDES_FL_TIMELINE, env SDES_FL_TIMELINE=1): clock64 stamps of CTA 0, or NULL
     int watch_all;                            // debugging (SDES_FL_DEBUG): watchdog on the CTA-internal waits too (fl_wait)
 };
 
@@ -388,10 +389,18 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
             // (observed as a hang under load).  Consecutive commits therefore alternate between two barriers; a barrier is
             // reused only after a `ready()` that every warp can reach only past its wait on that barrier's previous phase.
             uint32_t zbar = 0u;
+            int tl_c = 0;  // timeline: [0, 512): control warp — (before, after) every wait for the epilogue
+            auto stamp_c = [&]() {
+#ifdef SDES_FL_TIMELINE  // compile-time switch (build with -DSDES_FL_TIMELINE, run with SDES_FL_TIMELINE=1): no cost otherwise
+                if (a.timeline != nullptr && bx == 0 && lane == 0 && tl_c < 512) a.timeline[tl_c++] = (unsigned long long)clock64();
+#endif
+            };
             auto ready = [&]() {
+                stamp_c();
                 fl_wait(&s_aready, ph, dbg_in, 1u, (uint32_t)cur_ctl_item);
                 ph ^= 1u;
                 tc::fence_after();
+                stamp_c();
             };
             for (int64_t item = i0; item < i1; ++item) {
                 cur_ctl_item = item;
@@ -474,7 +483,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         float adj[16];  // kl: this thread's 16 dimensions of a_{s+1} = d loss / d x_{s+1}
 #pragma unroll
         for (int e = 0; e < 16; ++e) adj[e] = 0.f;
+        int tl_e = 0;  // timeline: [512, 1024): epilogue warp 2 — (before, after) every accumulator wait, and every arrive
+        auto stamp_e = [&]() {
+#ifdef SDES_FL_TIMELINE
+            if (a.timeline != nullptr && bx == 0 && warp == 2 && lane == 0 && tl_e < 512) a.timeline[512 + tl_e++] = (unsigned long long)clock64();
+#endif
+        };
         auto arrive = [&]() {
+            stamp_e();
             tc::fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor-core (async) proxy
             tc::fence_before();
             __syncwarp();
@@ -482,9 +498,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) lv_fused_kernel(const __grid_co
         };
         int64_t cur_e_item = 0;
         auto wait_acc = [&]() {
+            stamp_e();
             fl_wait(&s_acc, ph_acc, dbg_in, 2u, (uint32_t)cur_e_item);
             ph_acc ^= 1u;
             tc::fence_after();
+            stamp_e();
         };
         auto flush_emb = [&](int s_prev) {  // d loss / d emb(s_prev): column sums of delta_1 over the step's tiles of this CTA
             if (cw == 0) {
