@@ -1,5 +1,5 @@
-// sdes_grad_fused.cuh — the lv gradient of the control MLP as ONE persistent kernel (`loss.backward()` of
-// `Trainable.step`, solver/base.py:404-407, loss.method = lv): per 128-row tile of (step, trajectory) rows
+// sdes_grad_fused.cuh — the gradient of the control MLP as ONE persistent kernel (`loss.backward()` of
+// `Trainable.step`, solver/base.py:404-407, loss.method = lv | kl | kl_ito).  lv: per 128-row tile of (step, trajectory) rows
 //     replayed forward (models/mlp.py:114-122)  ->  output cotangent  ->  dgrad chain  ->  weight-gradient MMAs
 // with every activation / delta operand living in shared memory only and the weight gradients accumulating in TMEM for
 // the whole launch.  Nothing but the stored trajectory (200 B per row) is read from HBM and nothing but the final
@@ -17,8 +17,12 @@
 // The 64 x 64 weight images are the forward ones; W^T for the dgrad GEMMs is the SAME image read as an MN-major B operand.
 // Per layer of the backward chain the pre-activation is recomputed by one more GEMM into a second accumulator (the
 // tensor pipe is far from busy; storing GELU' would need another 96 KB), so  delta_l = (delta_{l+1} W^T) * GELU'(z_l).
-// MMAs complete in issue order, so a commit after {wgrad, dgrad, recompute} of one hop also frees the buffers the wgrad
-// read, which is what lets two ping-pong buffers serve the whole chain.
+// MMAs complete in issue order, so ONE commit also covers every MMA issued before it: per backward hop the control warp issues
+// the dgrad GEMM, commits (the epilogue may start), and only then the layer's weight-gradient MMAs and the next hop's recompute,
+// which run under the epilogue; the buffer the epilogue writes was last read by MMAs issued before this hop's dgrad, i.e.
+// complete by the time the commit fires — which is what lets two ping-pong buffers serve the whole chain.
+// The same kernel runs the kl / kl_ito reverse sweep (MODE 1-3): a CTA walks row tiles backwards in time with the adjoint in
+// registers, cut into two units per tile that hand the adjoint over through HBM (see the kernel body); details in DESIGN §4.5.
 // TMEM: 4 x 64 columns of weight-gradient accumulators (rows 0-63 / 64-127: contributions of the hi / lo half of delta),
 // 4 x 16 columns of column sums (bias gradients; the input layer's are d loss / d emb(s), flushed whenever the step
 // changes — items are step-major, so a CTA sees at most a few steps), 3 x 64 working accumulators (the dgrad result and
