@@ -200,17 +200,33 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
         "}" ::"r"(smem_u32(bar))
         : "memory");
 }
+// The three MMAs of one k-step behind ONE elect; the weight descriptors as (low word = address / LBO, constant high word):
+// no 64-bit shift / mask arithmetic per MMA (the issuing warp is one of the group's four epilogue warps).
+__device__ __forceinline__ void mma3_f16_ts_elect(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_lo32, uint32_t b_lo_lo32,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, t;\n\t"
+        ".reg .b64 dbh, dbl;\n\t"
+        "mov.b64 dbh, {%3, %7};\n\t"
+        "mov.b64 dbl, {%4, %7};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, %0, %0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], dbh, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbl, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbh, %5, t;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_hi), "r"(a_lo), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate), "n"((128u >> 4) | (1u << 14))
+        : "memory");
+}
 __device__ __forceinline__ void issue_layer_bf16x3_warp(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
                                                         uint32_t w_hi_saddr, uint32_t w_lo_saddr, int K16, int N) {
     const uint32_t id16 = idesc_bf16(128, N);
     const uint32_t lbo = (uint32_t)N * 16u;
-    for (int s = 0; s < (K16 >> 4); ++s) {
-        const uint64_t bh = smem_desc_kmajor(w_hi_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        const uint64_t bl = smem_desc_kmajor(w_lo_saddr + (uint32_t)s * 2u * lbo, lbo, 128u);
-        mma_f16_ts_elect(tmem_d, tmem_a_lo + 8u * s, bh, id16, s > 0 ? 1u : 0u);
-        mma_f16_ts_elect(tmem_d, tmem_a_hi + 8u * s, bl, id16, 1u);
-        mma_f16_ts_elect(tmem_d, tmem_a_hi + 8u * s, bh, id16, 1u);
-    }
+    const uint32_t bh = ((w_hi_saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16), bl = ((w_lo_saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+    const uint32_t step = (2u * lbo) >> 4;  // one k-step = two K-chunks of the weight image
+    for (int s = 0; s < (K16 >> 4); ++s)
+        mma3_f16_ts_elect(tmem_d, tmem_a_hi + 8u * s, tmem_a_lo + 8u * s, bh + (uint32_t)s * step, bl + (uint32_t)s * step, id16, s > 0 ? 1u : 0u);
 }
 
 }  // namespace tc
