@@ -30,6 +30,7 @@
 #include <cuda_bf16.h>
 
 #include "sdes_step.cuh"
+#include <cstdio>
 #include "sdes_tc.cuh"
 
 namespace sdes {
@@ -760,8 +761,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             const float* gate_row = ws + p.ws.gate + (int64_t)i * DPAD;
             // ---- control MLP on the tensor cores (models/mlp.py:114-122): input layer first, so that the target's global
             //      quantities are evaluated while its MMAs run
+#ifdef SDES_TC_TIMELINE
+            unsigned long long tl[16];
+            int tli = 0;
+#define TL() do { if (tli < 16) tl[tli++] = (unsigned long long)clock64(); } while (0)
+#else
+#define TL() do { } while (0)
+#endif
+            TL();
             store_a_from_x<DPAD>(c.l_hi, c.l_lo, xs);
+            TL();
             issue_layer(c, l0_hi, l0_lo, (int)K0B, C);
+            TL();
             TgtGlobals tg;
             float scd[DENSE ? DPAD : 1];
             if constexpr (DENSE) {
@@ -774,21 +785,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             } else if (ctrl_needs_target(CTRL)) {
                 target_globals<DPAD, TGT>(d, xs, lsm, gmm_mask, tg);
             }
+            TL();
             wait_layer(c);
+            TL();
             layer_epilogue(c, ws + p.ws.emb + (int64_t)i * C);  // + (emb_t + b_in), GELU
+            TL();
 #pragma unroll 1
             for (int l = 0; l < nh; ++l) {
                 issue_layer(c, lh_base + (uint32_t)l * 2u * LH_HALF, lh_base + (uint32_t)l * 2u * LH_HALF + LH_HALF, C, C);
+                TL();
                 wait_layer(c);
+                TL();
                 layer_epilogue(c, s_bias + l * C);
+                TL();
             }
             issue_layer(c, lo_hi, lo_lo, C, NOUT);
+            TL();
             const StepK k = make_step_k<CTRL>(d, tab);
             const float* nrow = from_hbm ? d.noise + ((int64_t)i * B + rrow) * dim : nullptr;
             const TrajRef xo_ref = traj_ref(d, d.xs, i + 1, rrow);
             float* xo = (ret_traj && valid) ? xo_ref.p : nullptr;
             float2 cost2 = make_float2(0.f, 0.f), ito2 = make_float2(0.f, 0.f);
             wait_layer(c);
+            TL();
             // ---- network output streamed from TMEM into the control / cost / state update
             float2 qs2 = make_float2(0.f, 0.f);
             const bool want_q = CTRL != SDES_CTRL_CLIPPED && (d.gate_cot != nullptr || d.score_keep != nullptr);
@@ -806,6 +825,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             rnd = fmaf(k.cost_scale, cost2.x + cost2.y, rnd);
             if (d.flags & SDES_F_SUB_DIV_INT) rnd -= tab[TAB_DIV_INT];
             if (d.flags & SDES_F_COMPUTE_ITO) rnd = fmaf(k.ito_scale, ito2.x + ito2.y, rnd);
+            TL();
+#ifdef SDES_TC_TIMELINE
+            if (blockIdx.x < 4 && (tid & 127) == 0 && i >= 42 && i < 44) {
+                for (int q = tli; q < 16; ++q) tl[q] = tl[0];
+                printf("TLSTEP %d cta %d g %d: %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i, (int)blockIdx.x, c.g,
+                       tl[1] - tl[0], tl[2] - tl[0], tl[3] - tl[0], tl[4] - tl[0], tl[5] - tl[0], tl[6] - tl[0], tl[7] - tl[0], tl[8] - tl[0],
+                       tl[9] - tl[0], tl[10] - tl[0], tl[11] - tl[0], tl[12] - tl[0], tl[13] - tl[0], tl[14] - tl[0], tl[15] - tl[0]);
+            }
+#endif
         }
         if (i_end == T) {
             rnd += terminal_rnd<DPAD>(d, xs, tsm);
